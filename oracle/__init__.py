@@ -1,0 +1,2 @@
+"""Oracle = TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this package.  See oracle/canonical.c."""

@@ -1,0 +1,620 @@
+// api.cu -- the extern "C" boundary declared in include/sdk_b200.h.
+#include <dlfcn.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+
+static std::string g_last_error;
+static std::mutex g_err_mu;
+
+int sdk_fail(sdk_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_last_error = msg;
+    return code;
+}
+
+int sdk_reserve(sdk_ctx* c, sdk_buf& b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return SDK_OK;
+    if (b.p) { cudaStreamSynchronize(c->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&b.p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.p = nullptr;
+        return sdk_fail(c, SDK_ENOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+    }
+    b.cap = want;
+    return SDK_OK;
+}
+
+static void sdk_release(sdk_buf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// ---- NCCL, loaded lazily so that single-GPU use has no link-time dependency ---------------------
+typedef struct { char internal[128]; } sdk_nccl_uid_t;
+struct sdk_nccl_api {
+    void* h = nullptr;
+    int (*GetUniqueId)(sdk_nccl_uid_t*) = nullptr;
+    int (*CommInitRank)(void**, int, sdk_nccl_uid_t, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static sdk_nccl_api g_nccl;
+static int sdk_nccl_load() {
+    if (g_nccl.h) return SDK_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return sdk_fail(nullptr, SDK_ENCCL, std::string("dlopen libnccl failed: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(sdk_nccl_uid_t*))dlsym(g_nccl.h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, sdk_nccl_uid_t, int))dlsym(g_nccl.h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.h, "ncclCommDestroy");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.h, "ncclAllGather");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather)
+        return sdk_fail(nullptr, SDK_ENCCL, "libnccl is missing required symbols");
+    return SDK_OK;
+}
+#define SDK_NCCL_CHAR 0  /* ncclChar / ncclInt8 */
+
+extern "C" {
+
+int sdk_abi_version(void) { return SDK_ABI_VERSION; }
+
+int sdk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int sdk_nccl_unique_id(void* out128) {
+    if (!out128) return sdk_fail(nullptr, SDK_EINVAL, "out128 is NULL");
+    SDK_TRY(sdk_nccl_load());
+    sdk_nccl_uid_t id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return sdk_fail(nullptr, SDK_ENCCL, "ncclGetUniqueId failed");
+    memcpy(out128, &id, 128);
+    return SDK_OK;
+}
+
+int sdk_create(sdk_ctx** out, int device, int world, int rank, const void* nccl_uid) {
+    if (!out) return sdk_fail(nullptr, SDK_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return sdk_fail(nullptr, SDK_EINVAL, "bad world/rank");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return sdk_fail(nullptr, SDK_ENODEV, "no CUDA device visible (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return sdk_fail(nullptr, SDK_ENODEV, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return sdk_fail(nullptr, SDK_ECUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return sdk_fail(nullptr, SDK_ENODEV, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                                 ", this library is built for sm_100a only");
+    sdk_ctx* c = new sdk_ctx();
+    c->device = device;
+    c->world = world;
+    c->rank = rank;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return sdk_fail(nullptr, SDK_ECUDA, "cudaSetDevice/cudaStreamCreate failed");
+    }
+    cudaEventCreate(&c->ev_t0);
+    cudaEventCreate(&c->ev_t1);
+    // cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        c->tmap_encode = fn;
+    else
+        cudaGetLastError();
+    if (world > 1) {
+        if (!nccl_uid) { sdk_destroy(c); return sdk_fail(nullptr, SDK_EINVAL, "world > 1 needs an NCCL unique id"); }
+        int r = sdk_nccl_load();
+        if (r != SDK_OK) { sdk_destroy(c); return r; }
+        sdk_nccl_uid_t id;
+        memcpy(&id, nccl_uid, 128);
+        int e = g_nccl.CommInitRank(&c->nccl_comm, world, id, rank);
+        if (e != 0) {
+            std::string m = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+            sdk_destroy(c);
+            return sdk_fail(nullptr, SDK_ENCCL, m);
+        }
+    }
+    *out = c;
+    return SDK_OK;
+}
+
+void sdk_destroy(sdk_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    sdk_buf* bufs[] = {&c->bank_f32, &c->bank_bf16, &c->row_speaker, &c->row_trust, &c->seg_raw, &c->seg_lab,
+                       &c->seg_f32, &c->seg_bf16, &c->goff, &c->qpool, &c->dense, &c->flags, &c->cand_row,
+                       &c->cand_val, &c->cand_cnt, &c->gbound, &c->slot_cnt, &c->slot_row, &c->slot_val,
+                       &c->slot_bound, &c->range_g, &c->fb_list, &c->fb_rows, &c->out_row, &c->out_score,
+                       &c->out_count, &c->out_trust, &c->out_spk, &c->as_idx, &c->as_score, &c->as_conf,
+                       &c->as_cidx, &c->as_cscore, &c->gather};
+    for (sdk_buf* b : bufs) sdk_release(*b);
+    for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* sdk_last_error(sdk_ctx* c) {
+    if (c) return c->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    return g_last_error.c_str();
+}
+
+int sdk_set_option(sdk_ctx* c, const char* key, double value) {
+    if (!c || !key) return sdk_fail(c, SDK_EINVAL, "NULL ctx/key");
+    std::string k(key);
+    if (k == "path") {
+        if (value < 0 || value > 2) return sdk_fail(c, SDK_EINVAL, "path must be 0, 1 or 2");
+        c->opt_path = (int)value;
+    } else if (k == "eps") c->opt_eps = value;
+    else if (k == "profile") c->opt_profile = value != 0;
+    else if (k == "cand") {
+        if (value < 1 || value > 64) return sdk_fail(c, SDK_EINVAL, "cand must be in 1..64");
+        c->opt_cand = (int)value;
+    } else return sdk_fail(c, SDK_EINVAL, "unknown option " + k);
+    return SDK_OK;
+}
+
+// ---- bank ---------------------------------------------------------------------------------------
+static int sdk_check_bank_args(sdk_ctx* c, const void* rows, const void* spk, int64_t P, int32_t D, int32_t dtype) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    if (P < 1 || D < 1 || D > 8192) return sdk_fail(c, SDK_EINVAL, "bank needs P >= 1 and 1 <= D <= 8192");
+    if (P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "at most 2^31-1 rows per shard");
+    if (!rows || !spk) return sdk_fail(c, SDK_EINVAL, "rows/row_speaker is NULL");
+    if (dtype != SDK_DTYPE_F32 && dtype != SDK_DTYPE_BF16) return sdk_fail(c, SDK_EINVAL, "dtype must be 0 (fp32) or 1 (bf16)");
+    return SDK_OK;
+}
+
+int sdk_bank_load_dev(sdk_ctx* c, const float* d_rows, const int32_t* d_row_speaker, const uint8_t* d_row_trust,
+                      int64_t P, int32_t D, int32_t dtype, int64_t global_row_offset) {
+    SDK_TRY(sdk_check_bank_args(c, d_rows, d_row_speaker, P, D, dtype));
+    cudaSetDevice(c->device);
+    c->P = 0;
+    int32_t Dp = (D + 63) / 64 * 64;
+    SDK_TRY(sdk_reserve(c, c->bank_bf16, (size_t)P * Dp * 2));
+    if (dtype == SDK_DTYPE_F32) SDK_TRY(sdk_reserve(c, c->bank_f32, (size_t)P * D * 4));
+    SDK_TRY(sdk_reserve(c, c->row_speaker, (size_t)P * 4));
+    SDK_TRY(sdk_reserve(c, c->row_trust, (size_t)P));
+    SDK_CUDA(c, cudaMemcpyAsync(c->row_speaker.p, d_row_speaker, (size_t)P * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (d_row_trust) SDK_CUDA(c, cudaMemcpyAsync(c->row_trust.p, d_row_trust, (size_t)P, cudaMemcpyDeviceToDevice, c->stream));
+    else SDK_CUDA(c, cudaMemsetAsync(c->row_trust.p, SDK_TRUST_UNKNOWN, (size_t)P, c->stream));
+    SDK_TRY(sdk_launch_normalize(c, d_rows, P, D, Dp, dtype == SDK_DTYPE_F32 ? (float*)c->bank_f32.p : nullptr,
+                                 (__nv_bfloat16*)c->bank_bf16.p));
+    c->P = P; c->D = D; c->Dp = Dp; c->dtype = dtype; c->row_offset = global_row_offset;
+    c->have_results = false;
+    return SDK_OK;
+}
+
+int sdk_bank_load(sdk_ctx* c, const float* rows, const int32_t* row_speaker, const uint8_t* row_trust, int64_t P,
+                  int32_t D, int32_t dtype, int64_t global_row_offset) {
+    SDK_TRY(sdk_check_bank_args(c, rows, row_speaker, P, D, dtype));
+    // rows of one speaker must be contiguous (the select kernel and the shard cut rely on it)
+    {
+        std::vector<int32_t> seen;
+        int32_t prev = row_speaker[0];
+        if (prev < 0) return sdk_fail(c, SDK_EINVAL, "row_speaker must be >= 0");
+        seen.push_back(prev);
+        for (int64_t i = 1; i < P; ++i) {
+            int32_t s = row_speaker[i];
+            if (s < 0) return sdk_fail(c, SDK_EINVAL, "row_speaker must be >= 0");
+            if (s != prev) { seen.push_back(s); prev = s; }
+        }
+        std::sort(seen.begin(), seen.end());
+        if (std::adjacent_find(seen.begin(), seen.end()) != seen.end())
+            return sdk_fail(c, SDK_EINVAL, "rows of one speaker must be contiguous in the bank");
+    }
+    cudaSetDevice(c->device);
+    SDK_TRY(sdk_reserve(c, c->seg_raw, (size_t)P * D * 4));
+    SDK_TRY(sdk_reserve(c, c->seg_lab, (size_t)P * 4 + (size_t)P));
+    SDK_CUDA(c, cudaMemcpyAsync(c->seg_raw.p, rows, (size_t)P * D * 4, cudaMemcpyHostToDevice, c->stream));
+    SDK_CUDA(c, cudaMemcpyAsync(c->seg_lab.p, row_speaker, (size_t)P * 4, cudaMemcpyHostToDevice, c->stream));
+    uint8_t* d_tr = nullptr;
+    if (row_trust) {
+        for (int64_t i = 0; i < P; ++i)
+            if (row_trust[i] > SDK_TRUST_UNKNOWN) return sdk_fail(c, SDK_EINVAL, "row_trust code out of range");
+        d_tr = (uint8_t*)c->seg_lab.p + (size_t)P * 4;
+        SDK_CUDA(c, cudaMemcpyAsync(d_tr, row_trust, (size_t)P, cudaMemcpyHostToDevice, c->stream));
+    }
+    int r = sdk_bank_load_dev(c, (const float*)c->seg_raw.p, (const int32_t*)c->seg_lab.p, d_tr, P, D, dtype, global_row_offset);
+    if (r != SDK_OK) return r;
+    SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SDK_OK;
+}
+
+// ---- identify -----------------------------------------------------------------------------------
+static int sdk_check_flags(sdk_ctx* c) {   // after a stream sync: label sanity flag lives in flags[0]
+    int32_t f = 0;
+    SDK_CUDA(c, cudaMemcpy(&f, c->flags.p, 4, cudaMemcpyDeviceToHost));
+    if (f & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
+    if (f & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
+    return SDK_OK;
+}
+
+static int sdk_allgather_merge(sdk_ctx* c, int32_t L, int32_t k);
+
+int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t pool,
+                     double threshold, int32_t k) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    if (c->P <= 0) return sdk_fail(c, SDK_ESTATE, "sdk_identify before sdk_bank_load");
+    if (k < 1 || k > SDK_MAX_K) return sdk_fail(c, SDK_EINVAL, "k must be in 1..32");
+    if (L < 1 || N < 0) return sdk_fail(c, SDK_EINVAL, "need L >= 1 and N >= 0");
+    if (pool != SDK_POOL_MEAN && pool != SDK_POOL_MAX) return sdk_fail(c, SDK_EINVAL, "pool must be 0 (mean) or 1 (max)");
+    if (N > 0 && (!d_seg || !d_seg_label)) return sdk_fail(c, SDK_EINVAL, "seg/seg_label is NULL");
+    if (!(threshold == threshold)) return sdk_fail(c, SDK_EINVAL, "threshold is NaN");
+    cudaSetDevice(c->device);
+    c->have_results = false;
+    c->have_assign = false;
+    const int32_t D = c->D, Dp = c->Dp;
+    const int64_t P = c->P;
+    const bool bf16 = c->dtype == SDK_DTYPE_BF16;
+
+    SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
+    SDK_TRY(sdk_reserve(c, c->flags, 64));
+    SDK_TRY(sdk_reserve(c, c->out_row, (size_t)L * k * 8));
+    SDK_TRY(sdk_reserve(c, c->out_score, (size_t)L * k * 4));
+    SDK_TRY(sdk_reserve(c, c->out_count, (size_t)L * 4));
+    SDK_TRY(sdk_reserve(c, c->out_trust, (size_t)L * k));
+    SDK_TRY(sdk_reserve(c, c->out_spk, (size_t)L * k * 4));
+    int32_t* d_flags = (int32_t*)c->flags.p;
+    SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, (int64_t*)c->goff.p, d_flags));
+    SDK_CUDA(c, cudaMemsetAsync(d_flags + 1, 0, 4, c->stream));   // fallback counter
+
+    // path choice: tcgen05 only where the contraction is big enough to be a real dense GEMM
+    const double macs = (double)N * (double)P * (double)Dp;
+    int path = c->opt_path;
+    if (path == 0) path = (macs > 2147483648.0 && sdk_poolgemm_supported(Dp) && c->tmap_encode) ? 2 : 1;
+    if (path == 2 && !(sdk_poolgemm_supported(Dp) && c->tmap_encode))
+        return sdk_fail(c, SDK_EINVAL, "tcgen05 path not available for this D / driver");
+    c->last_path = path;
+    c->last_fallback = 0;
+
+    const bool need_bf16 = bf16 || path == 2;
+    if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
+    if (need_bf16) SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
+    SDK_TRY(sdk_launch_normalize(c, d_seg, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
+                                 need_bf16 ? (__nv_bfloat16*)c->seg_bf16.p : nullptr));
+    const void* seg_ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
+    const void* bank_ops = bf16 ? c->bank_bf16.p : c->bank_f32.p;
+    const int32_t pitch = bf16 ? Dp : D;
+
+    if (path == 1) {
+        SDK_TRY(sdk_reserve(c, c->qpool, (size_t)L * P * 8));
+        SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, nullptr, L, nullptr, P,
+                                 pool, (long long*)c->qpool.p));
+        SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L, nullptr, P, pool,
+                                  (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
+                                  c->row_offset, nullptr, 0.f, nullptr, nullptr, (int64_t*)c->out_row.p,
+                                  (float*)c->out_score.p, (int32_t*)c->out_count.p, (uint8_t*)c->out_trust.p,
+                                  (int32_t*)c->out_spk.p));
+    } else {
+        // stage A: tcgen05 pooled GEMM -> per-label candidate rows + bound on everything else.
+        // eps bounds |approx - canonical|: bf16 operands are shared (exact products, fp32 accumulate);
+        // for an fp32 bank stage A additionally rounds the operands to bf16 (2 * 2^-8 relative).
+        float eps = c->opt_eps >= 0 ? (float)c->opt_eps : (bf16 ? 1e-3f : 1.2e-2f);
+        int ncand = std::max(c->opt_cand, k + 6);
+        if (ncand > 64) ncand = 64;
+        float tau = (float)(threshold - 2.0 * (double)eps);
+        if (!(tau > -3.0e38f)) tau = -3.0e38f;
+        SDK_TRY(sdk_reserve(c, c->cand_row, (size_t)L * ncand * 4));
+        SDK_TRY(sdk_reserve(c, c->gbound, (size_t)L * 4));
+        SDK_TRY(sdk_reserve(c, c->fb_list, (size_t)L * 4));
+        SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p,
+                                               N, Dp, (const int64_t*)c->goff.p, L, pool, tau, ncand,
+                                               (int32_t*)c->cand_row.p, (float*)c->gbound.p));
+        // stage B: canonical re-score of the candidates, ordered top-k, certificate
+        SDK_TRY(sdk_reserve(c, c->qpool, (size_t)L * ncand * 8));
+        SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, nullptr, L,
+                                 (const int32_t*)c->cand_row.p, ncand, pool, (long long*)c->qpool.p));
+        SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L,
+                                  (const int32_t*)c->cand_row.p, ncand, pool, (const int32_t*)c->row_speaker.p,
+                                  (const uint8_t*)c->row_trust.p, threshold, k, c->row_offset, (const float*)c->gbound.p,
+                                  eps, d_flags + 1, (int32_t*)c->fb_list.p, (int64_t*)c->out_row.p,
+                                  (float*)c->out_score.p, (int32_t*)c->out_count.p, (uint8_t*)c->out_trust.p,
+                                  (int32_t*)c->out_spk.p));
+        // groups whose certificate failed are re-done exhaustively in the canonical arithmetic
+        int32_t hf[2] = {0, 0};
+        SDK_CUDA(c, cudaMemcpyAsync(hf, d_flags, 8, cudaMemcpyDeviceToHost, c->stream));
+        SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (hf[0] & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
+        if (hf[0] & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
+        int32_t nfb = hf[1];
+        c->last_fallback = nfb;
+        const int32_t chunk = (int32_t)std::max<int64_t>(1, std::min<int64_t>(nfb, (int64_t)(1u << 28) / std::max<int64_t>(P, 1)));
+        for (int32_t done = 0; done < nfb; done += chunk) {
+            int32_t m = std::min(chunk, nfb - done);
+            SDK_TRY(sdk_reserve(c, c->dense, (size_t)m * P * 8));
+            const int32_t* gl = (const int32_t*)c->fb_list.p + done;
+            SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, gl, m, nullptr, P,
+                                     pool, (long long*)c->dense.p));
+            SDK_TRY(sdk_launch_select(c, (const long long*)c->dense.p, (const int64_t*)c->goff.p, gl, m, nullptr, P, pool,
+                                      (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
+                                      c->row_offset, nullptr, 0.f, nullptr, nullptr, (int64_t*)c->out_row.p,
+                                      (float*)c->out_score.p, (int32_t*)c->out_count.p, (uint8_t*)c->out_trust.p,
+                                      (int32_t*)c->out_spk.p));
+        }
+    }
+    c->L = L; c->k = k; c->N = N;
+    if (c->world > 1) SDK_TRY(sdk_allgather_merge(c, L, k));
+    c->have_results = true;
+    return SDK_OK;
+}
+
+// one ncclAllGather of the packed per-rank top-k, then K4 (the only collective)
+static int sdk_allgather_merge(sdk_ctx* c, int32_t L, int32_t k) {
+    const size_t n = (size_t)L * k;
+    // packed per-rank record: rows i64 | scores f32 | spk i32 | counts i32 | trust u8
+    const size_t off_rows = 0, off_score = off_rows + n * 8, off_spk = off_score + n * 4, off_cnt = off_spk + n * 4,
+                 off_trust = off_cnt + (size_t)L * 4;
+    size_t rec = off_trust + n;
+    rec = (rec + 15) / 16 * 16;
+    SDK_TRY(sdk_reserve(c, c->gather, rec * (size_t)(c->world + 1)));
+    char* mine = (char*)c->gather.p;
+    char* all = mine + rec;
+    SDK_CUDA(c, cudaMemcpyAsync(mine + off_rows, c->out_row.p, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    SDK_CUDA(c, cudaMemcpyAsync(mine + off_score, c->out_score.p, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    SDK_CUDA(c, cudaMemcpyAsync(mine + off_spk, c->out_spk.p, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    SDK_CUDA(c, cudaMemcpyAsync(mine + off_cnt, c->out_count.p, (size_t)L * 4, cudaMemcpyDeviceToDevice, c->stream));
+    SDK_CUDA(c, cudaMemcpyAsync(mine + off_trust, c->out_trust.p, n, cudaMemcpyDeviceToDevice, c->stream));
+    int e = g_nccl.AllGather(mine, all, rec, SDK_NCCL_CHAR, c->nccl_comm, c->stream);
+    if (e != 0) return sdk_fail(c, SDK_ENCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error"));
+    // the merge kernel reads rank r's lists at all + r*rec; lists are [world][L,k] with stride rec,
+    // so repack pointers: K4 takes base pointers and assumes dense [world,L,k] -> compact first.
+    // (rec is tiny: L*k*21 bytes; compaction is 5 small D2D copies per rank)
+    SDK_TRY(sdk_reserve(c, c->dense, (size_t)c->world * (n * 17 + (size_t)L * 4) + 64));
+    char* d = (char*)c->dense.p;
+    int64_t* g_rows = (int64_t*)d;
+    float* g_score = (float*)(d + (size_t)c->world * n * 8);
+    int32_t* g_spk = (int32_t*)(d + (size_t)c->world * n * 12);
+    int32_t* g_cnt = (int32_t*)(d + (size_t)c->world * n * 16);
+    uint8_t* g_trust = (uint8_t*)(d + (size_t)c->world * n * 16 + (size_t)c->world * L * 4);
+    for (int r = 0; r < c->world; ++r) {
+        const char* src = all + (size_t)r * rec;
+        SDK_CUDA(c, cudaMemcpyAsync(g_rows + (size_t)r * n, src + off_rows, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        SDK_CUDA(c, cudaMemcpyAsync(g_score + (size_t)r * n, src + off_score, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        SDK_CUDA(c, cudaMemcpyAsync(g_spk + (size_t)r * n, src + off_spk, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        SDK_CUDA(c, cudaMemcpyAsync(g_cnt + (size_t)r * L, src + off_cnt, (size_t)L * 4, cudaMemcpyDeviceToDevice, c->stream));
+        SDK_CUDA(c, cudaMemcpyAsync(g_trust + (size_t)r * n, src + off_trust, n, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return sdk_launch_merge_topk(c, g_rows, g_score, g_trust, g_spk, g_cnt, c->world, L, k, (int64_t*)c->out_row.p,
+                                 (float*)c->out_score.p, (int32_t*)c->out_count.p, (uint8_t*)c->out_trust.p,
+                                 (int32_t*)c->out_spk.p);
+}
+
+int sdk_identify(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
+                 double threshold, int32_t k, int64_t* out_row, float* out_score, int32_t* out_count) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    if (c->P <= 0) return sdk_fail(c, SDK_ESTATE, "sdk_identify before sdk_bank_load");
+    if (N < 0 || (N > 0 && (!seg || !seg_label))) return sdk_fail(c, SDK_EINVAL, "seg/seg_label is NULL");
+    cudaSetDevice(c->device);
+    SDK_TRY(sdk_reserve(c, c->seg_raw, (size_t)N * c->D * 4));
+    SDK_TRY(sdk_reserve(c, c->seg_lab, (size_t)N * 4));
+    if (N > 0) {
+        SDK_CUDA(c, cudaMemcpyAsync(c->seg_raw.p, seg, (size_t)N * c->D * 4, cudaMemcpyHostToDevice, c->stream));
+        SDK_CUDA(c, cudaMemcpyAsync(c->seg_lab.p, seg_label, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    SDK_TRY(sdk_identify_dev(c, (const float*)c->seg_raw.p, (const int32_t*)c->seg_lab.p, N, L, pool, threshold, k));
+    return sdk_results_fetch(c, out_row, out_score, out_count, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int sdk_assign(sdk_ctx* c, double assign_threshold, int32_t min_trust_code) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    if (!c->have_results) return sdk_fail(c, SDK_ESTATE, "sdk_assign before sdk_identify");
+    cudaSetDevice(c->device);
+    const int32_t L = c->L, k = c->k;
+    SDK_TRY(sdk_reserve(c, c->as_idx, (size_t)L * 4));
+    SDK_TRY(sdk_reserve(c, c->as_score, (size_t)L * 8));
+    SDK_TRY(sdk_reserve(c, c->as_conf, (size_t)L * 4));
+    SDK_TRY(sdk_reserve(c, c->as_cidx, (size_t)L * 12));
+    SDK_TRY(sdk_reserve(c, c->as_cscore, (size_t)L * 24));
+    SDK_TRY(sdk_launch_assign(c, (const int64_t*)c->out_row.p, (const float*)c->out_score.p, (const uint8_t*)c->out_trust.p,
+                              (const int32_t*)c->out_count.p, L, k, assign_threshold, min_trust_code, (int32_t*)c->as_idx.p,
+                              (double*)c->as_score.p, (int32_t*)c->as_conf.p, (int32_t*)c->as_cidx.p,
+                              (double*)c->as_cscore.p));
+    c->have_assign = true;
+    return SDK_OK;
+}
+
+int sdk_results_fetch(sdk_ctx* c, int64_t* out_row, float* out_score, int32_t* out_count, uint8_t* out_trust,
+                      int32_t* assign_idx, double* assign_score, int32_t* assign_conf, int32_t* cand_idx,
+                      double* cand_score) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    if (!c->have_results) return sdk_fail(c, SDK_ESTATE, "no results: call sdk_identify first");
+    if ((assign_idx || assign_score || assign_conf || cand_idx || cand_score) && !c->have_assign)
+        return sdk_fail(c, SDK_ESTATE, "assignment outputs requested before sdk_assign");
+    cudaSetDevice(c->device);
+    const size_t n = (size_t)c->L * c->k, L = (size_t)c->L;
+    cudaStream_t s = c->stream;
+    if (out_row) SDK_CUDA(c, cudaMemcpyAsync(out_row, c->out_row.p, n * 8, cudaMemcpyDeviceToHost, s));
+    if (out_score) SDK_CUDA(c, cudaMemcpyAsync(out_score, c->out_score.p, n * 4, cudaMemcpyDeviceToHost, s));
+    if (out_count) SDK_CUDA(c, cudaMemcpyAsync(out_count, c->out_count.p, L * 4, cudaMemcpyDeviceToHost, s));
+    if (out_trust) SDK_CUDA(c, cudaMemcpyAsync(out_trust, c->out_trust.p, n, cudaMemcpyDeviceToHost, s));
+    if (assign_idx) SDK_CUDA(c, cudaMemcpyAsync(assign_idx, c->as_idx.p, L * 4, cudaMemcpyDeviceToHost, s));
+    if (assign_score) SDK_CUDA(c, cudaMemcpyAsync(assign_score, c->as_score.p, L * 8, cudaMemcpyDeviceToHost, s));
+    if (assign_conf) SDK_CUDA(c, cudaMemcpyAsync(assign_conf, c->as_conf.p, L * 4, cudaMemcpyDeviceToHost, s));
+    if (cand_idx) SDK_CUDA(c, cudaMemcpyAsync(cand_idx, c->as_cidx.p, L * 12, cudaMemcpyDeviceToHost, s));
+    if (cand_score) SDK_CUDA(c, cudaMemcpyAsync(cand_score, c->as_cscore.p, L * 24, cudaMemcpyDeviceToHost, s));
+    SDK_CUDA(c, cudaStreamSynchronize(s));
+    return sdk_check_flags(c);
+}
+
+// ---- config 5: pooled self-affinity -------------------------------------------------------------
+__global__ void k_affinity_finish(const long long* __restrict__ qpool /*[L,N]*/, const int64_t* __restrict__ goff,
+                                  int64_t N, int32_t L, int32_t pool, float* __restrict__ out_nl) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * L) return;
+    int64_t n = i / L;
+    int32_t l = (int32_t)(i - n * L);
+    out_nl[i] = sdk_pool_finish(qpool[(int64_t)l * N + n], goff[l + 1] - goff[l], pool);
+}
+// out_ll[a,b] = mean over the segments of label a of out_nl[.,b], pooled in Q30 integers
+__global__ void k_affinity_ll(const float* __restrict__ out_nl, const int64_t* __restrict__ goff, int32_t L,
+                              float* __restrict__ out_ll) {
+    const int a = blockIdx.x, b = blockIdx.y;
+    const int64_t s0 = goff[a], s1 = goff[a + 1];
+    long long acc = 0;
+    for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) acc += __double2ll_rn((double)out_nl[s * L + b] * SDK_Q30);
+    __shared__ long long sh[32];
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+        out_ll[a * L + b] = s1 > s0 ? (float)((double)t / ((double)(s1 - s0) * SDK_Q30)) : 0.f;
+    }
+}
+
+int sdk_affinity_pooled_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t D, int32_t L,
+                            int32_t dtype, int32_t pool, float* d_out_nl, float* d_out_ll) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    if (N < 1 || D < 1 || D > 8192 || L < 1 || !d_seg || !d_seg_label || !d_out_nl)
+        return sdk_fail(c, SDK_EINVAL, "affinity: bad arguments");
+    if (dtype != SDK_DTYPE_F32 && dtype != SDK_DTYPE_BF16) return sdk_fail(c, SDK_EINVAL, "dtype must be 0 or 1");
+    if (pool != SDK_POOL_MEAN && pool != SDK_POOL_MAX) return sdk_fail(c, SDK_EINVAL, "pool must be 0 or 1");
+    cudaSetDevice(c->device);
+    const bool bf16 = dtype == SDK_DTYPE_BF16;
+    const int32_t Dp = (D + 63) / 64 * 64;
+    SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
+    SDK_TRY(sdk_reserve(c, c->flags, 64));
+    SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, (int64_t*)c->goff.p, (int32_t*)c->flags.p));
+    const double macs = (double)N * (double)N * (double)Dp;
+    int path = c->opt_path;
+    if (path == 0) path = (macs > 2147483648.0 && bf16 && sdk_poolgemm_supported(Dp) && c->tmap_encode) ? 2 : 1;
+    if (path == 2 && !(bf16 && sdk_poolgemm_supported(Dp) && c->tmap_encode))
+        return sdk_fail(c, SDK_EINVAL, "tcgen05 affinity needs dtype bf16 and a supported D");
+    c->last_path = path;
+    if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
+    else SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
+    SDK_TRY(sdk_launch_normalize(c, d_seg, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
+                                 bf16 ? (__nv_bfloat16*)c->seg_bf16.p : nullptr));
+    if (path == 2) {
+        SDK_TRY(sdk_launch_poolgemm_dense(c, (const __nv_bfloat16*)c->seg_bf16.p, N, (const __nv_bfloat16*)c->seg_bf16.p, N,
+                                          Dp, (const int64_t*)c->goff.p, L, pool, d_out_nl));
+    } else {
+        const void* ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
+        SDK_TRY(sdk_reserve(c, c->qpool, (size_t)L * N * 8));
+        SDK_TRY(sdk_launch_exact(c, ops, ops, bf16, D, bf16 ? Dp : D, (const int64_t*)c->goff.p, nullptr, L, nullptr, N, pool,
+                                 (long long*)c->qpool.p));
+        sdk_prof_scope ps(c, "affinity");
+        int64_t tot = N * L;
+        k_affinity_finish<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>((const long long*)c->qpool.p,
+                                                                                (const int64_t*)c->goff.p, N, L, pool, d_out_nl);
+        c->launches++;
+        SDK_CUDA(c, cudaGetLastError());
+    }
+    if (d_out_ll) {
+        k_affinity_ll<<<dim3(L, L), 256, 0, c->stream>>>(d_out_nl, (const int64_t*)c->goff.p, L, d_out_ll);
+        c->launches++;
+        SDK_CUDA(c, cudaGetLastError());
+    }
+    return SDK_OK;
+}
+
+int sdk_affinity_pooled(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t N, int32_t D, int32_t L,
+                        int32_t dtype, int32_t pool, float* out_nl, float* out_ll) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    if (N < 1 || !seg || !seg_label || !out_nl) return sdk_fail(c, SDK_EINVAL, "affinity: bad arguments");
+    cudaSetDevice(c->device);
+    SDK_TRY(sdk_reserve(c, c->seg_raw, (size_t)N * D * 4));
+    SDK_TRY(sdk_reserve(c, c->seg_lab, (size_t)N * 4));
+    SDK_TRY(sdk_reserve(c, c->dense, (size_t)N * L * 4 + (size_t)L * L * 4));
+    SDK_CUDA(c, cudaMemcpyAsync(c->seg_raw.p, seg, (size_t)N * D * 4, cudaMemcpyHostToDevice, c->stream));
+    SDK_CUDA(c, cudaMemcpyAsync(c->seg_lab.p, seg_label, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
+    float* d_nl = (float*)c->dense.p;
+    float* d_ll = out_ll ? d_nl + (size_t)N * L : nullptr;
+    SDK_TRY(sdk_affinity_pooled_dev(c, (const float*)c->seg_raw.p, (const int32_t*)c->seg_lab.p, N, D, L, dtype, pool, d_nl, d_ll));
+    SDK_CUDA(c, cudaMemcpyAsync(out_nl, d_nl, (size_t)N * L * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_ll) SDK_CUDA(c, cudaMemcpyAsync(out_ll, d_ll, (size_t)L * L * 4, cudaMemcpyDeviceToHost, c->stream));
+    SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return sdk_check_flags(c);
+}
+
+// ---- stream / timing ----------------------------------------------------------------------------
+int sdk_sync(sdk_ctx* c) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SDK_OK;
+}
+void* sdk_stream(sdk_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int sdk_timer_start(sdk_ctx* c) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    SDK_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    return SDK_OK;
+}
+int sdk_timer_stop(sdk_ctx* c, float* ms) {
+    if (!c || !ms) return sdk_fail(c, SDK_EINVAL, "NULL ctx/ms");
+    SDK_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    SDK_CUDA(c, cudaEventSynchronize(c->ev_t1));
+    SDK_CUDA(c, cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return SDK_OK;
+}
+static void sdk_prof_drain(sdk_ctx* c) {
+    if (c->pending.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& p : c->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            c->prof[p.name].ms += ms;
+            c->prof[p.name].launches += 1;
+        } else cudaGetLastError();
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    c->pending.clear();
+}
+int sdk_profile_get(sdk_ctx* c, const char* name, float* ms_total, int64_t* launches) {
+    if (!c || !name) return sdk_fail(c, SDK_EINVAL, "NULL ctx/name");
+    sdk_prof_drain(c);
+    auto it = c->prof.find(name);
+    if (ms_total) *ms_total = it == c->prof.end() ? 0.f : (float)it->second.ms;
+    if (launches) *launches = it == c->prof.end() ? 0 : it->second.launches;
+    return SDK_OK;
+}
+int sdk_profile_reset(sdk_ctx* c) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    sdk_prof_drain(c);
+    c->prof.clear();
+    return SDK_OK;
+}
+int64_t sdk_launch_count(sdk_ctx* c) { return c ? c->launches : 0; }
+int sdk_last_path(sdk_ctx* c, int32_t* path, int64_t* n_fallback) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    if (path) *path = c->last_path;
+    if (n_fallback) *n_fallback = c->last_fallback;
+    return SDK_OK;
+}
+
+}  // extern "C"

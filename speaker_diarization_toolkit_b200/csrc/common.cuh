@@ -1,0 +1,158 @@
+// common.cuh -- context, error plumbing and small device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <map>
+#include <vector>
+
+#include "../../include/sdk_b200.h"
+
+#define SDK_Q30 1073741824.0
+
+struct sdk_buf {               // grow-only device buffer
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct sdk_prof_entry {
+    double ms = 0.0;
+    int64_t launches = 0;
+};
+
+struct sdk_pending_ev {
+    std::string name;
+    cudaEvent_t a, b;
+};
+
+struct sdk_ctx {
+    int device = 0, world = 1, rank = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    std::string err;
+    int sm_count = 148;
+    // options
+    int opt_path = 0;          // 0 auto, 1 exact, 2 tensor
+    double opt_eps = -1.0;     // <0: default by dtype
+    int opt_profile = 0;
+    int opt_cand = 16;         // re-scored candidates per label group (tensor path)
+    // bank
+    int64_t P = 0;
+    int32_t D = 0, Dp = 0, dtype = 0;
+    int64_t row_offset = 0;
+    sdk_buf bank_f32, bank_bf16, row_speaker, row_trust;
+    // segments / scratch
+    sdk_buf seg_raw, seg_lab, seg_f32, seg_bf16, goff, qpool, dense, flags;
+    sdk_buf cand_row, cand_val, cand_cnt, gbound, slot_cnt, slot_row, slot_val, slot_bound, range_g;
+    sdk_buf fb_list, fb_rows;
+    // results of the last identify
+    int32_t L = 0, k = 0;
+    int64_t N = 0;
+    bool have_results = false, have_assign = false;
+    sdk_buf out_row, out_score, out_count, out_trust, out_spk;
+    sdk_buf as_idx, as_score, as_conf, as_cidx, as_cscore;
+    sdk_buf gather;            // NCCL all-gather staging
+    void* nccl_comm = nullptr;
+    int last_path = 0;
+    int64_t last_fallback = 0;
+    int64_t launches = 0;
+    std::map<std::string, sdk_prof_entry> prof;
+    std::vector<sdk_pending_ev> pending;
+    void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled
+};
+
+int sdk_fail(sdk_ctx* c, int code, const std::string& msg);
+int sdk_reserve(sdk_ctx* c, sdk_buf& b, size_t bytes);
+
+#define SDK_CUDA(c, expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return sdk_fail((c), _e == cudaErrorMemoryAllocation ? SDK_ENOMEM : SDK_ECUDA,  \
+                            std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+    } while (0)
+
+#define SDK_TRY(expr)             \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != SDK_OK) return _r; \
+    } while (0)
+
+// per-kernel timing scope (only active with option "profile")
+struct sdk_prof_scope {
+    sdk_ctx* c;
+    const char* name;
+    cudaEvent_t a = nullptr, b = nullptr;
+    sdk_prof_scope(sdk_ctx* c_, const char* n) : c(c_), name(n) {
+        if (c->opt_profile) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    ~sdk_prof_scope() {
+        if (c->opt_profile) {
+            cudaEventRecord(b, c->stream);
+            c->pending.push_back({name, a, b});
+        }
+    }
+};
+
+// ---- launchers implemented in the .cu files -------------------------------------------------
+// K1: canonical L2 normalise (+ optional fp32 copy, + optional zero-padded bf16 copy)
+int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int32_t Dp,
+                         float* d_f32 /*[n,D] or null*/, __nv_bfloat16* d_bf16 /*[n,Dp] or null*/);
+// group offsets from sorted labels; *d_flag != 0 when labels are unsorted / out of range
+int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_t L,
+                             int64_t* d_goff, int32_t* d_flag);
+// exact canonical Q30 pooling.  rows: dense (cand_row == null: slot == bank row, nslot == P) or
+// sparse (cand_row[g*nslot + j] = bank row or -1).  glist (may be null) maps launch group -> group.
+int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, int32_t is_bf16,
+                     int32_t D, int32_t pitch, const int64_t* d_goff, const int32_t* d_glist,
+                     int32_t ngroups, const int32_t* d_cand_row, int64_t nslot, int32_t pool,
+                     long long* d_qpool /*[ngroups,nslot]*/);
+// select: speaker dedupe + threshold + ordered top-k (+ certificate on the sparse path)
+int sdk_launch_select(sdk_ctx* c, const long long* d_qpool, const int64_t* d_goff,
+                      const int32_t* d_glist, int32_t ngroups, const int32_t* d_cand_row,
+                      int64_t nslot, int32_t pool, const int32_t* d_row_speaker,
+                      const uint8_t* d_row_trust, double threshold, int32_t k, int64_t row_offset,
+                      const float* d_gbound /*null on dense*/, float eps, int32_t* d_fb_count,
+                      int32_t* d_fb_list, int64_t* d_out_row, float* d_out_score,
+                      int32_t* d_out_count, uint8_t* d_out_trust, int32_t* d_out_spk);
+int sdk_launch_assign(sdk_ctx* c, const int64_t* d_row, const float* d_score,
+                      const uint8_t* d_trust, const int32_t* d_count, int32_t L, int32_t k,
+                      double thr, int32_t min_trust, int32_t* d_idx, double* d_ascore,
+                      int32_t* d_conf, int32_t* d_cidx, double* d_cscore);
+// merge after the all-gather: world lists of [L,k] -> [L,k]
+int sdk_launch_merge_topk(sdk_ctx* c, const int64_t* d_rows, const float* d_scores,
+                          const uint8_t* d_trust, const int32_t* d_spk, const int32_t* d_counts,
+                          int32_t world, int32_t L, int32_t k, int64_t* d_out_row,
+                          float* d_out_score, int32_t* d_out_count, uint8_t* d_out_trust,
+                          int32_t* d_out_spk);
+// tcgen05 pooled GEMM (stage A): approximate pooled scores -> per-label candidate rows + bound
+int sdk_poolgemm_supported(int32_t Dp);
+int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int64_t P,
+                                   const __nv_bfloat16* d_seg, int64_t N, int32_t Dp,
+                                   const int64_t* d_goff, int32_t G, int32_t pool, float tau,
+                                   int32_t ncand, int32_t* d_cand_row /*[G,ncand]*/,
+                                   float* d_gbound /*[G]*/);
+// tcgen05 pooled GEMM, dense output out[row, g] (config 5)
+int sdk_launch_poolgemm_dense(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P,
+                              const __nv_bfloat16* d_cols, int64_t N, int32_t Dp,
+                              const int64_t* d_goff, int32_t G, int32_t pool, float* d_out /*[P,G]*/);
+
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sdk_fkey(float f) {   // order-preserving float -> uint
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float sdk_funkey(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float sdk_pool_finish(long long q, long long n, int pool) {
+    if (n <= 0) return 0.0f;
+    if (pool == 0) return (float)((double)q / ((double)n * SDK_Q30));
+    return (float)((double)q / SDK_Q30);
+}

@@ -1,0 +1,187 @@
+// exact.cu -- K2a: canonical (bit-defined) pooled scores on the CUDA cores.
+//
+// This is (a) the "small bank" path of north_star (launch-latency-bound shapes: configs 1 and 2),
+// (b) stage B of the tcgen05 path: re-scoring of the few candidate rows per label in the canonical
+// arithmetic, and (c) the exhaustive fallback for label groups whose top-k certificate failed.
+//
+// Arithmetic = oracle/canonical.c steps (3)-(4): per pair an fp64 fma chain over ascending d
+// (products of fp32/bf16 operands are exact in fp64), q = rint(score * 2^30), then integer
+// sum / max per label group.  Integer pooling is order independent, so warps and CTAs combine their
+// partial pools with shuffles and 64-bit atomics and the result is still bit-defined.
+//
+// Mapping: CTA = (label group, tile of RT bank-row slots, segment split z); thread = one segment,
+// RT fp64 accumulators.  The RT bank rows of the tile are converted to fp64 once per 128-d chunk
+// into shared memory and read back as warp-wide broadcasts (no bank conflicts, no per-thread
+// conversion); each thread streams its own segment row with 128-bit loads.
+#include "common.cuh"
+
+#define SDK_EX_THREADS 256
+#define SDK_EX_DC 128
+
+__device__ __forceinline__ long long sdk_warp_sum_ll(long long v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ long long sdk_warp_max_ll(long long v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        long long o = __shfl_xor_sync(0xffffffffu, v, off);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+template <int RT, bool BF16>
+__global__ void __launch_bounds__(SDK_EX_THREADS)
+k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops, int32_t D, int32_t pitch,
+            const int64_t* __restrict__ goff, const int32_t* __restrict__ glist,
+            const int32_t* __restrict__ cand_row, int64_t nslot, int32_t ntiles, int32_t pool,
+            long long* __restrict__ qpool) {
+    __shared__ double bs[SDK_EX_DC][RT];
+    __shared__ int32_t srow[RT];
+    const int tid = threadIdx.x;
+    const int32_t gi = blockIdx.x / ntiles;
+    const int32_t tile = blockIdx.x - gi * ntiles;
+    const int32_t g = glist ? glist[gi] : gi;
+    const int64_t s0 = goff[g], s1 = goff[g + 1];
+    if (s1 <= s0) return;
+    if (tid < RT) {
+        int64_t slot = (int64_t)tile * RT + tid;
+        int32_t r = -1;
+        if (slot < nslot) r = cand_row ? cand_row[(int64_t)gi * nslot + slot] : (int32_t)slot;
+        srow[tid] = r;
+    }
+    __syncthreads();
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) any |= srow[r] >= 0;
+    if (!any) return;
+
+    const int nz = gridDim.y;
+    for (int64_t cbase = s0 + (int64_t)blockIdx.y * SDK_EX_THREADS; cbase < s1; cbase += (int64_t)nz * SDK_EX_THREADS) {
+        const int64_t s = cbase + tid;
+        const bool valid = s < s1;
+        double acc[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) acc[r] = 0.0;
+        for (int d0 = 0; d0 < D; d0 += SDK_EX_DC) {
+            const int dc = min(SDK_EX_DC, D - d0);
+            __syncthreads();
+            for (int idx = tid; idx < dc * RT; idx += SDK_EX_THREADS) {
+                int r = idx / dc, dd = idx - r * dc;     // consecutive threads -> consecutive d (coalesced)
+                int32_t row = srow[r];
+                double v = 0.0;
+                if (row >= 0) {
+                    if (BF16) v = (double)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bank_ops)[(int64_t)row * pitch + d0 + dd]);
+                    else v = (double)reinterpret_cast<const float*>(bank_ops)[(int64_t)row * pitch + d0 + dd];
+                }
+                bs[dd][r] = v;
+            }
+            __syncthreads();
+            if (valid) {
+                if (BF16) {
+                    const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(seg_ops) + s * (int64_t)pitch + d0;
+                    int dd = 0;
+                    for (; dd + 8 <= dc; dd += 8) {      // pitch % 8 == 0 and d0 % 8 == 0 -> 16-byte aligned
+                        uint4 pk = __ldg(reinterpret_cast<const uint4*>(xr + dd));
+                        uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            double x0 = (double)__uint_as_float(w[h] << 16);
+                            double x1 = (double)__uint_as_float(w[h] & 0xffff0000u);
+#pragma unroll
+                            for (int r = 0; r < RT; ++r) acc[r] = fma(x0, bs[dd + 2 * h][r], acc[r]);
+#pragma unroll
+                            for (int r = 0; r < RT; ++r) acc[r] = fma(x1, bs[dd + 2 * h + 1][r], acc[r]);
+                        }
+                    }
+                    for (; dd < dc; ++dd) {
+                        double x = (double)__bfloat162float(xr[dd]);
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) acc[r] = fma(x, bs[dd][r], acc[r]);
+                    }
+                } else {
+                    const float* xr = reinterpret_cast<const float*>(seg_ops) + s * (int64_t)pitch + d0;
+                    int dd = 0;
+                    if ((pitch & 3) == 0) {
+                        for (; dd + 4 <= dc; dd += 4) {
+                            float4 pk = __ldg(reinterpret_cast<const float4*>(xr + dd));
+                            float w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                double x = (double)w[h];
+#pragma unroll
+                                for (int r = 0; r < RT; ++r) acc[r] = fma(x, bs[dd + h][r], acc[r]);
+                            }
+                        }
+                    }
+                    for (; dd < dc; ++dd) {
+                        double x = (double)__ldg(xr + dd);
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) acc[r] = fma(x, bs[dd][r], acc[r]);
+                    }
+                }
+            }
+        }
+        // fixed point + integer pooling over this CTA's segments
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            long long q;
+            if (pool == 0) {
+                q = valid ? __double2ll_rn(acc[r] * SDK_Q30) : 0ll;
+                q = sdk_warp_sum_ll(q);
+            } else {
+                q = valid ? __double2ll_rn(acc[r] * SDK_Q30) : LLONG_MIN;
+                q = sdk_warp_max_ll(q);
+            }
+            if ((tid & 31) == 0 && srow[r] >= 0) {
+                long long* dst = qpool + (int64_t)gi * nslot + (int64_t)tile * RT + r;
+                if (pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)q);
+                else atomicMax(dst, q);
+            }
+        }
+    }
+}
+
+__global__ void k_fill_ll(long long* p, int64_t n, long long v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, int32_t is_bf16, int32_t D,
+                     int32_t pitch, const int64_t* d_goff, const int32_t* d_glist, int32_t ngroups,
+                     const int32_t* d_cand_row, int64_t nslot, int32_t pool, long long* d_qpool) {
+    if (ngroups <= 0 || nslot <= 0) return SDK_OK;
+    sdk_prof_scope ps(c, "exact");
+    int64_t total = (int64_t)ngroups * nslot;
+    int fb = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    k_fill_ll<<<fb, 256, 0, c->stream>>>(d_qpool, total, pool == 0 ? 0ll : LLONG_MIN);
+    c->launches++;
+    // row-slot tile width: wide tiles for dense scans, narrow for the few re-scored candidates
+    int RT = nslot >= 16 ? 16 : (nslot > 4 ? 8 : 4);
+    int64_t ntiles64 = (nslot + RT - 1) / RT;
+    int64_t blocks = ntiles64 * ngroups;
+    if (blocks > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "exact path: too many (group,row-tile) blocks");
+    // split long groups over blockIdx.y when there are too few CTAs to fill the GPU
+    int nz = 1;
+    if (blocks < 2 * c->sm_count) {
+        nz = (int)((2 * c->sm_count + blocks - 1) / blocks);
+        if (nz > 64) nz = 64;
+    }
+    dim3 grid((unsigned)blocks, (unsigned)nz);
+    int ntiles = (int)ntiles64;
+#define SDK_EX_CASE(RTV)                                                                                   \
+    do {                                                                                                   \
+        if (is_bf16) k_exact_q30<RTV, true><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool); \
+        else k_exact_q30<RTV, false><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool); \
+    } while (0)
+    if (RT == 16) SDK_EX_CASE(16);
+    else if (RT == 8) SDK_EX_CASE(8);
+    else SDK_EX_CASE(4);
+#undef SDK_EX_CASE
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}

@@ -1,0 +1,143 @@
+// normalize.cu -- K1: fused canonical L2-normalise-and-cast, plus label-group offsets.
+//
+// K1 is HBM-bound: one warp per row, 128-bit coalesced loads (lane j owns float4 chunks j, j+32, ..),
+// the row is held in registers between the norm and the scale, and the outputs are a zero-padded
+// bf16 copy (8-byte packed stores, operand of the tcgen05 GEMM and of bf16 canonical scoring) and/or
+// the fp32 normalised copy (operand of fp32 canonical scoring).
+// Algorithmic bytes per row: 4*D read + 2*Dp (bf16) [+ 4*D (fp32 copy)] written.
+//
+// The squared norm uses the canonical order of oracle/canonical.c step (1): fp64 partial sums per
+// lane over ascending elements, butterfly xor 16,8,4,2,1 -- identical on every lane.
+#include "common.cuh"
+
+template <int NQ>
+__global__ void __launch_bounds__(256) k_normalize_vec(const float* __restrict__ x, int64_t n, int32_t D,
+                                                       int32_t Dp, float* __restrict__ f32out,
+                                                       __nv_bfloat16* __restrict__ bf16out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nq = D >> 2, nqp = Dp >> 2;
+    for (int64_t row = warp0; row < n; row += nwarps) {
+        const float4* xr = reinterpret_cast<const float4*>(x + row * (int64_t)D);
+        float4 v[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            int q = lane + 32 * i;
+            v[i] = q < nq ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            double a = (double)v[i].x, b = (double)v[i].y, c = (double)v[i].z, d = (double)v[i].w;
+            s = fma(a, a, s);
+            s = fma(b, b, s);
+            s = fma(c, c, s);
+            s = fma(d, d, s);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+        float nrm = (float)sqrt(s);
+        float den = nrm > 1e-12f ? nrm : 1e-12f;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            int q = lane + 32 * i;
+            float4 o;
+            o.x = __fdiv_rn(v[i].x, den);
+            o.y = __fdiv_rn(v[i].y, den);
+            o.z = __fdiv_rn(v[i].z, den);
+            o.w = __fdiv_rn(v[i].w, den);
+            if (f32out && q < nq) reinterpret_cast<float4*>(f32out + row * (int64_t)D)[q] = o;
+            if (bf16out && q < nqp) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);   // zero beyond D (v was zero)
+                __nv_bfloat162 hi = __floats2bfloat162_rn(o.z, o.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                reinterpret_cast<uint2*>(bf16out + row * (int64_t)Dp)[q] = pk;
+            }
+        }
+        if (bf16out) {   // padding chunks beyond what the NQ registers cover
+            for (int q = lane + 32 * NQ; q < nqp; q += 32)
+                reinterpret_cast<uint2*>(bf16out + row * (int64_t)Dp)[q] = make_uint2(0u, 0u);
+        }
+    }
+}
+
+// any D (scalar loads, two passes over the row; second pass hits L1/L2)
+__global__ void __launch_bounds__(256) k_normalize_generic(const float* __restrict__ x, int64_t n, int32_t D,
+                                                           int32_t Dp, float* __restrict__ f32out,
+                                                           __nv_bfloat16* __restrict__ bf16out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp0; row < n; row += nwarps) {
+        const float* xr = x + row * (int64_t)D;
+        double s = 0.0;
+        for (int q = lane; 4 * q < D; q += 32)
+            for (int t = 0; t < 4; ++t) {
+                int e = 4 * q + t;
+                if (e < D) { double a = (double)xr[e]; s = fma(a, a, s); }
+            }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+        float nrm = (float)sqrt(s);
+        float den = nrm > 1e-12f ? nrm : 1e-12f;
+        for (int e = lane; e < Dp; e += 32) {
+            float o = e < D ? __fdiv_rn(xr[e], den) : 0.f;
+            if (f32out && e < D) f32out[row * (int64_t)D + e] = o;
+            if (bf16out) bf16out[row * (int64_t)Dp + e] = __float2bfloat16_rn(o);
+        }
+    }
+}
+
+int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int32_t Dp, float* d_f32,
+                         __nv_bfloat16* d_bf16) {
+    if (n <= 0) return SDK_OK;
+    sdk_prof_scope ps(c, "normalize");
+    int64_t blocks64 = (n + 7) / 8;
+    int blocks = (int)(blocks64 < (int64_t)c->sm_count * 8 ? blocks64 : (int64_t)c->sm_count * 8);
+    bool vec = (D % 4 == 0) && (Dp % 4 == 0) && D <= 2048 && ((uintptr_t)d_x % 16 == 0);
+    if (vec) {
+        int nq = (D / 4 + 31) / 32;
+#define SDK_NORM_CASE(NQ) k_normalize_vec<NQ><<<blocks, 256, 0, c->stream>>>(d_x, n, D, Dp, d_f32, d_bf16)
+        if (nq <= 1) SDK_NORM_CASE(1);
+        else if (nq <= 2) SDK_NORM_CASE(2);
+        else if (nq <= 4) SDK_NORM_CASE(4);
+        else if (nq <= 8) SDK_NORM_CASE(8);
+        else SDK_NORM_CASE(16);
+#undef SDK_NORM_CASE
+    } else {
+        k_normalize_generic<<<blocks, 256, 0, c->stream>>>(d_x, n, D, Dp, d_f32, d_bf16);
+    }
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}
+
+// goff[g] = first segment index whose label >= g  (labels non-decreasing in [0,L))
+__global__ void k_group_offsets(const int32_t* __restrict__ lab, int64_t N, int32_t L,
+                                int64_t* __restrict__ goff, int32_t* __restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (N == 0) {
+        if (i <= L) goff[i] = 0;
+        return;
+    }
+    if (i > N) return;
+    int32_t a = (i == 0) ? -1 : lab[i - 1];
+    int32_t b = (i == N) ? L : lab[i];
+    if (i < N && (b < 0 || b >= L)) { atomicOr(flag, 1); return; }
+    if (b < a) { atomicOr(flag, 2); return; }
+    for (int32_t g = a + 1; g <= b; ++g) goff[g] = i;
+}
+
+int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_t L, int64_t* d_goff,
+                             int32_t* d_flag) {
+    SDK_CUDA(c, cudaMemsetAsync(d_flag, 0, sizeof(int32_t), c->stream));
+    int64_t work = N == 0 ? (int64_t)L + 1 : N + 1;
+    int blocks = (int)((work + 255) / 256);
+    k_group_offsets<<<blocks, 256, 0, c->stream>>>(d_lab, N, L, d_goff, d_flag);
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}

@@ -1,0 +1,652 @@
+// poolgemm.cu -- K2b + K3(stage A): segment x profile cosine GEMM on tcgen05 tensor cores with the
+// per-label pooling fused into the epilogue.  The N x P score matrix never leaves TMEM/registers.
+//
+// Orientation.  The accumulator tile is  S^T = Bank(128 rows = TMEM lanes) x Segments(NC columns):
+//   A operand (M side)  = bank rows,    bf16, K-major, resident in shared memory for a whole work unit
+//   B operand (N side)  = segments,     bf16, K-major, streamed through a TMA ring, one 64-wide K chunk per stage
+// so that pooling over a label's segments is a reduction ALONG TMEM COLUMNS: after tcgen05.ld each epilogue
+// thread owns one bank row and simply adds (or maxes) the columns it receives into a running register --
+// no cross-lane traffic.  Segments are sorted by label group, a work unit's column range is made of whole
+// groups, and the running accumulator is flushed when the column index crosses a group end (goff[g+1]).
+//
+// Work unit = (column range of whole label groups, row block of MT*128 bank rows).  Units of the same column
+// range are adjacent in the schedule, so the CTAs streaming the same segments run together and share them in
+// L2; HBM sees every segment about once.  L2->SM operand traffic is 2/(MT*128) bytes per MAC.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+// (warp w owns TMEM lanes 32*(w%4)..+31).  Pipelines: bank tile full/empty, B ring full/empty, and a two-deep
+// TMEM accumulator ring (2 x MT x NC columns <= 512) so the epilogue of chunk j overlaps the MMAs of chunk j+1.
+//
+// Flush (candidate mode): the warp keeps, for its 32*MT rows of label group g, the rows whose approximate
+// pooled score is >= tau (at most CS of them; if more pass, the CS largest, found with a ballot-based binary
+// search on the orderable key, plus the bound below which everything was dropped).  A merge kernel then
+// picks the top `ncand` rows per label and the upper bound on every row left out; select.cu re-scores the
+// candidates canonically and checks the bound (the top-k certificate).
+// Flush (dense mode, config 5): out[row, g] = pooled value.
+#include <cuda.h>
+
+#include "common.cuh"
+
+#define PG_THREADS 192
+#define PG_CS 16            // candidate slots per (label group, row block, warp)
+#define PG_SMEM_LIMIT 232448
+
+struct PgParams {
+    const int64_t* goff;
+    const int32_t* range_g;     // [n_ranges+1] first group of each column range
+    int32_t n_ranges, RB;
+    int64_t P;
+    int32_t g_base;             // first group of this batch (slot arrays are batch-relative)
+    int32_t pool;
+    float tau;
+    int32_t mode;               // 0 candidates, 1 dense
+    int32_t* slot_cnt;
+    int32_t* slot_row;
+    float* slot_val;
+    float* slot_bound;
+    float* dense_out;
+    int32_t dense_ld;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pg_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void pg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pg_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void pg_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "PG_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra PG_DONE_%=;\n\t"
+        "bra PG_WAIT_%=;\n\t"
+        "PG_DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void pg_tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int32_t c0, int32_t c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void pg_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void pg_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void pg_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void pg_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void pg_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void pg_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (see cute/arch/mma_sm100_desc.hpp):
+// start>>4 | LBO(=1, unused for swizzled K-major)<<16 | SBO(=1024B: 8 rows x 128B)>>4<<32 | version 1<<46 | SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t pg_make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+// ---- the flush of one label group for this warp's 32*MT rows -----------------------------------
+template <int MT>
+__device__ __forceinline__ void pg_flush(const PgParams& p, float (&acc)[MT], int32_t g, int64_t n_g, int32_t rb, int32_t wq,
+                                         int32_t lane, int64_t row0) {
+    float val[MT];
+    bool pass[MT];
+    const float inv = p.pool == 0 ? 1.0f / (float)n_g : 1.0f;
+    if (p.mode == 1) {
+#pragma unroll
+        for (int rt = 0; rt < MT; ++rt) {
+            int64_t row = row0 + rt * 128;
+            if (row < p.P) p.dense_out[row * (int64_t)p.dense_ld + g] = acc[rt] * inv;
+        }
+        return;
+    }
+    int npass = 0;
+#pragma unroll
+    for (int rt = 0; rt < MT; ++rt) {
+        val[rt] = acc[rt] * inv;
+        pass[rt] = (val[rt] >= p.tau) && (row0 + rt * 128 < p.P);
+        npass += __popc(__ballot_sync(0xffffffffu, pass[rt]));
+    }
+    const int64_t sub = ((int64_t)(g - p.g_base) * p.RB + rb) * 4 + wq;
+    if (lane == 0) p.slot_cnt[sub] = npass;
+    if (npass == 0) return;
+    uint32_t T = 0;   // keys >= T are kept when npass > CS
+    int need_ties = 0;
+    if (npass > PG_CS) {
+        uint32_t key[MT];
+#pragma unroll
+        for (int rt = 0; rt < MT; ++rt) key[rt] = pass[rt] ? sdk_fkey(val[rt]) : 0u;
+        for (int bit = 31; bit >= 0; --bit) {
+            uint32_t cand = T | (1u << bit);
+            int cnt = 0;
+#pragma unroll
+            for (int rt = 0; rt < MT; ++rt) cnt += __popc(__ballot_sync(0xffffffffu, key[rt] >= cand));
+            if (cnt >= PG_CS) T = cand;
+        }
+        int above = 0;
+#pragma unroll
+        for (int rt = 0; rt < MT; ++rt) above += __popc(__ballot_sync(0xffffffffu, key[rt] > T));
+        need_ties = PG_CS - above;
+        if (lane == 0) p.slot_bound[sub] = sdk_funkey(T);
+        int base = 0, ties = 0;
+#pragma unroll
+        for (int rt = 0; rt < MT; ++rt) {
+            bool gt = key[rt] > T, eq = key[rt] == T && pass[rt];
+            uint32_t mg = __ballot_sync(0xffffffffu, gt), me = __ballot_sync(0xffffffffu, eq);
+            int my_tie = ties + __popc(me & ((1u << lane) - 1));
+            bool take_eq = eq && my_tie < need_ties;
+            uint32_t mt = __ballot_sync(0xffffffffu, take_eq);
+            uint32_t mall = mg | mt;
+            if (gt || take_eq) {
+                int pos = base + __popc(mall & ((1u << lane) - 1));
+                p.slot_row[sub * PG_CS + pos] = (int32_t)(row0 + rt * 128);
+                p.slot_val[sub * PG_CS + pos] = val[rt];
+            }
+            base += __popc(mall);
+            ties += __popc(me);
+        }
+    } else {
+        int base = 0;
+#pragma unroll
+        for (int rt = 0; rt < MT; ++rt) {
+            uint32_t m = __ballot_sync(0xffffffffu, pass[rt]);
+            if (pass[rt]) {
+                int pos = base + __popc(m & ((1u << lane) - 1));
+                p.slot_row[sub * PG_CS + pos] = (int32_t)(row0 + rt * 128);
+                p.slot_val[sub * PG_CS + pos] = val[rt];
+            }
+            base += __popc(m);
+        }
+    }
+}
+
+// ---- the kernel --------------------------------------------------------------------------------
+template <int KCH, int MT, int NC, int STAGES>
+__global__ void __launch_bounds__(PG_THREADS, 1)
+k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const PgParams p) {
+    constexpr uint32_t A_TILE = 128 * 128;               // 128 rows x 64 bf16
+    constexpr uint32_t A_BYTES = MT * KCH * A_TILE;
+    constexpr uint32_t B_STAGE = NC * 128;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    static_assert(2 * MT * NC <= 512, "TMEM: two accumulator stages must fit 512 columns");
+    static_assert(NC % 16 == 0 && NC >= 16 && NC <= 256, "UMMA N");
+
+    extern __shared__ uint8_t pg_smem_raw[];
+    const uint32_t raw = pg_smem_u32(pg_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sA = base;
+    const uint32_t sB = sA + A_BYTES;
+    const uint32_t sBar = sB + STAGES * B_STAGE;
+    // barrier layout (8 bytes each)
+    const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8;
+    const uint32_t bar_b_full = sBar + 16, bar_b_empty = bar_b_full + 8 * STAGES;
+    const uint32_t bar_t_full = bar_b_empty + 8 * STAGES, bar_t_empty = bar_t_full + 16;
+    const uint32_t s_tmem = bar_t_empty + 16;
+    uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(pg_smem_raw + (s_tmem - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        pg_mbar_init(bar_a_full, 1);
+        pg_mbar_init(bar_a_empty, 1);
+        for (int s = 0; s < STAGES; ++s) { pg_mbar_init(bar_b_full + 8 * s, 1); pg_mbar_init(bar_b_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { pg_mbar_init(bar_t_full + 8 * b, 1); pg_mbar_init(bar_t_empty + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pg_fence_before();
+    __syncthreads();
+    pg_fence_after();
+    const uint32_t tmem_base = *s_tmem_ptr;
+
+    const int64_t n_units = (int64_t)p.n_ranges * p.RB;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int32_t range = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)range * p.RB);
+                const int64_t c0 = p.goff[p.range_g[range]], c1 = p.goff[p.range_g[range + 1]];
+                if (c1 <= c0) continue;
+                pg_mbar_wait(bar_a_empty, a_phase ^ 1);
+                pg_mbar_expect_tx(bar_a_full, A_BYTES);
+#pragma unroll 1
+                for (int rt = 0; rt < MT; ++rt)
+#pragma unroll 1
+                    for (int kc = 0; kc < KCH; ++kc)
+                        pg_tma_load_2d(sA + (rt * KCH + kc) * A_TILE, &tmapA, kc * 64, (int32_t)((int64_t)rb * MT * 128 + rt * 128), bar_a_full);
+                a_phase ^= 1;
+                const int64_t nchunks = (c1 - c0 + NC - 1) / NC;
+                for (int64_t j = 0; j < nchunks; ++j) {
+                    const int32_t crow = (int32_t)(c0 + j * NC);
+#pragma unroll 1
+                    for (int kc = 0; kc < KCH; ++kc) {
+                        pg_mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+                        pg_mbar_expect_tx(bar_b_full + 8 * stage, B_STAGE);
+                        pg_tma_load_2d(sB + stage * B_STAGE, &tmapB, kc * 64, crow, bar_b_full + 8 * stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0;
+            uint32_t jglobal = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int32_t range = (int32_t)(u / p.RB);
+                const int64_t c0 = p.goff[p.range_g[range]], c1 = p.goff[p.range_g[range + 1]];
+                if (c1 <= c0) continue;
+                pg_mbar_wait(bar_a_full, a_phase);
+                a_phase ^= 1;
+                pg_fence_after();
+                const int64_t nchunks = (c1 - c0 + NC - 1) / NC;
+                for (int64_t j = 0; j < nchunks; ++j, ++jglobal) {
+                    const uint32_t b = jglobal & 1u, it = jglobal >> 1;
+                    pg_mbar_wait(bar_t_empty + 8 * b, (it & 1u) ^ 1u);
+                    pg_fence_after();
+#pragma unroll 1
+                    for (int kc = 0; kc < KCH; ++kc) {
+                        pg_mbar_wait(bar_b_full + 8 * stage, phase);
+                        pg_fence_after();
+                        const uint64_t db = pg_make_desc(sB + stage * B_STAGE);
+#pragma unroll
+                        for (int rt = 0; rt < MT; ++rt) {
+                            const uint64_t da = pg_make_desc(sA + (rt * KCH + kc) * A_TILE);
+                            const uint32_t td = tmem_base + (b * MT + rt) * NC;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                pg_mma_bf16(td, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC, (kc | kk) != 0 ? 1u : 0u);
+                        }
+                        pg_commit(bar_b_empty + 8 * stage);     // frees this B stage when the MMAs have read it
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    pg_commit(bar_t_full + 8 * b);               // accumulators of chunk j complete
+                }
+                pg_commit(bar_a_empty);                          // bank tiles may be overwritten
+            }
+        }
+    } else {
+        // ================= epilogue: 4 warps, thread <-> bank row (TMEM lane) =================
+        const int wq = warp & 3;                                 // TMEM lane quadrant of this warp
+        const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
+        uint32_t jglobal = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int32_t range = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)range * p.RB);
+            const int32_t g_lo = p.range_g[range], g_hi = p.range_g[range + 1];
+            const int64_t c0 = p.goff[g_lo], c1 = p.goff[g_hi];
+            if (c1 <= c0) continue;
+            const int64_t row0 = (int64_t)rb * MT * 128 + wq * 32 + lane;
+            int32_t g = g_lo;
+            int64_t gbeg = c0, gend = p.goff[g + 1];
+            while (gend == gbeg && g + 1 < g_hi) { ++g; gend = p.goff[g + 1]; }   // skip empty groups
+            float acc[MT];
+#pragma unroll
+            for (int rt = 0; rt < MT; ++rt) acc[rt] = p.pool == 0 ? 0.f : -3.0e38f;
+            const int64_t nchunks = (c1 - c0 + NC - 1) / NC;
+            for (int64_t j = 0; j < nchunks; ++j, ++jglobal) {
+                const uint32_t b = jglobal & 1u, it = jglobal >> 1;
+                pg_mbar_wait(bar_t_full + 8 * b, it & 1u);
+                pg_fence_after();
+#pragma unroll 1
+                for (int blk = 0; blk < NC / 16; ++blk) {
+                    const int64_t cbase = c0 + j * NC + blk * 16;
+                    if (cbase >= c1) break;
+                    float v[MT][16];
+#pragma unroll
+                    for (int rt = 0; rt < MT; ++rt) pg_tmem_ld16(tmem_base + lane_base + (b * MT + rt) * NC + blk * 16, v[rt]);
+                    pg_tmem_ld_wait();
+                    const int nvalid = (int)min((int64_t)16, c1 - cbase);
+                    if (nvalid == 16 && gend > cbase + 16) {
+                        // whole block inside the current label group
+#pragma unroll
+                        for (int rt = 0; rt < MT; ++rt) {
+                            if (p.pool == 0) {
+                                float s0 = (v[rt][0] + v[rt][1]) + (v[rt][2] + v[rt][3]);
+                                float s1 = (v[rt][4] + v[rt][5]) + (v[rt][6] + v[rt][7]);
+                                float s2 = (v[rt][8] + v[rt][9]) + (v[rt][10] + v[rt][11]);
+                                float s3 = (v[rt][12] + v[rt][13]) + (v[rt][14] + v[rt][15]);
+                                acc[rt] += (s0 + s1) + (s2 + s3);
+                            } else {
+                                float m = acc[rt];
+#pragma unroll
+                                for (int cc = 0; cc < 16; ++cc) m = fmaxf(m, v[rt][cc]);
+                                acc[rt] = m;
+                            }
+                        }
+                    } else {
+                        int c = 0;
+                        while (c < nvalid) {
+                            const int run_end = (int)min((int64_t)nvalid, gend - cbase);
+#pragma unroll
+                            for (int cc = 0; cc < 16; ++cc) {
+                                const bool on = cc >= c && cc < run_end;
+#pragma unroll
+                                for (int rt = 0; rt < MT; ++rt) {
+                                    if (p.pool == 0) acc[rt] += on ? v[rt][cc] : 0.f;
+                                    else acc[rt] = on ? fmaxf(acc[rt], v[rt][cc]) : acc[rt];
+                                }
+                            }
+                            c = run_end;
+                            if (cbase + run_end == gend) {
+                                pg_flush<MT>(p, acc, g, gend - gbeg, rb, wq, lane, row0);
+#pragma unroll
+                                for (int rt = 0; rt < MT; ++rt) acc[rt] = p.pool == 0 ? 0.f : -3.0e38f;
+                                gbeg = gend;
+                                if (g + 1 < g_hi) {
+                                    ++g;
+                                    gend = p.goff[g + 1];
+                                    while (gend == gbeg && g + 1 < g_hi) { ++g; gend = p.goff[g + 1]; }
+                                } else {
+                                    gend = 0x7fffffffffffffffLL;   // past the last group of the unit
+                                }
+                            }
+                        }
+                    }
+                }
+                pg_fence_before();
+                __syncwarp();
+                if (lane == 0) pg_mbar_arrive(bar_t_empty + 8 * b);
+            }
+        }
+    }
+
+    // ---- teardown ----
+    pg_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- column ranges: range i = groups whose first column falls in [i*T, (i+1)*T) of this batch ----
+__global__ void k_pg_ranges(const int64_t* __restrict__ goff, int32_t g_a, int32_t g_b, int64_t T, int32_t n_ranges,
+                            int32_t* __restrict__ range_g) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_ranges) return;
+    if (i == n_ranges) { range_g[i] = g_b; return; }
+    const int64_t target = goff[g_a] + (int64_t)i * T;
+    int32_t lo = g_a, hi = g_b;                      // first g in [g_a, g_b] with goff[g] >= target
+    while (lo < hi) {
+        int32_t mid = lo + (hi - lo) / 2;
+        if (goff[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    range_g[i] = lo;
+}
+
+// ---- merge of the per-(row block, warp) candidate slots of one label group ------------------------
+// Picks the `ncand` rows with the largest approximate score (radix select, 4 x 8 bits, on the orderable
+// key) and the upper bound on the approximate score of every row that is NOT in the list.
+__global__ void __launch_bounds__(256)
+k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t RB, const int32_t* __restrict__ slot_cnt,
+           const int32_t* __restrict__ slot_row, const float* __restrict__ slot_val, const float* __restrict__ slot_bound,
+           float tau, int32_t ncand, int32_t* __restrict__ cand_row, float* __restrict__ gbound) {
+    __shared__ int hist[256];
+    __shared__ int s_total, s_digit, s_need, s_out, s_ties;
+    __shared__ unsigned int s_bound_key;
+    const int gl = blockIdx.x, g = g_base + gl, tid = threadIdx.x;
+    int32_t* out = cand_row + (int64_t)g * ncand;
+    for (int i = tid; i < ncand; i += blockDim.x) out[i] = -1;
+    if (goff[g + 1] <= goff[g]) { if (tid == 0) gbound[g] = -3.0e38f; return; }
+    const int nsub = RB * 4;
+    const int32_t* cnt = slot_cnt + (int64_t)gl * nsub;
+    const int32_t* rows = slot_row + (int64_t)gl * nsub * PG_CS;
+    const float* vals = slot_val + (int64_t)gl * nsub * PG_CS;
+    const float* bnd = slot_bound + (int64_t)gl * nsub;
+    if (tid == 0) { s_total = 0; s_out = 0; s_ties = 0; s_bound_key = sdk_fkey(tau); }
+    __syncthreads();
+    int mytotal = 0;
+    unsigned int mybound = 0;
+    for (int s = tid; s < nsub; s += blockDim.x) {
+        int c = cnt[s];
+        mytotal += c < PG_CS ? c : PG_CS;
+        if (c > PG_CS) { unsigned int kb = sdk_fkey(bnd[s]); mybound = kb > mybound ? kb : mybound; }
+    }
+    atomicAdd(&s_total, mytotal);
+    if (mybound) atomicMax(&s_bound_key, mybound);
+    __syncthreads();
+    const int total = s_total;
+    const int64_t flat = (int64_t)nsub * PG_CS;
+    if (total <= ncand) {
+        for (int64_t f = tid; f < flat; f += blockDim.x) {
+            int s = (int)(f / PG_CS), i = (int)(f - (int64_t)s * PG_CS);
+            int c = cnt[s];
+            if (i < (c < PG_CS ? c : PG_CS)) out[atomicAdd(&s_out, 1)] = rows[f];
+        }
+        __syncthreads();
+        if (tid == 0) gbound[g] = sdk_funkey(s_bound_key);
+        return;
+    }
+    // radix select of the ncand-th largest key
+    unsigned int prefix = 0, mask = 0;
+    int need = ncand;
+    for (int pass = 3; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int64_t f = tid; f < flat; f += blockDim.x) {
+            int s = (int)(f / PG_CS), i = (int)(f - (int64_t)s * PG_CS);
+            int c = cnt[s];
+            if (i < (c < PG_CS ? c : PG_CS)) {
+                unsigned int key = sdk_fkey(vals[f]);
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int cum = 0, d = 255;
+            for (; d > 0; --d) {
+                if (cum + hist[d] >= need) break;
+                cum += hist[d];
+            }
+            s_digit = d;
+            s_need = need - cum;
+        }
+        __syncthreads();
+        prefix |= ((unsigned int)s_digit) << shift;
+        mask |= 255u << shift;
+        need = s_need;
+        __syncthreads();
+    }
+    const unsigned int T = prefix;      // ncand-th largest key; take all keys > T and `need` of the keys == T
+    for (int64_t f = tid; f < flat; f += blockDim.x) {
+        int s = (int)(f / PG_CS), i = (int)(f - (int64_t)s * PG_CS);
+        int c = cnt[s];
+        if (i < (c < PG_CS ? c : PG_CS)) {
+            unsigned int key = sdk_fkey(vals[f]);
+            if (key > T) out[atomicAdd(&s_out, 1)] = rows[f];
+            else if (key == T) {
+                int t = atomicAdd(&s_ties, 1);
+                if (t < need) out[atomicAdd(&s_out, 1)] = rows[f];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int kb = s_bound_key > T ? s_bound_key : T;   // dropped rows are <= T (or below a slot bound / tau)
+        gbound[g] = sdk_funkey(kb);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*pg_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int pg_make_tmap(sdk_ctx* c, CUtensorMap* tm, const void* base, int64_t rows, int32_t Dp, uint32_t box_rows) {
+    cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)Dp * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((pg_encode_fn)c->tmap_encode)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sdk_fail(c, SDK_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return SDK_OK;
+}
+
+struct pg_cfg { int KCH, MT, NC, STAGES; };
+static pg_cfg pg_config_for(int32_t Dp) {
+    int kch = Dp / 64;
+    switch (kch) {
+        case 1: return {1, 4, 64, 4};
+        case 2: return {2, 4, 64, 4};
+        case 3: return {3, 4, 64, 4};
+        case 4: return {4, 3, 64, 4};
+        case 5: return {5, 2, 64, 4};
+        case 6: return {6, 2, 64, 4};
+        case 7: return {7, 1, 128, 6};
+        default: return {8, 1, 128, 6};
+    }
+}
+
+int sdk_poolgemm_supported(int32_t Dp) { return Dp >= 64 && Dp <= 512 && Dp % 64 == 0; }
+
+template <int KCH, int MT, int NC, int STAGES>
+static int pg_launch_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const PgParams& p, int grid) {
+    constexpr size_t smem = (size_t)MT * KCH * 16384 + (size_t)STAGES * NC * 128 + 256 + 1024;
+    static_assert(smem <= PG_SMEM_LIMIT, "shared memory budget");
+    auto kern = k_poolgemm<KCH, MT, NC, STAGES>;
+    SDK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, PG_THREADS, smem, c->stream>>>(ta, tb, p);
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}
+
+static int pg_launch(sdk_ctx* c, const pg_cfg& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const PgParams& p, int grid) {
+    switch (cfg.KCH) {
+        case 1: return pg_launch_t<1, 4, 64, 4>(c, ta, tb, p, grid);
+        case 2: return pg_launch_t<2, 4, 64, 4>(c, ta, tb, p, grid);
+        case 3: return pg_launch_t<3, 4, 64, 4>(c, ta, tb, p, grid);
+        case 4: return pg_launch_t<4, 3, 64, 4>(c, ta, tb, p, grid);
+        case 5: return pg_launch_t<5, 2, 64, 4>(c, ta, tb, p, grid);
+        case 6: return pg_launch_t<6, 2, 64, 4>(c, ta, tb, p, grid);
+        case 7: return pg_launch_t<7, 1, 128, 6>(c, ta, tb, p, grid);
+        default: return pg_launch_t<8, 1, 128, 6>(c, ta, tb, p, grid);
+    }
+}
+
+// columns per range: enough units to balance 148 persistent CTAs, whole groups, multiple of NC
+static int64_t pg_range_cols(sdk_ctx* c, int64_t ncols, int32_t RB, int NC) {
+    int64_t want_units = (int64_t)c->sm_count * 8;
+    int64_t T = (ncols * RB + want_units - 1) / want_units;
+    T = (T + NC - 1) / NC * NC;
+    if (T < 4 * NC) T = 4 * NC;
+    if (T > 65536) T = 65536;
+    return T;
+}
+
+static int pg_run(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv_bfloat16* d_cols, int64_t N, int32_t Dp,
+                  const int64_t* d_goff, int32_t G, int32_t pool, int32_t mode, float tau, int32_t ncand, int32_t* d_cand_row,
+                  float* d_gbound, float* d_dense) {
+    if (!sdk_poolgemm_supported(Dp) || !c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "tcgen05 path unavailable");
+    if (N > 0x7fffffffLL || P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "tcgen05 path: at most 2^31-1 rows / segments");
+    const pg_cfg cfg = pg_config_for(Dp);
+    const int32_t RB = (int32_t)((P + (int64_t)cfg.MT * 128 - 1) / ((int64_t)cfg.MT * 128));
+    CUtensorMap ta, tb;
+    SDK_TRY(pg_make_tmap(c, &ta, d_rows, P, Dp, 128));
+    SDK_TRY(pg_make_tmap(c, &tb, d_cols, N, Dp, (uint32_t)cfg.NC));
+    // group offsets are needed on the host only to batch groups; read them once (G+1 int64)
+    std::vector<int64_t> hgoff((size_t)G + 1);
+    SDK_CUDA(c, cudaMemcpyAsync(hgoff.data(), d_goff, ((size_t)G + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    // batches of label groups so that the candidate slots stay under ~2 GB
+    const size_t per_group = (size_t)RB * 4 * (PG_CS * 8 + 8);
+    int64_t gbatch = mode == 0 ? (int64_t)((size_t)(2048ull << 20) / per_group) : (int64_t)G;
+    if (gbatch < 1) gbatch = 1;
+    if (gbatch > G) gbatch = G;
+    if (mode == 0) {
+        SDK_TRY(sdk_reserve(c, c->slot_cnt, (size_t)gbatch * RB * 4 * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_bound, (size_t)gbatch * RB * 4 * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)gbatch * RB * 4 * PG_CS * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)gbatch * RB * 4 * PG_CS * 4));
+    }
+    for (int64_t ga = 0; ga < G; ga += gbatch) {
+        const int64_t gb = std::min<int64_t>(G, ga + gbatch);
+        const int64_t ncols = hgoff[gb] - hgoff[ga];
+        if (ncols > 0) {
+            const int64_t T = pg_range_cols(c, ncols, RB, cfg.NC);
+            const int32_t n_ranges = (int32_t)((ncols + T - 1) / T);
+            SDK_TRY(sdk_reserve(c, c->range_g, (size_t)(n_ranges + 1) * 4));
+            k_pg_ranges<<<(n_ranges + 1 + 255) / 256, 256, 0, c->stream>>>(d_goff, (int32_t)ga, (int32_t)gb, T, n_ranges,
+                                                                          (int32_t*)c->range_g.p);
+            c->launches++;
+            SDK_CUDA(c, cudaGetLastError());
+            PgParams p;
+            p.goff = d_goff;
+            p.range_g = (const int32_t*)c->range_g.p;
+            p.n_ranges = n_ranges;
+            p.RB = RB;
+            p.P = P;
+            p.g_base = (int32_t)ga;
+            p.pool = pool;
+            p.tau = tau;
+            p.mode = mode;
+            p.slot_cnt = (int32_t*)c->slot_cnt.p;
+            p.slot_row = (int32_t*)c->slot_row.p;
+            p.slot_val = (float*)c->slot_val.p;
+            p.slot_bound = (float*)c->slot_bound.p;
+            p.dense_out = d_dense;
+            p.dense_ld = G;
+            const int64_t n_units = (int64_t)n_ranges * RB;
+            const int grid = (int)std::min<int64_t>(n_units, c->sm_count);
+            {
+                sdk_prof_scope ps(c, "poolgemm");
+                SDK_TRY(pg_launch(c, cfg, ta, tb, p, grid));
+            }
+        }
+        if (mode == 0) {
+            sdk_prof_scope ps(c, "merge");
+            k_pg_merge<<<(unsigned)(gb - ga), 256, 0, c->stream>>>(d_goff, (int32_t)ga, RB, (const int32_t*)c->slot_cnt.p,
+                                                                   (const int32_t*)c->slot_row.p, (const float*)c->slot_val.p,
+                                                                   (const float*)c->slot_bound.p, tau, ncand, d_cand_row, d_gbound);
+            c->launches++;
+            SDK_CUDA(c, cudaGetLastError());
+        }
+    }
+    return SDK_OK;
+}
+
+int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int64_t P, const __nv_bfloat16* d_seg, int64_t N,
+                                   int32_t Dp, const int64_t* d_goff, int32_t G, int32_t pool, float tau, int32_t ncand,
+                                   int32_t* d_cand_row, float* d_gbound) {
+    return pg_run(c, d_bank, P, d_seg, N, Dp, d_goff, G, pool, 0, tau, ncand, d_cand_row, d_gbound, nullptr);
+}
+
+int sdk_launch_poolgemm_dense(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv_bfloat16* d_cols, int64_t N,
+                              int32_t Dp, const int64_t* d_goff, int32_t G, int32_t pool, float* d_out) {
+    return pg_run(c, d_rows, P, d_cols, N, Dp, d_goff, G, pool, 1, 0.f, 0, nullptr, nullptr, d_out);
+}

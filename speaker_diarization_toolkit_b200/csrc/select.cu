@@ -1,0 +1,264 @@
+// select.cu -- K3 (ordered top-k with row->speaker max and threshold), the top-k certificate of the
+// tcgen05 path, the fp64 assignment (combine_signals restatement) and K4 (merge after all-gather).
+#include "common.cuh"
+
+#define SDK_SEL_THREADS 256
+
+__device__ __forceinline__ unsigned long long sdk_block_max_u64(unsigned long long v, unsigned long long* sh) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, v, off);
+        v = o > v ? o : v;
+    }
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[w] = v;
+    __syncthreads();
+    unsigned long long r = sh[0];
+    for (int i = 1; i < nw; ++i) r = sh[i] > r ? sh[i] : r;
+    return r;
+}
+
+// One CTA per label group.  Entries are (slot -> bank row, pooled Q30).  Keys are
+// (orderable fp32 score << 32) | ~row, so a descending key order is exactly (-score, row).
+// Keys are unique, so "already extracted" == key >= last extracted key: no per-entry state.
+// A speaker's first extracted row is its best row (max over rows, ties: lowest row); later rows of
+// the same speaker are skipped.  Stops at k matches or when the score drops below the threshold.
+__global__ void __launch_bounds__(SDK_SEL_THREADS)
+k_select(long long* __restrict__ qpool, const int64_t* __restrict__ goff, const int32_t* __restrict__ glist,
+         const int32_t* __restrict__ cand_row, int64_t nslot, int32_t pool,
+         const int32_t* __restrict__ row_speaker, const uint8_t* __restrict__ row_trust, double threshold,
+         int32_t k, int64_t row_offset, const float* __restrict__ gbound, float eps,
+         int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list, int64_t* __restrict__ out_row,
+         float* __restrict__ out_score, int32_t* __restrict__ out_count, uint8_t* __restrict__ out_trust,
+         int32_t* __restrict__ out_spk) {
+    __shared__ unsigned long long sh[SDK_SEL_THREADS / 32];
+    __shared__ int32_t sel_spk[SDK_MAX_K];
+    const int32_t gi = blockIdx.x;
+    const int32_t g = glist ? glist[gi] : gi;
+    const int tid = threadIdx.x;
+    const long long n = goff[g + 1] - goff[g];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(qpool) + (int64_t)gi * nslot;
+
+    for (int i = tid; i < k; i += SDK_SEL_THREADS) {
+        out_row[(int64_t)g * k + i] = -1;
+        out_score[(int64_t)g * k + i] = 0.f;
+        out_trust[(int64_t)g * k + i] = SDK_TRUST_UNKNOWN;
+        out_spk[(int64_t)g * k + i] = -1;
+    }
+    if (n <= 0) {
+        if (tid == 0) out_count[g] = 0;
+        return;
+    }
+    // pass 0: Q30 -> key, in place (0 = invalid slot)
+    for (int64_t j = tid; j < nslot; j += SDK_SEL_THREADS) {
+        int32_t row = cand_row ? cand_row[(int64_t)gi * nslot + j] : (int32_t)j;
+        unsigned long long key = 0ull;
+        if (row >= 0) {
+            float sim = sdk_pool_finish((long long)keys[j], n, pool);
+            key = ((unsigned long long)sdk_fkey(sim) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)row);
+        }
+        keys[j] = key;
+    }
+    __syncthreads();
+    unsigned long long last = ~0ull;
+    int cnt = 0;
+    float kth = 0.f;
+    while (cnt < k) {
+        unsigned long long best = 0ull;
+        for (int64_t j = tid; j < nslot; j += SDK_SEL_THREADS) {
+            unsigned long long key = keys[j];
+            if (key < last && key > best) best = key;
+        }
+        best = sdk_block_max_u64(best, sh);
+        if (best == 0ull) break;
+        last = best;
+        float sim = sdk_funkey((uint32_t)(best >> 32));
+        if (!((double)sim >= threshold)) break;
+        int32_t row = (int32_t)(0xffffffffu - (uint32_t)(best & 0xffffffffu));
+        int32_t spk = row_speaker[row];
+        bool dup = false;
+        for (int i = 0; i < cnt; ++i) dup |= sel_spk[i] == spk;
+        __syncthreads();
+        if (dup) continue;
+        if (tid == 0) {
+            sel_spk[cnt] = spk;
+            out_row[(int64_t)g * k + cnt] = (int64_t)row + row_offset;
+            out_score[(int64_t)g * k + cnt] = sim;
+            out_trust[(int64_t)g * k + cnt] = row_trust ? row_trust[row] : SDK_TRUST_UNKNOWN;
+            out_spk[(int64_t)g * k + cnt] = spk;
+        }
+        kth = sim;
+        ++cnt;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        out_count[g] = cnt;
+        if (gbound) {
+            // certificate: every row that was NOT re-scored has approx score <= bound, hence a
+            // canonical score <= bound + eps.  It cannot enter the result if that is below the
+            // threshold, or below the k-th kept score when the list is full.
+            double b = (double)gbound[g] + (double)eps;
+            bool safe = (b < threshold) || (cnt == k && b < (double)kth);
+            if (!safe) {
+                int pos = atomicAdd(fb_count, 1);
+                fb_list[pos] = g;
+            }
+        }
+    }
+}
+
+int sdk_launch_select(sdk_ctx* c, const long long* d_qpool, const int64_t* d_goff, const int32_t* d_glist,
+                      int32_t ngroups, const int32_t* d_cand_row, int64_t nslot, int32_t pool,
+                      const int32_t* d_row_speaker, const uint8_t* d_row_trust, double threshold, int32_t k,
+                      int64_t row_offset, const float* d_gbound, float eps, int32_t* d_fb_count,
+                      int32_t* d_fb_list, int64_t* d_out_row, float* d_out_score, int32_t* d_out_count,
+                      uint8_t* d_out_trust, int32_t* d_out_spk) {
+    if (ngroups <= 0) return SDK_OK;
+    sdk_prof_scope ps(c, "select");
+    k_select<<<ngroups, SDK_SEL_THREADS, 0, c->stream>>>(const_cast<long long*>(d_qpool), d_goff, d_glist, d_cand_row,
+                                                         nslot, pool, d_row_speaker, d_row_trust, threshold, k,
+                                                         row_offset, d_gbound, eps, d_fb_count, d_fb_list, d_out_row,
+                                                         d_out_score, d_out_count, d_out_trust, d_out_spk);
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}
+
+// ---- assignment: restates speaker-assign:418-492 for embedding_match-only signal lists ---------
+// (see oracle/canonical.c orc_assign for the line-by-line citation).  One thread per label group,
+// fp64, same operation order as the Python: weight = 0.4; weight *= mult; ws = weight * score;
+// scores[id] = 0.0 + ws; stable descending sort; bands; threshold.
+__global__ void k_assign(const int64_t* __restrict__ m_row, const float* __restrict__ m_score,
+                         const uint8_t* __restrict__ m_trust, const int32_t* __restrict__ m_count, int32_t L,
+                         int32_t k, double thr, int32_t min_trust, int32_t* __restrict__ a_idx,
+                         double* __restrict__ a_score, int32_t* __restrict__ a_conf, int32_t* __restrict__ c_idx,
+                         double* __restrict__ c_score) {
+    const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= L) return;
+    const double mult[5] = {1.0, 0.7, 0.4, 0.0, 0.5};
+    auto rank_of = [](int code) { return code == 2 ? 0 : code == 1 ? 1 : code == 0 ? 2 : -1; };
+    const int min_rank = rank_of(min_trust);
+    double w[SDK_MAX_K];
+    int32_t id[SDK_MAX_K];
+    int m = 0;
+    const int cnt = m_count[g];
+    for (int i = 0; i < cnt; ++i) {
+        if (m_row[(int64_t)g * k + i] < 0) continue;
+        int t = m_trust[(int64_t)g * k + i];
+        int tr = rank_of(t);
+        if (min_rank >= 0 && tr >= 0 && tr < min_rank) continue;
+        double weight = 0.4;
+        weight = __dmul_rn(weight, mult[t > 4 ? 4 : t]);
+        double ws = __dmul_rn(weight, (double)m_score[(int64_t)g * k + i]);
+        double wa = __dadd_rn(0.0, ws);
+        int b = m - 1;   // stable insertion, descending
+        while (b >= 0 && w[b] < wa) { w[b + 1] = w[b]; id[b + 1] = id[b]; --b; }
+        w[b + 1] = wa;
+        id[b + 1] = i;
+        ++m;
+    }
+    for (int j = 0; j < 3; ++j) { c_idx[g * 3 + j] = -1; c_score[g * 3 + j] = 0.0; }
+    if (m == 0) { a_idx[g] = -1; a_score[g] = 0.0; a_conf[g] = SDK_CONF_UNASSIGNED; return; }
+    const double best = w[0];
+    const int conf = best >= 0.7 ? SDK_CONF_HIGH : best >= 0.4 ? SDK_CONF_MEDIUM : best >= 0.2 ? SDK_CONF_LOW : SDK_CONF_UNASSIGNED;
+    a_score[g] = best;
+    if (best < thr) {
+        a_idx[g] = -1;
+        a_conf[g] = SDK_CONF_UNASSIGNED;
+        for (int j = 0; j < 3 && j < m; ++j) { c_idx[g * 3 + j] = id[j]; c_score[g * 3 + j] = w[j]; }
+    } else {
+        a_idx[g] = id[0];
+        a_conf[g] = conf;
+        for (int j = 0; j < 3 && j + 1 < m; ++j) { c_idx[g * 3 + j] = id[j + 1]; c_score[g * 3 + j] = w[j + 1]; }
+    }
+}
+
+int sdk_launch_assign(sdk_ctx* c, const int64_t* d_row, const float* d_score, const uint8_t* d_trust,
+                      const int32_t* d_count, int32_t L, int32_t k, double thr, int32_t min_trust, int32_t* d_idx,
+                      double* d_ascore, int32_t* d_conf, int32_t* d_cidx, double* d_cscore) {
+    if (L <= 0) return SDK_OK;
+    sdk_prof_scope ps(c, "assign");
+    k_assign<<<(L + 127) / 128, 128, 0, c->stream>>>(d_row, d_score, d_trust, d_count, L, k, thr, min_trust, d_idx,
+                                                      d_ascore, d_conf, d_cidx, d_cscore);
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}
+
+// ---- K4: merge `world` per-rank top-k lists (after ncclAllGather) by (-score, global row) -------
+// Bank shards are cut on speaker boundaries (asserted by the host), so no cross-rank speaker
+// de-duplication is needed.  One warp per label group; world*k <= 8*32 entries, 8 per lane.
+__global__ void k_merge_topk(const int64_t* __restrict__ rows, const float* __restrict__ scores,
+                             const uint8_t* __restrict__ trust, const int32_t* __restrict__ spk,
+                             const int32_t* __restrict__ counts, int32_t world, int32_t L, int32_t k,
+                             int64_t* __restrict__ o_row, float* __restrict__ o_score,
+                             int32_t* __restrict__ o_count, uint8_t* __restrict__ o_trust,
+                             int32_t* __restrict__ o_spk) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= L) return;
+    const int g = warp;
+    const int total = world * k;
+    int taken = 0;
+    unsigned long long last_hi = ~0ull;     // (score key << 32 | rank-major tiebreak) of the last pick
+    long long last_row = -1;
+    for (int it = 0; it < k; ++it) {
+        // best entry strictly after (last score, last row) in (-score, row) order
+        uint32_t bkey = 0;
+        long long brow = 0x7fffffffffffffffLL;
+        int bidx = -1;
+        for (int e = lane; e < total; e += 32) {
+            int r = e / k, i = e - r * k;
+            if (i >= counts[(int64_t)r * L + g]) continue;
+            int64_t off = ((int64_t)r * L + g) * k + i;
+            long long row = rows[off];
+            if (row < 0) continue;
+            uint32_t key = sdk_fkey(scores[off]);
+            bool after = (it == 0) || key < (uint32_t)(last_hi) || (key == (uint32_t)last_hi && row > last_row);
+            if (!after) continue;
+            if (bidx < 0 || key > bkey || (key == bkey && row < brow)) { bkey = key; brow = row; bidx = (int)off; }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            uint32_t ok = __shfl_xor_sync(0xffffffffu, bkey, off);
+            long long orow = __shfl_xor_sync(0xffffffffu, brow, off);
+            int oidx = __shfl_xor_sync(0xffffffffu, bidx, off);
+            if (oidx >= 0 && (bidx < 0 || ok > bkey || (ok == bkey && orow < brow))) { bkey = ok; brow = orow; bidx = oidx; }
+        }
+        if (bidx < 0) break;
+        if (lane == 0) {
+            o_row[(int64_t)g * k + taken] = brow;
+            o_score[(int64_t)g * k + taken] = scores[bidx];
+            o_trust[(int64_t)g * k + taken] = trust[bidx];
+            o_spk[(int64_t)g * k + taken] = spk[bidx];
+        }
+        last_hi = bkey;
+        last_row = brow;
+        ++taken;
+    }
+    if (lane == 0) {
+        o_count[g] = taken;
+        for (int i = taken; i < k; ++i) {
+            o_row[(int64_t)g * k + i] = -1;
+            o_score[(int64_t)g * k + i] = 0.f;
+            o_trust[(int64_t)g * k + i] = SDK_TRUST_UNKNOWN;
+            o_spk[(int64_t)g * k + i] = -1;
+        }
+    }
+}
+
+int sdk_launch_merge_topk(sdk_ctx* c, const int64_t* d_rows, const float* d_scores, const uint8_t* d_trust,
+                          const int32_t* d_spk, const int32_t* d_counts, int32_t world, int32_t L, int32_t k,
+                          int64_t* d_out_row, float* d_out_score, int32_t* d_out_count, uint8_t* d_out_trust,
+                          int32_t* d_out_spk) {
+    if (L <= 0) return SDK_OK;
+    sdk_prof_scope ps(c, "merge");
+    int threads = 128, warps_per_block = threads / 32;
+    int blocks = (L + warps_per_block - 1) / warps_per_block;
+    k_merge_topk<<<blocks, threads, 0, c->stream>>>(d_rows, d_scores, d_trust, d_spk, d_counts, world, L, k, d_out_row,
+                                                    d_out_score, d_out_count, d_out_trust, d_out_spk);
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}

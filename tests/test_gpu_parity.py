@@ -1,0 +1,179 @@
+"""GPU parity tests: the CUDA path, called THROUGH THE C-ABI, against the C oracle on identical inputs.
+
+Bar (BASELINE.json): matched rows / ids / counts bit-exact; scores here are bit-exact too, because the
+CUDA path re-scores in the oracle's canonical arithmetic (oracle/canonical.c).
+"""
+import numpy as np
+import pytest
+
+from speaker_diarization_toolkit_b200 import _native, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(ctx, case, dtype, pool, thr, k, path, cand=None, eps=None):
+    ctx.set_option("path", path)
+    ctx.set_option("cand", cand if cand is not None else 16)
+    ctx.set_option("eps", eps if eps is not None else -1.0)
+    ctx.bank_load(case.bank, case.row_speaker, case.row_trust, dtype=dtype)
+    rows, scores, counts = ctx.identify(case.seg, case.seg_label, case.G, pool=pool, threshold=thr, k=k)
+    return rows, scores, counts
+
+
+def run_oracle(oracle, case, dtype, pool, thr, k):
+    return oracle.identify(case.seg, case.goff, case.bank, case.row_speaker, case.n_speakers, mode=dtype, pool=pool,
+                           threshold=thr, k=k)
+
+
+def assert_same(gpu, ref, what=""):
+    (r, s, c), (orow, oscore, ocount) = gpu, ref
+    assert np.array_equal(c, ocount), f"{what}: counts differ"
+    assert np.array_equal(r, orow), f"{what}: matched rows differ\n{r[:4]}\n{orow[:4]}"
+    assert np.array_equal(s.view(np.uint32), oscore.view(np.uint32)), f"{what}: scores not bit-identical"
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("pool", [0, 1])
+def test_config1_exact(ctx, oracle, dtype, pool):
+    case = synth.config1()
+    gpu = run_gpu(ctx, case, dtype, pool, 0.354, 3, path=1)
+    assert_same(gpu, run_oracle(oracle, case, dtype, pool, 0.354, 3), "cfg1")
+    assert ctx.last_path()[0] == 1
+    # planted truth: S1 -> speaker 0, S2 -> speaker 1
+    assert gpu[0][0, 0] == 0 and gpu[0][1, 0] == 1
+
+
+@pytest.mark.parametrize("dtype,pool,thr,k", [(0, 0, 0.354, 10), (0, 1, 0.354, 10), (1, 0, 0.354, 10), (0, 0, -1.0, 10),
+                                              (1, 1, 0.1, 32), (0, 0, 0.95, 1)])
+def test_config2_exact(ctx, oracle, dtype, pool, thr, k):
+    case = synth.config2()
+    gpu = run_gpu(ctx, case, dtype, pool, thr, k, path=1)
+    assert_same(gpu, run_oracle(oracle, case, dtype, pool, thr, k), "cfg2")
+
+
+def test_auto_path_small_is_exact(ctx):
+    case = synth.config2()
+    run_gpu(ctx, case, 0, 0, 0.354, 10, path=0)
+    assert ctx.last_path()[0] == 1
+
+
+def ragged_case(seed, D, P_speakers=150, rps=(1, 2, 3)):
+    rng = np.random.default_rng(seed)
+    counts = [1, 15, 16, 17, 0, 63, 64, 65, 300, 0, 1000, 129, 2, 127]
+    rows_per = rng.choice(rps, size=P_speakers)
+    return synth.make_case(seed, counts, P_speakers, D, rows_per_speaker=rows_per, impostor_frac=0.2)
+
+
+@pytest.mark.parametrize("D", [64, 100, 128, 192, 256, 320, 384, 448, 512])
+def test_tensor_path_ragged_dims(ctx, oracle, D):
+    """tcgen05 path on every K-chunk configuration, ragged groups (empty, 1, straddling 16/64 boundaries),
+    bank size not a multiple of 128, several rows per speaker, bf16 operands."""
+    case = ragged_case(1000 + D, D)
+    gpu = run_gpu(ctx, case, 1, 0, 0.354, 10, path=2)
+    assert ctx.last_path()[0] == 2
+    assert_same(gpu, run_oracle(oracle, case, 1, 0, 0.354, 10), f"tc D={D}")
+
+
+@pytest.mark.parametrize("dtype,pool,thr,k", [(1, 1, 0.354, 10), (0, 0, 0.354, 10), (0, 1, 0.5, 3), (1, 0, -1.0, 10),
+                                              (1, 1, -1.0, 10), (1, 0, 0.05, 32)])
+def test_tensor_path_modes(ctx, oracle, dtype, pool, thr, k):
+    case = ragged_case(77, 192, P_speakers=400)
+    gpu = run_gpu(ctx, case, dtype, pool, thr, k, path=2)
+    assert_same(gpu, run_oracle(oracle, case, dtype, pool, thr, k), "tc modes")
+
+
+def test_tensor_path_certificate_fallback(ctx, oracle):
+    """A hopeless certificate (one candidate per label, huge eps) must route the groups through the
+    exhaustive canonical fallback and still give the oracle's answer."""
+    case = ragged_case(78, 128, P_speakers=300)
+    gpu = run_gpu(ctx, case, 1, 0, -1.0, 10, path=2, cand=1, eps=0.5)
+    assert ctx.last_path()[1] > 0, "expected certificate failures"
+    assert_same(gpu, run_oracle(oracle, case, 1, 0, -1.0, 10), "fallback")
+
+
+def test_tensor_path_large_bank_many_rowblocks(ctx, oracle):
+    rng = np.random.default_rng(5)
+    case = synth.make_case(5, synth.zipf_counts(rng, 600, 6), 2100, 192, neighbours=5, impostor_frac=0.0)
+    gpu = run_gpu(ctx, case, 1, 0, 0.354, 10, path=2)
+    assert_same(gpu, run_oracle(oracle, case, 1, 0, 0.354, 10), "tc many row blocks")
+    assert (gpu[2] >= 2).any(), "planted neighbours should give multi-entry top-k lists"
+
+
+def test_zero_rows_and_scale_invariance(ctx, oracle):
+    case = synth.config2(total=400, P=60)
+    case.seg[5] = 0.0
+    case.bank[7] = 0.0
+    gpu = run_gpu(ctx, case, 0, 0, 0.354, 5, path=1)
+    assert_same(gpu, run_oracle(oracle, case, 0, 0, 0.354, 5), "zero rows")
+
+
+def test_assign_matches_oracle_and_python(ctx, oracle):
+    from oracle import matching_np as mnp
+    case = synth.config2(total=1000, P=200)
+    # several rows per trust level, low threshold so that lists are long
+    ctx.set_option("path", 1)
+    ctx.bank_load(case.bank, case.row_speaker, case.row_trust, dtype=0)
+    rows, scores, counts = ctx.identify(case.seg, case.seg_label, case.G, threshold=0.05, k=8)
+    for thr, min_trust in [(0.3, "low"), (0.1, "medium"), (0.0, "high"), (0.3, "none")]:
+        ctx.assign(thr, min_trust)
+        out = ctx.fetch(with_assign=True)
+        code = _native.TRUST_CODES.get(min_trust, 99)
+        a_idx, a_score, a_conf, c_idx, c_score = oracle.assign(out["row"], out["score"], out["trust"], out["count"], thr, code)
+        assert np.array_equal(out["assign_idx"], a_idx)
+        assert np.array_equal(out["assign_score"].view(np.uint64), a_score.view(np.uint64))
+        assert np.array_equal(out["assign_conf"], a_conf)
+        assert np.array_equal(out["cand_idx"], c_idx)
+        assert np.array_equal(out["cand_score"].view(np.uint64), c_score.view(np.uint64))
+        # and against the Python restatement of combine_signals fed the same per-label signal lists
+        for g in range(case.G):
+            sigs = []
+            for i in range(out["count"][g]):
+                trust = _native.TRUST_NAMES[out["trust"][g, i]]
+                if not mnp.passes_min_trust(trust, min_trust):
+                    continue
+                sigs.append(mnp.Signal("embedding_match", str(int(out["row"][g, i])), float(out["score"][g, i]),
+                                       {"trust_level": trust}))
+            ref = mnp.combine_signals(f"S{g}", sigs, threshold=thr)
+            got_id = None if out["assign_idx"][g] < 0 else str(int(out["row"][g, out["assign_idx"][g]]))
+            assert got_id == ref["speaker_id"]
+            assert out["assign_score"][g] == ref["score"]
+            assert _native.CONF_NAMES[out["assign_conf"][g]] == ref["confidence"]
+            got_c = [(str(int(out["row"][g, j])), out["cand_score"][g, n]) for n, j in enumerate(out["cand_idx"][g]) if j >= 0]
+            assert got_c == [(c["speaker_id"], c["score"]) for c in ref["candidates"]]
+
+
+@pytest.mark.parametrize("dtype,pool,path", [(1, 0, 1), (1, 1, 1), (0, 0, 1), (1, 0, 2), (1, 1, 2)])
+def test_affinity_pooled(ctx, oracle, dtype, pool, path):
+    case = synth.config5(N=1500, L=7, D=256)
+    ctx.set_option("path", path)
+    nl, ll = ctx.affinity_pooled(case.seg, case.seg_label, case.G, dtype=dtype, pool=pool)
+    ref = oracle.affinity(case.seg, case.goff, mode=dtype, pool=pool)
+    if path == 1:
+        assert np.array_equal(nl.view(np.uint32), ref.view(np.uint32))
+    else:
+        # tcgen05: same bf16 operands, exact products, fp32 accumulation in a different order
+        np.testing.assert_allclose(nl, ref, rtol=0, atol=2e-5)
+    q = np.rint(nl.astype(np.float64) * 2.0 ** 30).astype(np.int64)
+    cnt = np.diff(case.goff)
+    ll_ref = np.stack([q[case.goff[a]:case.goff[a + 1]].sum(axis=0) / (cnt[a] * 2.0 ** 30) for a in range(case.G)])
+    assert np.array_equal(ll, ll_ref.astype(np.float32))
+    # every segment is closest to its own label on planted data
+    assert (nl.argmax(axis=1) == case.seg_label).mean() > 0.99
+
+
+def test_errors(ctx):
+    case = synth.config1()
+    ctx.set_option("path", 0)
+    ctx.bank_load(case.bank, case.row_speaker, case.row_trust)
+    with pytest.raises(_native.NativeError, match="non-decreasing"):
+        ctx.identify(case.seg, case.seg_label[::-1].copy(), case.G)
+    with pytest.raises(_native.NativeError, match="out of range"):
+        ctx.identify(case.seg, case.seg_label + 5, case.G)
+    with pytest.raises(_native.NativeError, match="k must be"):
+        ctx.identify(case.seg, case.seg_label, case.G, k=33)
+    with pytest.raises(_native.NativeError, match="contiguous"):
+        ctx.bank_load(case.bank, np.array([0, 1, 0], dtype=np.int32))
+    # empty input: no segments at all -> no matches
+    ctx.bank_load(case.bank, case.row_speaker, case.row_trust)
+    rows, scores, counts = ctx.identify(np.zeros((0, 192), np.float32), np.zeros(0, np.int32), 2)
+    assert (counts == 0).all() and (rows == -1).all()
