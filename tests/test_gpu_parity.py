@@ -70,7 +70,7 @@ def test_tensor_path_ragged_dims(ctx, oracle, D):
     bank size not a multiple of 128, several rows per speaker, bf16 operands."""
     case = ragged_case(1000 + D, D)
     gpu = run_gpu(ctx, case, 1, 0, 0.354, 10, path=2)
-    assert ctx.last_path()[0] == 2
+    assert ctx.last_path() == (2, 0), "tcgen05 path must certify every label (no exhaustive fallback)"
     assert_same(gpu, run_oracle(oracle, case, 1, 0, 0.354, 10), f"tc D={D}")
 
 
@@ -79,6 +79,10 @@ def test_tensor_path_ragged_dims(ctx, oracle, D):
 def test_tensor_path_modes(ctx, oracle, dtype, pool, thr, k):
     case = ragged_case(77, 192, P_speakers=400)
     gpu = run_gpu(ctx, case, dtype, pool, thr, k, path=2)
+    path, nfb = ctx.last_path()
+    assert path == 2
+    if thr > 0.2:
+        assert nfb == 0, "thresholded planted data must certify without fallback"
     assert_same(gpu, run_oracle(oracle, case, dtype, pool, thr, k), "tc modes")
 
 
@@ -95,6 +99,7 @@ def test_tensor_path_large_bank_many_rowblocks(ctx, oracle):
     rng = np.random.default_rng(5)
     case = synth.make_case(5, synth.zipf_counts(rng, 600, 6), 2100, 192, neighbours=5, impostor_frac=0.0)
     gpu = run_gpu(ctx, case, 1, 0, 0.354, 10, path=2)
+    assert ctx.last_path() == (2, 0)
     assert_same(gpu, run_oracle(oracle, case, 1, 0, 0.354, 10), "tc many row blocks")
     assert (gpu[2] >= 2).any(), "planted neighbours should give multi-entry top-k lists"
 
