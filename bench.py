@@ -1,0 +1,418 @@
+#!/usr/bin/env python3
+"""bench.py -- scored segment x profile pairs / second on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg2|cfg4|cfg5]
+
+Default workload = BASELINE.json configs[2] ("cfg3": batch of 10k recordings, ~20M segments, vs a 10k-profile
+bank, 192-d, bf16 operands) -- the configuration the metric "pairs/sec at 1/2/4/8 B200" is quoted on; it fits one
+GPU.  For N > 1 the recordings are split over the ranks (independent units, NO data-path collective), total
+work fixed -> "scaling": "strong".  A step = one pass of the hot path (normalise -> tcgen05 pooled GEMM ->
+canonical re-score -> top-k -> assignment) over the rank's batch.
+  value       inputs resident in HBM (device pointers through the C-ABI), CUDA-event timed on the library stream
+  e2e         same metric through the host-buffer C-ABI call: pinned host -> device copies and result read-back
+              inside the timed region
+  roofline    dominant kernel (tcgen05 pooled GEMM) against the measured bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the NumPy/OpenBLAS port of the path (oracle/matching_np.py) on a bounded sample, all host cores
+`--impl reference` times that CPU port only (rank 0), same metric/config.
+Synthetic data (the reference's embedding extractors are network APIs): planted speakers, sigma 0.35, 10 % impostors.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "scored segment x profile pairs per second"
+UNIT = "pairs/s"
+
+WORKLOADS = {
+    # name: recordings, segments/recording (Poisson mean), labels/recording, bank rows, D, dtype, k, threshold
+    "cfg3": dict(R=10000, seg=2000, labels=8, P=10000, D=192, dtype=1, k=4, thr=0.354, seed=303,
+                 desc="configs[2]: 10k recordings (~20M segments) vs 10k-profile bank, 192-d, bf16 operands, DP over recordings"),
+    "cfg2": dict(R=1, seg=2000, labels=8, P=500, D=256, dtype=0, k=10, thr=0.354, seed=202,
+                 desc="configs[1]: 1-hour meeting, 8 labels x 2k segments vs 500-profile bank, 256-d fp32 (latency-bound)"),
+    "cfg4": dict(R=64, seg=2000, labels=8, P=125000, D=512, dtype=1, k=10, thr=-1.0, seed=404,
+                 desc="configs[3]: 125k bank rows PER GPU (1M at 8 GPUs), 512-d bf16, top-10 per label, NCCL all-gather merge"),
+}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ---- synthetic batch (group counts on the host, embeddings generated on the device) -------------------
+def group_counts(cfg, scale):
+    rng = np.random.default_rng(cfg["seed"])
+    R = max(1, int(round(cfg["R"] * scale)))
+    L = cfg["labels"]
+    w = 1.0 / np.arange(1, L + 1)
+    counts = np.empty((R, L), dtype=np.int64)
+    tot = np.maximum(L, rng.poisson(cfg["seg"], size=R))
+    for r in range(R):
+        ww = rng.permutation(w)
+        c = np.maximum(1, np.floor(ww / ww.sum() * tot[r]).astype(np.int64))
+        c[np.argmax(c)] += tot[r] - c.sum()
+        counts[r] = c
+    truth = rng.integers(0, cfg["P"], size=(R, L))
+    truth[rng.random((R, L)) < 0.1] = -1
+    return counts, truth
+
+
+def make_bank(torch, cfg, dev, n_rows, row0=0):
+    g = torch.Generator(device=dev)
+    g.manual_seed(cfg["seed"] * 7919 + 1)
+    D = cfg["D"]
+    # centroids are generated for the whole bank id space so every rank agrees on them
+    cent = torch.randn((cfg["P_total"], D), generator=g, device=dev, dtype=torch.float32)
+    cent = cent / cent.norm(dim=1, keepdim=True)
+    rows = cent[row0:row0 + n_rows] + 0.35 / math.sqrt(D) * torch.randn((n_rows, D), generator=g, device=dev)
+    rows = rows / rows.norm(dim=1, keepdim=True) * (0.5 + 19.5 * torch.rand((n_rows, 1), generator=g, device=dev))
+    return cent, rows.contiguous()
+
+
+def make_segments(torch, cfg, dev, cent, counts, truth, seed):
+    """counts/truth: [R_local, L].  Returns (seg [N,D] fp32 device, label [N] int32 device, N, G)."""
+    D = cfg["D"]
+    flat_c = counts.reshape(-1)
+    G = flat_c.shape[0]
+    N = int(flat_c.sum())
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    lab = torch.repeat_interleave(torch.arange(G, device=dev, dtype=torch.int32), torch.as_tensor(flat_c, device=dev))
+    t = torch.as_tensor(truth.reshape(-1), device=dev)
+    imp = torch.randn((G, D), generator=g, device=dev)
+    imp = imp / imp.norm(dim=1, keepdim=True)
+    gcent = torch.where((t >= 0)[:, None], cent[t.clamp(min=0)], imp)           # [G, D]
+    seg = torch.empty((N, D), device=dev, dtype=torch.float32)
+    step = 1 << 21
+    for a in range(0, N, step):
+        b = min(N, a + step)
+        x = gcent[lab[a:b].long()] + 0.35 / math.sqrt(D) * torch.randn((b - a, D), generator=g, device=dev)
+        x = x / x.norm(dim=1, keepdim=True) * (0.5 + 19.5 * torch.rand((b - a, 1), generator=g, device=dev))
+        seg[a:b] = x
+    return seg, lab, N, G
+
+
+# ---- clocks sampler ------------------------------------------------------------------------------
+class Clocks:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev_index):
+        self.samples, self.proc, self.dev = [], None, dev_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        mhz, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                mhz.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+# ---- CPU port (cpu_baseline and --impl reference) -------------------------------------------------
+def cpu_port_rate(cfg, counts, truth, budget_s, rec_cap=None):
+    """Times oracle/matching_np.identify (+ the combine_signals restatement) recording by recording on the host.
+    Returns (pairs/s, recordings timed, seconds)."""
+    from oracle import matching_np as mnp
+    from speaker_diarization_toolkit_b200 import synth
+    P, D, L = cfg["P_cpu"], cfg["D"], cfg["labels"]
+    rng = np.random.default_rng(cfg["seed"] + 1)
+    cent = rng.standard_normal((P, D)).astype(np.float32)
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    bank = cent + (0.35 / math.sqrt(D)) * rng.standard_normal((P, D)).astype(np.float32)
+    row_speaker = np.arange(P, dtype=np.int32)
+    trust_names = ["high", "medium", "low"]
+    pairs, t_used, n_rec = 0, 0.0, 0
+    R = counts.shape[0]
+    while t_used < budget_s and n_rec < (rec_cap or R):
+        r = n_rec % R
+        c = counts[r]
+        goff = np.r_[0, np.cumsum(c)]
+        n = int(goff[-1])
+        tr = np.repeat(np.where(truth[r] >= 0, truth[r] % P, 0), c)
+        seg = cent[tr] + (0.35 / math.sqrt(D)) * rng.standard_normal((n, D)).astype(np.float32)
+        t0 = time.perf_counter()
+        rows, scores, cnt = mnp.identify(seg, goff, bank, row_speaker, mode=cfg["dtype"], pool=0, threshold=cfg["thr"], k=cfg["k"])
+        for g in range(L):
+            sigs = [mnp.Signal("embedding_match", str(int(rows[g, i])), float(scores[g, i]),
+                               {"trust_level": trust_names[int(rows[g, i]) % 3]}) for i in range(cnt[g])]
+            mnp.combine_signals(f"S{g}", sigs, threshold=0.3)
+        t_used += time.perf_counter() - t0
+        pairs += n * P
+        n_rec += 1
+    return pairs / max(t_used, 1e-9), n_rec, t_used
+
+
+def run_reference(args, cfg, counts, truth):
+    """`--impl reference`: the CPU port on the host cores; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = max(1.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_port_rate(cfg, counts, truth, per_step)
+    tot_pairs, tot_t, tot_rec = 0.0, 0.0, 0
+    for _ in range(args.steps):
+        rate, n_rec, t = cpu_port_rate(cfg, counts, truth, per_step)
+        tot_pairs += rate * t
+        tot_t += t
+        tot_rec += n_rec
+    value = tot_pairs / tot_t
+    sample = f"{tot_rec / max(1, args.steps):.0f} recordings per step (~{per_step:.0f} s of NumPy/OpenBLAS), bank {cfg['P_cpu']} rows"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
+            "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ---- main -----------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the recordings (debug runs only; 1.0 = the named config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(WORKLOADS[args.workload])
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sharded = args.workload == "cfg4"
+    cfg["scaling"] = "weak" if sharded else "strong"
+    cfg["P_total"] = cfg["P"] * (world if sharded else 1)
+    cfg["P_cpu"] = cfg["P_total"]
+    counts, truth = group_counts(cfg, args.scale)
+    if sharded:
+        truth = np.where(truth >= 0, truth * world, truth)        # true speakers spread over all shards
+    if args.impl == "reference":
+        return run_reference(args, cfg, counts, truth)
+
+    import torch
+    import torch.distributed as dist
+    from speaker_diarization_toolkit_b200 import _native
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    uid = None
+    if sharded and world > 1:
+        box = [_native.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    ctx = _native.Context(local_rank, world if sharded else 1, rank if sharded else 0, uid)
+    ctx.set_option("profile", 1)
+
+    # ---- data: bank (replicated, or this rank's row shard) + this rank's recordings ----
+    R = counts.shape[0]
+    if sharded:
+        r0, r1 = 0, R                                    # queries replicated, bank row-sharded
+        cent, bank = make_bank(torch, cfg, dev, cfg["P"], row0=rank * cfg["P"])
+        row_off = rank * cfg["P"]
+    else:
+        r0, r1 = rank * R // world, (rank + 1) * R // world   # recordings split over ranks
+        cent, bank = make_bank(torch, cfg, dev, cfg["P"])
+        row_off = 0
+    P, D = bank.shape
+    spk = torch.arange(P, device=dev, dtype=torch.int32)
+    trust = (torch.arange(P, device=dev) % 3).to(torch.uint8)
+    ctx.bank_load_dev(bank.data_ptr(), spk.data_ptr(), trust.data_ptr(), P, D, cfg["dtype"], row_off)
+    seg, lab, N, G = make_segments(torch, cfg, dev, cent, counts[r0:r1], truth[r0:r1], cfg["seed"] + (0 if sharded else 1000 + rank))
+    del cent
+    torch.cuda.synchronize()
+    pairs_rank = float(N) * float(P)
+    pairs_total = pairs_rank * (1 if False else 1)
+    if sharded:
+        pairs_total = float(N) * float(P) * world          # every rank scores all queries against its shard
+    else:
+        t = torch.tensor([pairs_rank], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t)
+        pairs_total = float(t.item())
+
+    def step_dev():
+        ctx.identify_dev(seg.data_ptr(), lab.data_ptr(), N, G, 0, cfg["thr"], cfg["k"])
+        ctx.assign(0.3, "low")
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    path, nfb = ctx.last_path()
+    ctx.profile_reset()
+    l0 = ctx.launch_count()
+    clocks = Clocks(local_rank)
+    if rank == 0:
+        clocks.start()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_dev()
+    ms = ctx.timer_stop()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = ctx.launch_count() - l0
+    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = pairs_total * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the library stream ----
+    pk, pk_src = peaks()
+    names = ["normalize", "poolgemm", "merge", "exact", "select", "assign"]
+    prof = {n: ctx.profile_get(n) for n in names}
+    tot_prof = sum(v[0] for v in prof.values()) or 1.0
+    if path == 2:
+        gms, gl = prof["poolgemm"]
+        per_launch_flops = 2.0 * pairs_rank * D / max(1, gl // max(1, args.steps))   # flops per launch = 2*D per pair
+        avg_ms = gms / max(1, gl)
+        ach = per_launch_flops / (avg_ms * 1e-3) / 1e12
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        roof = {"kernel": "k_poolgemm (tcgen05)", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "peak_source": f"{pk_src} bf16 sustained (kernel timed inside a long step)",
+                "avg_launch_ms": avg_ms, "share_of_step": gms / tot_prof}
+    else:
+        gms, gl = prof["exact"]
+        avg_ms = gms / max(1, gl)
+        bytes_alg = (N * D + P * D) * (2 if cfg["dtype"] else 4)
+        ach = bytes_alg / (avg_ms * 1e-3) / 1e9
+        roof = {"kernel": "k_exact_q30 (fp64 SIMT)", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_src} copy bandwidth",
+                "avg_launch_ms": avg_ms, "share_of_step": gms / tot_prof,
+                "note": "latency-bound shape: the fraction is informational (SURVEY 8d)"}
+    tfile = ROOT / "profiles" / "roofline_traffic.json"
+    if tfile.exists():
+        roof["traffic"] = json.loads(tfile.read_text()).get(args.workload)
+
+    # ---- e2e: host buffers through the host-pointer C-ABI call ----
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        need = N * D * 4
+        frac = 1.0
+        avail = psutil.virtual_memory().available
+        if need * 3 > avail:
+            frac = max(0.05, avail / (need * 3.0))
+        n_e = int(N * frac)
+        if frac < 1.0:                                     # cut at a label-group boundary
+            n_e = int((lab[:n_e] != lab[n_e - 1]).sum().item())
+        g_e = int(lab[n_e - 1].item()) + 1 if n_e else 0
+        h_seg = torch.empty((n_e, D), dtype=torch.float32, pin_memory=True)
+        h_lab = torch.empty((n_e,), dtype=torch.int32, pin_memory=True)
+        h_seg.copy_(seg[:n_e])
+        h_lab.copy_(lab[:n_e])
+        torch.cuda.synchronize()
+        hs, hl = h_seg.numpy(), h_lab.numpy()
+
+        def step_host():
+            ctx.identify(hs, hl, g_e, pool=0, threshold=cfg["thr"], k=cfg["k"])
+            ctx.assign(0.3, "low")
+            return ctx.fetch(with_assign=True)
+
+        step_host()
+        barrier()
+        e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            step_host()
+        ctx.sync()
+        te = time.perf_counter() - t0
+        tt = torch.tensor([te], device=dev, dtype=torch.float64)
+        pe = torch.tensor([float(n_e) * float(P) * (world if sharded else 1) / (1 if sharded else 1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if not sharded:
+                dist.all_reduce(pe)
+        k = cfg["k"]
+        e2e = {"value": float(pe.item()) * e_steps / float(tt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(n_e * D * 4 + n_e * 4), "d2h_bytes_per_step": int(g_e * (k * 13 + 4 + 4 + 8 + 4 + 12 + 24)),
+               "steps": e_steps, "sample": "whole batch" if frac == 1.0 else f"first {frac:.2f} of the rank's batch (host memory bound)"}
+        del h_seg, h_lab
+
+    # ---- CPU baseline (rank 0, bounded sample) ----
+    cpu = None
+    if rank == 0 and not args.no_cpu and world == 1:
+        rate, n_rec, t = cpu_port_rate(cfg, counts, truth, 12.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{n_rec} recordings of the same workload in {t:.1f} s (NumPy/OpenBLAS sgemm + combine_signals), extrapolates linearly"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+                "dtype": "bf16" if cfg["dtype"] else "f32", "data": "synthetic",
+                "config": {"workload": cfg["desc"], "segments_total": int(pairs_total / (P * (world if sharded else 1))),
+                           "segments_per_gpu": N, "label_groups_per_gpu": G, "bank_rows_per_gpu": P, "dim": D, "k": cfg["k"],
+                           "threshold": cfg["thr"], "pool": "mean", "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
+                           "l2": "inputs larger than L2 (no flush needed)" if N * D * 2 > 200e6 else "inputs fit L2 (latency-bound shape)",
+                           "path": "tcgen05" if path == 2 else "exact-simt", "certificate_fallback_groups": nfb, "scale": args.scale},
+                "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+                "kernel_ms_per_step": {n: v[0] / args.steps for n, v in prof.items()}}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

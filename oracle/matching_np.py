@@ -41,28 +41,42 @@ def l2_normalize(x: np.ndarray, eps: float = 1e-12) -> np.ndarray:
 
 
 def pooled_scores(seg_raw, goff, bank_raw, mode=0, pool=0, chunk_pairs=1 << 28) -> np.ndarray:
-    """Steps 1-3: [G,P] pooled cosine.  mode 1 rounds the normalised operands to bf16 first."""
+    """Steps 1-3: [G,P] pooled cosine.  mode 1 rounds the normalised operands to bf16 first.
+    One sgemm per chunk of whole label groups (S stays under chunk_pairs floats), then a segmented
+    sum / max over the rows of each group."""
     xs, bs = l2_normalize(seg_raw), l2_normalize(bank_raw)
     if mode == 1:
         xs, bs = bf16_round(xs), bf16_round(bs)
+    goff = np.asarray(goff, dtype=np.int64)
     G, P = len(goff) - 1, bs.shape[0]
     out = np.zeros((G, P), dtype=np.float32)
     bt = np.ascontiguousarray(bs.T)
-    for g in range(G):
-        s0, s1 = int(goff[g]), int(goff[g + 1])
-        if s1 <= s0:
-            continue
-        step = max(1, chunk_pairs // max(P, 1))
-        if pool == 0:
-            acc = np.zeros(P, dtype=np.float32)
-            for a in range(s0, s1, step):
-                acc += (xs[a:min(a + step, s1)] @ bt).sum(axis=0, dtype=np.float32)
-            out[g] = acc / np.float32(s1 - s0)
-        else:
-            acc = np.full(P, -np.inf, dtype=np.float32)
-            for a in range(s0, s1, step):
-                acc = np.maximum(acc, (xs[a:min(a + step, s1)] @ bt).max(axis=0))
-            out[g] = acc
+    max_rows = max(1, chunk_pairs // max(P, 1))
+    g = 0
+    while g < G:
+        h = g + 1                                         # groups [g, h): as many whole groups as fit
+        while h < G and goff[h + 1] - goff[g] <= max_rows:
+            h += 1
+        s0, s1 = int(goff[g]), int(goff[h])
+        if s1 - s0 > max_rows:                            # one oversized group: stream it
+            acc = np.zeros(P, np.float32) if pool == 0 else np.full(P, -np.inf, np.float32)
+            for a in range(s0, s1, max_rows):
+                blk = xs[a:min(a + max_rows, s1)] @ bt
+                acc = acc + blk.sum(axis=0, dtype=np.float32) if pool == 0 else np.maximum(acc, blk.max(axis=0))
+            out[g] = acc / np.float32(s1 - s0) if pool == 0 else acc
+        elif s1 > s0:
+            S = xs[s0:s1] @ bt
+            cnt = np.diff(goff[g:h + 1])
+            nz = np.flatnonzero(cnt > 0)
+            starts = (goff[g:h][nz] - s0).astype(np.int64)
+            if pool == 0:                                 # segmented mean as a second (tiny) sgemm
+                M = np.zeros((len(nz), s1 - s0), dtype=np.float32)
+                for i, j in enumerate(nz):
+                    M[i, starts[i]:starts[i] + cnt[j]] = np.float32(1.0) / np.float32(cnt[j])
+                out[g + nz] = M @ S
+            else:
+                out[g + nz] = np.maximum.reduceat(S, starts, axis=0)
+        g = h
     return out
 
 
@@ -76,16 +90,16 @@ def select_topk(sim, gcount, row_speaker, threshold=0.354, k=10, row_offset=0):
     order = np.lexsort((np.arange(P), row_speaker))  # by speaker then row
     spk_sorted = row_speaker[order]
     starts = np.flatnonzero(np.r_[True, spk_sorted[1:] != spk_sorted[:-1]])
+    runlen = np.diff(np.r_[starts, P])
+    pos = np.arange(P)
     for g in range(G):
         if gcount[g] <= 0:
             continue
         v = sim[g][order]
         best = np.maximum.reduceat(v, starts)
         # arg row: first (lowest) row attaining the max inside each speaker's run
-        ends = np.r_[starts[1:], P]
-        arg = np.empty(len(starts), dtype=np.int64)
-        for i, (a, b) in enumerate(zip(starts, ends)):
-            arg[i] = order[a + int(np.argmax(v[a:b]))]
+        first = np.minimum.reduceat(np.where(v == np.repeat(best, runlen), pos, P), starts)
+        arg = order[first]
         keep = best.astype(np.float64) >= threshold
         best, arg = best[keep], arg[keep]
         idx = np.lexsort((arg, -best))[:k]

@@ -1,0 +1,230 @@
+"""`speaker-assign assign` with a per-label embedding step (option (ii) of 8b).
+
+Same flags (speaker-assign:747-760), same YAML/JSON output (:598-649) and the same `combine_signals`
+semantics as the reference.  Differences, both on the embedding step only:
+  * ONE identify call per recording, in-process, instead of one `speaker_detection identify` subprocess per
+    label (speaker-assign:283-294);
+  * a label receives only the rows whose `label` equals it (the reference hands every label the same
+    whole-recording list, speaker-assign:276-278 "simplified implementation").
+The LLM signal (`--use-llm`) stays a subprocess to `speaker-llm` exactly as in the reference (:356-400); it is
+outside the hot path.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+from datetime import datetime, timezone
+from pathlib import Path
+from typing import List, Optional
+
+from . import signals as sg
+from . import store, transcript
+from .identify_cli import default_backend_name, identify_rows
+
+VERSION = "1.0.0"
+SCHEMA_VERSION = 1
+
+try:
+    import yaml
+    _YAML = True
+except ImportError:  # pragma: no cover
+    _YAML = False
+
+
+def compute_b3sum(path: Path) -> str:
+    """Blake3 via the `b3sum` binary, SHA-256 fallback, first 32 hex digits (speaker-assign:102-118)."""
+    try:
+        r = subprocess.run(["b3sum", "--no-names", str(path)], capture_output=True, text=True, check=True)
+        return r.stdout.strip()[:32]
+    except (subprocess.CalledProcessError, FileNotFoundError):
+        h = hashlib.sha256()
+        with open(path, "rb") as fh:
+            for chunk in iter(lambda: fh.read(1 << 16), b""):
+                h.update(chunk)
+        return h.hexdigest()[:32]
+
+
+def _load_yaml(path: Path) -> dict:
+    text = path.read_text()
+    return (yaml.safe_load(text) or {}) if _YAML else json.loads(text)
+
+
+def _save_yaml(path: Path, data: dict) -> None:
+    with open(path, "w") as fh:
+        if _YAML:
+            yaml.dump(data, fh, default_flow_style=False, sort_keys=False, allow_unicode=True)
+        else:
+            json.dump(data, fh, indent=2, ensure_ascii=False)
+
+
+def collect_llm_signals(speaker_label: str, transcript_path: Path, context_name: Optional[str]) -> List[sg.Signal]:
+    out: List[sg.Signal] = []
+    cmd = ["speaker-llm", "analyze", str(transcript_path)] + (["--context", context_name] if context_name else [])
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, env=os.environ.copy())
+    except FileNotFoundError:
+        return out
+    if r.returncode != 0 or not r.stdout.strip():
+        return out
+    try:
+        analysis = json.loads(r.stdout)
+    except json.JSONDecodeError:
+        return out
+    for det in analysis.get("detections", []):
+        if det.get("speaker_label") == speaker_label:
+            out.append(sg.Signal("llm_name_detection", det.get("detected_name", "").lower().replace(" ", "-"),
+                                 det.get("confidence", 0.5),
+                                 {"detected_name": det.get("detected_name"), "evidence": det.get("evidence", [])}))
+    return out
+
+
+def assign_labels(audio_path: Path, transcript_data: dict, *, use_embeddings: bool, min_trust: str, tags: Optional[str],
+                  threshold: float, expected_speakers: List[str], context_name: Optional[str], use_llm: bool,
+                  transcript_path: Optional[Path] = None, verbose: bool = False, backend=None) -> dict:
+    """The label loop of cmd_assign (speaker-assign:543-595) -> `mappings` dict."""
+    labels = transcript.get_speakers_from_transcript(transcript_data)
+    rows = None
+    if use_embeddings:
+        # identify is never given assign's --threshold / --backend by the reference either:
+        # backend from $SPEAKER_DETECTION_BACKEND, threshold 0.354
+        rc, rows, msg = identify_rows(audio_path, default_backend_name(None), tags, 0.354, backend)
+        if rc != 0:
+            if verbose:
+                print(f"  identify: {msg}", file=sys.stderr)
+            rows = None       # graceful degradation, as speaker-assign:296-326
+    mappings = {}
+    for label in labels:
+        segs = transcript.get_speaker_segments(transcript_data, label)
+        if verbose:
+            print(f"\nProcessing speaker {label} ({len(segs)} segments)...")
+        sigs: List[sg.Signal] = []
+        if use_embeddings and rows is not None:
+            emb = sg.signals_from_matches(rows, min_trust=min_trust, label=label)
+            sigs.extend(emb)
+            if verbose:
+                for s in emb:
+                    print(f"    - {s.speaker_id}: {s.score:.2f} (trust: {s.evidence.get('trust_level', '-')})")
+        if expected_speakers:
+            sigs.extend(sg.collect_context_signals(label, context_name, expected_speakers))
+        if use_llm and transcript_path is not None:
+            sigs.extend(collect_llm_signals(label, transcript_path, context_name))
+        a = sg.combine_signals(label, sigs, threshold=threshold)
+        mappings[label] = {"speaker_id": a.speaker_id, "confidence": a.confidence, "score": round(a.score, 3),
+                           "signals": a.signals}
+        if a.candidates:
+            mappings[label]["candidates"] = a.candidates
+    return mappings
+
+
+def cmd_assign(args, backend=None) -> int:
+    audio_path = Path(args.audio).resolve()
+    transcript_path = Path(args.transcript).resolve()
+    if not audio_path.exists():
+        print(f"Error: Audio file not found: {audio_path}", file=sys.stderr)
+        return 1
+    if not transcript_path.exists():
+        print(f"Error: Transcript file not found: {transcript_path}", file=sys.stderr)
+        return 1
+    with open(transcript_path, "r") as fh:
+        data = json.load(fh)
+    labels = transcript.get_speakers_from_transcript(data)
+    if not labels:
+        print("Error: No speakers found in transcript", file=sys.stderr)
+        return 1
+    if not args.quiet:
+        print(f"Found {len(labels)} speakers: {', '.join(labels)}")
+    context_name, expected = args.context, []
+    b3 = compute_b3sum(audio_path)
+    cat = store.get_db_dir() / "catalog" / f"{b3}.yaml"
+    if cat.exists():
+        entry = _load_yaml(cat)
+        context_name = context_name or entry.get("context", {}).get("name")
+        expected = entry.get("context", {}).get("expected_speakers", [])
+    if args.expected_speakers:
+        expected = args.expected_speakers.split(",")
+    mappings = assign_labels(audio_path, data, use_embeddings=args.use_embeddings, min_trust=args.min_trust, tags=args.tags,
+                             threshold=args.threshold, expected_speakers=expected, context_name=context_name,
+                             use_llm=args.use_llm, transcript_path=transcript_path, verbose=args.verbose, backend=backend)
+    output = {
+        "schema_version": SCHEMA_VERSION,
+        "recording_b3sum": b3,
+        "transcript_path": str(transcript_path),
+        "assigned_at": datetime.now(timezone.utc).strftime("%Y-%m-%dT%H:%M:%SZ"),
+        "method": f"speaker-assign-v{VERSION}",
+        "context": context_name,
+        "min_trust": args.min_trust,
+        "threshold": args.threshold,
+        "mappings": mappings,
+    }
+
+    def text_lines():
+        for label, d in mappings.items():
+            yield f"  {label} -> {d.get('speaker_id') or '(unassigned)'} ({d.get('confidence', '?')}, score: {d.get('score', 0):.2f})"
+
+    if args.dry_run:
+        print("\n=== DRY RUN - No changes saved ===")
+        if args.format == "json":
+            print(json.dumps(output, indent=2, ensure_ascii=False))
+        else:
+            print(f"\nAssignments for: {audio_path.name}")
+            print("-" * 50)
+            for label, d in mappings.items():
+                print(f"  {label} -> {d.get('speaker_id') or '(unassigned)'} ({d.get('confidence', '?')}, score: {d.get('score', 0):.2f})")
+                if d.get("candidates"):
+                    print(f"       candidates: {', '.join(c['speaker_id'] for c in d['candidates'])}")
+        return 0
+    adir = store.get_db_dir() / "assignments"
+    adir.mkdir(parents=True, exist_ok=True)
+    apath = adir / f"{b3}.yaml"
+    _save_yaml(apath, output)
+    if args.output:
+        _save_yaml(Path(args.output), output)
+    if args.format == "json":
+        print(json.dumps(output, indent=2, ensure_ascii=False))
+    elif not args.quiet:
+        print(f"\nAssignments saved: {apath.name}")
+        print("-" * 50)
+        print(f"Assigned: {sum(1 for a in mappings.values() if a.get('speaker_id'))}/{len(mappings)}")
+        for line in text_lines():
+            print(line)
+    return 0
+
+
+def build_parser() -> argparse.ArgumentParser:
+    parser = argparse.ArgumentParser(prog="speaker-assign", description="Multi-signal speaker name assignment (B200 embedding path)")
+    parser.add_argument("-V", "--version", action="version", version=f"speaker-assign {VERSION}")
+    parser.add_argument("-q", "--quiet", action="store_true")
+    parser.add_argument("-v", "--verbose", action="store_true")
+    sub = parser.add_subparsers(dest="command")
+    a = sub.add_parser("assign")
+    a.add_argument("audio")
+    a.add_argument("--transcript", "-t", required=True)
+    a.add_argument("--use-embeddings", "-e", action="store_true")
+    a.add_argument("--min-trust", default="low", choices=["high", "medium", "low"])
+    a.add_argument("--use-llm", "-l", action="store_true")
+    a.add_argument("--context", "-c")
+    a.add_argument("--expected-speakers")
+    a.add_argument("--tags")
+    a.add_argument("--threshold", type=float, default=0.3)
+    a.add_argument("--output", "-o")
+    a.add_argument("--format", "-f", choices=["text", "json"], default="text")
+    a.add_argument("--dry-run", "-n", action="store_true")
+    a.set_defaults(func=cmd_assign)
+    return parser
+
+
+def main(argv=None) -> int:
+    parser = build_parser()
+    args = parser.parse_args(argv)
+    if not args.command:
+        parser.print_help()
+        return 0
+    return args.func(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -108,3 +108,62 @@ def config5(seed: int = 505, N: int = 4096, L: int = 16, D: int = 256):
     rng = np.random.default_rng(seed)
     counts = zipf_counts(rng, N, L)
     return make_case(seed, counts, L, D, truth=list(range(L)), impostor_frac=0.0)
+
+
+# ---- on-disk fixtures: a $SPEAKERS_EMBEDDINGS_DIR store + recording + transcript + sidecar ----------
+def speechmatics_transcript(labels_per_segment, words_per_segment: int = 3):
+    """Speechmatics v2 shaped transcript whose per-label segmentation equals `labels_per_segment`
+    (words 0.35 s apart, a punctuation item, then a 0.5 s gap)."""
+    results, t = [], 0.0
+    for i, spk in enumerate(labels_per_segment):
+        for w in range(words_per_segment):
+            results.append({"type": "word", "start_time": round(t, 3), "end_time": round(t + 0.3, 3),
+                            "alternatives": [{"content": f"w{i}_{w}", "confidence": 1.0, "language": "en", "speaker": spk}]})
+            t += 0.35
+        results.append({"type": "punctuation", "start_time": round(t - 0.05, 3), "end_time": round(t - 0.05, 3),
+                        "attaches_to": "previous", "is_eos": True,
+                        "alternatives": [{"content": ".", "confidence": 1.0, "language": "en", "speaker": spk}]})
+        t += 0.5
+    return {"format": "2.9", "metadata": {"type": "transcription"}, "results": results}
+
+
+def write_store(case: Case, root, label_names, backend: str = "b200", speaker_names=None, audio_name: str = "rec.wav"):
+    """Writes the profile store, the bank vectors, a fake WAV, a transcript and the segment-embedding sidecar.
+    Returns (audio_path, transcript_path, speaker_ids)."""
+    import json
+    from pathlib import Path
+    from . import store as _store
+    root = Path(root)
+    (root / "db").mkdir(parents=True, exist_ok=True)
+    trust_names = ["high", "medium", "low", "invalidated", "unknown"]
+    speaker_ids = speaker_names or [f"spk{idx:04d}" for idx in range(case.n_speakers)]
+    for s, sid in enumerate(speaker_ids):
+        recs = []
+        for r in np.flatnonzero(case.row_speaker == s):
+            emb_id = f"emb-{r:08x}"
+            d = root / "embeddings" / sid
+            d.mkdir(parents=True, exist_ok=True)
+            np.save(d / f"{emb_id}.npy", case.bank[r])
+            recs.append({"id": emb_id, "external_id": None, "model_version": f"{backend}-cosine-v1",
+                         "trust_level": trust_names[int(case.row_trust[r])], "samples": {}, "created_at": "2026-01-01T00:00:00+00:00"})
+        prof = {"id": sid, "version": 1, "names": {"default": sid.title()}, "nicknames": [], "description": "", "metadata": {},
+                "tags": [], "embeddings": {backend: recs}, "created_at": "2026-01-01T00:00:00+00:00",
+                "updated_at": "2026-01-01T00:00:00+00:00"}
+        (root / "db" / f"{sid}.json").write_text(json.dumps(prof, indent=2))
+    audio = root / audio_name
+    audio.write_bytes(b"RIFF" + (36).to_bytes(4, "little") + b"WAVEfmt " + bytes(24) + audio_name.encode())
+    # interleave the labels' segments in time so that every segment is its own transcript run
+    per_label = [list(np.flatnonzero(case.seg_label == g)) for g in range(case.G)]
+    order, cursor = [], [0] * case.G
+    while any(cursor[g] < len(per_label[g]) for g in range(case.G)):
+        for g in range(case.G):
+            if cursor[g] < len(per_label[g]):
+                order.append(per_label[g][cursor[g]])
+                cursor[g] += 1
+    seg_labels = [label_names[int(case.seg_label[i])] for i in order]
+    tr = speechmatics_transcript(seg_labels)
+    tpath = root / (audio_name + ".speechmatics.json")
+    tpath.write_text(json.dumps(tr))
+    starts = np.arange(len(order)) * (3 * 0.35 + 0.5)
+    _store.save_segment_embeddings(audio, backend, case.seg[order], seg_labels, starts, starts + 0.95)
+    return audio, tpath, speaker_ids

@@ -8,6 +8,8 @@ Pins:
   * combine_signals_golden.json    -- speaker-assign:418-492 on the 7 survey KATs + 400 seeded random lists
   * embedding_signals_golden.json  -- speaker-assign:262-328 (min-trust filter, default score) with
                                       subprocess.run replaced by canned `speaker_detection identify` JSON
+  * assign_embedding_only_golden.json -- min-trust filter + combine_signals on embedding-only rows with
+                                      fp32 scores (what sdk_assign / orc_assign restate)
   * transcript_golden.json         -- label discovery / segmentation (speaker-assign:178-246,
                                       transcript.py:123-188) on the config-1 synthetic transcript
   * identify_decorate_golden.json  -- cmd_identify's decoration of backend rows (speaker_detection:1082-1123)
@@ -128,6 +130,32 @@ def main():
                                       "evidence": s.evidence} for s in sigs]})
     sa.subprocess.run = real_run
     (OUT / "embedding_signals_golden.json").write_text(json.dumps(cases, indent=0))
+
+    # ---- embedding-only pipeline: min-trust filter + combine_signals, fp32-representable scores ----
+    # This is exactly what the device-side `sdk_assign` (and oracle/canonical.c orc_assign) restate.
+    import numpy as _np
+    rng2 = random.Random(77)
+    eo = []
+    for _ in range(400):
+        n = rng2.randint(0, 10)
+        names = rng2.sample(["spk%02d" % i for i in range(40)], n)
+        sims = sorted((float(_np.float32(rng2.uniform(-0.2, 1.0))) for _ in range(n)), reverse=True)
+        if n >= 2 and rng2.random() < 0.3:
+            sims[1] = sims[0]                      # planted tie
+        rows = [{"speaker_id": nm, "score": sc, "trust_level": rng2.choice(["high", "medium", "low", "invalidated", "unknown"]),
+                 "embedding_id": "e", "backend": "b200"} for nm, sc in zip(names, sims)]
+        min_trust = rng2.choice(["low", "medium", "high"])
+        thr = rng2.choice([0.0, 0.1, 0.2, 0.3, 0.35, 0.5])
+        def fake_run(cmd, **kw):
+            return types.SimpleNamespace(returncode=0, stdout=json.dumps(rows), stderr="")
+        sa.subprocess.run = fake_run
+        sigs = sa.collect_embedding_signals("S1", [], Path("/tmp/x.wav"), min_trust=min_trust, tags=None)
+        a = sa.combine_signals("S1", sigs, threshold=thr)
+        eo.append({"rows": rows, "min_trust": min_trust, "threshold": thr,
+                   "expect": {"speaker_id": a.speaker_id, "confidence": a.confidence, "score": a.score,
+                              "candidates": a.candidates}})
+    sa.subprocess.run = real_run
+    (OUT / "assign_embedding_only_golden.json").write_text(json.dumps(eo, indent=0))
 
     # ---- transcript: labels + segments on the config-1 transcript ----
     tr = cfg1_transcript()

@@ -1,0 +1,108 @@
+"""Config 1 through the real command lines: synthetic store + Speechmatics-format transcript + sidecar ->
+`speaker_detection identify --format json` and `speaker-assign assign --use-embeddings`, checked against the
+C oracle (matching) and the restatement of the reference's combine_signals (assignment)."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import matching_np as mnp
+from speaker_diarization_toolkit_b200 import _native, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def cli(script, *args, env):
+    r = subprocess.run([sys.executable, str(ROOT / "bin" / script), *args], capture_output=True, text=True, env=env)
+    return r.returncode, r.stdout, r.stderr
+
+
+@pytest.fixture()
+def cfg1_store(tmp_path):
+    case = synth.config1()
+    audio, tpath, ids = synth.write_store(case, tmp_path, ["S1", "S2"], speaker_names=["alice", "bob", "carol"])
+    env = dict(os.environ, SPEAKERS_EMBEDDINGS_DIR=str(tmp_path), SPEAKER_DETECTION_BACKEND="b200", PYTHONPATH=str(ROOT))
+    env.pop("SPEAKER_BACKENDS_CONFIG", None)
+    return case, audio, tpath, ids, env
+
+
+def expected_rows(oracle, case, ids, thr=0.354, k=10):
+    rows, scores, counts = oracle.identify(case.seg, case.goff, case.bank, case.row_speaker, case.n_speakers, mode=0, pool=0,
+                                           threshold=thr, k=k)
+    return rows, scores, counts
+
+
+def test_identify_cli_config1(cfg1_store, oracle):
+    case, audio, tpath, ids, env = cfg1_store
+    rc, out, err = cli("speaker_detection", "identify", str(audio), "--format", "json", env=env)
+    assert rc == 0, err
+    got = json.loads(out)                                   # stdout is pure JSON, status went to stderr
+    assert "Identifying speaker in rec.wav against 3 candidates..." in err
+    rows, scores, counts = expected_rows(oracle, case, ids)
+    exp = []
+    trust = ["high", "medium", "low"]
+    for g, label in enumerate(["S1", "S2"]):
+        for i in range(counts[g]):
+            r = int(rows[g, i])
+            sid = ids[case.row_speaker[r]]
+            exp.append({"speaker_id": sid, "name": sid.title(), "score": float(scores[g, i]), "confidence": float(scores[g, i]),
+                        "trust_level": trust[case.row_trust[r]], "embedding_id": f"emb-{r:08x}", "backend": "b200",
+                        "label": label, "rank": i})
+    assert got == exp
+    assert [r["speaker_id"] for r in got] == ["alice", "bob"]
+
+
+def test_assign_cli_config1(cfg1_store, oracle):
+    case, audio, tpath, ids, env = cfg1_store
+    rc, out, err = cli("speaker-assign", "-q", "assign", str(audio), "-t", str(tpath), "--use-embeddings", "--format", "json",
+                       "--threshold", "0.2", env=env)
+    assert rc == 0, err
+    got = json.loads(out)
+    rows, scores, counts = expected_rows(oracle, case, ids)
+    trust = ["high", "medium", "low"]
+    for g, label in enumerate(["S1", "S2"]):
+        sigs = [mnp.Signal("embedding_match", ids[case.row_speaker[int(rows[g, i])]], float(scores[g, i]),
+                           {"embedding_id": f"emb-{int(rows[g, i]):08x}", "trust_level": trust[case.row_trust[int(rows[g, i])]],
+                            "backend": "b200"}) for i in range(counts[g])]
+        ref = mnp.combine_signals(label, sigs, threshold=0.2)
+        m = got["mappings"][label]
+        assert m["speaker_id"] == ref["speaker_id"]
+        assert m["confidence"] == ref["confidence"]
+        assert m["score"] == round(ref["score"], 3)
+        assert m["signals"] == ref["signals"]
+        assert m.get("candidates", []) == ref["candidates"]
+    # alice is enrolled at high trust (0.4*1.0*0.89 = 0.36 -> assigned); bob at medium trust (0.4*0.7*0.89 = 0.25 -> assigned at 0.2)
+    assert got["mappings"]["S1"]["speaker_id"] == "alice" and got["mappings"]["S2"]["speaker_id"] == "bob"
+    saved = list((Path(env["SPEAKERS_EMBEDDINGS_DIR"]) / "assignments").glob("*.yaml"))
+    assert len(saved) == 1 and saved[0].stem == got["recording_b3sum"]
+
+
+def test_assign_cli_default_threshold_needs_high_trust(cfg1_store):
+    """With speaker-assign's default 0.3 an embedding-only match is impossible at medium trust."""
+    case, audio, tpath, ids, env = cfg1_store
+    rc, out, err = cli("speaker-assign", "-q", "assign", str(audio), "-t", str(tpath), "-e", "-n", "--format", "json", env=env)
+    assert rc == 0, err
+    got = json.loads(out[out.index("{"):])
+    assert got["mappings"]["S1"]["speaker_id"] == "alice"
+    assert got["mappings"]["S2"]["speaker_id"] is None and got["mappings"]["S2"]["candidates"][0]["speaker_id"] == "bob"
+
+
+def test_verify_cli(cfg1_store):
+    case, audio, tpath, ids, env = cfg1_store
+    rc, out, err = cli("speaker_detection", "verify", "carol", str(audio), env=env)
+    assert rc == 1 and "NO MATCH" in out                    # carol speaks in neither label
+    # a recording of alice only
+    solo = synth.make_case(9, [12], 3, 192, truth=[0])
+    solo.bank[:] = case.bank
+    from speaker_diarization_toolkit_b200 import store
+    os.environ["SPEAKERS_EMBEDDINGS_DIR"] = env["SPEAKERS_EMBEDDINGS_DIR"]
+    a2 = Path(env["SPEAKERS_EMBEDDINGS_DIR"]) / "solo.wav"
+    a2.write_bytes(b"RIFFsolo")
+    store.save_segment_embeddings(a2, "b200", solo.seg, ["S1"] * 12)
+    rc, out, err = cli("speaker_detection", "verify", "alice", str(a2), env=env)
+    assert rc == 0 and "MATCH: Speaker 'alice' verified (confidence: 0." in out

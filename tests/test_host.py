@@ -1,0 +1,199 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU, no compute calls)."""
+import argparse
+import ctypes
+import io
+import json
+import re
+from contextlib import redirect_stderr, redirect_stdout
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from speaker_diarization_toolkit_b200 import _native, identify_cli, plugin_api, signals, store, transcript
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = Path(__file__).parent / "golden"
+
+
+def load(name):
+    return json.loads((GOLD / name).read_text())
+
+
+# ---- C-ABI: library loads and exports every symbol the header declares ----
+def test_abi_exports_every_declared_symbol():
+    header = (ROOT / "include" / "sdk_b200.h").read_text()
+    declared = set(re.findall(r"\b(sdk_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    lib = _native.load()
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} not exported"
+    assert lib.sdk_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a B200 the product path must fail loudly (no oracle, no NumPy behind the API)."""
+    if _native.device_count() > 0:
+        pytest.skip("a B200 is present")
+    with pytest.raises(_native.NativeError) as ei:
+        _native.Context(0)
+    assert ei.value.code == -19 and "no CPU fallback" in str(ei.value)
+    import speaker_diarization_toolkit_b200 as pkg
+    for py in Path(pkg.__file__).parent.glob("*.py"):
+        src = py.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f"{py.name} must not touch oracle/"
+
+
+# ---- signal fusion mirror == reference golden ----
+def test_combine_signals_mirror_matches_reference():
+    for case in load("combine_signals_golden.json"):
+        sigs = [signals.Signal(t, i, s, dict(ev)) for t, i, s, ev in case["signals"]]
+        a = signals.combine_signals("S1", sigs, threshold=case["threshold"])
+        e = case["expect"]
+        assert (a.speaker_id, a.confidence, a.score, a.candidates, a.signals) == \
+               (e["speaker_id"], e["confidence"], e["score"], e["candidates"], e["signals"])
+
+
+def test_signals_from_matches_matches_reference():
+    for case in load("embedding_signals_golden.json"):
+        got = signals.signals_from_matches(case["canned"], min_trust=case["min_trust"])
+        assert [{"type": s.type, "speaker_id": s.speaker_id, "score": s.score, "evidence": s.evidence} for s in got] == case["expect"]
+
+
+def test_signals_per_label_filter():
+    rows = [{"speaker_id": "a", "score": 0.9, "trust_level": "high", "label": "S1"},
+            {"speaker_id": "b", "score": 0.8, "trust_level": "high", "label": "S2"},
+            {"speaker_id": "c", "score": 0.7, "trust_level": "high"}]
+    assert [s.speaker_id for s in signals.signals_from_matches(rows, label="S1")] == ["a", "c"]
+    assert [s.speaker_id for s in signals.signals_from_matches(rows, label="S2")] == ["b", "c"]
+    assert [s.speaker_id for s in signals.signals_from_matches(rows)] == ["a", "b", "c"]
+
+
+# ---- transcript mirror == reference golden ----
+def test_transcript_mirror_matches_reference():
+    g = load("transcript_golden.json")
+    tr = g["transcript"]
+    assert transcript.get_speakers_from_transcript(tr) == g["labels_assign"] == ["S1", "S2"]
+    for lab in ["S1", "S2"]:
+        assert transcript.get_speaker_segments(tr, lab) == g["segments_assign"][lab]
+        assert [list(t) for t in transcript.extract_segments_as_tuples(tr, lab)] == g["tuples_backend"][lab]
+        assert len(g["tuples_backend"][lab]) == 20
+    a = g["assemblyai"]
+    assert transcript.get_speakers_from_transcript(a["transcript"]) == a["labels_assign"]
+    for lab in ["A", "B"]:
+        assert transcript.get_speaker_segments(a["transcript"], lab) == a["segments_assign"][lab]
+        assert [list(t) for t in transcript.extract_segments_as_tuples(a["transcript"], lab)] == a["tuples_backend"][lab]
+
+
+# ---- profile store mirror ----
+def test_trust_and_tag_filter_match_reference():
+    g = load("trust_golden.json")
+    for c in g["trust"]:
+        assert store.compute_trust_level(c["samples"]) == c["expect"]
+    for c in g["filter"]:
+        assert [s["id"] for s in store.filter_speakers_by_tags(g["speakers"], c["tags"], c["any_tag"])] == c["expect"]
+
+
+def _write_profiles(root: Path, profiles: dict):
+    (root / "db").mkdir(parents=True, exist_ok=True)
+    for pid, p in profiles.items():
+        (root / "db" / f"{pid}.json").write_text(json.dumps(p))
+
+
+def test_cmd_identify_decoration_matches_reference(tmp_path, monkeypatch):
+    """Same stdout JSON, stderr status line and rc as the reference's cmd_identify for a stub backend."""
+    for case in load("identify_decorate_golden.json"):
+        root = tmp_path / f"store{len(case['backend_rows'])}"
+        _write_profiles(root, case["profiles"])
+        monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(root))
+        audio = root / "a.wav"
+        audio.write_bytes(b"RIFF0000WAVE")
+        rows = [dict(r) for r in case["backend_rows"]]
+        for r in rows:
+            r.pop("label", None)          # the reference CLI drops unknown keys; compare like for like
+
+        class Stub:
+            def identify_speaker(self, audio_path, candidates, threshold):
+                self.seen = [c["id"] for c in candidates]
+                return rows
+        stub = Stub()
+        args = argparse.Namespace(audio=str(audio), backend="stub", tags=None, threshold=0.354, format="json")
+        so, se = io.StringIO(), io.StringIO()
+        with redirect_stdout(so), redirect_stderr(se):
+            rc = identify_cli.cmd_identify(args, backend=stub)
+        assert rc == case["rc"]
+        assert stub.seen == case["candidates_seen"]
+        assert json.loads(so.getvalue()) == case["stdout_json"]
+        assert se.getvalue() == case["stderr"]
+
+
+def test_cmd_identify_error_paths(tmp_path, monkeypatch, capsys):
+    """Error strings / return codes of speaker_detection:1033-1074 (reference test_cli.py:594-678)."""
+    monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(tmp_path))
+    ns = lambda **kw: argparse.Namespace(**{"backend": "b200", "tags": None, "threshold": 0.354, "format": "json", **kw})
+    assert identify_cli.cmd_identify(ns(audio=str(tmp_path / "missing.wav"))) == 1
+    assert "Error: Audio file not found" in capsys.readouterr().err
+    audio = tmp_path / "a.wav"
+    audio.write_bytes(b"x")
+    assert identify_cli.cmd_identify(ns(audio=str(audio))) == 1
+    assert "No speakers to match against." in capsys.readouterr().err
+    _write_profiles(tmp_path, {"al": {"id": "al", "names": {"default": "Al"}, "embeddings": {}}})
+    assert identify_cli.cmd_identify(ns(audio=str(audio))) == 1
+    assert "No speakers with b200 embeddings." in capsys.readouterr().err
+    _write_profiles(tmp_path, {"al": {"id": "al", "names": {"default": "Al"}, "embeddings": {"nope": [{"id": "e"}]}}})
+    assert identify_cli.cmd_identify(ns(audio=str(audio), backend="nope")) == 1
+    assert "Error loading backend: Unknown backend: nope" in capsys.readouterr().err
+
+
+def test_bank_build_and_sidecar(tmp_path, monkeypatch):
+    monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(tmp_path))
+    rng = np.random.default_rng(1)
+    vecs = {("amy", "emb-1"): rng.standard_normal(8).astype(np.float32), ("amy", "emb-2"): rng.standard_normal(8).astype(np.float32),
+            ("bob", "emb-3"): rng.standard_normal(8).astype(np.float32)}
+    for (sid, eid), v in vecs.items():
+        d = tmp_path / "embeddings" / sid
+        d.mkdir(parents=True, exist_ok=True)
+        np.save(d / f"{eid}.npy", v)
+    handle = store.store_vector_cas(np.ones(8, np.float32))
+    cands = [
+        {"id": "amy", "embeddings": {"b200": [{"id": "emb-1", "trust_level": "high"}, {"id": "emb-2", "trust_level": "low"}]}},
+        {"id": "ghost", "embeddings": {"b200": [{"id": "emb-missing"}]}},
+        {"id": "bob", "embeddings": {"b200": [{"id": "emb-3"}, {"id": "emb-x", "external_id": handle, "trust_level": "medium"}]}},
+    ]
+    snapshot = json.dumps(cands)
+    bank = store.build_bank(cands, "b200")
+    assert json.dumps(cands) == snapshot, "candidates must not be mutated"
+    assert bank.speaker_ids == ["amy", "bob"] and bank.row_speaker.tolist() == [0, 0, 1, 1]
+    assert bank.row_trust.tolist() == [0, 2, 4, 1] and bank.row_emb_id == ["emb-1", "emb-2", "emb-3", "emb-x"]
+    assert np.array_equal(bank.rows[3], np.ones(8, np.float32))
+    with pytest.raises(ValueError, match="dimension"):
+        store.build_bank(cands, "b200", dim=16)
+    audio = tmp_path / "rec.wav"
+    store.save_segment_embeddings(audio, "b200", rng.standard_normal((5, 8)), ["S2", "S1", "S2", "S1", "S10"], [0, 1, 2, 3, 4], [1, 2, 3, 4, 5])
+    se = store.load_segment_embeddings(audio, "b200")
+    assert se.labels == ["S1", "S10", "S2"] and se.label_index.tolist() == [0, 0, 1, 2, 2] and se.start.tolist() == [1, 3, 4, 0, 2]
+
+
+# ---- plugin API mirror ----
+def test_plugin_registry_and_abc(tmp_path, monkeypatch):
+    plugin_api.reload_backends_config()
+    monkeypatch.delenv("SPEAKER_BACKENDS_CONFIG", raising=False)
+    assert "b200" in plugin_api.list_backends()
+    b = plugin_api.get_backend("b200")
+    assert b.name == "b200" and b.requires_api_key is False and b.model_version.startswith("b200-")
+    assert b.check_embedding_compatibility({"model_version": "b200-cosine-v1"})["compatible"]
+    bad = b.check_embedding_compatibility({"model_version": "speechmatics-v2"})
+    assert not bad["compatible"] and "Consider re-enrolling" in bad["warning"]
+    assert b.get_audio_profile() == plugin_api.AudioProfile()
+    with pytest.raises(ValueError, match="Unknown backend: zzz. Available:"):
+        plugin_api.get_backend("zzz")
+    cfg = tmp_path / "b.yaml"
+    cfg.write_text("backends:\n  mine: speaker_diarization_toolkit_b200.backend\n  other:\n    module: json\n")
+    monkeypatch.setenv("SPEAKER_BACKENDS_CONFIG", str(cfg))
+    plugin_api.reload_backends_config()
+    assert plugin_api.list_backends() == ["mine", "other"]
+    assert plugin_api.get_backend("mine").name == "b200"
+    plugin_api.reload_backends_config()
+    assert plugin_api.format_ffmpeg_args(plugin_api.AudioProfile(sample_rate=8000, channels=2, bit_depth=24)) == \
+           ["-ar", "8000", "-ac", "2", "-f", "wav", "-acodec", "pcm_s24le"]
+    assert plugin_api.format_ffmpeg_args(plugin_api.AudioProfile(format="flac")) == ["-ar", "16000", "-ac", "1", "-f", "flac"]
