@@ -24,7 +24,8 @@
  * this arithmetic before it orders them:
  *   (1) squared norm: fp64, 32 interleaved partial sums (element e goes to partial (e/4)%32,
  *       ascending e), combined by a butterfly (xor 16,8,4,2,1); norm = (float)sqrt(.);
- *       x_hat[e] = x[e] / max(norm, 1e-12f) in IEEE fp32.            [SURVEY 8(c) step 1]
+ *       x_hat[e] = x[e] * (1.0f / max(norm, 1e-12f)), both IEEE fp32 (one reciprocal per row, one
+ *       rounding per element; within 1 ulp of NumPy's x / norm).      [SURVEY 8(c) step 1]
  *   (2) operand rounding: mode 0 keeps x_hat in fp32; mode 1 rounds it to bf16 (RNE).
  *                                                                     [SURVEY 8(c) step 2]
  *   (3) pair score: fp64 fma chain over ascending d (products of fp32/bf16 operands are exact
@@ -81,8 +82,9 @@ void orc_normalize(const float* x, int64_t n, int32_t D, int32_t mode,
         float nrm = (float)sqrt(part[0]);
         if (norms) norms[r] = nrm;
         float den = nrm > 1e-12f ? nrm : 1e-12f;
+        float inv = 1.0f / den;
         for (int32_t e = 0; e < D; ++e) {
-            float v = xr[e] / den;
+            float v = xr[e] * inv;
             out[r * (int64_t)D + e] = mode == 1 ? orc_bf16_round(v) : v;
         }
     }

@@ -160,7 +160,8 @@ int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, 
     k_fill_ll<<<fb, 256, 0, c->stream>>>(d_qpool, total, pool == 0 ? 0ll : LLONG_MIN);
     c->launches++;
     // row-slot tile width: wide tiles for dense scans, narrow for the few re-scored candidates
-    int RT = nslot >= 16 ? 16 : (nslot > 4 ? 8 : 4);
+    // the candidate list is front-packed, so on the sparse path tiles of 4 slots let the empty tail exit at once
+    int RT = d_cand_row ? 4 : (nslot >= 16 ? 16 : (nslot > 4 ? 8 : 4));
     int64_t ntiles64 = (nslot + RT - 1) / RT;
     int64_t blocks = ntiles64 * ngroups;
     if (blocks > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "exact path: too many (group,row-tile) blocks");

@@ -39,14 +39,15 @@ __global__ void __launch_bounds__(256) k_normalize_vec(const float* __restrict__
         for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
         float nrm = (float)sqrt(s);
         float den = nrm > 1e-12f ? nrm : 1e-12f;
+        const float inv = __fdiv_rn(1.0f, den);
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
             int q = lane + 32 * i;
             float4 o;
-            o.x = __fdiv_rn(v[i].x, den);
-            o.y = __fdiv_rn(v[i].y, den);
-            o.z = __fdiv_rn(v[i].z, den);
-            o.w = __fdiv_rn(v[i].w, den);
+            o.x = __fmul_rn(v[i].x, inv);
+            o.y = __fmul_rn(v[i].y, inv);
+            o.z = __fmul_rn(v[i].z, inv);
+            o.w = __fmul_rn(v[i].w, inv);
             if (f32out && q < nq) reinterpret_cast<float4*>(f32out + row * (int64_t)D)[q] = o;
             if (bf16out && q < nqp) {
                 __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);   // zero beyond D (v was zero)
@@ -83,8 +84,9 @@ __global__ void __launch_bounds__(256) k_normalize_generic(const float* __restri
         for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
         float nrm = (float)sqrt(s);
         float den = nrm > 1e-12f ? nrm : 1e-12f;
+        const float inv = __fdiv_rn(1.0f, den);
         for (int e = lane; e < Dp; e += 32) {
-            float o = e < D ? __fdiv_rn(xr[e], den) : 0.f;
+            float o = e < D ? __fmul_rn(xr[e], inv) : 0.f;
             if (f32out && e < D) f32out[row * (int64_t)D + e] = o;
             if (bf16out) bf16out[row * (int64_t)Dp + e] = __float2bfloat16_rn(o);
         }

@@ -28,7 +28,7 @@
 #include "common.cuh"
 
 #define PG_THREADS 192
-#define PG_CS 16            // candidate slots per (label group, row block, warp)
+#define PG_CS 16            // candidate slots per (label group, row block, row tile, warp) = per 32 bank rows
 #define PG_SMEM_LIMIT 232448
 
 struct PgParams {
@@ -110,91 +110,80 @@ __device__ __forceinline__ uint64_t pg_make_desc(uint32_t smem_addr) {
            ((uint64_t)2 << 61);
 }
 
-// ---- the flush of one label group for this warp's 32*MT rows -----------------------------------
-template <int MT>
-__device__ __forceinline__ void pg_flush(const PgParams& p, float (&acc)[MT], int32_t g, int64_t n_g, int32_t rb, int32_t wq,
-                                         int32_t lane, int64_t row0) {
-    float val[MT];
-    bool pass[MT];
-    const float inv = p.pool == 0 ? 1.0f / (float)n_g : 1.0f;
+// ---- the flush of one label group for this warp's 32 rows of row tile rt --------------------------
+// sub-slot = (label group, row block, row tile, warp): at most PG_CS rows with approx >= tau are kept; if
+// more pass, the PG_CS largest (ballot-based binary search on the orderable key) and the bound below
+// which rows were dropped.
+__device__ __forceinline__ void pg_flush(const PgParams& p, float accv, int32_t g, int64_t n_g, int64_t sub, int32_t lane,
+                                         int64_t row) {
+    const float val = p.pool == 0 ? accv * (1.0f / (float)n_g) : accv;
     if (p.mode == 1) {
-#pragma unroll
-        for (int rt = 0; rt < MT; ++rt) {
-            int64_t row = row0 + rt * 128;
-            if (row < p.P) p.dense_out[row * (int64_t)p.dense_ld + g] = acc[rt] * inv;
+        if (row < p.P) p.dense_out[row * (int64_t)p.dense_ld + g] = val;
+        return;
+    }
+    const bool pass = (val >= p.tau) && (row < p.P);
+    const uint32_t mpass = __ballot_sync(0xffffffffu, pass);
+    const int npass = __popc(mpass);
+    if (lane == 0) p.slot_cnt[sub] = npass;
+    if (npass == 0) return;
+    const uint32_t lt = (1u << lane) - 1u;
+    if (npass <= PG_CS) {
+        if (pass) {
+            const int pos = __popc(mpass & lt);
+            p.slot_row[sub * PG_CS + pos] = (int32_t)row;
+            p.slot_val[sub * PG_CS + pos] = val;
         }
         return;
     }
-    int npass = 0;
-#pragma unroll
-    for (int rt = 0; rt < MT; ++rt) {
-        val[rt] = acc[rt] * inv;
-        pass[rt] = (val[rt] >= p.tau) && (row0 + rt * 128 < p.P);
-        npass += __popc(__ballot_sync(0xffffffffu, pass[rt]));
+    const uint32_t key = pass ? sdk_fkey(val) : 0u;
+    uint32_t T = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        if (__popc(__ballot_sync(0xffffffffu, key >= cand)) >= PG_CS) T = cand;
     }
-    const int64_t sub = ((int64_t)(g - p.g_base) * p.RB + rb) * 4 + wq;
-    if (lane == 0) p.slot_cnt[sub] = npass;
-    if (npass == 0) return;
-    uint32_t T = 0;   // keys >= T are kept when npass > CS
-    int need_ties = 0;
-    if (npass > PG_CS) {
-        uint32_t key[MT];
-#pragma unroll
-        for (int rt = 0; rt < MT; ++rt) key[rt] = pass[rt] ? sdk_fkey(val[rt]) : 0u;
-        for (int bit = 31; bit >= 0; --bit) {
-            uint32_t cand = T | (1u << bit);
-            int cnt = 0;
-#pragma unroll
-            for (int rt = 0; rt < MT; ++rt) cnt += __popc(__ballot_sync(0xffffffffu, key[rt] >= cand));
-            if (cnt >= PG_CS) T = cand;
-        }
-        int above = 0;
-#pragma unroll
-        for (int rt = 0; rt < MT; ++rt) above += __popc(__ballot_sync(0xffffffffu, key[rt] > T));
-        need_ties = PG_CS - above;
-        if (lane == 0) p.slot_bound[sub] = sdk_funkey(T);
-        int base = 0, ties = 0;
-#pragma unroll
-        for (int rt = 0; rt < MT; ++rt) {
-            bool gt = key[rt] > T, eq = key[rt] == T && pass[rt];
-            uint32_t mg = __ballot_sync(0xffffffffu, gt), me = __ballot_sync(0xffffffffu, eq);
-            int my_tie = ties + __popc(me & ((1u << lane) - 1));
-            bool take_eq = eq && my_tie < need_ties;
-            uint32_t mt = __ballot_sync(0xffffffffu, take_eq);
-            uint32_t mall = mg | mt;
-            if (gt || take_eq) {
-                int pos = base + __popc(mall & ((1u << lane) - 1));
-                p.slot_row[sub * PG_CS + pos] = (int32_t)(row0 + rt * 128);
-                p.slot_val[sub * PG_CS + pos] = val[rt];
-            }
-            base += __popc(mall);
-            ties += __popc(me);
-        }
-    } else {
-        int base = 0;
-#pragma unroll
-        for (int rt = 0; rt < MT; ++rt) {
-            uint32_t m = __ballot_sync(0xffffffffu, pass[rt]);
-            if (pass[rt]) {
-                int pos = base + __popc(m & ((1u << lane) - 1));
-                p.slot_row[sub * PG_CS + pos] = (int32_t)(row0 + rt * 128);
-                p.slot_val[sub * PG_CS + pos] = val[rt];
-            }
-            base += __popc(m);
-        }
+    const uint32_t mg = __ballot_sync(0xffffffffu, key > T);
+    const uint32_t me = __ballot_sync(0xffffffffu, key == T && pass);
+    const int need_ties = PG_CS - __popc(mg);
+    const bool take_eq = (key == T && pass) && __popc(me & lt) < need_ties;
+    const uint32_t mall = mg | __ballot_sync(0xffffffffu, take_eq);
+    if (lane == 0) p.slot_bound[sub] = sdk_funkey(T);
+    if (key > T || take_eq) {
+        const int pos = __popc(mall & lt);
+        p.slot_row[sub * PG_CS + pos] = (int32_t)row;
+        p.slot_val[sub * PG_CS + pos] = val;
     }
 }
 
+__device__ __forceinline__ void pg_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- the kernel --------------------------------------------------------------------------------
+// A "job" is (column chunk j, row tile rt): KCH*4 MMAs of 128 x NC x 16 into accumulator slot (job % NSLOT).
+// Jobs run chunk-major, row-tile-minor, so with MT > 1 the whole B chunk (KCH stages) stays resident until its
+// last row tile has consumed it (STAGES >= KCH + 1), and the epilogue of job i overlaps the MMAs of job i+1.
+// N = NC = 256 keeps the per-MMA shared-memory operand fetch (4 KB of A + NC*32 B of B) under the MMA time.
 template <int KCH, int MT, int NC, int STAGES>
 __global__ void __launch_bounds__(PG_THREADS, 1)
 k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const PgParams p) {
     constexpr uint32_t A_TILE = 128 * 128;               // 128 rows x 64 bf16
     constexpr uint32_t A_BYTES = MT * KCH * A_TILE;
     constexpr uint32_t B_STAGE = NC * 128;
+    constexpr uint32_t NSLOT = 512 / NC;                 // accumulator slots in TMEM
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    static_assert(2 * MT * NC <= 512, "TMEM: two accumulator stages must fit 512 columns");
-    static_assert(NC % 16 == 0 && NC >= 16 && NC <= 256, "UMMA N");
+    static_assert(NC == 128 || NC == 256, "accumulator slot width");
+    static_assert(MT == 1 || STAGES >= KCH + 1, "B chunk must stay resident across the row tiles");
 
     extern __shared__ uint8_t pg_smem_raw[];
     const uint32_t raw = pg_smem_u32(pg_smem_raw);
@@ -202,11 +191,10 @@ k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
     const uint32_t sA = base;
     const uint32_t sB = sA + A_BYTES;
     const uint32_t sBar = sB + STAGES * B_STAGE;
-    // barrier layout (8 bytes each)
     const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8;
     const uint32_t bar_b_full = sBar + 16, bar_b_empty = bar_b_full + 8 * STAGES;
-    const uint32_t bar_t_full = bar_b_empty + 8 * STAGES, bar_t_empty = bar_t_full + 16;
-    const uint32_t s_tmem = bar_t_empty + 16;
+    const uint32_t bar_t_full = bar_b_empty + 8 * STAGES, bar_t_empty = bar_t_full + 8 * NSLOT;
+    const uint32_t s_tmem = bar_t_empty + 8 * NSLOT;
     uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(pg_smem_raw + (s_tmem - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,7 +203,7 @@ k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
         pg_mbar_init(bar_a_full, 1);
         pg_mbar_init(bar_a_empty, 1);
         for (int s = 0; s < STAGES; ++s) { pg_mbar_init(bar_b_full + 8 * s, 1); pg_mbar_init(bar_b_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { pg_mbar_init(bar_t_full + 8 * b, 1); pg_mbar_init(bar_t_empty + 8 * b, 4); }
+        for (uint32_t b = 0; b < NSLOT; ++b) { pg_mbar_init(bar_t_full + 8 * b, 1); pg_mbar_init(bar_t_empty + 8 * b, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -263,7 +251,7 @@ k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, a_phase = 0;
-            uint32_t jglobal = 0;
+            uint32_t job = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const int32_t range = (int32_t)(u / p.RB);
                 const int64_t c0 = p.goff[p.range_g[range]], c1 = p.goff[p.range_g[range + 1]];
@@ -272,112 +260,120 @@ k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
                 a_phase ^= 1;
                 pg_fence_after();
                 const int64_t nchunks = (c1 - c0 + NC - 1) / NC;
-                for (int64_t j = 0; j < nchunks; ++j, ++jglobal) {
-                    const uint32_t b = jglobal & 1u, it = jglobal >> 1;
-                    pg_mbar_wait(bar_t_empty + 8 * b, (it & 1u) ^ 1u);
-                    pg_fence_after();
-#pragma unroll 1
-                    for (int kc = 0; kc < KCH; ++kc) {
-                        pg_mbar_wait(bar_b_full + 8 * stage, phase);
-                        pg_fence_after();
-                        const uint64_t db = pg_make_desc(sB + stage * B_STAGE);
+                for (int64_t j = 0; j < nchunks; ++j) {
+                    const uint32_t stage0 = stage, phase0 = phase;       // ring position of this chunk's first K stage
 #pragma unroll
-                        for (int rt = 0; rt < MT; ++rt) {
+                    for (int rt = 0; rt < MT; ++rt, ++job) {
+                        const uint32_t slot = job % NSLOT, it = job / NSLOT;
+                        pg_mbar_wait(bar_t_empty + 8 * slot, (it & 1u) ^ 1u);
+                        pg_fence_after();
+                        const uint32_t td = tmem_base + slot * NC;
+                        uint32_t st = stage0, ph = phase0;
+#pragma unroll 1
+                        for (int kc = 0; kc < KCH; ++kc) {
+                            if (rt == 0) {
+                                pg_mbar_wait(bar_b_full + 8 * st, ph);
+                                pg_fence_after();
+                            }
+                            const uint64_t db = pg_make_desc(sB + st * B_STAGE);
                             const uint64_t da = pg_make_desc(sA + (rt * KCH + kc) * A_TILE);
-                            const uint32_t td = tmem_base + (b * MT + rt) * NC;
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
                                 pg_mma_bf16(td, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC, (kc | kk) != 0 ? 1u : 0u);
+                            if (rt == MT - 1) pg_commit(bar_b_empty + 8 * st);   // last row tile: this K stage is free
+                            if (++st == STAGES) { st = 0; ph ^= 1; }
                         }
-                        pg_commit(bar_b_empty + 8 * stage);     // frees this B stage when the MMAs have read it
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        pg_commit(bar_t_full + 8 * slot);                         // accumulator of this job complete
+                        if (rt == MT - 1) { stage = st; phase = ph; }
                     }
-                    pg_commit(bar_t_full + 8 * b);               // accumulators of chunk j complete
                 }
-                pg_commit(bar_a_empty);                          // bank tiles may be overwritten
+                pg_commit(bar_a_empty);                                           // bank tiles may be overwritten
             }
         }
     } else {
         // ================= epilogue: 4 warps, thread <-> bank row (TMEM lane) =================
         const int wq = warp & 3;                                 // TMEM lane quadrant of this warp
         const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
-        uint32_t jglobal = 0;
+        uint32_t job = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int32_t range = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)range * p.RB);
             const int32_t g_lo = p.range_g[range], g_hi = p.range_g[range + 1];
             const int64_t c0 = p.goff[g_lo], c1 = p.goff[g_hi];
             if (c1 <= c0) continue;
-            const int64_t row0 = (int64_t)rb * MT * 128 + wq * 32 + lane;
-            int32_t g = g_lo;
-            int64_t gbeg = c0, gend = p.goff[g + 1];
-            while (gend == gbeg && g + 1 < g_hi) { ++g; gend = p.goff[g + 1]; }   // skip empty groups
+            // running pooling state, one per row tile (all row tiles walk the same columns)
+            int32_t g[MT];
+            int64_t gbeg[MT], gend[MT];
             float acc[MT];
+            {
+                int32_t g0 = g_lo;
+                int64_t e0 = p.goff[g0 + 1];
+                while (e0 == c0 && g0 + 1 < g_hi) { ++g0; e0 = p.goff[g0 + 1]; }   // skip empty groups
 #pragma unroll
-            for (int rt = 0; rt < MT; ++rt) acc[rt] = p.pool == 0 ? 0.f : -3.0e38f;
+                for (int rt = 0; rt < MT; ++rt) { g[rt] = g0; gbeg[rt] = c0; gend[rt] = e0; acc[rt] = p.pool == 0 ? 0.f : -3.0e38f; }
+            }
             const int64_t nchunks = (c1 - c0 + NC - 1) / NC;
-            for (int64_t j = 0; j < nchunks; ++j, ++jglobal) {
-                const uint32_t b = jglobal & 1u, it = jglobal >> 1;
-                pg_mbar_wait(bar_t_full + 8 * b, it & 1u);
-                pg_fence_after();
+            for (int64_t j = 0; j < nchunks; ++j) {
+#pragma unroll
+                for (int rt = 0; rt < MT; ++rt, ++job) {
+                    const uint32_t slot = job % NSLOT, it = job / NSLOT;
+                    const int64_t row = ((int64_t)rb * MT + rt) * 128 + wq * 32 + lane;
+                    const int64_t subbase = (((int64_t)rb * MT + rt) * 4 + wq);
+                    pg_mbar_wait(bar_t_full + 8 * slot, it & 1u);
+                    pg_fence_after();
 #pragma unroll 1
-                for (int blk = 0; blk < NC / 16; ++blk) {
-                    const int64_t cbase = c0 + j * NC + blk * 16;
-                    if (cbase >= c1) break;
-                    float v[MT][16];
-#pragma unroll
-                    for (int rt = 0; rt < MT; ++rt) pg_tmem_ld16(tmem_base + lane_base + (b * MT + rt) * NC + blk * 16, v[rt]);
-                    pg_tmem_ld_wait();
-                    const int nvalid = (int)min((int64_t)16, c1 - cbase);
-                    if (nvalid == 16 && gend > cbase + 16) {
-                        // whole block inside the current label group
-#pragma unroll
-                        for (int rt = 0; rt < MT; ++rt) {
+                    for (int blk = 0; blk < NC / 32; ++blk) {
+                        const int64_t cbase = c0 + j * NC + blk * 32;
+                        if (cbase >= c1) break;
+                        float v[32];
+                        pg_tmem_ld32(tmem_base + lane_base + slot * NC + blk * 32, v);
+                        pg_tmem_ld_wait();
+                        const int64_t left = c1 - cbase;
+                        const int nvalid = left < 32 ? (int)left : 32;
+                        if (nvalid == 32 && gend[rt] > cbase + 32) {
+                            // whole block inside the current label group
                             if (p.pool == 0) {
-                                float s0 = (v[rt][0] + v[rt][1]) + (v[rt][2] + v[rt][3]);
-                                float s1 = (v[rt][4] + v[rt][5]) + (v[rt][6] + v[rt][7]);
-                                float s2 = (v[rt][8] + v[rt][9]) + (v[rt][10] + v[rt][11]);
-                                float s3 = (v[rt][12] + v[rt][13]) + (v[rt][14] + v[rt][15]);
-                                acc[rt] += (s0 + s1) + (s2 + s3);
+                                float s[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) s[q] = (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
+                                acc[rt] += ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
                             } else {
                                 float m = acc[rt];
 #pragma unroll
-                                for (int cc = 0; cc < 16; ++cc) m = fmaxf(m, v[rt][cc]);
+                                for (int cc = 0; cc < 32; ++cc) m = fmaxf(m, v[cc]);
                                 acc[rt] = m;
                             }
-                        }
-                    } else {
-                        int c = 0;
-                        while (c < nvalid) {
-                            const int run_end = (int)min((int64_t)nvalid, gend - cbase);
+                        } else {
+                            int c = 0;
+                            while (c < nvalid) {
+                                const int64_t togo = gend[rt] - cbase;
+                                const int run_end = togo < nvalid ? (int)togo : nvalid;
 #pragma unroll
-                            for (int cc = 0; cc < 16; ++cc) {
-                                const bool on = cc >= c && cc < run_end;
-#pragma unroll
-                                for (int rt = 0; rt < MT; ++rt) {
-                                    if (p.pool == 0) acc[rt] += on ? v[rt][cc] : 0.f;
-                                    else acc[rt] = on ? fmaxf(acc[rt], v[rt][cc]) : acc[rt];
+                                for (int cc = 0; cc < 32; ++cc) {
+                                    const bool on = cc >= c && cc < run_end;
+                                    if (p.pool == 0) acc[rt] += on ? v[cc] : 0.f;
+                                    else acc[rt] = on ? fmaxf(acc[rt], v[cc]) : acc[rt];
                                 }
-                            }
-                            c = run_end;
-                            if (cbase + run_end == gend) {
-                                pg_flush<MT>(p, acc, g, gend - gbeg, rb, wq, lane, row0);
-#pragma unroll
-                                for (int rt = 0; rt < MT; ++rt) acc[rt] = p.pool == 0 ? 0.f : -3.0e38f;
-                                gbeg = gend;
-                                if (g + 1 < g_hi) {
-                                    ++g;
-                                    gend = p.goff[g + 1];
-                                    while (gend == gbeg && g + 1 < g_hi) { ++g; gend = p.goff[g + 1]; }
-                                } else {
-                                    gend = 0x7fffffffffffffffLL;   // past the last group of the unit
+                                c = run_end;
+                                if (cbase + run_end == gend[rt]) {
+                                    const int64_t sub = ((int64_t)(g[rt] - p.g_base) * p.RB * MT * 4) + subbase;
+                                    pg_flush(p, acc[rt], g[rt], gend[rt] - gbeg[rt], sub, lane, row);
+                                    acc[rt] = p.pool == 0 ? 0.f : -3.0e38f;
+                                    gbeg[rt] = gend[rt];
+                                    if (g[rt] + 1 < g_hi) {
+                                        ++g[rt];
+                                        gend[rt] = p.goff[g[rt] + 1];
+                                        while (gend[rt] == gbeg[rt] && g[rt] + 1 < g_hi) { ++g[rt]; gend[rt] = p.goff[g[rt] + 1]; }
+                                    } else {
+                                        gend[rt] = 0x7fffffffffffffffLL;   // past the last group of the unit
+                                    }
                                 }
                             }
                         }
                     }
+                    pg_fence_before();
+                    __syncwarp();
+                    if (lane == 0) pg_mbar_arrive(bar_t_empty + 8 * slot);
                 }
-                pg_fence_before();
-                __syncwarp();
-                if (lane == 0) pg_mbar_arrive(bar_t_empty + 8 * b);
             }
         }
     }
@@ -410,7 +406,7 @@ __global__ void k_pg_ranges(const int64_t* __restrict__ goff, int32_t g_a, int32
 // Picks the `ncand` rows with the largest approximate score (radix select, 4 x 8 bits, on the orderable
 // key) and the upper bound on the approximate score of every row that is NOT in the list.
 __global__ void __launch_bounds__(256)
-k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t RB, const int32_t* __restrict__ slot_cnt,
+k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const int32_t* __restrict__ slot_cnt,
            const int32_t* __restrict__ slot_row, const float* __restrict__ slot_val, const float* __restrict__ slot_bound,
            float tau, int32_t ncand, int32_t* __restrict__ cand_row, float* __restrict__ gbound) {
     __shared__ int hist[256];
@@ -420,7 +416,6 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t RB, const i
     int32_t* out = cand_row + (int64_t)g * ncand;
     for (int i = tid; i < ncand; i += blockDim.x) out[i] = -1;
     if (goff[g + 1] <= goff[g]) { if (tid == 0) gbound[g] = -3.0e38f; return; }
-    const int nsub = RB * 4;
     const int32_t* cnt = slot_cnt + (int64_t)gl * nsub;
     const int32_t* rows = slot_row + (int64_t)gl * nsub * PG_CS;
     const float* vals = slot_val + (int64_t)gl * nsub * PG_CS;
@@ -518,17 +513,18 @@ static int pg_make_tmap(sdk_ctx* c, CUtensorMap* tm, const void* base, int64_t r
 }
 
 struct pg_cfg { int KCH, MT, NC, STAGES; };
+// (KCH, MT, NC, STAGES) per padded dimension; shared memory = MT*KCH*16 KB (bank tiles) + STAGES*NC*128 B (ring)
 static pg_cfg pg_config_for(int32_t Dp) {
     int kch = Dp / 64;
     switch (kch) {
-        case 1: return {1, 4, 64, 4};
-        case 2: return {2, 4, 64, 4};
-        case 3: return {3, 4, 64, 4};
-        case 4: return {4, 3, 64, 4};
-        case 5: return {5, 2, 64, 4};
-        case 6: return {6, 2, 64, 4};
-        case 7: return {7, 1, 128, 6};
-        default: return {8, 1, 128, 6};
+        case 1: return {1, 2, 256, 6};
+        case 2: return {2, 2, 256, 5};
+        case 3: return {3, 2, 256, 4};
+        case 4: return {4, 2, 128, 6};
+        case 5: return {5, 1, 256, 4};
+        case 6: return {6, 1, 256, 4};
+        case 7: return {7, 1, 256, 3};
+        default: return {8, 1, 256, 3};
     }
 }
 
@@ -548,14 +544,14 @@ static int pg_launch_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb,
 
 static int pg_launch(sdk_ctx* c, const pg_cfg& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const PgParams& p, int grid) {
     switch (cfg.KCH) {
-        case 1: return pg_launch_t<1, 4, 64, 4>(c, ta, tb, p, grid);
-        case 2: return pg_launch_t<2, 4, 64, 4>(c, ta, tb, p, grid);
-        case 3: return pg_launch_t<3, 4, 64, 4>(c, ta, tb, p, grid);
-        case 4: return pg_launch_t<4, 3, 64, 4>(c, ta, tb, p, grid);
-        case 5: return pg_launch_t<5, 2, 64, 4>(c, ta, tb, p, grid);
-        case 6: return pg_launch_t<6, 2, 64, 4>(c, ta, tb, p, grid);
-        case 7: return pg_launch_t<7, 1, 128, 6>(c, ta, tb, p, grid);
-        default: return pg_launch_t<8, 1, 128, 6>(c, ta, tb, p, grid);
+        case 1: return pg_launch_t<1, 2, 256, 6>(c, ta, tb, p, grid);
+        case 2: return pg_launch_t<2, 2, 256, 5>(c, ta, tb, p, grid);
+        case 3: return pg_launch_t<3, 2, 256, 4>(c, ta, tb, p, grid);
+        case 4: return pg_launch_t<4, 2, 128, 6>(c, ta, tb, p, grid);
+        case 5: return pg_launch_t<5, 1, 256, 4>(c, ta, tb, p, grid);
+        case 6: return pg_launch_t<6, 1, 256, 4>(c, ta, tb, p, grid);
+        case 7: return pg_launch_t<7, 1, 256, 3>(c, ta, tb, p, grid);
+        default: return pg_launch_t<8, 1, 256, 3>(c, ta, tb, p, grid);
     }
 }
 
@@ -583,16 +579,17 @@ static int pg_run(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv
     std::vector<int64_t> hgoff((size_t)G + 1);
     SDK_CUDA(c, cudaMemcpyAsync(hgoff.data(), d_goff, ((size_t)G + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     SDK_CUDA(c, cudaStreamSynchronize(c->stream));
-    // batches of label groups so that the candidate slots stay under ~2 GB
-    const size_t per_group = (size_t)RB * 4 * (PG_CS * 8 + 8);
-    int64_t gbatch = mode == 0 ? (int64_t)((size_t)(2048ull << 20) / per_group) : (int64_t)G;
+    // batches of label groups so that the candidate slots stay under ~6 GB
+    const int32_t nsub = RB * cfg.MT * 4;                 // (row block, row tile, warp) sub-slots per label group
+    const size_t per_group = (size_t)nsub * (PG_CS * 8 + 8);
+    int64_t gbatch = mode == 0 ? (int64_t)((size_t)(6144ull << 20) / per_group) : (int64_t)G;
     if (gbatch < 1) gbatch = 1;
     if (gbatch > G) gbatch = G;
     if (mode == 0) {
-        SDK_TRY(sdk_reserve(c, c->slot_cnt, (size_t)gbatch * RB * 4 * 4));
-        SDK_TRY(sdk_reserve(c, c->slot_bound, (size_t)gbatch * RB * 4 * 4));
-        SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)gbatch * RB * 4 * PG_CS * 4));
-        SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)gbatch * RB * 4 * PG_CS * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_cnt, (size_t)gbatch * nsub * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_bound, (size_t)gbatch * nsub * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)gbatch * nsub * PG_CS * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)gbatch * nsub * PG_CS * 4));
     }
     for (int64_t ga = 0; ga < G; ga += gbatch) {
         const int64_t gb = std::min<int64_t>(G, ga + gbatch);
@@ -630,7 +627,7 @@ static int pg_run(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv
         }
         if (mode == 0) {
             sdk_prof_scope ps(c, "merge");
-            k_pg_merge<<<(unsigned)(gb - ga), 256, 0, c->stream>>>(d_goff, (int32_t)ga, RB, (const int32_t*)c->slot_cnt.p,
+            k_pg_merge<<<(unsigned)(gb - ga), 256, 0, c->stream>>>(d_goff, (int32_t)ga, nsub, (const int32_t*)c->slot_cnt.p,
                                                                    (const int32_t*)c->slot_row.p, (const float*)c->slot_val.p,
                                                                    (const float*)c->slot_bound.p, tau, ncand, d_cand_row, d_gbound);
             c->launches++;

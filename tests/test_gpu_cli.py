@@ -96,13 +96,11 @@ def test_verify_cli(cfg1_store):
     case, audio, tpath, ids, env = cfg1_store
     rc, out, err = cli("speaker_detection", "verify", "carol", str(audio), env=env)
     assert rc == 1 and "NO MATCH" in out                    # carol speaks in neither label
-    # a recording of alice only
-    solo = synth.make_case(9, [12], 3, 192, truth=[0])
-    solo.bank[:] = case.bank
+    # a recording of alice only (the S1 segments of config 1)
     from speaker_diarization_toolkit_b200 import store
-    os.environ["SPEAKERS_EMBEDDINGS_DIR"] = env["SPEAKERS_EMBEDDINGS_DIR"]
     a2 = Path(env["SPEAKERS_EMBEDDINGS_DIR"]) / "solo.wav"
     a2.write_bytes(b"RIFFsolo")
-    store.save_segment_embeddings(a2, "b200", solo.seg, ["S1"] * 12)
+    solo = case.seg[case.seg_label == 0]
+    store.save_segment_embeddings(a2, "b200", solo, ["S1"] * len(solo))
     rc, out, err = cli("speaker_detection", "verify", "alice", str(a2), env=env)
     assert rc == 0 and "MATCH: Speaker 'alice' verified (confidence: 0." in out
