@@ -158,9 +158,15 @@ void sdk_destroy(sdk_ctx* c) {
                        &c->cand_val, &c->cand_cnt, &c->gbound, &c->slot_cnt, &c->slot_row, &c->slot_val,
                        &c->slot_bound, &c->range_g, &c->fb_list, &c->fb_rows, &c->out_row, &c->out_score,
                        &c->out_count, &c->out_trust, &c->out_spk, &c->as_idx, &c->as_score, &c->as_conf,
-                       &c->as_cidx, &c->as_cscore, &c->gather};
+                       &c->as_cidx, &c->as_cscore, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
+                       &c->stage_lab[0], &c->stage_lab[1]};
     for (sdk_buf* b : bufs) sdk_release(*b);
     for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (int b = 0; b < 2; ++b) {
+        if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]);
+        if (c->ev_consumed[b]) cudaEventDestroy(c->ev_consumed[b]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -184,6 +190,9 @@ int sdk_set_option(sdk_ctx* c, const char* key, double value) {
     else if (k == "cand") {
         if (value < 1 || value > 64) return sdk_fail(c, SDK_EINVAL, "cand must be in 1..64");
         c->opt_cand = (int)value;
+    } else if (k == "chunk_mb") {
+        if (value < 1 || value > 65536) return sdk_fail(c, SDK_EINVAL, "chunk_mb must be in 1..65536");
+        c->opt_chunk_mb = (int)value;
     } else return sdk_fail(c, SDK_EINVAL, "unknown option " + k);
     return SDK_OK;
 }
@@ -265,32 +274,45 @@ static int sdk_check_flags(sdk_ctx* c) {   // after a stream sync: label sanity 
 
 static int sdk_allgather_merge(sdk_ctx* c, int32_t L, int32_t k);
 
-int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t pool,
-                     double threshold, int32_t k) {
+static int sdk_check_identify_args(sdk_ctx* c, const void* seg, const void* lab, int64_t N, int32_t L, int32_t pool,
+                                   double threshold, int32_t k) {
     if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
     if (c->P <= 0) return sdk_fail(c, SDK_ESTATE, "sdk_identify before sdk_bank_load");
     if (k < 1 || k > SDK_MAX_K) return sdk_fail(c, SDK_EINVAL, "k must be in 1..32");
     if (L < 1 || N < 0) return sdk_fail(c, SDK_EINVAL, "need L >= 1 and N >= 0");
     if (pool != SDK_POOL_MEAN && pool != SDK_POOL_MAX) return sdk_fail(c, SDK_EINVAL, "pool must be 0 (mean) or 1 (max)");
-    if (N > 0 && (!d_seg || !d_seg_label)) return sdk_fail(c, SDK_EINVAL, "seg/seg_label is NULL");
+    if (N > 0 && (!seg || !lab)) return sdk_fail(c, SDK_EINVAL, "seg/seg_label is NULL");
     if (!(threshold == threshold)) return sdk_fail(c, SDK_EINVAL, "threshold is NaN");
-    cudaSetDevice(c->device);
-    c->have_results = false;
-    c->have_assign = false;
-    const int32_t D = c->D, Dp = c->Dp;
-    const int64_t P = c->P;
-    const bool bf16 = c->dtype == SDK_DTYPE_BF16;
+    return SDK_OK;
+}
 
-    SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
+static int sdk_reserve_results(sdk_ctx* c, int32_t L, int32_t k) {
     SDK_TRY(sdk_reserve(c, c->flags, 64));
     SDK_TRY(sdk_reserve(c, c->out_row, (size_t)L * k * 8));
     SDK_TRY(sdk_reserve(c, c->out_score, (size_t)L * k * 4));
     SDK_TRY(sdk_reserve(c, c->out_count, (size_t)L * 4));
     SDK_TRY(sdk_reserve(c, c->out_trust, (size_t)L * k));
     SDK_TRY(sdk_reserve(c, c->out_spk, (size_t)L * k * 4));
+    SDK_CUDA(c, cudaMemsetAsync(c->flags.p, 0, 8, c->stream));   // [0] label sanity flag, [1] fallback counter
+    return SDK_OK;
+}
+
+// One pass of the hot path over the label groups [label_base, label_base + L): segments d_seg (N rows) carry
+// GLOBAL label ids; results land at group offset label_base of the context's result arrays.
+static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L,
+                             int32_t label_base, int32_t pool, double threshold, int32_t k) {
+    const int32_t D = c->D, Dp = c->Dp;
+    const int64_t P = c->P;
+    const bool bf16 = c->dtype == SDK_DTYPE_BF16;
+    int64_t* o_row = (int64_t*)c->out_row.p + (size_t)label_base * k;
+    float* o_score = (float*)c->out_score.p + (size_t)label_base * k;
+    int32_t* o_count = (int32_t*)c->out_count.p + label_base;
+    uint8_t* o_trust = (uint8_t*)c->out_trust.p + (size_t)label_base * k;
+    int32_t* o_spk = (int32_t*)c->out_spk.p + (size_t)label_base * k;
+
+    SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
     int32_t* d_flags = (int32_t*)c->flags.p;
-    SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, (int64_t*)c->goff.p, d_flags));
-    SDK_CUDA(c, cudaMemsetAsync(d_flags + 1, 0, 4, c->stream));   // fallback counter
+    SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, label_base, (int64_t*)c->goff.p, d_flags));
 
     // path choice: tcgen05 only where the contraction is big enough to be a real dense GEMM
     const double macs = (double)N * (double)P * (double)Dp;
@@ -299,7 +321,6 @@ int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label,
     if (path == 2 && !(sdk_poolgemm_supported(Dp) && c->tmap_encode))
         return sdk_fail(c, SDK_EINVAL, "tcgen05 path not available for this D / driver");
     c->last_path = path;
-    c->last_fallback = 0;
 
     const bool need_bf16 = bf16 || path == 2;
     if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
@@ -316,9 +337,7 @@ int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label,
                                  pool, (long long*)c->qpool.p));
         SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L, nullptr, P, pool,
                                   (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
-                                  c->row_offset, nullptr, 0.f, nullptr, nullptr, (int64_t*)c->out_row.p,
-                                  (float*)c->out_score.p, (int32_t*)c->out_count.p, (uint8_t*)c->out_trust.p,
-                                  (int32_t*)c->out_spk.p));
+                                  c->row_offset, nullptr, 0.f, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
     } else {
         // stage A: tcgen05 pooled GEMM -> per-label candidate rows + bound on everything else.
         // eps bounds |approx - canonical|: bf16 operands are shared (exact products, fp32 accumulate);
@@ -341,9 +360,7 @@ int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label,
         SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L,
                                   (const int32_t*)c->cand_row.p, ncand, pool, (const int32_t*)c->row_speaker.p,
                                   (const uint8_t*)c->row_trust.p, threshold, k, c->row_offset, (const float*)c->gbound.p,
-                                  eps, d_flags + 1, (int32_t*)c->fb_list.p, (int64_t*)c->out_row.p,
-                                  (float*)c->out_score.p, (int32_t*)c->out_count.p, (uint8_t*)c->out_trust.p,
-                                  (int32_t*)c->out_spk.p));
+                                  eps, d_flags + 1, (int32_t*)c->fb_list.p, o_row, o_score, o_count, o_trust, o_spk));
         // groups whose certificate failed are re-done exhaustively in the canonical arithmetic
         int32_t hf[2] = {0, 0};
         SDK_CUDA(c, cudaMemcpyAsync(hf, d_flags, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -351,7 +368,7 @@ int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label,
         if (hf[0] & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
         if (hf[0] & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
         int32_t nfb = hf[1];
-        c->last_fallback = nfb;
+        c->last_fallback += nfb;
         const int32_t chunk = (int32_t)std::max<int64_t>(1, std::min<int64_t>(nfb, (int64_t)(1u << 28) / std::max<int64_t>(P, 1)));
         for (int32_t done = 0; done < nfb; done += chunk) {
             int32_t m = std::min(chunk, nfb - done);
@@ -361,11 +378,22 @@ int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label,
                                      pool, (long long*)c->dense.p));
             SDK_TRY(sdk_launch_select(c, (const long long*)c->dense.p, (const int64_t*)c->goff.p, gl, m, nullptr, P, pool,
                                       (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
-                                      c->row_offset, nullptr, 0.f, nullptr, nullptr, (int64_t*)c->out_row.p,
-                                      (float*)c->out_score.p, (int32_t*)c->out_count.p, (uint8_t*)c->out_trust.p,
-                                      (int32_t*)c->out_spk.p));
+                                      c->row_offset, nullptr, 0.f, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
         }
+        SDK_CUDA(c, cudaMemsetAsync(d_flags + 1, 0, 4, c->stream));   // fallback counter consumed
     }
+    return SDK_OK;
+}
+
+int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t pool,
+                     double threshold, int32_t k) {
+    SDK_TRY(sdk_check_identify_args(c, d_seg, d_seg_label, N, L, pool, threshold, k));
+    cudaSetDevice(c->device);
+    c->have_results = false;
+    c->have_assign = false;
+    c->last_fallback = 0;
+    SDK_TRY(sdk_reserve_results(c, L, k));
+    SDK_TRY(sdk_identify_core(c, d_seg, d_seg_label, N, L, 0, pool, threshold, k));
     c->L = L; c->k = k; c->N = N;
     if (c->world > 1) SDK_TRY(sdk_allgather_merge(c, L, k));
     c->have_results = true;
@@ -413,19 +441,82 @@ static int sdk_allgather_merge(sdk_ctx* c, int32_t L, int32_t k) {
                                  (int32_t*)c->out_spk.p);
 }
 
+// Host-buffer entry point.  Large batches are cut at label-group boundaries into chunks that are copied on a second
+// stream into two staging buffers while the previous chunk is being scored, so end-to-end time is
+// max(PCIe, compute) instead of their sum, and the device footprint is two chunks instead of the whole batch.
 int sdk_identify(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
                  double threshold, int32_t k, int64_t* out_row, float* out_score, int32_t* out_count) {
-    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
-    if (c->P <= 0) return sdk_fail(c, SDK_ESTATE, "sdk_identify before sdk_bank_load");
-    if (N < 0 || (N > 0 && (!seg || !seg_label))) return sdk_fail(c, SDK_EINVAL, "seg/seg_label is NULL");
+    SDK_TRY(sdk_check_identify_args(c, seg, seg_label, N, L, pool, threshold, k));
     cudaSetDevice(c->device);
-    SDK_TRY(sdk_reserve(c, c->seg_raw, (size_t)N * c->D * 4));
-    SDK_TRY(sdk_reserve(c, c->seg_lab, (size_t)N * 4));
-    if (N > 0) {
-        SDK_CUDA(c, cudaMemcpyAsync(c->seg_raw.p, seg, (size_t)N * c->D * 4, cudaMemcpyHostToDevice, c->stream));
-        SDK_CUDA(c, cudaMemcpyAsync(c->seg_lab.p, seg_label, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
+    c->have_results = false;
+    c->have_assign = false;
+    c->last_fallback = 0;
+    const int32_t D = c->D;
+    SDK_TRY(sdk_reserve_results(c, L, k));
+    const size_t row_bytes = (size_t)D * 4;
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)((size_t)c->opt_chunk_mb << 20) / (int64_t)row_bytes);
+    if (N <= chunk_rows + chunk_rows / 4) {
+        SDK_TRY(sdk_reserve(c, c->seg_raw, (size_t)N * row_bytes));
+        SDK_TRY(sdk_reserve(c, c->seg_lab, (size_t)N * 4));
+        if (N > 0) {
+            SDK_CUDA(c, cudaMemcpyAsync(c->seg_raw.p, seg, (size_t)N * row_bytes, cudaMemcpyHostToDevice, c->stream));
+            SDK_CUDA(c, cudaMemcpyAsync(c->seg_lab.p, seg_label, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        SDK_TRY(sdk_identify_core(c, (const float*)c->seg_raw.p, (const int32_t*)c->seg_lab.p, N, L, 0, pool, threshold, k));
+    } else {
+        // chunk cut points: first label change at or after each multiple of chunk_rows
+        for (int64_t i = 1; i < N; ++i)
+            if (seg_label[i] < seg_label[i - 1]) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
+        if (seg_label[0] < 0 || seg_label[N - 1] >= L) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
+        std::vector<int64_t> cut{0};
+        while (cut.back() < N) {
+            int64_t e = std::min<int64_t>(N, cut.back() + chunk_rows);
+            while (e < N && seg_label[e] == seg_label[e - 1]) ++e;
+            cut.push_back(e);
+        }
+        int64_t max_rows = 0;
+        for (size_t i = 1; i < cut.size(); ++i) max_rows = std::max(max_rows, cut[i] - cut[i - 1]);
+        if (!c->copy_stream) {
+            SDK_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                SDK_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
+                SDK_CUDA(c, cudaEventCreateWithFlags(&c->ev_consumed[b], cudaEventDisableTiming));
+            }
+        }
+        for (int b = 0; b < 2; ++b) {
+            SDK_TRY(sdk_reserve(c, c->stage_seg[b], (size_t)max_rows * row_bytes));
+            SDK_TRY(sdk_reserve(c, c->stage_lab[b], (size_t)max_rows * 4));
+        }
+        SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+        const size_t nchunk = cut.size() - 1;
+        auto enqueue_copy = [&](size_t i) -> int {
+            const int b = (int)(i & 1);
+            const int64_t a = cut[i], n = cut[i + 1] - cut[i];
+            if (i >= 2) SDK_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+            SDK_CUDA(c, cudaMemcpyAsync(c->stage_seg[b].p, seg + a * (int64_t)D, (size_t)n * row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+            SDK_CUDA(c, cudaMemcpyAsync(c->stage_lab[b].p, seg_label + a, (size_t)n * 4, cudaMemcpyHostToDevice, c->copy_stream));
+            SDK_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+            return SDK_OK;
+        };
+        SDK_TRY(enqueue_copy(0));
+        for (size_t i = 0; i < nchunk; ++i) {
+            if (i + 1 < nchunk) SDK_TRY(enqueue_copy(i + 1));
+            const int b = (int)(i & 1);
+            const int64_t a = cut[i], n = cut[i + 1] - cut[i];
+            const int32_t g0 = seg_label[a];
+            // groups of this chunk: [g0, g1) where g1 = first label of the next chunk (empty groups in between
+            // belong to this chunk); the last chunk runs to L
+            const int32_t g1 = (i + 1 < nchunk) ? seg_label[cut[i + 1]] : L;
+            const int32_t gbeg = (i == 0) ? 0 : g0;
+            SDK_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+            SDK_TRY(sdk_identify_core(c, (const float*)c->stage_seg[b].p, (const int32_t*)c->stage_lab[b].p, n, g1 - gbeg, gbeg,
+                                      pool, threshold, k));
+            SDK_CUDA(c, cudaEventRecord(c->ev_consumed[b], c->stream));
+        }
     }
-    SDK_TRY(sdk_identify_dev(c, (const float*)c->seg_raw.p, (const int32_t*)c->seg_lab.p, N, L, pool, threshold, k));
+    c->L = L; c->k = k; c->N = N;
+    if (c->world > 1) SDK_TRY(sdk_allgather_merge(c, L, k));
+    c->have_results = true;
     return sdk_results_fetch(c, out_row, out_score, out_count, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
@@ -509,7 +600,8 @@ int sdk_affinity_pooled_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg
     const int32_t Dp = (D + 63) / 64 * 64;
     SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
     SDK_TRY(sdk_reserve(c, c->flags, 64));
-    SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, (int64_t*)c->goff.p, (int32_t*)c->flags.p));
+    SDK_CUDA(c, cudaMemsetAsync(c->flags.p, 0, 8, c->stream));
+    SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, 0, (int64_t*)c->goff.p, (int32_t*)c->flags.p));
     const double macs = (double)N * (double)N * (double)Dp;
     int path = c->opt_path;
     if (path == 0) path = (macs > 2147483648.0 && bf16 && sdk_poolgemm_supported(Dp) && c->tmap_encode) ? 2 : 1;

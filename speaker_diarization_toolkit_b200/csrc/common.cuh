@@ -37,6 +37,7 @@ struct sdk_ctx {
     double opt_eps = -1.0;     // <0: default by dtype
     int opt_profile = 0;
     int opt_cand = 16;         // re-scored candidates per label group (tensor path)
+    int opt_chunk_mb = 512;    // host-buffer identify: H2D/compute pipeline chunk size
     // bank
     int64_t P = 0;
     int32_t D = 0, Dp = 0, dtype = 0;
@@ -46,6 +47,9 @@ struct sdk_ctx {
     sdk_buf seg_raw, seg_lab, seg_f32, seg_bf16, goff, qpool, dense, flags;
     sdk_buf cand_row, cand_val, cand_cnt, gbound, slot_cnt, slot_row, slot_val, slot_bound, range_g;
     sdk_buf fb_list, fb_rows;
+    sdk_buf stage_seg[2], stage_lab[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     // results of the last identify
     int32_t L = 0, k = 0;
     int64_t N = 0;
@@ -104,7 +108,7 @@ struct sdk_prof_scope {
 int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int32_t Dp,
                          float* d_f32 /*[n,D] or null*/, __nv_bfloat16* d_bf16 /*[n,Dp] or null*/);
 // group offsets from sorted labels; *d_flag != 0 when labels are unsorted / out of range
-int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_t L,
+int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_t L, int32_t label_base,
                              int64_t* d_goff, int32_t* d_flag);
 // exact canonical Q30 pooling.  rows: dense (cand_row == null: slot == bank row, nslot == P) or
 // sparse (cand_row[g*nslot + j] = bank row or -1).  glist (may be null) maps launch group -> group.

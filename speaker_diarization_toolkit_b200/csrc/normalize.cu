@@ -117,8 +117,8 @@ int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int
     return SDK_OK;
 }
 
-// goff[g] = first segment index whose label >= g  (labels non-decreasing in [0,L))
-__global__ void k_group_offsets(const int32_t* __restrict__ lab, int64_t N, int32_t L,
+// goff[g] = first segment index whose (label - label_base) >= g  (labels non-decreasing, in [base, base+L))
+__global__ void k_group_offsets(const int32_t* __restrict__ lab, int64_t N, int32_t L, int32_t label_base,
                                 int64_t* __restrict__ goff, int32_t* __restrict__ flag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (N == 0) {
@@ -126,19 +126,18 @@ __global__ void k_group_offsets(const int32_t* __restrict__ lab, int64_t N, int3
         return;
     }
     if (i > N) return;
-    int32_t a = (i == 0) ? -1 : lab[i - 1];
-    int32_t b = (i == N) ? L : lab[i];
+    int32_t a = (i == 0) ? -1 : lab[i - 1] - label_base;
+    int32_t b = (i == N) ? L : lab[i] - label_base;
     if (i < N && (b < 0 || b >= L)) { atomicOr(flag, 1); return; }
     if (b < a) { atomicOr(flag, 2); return; }
     for (int32_t g = a + 1; g <= b; ++g) goff[g] = i;
 }
 
-int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_t L, int64_t* d_goff,
-                             int32_t* d_flag) {
-    SDK_CUDA(c, cudaMemsetAsync(d_flag, 0, sizeof(int32_t), c->stream));
+int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_t L, int32_t label_base,
+                             int64_t* d_goff, int32_t* d_flag) {
     int64_t work = N == 0 ? (int64_t)L + 1 : N + 1;
     int blocks = (int)((work + 255) / 256);
-    k_group_offsets<<<blocks, 256, 0, c->stream>>>(d_lab, N, L, d_goff, d_flag);
+    k_group_offsets<<<blocks, 256, 0, c->stream>>>(d_lab, N, L, label_base, d_goff, d_flag);
     c->launches++;
     SDK_CUDA(c, cudaGetLastError());
     return SDK_OK;

@@ -104,6 +104,21 @@ def test_tensor_path_large_bank_many_rowblocks(ctx, oracle):
     assert (gpu[2] >= 2).any(), "planted neighbours should give multi-entry top-k lists"
 
 
+@pytest.mark.parametrize("path", [1, 2])
+def test_host_pipeline_chunks(ctx, oracle, path):
+    """The host-buffer call cuts big batches at label boundaries and overlaps H2D with scoring; force many small
+    chunks (1 MB) including empty labels at chunk edges and check the stitched result."""
+    rng = np.random.default_rng(8)
+    counts = [700, 0, 0, 900, 1500, 3, 0, 2200, 64, 1, 0]
+    case = synth.make_case(88, counts, 300, 192, rows_per_speaker=rng.choice([1, 2], size=300), impostor_frac=0.2)
+    ctx.set_option("chunk_mb", 1)
+    try:
+        gpu = run_gpu(ctx, case, 1, 0, 0.354, 6, path=path)
+    finally:
+        ctx.set_option("chunk_mb", 512)
+    assert_same(gpu, run_oracle(oracle, case, 1, 0, 0.354, 6), "pipelined host path")
+
+
 def test_zero_rows_and_scale_invariance(ctx, oracle):
     case = synth.config2(total=400, P=60)
     case.seg[5] = 0.0

@@ -1,0 +1,66 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity check of the row-sharded bank path (config 4): run under torchrun, one rank per GPU.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tools/sharded_check.py
+
+Every rank loads its shard of the bank (cut on speaker boundaries), runs sdk_identify -- which ends with the single
+ncclAllGather + merge kernel -- and compares the GLOBAL result with the C oracle run on the whole bank.
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from oracle import canonical
+    from speaker_diarization_toolkit_b200 import _native, sharding, synth
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    box = [_native.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx = _native.Context(local, world, rank, box[0])
+    ok = True
+    for name, path, dtype, pool, thr, k in [("tc-top10", 2, 1, 0, -1.0, 10), ("tc-thr", 2, 1, 1, 0.354, 10),
+                                            ("exact-f32", 1, 0, 0, 0.3, 5)]:
+        rng = np.random.default_rng(11)
+        rps = rng.choice([1, 2, 3], size=900)
+        case = synth.make_case(404, synth.zipf_counts(rng, 900, 8), 900, 128 if path == 1 else 512, rows_per_speaker=rps,
+                               neighbours=5, impostor_frac=0.1)
+        shards = sharding.shard_bank_rows(case.row_speaker, world)
+        p0, p1 = shards[rank]
+        ctx.set_option("path", path)
+        ctx.bank_load(case.bank[p0:p1], case.row_speaker[p0:p1], case.row_trust[p0:p1], dtype=dtype, global_row_offset=p0)
+        rows, scores, counts = ctx.identify(case.seg, case.seg_label, case.G, pool=pool, threshold=thr, k=k)
+        ctx.assign(0.2, "low")
+        out = ctx.fetch(with_assign=True)
+        ref = canonical.identify(case.seg, case.goff, case.bank, case.row_speaker, case.n_speakers, mode=dtype, pool=pool,
+                                 threshold=thr, k=k)
+        same = (np.array_equal(rows, ref[0]) and np.array_equal(counts, ref[2])
+                and np.array_equal(scores.view(np.uint32), ref[1].view(np.uint32)))
+        tr_ref = np.where(ref[0] >= 0, case.row_trust[np.clip(ref[0], 0, None)], 4)
+        same = same and np.array_equal(out["trust"], tr_ref.astype(np.uint8))
+        a = canonical.assign(ref[0], ref[1], tr_ref.astype(np.uint8), ref[2], 0.2, 2)
+        same = same and np.array_equal(out["assign_idx"], a[0]) and np.array_equal(out["assign_score"], a[1])
+        print(f"[rank {rank}/{world}] {name}: shard rows [{p0},{p1}) path={ctx.last_path()} -> {'OK' if same else 'MISMATCH'}", flush=True)
+        ok = ok and same
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    ctx.close()
+    dist.destroy_process_group()
+    if flag.item() != 0:
+        sys.exit(1)
+    if rank == 0:
+        print("SHARDED_CHECK_OK")
+
+
+if __name__ == "__main__":
+    main()
