@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the recordings (debug runs only; 1.0 = the named config)")
+    ap.add_argument("--cta-group", type=int, default=1, choices=[1, 2], help="tcgen05 kernel variant (2 = CTA pairs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -257,6 +258,7 @@ def main():
         uid = box[0]
     ctx = _native.Context(local_rank, world if sharded else 1, rank if sharded else 0, uid)
     ctx.set_option("profile", 1)
+    ctx.set_option("cta_group", args.cta_group)
 
     # ---- data: bank (replicated, or this rank's row shard) + this rank's recordings ----
     R = counts.shape[0]
@@ -404,7 +406,7 @@ def main():
                            "segments_per_gpu": N, "label_groups_per_gpu": G, "bank_rows_per_gpu": P, "dim": D, "k": cfg["k"],
                            "threshold": cfg["thr"], "pool": "mean", "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
                            "l2": "inputs larger than L2 (no flush needed)" if N * D * 2 > 200e6 else "inputs fit L2 (latency-bound shape)",
-                           "path": "tcgen05" if path == 2 else "exact-simt", "certificate_fallback_groups": nfb, "scale": args.scale},
+                           "path": (f"tcgen05 cta_group::{args.cta_group}" if path == 2 else "exact-simt"), "certificate_fallback_groups": nfb, "scale": args.scale},
                 "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
                 "kernel_ms_per_step": {n: v[0] / args.steps for n, v in prof.items()}}
         print(json.dumps(line))

@@ -190,6 +190,9 @@ int sdk_set_option(sdk_ctx* c, const char* key, double value) {
     else if (k == "cand") {
         if (value < 1 || value > 64) return sdk_fail(c, SDK_EINVAL, "cand must be in 1..64");
         c->opt_cand = (int)value;
+    } else if (k == "cta_group") {
+        if (value != 1 && value != 2) return sdk_fail(c, SDK_EINVAL, "cta_group must be 1 or 2");
+        c->opt_cta_group = (int)value;
     } else if (k == "chunk_mb") {
         if (value < 1 || value > 65536) return sdk_fail(c, SDK_EINVAL, "chunk_mb must be in 1..65536");
         c->opt_chunk_mb = (int)value;

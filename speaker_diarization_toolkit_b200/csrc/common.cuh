@@ -37,6 +37,7 @@ struct sdk_ctx {
     double opt_eps = -1.0;     // <0: default by dtype
     int opt_profile = 0;
     int opt_cand = 16;         // re-scored candidates per label group (tensor path)
+    int opt_cta_group = 1;     // tcgen05 path: 1 = single CTA (measured faster at D <= 256), 2 = CTA pairs (cta_group::2)
     int opt_chunk_mb = 512;    // host-buffer identify: H2D/compute pipeline chunk size
     // bank
     int64_t P = 0;

@@ -27,7 +27,8 @@
 
 #include "common.cuh"
 
-#define PG_THREADS 192
+#define PG_THREADS 192    // MT == 1: TMA warp, MMA warp, one epilogue warpgroup
+#define PG_THREADS2 320   // MT == 2: two epilogue warpgroups, one per row tile
 #define PG_CS 16            // candidate slots per (label group, row block, row tile, warp) = per 32 bank rows
 #define PG_SMEM_LIMIT 232448
 
@@ -169,13 +170,101 @@ __device__ __forceinline__ void pg_tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+
+// ---- epilogue of one job: pool NC accumulator columns of this thread's bank row -------------------
+// Pooling state of one row tile: current label group, its column range, the prefetched end of the NEXT
+// group (so the goff load is off the critical path at a group boundary) and the running sum / max.
+struct PgPool {
+    int32_t g;
+    int64_t gbeg, gend, gend_next;
+    float acc;
+};
+
+__device__ __forceinline__ void pg_pool_init(PgPool& st, const PgParams& p, int32_t g_lo, int32_t g_hi, int64_t c0) {
+    int32_t g0 = g_lo;
+    int64_t e0 = p.goff[g0 + 1];
+    while (e0 == c0 && g0 + 1 < g_hi) { ++g0; e0 = p.goff[g0 + 1]; }   // skip empty groups
+    st.g = g0;
+    st.gbeg = c0;
+    st.gend = e0;
+    st.gend_next = (g0 + 1 < g_hi) ? p.goff[g0 + 2] : 0x7fffffffffffffffLL;
+    st.acc = p.pool == 0 ? 0.f : -3.0e38f;
+}
+
+__device__ __forceinline__ void pg_pool_block(PgPool& st, const PgParams& p, const float (&v)[32], int64_t cbase, int64_t c1,
+                                              int32_t g_hi, int64_t sub_stride_base, int64_t subbase, int32_t lane, int64_t row) {
+    const int64_t left = c1 - cbase;
+    const int nvalid = left < 32 ? (int)left : 32;
+    if (nvalid == 32 && st.gend > cbase + 32) {
+        // whole block inside the current label group
+        if (p.pool == 0) {
+            float s[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s[q] = (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
+            st.acc += ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+        } else {
+            float m = st.acc;
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) m = fmaxf(m, v[cc]);
+            st.acc = m;
+        }
+        return;
+    }
+    int c = 0;
+    while (c < nvalid) {
+        const int64_t togo = st.gend - cbase;
+        const int run_end = togo < nvalid ? (int)togo : nvalid;
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) {
+            const bool on = cc >= c && cc < run_end;
+            if (p.pool == 0) st.acc += on ? v[cc] : 0.f;
+            else st.acc = on ? fmaxf(st.acc, v[cc]) : st.acc;
+        }
+        c = run_end;
+        if (cbase + run_end == st.gend) {
+            const int64_t sub = (int64_t)(st.g - p.g_base) * sub_stride_base + subbase;
+            pg_flush(p, st.acc, st.g, st.gend - st.gbeg, sub, lane, row);
+            st.acc = p.pool == 0 ? 0.f : -3.0e38f;
+            st.gbeg = st.gend;
+            if (st.g + 1 < g_hi) {
+                ++st.g;
+                st.gend = st.gend_next;
+                while (st.gend == st.gbeg && st.g + 1 < g_hi) { ++st.g; st.gend = p.goff[st.g + 1]; }
+                st.gend_next = (st.g + 1 < g_hi) ? p.goff[st.g + 2] : 0x7fffffffffffffffLL;   // prefetch
+            } else {
+                st.gend = 0x7fffffffffffffffLL;   // past the last group of the unit
+            }
+        }
+    }
+}
+
+// TMEM loads are software pipelined: the load of block b+1 is in flight while block b is pooled.
+template <int NC>
+__device__ __forceinline__ void pg_epi_job(PgPool& st, const PgParams& p, uint32_t taddr, int64_t cjob, int64_t c1, int32_t g_hi,
+                                           int64_t sub_stride_base, int64_t subbase, int32_t lane, int64_t row) {
+    float va[32], vb[32];
+    pg_tmem_ld32(taddr, va);
+#pragma unroll 1
+    for (int blk = 0; blk < NC / 32; blk += 2) {
+        const int64_t cb0 = cjob + blk * 32, cb1 = cb0 + 32;
+        pg_tmem_ld_wait();
+        if (cb1 < c1) pg_tmem_ld32(taddr + (blk + 1) * 32, vb);
+        pg_pool_block(st, p, va, cb0, c1, g_hi, sub_stride_base, subbase, lane, row);
+        if (cb1 >= c1) break;
+        pg_tmem_ld_wait();
+        if (blk + 2 < NC / 32 && cb1 + 32 < c1) pg_tmem_ld32(taddr + (blk + 2) * 32, va);
+        pg_pool_block(st, p, vb, cb1, c1, g_hi, sub_stride_base, subbase, lane, row);
+        if (cb1 + 32 >= c1) break;
+    }
+}
+
 // ---- the kernel --------------------------------------------------------------------------------
 // A "job" is (column chunk j, row tile rt): KCH*4 MMAs of 128 x NC x 16 into accumulator slot (job % NSLOT).
 // Jobs run chunk-major, row-tile-minor, so with MT > 1 the whole B chunk (KCH stages) stays resident until its
 // last row tile has consumed it (STAGES >= KCH + 1), and the epilogue of job i overlaps the MMAs of job i+1.
 // N = NC = 256 keeps the per-MMA shared-memory operand fetch (4 KB of A + NC*32 B of B) under the MMA time.
 template <int KCH, int MT, int NC, int STAGES>
-__global__ void __launch_bounds__(PG_THREADS, 1)
+__global__ void __launch_bounds__(MT == 2 ? PG_THREADS2 : PG_THREADS, 1)
 k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const PgParams p) {
     constexpr uint32_t A_TILE = 128 * 128;               // 128 rows x 64 bf16
     constexpr uint32_t A_BYTES = MT * KCH * A_TILE;
@@ -184,6 +273,7 @@ k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     static_assert(NC == 128 || NC == 256, "accumulator slot width");
     static_assert(MT == 1 || STAGES >= KCH + 1, "B chunk must stay resident across the row tiles");
+    static_assert(MT == 1 || (MT == 2 && NSLOT % 2 == 0), "two epilogue warpgroups: every accumulator slot belongs to one row tile");
 
     extern __shared__ uint8_t pg_smem_raw[];
     const uint32_t raw = pg_smem_u32(pg_smem_raw);
@@ -291,90 +381,35 @@ k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
             }
         }
     } else {
-        // ================= epilogue: 4 warps, thread <-> bank row (TMEM lane) =================
+        // ================= epilogue: warpgroup wg handles row tile rt == wg (MT == 2) or all jobs (MT == 1);
+        //                    thread <-> bank row (TMEM lane) =================
         const int wq = warp & 3;                                 // TMEM lane quadrant of this warp
+        const int wg = (warp - 2) >> 2;                          // epilogue warpgroup 0/1
         const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
-        uint32_t job = 0;
+        uint32_t jobbase = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int32_t range = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)range * p.RB);
             const int32_t g_lo = p.range_g[range], g_hi = p.range_g[range + 1];
             const int64_t c0 = p.goff[g_lo], c1 = p.goff[g_hi];
             if (c1 <= c0) continue;
-            // running pooling state, one per row tile (all row tiles walk the same columns)
-            int32_t g[MT];
-            int64_t gbeg[MT], gend[MT];
-            float acc[MT];
-            {
-                int32_t g0 = g_lo;
-                int64_t e0 = p.goff[g0 + 1];
-                while (e0 == c0 && g0 + 1 < g_hi) { ++g0; e0 = p.goff[g0 + 1]; }   // skip empty groups
-#pragma unroll
-                for (int rt = 0; rt < MT; ++rt) { g[rt] = g0; gbeg[rt] = c0; gend[rt] = e0; acc[rt] = p.pool == 0 ? 0.f : -3.0e38f; }
-            }
+            const int rt = MT == 2 ? wg : 0;
+            const int64_t tile128 = (int64_t)rb * MT + rt;
+            const int64_t row = tile128 * 128 + wq * 32 + lane;
+            const int64_t subbase = tile128 * 4 + wq;
+            PgPool st;
+            pg_pool_init(st, p, g_lo, g_hi, c0);
             const int64_t nchunks = (c1 - c0 + NC - 1) / NC;
             for (int64_t j = 0; j < nchunks; ++j) {
-#pragma unroll
-                for (int rt = 0; rt < MT; ++rt, ++job) {
-                    const uint32_t slot = job % NSLOT, it = job / NSLOT;
-                    const int64_t row = ((int64_t)rb * MT + rt) * 128 + wq * 32 + lane;
-                    const int64_t subbase = (((int64_t)rb * MT + rt) * 4 + wq);
-                    pg_mbar_wait(bar_t_full + 8 * slot, it & 1u);
-                    pg_fence_after();
-#pragma unroll 1
-                    for (int blk = 0; blk < NC / 32; ++blk) {
-                        const int64_t cbase = c0 + j * NC + blk * 32;
-                        if (cbase >= c1) break;
-                        float v[32];
-                        pg_tmem_ld32(tmem_base + lane_base + slot * NC + blk * 32, v);
-                        pg_tmem_ld_wait();
-                        const int64_t left = c1 - cbase;
-                        const int nvalid = left < 32 ? (int)left : 32;
-                        if (nvalid == 32 && gend[rt] > cbase + 32) {
-                            // whole block inside the current label group
-                            if (p.pool == 0) {
-                                float s[8];
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) s[q] = (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
-                                acc[rt] += ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-                            } else {
-                                float m = acc[rt];
-#pragma unroll
-                                for (int cc = 0; cc < 32; ++cc) m = fmaxf(m, v[cc]);
-                                acc[rt] = m;
-                            }
-                        } else {
-                            int c = 0;
-                            while (c < nvalid) {
-                                const int64_t togo = gend[rt] - cbase;
-                                const int run_end = togo < nvalid ? (int)togo : nvalid;
-#pragma unroll
-                                for (int cc = 0; cc < 32; ++cc) {
-                                    const bool on = cc >= c && cc < run_end;
-                                    if (p.pool == 0) acc[rt] += on ? v[cc] : 0.f;
-                                    else acc[rt] = on ? fmaxf(acc[rt], v[cc]) : acc[rt];
-                                }
-                                c = run_end;
-                                if (cbase + run_end == gend[rt]) {
-                                    const int64_t sub = ((int64_t)(g[rt] - p.g_base) * p.RB * MT * 4) + subbase;
-                                    pg_flush(p, acc[rt], g[rt], gend[rt] - gbeg[rt], sub, lane, row);
-                                    acc[rt] = p.pool == 0 ? 0.f : -3.0e38f;
-                                    gbeg[rt] = gend[rt];
-                                    if (g[rt] + 1 < g_hi) {
-                                        ++g[rt];
-                                        gend[rt] = p.goff[g[rt] + 1];
-                                        while (gend[rt] == gbeg[rt] && g[rt] + 1 < g_hi) { ++g[rt]; gend[rt] = p.goff[g[rt] + 1]; }
-                                    } else {
-                                        gend[rt] = 0x7fffffffffffffffLL;   // past the last group of the unit
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    pg_fence_before();
-                    __syncwarp();
-                    if (lane == 0) pg_mbar_arrive(bar_t_empty + 8 * slot);
-                }
+                const uint32_t job = jobbase + (uint32_t)j * MT + rt;
+                const uint32_t slot = job % NSLOT, it = job / NSLOT;
+                pg_mbar_wait(bar_t_full + 8 * slot, it & 1u);
+                pg_fence_after();
+                pg_epi_job<NC>(st, p, tmem_base + lane_base + slot * NC, c0 + j * NC, c1, g_hi, (int64_t)p.RB * MT * 4, subbase, lane, row);
+                pg_fence_before();
+                __syncwarp();
+                if (lane == 0) pg_mbar_arrive(bar_t_empty + 8 * slot);
             }
+            jobbase += (uint32_t)nchunks * MT;
         }
     }
 
@@ -384,6 +419,220 @@ k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// =================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC issues 256 x NC x 16 MMAs.  CTA r owns bank rows
+// [.., r*128 .. r*128+127] of every 256-row tile (its half of A and of the accumulator) and HALF of every
+// segment chunk (B is split along N across the pair), so per CTA the shared-memory operand fetch and the
+// L2 -> SM traffic of the streamed operand are halved, and a B stage is NC/2 x 128 B: the ring is twice as deep.
+// The leader CTA (rank 0) issues all MMAs; full barriers live in the leader and collect the TMA bytes of
+// both CTAs; empty / accumulator-full barriers are signalled in both CTAs by multicast tcgen05.commit;
+// the accumulator-empty barrier lives in the leader and is armed by the epilogue warps of both CTAs.
+// =================================================================================================
+__device__ __forceinline__ uint32_t pg_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void pg_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pg_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void pg_mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void pg_tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tmap, int32_t c0, int32_t c1, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar_cluster)
+        : "memory");
+}
+__device__ __forceinline__ void pg_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void pg_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <int KCH, int MT, int NC, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MT == 2 ? PG_THREADS2 : PG_THREADS, 1)
+k_poolgemm2(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const PgParams p) {
+    constexpr uint32_t A_TILE = 128 * 128;               // this CTA's 128 rows x 64 bf16 of a 256-row tile
+    constexpr uint32_t A_BYTES = MT * KCH * A_TILE;
+    constexpr uint32_t B_HALF = (NC / 2) * 128;          // this CTA's half of a chunk's K stage
+    constexpr uint32_t NSLOT = 512 / NC;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    static_assert(NC == 128 || NC == 256, "accumulator slot width");
+    static_assert(MT == 1 || STAGES >= KCH + 1, "B chunk must stay resident across the row tiles");
+    static_assert(MT == 1 || (MT == 2 && NSLOT % 2 == 0), "two epilogue warpgroups: every accumulator slot belongs to one row tile");
+
+    extern __shared__ uint8_t pg_smem_raw[];
+    const uint32_t raw = pg_smem_u32(pg_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sA = base;
+    const uint32_t sB = sA + A_BYTES;
+    const uint32_t sBar = sB + STAGES * B_HALF;
+    const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8;
+    const uint32_t bar_b_full = sBar + 16, bar_b_empty = bar_b_full + 8 * STAGES;
+    const uint32_t bar_t_full = bar_b_empty + 8 * STAGES, bar_t_empty = bar_t_full + 8 * NSLOT;
+    const uint32_t s_tmem = bar_t_empty + 8 * NSLOT;
+    uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(pg_smem_raw + (s_tmem - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = pg_cluster_rank();
+    const bool leader = crank == 0;
+
+    if (warp == 0 && lane == 0) {
+        pg_mbar_init(bar_a_full, 1);
+        pg_mbar_init(bar_a_empty, 1);
+        for (int s = 0; s < STAGES; ++s) { pg_mbar_init(bar_b_full + 8 * s, 1); pg_mbar_init(bar_b_empty + 8 * s, 1); }
+        for (uint32_t b = 0; b < NSLOT; ++b) { pg_mbar_init(bar_t_full + 8 * b, 1); pg_mbar_init(bar_t_empty + 8 * b, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    pg_fence_before();
+    __syncthreads();
+    pg_cluster_sync();                                   // peer barriers are initialised before anyone signals them
+    pg_fence_after();
+    const uint32_t tmem_base = *s_tmem_ptr;
+
+    const int64_t n_units = (int64_t)p.n_ranges * p.RB;  // RB = row blocks of MT*256 rows
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    // leader-side addresses of the barriers that collect both CTAs' traffic
+    const uint32_t l_a_full = pg_mapa(bar_a_full, 0), l_b_full = pg_mapa(bar_b_full, 0), l_t_empty = pg_mapa(bar_t_empty, 0);
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0;
+            for (int64_t u = pair; u < n_units; u += npairs) {
+                const int32_t range = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)range * p.RB);
+                const int64_t c0 = p.goff[p.range_g[range]], c1 = p.goff[p.range_g[range + 1]];
+                if (c1 <= c0) continue;
+                pg_mbar_wait(bar_a_empty, a_phase ^ 1);
+                if (leader) pg_mbar_expect_tx(bar_a_full, 2 * A_BYTES);
+#pragma unroll 1
+                for (int rt = 0; rt < MT; ++rt)
+#pragma unroll 1
+                    for (int kc = 0; kc < KCH; ++kc)
+                        pg_tma_load_2d_2sm(sA + (rt * KCH + kc) * A_TILE, &tmapA, kc * 64,
+                                           (int32_t)(((int64_t)rb * MT + rt) * 256 + crank * 128), l_a_full);
+                a_phase ^= 1;
+                const int64_t nchunks = (c1 - c0 + NC - 1) / NC;
+                for (int64_t j = 0; j < nchunks; ++j) {
+                    const int32_t crow = (int32_t)(c0 + j * NC + crank * (NC / 2));
+#pragma unroll 1
+                    for (int kc = 0; kc < KCH; ++kc) {
+                        pg_mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+                        if (leader) pg_mbar_expect_tx(bar_b_full + 8 * stage, 2 * B_HALF);
+                        pg_tma_load_2d_2sm(sB + stage * B_HALF, &tmapB, kc * 64, crow, l_b_full + 8 * stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader && lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0;
+            uint32_t job = 0;
+            for (int64_t u = pair; u < n_units; u += npairs) {
+                const int32_t range = (int32_t)(u / p.RB);
+                const int64_t c0 = p.goff[p.range_g[range]], c1 = p.goff[p.range_g[range + 1]];
+                if (c1 <= c0) continue;
+                pg_mbar_wait(bar_a_full, a_phase);
+                a_phase ^= 1;
+                pg_fence_after();
+                const int64_t nchunks = (c1 - c0 + NC - 1) / NC;
+                for (int64_t j = 0; j < nchunks; ++j) {
+                    const uint32_t stage0 = stage, phase0 = phase;
+#pragma unroll
+                    for (int rt = 0; rt < MT; ++rt, ++job) {
+                        const uint32_t slot = job % NSLOT, it = job / NSLOT;
+                        pg_mbar_wait(bar_t_empty + 8 * slot, (it & 1u) ^ 1u);
+                        pg_fence_after();
+                        const uint32_t td = tmem_base + slot * NC;
+                        uint32_t st = stage0, ph = phase0;
+#pragma unroll 1
+                        for (int kc = 0; kc < KCH; ++kc) {
+                            if (rt == 0) {
+                                pg_mbar_wait(bar_b_full + 8 * st, ph);
+                                pg_fence_after();
+                            }
+                            const uint64_t db = pg_make_desc(sB + st * B_HALF);
+                            const uint64_t da = pg_make_desc(sA + (rt * KCH + kc) * A_TILE);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                pg_mma_bf16_2sm(td, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC, (kc | kk) != 0 ? 1u : 0u);
+                            if (rt == MT - 1) pg_commit_2sm(bar_b_empty + 8 * st);
+                            if (++st == STAGES) { st = 0; ph ^= 1; }
+                        }
+                        pg_commit_2sm(bar_t_full + 8 * slot);
+                        if (rt == MT - 1) { stage = st; phase = ph; }
+                    }
+                }
+                pg_commit_2sm(bar_a_empty);
+            }
+        }
+    } else {
+        // ================= epilogue (both CTAs): warpgroup wg <-> row tile (MT == 2); thread <-> one of this CTA's
+        //                    128 bank rows of that tile =================
+        const int wq = warp & 3;
+        const int wg = (warp - 2) >> 2;
+        const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
+        uint32_t jobbase = 0;
+        for (int64_t u = pair; u < n_units; u += npairs) {
+            const int32_t range = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)range * p.RB);
+            const int32_t g_lo = p.range_g[range], g_hi = p.range_g[range + 1];
+            const int64_t c0 = p.goff[g_lo], c1 = p.goff[g_hi];
+            if (c1 <= c0) continue;
+            const int rt = MT == 2 ? wg : 0;
+            const int64_t tile128 = ((int64_t)rb * MT + rt) * 2 + crank;          // index of this CTA's 128-row tile
+            const int64_t row = tile128 * 128 + wq * 32 + lane;
+            const int64_t subbase = tile128 * 4 + wq;
+            PgPool st;
+            pg_pool_init(st, p, g_lo, g_hi, c0);
+            const int64_t nchunks = (c1 - c0 + NC - 1) / NC;
+            for (int64_t j = 0; j < nchunks; ++j) {
+                const uint32_t job = jobbase + (uint32_t)j * MT + rt;
+                const uint32_t slot = job % NSLOT, it = job / NSLOT;
+                pg_mbar_wait(bar_t_full + 8 * slot, it & 1u);
+                pg_fence_after();
+                pg_epi_job<NC>(st, p, tmem_base + lane_base + slot * NC, c0 + j * NC, c1, g_hi, (int64_t)p.RB * MT * 8, subbase, lane, row);
+                pg_fence_before();
+                __syncwarp();
+                if (lane == 0) pg_mbar_arrive_cluster(l_t_empty + 8 * slot);
+            }
+            jobbase += (uint32_t)nchunks * MT;
+        }
+    }
+
+    // ---- teardown: nobody leaves (or frees TMEM) while the pair still signals each other ----
+    pg_fence_before();
+    __syncthreads();
+    pg_cluster_sync();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -536,7 +785,7 @@ static int pg_launch_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb,
     static_assert(smem <= PG_SMEM_LIMIT, "shared memory budget");
     auto kern = k_poolgemm<KCH, MT, NC, STAGES>;
     SDK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, PG_THREADS, smem, c->stream>>>(ta, tb, p);
+    kern<<<grid, MT == 2 ? PG_THREADS2 : PG_THREADS, smem, c->stream>>>(ta, tb, p);
     c->launches++;
     SDK_CUDA(c, cudaGetLastError());
     return SDK_OK;
@@ -555,9 +804,49 @@ static int pg_launch(sdk_ctx* c, const pg_cfg& cfg, const CUtensorMap& ta, const
     }
 }
 
-// columns per range: enough units to balance 148 persistent CTAs, whole groups, multiple of NC
-static int64_t pg_range_cols(sdk_ctx* c, int64_t ncols, int32_t RB, int NC) {
-    int64_t want_units = (int64_t)c->sm_count * 8;
+// (KCH, MT, NC, STAGES) of the 2-CTA kernel; per CTA: MT*KCH*16 KB of bank tiles + STAGES*(NC/2)*128 B ring
+static pg_cfg pg_config2_for(int32_t Dp) {
+    int kch = Dp / 64;
+    switch (kch) {
+        case 1: return {1, 2, 256, 8};
+        case 2: return {2, 2, 256, 8};
+        case 3: return {3, 2, 256, 8};
+        case 4: return {4, 2, 256, 6};
+        case 5: return {5, 1, 256, 8};
+        case 6: return {6, 1, 256, 8};
+        case 7: return {7, 1, 256, 6};
+        default: return {8, 1, 256, 6};
+    }
+}
+
+template <int KCH, int MT, int NC, int STAGES>
+static int pg_launch2_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const PgParams& p, int grid) {
+    constexpr size_t smem = (size_t)MT * KCH * 16384 + (size_t)STAGES * (NC / 2) * 128 + 256 + 1024;
+    static_assert(smem <= PG_SMEM_LIMIT, "shared memory budget");
+    auto kern = k_poolgemm2<KCH, MT, NC, STAGES>;
+    SDK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, MT == 2 ? PG_THREADS2 : PG_THREADS, smem, c->stream>>>(ta, tb, p);      // __cluster_dims__(2,1,1): grid must be even
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}
+
+static int pg_launch2(sdk_ctx* c, const pg_cfg& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const PgParams& p, int grid) {
+    switch (cfg.KCH) {
+        case 1: return pg_launch2_t<1, 2, 256, 8>(c, ta, tb, p, grid);
+        case 2: return pg_launch2_t<2, 2, 256, 8>(c, ta, tb, p, grid);
+        case 3: return pg_launch2_t<3, 2, 256, 8>(c, ta, tb, p, grid);
+        case 4: return pg_launch2_t<4, 2, 256, 6>(c, ta, tb, p, grid);
+        case 5: return pg_launch2_t<5, 1, 256, 8>(c, ta, tb, p, grid);
+        case 6: return pg_launch2_t<6, 1, 256, 8>(c, ta, tb, p, grid);
+        case 7: return pg_launch2_t<7, 1, 256, 6>(c, ta, tb, p, grid);
+        default: return pg_launch2_t<8, 1, 256, 6>(c, ta, tb, p, grid);
+    }
+}
+
+// columns per range: enough units to balance the persistent CTAs (or CTA pairs), whole groups, multiple of NC
+static int64_t pg_range_cols(int64_t ncols, int32_t RB, int NC, int64_t workers) {
+    int64_t want_units = workers * 8;
     int64_t T = (ncols * RB + want_units - 1) / want_units;
     T = (T + NC - 1) / NC * NC;
     if (T < 4 * NC) T = 4 * NC;
@@ -570,17 +859,19 @@ static int pg_run(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv
                   float* d_gbound, float* d_dense) {
     if (!sdk_poolgemm_supported(Dp) || !c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "tcgen05 path unavailable");
     if (N > 0x7fffffffLL || P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "tcgen05 path: at most 2^31-1 rows / segments");
-    const pg_cfg cfg = pg_config_for(Dp);
-    const int32_t RB = (int32_t)((P + (int64_t)cfg.MT * 128 - 1) / ((int64_t)cfg.MT * 128));
+    const bool two = c->opt_cta_group == 2 && c->sm_count >= 2;
+    const pg_cfg cfg = two ? pg_config2_for(Dp) : pg_config_for(Dp);
+    const int64_t rows_per_block = (int64_t)cfg.MT * (two ? 256 : 128);
+    const int32_t RB = (int32_t)((P + rows_per_block - 1) / rows_per_block);
     CUtensorMap ta, tb;
     SDK_TRY(pg_make_tmap(c, &ta, d_rows, P, Dp, 128));
-    SDK_TRY(pg_make_tmap(c, &tb, d_cols, N, Dp, (uint32_t)cfg.NC));
+    SDK_TRY(pg_make_tmap(c, &tb, d_cols, N, Dp, (uint32_t)(two ? cfg.NC / 2 : cfg.NC)));
     // group offsets are needed on the host only to batch groups; read them once (G+1 int64)
     std::vector<int64_t> hgoff((size_t)G + 1);
     SDK_CUDA(c, cudaMemcpyAsync(hgoff.data(), d_goff, ((size_t)G + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     SDK_CUDA(c, cudaStreamSynchronize(c->stream));
     // batches of label groups so that the candidate slots stay under ~6 GB
-    const int32_t nsub = RB * cfg.MT * 4;                 // (row block, row tile, warp) sub-slots per label group
+    const int32_t nsub = (int32_t)(RB * rows_per_block / 32);   // one sub-slot per 32 bank rows (warp) per label group
     const size_t per_group = (size_t)nsub * (PG_CS * 8 + 8);
     int64_t gbatch = mode == 0 ? (int64_t)((size_t)(6144ull << 20) / per_group) : (int64_t)G;
     if (gbatch < 1) gbatch = 1;
@@ -591,11 +882,12 @@ static int pg_run(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv
         SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)gbatch * nsub * PG_CS * 4));
         SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)gbatch * nsub * PG_CS * 4));
     }
+    const int64_t workers = two ? c->sm_count / 2 : c->sm_count;
     for (int64_t ga = 0; ga < G; ga += gbatch) {
         const int64_t gb = std::min<int64_t>(G, ga + gbatch);
         const int64_t ncols = hgoff[gb] - hgoff[ga];
         if (ncols > 0) {
-            const int64_t T = pg_range_cols(c, ncols, RB, cfg.NC);
+            const int64_t T = pg_range_cols(ncols, RB, cfg.NC, workers);
             const int32_t n_ranges = (int32_t)((ncols + T - 1) / T);
             SDK_TRY(sdk_reserve(c, c->range_g, (size_t)(n_ranges + 1) * 4));
             k_pg_ranges<<<(n_ranges + 1 + 255) / 256, 256, 0, c->stream>>>(d_goff, (int32_t)ga, (int32_t)gb, T, n_ranges,
@@ -619,10 +911,15 @@ static int pg_run(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv
             p.dense_out = d_dense;
             p.dense_ld = G;
             const int64_t n_units = (int64_t)n_ranges * RB;
-            const int grid = (int)std::min<int64_t>(n_units, c->sm_count);
             {
                 sdk_prof_scope ps(c, "poolgemm");
-                SDK_TRY(pg_launch(c, cfg, ta, tb, p, grid));
+                if (two) {
+                    const int grid = 2 * (int)std::min<int64_t>(n_units, workers);
+                    SDK_TRY(pg_launch2(c, cfg, ta, tb, p, grid));
+                } else {
+                    const int grid = (int)std::min<int64_t>(n_units, workers);
+                    SDK_TRY(pg_launch(c, cfg, ta, tb, p, grid));
+                }
             }
         }
         if (mode == 0) {
