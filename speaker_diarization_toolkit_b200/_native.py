@@ -12,7 +12,10 @@ from typing import Optional
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libsdk_b200.so"
+import os as _os
+
+# SDK_B200_LIB overrides the library path (A/B runs of kernel variants on one box)
+LIB_PATH = Path(_os.environ.get("SDK_B200_LIB") or PKG / "libsdk_b200.so")
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 POOL_MEAN, POOL_MAX = 0, 1

@@ -12,7 +12,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libsdk_b200.so"
-SOURCES = ["api.cu", "normalize.cu", "exact.cu", "select.cu", "poolgemm.cu"]
+SOURCES = ["api.cu", "normalize.cu", "exact.cu", "select.cu", "poolgemm.cu", "poolacc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -28,7 +28,7 @@ def _stale(obj: Path, src: Path) -> bool:
     if not obj.exists():
         return True
     t = obj.stat().st_mtime
-    deps = [src, CSRC / "common.cuh", PKG.parent / "include" / "sdk_b200.h"]
+    deps = [src, CSRC / "common.cuh", CSRC / "tcgen05.cuh", PKG.parent / "include" / "sdk_b200.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return r.stderr
 
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(5, len(jobs))) as ex:
+        with ThreadPoolExecutor(max_workers=min(6, len(jobs))) as ex:
             for log in ex.map(run, jobs):
                 if verbose and log:
                     print(log, file=sys.stderr)

@@ -159,7 +159,8 @@ void sdk_destroy(sdk_ctx* c) {
                        &c->slot_bound, &c->range_g, &c->fb_list, &c->fb_rows, &c->out_row, &c->out_score,
                        &c->out_count, &c->out_trust, &c->out_spk, &c->as_idx, &c->as_score, &c->as_conf,
                        &c->as_cidx, &c->as_cscore, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
-                       &c->stage_lab[0], &c->stage_lab[1]};
+                       &c->stage_lab[0], &c->stage_lab[1], &c->pa_hist, &c->pa_sorted, &c->pa_pos, &c->pa_sorted_pad,
+                       &c->pa_blockT, &c->pa_step0, &c->pa_step_block, &c->pa_seg_base};
     for (sdk_buf* b : bufs) sdk_release(*b);
     for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int b = 0; b < 2; ++b) {
@@ -193,6 +194,8 @@ int sdk_set_option(sdk_ctx* c, const char* key, double value) {
     } else if (k == "cta_group") {
         if (value != 1 && value != 2) return sdk_fail(c, SDK_EINVAL, "cta_group must be 1 or 2");
         c->opt_cta_group = (int)value;
+    } else if (k == "acc") {
+        c->opt_acc = value != 0;
     } else if (k == "chunk_mb") {
         if (value < 1 || value > 65536) return sdk_fail(c, SDK_EINVAL, "chunk_mb must be in 1..65536");
         c->opt_chunk_mb = (int)value;
@@ -325,16 +328,29 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         return sdk_fail(c, SDK_EINVAL, "tcgen05 path not available for this D / driver");
     c->last_path = path;
 
-    const bool need_bf16 = bf16 || path == 2;
+    // accumulate-pooling (poolacc.cu): mean pooling over many label groups is done inside the MMA accumulation; it
+    // normalises the raw segments straight into its group-interleaved bf16 layout
+    const bool use_acc = path == 2 && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048;
+    if (path == 2) {   // the plan of either tcgen05 kernel trusts goff: reject bad labels before going on
+        int32_t lf = 0;
+        SDK_CUDA(c, cudaMemcpyAsync(&lf, d_flags, 4, cudaMemcpyDeviceToHost, c->stream));
+        SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (lf & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
+        if (lf & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
+    }
+    const bool need_bf16 = (bf16 || path == 2) && !use_acc;
     if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
     if (need_bf16) SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
-    SDK_TRY(sdk_launch_normalize(c, d_seg, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
-                                 need_bf16 ? (__nv_bfloat16*)c->seg_bf16.p : nullptr));
-    const void* seg_ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
+    if (!bf16 || need_bf16)
+        SDK_TRY(sdk_launch_normalize(c, d_seg, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
+                                     need_bf16 ? (__nv_bfloat16*)c->seg_bf16.p : nullptr));
     const void* bank_ops = bf16 ? c->bank_bf16.p : c->bank_f32.p;
     const int32_t pitch = bf16 ? Dp : D;
+    const int64_t* seg_base = nullptr;     // row addressing of the segment operands (identity unless interleaved)
+    int64_t seg_stride = 1;
 
     if (path == 1) {
+        const void* seg_ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
         SDK_TRY(sdk_reserve(c, c->qpool, (size_t)L * P * 8));
         SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, nullptr, L, nullptr, P,
                                  pool, (long long*)c->qpool.p));
@@ -353,13 +369,22 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         SDK_TRY(sdk_reserve(c, c->cand_row, (size_t)L * ncand * 4));
         SDK_TRY(sdk_reserve(c, c->gbound, (size_t)L * 4));
         SDK_TRY(sdk_reserve(c, c->fb_list, (size_t)L * 4));
-        SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p,
-                                               N, Dp, (const int64_t*)c->goff.p, L, pool, tau, ncand,
-                                               (int32_t*)c->cand_row.p, (float*)c->gbound.p));
+        if (use_acc) {
+            const int64_t* ib = nullptr;
+            int64_t is = 1;
+            SDK_TRY(sdk_launch_poolacc_candidates(c, d_seg, N, D, Dp, (const __nv_bfloat16*)c->bank_bf16.p, P, (const int64_t*)c->goff.p,
+                                                  L, tau, ncand, (int32_t*)c->cand_row.p, (float*)c->gbound.p, &ib, &is));
+            if (bf16) { seg_base = ib; seg_stride = is; }     // bf16 operands live in the interleaved matrix
+        } else {
+            SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p,
+                                                   N, Dp, (const int64_t*)c->goff.p, L, pool, tau, ncand,
+                                                   (int32_t*)c->cand_row.p, (float*)c->gbound.p));
+        }
+        const void* seg_ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
         // stage B: canonical re-score of the candidates, ordered top-k, certificate
         SDK_TRY(sdk_reserve(c, c->qpool, (size_t)L * ncand * 8));
         SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, nullptr, L,
-                                 (const int32_t*)c->cand_row.p, ncand, pool, (long long*)c->qpool.p));
+                                 (const int32_t*)c->cand_row.p, ncand, pool, (long long*)c->qpool.p, seg_base, seg_stride));
         SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L,
                                   (const int32_t*)c->cand_row.p, ncand, pool, (const int32_t*)c->row_speaker.p,
                                   (const uint8_t*)c->row_trust.p, threshold, k, c->row_offset, (const float*)c->gbound.p,
@@ -378,7 +403,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
             SDK_TRY(sdk_reserve(c, c->dense, (size_t)m * P * 8));
             const int32_t* gl = (const int32_t*)c->fb_list.p + done;
             SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, gl, m, nullptr, P,
-                                     pool, (long long*)c->dense.p));
+                                     pool, (long long*)c->dense.p, seg_base, seg_stride));
             SDK_TRY(sdk_launch_select(c, (const long long*)c->dense.p, (const int64_t*)c->goff.p, gl, m, nullptr, P, pool,
                                       (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
                                       c->row_offset, nullptr, 0.f, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));

@@ -38,6 +38,7 @@ struct sdk_ctx {
     int opt_profile = 0;
     int opt_cand = 16;         // re-scored candidates per label group (tensor path)
     int opt_cta_group = 1;     // tcgen05 path: 1 = single CTA (measured faster at D <= 256), 2 = CTA pairs (cta_group::2)
+    int opt_acc = 1;           // mean pooling with many label groups: pool inside the MMA accumulation (poolacc.cu)
     int opt_chunk_mb = 512;    // host-buffer identify: H2D/compute pipeline chunk size
     // bank
     int64_t P = 0;
@@ -49,6 +50,7 @@ struct sdk_ctx {
     sdk_buf cand_row, cand_val, cand_cnt, gbound, slot_cnt, slot_row, slot_val, slot_bound, range_g;
     sdk_buf fb_list, fb_rows;
     sdk_buf stage_seg[2], stage_lab[2];
+    sdk_buf pa_hist, pa_sorted, pa_pos, pa_sorted_pad, pa_blockT, pa_step0, pa_step_block, pa_seg_base;   // accumulate-pooling plan
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     // results of the last identify
@@ -113,10 +115,12 @@ int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_
                              int64_t* d_goff, int32_t* d_flag);
 // exact canonical Q30 pooling.  rows: dense (cand_row == null: slot == bank row, nslot == P) or
 // sparse (cand_row[g*nslot + j] = bank row or -1).  glist (may be null) maps launch group -> group.
+// Segment t of group g lives at row seg_base[g] + t*seg_stride of d_seg_ops (seg_base == null: goff[g] + t).
 int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, int32_t is_bf16,
                      int32_t D, int32_t pitch, const int64_t* d_goff, const int32_t* d_glist,
                      int32_t ngroups, const int32_t* d_cand_row, int64_t nslot, int32_t pool,
-                     long long* d_qpool /*[ngroups,nslot]*/);
+                     long long* d_qpool /*[ngroups,nslot]*/, const int64_t* d_seg_base = nullptr,
+                     int64_t seg_stride = 1);
 // select: speaker dedupe + threshold + ordered top-k (+ certificate on the sparse path)
 int sdk_launch_select(sdk_ctx* c, const long long* d_qpool, const int64_t* d_goff,
                       const int32_t* d_glist, int32_t ngroups, const int32_t* d_cand_row,
@@ -142,6 +146,13 @@ int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int6
                                    const int64_t* d_goff, int32_t G, int32_t pool, float tau,
                                    int32_t ncand, int32_t* d_cand_row /*[G,ncand]*/,
                                    float* d_gbound /*[G]*/);
+// tcgen05 accumulate-pooling GEMM (mean pooling, >= 128 label groups): normalises the RAW segments into the group-
+// interleaved bf16 layout (c->seg_bf16), pools inside the MMA accumulation; returns the row addressing of the layout
+int sdk_poolacc_applicable(int32_t Dp, int32_t G, int32_t pool);
+int sdk_launch_poolacc_candidates(sdk_ctx* c, const float* d_seg_raw, int64_t N, int32_t D, int32_t Dp,
+                                  const __nv_bfloat16* d_bank, int64_t P, const int64_t* d_goff, int32_t G, float tau,
+                                  int32_t ncand, int32_t* d_cand_row, float* d_gbound,
+                                  const int64_t** d_seg_base_out, int64_t* seg_stride_out);
 // tcgen05 pooled GEMM, dense output out[row, g] (config 5)
 int sdk_launch_poolgemm_dense(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P,
                               const __nv_bfloat16* d_cols, int64_t N, int32_t Dp,

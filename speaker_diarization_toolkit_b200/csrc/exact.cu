@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(SDK_EX_THREADS)
 k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops, int32_t D, int32_t pitch,
             const int64_t* __restrict__ goff, const int32_t* __restrict__ glist,
             const int32_t* __restrict__ cand_row, int64_t nslot, int32_t ntiles, int32_t pool,
-            long long* __restrict__ qpool) {
+            long long* __restrict__ qpool, const int64_t* __restrict__ seg_base, int64_t seg_stride) {
     __shared__ double bs[SDK_EX_DC][RT];
     __shared__ int32_t srow[RT];
     const int tid = threadIdx.x;
@@ -46,6 +46,7 @@ k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops,
     const int32_t g = glist ? glist[gi] : gi;
     const int64_t s0 = goff[g], s1 = goff[g + 1];
     if (s1 <= s0) return;
+    const int64_t rbase = seg_base ? seg_base[g] : s0;      // row of the group's first segment in seg_ops
     if (tid < RT) {
         int64_t slot = (int64_t)tile * RT + tid;
         int32_t r = -1;
@@ -81,7 +82,7 @@ k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops,
             __syncthreads();
             if (valid) {
                 if (BF16) {
-                    const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(seg_ops) + s * (int64_t)pitch + d0;
+                    const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(seg_ops) + (rbase + (s - s0) * seg_stride) * (int64_t)pitch + d0;
                     int dd = 0;
                     for (; dd + 8 <= dc; dd += 8) {      // pitch % 8 == 0 and d0 % 8 == 0 -> 16-byte aligned
                         uint4 pk = __ldg(reinterpret_cast<const uint4*>(xr + dd));
@@ -102,7 +103,7 @@ k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops,
                         for (int r = 0; r < RT; ++r) acc[r] = fma(x, bs[dd][r], acc[r]);
                     }
                 } else {
-                    const float* xr = reinterpret_cast<const float*>(seg_ops) + s * (int64_t)pitch + d0;
+                    const float* xr = reinterpret_cast<const float*>(seg_ops) + (rbase + (s - s0) * seg_stride) * (int64_t)pitch + d0;
                     int dd = 0;
                     if ((pitch & 3) == 0) {
                         for (; dd + 4 <= dc; dd += 4) {
@@ -152,7 +153,8 @@ __global__ void k_fill_ll(long long* p, int64_t n, long long v) {
 
 int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, int32_t is_bf16, int32_t D,
                      int32_t pitch, const int64_t* d_goff, const int32_t* d_glist, int32_t ngroups,
-                     const int32_t* d_cand_row, int64_t nslot, int32_t pool, long long* d_qpool) {
+                     const int32_t* d_cand_row, int64_t nslot, int32_t pool, long long* d_qpool, const int64_t* d_seg_base,
+                     int64_t seg_stride) {
     if (ngroups <= 0 || nslot <= 0) return SDK_OK;
     sdk_prof_scope ps(c, "exact");
     int64_t total = (int64_t)ngroups * nslot;
@@ -175,8 +177,8 @@ int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, 
     int ntiles = (int)ntiles64;
 #define SDK_EX_CASE(RTV)                                                                                   \
     do {                                                                                                   \
-        if (is_bf16) k_exact_q30<RTV, true><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool); \
-        else k_exact_q30<RTV, false><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool); \
+        if (is_bf16) k_exact_q30<RTV, true><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool, d_seg_base, seg_stride); \
+        else k_exact_q30<RTV, false><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool, d_seg_base, seg_stride); \
     } while (0)
     if (RT == 16) SDK_EX_CASE(16);
     else if (RT == 8) SDK_EX_CASE(8);

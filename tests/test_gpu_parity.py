@@ -104,6 +104,37 @@ def test_tensor_path_large_bank_many_rowblocks(ctx, oracle):
     assert (gpu[2] >= 2).any(), "planted neighbours should give multi-entry top-k lists"
 
 
+def many_groups_case(seed, D, G=300, P_speakers=260, max_size=120):
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, max_size, size=G)
+    counts[rng.integers(0, G, size=12)] = 0            # empty labels
+    counts[:3] = [1, 400, 257]                         # a singleton, and groups longer than one accumulator tile is wide
+    rps = rng.choice([1, 2, 3], size=P_speakers)
+    return synth.make_case(seed, counts, P_speakers, D, rows_per_speaker=rps, impostor_frac=0.15, neighbours=3)
+
+
+@pytest.mark.parametrize("D,dtype,thr,k", [(192, 1, 0.354, 4), (64, 1, 0.354, 10), (256, 1, -1.0, 10), (320, 1, 0.354, 5),
+                                           (512, 1, 0.2, 8), (192, 0, 0.354, 4), (100, 1, 0.354, 3)])
+def test_accumulate_pooling_path(ctx, oracle, D, dtype, thr, k):
+    """Mean pooling over >= 128 label groups runs the accumulate-pooling kernel (group-interleaved layout, pooled sum
+    formed inside the MMA accumulation).  Same oracle, bit-exact; and identical to the generic tcgen05 kernel."""
+    case = many_groups_case(500 + D, D, max_size=30 if D >= 320 else 60)
+    ctx.set_option("acc", 1)
+    gpu = run_gpu(ctx, case, dtype, 0, thr, k, path=2)
+    path, nfb = ctx.last_path()
+    assert path == 2
+    if thr > 0.3:
+        assert nfb == 0
+    ref = run_oracle(oracle, case, dtype, 0, thr, k)
+    assert_same(gpu, ref, f"acc D={D}")
+    ctx.set_option("acc", 0)
+    try:
+        gpu2 = run_gpu(ctx, case, dtype, 0, thr, k, path=2)
+    finally:
+        ctx.set_option("acc", 1)
+    assert_same(gpu2, ref, f"generic D={D}")
+
+
 @pytest.mark.parametrize("path", [1, 2])
 def test_host_pipeline_chunks(ctx, oracle, path):
     """The host-buffer call cuts big batches at label boundaries and overlaps H2D with scoring; force many small
