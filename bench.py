@@ -42,6 +42,8 @@ WORKLOADS = {
                  desc="configs[2]: 10k recordings (~20M segments) vs 10k-profile bank, 192-d, bf16 operands, DP over recordings"),
     "cfg2": dict(R=1, seg=2000, labels=8, P=500, D=256, dtype=0, k=10, thr=0.354, seed=202,
                  desc="configs[1]: 1-hour meeting, 8 labels x 2k segments vs 500-profile bank, 256-d fp32 (latency-bound)"),
+    "cfg5": dict(R=1, seg=50000, labels=16, P=50000, D=256, dtype=1, k=0, thr=0.0, seed=505,
+                 desc="configs[4]: 50k x 50k segment-segment cosine affinity pooled per label (16 labels), 256-d bf16, single GPU"),
     "cfg4": dict(R=64, seg=2000, labels=8, P=125000, D=512, dtype=1, k=10, thr=-1.0, seed=404,
                  desc="configs[3]: 125k bank rows PER GPU (1M at 8 GPUs), 512-d bf16, top-10 per label, NCCL all-gather merge"),
 }
@@ -216,6 +218,93 @@ def run_reference(args, cfg, counts, truth):
     return 0
 
 
+# ---- config 5: pooled self-affinity (single GPU; the path does not need a collective) -------------------------
+def run_cfg5(args, cfg):
+    import torch
+    from speaker_diarization_toolkit_b200 import _native
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    N, L, D = max(1024, int(cfg["seg"] * args.scale)), cfg["labels"], cfg["D"]
+    rng = np.random.default_rng(cfg["seed"])
+    w = rng.permutation(1.0 / np.arange(1, L + 1))
+    cnt = np.maximum(1, np.floor(w / w.sum() * N).astype(np.int64))
+    cnt[np.argmax(cnt)] += N - cnt.sum()
+    g = torch.Generator(device=dev)
+    g.manual_seed(cfg["seed"])
+    cent = torch.randn((L, D), generator=g, device=dev)
+    cent = cent / cent.norm(dim=1, keepdim=True)
+    lab = torch.repeat_interleave(torch.arange(L, device=dev, dtype=torch.int32), torch.as_tensor(cnt, device=dev))
+    seg = cent[lab.long()] + 0.35 / math.sqrt(D) * torch.randn((N, D), generator=g, device=dev)
+    seg = (seg / seg.norm(dim=1, keepdim=True) * (0.5 + 19.5 * torch.rand((N, 1), generator=g, device=dev))).contiguous()
+    out_nl = torch.empty((N, L), device=dev, dtype=torch.float32)
+    out_ll = torch.empty((L, L), device=dev, dtype=torch.float32)
+    ctx = _native.Context(0)
+    ctx.set_option("profile", 1)
+    ctx.set_option("cta_group", args.cta_group)
+
+    def step():
+        ctx.affinity_pooled_dev(seg.data_ptr(), lab.data_ptr(), N, D, L, 1, 0, out_nl.data_ptr(), out_ll.data_ptr())
+
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)          # > L2: inputs (51 MB) would otherwise stay cached
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    ctx.profile_reset()
+    l0 = ctx.launch_count()
+    clocks = Clocks(0)
+    clocks.start()
+    tot = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        step()
+        tot += ctx.timer_stop()
+    clk = clocks.stop()
+    launches = ctx.launch_count() - l0
+    pairs = float(N) * float(N)
+    value = pairs * args.steps / (tot * 1e-3)
+    pk, pk_src = peaks()
+    gms, gl = ctx.profile_get("poolgemm")
+    avg_ms = gms / max(1, gl)
+    ach = 2.0 * pairs * D / (avg_ms * 1e-3) / 1e12
+    roof = {"kernel": f"k_poolgemm (tcgen05 cta_group::{args.cta_group}, dense pooled output)", "bound": "tensor", "achieved": ach,
+            "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+            "peak_source": f"{pk_src} bf16 burst (kernel timed alone, ~1 ms)", "avg_launch_ms": avg_ms}
+    hs, hl = seg.cpu().numpy(), lab.cpu().numpy()
+    ctx.affinity_pooled(hs, hl, L, dtype=1, pool=0)
+    t0 = time.perf_counter()
+    e_steps = max(1, min(3, args.steps))
+    for _ in range(e_steps):
+        nl, ll = ctx.affinity_pooled(hs, hl, L, dtype=1, pool=0)
+    te = time.perf_counter() - t0
+    e2e = {"value": pairs * e_steps / te, "unit": UNIT, "h2d_bytes_per_step": int(hs.nbytes + hl.nbytes),
+           "d2h_bytes_per_step": int(nl.nbytes + ll.nbytes), "steps": e_steps}
+    cpu = None
+    if not args.no_cpu:
+        from oracle import matching_np as mnp
+        n_c = min(N, 8192)
+        xs = mnp.bf16_round(mnp.l2_normalize(hs))
+        t0 = time.perf_counter()
+        S = xs[:n_c] @ xs.T
+        starts = np.r_[0, np.cumsum(cnt)[:-1]]
+        pooled = np.add.reduceat(S, starts, axis=1) / cnt[None, :].astype(np.float32)
+        tc = time.perf_counter() - t0
+        cpu = {"value": float(n_c) * N / tc, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {n_c} rows of the affinity ({tc:.1f} s, NumPy/OpenBLAS), extrapolates linearly"}
+        del S, pooled
+    print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": tot / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": cfg["desc"], "segments": N, "labels": L, "dim": D, "pool": "mean",
+                                 "l2": "256 MB flush buffer written between timed iterations", "outputs": "[N,L] and [L,L] fp32"},
+                      "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}))
+    ctx.close()
+    return 0
+
+
 # ---- main -----------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -242,6 +331,8 @@ def main():
         truth = np.where(truth >= 0, truth * world, truth)        # true speakers spread over all shards
     if args.impl == "reference":
         return run_reference(args, cfg, counts, truth)
+    if args.workload == "cfg5":
+        return run_cfg5(args, cfg)
 
     import torch
     import torch.distributed as dist
@@ -321,17 +412,20 @@ def main():
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on the library stream ----
     pk, pk_src = peaks()
-    names = ["normalize", "poolgemm", "merge", "exact", "select", "assign"]
+    names = ["plan", "normalize", "poolgemm", "merge", "exact", "select", "assign"]
     prof = {n: ctx.profile_get(n) for n in names}
     tot_prof = sum(v[0] for v in prof.values()) or 1.0
-    if path == 2:
+    if path >= 2:
         gms, gl = prof["poolgemm"]
         per_launch_flops = 2.0 * pairs_rank * D / max(1, gl // max(1, args.steps))   # flops per launch = 2*D per pair
         avg_ms = gms / max(1, gl)
         ach = per_launch_flops / (avg_ms * 1e-3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-        roof = {"kernel": "k_poolgemm (tcgen05)", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+        kname = "k_poolacc (tcgen05, mean pooling inside the MMA accumulation)" if path == 3 else \
+            f"k_poolgemm (tcgen05 cta_group::{args.cta_group}, pooling in the epilogue)"
+        roof = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "peak_source": f"{pk_src} bf16 sustained (kernel timed inside a long step)",
+                "frac_of_burst_peak": ach / pk["bf16_tflops"], "algorithmic_flop_per_pair": 2 * D,
                 "avg_launch_ms": avg_ms, "share_of_step": gms / tot_prof}
     else:
         gms, gl = prof["exact"]
@@ -406,7 +500,7 @@ def main():
                            "segments_per_gpu": N, "label_groups_per_gpu": G, "bank_rows_per_gpu": P, "dim": D, "k": cfg["k"],
                            "threshold": cfg["thr"], "pool": "mean", "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
                            "l2": "inputs larger than L2 (no flush needed)" if N * D * 2 > 200e6 else "inputs fit L2 (latency-bound shape)",
-                           "path": (f"tcgen05 cta_group::{args.cta_group}" if path == 2 else "exact-simt"), "certificate_fallback_groups": nfb, "scale": args.scale},
+                           "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{args.cta_group}", 3: "tcgen05 accumulate-pooling"}.get(path, str(path)), "certificate_fallback_groups": nfb, "scale": args.scale},
                 "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
                 "kernel_ms_per_step": {n: v[0] / args.steps for n, v in prof.items()}}
         print(json.dumps(line))

@@ -151,7 +151,8 @@ int sdk_profile_get(sdk_ctx* ctx, const char* name, float* ms_total, int64_t* la
 int sdk_profile_reset(sdk_ctx* ctx);
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 int64_t sdk_launch_count(sdk_ctx* ctx);
-/* which path the last identify took: 1 exact SIMT, 2 tcgen05; *n_fallback = label groups whose
+/* which path the last identify took: 1 exact SIMT, 2 tcgen05 (pooling in the epilogue), 3 tcgen05 accumulate-pooling
+ * (mean pooling inside the MMA accumulation); *n_fallback = label groups whose
  * top-k certificate failed and were re-done exhaustively */
 int sdk_last_path(sdk_ctx* ctx, int32_t* path, int64_t* n_fallback);
 

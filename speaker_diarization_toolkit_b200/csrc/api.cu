@@ -195,7 +195,8 @@ int sdk_set_option(sdk_ctx* c, const char* key, double value) {
         if (value != 1 && value != 2) return sdk_fail(c, SDK_EINVAL, "cta_group must be 1 or 2");
         c->opt_cta_group = (int)value;
     } else if (k == "acc") {
-        c->opt_acc = value != 0;
+        if (value != 0 && value != 1 && value != 2) return sdk_fail(c, SDK_EINVAL, "acc must be 0 (off), 1 (auto) or 2 (force)");
+        c->opt_acc = (int)value;
     } else if (k == "chunk_mb") {
         if (value < 1 || value > 65536) return sdk_fail(c, SDK_EINVAL, "chunk_mb must be in 1..65536");
         c->opt_chunk_mb = (int)value;
@@ -330,7 +331,8 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
 
     // accumulate-pooling (poolacc.cu): mean pooling over many label groups is done inside the MMA accumulation; it
     // normalises the raw segments straight into its group-interleaved bf16 layout
-    const bool use_acc = path == 2 && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048;
+    bool use_acc = path == 2 && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048;
+    int64_t acc_steps = 0;
     if (path == 2) {   // the plan of either tcgen05 kernel trusts goff: reject bad labels before going on
         int32_t lf = 0;
         SDK_CUDA(c, cudaMemcpyAsync(&lf, d_flags, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -338,6 +340,13 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         if (lf & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
         if (lf & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
     }
+    if (use_acc) {
+        // the interleaved layout pads every block of 256 size-sorted groups to its longest group: worth it only
+        // when there are enough groups for tight size classes (<= 12 % zero rows), else the generic kernel is faster
+        SDK_TRY(sdk_poolacc_plan(c, (const int64_t*)c->goff.p, L, &acc_steps));
+        if (c->opt_acc != 2 && (double)acc_steps * 256.0 > 1.12 * (double)N + 1024.0) use_acc = false;   // acc == 2 forces it (tests)
+    }
+    if (use_acc) c->last_path = 3;
     const bool need_bf16 = (bf16 || path == 2) && !use_acc;
     if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
     if (need_bf16) SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
@@ -373,7 +382,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
             const int64_t* ib = nullptr;
             int64_t is = 1;
             SDK_TRY(sdk_launch_poolacc_candidates(c, d_seg, N, D, Dp, (const __nv_bfloat16*)c->bank_bf16.p, P, (const int64_t*)c->goff.p,
-                                                  L, tau, ncand, (int32_t*)c->cand_row.p, (float*)c->gbound.p, &ib, &is));
+                                                  L, acc_steps, tau, ncand, (int32_t*)c->cand_row.p, (float*)c->gbound.p, &ib, &is));
             if (bf16) { seg_base = ib; seg_stride = is; }     // bf16 operands live in the interleaved matrix
         } else {
             SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p,

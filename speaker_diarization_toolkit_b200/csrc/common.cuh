@@ -149,9 +149,10 @@ int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int6
 // tcgen05 accumulate-pooling GEMM (mean pooling, >= 128 label groups): normalises the RAW segments into the group-
 // interleaved bf16 layout (c->seg_bf16), pools inside the MMA accumulation; returns the row addressing of the layout
 int sdk_poolacc_applicable(int32_t Dp, int32_t G, int32_t pool);
+int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t* steps_out);
 int sdk_launch_poolacc_candidates(sdk_ctx* c, const float* d_seg_raw, int64_t N, int32_t D, int32_t Dp,
-                                  const __nv_bfloat16* d_bank, int64_t P, const int64_t* d_goff, int32_t G, float tau,
-                                  int32_t ncand, int32_t* d_cand_row, float* d_gbound,
+                                  const __nv_bfloat16* d_bank, int64_t P, const int64_t* d_goff, int32_t G, int64_t S,
+                                  float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound,
                                   const int64_t** d_seg_base_out, int64_t* seg_stride_out);
 // tcgen05 pooled GEMM, dense output out[row, g] (config 5)
 int sdk_launch_poolgemm_dense(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P,

@@ -105,67 +105,79 @@ __global__ void k_pa_group_rows(const int32_t* __restrict__ group_pos, const int
     seg_base[g] = step0[pos / PA_NB] * PA_NB + (pos % PA_NB);
 }
 
-// ---- K1 (gather form): one warp per DESTINATION row of the interleaved bf16 matrix -----------------------------
-// canonical normalise (same arithmetic as k_normalize_vec) of the source segment, or a zero row for padding
+// ---- K1 (gather form): the interleaved bf16 matrix is written in runs of 8 consecutive destination rows per warp ---
+// (8 slots of one step: block b and step t are looked up once, lanes 0..7 resolve the 8 source segments in parallel,
+// then the 8 rows' 128-bit loads are all in flight before the first norm is reduced -- the per-row metadata chain
+// step -> block -> group -> goff would otherwise serialise ~4 dependent loads in front of every row).
+// Arithmetic = k_normalize_vec (canonical); padding slots become zero rows.
 template <int NQ>
 __global__ void __launch_bounds__(256)
 k_pa_normalize_gather(const float* __restrict__ x, int32_t D, int32_t Dp, const int64_t* __restrict__ goff,
                       const int32_t* __restrict__ sorted_pad, const int32_t* __restrict__ step_block, const int64_t* __restrict__ step0,
                       int64_t n_rows, __nv_bfloat16* __restrict__ out) {
+    constexpr int R = (NQ <= 2) ? 8 : (NQ <= 4 ? 4 : 1);       // rows per warp iteration (register budget)
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int nq = D >> 2, nqp = Dp >> 2;
-    for (int64_t row = warp0; row < n_rows; row += nwarps) {
-        const int64_t step = row / PA_NB;
-        const int j = (int)(row - step * PA_NB);
+    const int64_t n_runs = n_rows / R;                          // n_rows is a multiple of 256
+    for (int64_t run = warp0; run < n_runs; run += nwarps) {
+        const int64_t row0 = run * R;
+        const int64_t step = row0 / PA_NB;
+        const int j0 = (int)(row0 - step * PA_NB);
         const int b = step_block[step];
         const int64_t t = step - step0[b];
-        const int g = sorted_pad[b * PA_NB + j];
-        int64_t src = -1;
-        if (g >= 0) {
-            const int64_t s0 = goff[g];
-            if (t < goff[g + 1] - s0) src = s0 + t;
-        }
-        uint2* orow = reinterpret_cast<uint2*>(out + row * (int64_t)Dp);
-        if (src < 0) {
-            for (int q = lane; q < nqp; q += 32) orow[q] = make_uint2(0u, 0u);
-            continue;
-        }
-        const float4* xr = reinterpret_cast<const float4*>(x + src * (int64_t)D);
-        float4 v[NQ];
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            int q = lane + 32 * i;
-            v[i] = q < nq ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            double a = (double)v[i].x, bb = (double)v[i].y, c = (double)v[i].z, d = (double)v[i].w;
-            s = fma(a, a, s);
-            s = fma(bb, bb, s);
-            s = fma(c, c, s);
-            s = fma(d, d, s);
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
-        float nrm = (float)sqrt(s);
-        float den = nrm > 1e-12f ? nrm : 1e-12f;
-        const float inv = __fdiv_rn(1.0f, den);
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            int q = lane + 32 * i;
-            if (q < nqp) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(__fmul_rn(v[i].x, inv), __fmul_rn(v[i].y, inv));
-                __nv_bfloat162 hi = __floats2bfloat162_rn(__fmul_rn(v[i].z, inv), __fmul_rn(v[i].w, inv));
-                uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                orow[q] = pk;
+        int64_t my_src = -1;
+        if (lane < R) {
+            const int g = sorted_pad[b * PA_NB + j0 + lane];
+            if (g >= 0) {
+                const int64_t s0 = goff[g];
+                if (t < goff[g + 1] - s0) my_src = s0 + t;
             }
         }
-        for (int q = lane + 32 * NQ; q < nqp; q += 32) orow[q] = make_uint2(0u, 0u);
+        float4 v[R][NQ];
+        int64_t src[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            src[r] = __shfl_sync(0xffffffffu, my_src, r);
+            const float4* xr = reinterpret_cast<const float4*>(x + (src[r] < 0 ? 0 : src[r]) * (int64_t)D);
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                int q = lane + 32 * i;
+                v[r][i] = (src[r] >= 0 && q < nq) ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                double a = (double)v[r][i].x, bb = (double)v[r][i].y, c = (double)v[r][i].z, d = (double)v[r][i].w;
+                s = fma(a, a, s);
+                s = fma(bb, bb, s);
+                s = fma(c, c, s);
+                s = fma(d, d, s);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+            float nrm = (float)sqrt(s);
+            float den = nrm > 1e-12f ? nrm : 1e-12f;
+            const float inv = __fdiv_rn(1.0f, den);
+            uint2* orow = reinterpret_cast<uint2*>(out + (row0 + r) * (int64_t)Dp);
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                int q = lane + 32 * i;
+                if (q < nqp) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(__fmul_rn(v[r][i].x, inv), __fmul_rn(v[r][i].y, inv));
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(__fmul_rn(v[r][i].z, inv), __fmul_rn(v[r][i].w, inv));
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    orow[q] = pk;                               // zero rows: v == 0 -> 0 * inv == 0
+                }
+            }
+            for (int q = lane + 32 * NQ; q < nqp; q += 32) orow[q] = make_uint2(0u, 0u);
+        }
     }
 }
 
@@ -378,16 +390,9 @@ int sdk_poolacc_applicable(int32_t Dp, int32_t G, int32_t pool) {
     return sdk_poolgemm_supported(Dp) && pool == SDK_POOL_MEAN && G >= 128;
 }
 
-// Plans the interleaved layout, normalises the raw segments into it, runs the accumulate-pooling GEMM and the slot
-// merge.  Outputs: candidate rows + bound per label group, and (seg_base, stride) of every group's segments in the
-// interleaved bf16 matrix c->seg_bf16 for the canonical re-score.
-int sdk_launch_poolacc_candidates(sdk_ctx* c, const float* d_seg_raw, int64_t N, int32_t D, int32_t Dp, const __nv_bfloat16* d_bank,
-                                  int64_t P, const int64_t* d_goff, int32_t G, float tau, int32_t ncand, int32_t* d_cand_row,
-                                  float* d_gbound, const int64_t** d_seg_base_out, int64_t* seg_stride_out) {
-    if (!sdk_poolacc_applicable(Dp, G, SDK_POOL_MEAN) || !c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path unavailable");
-    if (P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "tcgen05 path: at most 2^31-1 bank rows");
-    if (D % 4 != 0 || D > 2048) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path needs D % 4 == 0");
-    const int kch = Dp / 64, MT = pa_mt_for(kch);
+// Plan of the interleaved layout: groups sorted by size (counting sort), blocks of 256 groups, steps per block.
+// Returns the total number of 256-row steps in *steps_out (one stream sync); S*256 / N - 1 is the zero padding.
+int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t* steps_out) {
     const int32_t n_blocks = (G + PA_NB - 1) / PA_NB;
     const int32_t Gpad = n_blocks * PA_NB;
     // ---- plan ----
@@ -417,6 +422,22 @@ int sdk_launch_poolacc_candidates(sdk_ctx* c, const float* d_seg_raw, int64_t N,
     int64_t S = 0;
     SDK_CUDA(c, cudaMemcpyAsync(&S, plan_total, 8, cudaMemcpyDeviceToHost, c->stream));
     SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    *steps_out = S;
+    return SDK_OK;
+}
+
+// Normalises the raw segments into the planned interleaved layout, runs the accumulate-pooling GEMM and the slot
+// merge.  Outputs: candidate rows + bound per label group, and (seg_base, stride) of every group's segments in the
+// interleaved bf16 matrix c->seg_bf16 for the canonical re-score.  `S` = steps from sdk_poolacc_plan.
+int sdk_launch_poolacc_candidates(sdk_ctx* c, const float* d_seg_raw, int64_t N, int32_t D, int32_t Dp, const __nv_bfloat16* d_bank,
+                                  int64_t P, const int64_t* d_goff, int32_t G, int64_t S, float tau, int32_t ncand,
+                                  int32_t* d_cand_row, float* d_gbound, const int64_t** d_seg_base_out, int64_t* seg_stride_out) {
+    if (!sdk_poolacc_applicable(Dp, G, SDK_POOL_MEAN) || !c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path unavailable");
+    if (P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "tcgen05 path: at most 2^31-1 bank rows");
+    if (D % 4 != 0 || D > 2048) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path needs D % 4 == 0");
+    const int kch = Dp / 64, MT = pa_mt_for(kch);
+    const int32_t n_blocks = (G + PA_NB - 1) / PA_NB;
+    int64_t* step0 = (int64_t*)c->pa_step0.p;
     const int64_t n_rows = S * PA_NB;
     if (n_rows > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path: interleaved matrix exceeds 2^31-1 rows");
     *d_seg_base_out = (const int64_t*)c->pa_seg_base.p;
@@ -432,7 +453,8 @@ int sdk_launch_poolacc_candidates(sdk_ctx* c, const float* d_seg_raw, int64_t N,
     // ---- K1, gather form ----
     {
         sdk_prof_scope ps(c, "normalize");
-        int64_t blocks64 = (n_rows + 7) / 8;
+        int64_t blocks64 = (n_rows / 8 + 7) / 8;                    // a warp handles runs of up to 8 rows
+        if (blocks64 < 1) blocks64 = 1;
         int blocks = (int)(blocks64 < (int64_t)c->sm_count * 8 ? blocks64 : (int64_t)c->sm_count * 8);
         int nq = (D / 4 + 31) / 32;
 #define PA_NORM(NQ) k_pa_normalize_gather<NQ><<<blocks, 256, 0, c->stream>>>(d_seg_raw, D, Dp, d_goff, (const int32_t*)c->pa_sorted_pad.p, \

@@ -113,16 +113,28 @@ def many_groups_case(seed, D, G=300, P_speakers=260, max_size=120):
     return synth.make_case(seed, counts, P_speakers, D, rows_per_speaker=rps, impostor_frac=0.15, neighbours=3)
 
 
+def test_accumulate_pooling_auto_choice(ctx):
+    """auto mode: uniform group sizes -> accumulate-pooling (path 3); a few outsized groups -> too much zero padding,
+    the generic tcgen05 kernel is chosen (path 2)."""
+    ctx.set_option("acc", 1)
+    even = synth.make_case(1, [40] * 512, 100, 64)
+    run_gpu(ctx, even, 1, 0, 0.354, 3, path=2)
+    assert ctx.last_path()[0] == 3
+    skew = synth.make_case(2, [2000] + [10] * 511, 100, 64)
+    run_gpu(ctx, skew, 1, 0, 0.354, 3, path=2)
+    assert ctx.last_path()[0] == 2
+
+
 @pytest.mark.parametrize("D,dtype,thr,k", [(192, 1, 0.354, 4), (64, 1, 0.354, 10), (256, 1, -1.0, 10), (320, 1, 0.354, 5),
                                            (512, 1, 0.2, 8), (192, 0, 0.354, 4), (100, 1, 0.354, 3)])
 def test_accumulate_pooling_path(ctx, oracle, D, dtype, thr, k):
     """Mean pooling over >= 128 label groups runs the accumulate-pooling kernel (group-interleaved layout, pooled sum
     formed inside the MMA accumulation).  Same oracle, bit-exact; and identical to the generic tcgen05 kernel."""
     case = many_groups_case(500 + D, D, max_size=30 if D >= 320 else 60)
-    ctx.set_option("acc", 1)
+    ctx.set_option("acc", 2)        # force it: this small ragged case pads far beyond the auto heuristic's 12 %
     gpu = run_gpu(ctx, case, dtype, 0, thr, k, path=2)
     path, nfb = ctx.last_path()
-    assert path == 2
+    assert path == 3, "expected the accumulate-pooling kernel"
     if thr > 0.3:
         assert nfb == 0
     ref = run_oracle(oracle, case, dtype, 0, thr, k)
@@ -130,6 +142,7 @@ def test_accumulate_pooling_path(ctx, oracle, D, dtype, thr, k):
     ctx.set_option("acc", 0)
     try:
         gpu2 = run_gpu(ctx, case, dtype, 0, thr, k, path=2)
+        assert ctx.last_path()[0] == 2
     finally:
         ctx.set_option("acc", 1)
     assert_same(gpu2, ref, f"generic D={D}")
