@@ -194,6 +194,71 @@ def cmd_assign(args, backend=None) -> int:
     return 0
 
 
+def cmd_assign_batch(args, matcher=None) -> int:
+    """Many recordings, one resident backend call (replaces one `speaker-assign assign` process tree
+    per recording, speaker-process:478-509).  MANIFEST: JSON list or JSON-lines of {"audio": ..., "transcript": ...}.
+    Writes the same assignments/<b3sum>.yaml per recording as `assign --use-embeddings`."""
+    from .batch import BatchMatcher
+    text = Path(args.manifest).read_text()
+    try:
+        items = json.loads(text)
+    except json.JSONDecodeError:
+        items = [json.loads(line) for line in text.splitlines() if line.strip()]
+    audios, transcripts, b3s, expected = [], [], [], []
+    for it in items:
+        a, t = Path(it["audio"]).resolve(), Path(it["transcript"]).resolve()
+        if not a.exists():
+            print(f"Error: Audio file not found: {a}", file=sys.stderr)
+            return 1
+        if not t.exists():
+            print(f"Error: Transcript file not found: {t}", file=sys.stderr)
+            return 1
+        b3 = compute_b3sum(a)
+        ctx_name, exp = None, []
+        cat = store.get_db_dir() / "catalog" / f"{b3}.yaml"
+        if cat.exists():
+            entry = _load_yaml(cat)
+            ctx_name = entry.get("context", {}).get("name")
+            exp = entry.get("context", {}).get("expected_speakers", [])
+        audios.append(a); transcripts.append(t); b3s.append(b3); expected.append((ctx_name, exp) if exp else None)
+    own = matcher is None
+    matcher = matcher or BatchMatcher()
+    try:
+        matcher.load_bank(args.tags)
+        results = matcher.identify(audios, assign_threshold=args.threshold, min_trust=args.min_trust, expected=expected)
+    except Exception as exc:
+        print(f"Error during identification: {exc}", file=sys.stderr)
+        return 1
+    finally:
+        if own:
+            matcher.close()
+    outputs = []
+    for a, t, b3, res, exp in zip(audios, transcripts, b3s, results, expected):
+        with open(t, "r") as fh:
+            labels = transcript.get_speakers_from_transcript(json.load(fh))
+        mappings = {}
+        for label in labels:
+            m = res.mappings.get(label)
+            if m is None:       # a transcript label without segment embeddings: no signal
+                m = {"speaker_id": None, "confidence": "unassigned", "score": 0.0, "signals": []}
+            mappings[label] = m
+        out = {"schema_version": SCHEMA_VERSION, "recording_b3sum": b3, "transcript_path": str(t),
+               "assigned_at": datetime.now(timezone.utc).strftime("%Y-%m-%dT%H:%M:%SZ"), "method": f"speaker-assign-v{VERSION}",
+               "context": exp[0] if exp else None, "min_trust": args.min_trust, "threshold": args.threshold, "mappings": mappings}
+        outputs.append(out)
+        if not args.dry_run:
+            adir = store.get_db_dir() / "assignments"
+            adir.mkdir(parents=True, exist_ok=True)
+            _save_yaml(adir / f"{b3}.yaml", out)
+    if args.format == "json":
+        print(json.dumps(outputs, indent=2, ensure_ascii=False))
+    elif not args.quiet:
+        for a, out in zip(audios, outputs):
+            done = sum(1 for m in out["mappings"].values() if m.get("speaker_id"))
+            print(f"{a.name}: assigned {done}/{len(out['mappings'])}")
+    return 0
+
+
 def build_parser() -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser(prog="speaker-assign", description="Multi-signal speaker name assignment (B200 embedding path)")
     parser.add_argument("-V", "--version", action="version", version=f"speaker-assign {VERSION}")
@@ -214,6 +279,14 @@ def build_parser() -> argparse.ArgumentParser:
     a.add_argument("--format", "-f", choices=["text", "json"], default="text")
     a.add_argument("--dry-run", "-n", action="store_true")
     a.set_defaults(func=cmd_assign)
+    b = sub.add_parser("assign-batch", help="assign many recordings with one resident backend call")
+    b.add_argument("manifest", help='JSON list / JSON-lines of {"audio": ..., "transcript": ...}')
+    b.add_argument("--min-trust", default="low", choices=["high", "medium", "low"])
+    b.add_argument("--tags")
+    b.add_argument("--threshold", type=float, default=0.3)
+    b.add_argument("--format", "-f", choices=["text", "json"], default="text")
+    b.add_argument("--dry-run", "-n", action="store_true")
+    b.set_defaults(func=cmd_assign_batch)
     return parser
 
 

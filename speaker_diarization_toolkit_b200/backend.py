@@ -34,7 +34,8 @@ class B200Backend(EmbeddingBackend):
     """Settings come from the environment (the reference rule: every path/knob from env, evals/TESTING.md:52-66):
     SPEAKER_B200_POOL = mean|max, SPEAKER_B200_TOPK (matches per label, default 10),
     SPEAKER_B200_SCOPE = label|recording (per-label rows, or whole-recording rows as the reference's
-    speaker-assign expects), SPEAKER_B200_DTYPE = fp32|bf16, SPEAKER_B200_DEVICE (cuda index), SPEAKER_B200_DIM."""
+    speaker-assign expects), SPEAKER_B200_DTYPE = fp32|bf16, SPEAKER_B200_DEVICE (cuda index), SPEAKER_B200_DIM,
+    SPEAKER_B200_BANK_CACHE = 0 disables the packed bank cache (store.build_bank_cached)."""
 
     def __init__(self):
         self._ctx: Optional[_native.Context] = None
@@ -74,7 +75,8 @@ class B200Backend(EmbeddingBackend):
                      c.get("updated_at")) for c in candidates)
         dtype = _native.DTYPE_BF16 if os.environ.get("SPEAKER_B200_DTYPE", "fp32") == "bf16" else _native.DTYPE_F32
         if self._bank is None or key != self._bank_key or dtype != getattr(self, "_bank_dtype", None):
-            bank = store.build_bank(candidates, self.name, _env_int("SPEAKER_B200_DIM", 0) or None)
+            build = store.build_bank if os.environ.get("SPEAKER_B200_BANK_CACHE", "1") == "0" else store.build_bank_cached
+            bank = build(candidates, self.name, _env_int("SPEAKER_B200_DIM", 0) or None)
             if bank.P:
                 self._context().bank_load(bank.rows, bank.row_speaker, bank.row_trust, dtype=dtype)
             self._bank, self._bank_key, self._bank_dtype = bank, key, dtype

@@ -202,3 +202,93 @@ def load_segment_embeddings(audio_path, backend_name: str) -> SegmentEmbeddings:
     idx = np.asarray([pos[l] for l in lab], dtype=np.int32)
     order = np.argsort(idx, kind="stable")
     return SegmentEmbeddings(emb[order], idx[order], labels, start[order], end[order])
+
+
+# ---- packed bank cache ------------------------------------------------------------
+# `cmd_identify` would otherwise open one .npy per embedding record on every call (speaker_detection:1054 ->
+# base.py:123); at a million-profile bank that, not the GPU, is the wall time.  The per-file layout stays
+# authoritative: the cache is `embeddings/.bank-<backend>-D<d>.f32` (raw fp32 [rows, D], mmap-able) +
+# `embeddings/.bank-<backend>-D<d>.idx.json` (speaker/emb id -> row, file size + mtime_ns).  A row is reused only if
+# its source file's (size, mtime_ns) still match; new / changed files are re-read and appended; the pack is
+# rewritten compacted when more than a quarter of it is stale.
+def _cache_paths(backend_name: str, dim: int):
+    root = get_embeddings_path()
+    return root / f".bank-{backend_name}-D{dim}.f32", root / f".bank-{backend_name}-D{dim}.idx.json"
+
+
+def build_bank_cached(candidates: List[Dict[str, Any]], backend_name: str, dim: Optional[int] = None) -> Bank:
+    wanted = []     # (speaker index, speaker id, record, path, stat key)
+    speaker_ids: List[str] = []
+    for prof in candidates:
+        sid = prof.get("id")
+        idx = None
+        for rec in (prof.get("embeddings") or {}).get(backend_name) or []:
+            path = vector_path(sid, rec)
+            if path is None:
+                print(f"Warning: no vector file for {sid}/{rec.get('id')} ({backend_name})", file=sys.stderr)
+                continue
+            if idx is None:
+                idx = len(speaker_ids)
+                speaker_ids.append(sid)
+            st = path.stat()
+            wanted.append((idx, sid, rec, path, [str(path), st.st_size, st.st_mtime_ns]))
+    if not wanted:
+        return Bank(np.zeros((0, dim or 0), np.float32), np.zeros(0, np.int32), np.zeros(0, np.uint8), [], [])
+    if dim is None:
+        packs = sorted(get_embeddings_path().glob(f".bank-{backend_name}-D*.idx.json"), key=lambda q: q.stat().st_mtime_ns)
+        if packs:       # a pack exists: its dimension (a mismatching vector is caught when it is read)
+            dim = int(packs[-1].name.split("-D")[-1].split(".")[0])
+        else:
+            dim = int(np.load(wanted[0][3]).reshape(-1).shape[0])
+    pack_path, idx_path = _cache_paths(backend_name, dim)
+    index, pack = {}, None
+    if pack_path.exists() and idx_path.exists():
+        try:
+            meta = json.loads(idx_path.read_text())
+            if meta.get("dim") == dim and pack_path.stat().st_size == meta.get("rows", -1) * dim * 4:
+                index = {k: v for k, v in meta.get("entries", {}).items()}
+                pack = np.memmap(pack_path, dtype=np.float32, mode="r", shape=(meta["rows"], dim)) if meta["rows"] else None
+        except (json.JSONDecodeError, OSError, ValueError):
+            index, pack = {}, None
+    rows = np.empty((len(wanted), dim), dtype=np.float32)
+    fresh = []      # (position, key, stat) that had to be read from the per-file layout
+    for pos, (_, sid, rec, path, stat) in enumerate(wanted):
+        key = f"{sid}/{rec.get('id')}"
+        ent = index.get(key)
+        if ent is not None and pack is not None and ent["stat"] == stat and ent["row"] < pack.shape[0]:
+            rows[pos] = pack[ent["row"]]
+            continue
+        vec = np.load(path).astype(np.float32).reshape(-1)
+        if vec.shape[0] != dim:
+            raise ValueError(f"embedding {key} has dimension {vec.shape[0]}, expected {dim}")
+        rows[pos] = vec
+        fresh.append((pos, key, stat))
+    if fresh or pack is None:
+        live = {f"{sid}/{rec.get('id')}" for _, sid, rec, _, _ in wanted}
+        stale = sum(1 for k in index if k not in live)
+        try:
+            if pack is None or stale * 4 > max(1, len(index)):
+                # rewrite compacted: exactly the rows in use now
+                tmp = pack_path.with_suffix(".tmp")
+                rows.tofile(tmp)
+                os.replace(tmp, pack_path)
+                entries = {f"{sid}/{rec.get('id')}": {"row": pos, "stat": stat} for pos, (_, sid, rec, _, stat) in enumerate(wanted)}
+                n_rows = len(wanted)
+            else:
+                # append the new / changed rows
+                n_rows = pack.shape[0]
+                del pack
+                with open(pack_path, "ab") as fh:
+                    for pos, key, stat in fresh:
+                        rows[pos].tofile(fh)
+                        index[key] = {"row": n_rows, "stat": stat}
+                        n_rows += 1
+                entries = index
+            tmpi = idx_path.with_suffix(".tmp")
+            tmpi.write_text(json.dumps({"dim": dim, "rows": n_rows, "backend": backend_name, "entries": entries}))
+            os.replace(tmpi, idx_path)
+        except OSError as exc:      # read-only store: the cache is an optimisation, never a requirement
+            print(f"Warning: could not update the packed bank cache: {exc}", file=sys.stderr)
+    row_speaker = np.asarray([w[0] for w in wanted], np.int32)
+    row_trust = np.asarray([TRUST_CODES.get(w[2].get("trust_level", "unknown"), TRUST_CODES["unknown"]) for w in wanted], np.uint8)
+    return Bank(rows, row_speaker, row_trust, [w[2].get("id") for w in wanted], speaker_ids)

@@ -104,3 +104,47 @@ def test_verify_cli(cfg1_store):
     store.save_segment_embeddings(a2, "b200", solo, ["S1"] * len(solo))
     rc, out, err = cli("speaker_detection", "verify", "alice", str(a2), env=env)
     assert rc == 0 and "MATCH: Speaker 'alice' verified (confidence: 0." in out
+
+
+def test_assign_batch_equals_per_recording_assign(tmp_path, oracle):
+    """`assign-batch` (one resident backend call for all recordings, assignment on the device) writes
+    the same mappings as one `assign --use-embeddings` per recording."""
+    bank_case = synth.make_case(7, [1], 12, 192, rows_per_speaker=[1, 2, 1, 3, 1, 1, 2, 1, 1, 1, 2, 1], trust_cycle=(0, 0, 1, 2))
+    ids = [f"spk{idx:04d}" for idx in range(12)]
+    manifest, singles = [], {}
+    env = dict(os.environ, SPEAKERS_EMBEDDINGS_DIR=str(tmp_path), SPEAKER_DETECTION_BACKEND="b200", PYTHONPATH=str(ROOT))
+    env.pop("SPEAKER_BACKENDS_CONFIG", None)
+    from speaker_diarization_toolkit_b200.synth import Case
+    rng = np.random.default_rng(3)
+    for r in range(5):
+        labels = [f"S{i + 1}" for i in range(2 + r % 3)]
+        counts = rng.integers(3, 30, size=len(labels))
+        rec = synth.make_case(100 + r, counts, 12, 192, truth=list(rng.integers(0, 12, size=len(labels))))
+        # same enrolled speakers for every recording: regenerate the segments around the bank's centroids
+        merged = Case(rec.seg, rec.seg_label, rec.goff, bank_case.bank, bank_case.row_speaker, bank_case.row_trust, rec.truth, 12)
+        for g in range(len(labels)):
+            spk = int(rec.truth[g])
+            row = int(np.flatnonzero(bank_case.row_speaker == spk)[0])
+            base = bank_case.bank[row] / np.linalg.norm(bank_case.bank[row])
+            n = int(counts[g])
+            x = base[None, :] + 0.25 / np.sqrt(192) * rng.standard_normal((n, 192))
+            merged.seg[rec.goff[g]:rec.goff[g + 1]] = x.astype(np.float32)
+        audio, tpath, _ = synth.write_store(merged, tmp_path, labels, speaker_names=ids, audio_name=f"rec{r}.wav")
+        manifest.append({"audio": str(audio), "transcript": str(tpath)})
+    mpath = tmp_path / "manifest.json"
+    mpath.write_text(json.dumps(manifest))
+    for item in manifest:
+        rc, out, err = cli("speaker-assign", "-q", "assign", item["audio"], "-t", item["transcript"], "-e", "-n", "--format", "json",
+                           "--threshold", "0.2", env=env)
+        assert rc == 0, err
+        singles[item["audio"]] = json.loads(out[out.index("{"):])["mappings"]
+    rc, out, err = cli("speaker-assign", "-q", "assign-batch", str(mpath), "--threshold", "0.2", "--format", "json", env=env)
+    assert rc == 0, err
+    batch = json.loads(out)
+    assert len(batch) == 5
+    n_assigned = 0
+    for item, b in zip(manifest, batch):
+        assert b["mappings"] == singles[item["audio"]]
+        n_assigned += sum(1 for m in b["mappings"].values() if m["speaker_id"])
+    assert n_assigned >= 5
+    assert len(list((tmp_path / "assignments").glob("*.yaml"))) == 5

@@ -197,3 +197,48 @@ def test_plugin_registry_and_abc(tmp_path, monkeypatch):
     assert plugin_api.format_ffmpeg_args(plugin_api.AudioProfile(sample_rate=8000, channels=2, bit_depth=24)) == \
            ["-ar", "8000", "-ac", "2", "-f", "wav", "-acodec", "pcm_s24le"]
     assert plugin_api.format_ffmpeg_args(plugin_api.AudioProfile(format="flac")) == ["-ar", "16000", "-ac", "1", "-f", "flac"]
+
+
+def test_packed_bank_cache(tmp_path, monkeypatch):
+    """the packed cache returns exactly what the per-file layout holds, survives additions,
+    edits and deletions, and never wins over a changed .npy."""
+    monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(tmp_path))
+    rng = np.random.default_rng(4)
+
+    def put(sid, eid, vec):
+        d = tmp_path / "embeddings" / sid
+        d.mkdir(parents=True, exist_ok=True)
+        np.save(d / f"{eid}.npy", vec.astype(np.float32))
+
+    cands = []
+    for s in range(6):
+        recs = []
+        for e in range(1 + s % 3):
+            put(f"spk{s}", f"emb-{s}{e}", rng.standard_normal(16))
+            recs.append({"id": f"emb-{s}{e}", "trust_level": ["high", "medium", "low"][e]})
+        cands.append({"id": f"spk{s}", "embeddings": {"b200": recs}})
+
+    def same(a, b):
+        return (np.array_equal(a.rows, b.rows) and np.array_equal(a.row_speaker, b.row_speaker) and np.array_equal(a.row_trust, b.row_trust)
+                and a.row_emb_id == b.row_emb_id and a.speaker_ids == b.speaker_ids)
+
+    plain = store.build_bank(cands, "b200")
+    assert same(store.build_bank_cached(cands, "b200"), plain)               # cold: builds the pack
+    pack = tmp_path / "embeddings" / ".bank-b200-D16.f32"
+    assert pack.exists() and pack.stat().st_size == plain.P * 16 * 4
+    reads = []
+    real_load = np.load
+    monkeypatch.setattr(np, "load", lambda p, *a, **k: (reads.append(str(p)), real_load(p, *a, **k))[1])
+    assert same(store.build_bank_cached(cands, "b200"), plain) and reads == []   # warm: no .npy opened
+    # a changed vector is re-read (mtime/size), a new record is appended, a removed speaker disappears
+    import os as _os, time as _time
+    put("spk2", "emb-20", np.arange(16))
+    _os.utime(tmp_path / "embeddings" / "spk2" / "emb-20.npy", ns=(_time.time_ns(), _time.time_ns() + 10**9))
+    put("spk9", "emb-90", rng.standard_normal(16))
+    cands2 = [c for c in cands if c["id"] != "spk0"] + [{"id": "spk9", "embeddings": {"b200": [{"id": "emb-90"}]}}]
+    reads.clear()
+    got = store.build_bank_cached(cands2, "b200")
+    monkeypatch.setattr(np, "load", real_load)
+    assert same(got, store.build_bank(cands2, "b200"))
+    assert sorted(Path(r).name for r in reads) == ["emb-20.npy", "emb-90.npy"]
+    assert np.array_equal(got.rows[got.row_emb_id.index("emb-20")], np.arange(16, dtype=np.float32))
