@@ -243,6 +243,7 @@ def run_cfg5(args, cfg):
     ctx = _native.Context(0)
     ctx.set_option("profile", 1)
     ctx.set_option("cta_group", args.cta_group)
+    ctx.set_option("acc", args.acc)
 
     def step():
         ctx.affinity_pooled_dev(seg.data_ptr(), lab.data_ptr(), N, D, L, 1, 0, out_nl.data_ptr(), out_ll.data_ptr())
@@ -270,7 +271,9 @@ def run_cfg5(args, cfg):
     gms, gl = ctx.profile_get("poolgemm")
     avg_ms = gms / max(1, gl)
     ach = 2.0 * pairs * D / (avg_ms * 1e-3) / 1e12
-    roof = {"kernel": f"k_poolgemm (tcgen05 cta_group::{args.cta_group}, dense pooled output)", "bound": "tensor", "achieved": ach,
+    kname = "k_poolacc (tcgen05, label columns split, mean pooling inside the MMA accumulation, dense output)" if ctx.last_path()[0] == 3 \
+        else f"k_poolgemm (tcgen05 cta_group::{args.cta_group}, dense pooled output)"
+    roof = {"kernel": kname, "bound": "tensor", "achieved": ach,
             "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
             "peak_source": f"{pk_src} bf16 burst (kernel timed alone, ~1 ms)", "avg_launch_ms": avg_ms}
     hs, hl = seg.cpu().numpy(), lab.cpu().numpy()
@@ -315,6 +318,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the recordings (debug runs only; 1.0 = the named config)")
     ap.add_argument("--cta-group", type=int, default=1, choices=[1, 2], help="tcgen05 kernel variant (2 = CTA pairs)")
+    ap.add_argument("--acc", type=int, default=1, choices=[0, 1, 2], help="accumulate-pooling kernel: 0 off, 1 auto, 2 force (A/B runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -350,6 +354,7 @@ def main():
     ctx = _native.Context(local_rank, world if sharded else 1, rank if sharded else 0, uid)
     ctx.set_option("profile", 1)
     ctx.set_option("cta_group", args.cta_group)
+    ctx.set_option("acc", args.acc)
 
     # ---- data: bank (replicated, or this rank's row shard) + this rank's recordings ----
     R = counts.shape[0]

@@ -159,8 +159,8 @@ void sdk_destroy(sdk_ctx* c) {
                        &c->slot_bound, &c->range_g, &c->fb_list, &c->fb_rows, &c->out_row, &c->out_score,
                        &c->out_count, &c->out_trust, &c->out_spk, &c->as_idx, &c->as_score, &c->as_conf,
                        &c->as_cidx, &c->as_cscore, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
-                       &c->stage_lab[0], &c->stage_lab[1], &c->pa_hist, &c->pa_sorted, &c->pa_pos, &c->pa_sorted_pad,
-                       &c->pa_blockT, &c->pa_step0, &c->pa_step_block, &c->pa_seg_base};
+                       &c->stage_lab[0], &c->stage_lab[1], &c->pa_hist, &c->pa_sorted, &c->pa_pos, &c->pa_col_group,
+                       &c->pa_col_meta, &c->pa_blockT, &c->pa_step0, &c->pa_grp, &c->seg_il};
     for (sdk_buf* b : bufs) sdk_release(*b);
     for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int b = 0; b < 2; ++b) {
@@ -329,9 +329,12 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         return sdk_fail(c, SDK_EINVAL, "tcgen05 path not available for this D / driver");
     c->last_path = path;
 
-    // accumulate-pooling (poolacc.cu): mean pooling over many label groups is done inside the MMA accumulation; it
-    // normalises the raw segments straight into its group-interleaved bf16 layout
+    // accumulate-pooling (poolacc.cu): mean pooling is done inside the MMA accumulation; it normalises the raw segments
+    // straight into its group-interleaved bf16 layout.  Auto mode takes it where the generic kernel is bound by its
+    // epilogue (D <= 256) or where there are enough groups for tight size classes, and only if the layout's zero
+    // padding stays under 12 %.
     bool use_acc = path == 2 && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048;
+    if (use_acc && c->opt_acc != 2 && !(Dp <= 256 || L > 2048)) use_acc = false;
     int64_t acc_steps = 0;
     if (path == 2) {   // the plan of either tcgen05 kernel trusts goff: reject bad labels before going on
         int32_t lf = 0;
@@ -341,9 +344,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         if (lf & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
     }
     if (use_acc) {
-        // the interleaved layout pads every block of 256 size-sorted groups to its longest group: worth it only
-        // when there are enough groups for tight size classes (<= 12 % zero rows), else the generic kernel is faster
-        SDK_TRY(sdk_poolacc_plan(c, (const int64_t*)c->goff.p, L, &acc_steps));
+        SDK_TRY(sdk_poolacc_plan(c, (const int64_t*)c->goff.p, L, N, P, Dp, &acc_steps));
         if (c->opt_acc != 2 && (double)acc_steps * 256.0 > 1.12 * (double)N + 1024.0) use_acc = false;   // acc == 2 forces it (tests)
     }
     if (use_acc) c->last_path = 3;
@@ -355,8 +356,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
                                      need_bf16 ? (__nv_bfloat16*)c->seg_bf16.p : nullptr));
     const void* bank_ops = bf16 ? c->bank_bf16.p : c->bank_f32.p;
     const int32_t pitch = bf16 ? Dp : D;
-    const int64_t* seg_base = nullptr;     // row addressing of the segment operands (identity unless interleaved)
-    int64_t seg_stride = 1;
+    const PaGroup* seg_grp = nullptr;      // row addressing of the segment operands (identity unless interleaved)
 
     if (path == 1) {
         const void* seg_ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
@@ -379,11 +379,11 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         SDK_TRY(sdk_reserve(c, c->gbound, (size_t)L * 4));
         SDK_TRY(sdk_reserve(c, c->fb_list, (size_t)L * 4));
         if (use_acc) {
-            const int64_t* ib = nullptr;
-            int64_t is = 1;
-            SDK_TRY(sdk_launch_poolacc_candidates(c, d_seg, N, D, Dp, (const __nv_bfloat16*)c->bank_bf16.p, P, (const int64_t*)c->goff.p,
-                                                  L, acc_steps, tau, ncand, (int32_t*)c->cand_row.p, (float*)c->gbound.p, &ib, &is));
-            if (bf16) { seg_base = ib; seg_stride = is; }     // bf16 operands live in the interleaved matrix
+            const PaGroup* ig = nullptr;
+            SDK_TRY(sdk_launch_poolacc(c, d_seg, d_seg_label, label_base, N, D, Dp, (const __nv_bfloat16*)c->bank_bf16.p, P,
+                                       (const int64_t*)c->goff.p, L, acc_steps, 0, tau, ncand, (int32_t*)c->cand_row.p,
+                                       (float*)c->gbound.p, nullptr, c->seg_bf16, &ig));
+            if (bf16) seg_grp = ig;                            // bf16 operands live in the interleaved matrix
         } else {
             SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p,
                                                    N, Dp, (const int64_t*)c->goff.p, L, pool, tau, ncand,
@@ -393,7 +393,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         // stage B: canonical re-score of the candidates, ordered top-k, certificate
         SDK_TRY(sdk_reserve(c, c->qpool, (size_t)L * ncand * 8));
         SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, nullptr, L,
-                                 (const int32_t*)c->cand_row.p, ncand, pool, (long long*)c->qpool.p, seg_base, seg_stride));
+                                 (const int32_t*)c->cand_row.p, ncand, pool, (long long*)c->qpool.p, seg_grp));
         SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L,
                                   (const int32_t*)c->cand_row.p, ncand, pool, (const int32_t*)c->row_speaker.p,
                                   (const uint8_t*)c->row_trust.p, threshold, k, c->row_offset, (const float*)c->gbound.p,
@@ -412,7 +412,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
             SDK_TRY(sdk_reserve(c, c->dense, (size_t)m * P * 8));
             const int32_t* gl = (const int32_t*)c->fb_list.p + done;
             SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, gl, m, nullptr, P,
-                                     pool, (long long*)c->dense.p, seg_base, seg_stride));
+                                     pool, (long long*)c->dense.p, seg_grp));
             SDK_TRY(sdk_launch_select(c, (const long long*)c->dense.p, (const int64_t*)c->goff.p, gl, m, nullptr, P, pool,
                                       (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
                                       c->row_offset, nullptr, 0.f, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
@@ -650,8 +650,27 @@ int sdk_affinity_pooled_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg
     SDK_TRY(sdk_launch_normalize(c, d_seg, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
                                  bf16 ? (__nv_bfloat16*)c->seg_bf16.p : nullptr));
     if (path == 2) {
-        SDK_TRY(sdk_launch_poolgemm_dense(c, (const __nv_bfloat16*)c->seg_bf16.p, N, (const __nv_bfloat16*)c->seg_bf16.p, N,
-                                          Dp, (const int64_t*)c->goff.p, L, pool, d_out_nl));
+        SDK_CUDA(c, cudaMemsetAsync(d_out_nl, 0, (size_t)N * L * 4, c->stream));     // labels without segments: affinity 0
+        // mean pooling: accumulate-pooling with the label columns split (poolacc.cu plan B); max pooling: generic kernel
+        bool use_acc = c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048;
+        int64_t acc_steps = 0;
+        if (use_acc) {
+            int32_t lf = 0;
+            SDK_CUDA(c, cudaMemcpyAsync(&lf, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
+            SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+            if (lf & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
+            if (lf & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
+            SDK_TRY(sdk_poolacc_plan(c, (const int64_t*)c->goff.p, L, N, N, Dp, &acc_steps));
+            if (c->opt_acc != 2 && (double)acc_steps * 256.0 > 1.12 * (double)N + 1024.0) use_acc = false;
+        }
+        if (use_acc) {
+            c->last_path = 3;
+            SDK_TRY(sdk_launch_poolacc(c, d_seg, d_seg_label, 0, N, D, Dp, (const __nv_bfloat16*)c->seg_bf16.p, N,
+                                       (const int64_t*)c->goff.p, L, acc_steps, 1, 0.f, 0, nullptr, nullptr, d_out_nl, c->seg_il, nullptr));
+        } else {
+            SDK_TRY(sdk_launch_poolgemm_dense(c, (const __nv_bfloat16*)c->seg_bf16.p, N, (const __nv_bfloat16*)c->seg_bf16.p, N,
+                                              Dp, (const int64_t*)c->goff.p, L, pool, d_out_nl));
+        }
     } else {
         const void* ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
         SDK_TRY(sdk_reserve(c, c->qpool, (size_t)L * N * 8));

@@ -16,6 +16,14 @@ struct sdk_buf {               // grow-only device buffer
     size_t cap = 0;
 };
 
+// Accumulate-pooling layout (poolacc.cu): segment t of a label group lives at row  base + (t / c) * 256 + (t % c)  of the
+// group-interleaved bf16 matrix (c = accumulator columns the group is dealt over, round robin).
+struct PaGroup {
+    int64_t goff0;             // first segment of the group in the caller's (label-sorted) order
+    int32_t base;              // row of segment 0 in the interleaved matrix
+    int32_t c;                 // columns (parts) of the group, >= 1
+};
+
 struct sdk_prof_entry {
     double ms = 0.0;
     int64_t launches = 0;
@@ -50,7 +58,9 @@ struct sdk_ctx {
     sdk_buf cand_row, cand_val, cand_cnt, gbound, slot_cnt, slot_row, slot_val, slot_bound, range_g;
     sdk_buf fb_list, fb_rows;
     sdk_buf stage_seg[2], stage_lab[2];
-    sdk_buf pa_hist, pa_sorted, pa_pos, pa_sorted_pad, pa_blockT, pa_step0, pa_step_block, pa_seg_base;   // accumulate-pooling plan
+    sdk_buf pa_hist, pa_sorted, pa_pos, pa_col_group, pa_col_meta, pa_blockT, pa_step0, pa_grp, seg_il;   // accumulate-pooling plan + layout
+    int32_t pa_blocks = 0;     // blocks of 256 accumulator columns in the current plan
+    bool pa_split = false;     // current plan deals groups over several columns (col_meta != col_group)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     // results of the last identify
@@ -115,12 +125,11 @@ int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_
                              int64_t* d_goff, int32_t* d_flag);
 // exact canonical Q30 pooling.  rows: dense (cand_row == null: slot == bank row, nslot == P) or
 // sparse (cand_row[g*nslot + j] = bank row or -1).  glist (may be null) maps launch group -> group.
-// Segment t of group g lives at row seg_base[g] + t*seg_stride of d_seg_ops (seg_base == null: goff[g] + t).
+// Segment t of group g lives at row grp[g].base + (t / grp[g].c) * 256 + t % grp[g].c of d_seg_ops (grp == null: goff[g] + t).
 int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, int32_t is_bf16,
                      int32_t D, int32_t pitch, const int64_t* d_goff, const int32_t* d_glist,
                      int32_t ngroups, const int32_t* d_cand_row, int64_t nslot, int32_t pool,
-                     long long* d_qpool /*[ngroups,nslot]*/, const int64_t* d_seg_base = nullptr,
-                     int64_t seg_stride = 1);
+                     long long* d_qpool /*[ngroups,nslot]*/, const PaGroup* d_grp = nullptr);
 // select: speaker dedupe + threshold + ordered top-k (+ certificate on the sparse path)
 int sdk_launch_select(sdk_ctx* c, const long long* d_qpool, const int64_t* d_goff,
                       const int32_t* d_glist, int32_t ngroups, const int32_t* d_cand_row,
@@ -149,11 +158,14 @@ int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int6
 // tcgen05 accumulate-pooling GEMM (mean pooling, >= 128 label groups): normalises the RAW segments into the group-
 // interleaved bf16 layout (c->seg_bf16), pools inside the MMA accumulation; returns the row addressing of the layout
 int sdk_poolacc_applicable(int32_t Dp, int32_t G, int32_t pool);
-int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t* steps_out);
-int sdk_launch_poolacc_candidates(sdk_ctx* c, const float* d_seg_raw, int64_t N, int32_t D, int32_t Dp,
-                                  const __nv_bfloat16* d_bank, int64_t P, const int64_t* d_goff, int32_t G, int64_t S,
-                                  float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound,
-                                  const int64_t** d_seg_base_out, int64_t* seg_stride_out);
+// plan of the layout for G label groups / N segments scored against P rows; *steps_out = 256-row steps (one stream sync)
+int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, int64_t P, int32_t Dp, int64_t* steps_out);
+// mode 0: candidates (+ merge) into d_cand_row / d_gbound; mode 1: dense out[row, g] (config 5).  The interleaved
+// operands are written to `il` (grown as needed); *d_grp_out = per-group addressing for the canonical re-score.
+int sdk_launch_poolacc(sdk_ctx* c, const float* d_seg_raw, const int32_t* d_seg_label, int32_t label_base, int64_t N, int32_t D,
+                       int32_t Dp, const __nv_bfloat16* d_rows, int64_t P, const int64_t* d_goff, int32_t G, int64_t S,
+                       int32_t mode, float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, float* d_dense,
+                       sdk_buf& il, const PaGroup** d_grp_out);
 // tcgen05 pooled GEMM, dense output out[row, g] (config 5)
 int sdk_launch_poolgemm_dense(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P,
                               const __nv_bfloat16* d_cols, int64_t N, int32_t Dp,

@@ -32,12 +32,60 @@ __device__ __forceinline__ long long sdk_warp_max_ll(long long v) {
     return v;
 }
 
+// acc[r] += sum_d x[d] * bs[d][r] for r < A (fp64 fma chain over ascending d: the canonical order)
+template <int A, int RT, bool BF16>
+__device__ __forceinline__ void sdk_ex_dot(double (&acc)[RT], const double (&bs)[SDK_EX_DC][RT], const void* __restrict__ seg_ops,
+                                           int64_t srow, int32_t pitch, int d0, int dc) {
+    if (BF16) {
+        const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(seg_ops) + srow * (int64_t)pitch + d0;
+        int dd = 0;
+        for (; dd + 8 <= dc; dd += 8) {      // pitch % 8 == 0 and d0 % 8 == 0 -> 16-byte aligned
+            uint4 pk = __ldg(reinterpret_cast<const uint4*>(xr + dd));
+            uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                double x0 = (double)__uint_as_float(w[h] << 16);
+                double x1 = (double)__uint_as_float(w[h] & 0xffff0000u);
+#pragma unroll
+                for (int r = 0; r < A; ++r) acc[r] = fma(x0, bs[dd + 2 * h][r], acc[r]);
+#pragma unroll
+                for (int r = 0; r < A; ++r) acc[r] = fma(x1, bs[dd + 2 * h + 1][r], acc[r]);
+            }
+        }
+        for (; dd < dc; ++dd) {
+            double x = (double)__bfloat162float(xr[dd]);
+#pragma unroll
+            for (int r = 0; r < A; ++r) acc[r] = fma(x, bs[dd][r], acc[r]);
+        }
+    } else {
+        const float* xr = reinterpret_cast<const float*>(seg_ops) + srow * (int64_t)pitch + d0;
+        int dd = 0;
+        if ((pitch & 3) == 0) {
+            for (; dd + 4 <= dc; dd += 4) {
+                float4 pk = __ldg(reinterpret_cast<const float4*>(xr + dd));
+                float w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    double x = (double)w[h];
+#pragma unroll
+                    for (int r = 0; r < A; ++r) acc[r] = fma(x, bs[dd + h][r], acc[r]);
+                }
+            }
+        }
+        for (; dd < dc; ++dd) {
+            double x = (double)__ldg(xr + dd);
+#pragma unroll
+            for (int r = 0; r < A; ++r) acc[r] = fma(x, bs[dd][r], acc[r]);
+        }
+    }
+}
+
 template <int RT, bool BF16>
 __global__ void __launch_bounds__(SDK_EX_THREADS)
 k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops, int32_t D, int32_t pitch,
             const int64_t* __restrict__ goff, const int32_t* __restrict__ glist,
             const int32_t* __restrict__ cand_row, int64_t nslot, int32_t ntiles, int32_t pool,
-            long long* __restrict__ qpool, const int64_t* __restrict__ seg_base, int64_t seg_stride) {
+            long long* __restrict__ qpool, const PaGroup* __restrict__ grp) {
     __shared__ double bs[SDK_EX_DC][RT];
     __shared__ int32_t srow[RT];
     const int tid = threadIdx.x;
@@ -46,7 +94,10 @@ k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops,
     const int32_t g = glist ? glist[gi] : gi;
     const int64_t s0 = goff[g], s1 = goff[g + 1];
     if (s1 <= s0) return;
-    const int64_t rbase = seg_base ? seg_base[g] : s0;      // row of the group's first segment in seg_ops
+    // row of segment t in seg_ops: rbase + (t / gc) * gstep + t % gc   (plain layout: gc == 1, gstep == 1)
+    int64_t rbase = s0, gstep = 1;
+    int32_t gc = 1;
+    if (grp) { const PaGroup pg = grp[g]; rbase = pg.base; gc = pg.c; gstep = 256; }
     if (tid < RT) {
         int64_t slot = (int64_t)tile * RT + tid;
         int32_t r = -1;
@@ -54,15 +105,18 @@ k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops,
         srow[tid] = r;
     }
     __syncthreads();
-    bool any = false;
+    int nact = 0;                       // 1: only slot 0 holds a row (front-packed candidate list); else treat all RT
 #pragma unroll
-    for (int r = 0; r < RT; ++r) any |= srow[r] >= 0;
-    if (!any) return;
+    for (int r = 0; r < RT; ++r) nact += srow[r] >= 0 ? 1 : 0;
+    if (nact == 0) return;
+    if (!(nact == 1 && srow[0] >= 0)) nact = RT;
 
     const int nz = gridDim.y;
     for (int64_t cbase = s0 + (int64_t)blockIdx.y * SDK_EX_THREADS; cbase < s1; cbase += (int64_t)nz * SDK_EX_THREADS) {
         const int64_t s = cbase + tid;
         const bool valid = s < s1;
+        const int32_t t = (int32_t)(s - s0);
+        const int64_t srow_of = gc == 1 ? rbase + (int64_t)t * gstep : rbase + (int64_t)(t / gc) * gstep + (t % gc);
         double acc[RT];
 #pragma unroll
         for (int r = 0; r < RT; ++r) acc[r] = 0.0;
@@ -81,48 +135,10 @@ k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops,
             }
             __syncthreads();
             if (valid) {
-                if (BF16) {
-                    const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(seg_ops) + (rbase + (s - s0) * seg_stride) * (int64_t)pitch + d0;
-                    int dd = 0;
-                    for (; dd + 8 <= dc; dd += 8) {      // pitch % 8 == 0 and d0 % 8 == 0 -> 16-byte aligned
-                        uint4 pk = __ldg(reinterpret_cast<const uint4*>(xr + dd));
-                        uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            double x0 = (double)__uint_as_float(w[h] << 16);
-                            double x1 = (double)__uint_as_float(w[h] & 0xffff0000u);
-#pragma unroll
-                            for (int r = 0; r < RT; ++r) acc[r] = fma(x0, bs[dd + 2 * h][r], acc[r]);
-#pragma unroll
-                            for (int r = 0; r < RT; ++r) acc[r] = fma(x1, bs[dd + 2 * h + 1][r], acc[r]);
-                        }
-                    }
-                    for (; dd < dc; ++dd) {
-                        double x = (double)__bfloat162float(xr[dd]);
-#pragma unroll
-                        for (int r = 0; r < RT; ++r) acc[r] = fma(x, bs[dd][r], acc[r]);
-                    }
-                } else {
-                    const float* xr = reinterpret_cast<const float*>(seg_ops) + (rbase + (s - s0) * seg_stride) * (int64_t)pitch + d0;
-                    int dd = 0;
-                    if ((pitch & 3) == 0) {
-                        for (; dd + 4 <= dc; dd += 4) {
-                            float4 pk = __ldg(reinterpret_cast<const float4*>(xr + dd));
-                            float w[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                double x = (double)w[h];
-#pragma unroll
-                                for (int r = 0; r < RT; ++r) acc[r] = fma(x, bs[dd + h][r], acc[r]);
-                            }
-                        }
-                    }
-                    for (; dd < dc; ++dd) {
-                        double x = (double)__ldg(xr + dd);
-#pragma unroll
-                        for (int r = 0; r < RT; ++r) acc[r] = fma(x, bs[dd][r], acc[r]);
-                    }
-                }
+                // the candidate lists of the sparse path are front-packed and usually hold ONE row: do not spend
+                // RT fp64 fma chains on the empty slots
+                if (nact == 1) sdk_ex_dot<1, RT, BF16>(acc, bs, seg_ops, srow_of, pitch, d0, dc);
+                else sdk_ex_dot<RT, RT, BF16>(acc, bs, seg_ops, srow_of, pitch, d0, dc);
             }
         }
         // fixed point + integer pooling over this CTA's segments
@@ -153,8 +169,7 @@ __global__ void k_fill_ll(long long* p, int64_t n, long long v) {
 
 int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, int32_t is_bf16, int32_t D,
                      int32_t pitch, const int64_t* d_goff, const int32_t* d_glist, int32_t ngroups,
-                     const int32_t* d_cand_row, int64_t nslot, int32_t pool, long long* d_qpool, const int64_t* d_seg_base,
-                     int64_t seg_stride) {
+                     const int32_t* d_cand_row, int64_t nslot, int32_t pool, long long* d_qpool, const PaGroup* d_grp) {
     if (ngroups <= 0 || nslot <= 0) return SDK_OK;
     sdk_prof_scope ps(c, "exact");
     int64_t total = (int64_t)ngroups * nslot;
@@ -177,8 +192,8 @@ int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, 
     int ntiles = (int)ntiles64;
 #define SDK_EX_CASE(RTV)                                                                                   \
     do {                                                                                                   \
-        if (is_bf16) k_exact_q30<RTV, true><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool, d_seg_base, seg_stride); \
-        else k_exact_q30<RTV, false><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool, d_seg_base, seg_stride); \
+        if (is_bf16) k_exact_q30<RTV, true><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool, d_grp); \
+        else k_exact_q30<RTV, false><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool, d_grp); \
     } while (0)
     if (RT == 16) SDK_EX_CASE(16);
     else if (RT == 8) SDK_EX_CASE(8);

@@ -14,53 +14,67 @@ template <int NQ>
 __global__ void __launch_bounds__(256) k_normalize_vec(const float* __restrict__ x, int64_t n, int32_t D,
                                                        int32_t Dp, float* __restrict__ f32out,
                                                        __nv_bfloat16* __restrict__ bf16out) {
+    // R consecutive rows per warp iteration: all of their loads are in flight before the first norm is reduced
+    // (one 768-byte row per warp does not cover the HBM latency-bandwidth product)
+    constexpr int R = (NQ <= 2) ? 4 : (NQ <= 4 ? 2 : 1);
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int nq = D >> 2, nqp = Dp >> 2;
-    for (int64_t row = warp0; row < n; row += nwarps) {
-        const float4* xr = reinterpret_cast<const float4*>(x + row * (int64_t)D);
-        float4 v[NQ];
+    const int64_t n_runs = (n + R - 1) / R;
+    for (int64_t run = warp0; run < n_runs; run += nwarps) {
+        const int64_t row0 = run * R;
+        float4 v[R][NQ];
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            int q = lane + 32 * i;
-            v[i] = q < nq ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        double s = 0.0;
+        for (int r = 0; r < R; ++r) {
+            const bool live = row0 + r < n;
+            const float4* xr = reinterpret_cast<const float4*>(x + (live ? row0 + r : row0) * (int64_t)D);
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            double a = (double)v[i].x, b = (double)v[i].y, c = (double)v[i].z, d = (double)v[i].w;
-            s = fma(a, a, s);
-            s = fma(b, b, s);
-            s = fma(c, c, s);
-            s = fma(d, d, s);
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
-        float nrm = (float)sqrt(s);
-        float den = nrm > 1e-12f ? nrm : 1e-12f;
-        const float inv = __fdiv_rn(1.0f, den);
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            int q = lane + 32 * i;
-            float4 o;
-            o.x = __fmul_rn(v[i].x, inv);
-            o.y = __fmul_rn(v[i].y, inv);
-            o.z = __fmul_rn(v[i].z, inv);
-            o.w = __fmul_rn(v[i].w, inv);
-            if (f32out && q < nq) reinterpret_cast<float4*>(f32out + row * (int64_t)D)[q] = o;
-            if (bf16out && q < nqp) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);   // zero beyond D (v was zero)
-                __nv_bfloat162 hi = __floats2bfloat162_rn(o.z, o.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                reinterpret_cast<uint2*>(bf16out + row * (int64_t)Dp)[q] = pk;
+            for (int i = 0; i < NQ; ++i) {
+                int q = lane + 32 * i;
+                v[r][i] = (live && q < nq) ? __ldcs(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        if (bf16out) {   // padding chunks beyond what the NQ registers cover
-            for (int q = lane + 32 * NQ; q < nqp; q += 32)
-                reinterpret_cast<uint2*>(bf16out + row * (int64_t)Dp)[q] = make_uint2(0u, 0u);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+            if (row >= n) break;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                double a = (double)v[r][i].x, b = (double)v[r][i].y, c = (double)v[r][i].z, d = (double)v[r][i].w;
+                s = fma(a, a, s);
+                s = fma(b, b, s);
+                s = fma(c, c, s);
+                s = fma(d, d, s);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+            float nrm = (float)sqrt(s);
+            float den = nrm > 1e-12f ? nrm : 1e-12f;
+            const float inv = __fdiv_rn(1.0f, den);
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                int q = lane + 32 * i;
+                float4 o;
+                o.x = __fmul_rn(v[r][i].x, inv);
+                o.y = __fmul_rn(v[r][i].y, inv);
+                o.z = __fmul_rn(v[r][i].z, inv);
+                o.w = __fmul_rn(v[r][i].w, inv);
+                if (f32out && q < nq) reinterpret_cast<float4*>(f32out + row * (int64_t)D)[q] = o;
+                if (bf16out && q < nqp) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);   // zero beyond D (v was zero)
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(o.z, o.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    reinterpret_cast<uint2*>(bf16out + row * (int64_t)Dp)[q] = pk;
+                }
+            }
+            if (bf16out) {   // padding chunks beyond what the NQ registers cover
+                for (int q = lane + 32 * NQ; q < nqp; q += 32)
+                    reinterpret_cast<uint2*>(bf16out + row * (int64_t)Dp)[q] = make_uint2(0u, 0u);
+            }
         }
     }
 }
@@ -97,11 +111,12 @@ int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int
                          __nv_bfloat16* d_bf16) {
     if (n <= 0) return SDK_OK;
     sdk_prof_scope ps(c, "normalize");
-    int64_t blocks64 = (n + 7) / 8;
-    int blocks = (int)(blocks64 < (int64_t)c->sm_count * 8 ? blocks64 : (int64_t)c->sm_count * 8);
     bool vec = (D % 4 == 0) && (Dp % 4 == 0) && D <= 2048 && ((uintptr_t)d_x % 16 == 0);
     if (vec) {
         int nq = (D / 4 + 31) / 32;
+        const int R = nq <= 2 ? 4 : (nq <= 4 ? 2 : 1);
+        int64_t blocks64 = ((n + R - 1) / R + 7) / 8;
+        int blocks = (int)(blocks64 < (int64_t)c->sm_count * 8 ? blocks64 : (int64_t)c->sm_count * 8);
 #define SDK_NORM_CASE(NQ) k_normalize_vec<NQ><<<blocks, 256, 0, c->stream>>>(d_x, n, D, Dp, d_f32, d_bf16)
         if (nq <= 1) SDK_NORM_CASE(1);
         else if (nq <= 2) SDK_NORM_CASE(2);
@@ -110,6 +125,8 @@ int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int
         else SDK_NORM_CASE(16);
 #undef SDK_NORM_CASE
     } else {
+        int64_t blocks64 = (n + 7) / 8;
+        int blocks = (int)(blocks64 < (int64_t)c->sm_count * 8 ? blocks64 : (int64_t)c->sm_count * 8);
         k_normalize_generic<<<blocks, 256, 0, c->stream>>>(d_x, n, D, Dp, d_f32, d_bf16);
     }
     c->launches++;

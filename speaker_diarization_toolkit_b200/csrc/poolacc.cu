@@ -1,28 +1,36 @@
 // poolacc.cu -- K2c: mean pooling fused INTO the tensor-core accumulation ("accumulate-pooling").
 //
 // poolgemm.cu puts segments on the accumulator columns and pools them in the epilogue: every scored pair is read
-// out of TMEM once and added on the CUDA cores.  With D = 192 a 128x256 tile is only 12 MMAs (1536 tensor cycles)
+// out of TMEM once and added on the CUDA cores.  With D <= 256 a 128x256 tile is at most 16 MMAs (2048 tensor cycles)
 // but 128 KB of TMEM read-out + 32k FADDs, so the epilogue, not the tensor pipe, is the bound (profiles/r01_*).
 //
 // For MEAN pooling the sum over a label's segments can be done by the MMA itself.  Segments are laid out
-// "group interleaved": label groups are sorted by size and cut into blocks of 256 groups; step t of a block is the
-// 256-row slab holding the t-th segment of each of its 256 groups (zero rows once a group is exhausted).  Column j of
-// the accumulator tile therefore always belongs to group j of the block, and issuing the MMAs of step 0,1,..,T-1
-// into the SAME TMEM tile (accumulate = true across steps as well as across K) leaves
-//        D[row, j] = sum_t  bank[row] . seg_t(group j)            -- the pooled sum, every pair contracted --
-// after T*D/16 MMAs.  The tile is read out once per 256 GROUPS instead of once per 256 segments (~250x fewer TMEM
-// reads and epilogue instructions for hour-long recordings), the B ring needs no chunk residency, and the kernel
-// behaves like a large-K GEMM.  Sorting by size keeps the zero padding to a few percent.
+// "group interleaved": every label group owns c >= 1 accumulator COLUMNS of a block of 256 columns and deals its
+// segments over them round robin; step t of a block is the 256-row slab holding the t-th segment of each of its
+// columns (zero rows once a column is exhausted).  Issuing the MMAs of step 0,1,..,T-1 into the SAME TMEM tile
+// (accumulate = true across steps as well as across K) leaves
+//        D[row, j] = sum_t  bank[row] . seg_t(column j)           -- a partial pooled sum, every pair contracted --
+// after T*D/16 MMAs; the epilogue adds the c columns of a group and scales by 1/n.  The tile is read out once per
+// T*256 segments instead of once per 256 segments, the B ring needs no chunk residency, and the kernel behaves like a
+// large-K GEMM.
+//
+// Plans.  (A) many groups (> 2048): c = 1, groups sorted by size (counting sort), blocks of 256 sorted groups -- hour-
+// long recordings by the ten thousand (config 3).  (B) few groups: one CTA sorts the groups, simulates the packing
+// for ~60 candidate step caps T (c = ceil(n / T) columns per group, next-fit into blocks, no group straddles a block)
+// under a cost model (MMA steps + per-unit tile load / read-out + wave quantisation over the SMs) and emits the best
+// -- the 16-label affinity of config 5 and single-meeting shapes.  Zero padding stays at a few percent in both.
 //
 // Everything downstream is unchanged: the epilogue flushes per (group, 32 bank rows) candidate slots, k_pg_merge picks
 // the candidates, exact.cu re-scores them canonically (reading segments from the interleaved layout), select.cu
-// certifies.  Max pooling, few-group shapes and the dense (config 5) mode stay on poolgemm.cu.
+// certifies.  Max pooling stays on poolgemm.cu.
 #include "tcgen05.cuh"
 
-#define PA_NB 256                 // label groups per block == accumulator columns
+#define PA_NB 256                 // accumulator columns per block
 #define PA_BUCKETS 65536
+#define PA_SMALL_G 2048           // plan (B) up to this many label groups
+#define PA_NCAND 64               // candidate step caps evaluated by plan (B)
 
-// ---- planning: counting sort of the groups by (clipped) size, descending -------------------------------------
+// ---- plan (A): counting sort of the groups by (clipped) size, descending; one column per group ----------------------
 __global__ void k_pa_hist(const int64_t* __restrict__ goff, int32_t G, int32_t* __restrict__ hist) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
@@ -59,93 +67,185 @@ __global__ void k_pa_scatter(const int64_t* __restrict__ goff, int32_t G, int32_
     sorted_group[pos] = g;
     group_pos[g] = pos;
 }
-// per block of 256 sorted groups: T_b = largest group; step0 = exclusive prefix of T_b; plan_total[0] = total steps
+// per block of 256 sorted groups: T_b = largest group; column -> group table (-1 = padding column)
 __global__ void k_pa_blocks(const int64_t* __restrict__ goff, const int32_t* __restrict__ sorted_group, int32_t G, int32_t n_blocks,
-                            int32_t Gpad, int32_t* __restrict__ sorted_pad, int32_t* __restrict__ blockT, int64_t* __restrict__ step0,
-                            int64_t* __restrict__ plan_total) {
-    // phase 1: T_b
+                            int32_t* __restrict__ col_group, int32_t* __restrict__ blockT) {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += gridDim.x * blockDim.x) {
         int64_t m = 0;
         for (int j = 0; j < PA_NB; ++j) {
             int pos = b * PA_NB + j;
             int g = pos < G ? sorted_group[pos] : -1;
-            sorted_pad[pos] = g;
+            col_group[pos] = g;
             if (g >= 0) { int64_t n = goff[g + 1] - goff[g]; m = n > m ? n : m; }
         }
         blockT[b] = (int32_t)(m > 0x7fffffff ? 0x7fffffff : m);
     }
-    (void)Gpad;
-    (void)step0;
-    (void)plan_total;
 }
-__global__ void k_pa_steps(const int32_t* __restrict__ blockT, int32_t n_blocks, int64_t* __restrict__ step0, int64_t* __restrict__ plan_total) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    int64_t acc = 0;
-    for (int b = 0; b < n_blocks; ++b) { step0[b] = acc; acc += blockT[b]; }
-    step0[n_blocks] = acc;
-    plan_total[0] = acc;
-}
-// step -> block
-__global__ void k_pa_step_table(const int64_t* __restrict__ step0, int32_t n_blocks, int64_t S, int32_t* __restrict__ step_block) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    int lo = 0, hi = n_blocks;                 // last b with step0[b] <= s
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (step0[mid] <= s) lo = mid; else hi = mid;
+// step0 = exclusive prefix of T_b (one warp); plan_out = {total steps, blocks}
+__global__ void k_pa_steps(const int32_t* __restrict__ blockT, int32_t n_blocks, int64_t* __restrict__ step0, int64_t* __restrict__ plan_out) {
+    const int lane = threadIdx.x;
+    int64_t carry = 0;
+    for (int b0 = 0; b0 < n_blocks; b0 += 32) {
+        const int b = b0 + lane;
+        int64_t v = b < n_blocks ? blockT[b] : 0, incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int64_t o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        if (b < n_blocks) step0[b] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    step_block[s] = lo;
+    if (lane == 0) { step0[n_blocks] = carry; plan_out[0] = carry; plan_out[1] = n_blocks; }
 }
-// per group: first row and row stride of its segments in the interleaved matrix (for the canonical re-score)
-__global__ void k_pa_group_rows(const int32_t* __restrict__ group_pos, const int64_t* __restrict__ step0, int32_t G,
-                                int64_t* __restrict__ seg_base) {
+__global__ void k_pa_group_rows(const int64_t* __restrict__ goff, const int32_t* __restrict__ group_pos, const int64_t* __restrict__ step0,
+                                int32_t G, PaGroup* __restrict__ grp) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
     int pos = group_pos[g];
-    seg_base[g] = step0[pos / PA_NB] * PA_NB + (pos % PA_NB);
+    PaGroup r;
+    r.goff0 = goff[g];
+    const int64_t base = step0[pos / PA_NB] * PA_NB + (pos % PA_NB);
+    r.base = (int32_t)(base > 0x7fffffff ? 0x7fffffff : base);      // the host rejects layouts of more than 2^31-1 rows
+    r.c = 1;
+    grp[g] = r;
 }
 
-// ---- K1 (gather form): the interleaved bf16 matrix is written in runs of 8 consecutive destination rows per warp ---
-// (8 slots of one step: block b and step t are looked up once, lanes 0..7 resolve the 8 source segments in parallel,
-// then the 8 rows' 128-bit loads are all in flight before the first norm is reduced -- the per-row metadata chain
-// step -> block -> group -> goff would otherwise serialise ~4 dependent loads in front of every row).
-// Arithmetic = k_normalize_vec (canonical); padding slots become zero rows.
+// ---- plan (B): few groups, columns split; one CTA ------------------------------------------------------------------
+struct PaCost {
+    float step_cycles;      // tensor cycles of one 256-row step of a unit (KCH * 4 * MT MMAs of 128 x 256 x 16)
+    float unit_cycles;      // exposed per unit: bank tile load + TMEM read-out
+    int32_t RB, sms, t_min;
+};
+__device__ __forceinline__ int pa_cand_T(int i, int t_min) {      // geometric ladder, ratio 2^(1/4)
+    float t = (float)t_min * exp2f(0.25f * (float)i);
+    int T = (int)(t + 0.5f);
+    return T > 65535 ? 65535 : T;
+}
+__global__ void __launch_bounds__(1024)
+k_pa_plan_small(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t max_blocks, int32_t* __restrict__ col_group,
+                int32_t* __restrict__ col_meta, int32_t* __restrict__ blockT, int64_t* __restrict__ step0, int64_t* __restrict__ plan_out,
+                PaGroup* __restrict__ grp) {
+    __shared__ int32_t sn[PA_SMALL_G];          // group sizes
+    __shared__ int16_t sorder[PA_SMALL_G];      // groups by size, descending (ties: lower id first)
+    __shared__ int32_t scol0[PA_SMALL_G];       // first column of the group (global column index)
+    __shared__ int16_t scnt[PA_SMALL_G];        // columns of the group
+    __shared__ float scost[PA_NCAND];
+    __shared__ int sbest, s_nblocks;
+    const int tid = threadIdx.x;
+    for (int g = tid; g < G; g += blockDim.x) {
+        int64_t n = goff[g + 1] - goff[g];
+        sn[g] = (int32_t)(n > 0x7fffffff ? 0x7fffffff : n);
+    }
+    __syncthreads();
+    for (int g = tid; g < G; g += blockDim.x) {
+        const int32_t n = sn[g];
+        int rank = 0;
+        for (int j = 0; j < G; ++j) { const int32_t m = sn[j]; rank += (m > n || (m == n && j < g)) ? 1 : 0; }
+        sorder[rank] = (int16_t)g;
+    }
+    __syncthreads();
+    // every candidate step cap is simulated exactly (next-fit in size order) by one thread
+    if (tid < PA_NCAND) {
+        const int T = pa_cand_T(tid, pc.t_min);
+        int fill = 0, Tb = 0, nb = 0, Tmax = 0;
+        long long steps = 0;
+        for (int i = 0; i < G; ++i) {
+            const int32_t n = sn[sorder[i]];
+            int c = n > 0 ? (n + T - 1) / T : 1;
+            if (c > PA_NB) c = PA_NB;
+            const int s = n > 0 ? (n + c - 1) / c : 0;
+            if (fill + c > PA_NB) { steps += Tb; ++nb; Tmax = Tb > Tmax ? Tb : Tmax; fill = 0; Tb = 0; }
+            fill += c;
+            Tb = s > Tb ? s : Tb;
+        }
+        if (fill > 0) { steps += Tb; ++nb; Tmax = Tb > Tmax ? Tb : Tmax; }
+        const float units = (float)nb * (float)pc.RB;
+        const float waves = ceilf(units / (float)pc.sms);
+        // MMA time: perfectly spread steps, plus one longest unit of tail when the units do not fill the last wave
+        float cost = ((float)steps * (float)pc.RB / (float)pc.sms) * pc.step_cycles + waves * pc.unit_cycles;
+        const float frac = units / (float)pc.sms - floorf(units / (float)pc.sms);
+        if (units < (float)pc.sms) cost = (float)Tmax * pc.step_cycles + pc.unit_cycles;     // single partial wave
+        else if (frac > 0.f) cost += (1.f - frac) * (float)Tmax * pc.step_cycles * 0.5f;
+        if (nb > max_blocks) cost = 3.0e38f;
+        scost[tid] = cost;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0;
+        for (int i = 1; i < PA_NCAND; ++i) if (scost[i] < scost[best]) best = i;
+        if (!(scost[best] < 3.0e38f)) best = PA_NCAND - 1;      // cannot happen: the largest cap needs the fewest blocks
+        sbest = best;
+        const int T = pa_cand_T(best, pc.t_min);
+        int fill = 0, Tb = 0, nb = 0;
+        long long steps = 0;
+        for (int i = 0; i < G; ++i) {
+            const int g = sorder[i];
+            const int32_t n = sn[g];
+            int c = n > 0 ? (n + T - 1) / T : 1;
+            if (c > PA_NB) c = PA_NB;
+            const int s = n > 0 ? (n + c - 1) / c : 0;
+            if (fill + c > PA_NB) { blockT[nb] = Tb; step0[nb] = steps; steps += Tb; ++nb; fill = 0; Tb = 0; }
+            scol0[g] = nb * PA_NB + fill;
+            scnt[g] = (int16_t)c;
+            fill += c;
+            Tb = s > Tb ? s : Tb;
+        }
+        if (fill > 0) { blockT[nb] = Tb; step0[nb] = steps; steps += Tb; ++nb; }
+        step0[nb] = steps;
+        plan_out[0] = steps;
+        plan_out[1] = nb;
+        s_nblocks = nb;
+    }
+    __syncthreads();
+    const int ncol = s_nblocks * PA_NB;
+    for (int i = tid; i < ncol; i += blockDim.x) { col_group[i] = -1; col_meta[i] = -1; }
+    __syncthreads();
+    for (int g = tid; g < G; g += blockDim.x) {
+        const int c0 = scol0[g], c = scnt[g];
+        for (int j = 0; j < c; ++j) { col_group[c0 + j] = g; col_meta[c0 + j] = j == c - 1 ? g : -2; }
+        PaGroup r;
+        r.goff0 = goff[g];
+        const int64_t base = step0[c0 / PA_NB] * PA_NB + (c0 % PA_NB);
+        r.base = (int32_t)(base > 0x7fffffff ? 0x7fffffff : base);
+        r.c = c;
+        grp[g] = r;
+    }
+}
+
+// ---- K1, scatter form: canonical normalise of the label-sorted raw segments straight into the interleaved layout ----
+// Source ordered: a warp owns R consecutive raw rows, all of their 128-bit loads are issued before anything else, the
+// (label -> group record) lookups of lanes 0..R-1 fly alongside; each row is written as one contiguous 2*Dp-byte run at
+// its interleaved position.  Arithmetic = k_normalize_vec (canonical).
 template <int NQ>
 __global__ void __launch_bounds__(256)
-k_pa_normalize_gather(const float* __restrict__ x, int32_t D, int32_t Dp, const int64_t* __restrict__ goff,
-                      const int32_t* __restrict__ sorted_pad, const int32_t* __restrict__ step_block, const int64_t* __restrict__ step0,
-                      int64_t n_rows, __nv_bfloat16* __restrict__ out) {
-    constexpr int R = (NQ <= 2) ? 8 : (NQ <= 4 ? 4 : 1);       // rows per warp iteration (register budget)
+k_pa_normalize_scatter(const float* __restrict__ x, const int32_t* __restrict__ lab, int32_t label_base, int64_t n, int32_t D, int32_t Dp,
+                       const PaGroup* __restrict__ grp, __nv_bfloat16* __restrict__ out) {
+    constexpr int R = (NQ <= 2) ? 4 : (NQ <= 4 ? 2 : 1);       // rows per warp iteration (register budget)
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int nq = D >> 2, nqp = Dp >> 2;
-    const int64_t n_runs = n_rows / R;                          // n_rows is a multiple of 256
+    const int64_t n_runs = (n + R - 1) / R;
     for (int64_t run = warp0; run < n_runs; run += nwarps) {
         const int64_t row0 = run * R;
-        const int64_t step = row0 / PA_NB;
-        const int j0 = (int)(row0 - step * PA_NB);
-        const int b = step_block[step];
-        const int64_t t = step - step0[b];
-        int64_t my_src = -1;
-        if (lane < R) {
-            const int g = sorted_pad[b * PA_NB + j0 + lane];
-            if (g >= 0) {
-                const int64_t s0 = goff[g];
-                if (t < goff[g + 1] - s0) my_src = s0 + t;
-            }
-        }
         float4 v[R][NQ];
-        int64_t src[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            src[r] = __shfl_sync(0xffffffffu, my_src, r);
-            const float4* xr = reinterpret_cast<const float4*>(x + (src[r] < 0 ? 0 : src[r]) * (int64_t)D);
+            const bool live = row0 + r < n;
+            const float4* xr = reinterpret_cast<const float4*>(x + (live ? row0 + r : row0) * (int64_t)D);
 #pragma unroll
             for (int i = 0; i < NQ; ++i) {
                 int q = lane + 32 * i;
-                v[r][i] = (src[r] >= 0 && q < nq) ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[r][i] = (live && q < nq) ? __ldcs(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        }
+        int64_t my_dst = -1;
+        if (lane < R && row0 + lane < n) {
+            const int g = lab[row0 + lane] - label_base;
+            const PaGroup pg = grp[g];
+            const int32_t t = (int32_t)(row0 + lane - pg.goff0);
+            my_dst = pg.c == 1 ? (int64_t)pg.base + (int64_t)t * PA_NB : (int64_t)pg.base + (int64_t)(t / pg.c) * PA_NB + (t % pg.c);
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -163,7 +263,9 @@ k_pa_normalize_gather(const float* __restrict__ x, int32_t D, int32_t Dp, const 
             float nrm = (float)sqrt(s);
             float den = nrm > 1e-12f ? nrm : 1e-12f;
             const float inv = __fdiv_rn(1.0f, den);
-            uint2* orow = reinterpret_cast<uint2*>(out + (row0 + r) * (int64_t)Dp);
+            const int64_t dst = __shfl_sync(0xffffffffu, my_dst, r);
+            if (dst < 0) continue;                              // past the last row (uniform)
+            uint2* orow = reinterpret_cast<uint2*>(out + dst * (int64_t)Dp);
 #pragma unroll
             for (int i = 0; i < NQ; ++i) {
                 int q = lane + 32 * i;
@@ -173,18 +275,43 @@ k_pa_normalize_gather(const float* __restrict__ x, int32_t D, int32_t Dp, const 
                     uint2 pk;
                     pk.x = *reinterpret_cast<uint32_t*>(&lo);
                     pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                    orow[q] = pk;                               // zero rows: v == 0 -> 0 * inv == 0
+                    orow[q] = pk;
                 }
             }
             for (int q = lane + 32 * NQ; q < nqp; q += 32) orow[q] = make_uint2(0u, 0u);
         }
     }
 }
+// zero rows of the layout: steps of a column beyond its last segment (and every step of an unused column); warp per column
+__global__ void __launch_bounds__(256)
+k_pa_zero_pad(const int32_t* __restrict__ col_group, const int32_t* __restrict__ blockT, const int64_t* __restrict__ step0,
+              const int64_t* __restrict__ goff, const PaGroup* __restrict__ grp, int32_t n_cols, int32_t Dp, __nv_bfloat16* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int col = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (col >= n_cols) return;
+    const int b = col / PA_NB, slot = col % PA_NB;
+    const int32_t Tb = blockT[b];
+    const int64_t s0 = step0[b];
+    const int g = col_group[col];
+    int32_t len = 0;
+    if (g >= 0) {
+        const PaGroup pg = grp[g];
+        const int64_t n = goff[g + 1] - goff[g];
+        const int j = slot - (int)((int64_t)pg.base - s0 * PA_NB);          // part index of this column
+        len = n > j ? (int32_t)((n - j + pg.c - 1) / pg.c) : 0;
+    }
+    const int n16 = Dp >> 3;                                                // 16-byte pieces per row
+    for (int32_t t = len; t < Tb; ++t) {
+        uint4* orow = reinterpret_cast<uint4*>(out + ((s0 + t) * PA_NB + slot) * (int64_t)Dp);
+        for (int q = lane; q < n16; q += 32) orow[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
 struct PaParams {
-    PgParams pg;                   // slot arrays, P, tau, RB, g_base (= first SORTED POSITION of this batch)
-    const int32_t* sorted_pad;     // [n_blocks*256] label group of every block slot, -1 = padding
+    PgParams pg;                   // slot arrays, P, tau, RB, mode, g_base (= first COLUMN of this batch)
+    const int32_t* col_meta;       // [n_blocks*256] per column: label group g when it is the LAST column of g, -2 = inner
+                                   //                column of a group (more follow), -1 = unused column
     const int32_t* blockT;         // [n_blocks] steps of each block
     const int64_t* step0;          // [n_blocks+1] first step of each block
     int32_t block_lo, n_blocks;    // blocks [block_lo, block_lo + n_blocks) of this batch
@@ -313,18 +440,19 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
             const int64_t tile128 = (int64_t)rb * MT + rt;
             const int64_t row = tile128 * 128 + wq * 32 + lane;
             const int64_t nsub = (int64_t)p.RB * MT * 4;
-            // lane l holds the group ids / sizes of columns l, l+32, ..: 8 coalesced loads instead of 256 serial ones
+            // lane l holds the column records of columns l, l+32, ..: 8 coalesced loads instead of 256 serial ones
             int32_t gid[NC / 32];
             float ginv[NC / 32];
 #pragma unroll
             for (int i = 0; i < NC / 32; ++i) {
-                const int g = q.sorted_pad[b * NC + i * 32 + lane];
+                const int g = q.col_meta[b * NC + i * 32 + lane];
                 gid[i] = g;
                 const int64_t n = g >= 0 ? p.goff[g + 1] - p.goff[g] : 0;
                 ginv[i] = n > 0 ? 1.0f / (float)n : 0.f;
             }
             pg_mbar_wait(bar_t_full, uidx & 1u);
             pg_fence_after();
+            float run = 0.f;                                                          // sum over the columns of one group
 #pragma unroll
             for (int blk = 0; blk < NC / 32; ++blk) {
                 float v[32];
@@ -334,12 +462,20 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
                 for (int cc = 0; cc < 32; ++cc) {
                     const int g = __shfl_sync(0xffffffffu, gid[blk], cc);
                     const float inv = __shfl_sync(0xffffffffu, ginv[blk], cc);
-                    if (g < 0 || inv == 0.f) continue;                                // padding slot or empty group (uniform)
-                    const float val = v[cc] * inv;
+                    if (g == -1) continue;                                            // unused column (uniform)
+                    run += v[cc];
+                    if (g < 0) continue;                                              // inner column: the group goes on
+                    const float val = run * inv;
+                    run = 0.f;
+                    if (inv == 0.f) continue;                                         // empty group
+                    if (p.mode == 1) {
+                        if (row < p.P) p.dense_out[row * (int64_t)p.dense_ld + g] = val;
+                        continue;
+                    }
                     const bool pass = (val >= p.tau) && (row < p.P);
                     const uint32_t mpass = __ballot_sync(0xffffffffu, pass);
                     if (mpass == 0) continue;                                         // slot counts were zeroed before the launch
-                    const int64_t pos = (int64_t)b * NC + blk * 32 + cc - p.g_base;   // sorted position inside the batch
+                    const int64_t pos = (int64_t)b * NC + blk * 32 + cc - p.g_base;   // column inside the batch
                     pg_flush_write_call(&p, val, pass, mpass, pos * nsub + tile128 * 4 + wq, lane, row);
                 }
             }
@@ -387,103 +523,127 @@ static int pa_launch(sdk_ctx* c, int kch, const CUtensorMap& ta, const CUtensorM
 }
 
 int sdk_poolacc_applicable(int32_t Dp, int32_t G, int32_t pool) {
-    return sdk_poolgemm_supported(Dp) && pool == SDK_POOL_MEAN && G >= 128;
+    return sdk_poolgemm_supported(Dp) && pool == SDK_POOL_MEAN && G >= 1;
 }
 
-// Plan of the interleaved layout: groups sorted by size (counting sort), blocks of 256 groups, steps per block.
-// Returns the total number of 256-row steps in *steps_out (one stream sync); S*256 / N - 1 is the zero padding.
-int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t* steps_out) {
-    const int32_t n_blocks = (G + PA_NB - 1) / PA_NB;
-    const int32_t Gpad = n_blocks * PA_NB;
-    // ---- plan ----
-    SDK_TRY(sdk_reserve(c, c->pa_hist, (size_t)PA_BUCKETS * 4));
-    SDK_TRY(sdk_reserve(c, c->pa_sorted, (size_t)G * 4));
-    SDK_TRY(sdk_reserve(c, c->pa_pos, (size_t)G * 4));
-    SDK_TRY(sdk_reserve(c, c->pa_sorted_pad, (size_t)Gpad * 4));
-    SDK_TRY(sdk_reserve(c, c->pa_blockT, (size_t)n_blocks * 4));
-    SDK_TRY(sdk_reserve(c, c->pa_step0, (size_t)(n_blocks + 2) * 8));
-    SDK_TRY(sdk_reserve(c, c->pa_seg_base, (size_t)G * 8));
-    int32_t* hist = (int32_t*)c->pa_hist.p;
+// Plan of the interleaved layout (see the header).  Returns the total number of 256-row steps in *steps_out (one
+// stream sync); S*256 / N - 1 is the zero padding.  The plan stays in the context until the next call.
+int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, int64_t P, int32_t Dp, int64_t* steps_out) {
+    const bool small = G <= PA_SMALL_G;
+    const int kch = Dp / 64, MT = pa_mt_for(kch);
+    int32_t t_min = 8;
+    if (N / ((int64_t)PA_NB * 2048) > t_min) t_min = (int32_t)(N / ((int64_t)PA_NB * 2048));
+    const int64_t max_blocks64 = small ? 2 * (((int64_t)G + N / t_min) / PA_NB + 1) + 2 : ((int64_t)G + PA_NB - 1) / PA_NB;
+    if (max_blocks64 > (1 << 22)) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling plan: too many column blocks");
+    const int32_t max_blocks = (int32_t)max_blocks64;
+    SDK_TRY(sdk_reserve(c, c->pa_col_group, (size_t)max_blocks * PA_NB * 4));
+    SDK_TRY(sdk_reserve(c, c->pa_blockT, (size_t)max_blocks * 4));
+    SDK_TRY(sdk_reserve(c, c->pa_step0, (size_t)(max_blocks + 4) * 8));
+    SDK_TRY(sdk_reserve(c, c->pa_grp, (size_t)G * sizeof(PaGroup)));
     int64_t* step0 = (int64_t*)c->pa_step0.p;
-    int64_t* plan_total = step0 + n_blocks + 1;
-    {
+    int64_t* plan_out = step0 + max_blocks + 1;                     // {steps, blocks}
+    if (small) {
+        SDK_TRY(sdk_reserve(c, c->pa_col_meta, (size_t)max_blocks * PA_NB * 4));
+        PaCost pc;
+        pc.step_cycles = (float)(kch * 4 * MT * 128);
+        pc.unit_cycles = 6000.f + (float)(MT * kch) * 1400.f;       // TMEM read-out + bank tile load (16 KB tiles over TMA)
+        pc.RB = (int32_t)((P + (int64_t)MT * 128 - 1) / ((int64_t)MT * 128));
+        pc.sms = c->sm_count;
+        pc.t_min = t_min;
+        sdk_prof_scope ps(c, "plan");
+        k_pa_plan_small<<<1, 1024, 0, c->stream>>>(d_goff, G, pc, max_blocks, (int32_t*)c->pa_col_group.p, (int32_t*)c->pa_col_meta.p,
+                                                   (int32_t*)c->pa_blockT.p, step0, plan_out, (PaGroup*)c->pa_grp.p);
+        c->launches += 1;
+        SDK_CUDA(c, cudaGetLastError());
+    } else {
+        SDK_TRY(sdk_reserve(c, c->pa_hist, (size_t)PA_BUCKETS * 4));
+        SDK_TRY(sdk_reserve(c, c->pa_sorted, (size_t)G * 4));
+        SDK_TRY(sdk_reserve(c, c->pa_pos, (size_t)G * 4));
+        int32_t* hist = (int32_t*)c->pa_hist.p;
         sdk_prof_scope ps(c, "plan");
         SDK_CUDA(c, cudaMemsetAsync(hist, 0, (size_t)PA_BUCKETS * 4, c->stream));
         k_pa_hist<<<(G + 255) / 256, 256, 0, c->stream>>>(d_goff, G, hist);
         k_pa_scan<<<1, 1024, 0, c->stream>>>(hist);
         k_pa_scatter<<<(G + 255) / 256, 256, 0, c->stream>>>(d_goff, G, hist, (int32_t*)c->pa_sorted.p, (int32_t*)c->pa_pos.p);
-        k_pa_blocks<<<(n_blocks + 127) / 128, 128, 0, c->stream>>>(d_goff, (const int32_t*)c->pa_sorted.p, G, n_blocks, Gpad,
-                                                                   (int32_t*)c->pa_sorted_pad.p, (int32_t*)c->pa_blockT.p, step0, plan_total);
-        k_pa_steps<<<1, 32, 0, c->stream>>>((const int32_t*)c->pa_blockT.p, n_blocks, step0, plan_total);
-        k_pa_group_rows<<<(G + 255) / 256, 256, 0, c->stream>>>((const int32_t*)c->pa_pos.p, step0, G, (int64_t*)c->pa_seg_base.p);
+        k_pa_blocks<<<(max_blocks + 127) / 128, 128, 0, c->stream>>>(d_goff, (const int32_t*)c->pa_sorted.p, G, max_blocks,
+                                                                     (int32_t*)c->pa_col_group.p, (int32_t*)c->pa_blockT.p);
+        k_pa_steps<<<1, 32, 0, c->stream>>>((const int32_t*)c->pa_blockT.p, max_blocks, step0, plan_out);
+        k_pa_group_rows<<<(G + 255) / 256, 256, 0, c->stream>>>(d_goff, (const int32_t*)c->pa_pos.p, step0, G, (PaGroup*)c->pa_grp.p);
         c->launches += 6;
         SDK_CUDA(c, cudaGetLastError());
     }
-    int64_t S = 0;
-    SDK_CUDA(c, cudaMemcpyAsync(&S, plan_total, 8, cudaMemcpyDeviceToHost, c->stream));
+    int64_t h[2] = {0, 0};
+    SDK_CUDA(c, cudaMemcpyAsync(h, plan_out, 16, cudaMemcpyDeviceToHost, c->stream));
     SDK_CUDA(c, cudaStreamSynchronize(c->stream));
-    *steps_out = S;
+    if (h[1] < 0 || h[1] > max_blocks) return sdk_fail(c, SDK_ECUDA, "accumulate-pooling plan: inconsistent block count");
+    c->pa_blocks = (int32_t)h[1];
+    c->pa_split = small;
+    *steps_out = h[0];
     return SDK_OK;
 }
 
-// Normalises the raw segments into the planned interleaved layout, runs the accumulate-pooling GEMM and the slot
-// merge.  Outputs: candidate rows + bound per label group, and (seg_base, stride) of every group's segments in the
-// interleaved bf16 matrix c->seg_bf16 for the canonical re-score.  `S` = steps from sdk_poolacc_plan.
-int sdk_launch_poolacc_candidates(sdk_ctx* c, const float* d_seg_raw, int64_t N, int32_t D, int32_t Dp, const __nv_bfloat16* d_bank,
-                                  int64_t P, const int64_t* d_goff, int32_t G, int64_t S, float tau, int32_t ncand,
-                                  int32_t* d_cand_row, float* d_gbound, const int64_t** d_seg_base_out, int64_t* seg_stride_out) {
+// Normalises the raw segments into the planned interleaved layout (buffer `il`), runs the accumulate-pooling GEMM and,
+// in candidate mode, the slot merge.  `S` = steps from sdk_poolacc_plan (same goff, no other plan in between).
+int sdk_launch_poolacc(sdk_ctx* c, const float* d_seg_raw, const int32_t* d_seg_label, int32_t label_base, int64_t N, int32_t D,
+                       int32_t Dp, const __nv_bfloat16* d_rows, int64_t P, const int64_t* d_goff, int32_t G, int64_t S, int32_t mode,
+                       float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, float* d_dense, sdk_buf& il,
+                       const PaGroup** d_grp_out) {
     if (!sdk_poolacc_applicable(Dp, G, SDK_POOL_MEAN) || !c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path unavailable");
     if (P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "tcgen05 path: at most 2^31-1 bank rows");
     if (D % 4 != 0 || D > 2048) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path needs D % 4 == 0");
     const int kch = Dp / 64, MT = pa_mt_for(kch);
-    const int32_t n_blocks = (G + PA_NB - 1) / PA_NB;
+    const int32_t n_blocks = c->pa_blocks;
     int64_t* step0 = (int64_t*)c->pa_step0.p;
+    const int32_t* col_group = (const int32_t*)c->pa_col_group.p;
+    const int32_t* col_meta = c->pa_split ? (const int32_t*)c->pa_col_meta.p : col_group;    // c == 1: every column is a last column
+    const PaGroup* grp = (const PaGroup*)c->pa_grp.p;
     const int64_t n_rows = S * PA_NB;
     if (n_rows > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path: interleaved matrix exceeds 2^31-1 rows");
-    *d_seg_base_out = (const int64_t*)c->pa_seg_base.p;
-    *seg_stride_out = PA_NB;
+    if (d_grp_out) *d_grp_out = grp;
     if (S == 0) {
-        SDK_CUDA(c, cudaMemsetAsync(d_cand_row, 0xff, (size_t)G * ncand * 4, c->stream));
+        if (mode == 0) SDK_CUDA(c, cudaMemsetAsync(d_cand_row, 0xff, (size_t)G * ncand * 4, c->stream));
         return SDK_OK;
     }
-    SDK_TRY(sdk_reserve(c, c->pa_step_block, (size_t)S * 4));
-    SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)n_rows * Dp * 2));
-    k_pa_step_table<<<(unsigned)((S + 255) / 256), 256, 0, c->stream>>>(step0, n_blocks, S, (int32_t*)c->pa_step_block.p);
-    c->launches++;
-    // ---- K1, gather form ----
+    SDK_TRY(sdk_reserve(c, il, (size_t)n_rows * Dp * 2));
+    // ---- K1, scatter form + zero rows ----
     {
         sdk_prof_scope ps(c, "normalize");
-        int64_t blocks64 = (n_rows / 8 + 7) / 8;                    // a warp handles runs of up to 8 rows
+        int nq = (D / 4 + 31) / 32;
+        const int R = nq <= 2 ? 4 : (nq <= 4 ? 2 : 1);
+        int64_t blocks64 = ((N + R - 1) / R + 7) / 8;
         if (blocks64 < 1) blocks64 = 1;
         int blocks = (int)(blocks64 < (int64_t)c->sm_count * 8 ? blocks64 : (int64_t)c->sm_count * 8);
-        int nq = (D / 4 + 31) / 32;
-#define PA_NORM(NQ) k_pa_normalize_gather<NQ><<<blocks, 256, 0, c->stream>>>(d_seg_raw, D, Dp, d_goff, (const int32_t*)c->pa_sorted_pad.p, \
-        (const int32_t*)c->pa_step_block.p, step0, n_rows, (__nv_bfloat16*)c->seg_bf16.p)
+#define PA_NORM(NQ) k_pa_normalize_scatter<NQ><<<blocks, 256, 0, c->stream>>>(d_seg_raw, d_seg_label, label_base, N, D, Dp, grp, (__nv_bfloat16*)il.p)
         if (nq <= 1) PA_NORM(1);
         else if (nq <= 2) PA_NORM(2);
         else if (nq <= 4) PA_NORM(4);
         else if (nq <= 8) PA_NORM(8);
         else PA_NORM(16);
 #undef PA_NORM
-        c->launches++;
+        const int32_t n_cols = n_blocks * PA_NB;
+        k_pa_zero_pad<<<(n_cols + 7) / 8, 256, 0, c->stream>>>(col_group, (const int32_t*)c->pa_blockT.p, step0, d_goff, grp, n_cols, Dp,
+                                                               (__nv_bfloat16*)il.p);
+        c->launches += 2;
         SDK_CUDA(c, cudaGetLastError());
     }
-    // ---- GEMM + merge, in batches of blocks that keep the candidate slots under ~6 GB ----
+    // ---- GEMM (+ merge), in batches of blocks that keep the candidate slots under ~6 GB ----
     const int64_t rows_per_block = (int64_t)MT * 128;
     const int32_t RB = (int32_t)((P + rows_per_block - 1) / rows_per_block);
     const int32_t nsub = RB * MT * 4;
     const size_t per_group = (size_t)nsub * (PG_CS * 8 + 8);
-    int64_t bbatch = (int64_t)((size_t)(6144ull << 20) / (per_group * PA_NB));
-    if (bbatch < 1) bbatch = 1;
-    if (bbatch > n_blocks) bbatch = n_blocks;
-    SDK_TRY(sdk_reserve(c, c->slot_cnt, (size_t)bbatch * PA_NB * nsub * 4));
-    SDK_TRY(sdk_reserve(c, c->slot_bound, (size_t)bbatch * PA_NB * nsub * 4));
-    SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)bbatch * PA_NB * nsub * PG_CS * 4));
-    SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)bbatch * PA_NB * nsub * PG_CS * 4));
+    int64_t bbatch = n_blocks;
+    if (mode == 0) {
+        bbatch = (int64_t)((size_t)(6144ull << 20) / (per_group * PA_NB));
+        if (bbatch < 1) bbatch = 1;
+        if (bbatch > n_blocks) bbatch = n_blocks;
+        SDK_TRY(sdk_reserve(c, c->slot_cnt, (size_t)bbatch * PA_NB * nsub * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_bound, (size_t)bbatch * PA_NB * nsub * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)bbatch * PA_NB * nsub * PG_CS * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)bbatch * PA_NB * nsub * PG_CS * 4));
+    }
     CUtensorMap ta, tb;
-    SDK_TRY(pg_make_tmap(c, &ta, d_bank, P, Dp, 128));
-    SDK_TRY(pg_make_tmap(c, &tb, c->seg_bf16.p, n_rows, Dp, PA_NB));
-    (void)N;
+    SDK_TRY(pg_make_tmap(c, &ta, d_rows, P, Dp, 128));
+    SDK_TRY(pg_make_tmap(c, &tb, il.p, n_rows, Dp, PA_NB));
     for (int64_t ba = 0; ba < n_blocks; ba += bbatch) {
         const int64_t bb = std::min<int64_t>(n_blocks, ba + bbatch);
         PaParams q;
@@ -495,29 +655,30 @@ int sdk_launch_poolacc_candidates(sdk_ctx* c, const float* d_seg_raw, int64_t N,
         q.pg.g_base = (int32_t)(ba * PA_NB);
         q.pg.pool = SDK_POOL_MEAN;
         q.pg.tau = tau;
-        q.pg.mode = 0;
+        q.pg.mode = mode;
         q.pg.slot_cnt = (int32_t*)c->slot_cnt.p;
         q.pg.slot_row = (int32_t*)c->slot_row.p;
         q.pg.slot_val = (float*)c->slot_val.p;
         q.pg.slot_bound = (float*)c->slot_bound.p;
-        q.pg.dense_out = nullptr;
-        q.pg.dense_ld = 0;
-        q.sorted_pad = (const int32_t*)c->pa_sorted_pad.p;
+        q.pg.dense_out = d_dense;
+        q.pg.dense_ld = G;
+        q.col_meta = col_meta;
         q.blockT = (const int32_t*)c->pa_blockT.p;
         q.step0 = step0;
         q.block_lo = (int32_t)ba;
         q.n_blocks = (int32_t)(bb - ba);
         const int64_t n_units = (bb - ba) * RB;
         const int grid = (int)std::min<int64_t>(n_units, c->sm_count);
-        // slots of groups that are never flushed (padding / empty) must read as empty
-        SDK_CUDA(c, cudaMemsetAsync(c->slot_cnt.p, 0, (size_t)(bb - ba) * PA_NB * nsub * 4, c->stream));
+        // slots of columns that are never flushed (inner / unused columns, empty groups) must read as empty
+        if (mode == 0) SDK_CUDA(c, cudaMemsetAsync(c->slot_cnt.p, 0, (size_t)(bb - ba) * PA_NB * nsub * 4, c->stream));
         {
             sdk_prof_scope ps(c, "poolgemm");
             SDK_TRY(pa_launch(c, kch, ta, tb, q, grid));
         }
-        pg_launch_merge(c, d_goff, (int32_t)(ba * PA_NB), (int32_t)((bb - ba) * PA_NB), nsub, (const int32_t*)c->pa_sorted_pad.p, tau, ncand,
-                        d_cand_row, d_gbound);
-        SDK_CUDA(c, cudaGetLastError());
+        if (mode == 0) {
+            pg_launch_merge(c, d_goff, (int32_t)(ba * PA_NB), (int32_t)((bb - ba) * PA_NB), nsub, col_meta, tau, ncand, d_cand_row, d_gbound);
+            SDK_CUDA(c, cudaGetLastError());
+        }
     }
     return SDK_OK;
 }

@@ -11,8 +11,10 @@ from speaker_diarization_toolkit_b200 import _native, synth
 pytestmark = pytest.mark.gpu
 
 
-def run_gpu(ctx, case, dtype, pool, thr, k, path, cand=None, eps=None):
+def run_gpu(ctx, case, dtype, pool, thr, k, path, cand=None, eps=None, acc=0):
+    """acc: 0 = generic tcgen05 kernel (pooling in the epilogue), 1 = auto, 2 = force accumulate-pooling."""
     ctx.set_option("path", path)
+    ctx.set_option("acc", acc)
     ctx.set_option("cand", cand if cand is not None else 16)
     ctx.set_option("eps", eps if eps is not None else -1.0)
     ctx.bank_load(case.bank, case.row_speaker, case.row_trust, dtype=dtype)
@@ -114,15 +116,41 @@ def many_groups_case(seed, D, G=300, P_speakers=260, max_size=120):
 
 
 def test_accumulate_pooling_auto_choice(ctx):
-    """auto mode: uniform group sizes -> accumulate-pooling (path 3); a few outsized groups -> too much zero padding,
-    the generic tcgen05 kernel is chosen (path 2)."""
-    ctx.set_option("acc", 1)
+    """auto mode: D <= 256 (the generic kernel is epilogue-bound there) or thousands of groups -> accumulate-pooling
+    (path 3), also for a few outsized groups, whose columns are split; D = 512 with few groups, and max pooling,
+    stay on the generic tcgen05 kernel (path 2)."""
     even = synth.make_case(1, [40] * 512, 100, 64)
-    run_gpu(ctx, even, 1, 0, 0.354, 3, path=2)
+    run_gpu(ctx, even, 1, 0, 0.354, 3, path=2, acc=1)
     assert ctx.last_path()[0] == 3
     skew = synth.make_case(2, [2000] + [10] * 511, 100, 64)
-    run_gpu(ctx, skew, 1, 0, 0.354, 3, path=2)
+    run_gpu(ctx, skew, 1, 0, 0.354, 3, path=2, acc=1)
+    assert ctx.last_path()[0] == 3
+    run_gpu(ctx, skew, 1, 1, 0.354, 3, path=2, acc=1)
     assert ctx.last_path()[0] == 2
+    wide = synth.make_case(3, [40] * 64, 100, 512)
+    run_gpu(ctx, wide, 1, 0, 0.354, 3, path=2, acc=1)
+    assert ctx.last_path()[0] == 2
+
+
+@pytest.mark.parametrize("D,dtype,thr,k,counts", [
+    (256, 1, 0.354, 10, [250, 251, 0, 249, 260, 1, 244, 255]),                 # one meeting, 8 labels (config 2 shape)
+    (192, 1, 0.354, 4, [5000, 0, 3, 700, 64, 65, 1, 1300, 2, 256, 257, 40000]),  # outsized groups: up to 256 columns each
+    (64, 1, -1.0, 10, [33] * 40 + [0, 1, 2, 3]),
+    (512, 1, 0.2, 8, [900, 30, 31, 1200, 7]),
+    (128, 0, 0.354, 5, [400, 1, 0, 2000, 129, 77]),                            # fp32 bank: re-score from the plain fp32 copy
+    (320, 1, 0.354, 3, [1]),
+])
+def test_accumulate_pooling_split_columns(ctx, oracle, D, dtype, thr, k, counts):
+    """Few label groups: the planner deals every group over several accumulator columns (plan B), the epilogue adds
+    them up.  Same oracle, bit-exact, identical to the generic kernel."""
+    rng = np.random.default_rng(D)
+    case = synth.make_case(900 + D, counts, 180, D, rows_per_speaker=rng.choice([1, 2, 3], size=180), impostor_frac=0.2, neighbours=3)
+    gpu = run_gpu(ctx, case, dtype, 0, thr, k, path=2, acc=2)
+    path, nfb = ctx.last_path()
+    assert path == 3, "expected the accumulate-pooling kernel"
+    if thr > 0.3:
+        assert nfb == 0
+    assert_same(gpu, run_oracle(oracle, case, dtype, 0, thr, k), f"acc split D={D}")
 
 
 @pytest.mark.parametrize("D,dtype,thr,k", [(192, 1, 0.354, 4), (64, 1, 0.354, 10), (256, 1, -1.0, 10), (320, 1, 0.354, 5),
@@ -131,25 +159,20 @@ def test_accumulate_pooling_path(ctx, oracle, D, dtype, thr, k):
     """Mean pooling over >= 128 label groups runs the accumulate-pooling kernel (group-interleaved layout, pooled sum
     formed inside the MMA accumulation).  Same oracle, bit-exact; and identical to the generic tcgen05 kernel."""
     case = many_groups_case(500 + D, D, max_size=30 if D >= 320 else 60)
-    ctx.set_option("acc", 2)        # force it: this small ragged case pads far beyond the auto heuristic's 12 %
-    gpu = run_gpu(ctx, case, dtype, 0, thr, k, path=2)
+    gpu = run_gpu(ctx, case, dtype, 0, thr, k, path=2, acc=2)   # forced: this small ragged case pads beyond the auto limit
     path, nfb = ctx.last_path()
     assert path == 3, "expected the accumulate-pooling kernel"
     if thr > 0.3:
         assert nfb == 0
     ref = run_oracle(oracle, case, dtype, 0, thr, k)
     assert_same(gpu, ref, f"acc D={D}")
-    ctx.set_option("acc", 0)
-    try:
-        gpu2 = run_gpu(ctx, case, dtype, 0, thr, k, path=2)
-        assert ctx.last_path()[0] == 2
-    finally:
-        ctx.set_option("acc", 1)
+    gpu2 = run_gpu(ctx, case, dtype, 0, thr, k, path=2, acc=0)
+    assert ctx.last_path()[0] == 2
     assert_same(gpu2, ref, f"generic D={D}")
 
 
-@pytest.mark.parametrize("path", [1, 2])
-def test_host_pipeline_chunks(ctx, oracle, path):
+@pytest.mark.parametrize("path,acc", [(1, 0), (2, 0), (2, 2)])
+def test_host_pipeline_chunks(ctx, oracle, path, acc):
     """The host-buffer call cuts big batches at label boundaries and overlaps H2D with scoring; force many small
     chunks (1 MB) including empty labels at chunk edges and check the stitched result."""
     rng = np.random.default_rng(8)
@@ -157,7 +180,7 @@ def test_host_pipeline_chunks(ctx, oracle, path):
     case = synth.make_case(88, counts, 300, 192, rows_per_speaker=rng.choice([1, 2], size=300), impostor_frac=0.2)
     ctx.set_option("chunk_mb", 1)
     try:
-        gpu = run_gpu(ctx, case, 1, 0, 0.354, 6, path=path)
+        gpu = run_gpu(ctx, case, 1, 0, 0.354, 6, path=path, acc=acc)
     finally:
         ctx.set_option("chunk_mb", 512)
     assert_same(gpu, run_oracle(oracle, case, 1, 0, 0.354, 6), "pipelined host path")
@@ -210,8 +233,11 @@ def test_assign_matches_oracle_and_python(ctx, oracle):
 def test_affinity_pooled(ctx, oracle, dtype, pool, path):
     case = synth.config5(N=1500, L=7, D=256)
     ctx.set_option("path", path)
+    ctx.set_option("acc", 1)
     nl, ll = ctx.affinity_pooled(case.seg, case.seg_label, case.G, dtype=dtype, pool=pool)
     ref = oracle.affinity(case.seg, case.goff, mode=dtype, pool=pool)
+    if path == 2:
+        assert ctx.last_path()[0] == (3 if pool == 0 else 2), "mean pooling runs the accumulate-pooling kernel"
     if path == 1:
         assert np.array_equal(nl.view(np.uint32), ref.view(np.uint32))
     else:
@@ -223,6 +249,26 @@ def test_affinity_pooled(ctx, oracle, dtype, pool, path):
     assert np.array_equal(ll, ll_ref.astype(np.float32))
     # every segment is closest to its own label on planted data
     assert (nl.argmax(axis=1) == case.seg_label).mean() > 0.99
+
+
+def test_affinity_pooled_skewed_labels_and_empty_label(ctx, oracle):
+    """config-5 shape with Zipf-skewed labels and a label without segments (its column of the output is 0)."""
+    counts = [1400, 0, 700, 350, 12, 1, 233, 90]
+    case = synth.make_case(55, counts, 8, 256, impostor_frac=0.0)
+    ctx.set_option("path", 2)
+    ctx.set_option("acc", 1)
+    nl, ll = ctx.affinity_pooled(case.seg, case.seg_label, case.G, dtype=1, pool=0)
+    assert ctx.last_path()[0] == 3
+    ref = oracle.affinity(case.seg, case.goff, mode=1, pool=0)
+    np.testing.assert_allclose(nl, ref, rtol=0, atol=2e-5)
+    assert (nl[:, 1] == 0).all()
+    ctx.set_option("acc", 0)
+    try:
+        nl2, _ = ctx.affinity_pooled(case.seg, case.seg_label, case.G, dtype=1, pool=0)
+        assert ctx.last_path()[0] == 2
+    finally:
+        ctx.set_option("acc", 1)
+    np.testing.assert_allclose(nl2, ref, rtol=0, atol=2e-5)
 
 
 def test_errors(ctx):
