@@ -57,6 +57,18 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic(workload, kernel_label, same_launch_shape):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this very workload
+    (tools/ncu_summary.py --traffic-key); None when the launch being timed is not the one that was captured."""
+    tfile = ROOT / "profiles" / "roofline_traffic.json"
+    if not same_launch_shape or not tfile.exists():
+        return None
+    ent = json.loads(tfile.read_text()).get(workload)
+    if not ent or ent.get("kernel", "?") not in kernel_label:
+        return None
+    return ent["dram_bytes_per_launch"]
+
+
 # ---- synthetic batch (group counts on the host, embeddings generated on the device) -------------------
 def group_counts(cfg, scale):
     rng = np.random.default_rng(cfg["seed"])
@@ -274,7 +286,8 @@ def run_cfg5(args, cfg):
     kname = "k_poolacc (tcgen05, label columns split, mean pooling inside the MMA accumulation, dense output)" if ctx.last_path()[0] == 3 \
         else f"k_poolgemm (tcgen05 cta_group::{args.cta_group}, dense pooled output)"
     roof = {"kernel": kname, "bound": "tensor", "achieved": ach,
-            "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+            "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+            "traffic": ncu_traffic("cfg5", kname, args.scale == 1.0),
             "peak_source": f"{pk_src} bf16 burst (kernel timed alone, ~1 ms)", "avg_launch_ms": avg_ms}
     hs, hl = seg.cpu().numpy(), lab.cpu().numpy()
     ctx.affinity_pooled(hs, hl, L, dtype=1, pool=0)
@@ -397,6 +410,7 @@ def main():
         step_dev()
     barrier()
     path, nfb = ctx.last_path()
+    nretry = ctx.last_retry()
     ctx.profile_reset()
     l0 = ctx.launch_count()
     clocks = Clocks(local_rank)
@@ -441,9 +455,7 @@ def main():
                 "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_src} copy bandwidth",
                 "avg_launch_ms": avg_ms, "share_of_step": gms / tot_prof,
                 "note": "latency-bound shape: the fraction is informational (SURVEY 8d)"}
-    tfile = ROOT / "profiles" / "roofline_traffic.json"
-    if tfile.exists():
-        roof["traffic"] = json.loads(tfile.read_text()).get(args.workload)
+    roof["traffic"] = ncu_traffic(args.workload, roof["kernel"], args.scale == 1.0 and (world == 1 or sharded))
 
     # ---- e2e: host buffers through the host-pointer C-ABI call ----
     e2e = None
@@ -505,7 +517,7 @@ def main():
                            "segments_per_gpu": N, "label_groups_per_gpu": G, "bank_rows_per_gpu": P, "dim": D, "k": cfg["k"],
                            "threshold": cfg["thr"], "pool": "mean", "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
                            "l2": "inputs larger than L2 (no flush needed)" if N * D * 2 > 200e6 else "inputs fit L2 (latency-bound shape)",
-                           "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{args.cta_group}", 3: "tcgen05 accumulate-pooling"}.get(path, str(path)), "certificate_fallback_groups": nfb, "scale": args.scale},
+                           "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{args.cta_group}", 3: "tcgen05 accumulate-pooling"}.get(path, str(path)), "certificate_fallback_groups": nfb, "certificate_retry_groups": nretry, "scale": args.scale},
                 "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
                 "kernel_ms_per_step": {n: v[0] / args.steps for n, v in prof.items()}}
         print(json.dumps(line))

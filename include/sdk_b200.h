@@ -155,6 +155,9 @@ int64_t sdk_launch_count(sdk_ctx* ctx);
  * (mean pooling inside the MMA accumulation); *n_fallback = label groups whose
  * top-k certificate failed and were re-done exhaustively */
 int sdk_last_path(sdk_ctx* ctx, int32_t* path, int64_t* n_fallback);
+/* label groups of the last identify whose top-k certificate failed on the first candidate list and was settled by the
+ * second, wider one (64 candidates) without an exhaustive pass */
+int64_t sdk_last_retry(sdk_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,7 @@ EXPORTS = [
     "sdk_set_option", "sdk_bank_load", "sdk_bank_load_dev", "sdk_identify", "sdk_identify_dev", "sdk_assign",
     "sdk_results_fetch", "sdk_affinity_pooled", "sdk_affinity_pooled_dev", "sdk_sync", "sdk_stream",
     "sdk_timer_start", "sdk_timer_stop", "sdk_profile_get", "sdk_profile_reset", "sdk_launch_count", "sdk_last_path",
+    "sdk_last_retry",
 ]
 
 
@@ -79,6 +80,8 @@ def load() -> C.CDLL:
     lib.sdk_launch_count.argtypes = [vp]
     lib.sdk_launch_count.restype = i64
     lib.sdk_last_path.argtypes = [vp, C.POINTER(i32), C.POINTER(i64)]
+    lib.sdk_last_retry.argtypes = [vp]
+    lib.sdk_last_retry.restype = i64
     _lib = lib
     return lib
 
@@ -226,6 +229,9 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.sdk_launch_count(self.h))
+
+    def last_retry(self) -> int:
+        return int(self.lib.sdk_last_retry(self.h))
 
     def last_path(self):
         p, f = C.c_int32(), C.c_int64()

@@ -160,7 +160,7 @@ void sdk_destroy(sdk_ctx* c) {
                        &c->out_count, &c->out_trust, &c->out_spk, &c->as_idx, &c->as_score, &c->as_conf,
                        &c->as_cidx, &c->as_cscore, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
                        &c->stage_lab[0], &c->stage_lab[1], &c->pa_hist, &c->pa_sorted, &c->pa_pos, &c->pa_col_group,
-                       &c->pa_col_meta, &c->pa_blockT, &c->pa_step0, &c->pa_grp, &c->seg_il};
+                       &c->pa_col_meta, &c->pa_blockT, &c->pa_step0, &c->pa_grp, &c->seg_il, &c->fb_list2, &c->cand_row2, &c->qpool2};
     for (sdk_buf* b : bufs) sdk_release(*b);
     for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int b = 0; b < 2; ++b) {
@@ -365,7 +365,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
                                  pool, (long long*)c->qpool.p));
         SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L, nullptr, P, pool,
                                   (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
-                                  c->row_offset, nullptr, 0.f, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
+                                  c->row_offset, nullptr, 0.f, nullptr, 0, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
     } else {
         // stage A: tcgen05 pooled GEMM -> per-label candidate rows + bound on everything else.
         // eps bounds |approx - canonical|: bf16 operands are shared (exact products, fp32 accumulate);
@@ -378,12 +378,15 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         SDK_TRY(sdk_reserve(c, c->cand_row, (size_t)L * ncand * 4));
         SDK_TRY(sdk_reserve(c, c->gbound, (size_t)L * 4));
         SDK_TRY(sdk_reserve(c, c->fb_list, (size_t)L * 4));
+        const PaGroup* acc_grp = nullptr;       // accumulation chain per column (certificate margin of giant groups)
+        c->slot_g0 = c->slot_g1 = 0;
         if (use_acc) {
             const PaGroup* ig = nullptr;
             SDK_TRY(sdk_launch_poolacc(c, d_seg, d_seg_label, label_base, N, D, Dp, (const __nv_bfloat16*)c->bank_bf16.p, P,
                                        (const int64_t*)c->goff.p, L, acc_steps, 0, tau, ncand, (int32_t*)c->cand_row.p,
                                        (float*)c->gbound.p, nullptr, c->seg_bf16, &ig));
             if (bf16) seg_grp = ig;                            // bf16 operands live in the interleaved matrix
+            acc_grp = ig;
         } else {
             SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p,
                                                    N, Dp, (const int64_t*)c->goff.p, L, pool, tau, ncand,
@@ -397,7 +400,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L,
                                   (const int32_t*)c->cand_row.p, ncand, pool, (const int32_t*)c->row_speaker.p,
                                   (const uint8_t*)c->row_trust.p, threshold, k, c->row_offset, (const float*)c->gbound.p,
-                                  eps, d_flags + 1, (int32_t*)c->fb_list.p, o_row, o_score, o_count, o_trust, o_spk));
+                                  eps, acc_grp, Dp / 16, d_flags + 1, (int32_t*)c->fb_list.p, o_row, o_score, o_count, o_trust, o_spk));
         // groups whose certificate failed are re-done exhaustively in the canonical arithmetic
         int32_t hf[2] = {0, 0};
         SDK_CUDA(c, cudaMemcpyAsync(hf, d_flags, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -405,17 +408,41 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         if (hf[0] & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
         if (hf[0] & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
         int32_t nfb = hf[1];
+        const int32_t* fb = (const int32_t*)c->fb_list.p;
+        // second chance (generic kernel, all groups' candidate slots still live): re-merge the failed groups with the
+        // widest candidate list, re-score, certify again -- an exhaustive pass over a 125k-row shard costs ~2 ms per
+        // group, this costs microseconds
+        if (nfb > 0 && ncand < 64 && !use_acc && c->slot_g0 == 0 && c->slot_g1 == L) {
+            const int32_t ncand2 = 64;
+            SDK_TRY(sdk_reserve(c, c->cand_row2, (size_t)nfb * ncand2 * 4));
+            SDK_TRY(sdk_reserve(c, c->qpool2, (size_t)nfb * ncand2 * 8));
+            SDK_TRY(sdk_reserve(c, c->fb_list2, (size_t)L * 4));
+            SDK_CUDA(c, cudaMemsetAsync(d_flags + 1, 0, 4, c->stream));
+            SDK_TRY(sdk_launch_poolgemm_remerge(c, (const int64_t*)c->goff.p, fb, nfb, tau, ncand2, (int32_t*)c->cand_row2.p,
+                                                (float*)c->gbound.p));
+            SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, fb, nfb,
+                                     (const int32_t*)c->cand_row2.p, ncand2, pool, (long long*)c->qpool2.p, seg_grp));
+            SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool2.p, (const int64_t*)c->goff.p, fb, nfb,
+                                      (const int32_t*)c->cand_row2.p, ncand2, pool, (const int32_t*)c->row_speaker.p,
+                                      (const uint8_t*)c->row_trust.p, threshold, k, c->row_offset, (const float*)c->gbound.p,
+                                      eps, acc_grp, Dp / 16, d_flags + 1, (int32_t*)c->fb_list2.p, o_row, o_score, o_count, o_trust, o_spk));
+            SDK_CUDA(c, cudaMemcpyAsync(hf, d_flags, 8, cudaMemcpyDeviceToHost, c->stream));
+            SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+            c->last_retry += nfb;
+            nfb = hf[1];
+            fb = (const int32_t*)c->fb_list2.p;
+        }
         c->last_fallback += nfb;
         const int32_t chunk = (int32_t)std::max<int64_t>(1, std::min<int64_t>(nfb, (int64_t)(1u << 28) / std::max<int64_t>(P, 1)));
         for (int32_t done = 0; done < nfb; done += chunk) {
             int32_t m = std::min(chunk, nfb - done);
             SDK_TRY(sdk_reserve(c, c->dense, (size_t)m * P * 8));
-            const int32_t* gl = (const int32_t*)c->fb_list.p + done;
+            const int32_t* gl = fb + done;
             SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, gl, m, nullptr, P,
                                      pool, (long long*)c->dense.p, seg_grp));
             SDK_TRY(sdk_launch_select(c, (const long long*)c->dense.p, (const int64_t*)c->goff.p, gl, m, nullptr, P, pool,
                                       (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
-                                      c->row_offset, nullptr, 0.f, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
+                                      c->row_offset, nullptr, 0.f, nullptr, 0, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
         }
         SDK_CUDA(c, cudaMemsetAsync(d_flags + 1, 0, 4, c->stream));   // fallback counter consumed
     }
@@ -429,6 +456,7 @@ int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label,
     c->have_results = false;
     c->have_assign = false;
     c->last_fallback = 0;
+    c->last_retry = 0;
     SDK_TRY(sdk_reserve_results(c, L, k));
     SDK_TRY(sdk_identify_core(c, d_seg, d_seg_label, N, L, 0, pool, threshold, k));
     c->L = L; c->k = k; c->N = N;
@@ -488,6 +516,7 @@ int sdk_identify(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t
     c->have_results = false;
     c->have_assign = false;
     c->last_fallback = 0;
+    c->last_retry = 0;
     const int32_t D = c->D;
     SDK_TRY(sdk_reserve_results(c, L, k));
     const size_t row_bytes = (size_t)D * 4;
@@ -758,6 +787,7 @@ int sdk_profile_reset(sdk_ctx* c) {
     return SDK_OK;
 }
 int64_t sdk_launch_count(sdk_ctx* c) { return c ? c->launches : 0; }
+int64_t sdk_last_retry(sdk_ctx* c) { return c ? c->last_retry : 0; }
 int sdk_last_path(sdk_ctx* c, int32_t* path, int64_t* n_fallback) {
     if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
     if (path) *path = c->last_path;

@@ -56,7 +56,8 @@ struct sdk_ctx {
     // segments / scratch
     sdk_buf seg_raw, seg_lab, seg_f32, seg_bf16, goff, qpool, dense, flags;
     sdk_buf cand_row, cand_val, cand_cnt, gbound, slot_cnt, slot_row, slot_val, slot_bound, range_g;
-    sdk_buf fb_list, fb_rows;
+    sdk_buf fb_list, fb_rows, fb_list2, cand_row2, qpool2;
+    int32_t slot_g0 = 0, slot_g1 = 0, slot_nsub = 0;   // label groups whose candidate slots (generic tcgen05 kernel) are live
     sdk_buf stage_seg[2], stage_lab[2];
     sdk_buf pa_hist, pa_sorted, pa_pos, pa_col_group, pa_col_meta, pa_blockT, pa_step0, pa_grp, seg_il;   // accumulate-pooling plan + layout
     int32_t pa_blocks = 0;     // blocks of 256 accumulator columns in the current plan
@@ -72,7 +73,8 @@ struct sdk_ctx {
     sdk_buf gather;            // NCCL all-gather staging
     void* nccl_comm = nullptr;
     int last_path = 0;
-    int64_t last_fallback = 0;
+    int64_t last_fallback = 0;   // label groups re-done exhaustively (certificate failed twice)
+    int64_t last_retry = 0;      // label groups whose certificate needed the second, wider candidate list
     int64_t launches = 0;
     std::map<std::string, sdk_prof_entry> prof;
     std::vector<sdk_pending_ev> pending;
@@ -135,7 +137,8 @@ int sdk_launch_select(sdk_ctx* c, const long long* d_qpool, const int64_t* d_gof
                       const int32_t* d_glist, int32_t ngroups, const int32_t* d_cand_row,
                       int64_t nslot, int32_t pool, const int32_t* d_row_speaker,
                       const uint8_t* d_row_trust, double threshold, int32_t k, int64_t row_offset,
-                      const float* d_gbound /*null on dense*/, float eps, int32_t* d_fb_count,
+                      const float* d_gbound /*null on dense*/, float eps, const PaGroup* d_grp, int32_t upd_per_seg,
+                      int32_t* d_fb_count,
                       int32_t* d_fb_list, int64_t* d_out_row, float* d_out_score,
                       int32_t* d_out_count, uint8_t* d_out_trust, int32_t* d_out_spk);
 int sdk_launch_assign(sdk_ctx* c, const int64_t* d_row, const float* d_score,
@@ -155,6 +158,8 @@ int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int6
                                    const int64_t* d_goff, int32_t G, int32_t pool, float tau,
                                    int32_t ncand, int32_t* d_cand_row /*[G,ncand]*/,
                                    float* d_gbound /*[G]*/);
+int sdk_launch_poolgemm_remerge(sdk_ctx* c, const int64_t* d_goff, const int32_t* d_glist, int32_t ngroups, float tau,
+                                int32_t ncand, int32_t* d_cand_row, float* d_gbound);
 // tcgen05 accumulate-pooling GEMM (mean pooling, >= 128 label groups): normalises the RAW segments into the group-
 // interleaved bf16 layout (c->seg_bf16), pools inside the MMA accumulation; returns the row addressing of the layout
 int sdk_poolacc_applicable(int32_t Dp, int32_t G, int32_t pool);

@@ -213,6 +213,151 @@ k_pa_plan_small(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t 
     }
 }
 
+// ---- plan (B1): at most PA_BINS_G groups -- balanced bins, one step count per block ------------------------------------
+// With a handful of groups (the 16 labels of config 5, the 8 labels of one meeting) next-fit leaves blocks part empty and
+// the number of units rarely divides over the SMs.  Here the groups are dealt into nb bins (= blocks) by LPT, every
+// block gets ITS OWN step count T_b = min T with sum_g max(1, ceil(n_g / T)) <= 256 -- so every block is full -- and
+// nb is chosen by simulating the kernel's static unit -> CTA assignment (wave quantisation included).  Warp per candidate.
+#define PA_BINS_G 256
+#define PA_MAX_BINS 64
+__device__ __forceinline__ void pa_warp_argmin(long long& v, int& idx) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const long long ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+}
+__global__ void __launch_bounds__(1024)
+k_pa_plan_bins(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t* __restrict__ col_group, int32_t* __restrict__ col_meta,
+               int32_t* __restrict__ blockT, int64_t* __restrict__ step0, int64_t* __restrict__ plan_out, PaGroup* __restrict__ grp) {
+    __shared__ int32_t sn[PA_BINS_G];
+    __shared__ int16_t sorder[PA_BINS_G];
+    __shared__ int16_t sbin[PA_BINS_G];
+    __shared__ int32_t sT[PA_MAX_BINS];
+    __shared__ int32_t sTw[32][PA_MAX_BINS];   // per warp: estimated T_b of the candidate being evaluated
+    __shared__ float scost[PA_MAX_BINS];
+    __shared__ int s_nb;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int g = tid; g < G; g += blockDim.x) {
+        int64_t n = goff[g + 1] - goff[g];
+        sn[g] = (int32_t)(n > 0x7fffffff ? 0x7fffffff : n);
+    }
+    __syncthreads();
+    for (int g = tid; g < G; g += blockDim.x) {
+        const int32_t n = sn[g];
+        int rank = 0;
+        for (int j = 0; j < G; ++j) { const int32_t m = sn[j]; rank += (m > n || (m == n && j < g)) ? 1 : 0; }
+        sorder[rank] = (int16_t)g;
+    }
+    __syncthreads();
+    const int nb_max = G < PA_MAX_BINS ? G : PA_MAX_BINS;
+    for (int nb = warp + 1; nb <= PA_MAX_BINS; nb += 32) {
+        if (nb > nb_max) { if (lane == 0) scost[nb - 1] = 3.0e38f; continue; }
+        // LPT: lane owns bins lane and lane + 32
+        long long load0 = lane < nb ? 0 : 0x7fffffffffffffffLL, load1 = lane + 32 < nb ? 0 : 0x7fffffffffffffffLL;
+        int cnt0 = 0, cnt1 = 0;
+        for (int i = 0; i < G; ++i) {
+            const int32_t n = sn[sorder[i]];
+            long long v = load0 <= load1 ? load0 : load1;
+            int idx = load0 <= load1 ? lane : lane + 32;
+            pa_warp_argmin(v, idx);
+            if (idx == lane) { load0 += n; ++cnt0; }
+            if (idx == lane + 32) { load1 += n; ++cnt1; }
+        }
+        // estimate of T_b (sufficient, a few percent high): load / (256 - groups)
+        int T0 = 0, T1 = 0;
+        if (lane < nb) { const int d = 256 - cnt0 > 1 ? 256 - cnt0 : 1; T0 = (int)((load0 + d - 1) / d); }
+        if (lane + 32 < nb) { const int d = 256 - cnt1 > 1 ? 256 - cnt1 : 1; T1 = (int)((load1 + d - 1) / d); }
+        sTw[warp][lane] = T0;
+        sTw[warp][lane + 32] = T1;
+        __syncwarp();
+        // the kernel's schedule: unit u = b * RB + rb runs on CTA u % sms
+        float worst = 0.f;
+        for (int i = lane; i < pc.sms; i += 32) {
+            float t = 0.f;
+            for (int b = 0; b < nb; ++b) {
+                const int Tb = sTw[warp][b];
+                const long long u0 = (long long)b * pc.RB;                       // units u0 .. u0 + RB - 1
+                const int first = (int)((i - u0 % pc.sms + pc.sms) % pc.sms);    // first rb that lands on CTA i
+                const int cntu = first < pc.RB ? (pc.RB - first + pc.sms - 1) / pc.sms : 0;
+                if (Tb > 0) t += (float)cntu * ((float)Tb * pc.step_cycles + pc.unit_cycles);
+            }
+            worst = fmaxf(worst, t);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, off));
+        if (lane == 0) scost[nb - 1] = worst;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0;
+        for (int i = 1; i < PA_MAX_BINS; ++i) if (scost[i] < scost[best]) best = i;
+        s_nb = best + 1;
+    }
+    __syncthreads();
+    const int nb = s_nb;
+    if (warp == 0) {
+        long long load0 = lane < nb ? 0 : 0x7fffffffffffffffLL, load1 = lane + 32 < nb ? 0 : 0x7fffffffffffffffLL;
+        for (int i = 0; i < G; ++i) {
+            const int g = sorder[i];
+            const int32_t n = sn[g];
+            long long v = load0 <= load1 ? load0 : load1;
+            int idx = load0 <= load1 ? lane : lane + 32;
+            pa_warp_argmin(v, idx);
+            if (idx == lane) load0 += n;
+            if (idx == lane + 32) load1 += n;
+            if (lane == 0) sbin[g] = (int16_t)idx;
+        }
+        __syncwarp();
+        // exact T_b: smallest T with sum max(1, ceil(n / T)) <= 256 over the bin's groups
+        for (int b = lane; b < nb; b += 32) {
+            long long tot = 0;
+            int32_t mx = 0;
+            for (int g = 0; g < G; ++g) if (sbin[g] == b) { tot += sn[g]; mx = sn[g] > mx ? sn[g] : mx; }
+            int lo = 1, hi = mx > 1 ? mx : 1;                       // T = max n always fits (<= 256 groups, one column each)
+            if (tot == 0) { sT[b] = 0; continue; }
+            while (lo < hi) {
+                const int T = lo + (hi - lo) / 2;
+                int cols = 0;
+                for (int g = 0; g < G; ++g) if (sbin[g] == b) cols += sn[g] > 0 ? (sn[g] + T - 1) / T : 1;
+                if (cols <= PA_NB) hi = T; else lo = T + 1;
+            }
+            sT[b] = lo;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            long long steps = 0;
+            for (int b = 0; b < nb; ++b) { blockT[b] = sT[b]; step0[b] = steps; steps += sT[b]; }
+            step0[nb] = steps;
+            plan_out[0] = steps;
+            plan_out[1] = nb;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nb * PA_NB; i += blockDim.x) { col_group[i] = -1; col_meta[i] = -1; }
+    __syncthreads();
+    // columns of a block: its groups in id order, c = ceil(n / T_b) each (lane-free, one thread per block)
+    if (tid < nb) {
+        const int b = tid, T = sT[b];
+        int fill = 0;
+        for (int g = 0; g < G; ++g) {
+            if (sbin[g] != b) continue;
+            const int32_t n = sn[g];
+            const int c = (n > 0 && T > 0) ? (n + T - 1) / T : 1;
+            for (int j = 0; j < c; ++j) { col_group[b * PA_NB + fill + j] = g; col_meta[b * PA_NB + fill + j] = j == c - 1 ? g : -2; }
+            PaGroup r;
+            r.goff0 = goff[g];
+            const int64_t base = step0[b] * PA_NB + fill;
+            r.base = (int32_t)(base > 0x7fffffff ? 0x7fffffff : base);
+            r.c = c;
+            grp[g] = r;
+            fill += c;
+        }
+    }
+}
+
 // ---- K1, scatter form: canonical normalise of the label-sorted raw segments straight into the interleaved layout ----
 // Source ordered: a warp owns R consecutive raw rows, all of their 128-bit loads are issued before anything else, the
 // (label -> group record) lookups of lanes 0..R-1 fly alongside; each row is written as one contiguous 2*Dp-byte run at
@@ -533,7 +678,8 @@ int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, in
     const int kch = Dp / 64, MT = pa_mt_for(kch);
     int32_t t_min = 8;
     if (N / ((int64_t)PA_NB * 2048) > t_min) t_min = (int32_t)(N / ((int64_t)PA_NB * 2048));
-    const int64_t max_blocks64 = small ? 2 * (((int64_t)G + N / t_min) / PA_NB + 1) + 2 : ((int64_t)G + PA_NB - 1) / PA_NB;
+    int64_t max_blocks64 = small ? 2 * (((int64_t)G + N / t_min) / PA_NB + 1) + 2 : ((int64_t)G + PA_NB - 1) / PA_NB;
+    if (small && max_blocks64 < PA_MAX_BINS) max_blocks64 = PA_MAX_BINS;
     if (max_blocks64 > (1 << 22)) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling plan: too many column blocks");
     const int32_t max_blocks = (int32_t)max_blocks64;
     SDK_TRY(sdk_reserve(c, c->pa_col_group, (size_t)max_blocks * PA_NB * 4));
@@ -551,8 +697,12 @@ int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, in
         pc.sms = c->sm_count;
         pc.t_min = t_min;
         sdk_prof_scope ps(c, "plan");
-        k_pa_plan_small<<<1, 1024, 0, c->stream>>>(d_goff, G, pc, max_blocks, (int32_t*)c->pa_col_group.p, (int32_t*)c->pa_col_meta.p,
-                                                   (int32_t*)c->pa_blockT.p, step0, plan_out, (PaGroup*)c->pa_grp.p);
+        if (G <= PA_BINS_G)
+            k_pa_plan_bins<<<1, 1024, 0, c->stream>>>(d_goff, G, pc, (int32_t*)c->pa_col_group.p, (int32_t*)c->pa_col_meta.p,
+                                                      (int32_t*)c->pa_blockT.p, step0, plan_out, (PaGroup*)c->pa_grp.p);
+        else
+            k_pa_plan_small<<<1, 1024, 0, c->stream>>>(d_goff, G, pc, max_blocks, (int32_t*)c->pa_col_group.p, (int32_t*)c->pa_col_meta.p,
+                                                       (int32_t*)c->pa_blockT.p, step0, plan_out, (PaGroup*)c->pa_grp.p);
         c->launches += 1;
         SDK_CUDA(c, cudaGetLastError());
     } else {

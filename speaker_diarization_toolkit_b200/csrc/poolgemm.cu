@@ -510,16 +510,20 @@ __global__ void k_pg_ranges(const int64_t* __restrict__ goff, int32_t g_a, int32
 // key) and the upper bound on the approximate score of every row that is NOT in the list.
 __global__ void __launch_bounds__(256)
 k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const int32_t* __restrict__ sorted_group,
+           const int32_t* __restrict__ glist,
            const int32_t* __restrict__ slot_cnt, const int32_t* __restrict__ slot_row, const float* __restrict__ slot_val,
            const float* __restrict__ slot_bound, float tau, int32_t ncand, int32_t* __restrict__ cand_row,
            float* __restrict__ gbound) {
     __shared__ int hist[256];
     __shared__ int s_total, s_digit, s_need, s_out, s_ties;
     __shared__ unsigned int s_bound_key;
-    const int gl = blockIdx.x, tid = threadIdx.x;
-    const int g = sorted_group ? sorted_group[g_base + gl] : g_base + gl;   // slot index gl -> label group
+    const int tid = threadIdx.x;
+    // slot index gl -> label group; with a group list (second-chance merge of the groups whose certificate failed) the
+    // launch index selects the group and the compact output row
+    const int gl = glist ? glist[blockIdx.x] - g_base : blockIdx.x;
+    const int g = glist ? glist[blockIdx.x] : (sorted_group ? sorted_group[g_base + gl] : g_base + gl);
     if (g < 0) return;
-    int32_t* out = cand_row + (int64_t)g * ncand;
+    int32_t* out = cand_row + (int64_t)(glist ? blockIdx.x : g) * ncand;
     for (int i = tid; i < ncand; i += blockDim.x) out[i] = -1;
     if (goff[g + 1] <= goff[g]) { if (tid == 0) gbound[g] = -3.0e38f; return; }
     const int32_t* cnt = slot_cnt + (int64_t)gl * nsub;
@@ -603,10 +607,10 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const
 
 // ---- host side -----------------------------------------------------------------------------------
 void pg_launch_merge(sdk_ctx* c, const int64_t* d_goff, int32_t g_base, int32_t ngroups, int32_t nsub, const int32_t* d_sorted_group,
-                     float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound) {
+                     float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, const int32_t* d_glist) {
     if (ngroups <= 0) return;
     sdk_prof_scope ps(c, "merge");
-    k_pg_merge<<<(unsigned)ngroups, 256, 0, c->stream>>>(d_goff, g_base, nsub, d_sorted_group, (const int32_t*)c->slot_cnt.p,
+    k_pg_merge<<<(unsigned)ngroups, 256, 0, c->stream>>>(d_goff, g_base, nsub, d_sorted_group, d_glist, (const int32_t*)c->slot_cnt.p,
                                                          (const int32_t*)c->slot_row.p, (const float*)c->slot_val.p,
                                                          (const float*)c->slot_bound.p, tau, ncand, d_cand_row, d_gbound);
     c->launches++;
@@ -734,6 +738,7 @@ static int pg_run(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv
         SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)gbatch * nsub * PG_CS * 4));
     }
     const int64_t workers = two ? c->sm_count / 2 : c->sm_count;
+    c->slot_g0 = c->slot_g1 = 0;
     for (int64_t ga = 0; ga < G; ga += gbatch) {
         const int64_t gb = std::min<int64_t>(G, ga + gbatch);
         const int64_t ncols = hgoff[gb] - hgoff[ga];
@@ -776,6 +781,9 @@ static int pg_run(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv
         if (mode == 0) {
             pg_launch_merge(c, d_goff, (int32_t)ga, (int32_t)(gb - ga), nsub, nullptr, tau, ncand, d_cand_row, d_gbound);
             SDK_CUDA(c, cudaGetLastError());
+            c->slot_g0 = (int32_t)ga;        // groups whose candidate slots are still in memory after the call
+            c->slot_g1 = (int32_t)gb;
+            c->slot_nsub = nsub;
         }
     }
     return SDK_OK;
@@ -790,4 +798,13 @@ int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int6
 int sdk_launch_poolgemm_dense(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv_bfloat16* d_cols, int64_t N,
                               int32_t Dp, const int64_t* d_goff, int32_t G, int32_t pool, float* d_out) {
     return pg_run(c, d_rows, P, d_cols, N, Dp, d_goff, G, pool, 1, 0.f, 0, nullptr, nullptr, d_out);
+}
+
+// Second chance for label groups whose top-k certificate failed: a wider candidate list from the slots of the last batch.
+int sdk_launch_poolgemm_remerge(sdk_ctx* c, const int64_t* d_goff, const int32_t* d_glist, int32_t ngroups, float tau, int32_t ncand,
+                                int32_t* d_cand_row /*[ngroups,ncand]*/, float* d_gbound /*[G]*/) {
+    if (ngroups <= 0) return SDK_OK;
+    pg_launch_merge(c, d_goff, c->slot_g0, ngroups, c->slot_nsub, nullptr, tau, ncand, d_cand_row, d_gbound, d_glist);
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
 }

@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(SDK_SEL_THREADS)
 k_select(long long* __restrict__ qpool, const int64_t* __restrict__ goff, const int32_t* __restrict__ glist,
          const int32_t* __restrict__ cand_row, int64_t nslot, int32_t pool,
          const int32_t* __restrict__ row_speaker, const uint8_t* __restrict__ row_trust, double threshold,
-         int32_t k, int64_t row_offset, const float* __restrict__ gbound, float eps,
-         int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list, int64_t* __restrict__ out_row,
+         int32_t k, int64_t row_offset, const float* __restrict__ gbound, float eps, const PaGroup* __restrict__ grp,
+         int32_t upd_per_seg, int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list, int64_t* __restrict__ out_row,
          float* __restrict__ out_score, int32_t* __restrict__ out_count, uint8_t* __restrict__ out_trust,
          int32_t* __restrict__ out_spk) {
     __shared__ unsigned long long sh[SDK_SEL_THREADS / 32];
@@ -98,7 +98,11 @@ k_select(long long* __restrict__ qpool, const int64_t* __restrict__ goff, const 
             // certificate: every row that was NOT re-scored has approx score <= bound, hence a
             // canonical score <= bound + eps.  It cannot enter the result if that is below the
             // threshold, or below the k-th kept score when the list is full.
-            double b = (double)gbound[g] + (double)eps;
+            // eps is the measured bound on |tensor-core pooled score - canonical| with a ~50x margin for chains of up to
+            // 2^16 fp32 accumulator updates; it grows linearly with the chain beyond that (giant label groups)
+            const double chain = grp ? (double)((n + grp[g].c - 1) / grp[g].c) * (double)upd_per_seg : (double)n;
+            const double eps_g = (double)eps * (chain > 65536.0 ? chain / 65536.0 : 1.0);
+            double b = (double)gbound[g] + eps_g;
             bool safe = (b < threshold) || (cnt == k && b < (double)kth);
             if (!safe) {
                 int pos = atomicAdd(fb_count, 1);
@@ -111,14 +115,14 @@ k_select(long long* __restrict__ qpool, const int64_t* __restrict__ goff, const 
 int sdk_launch_select(sdk_ctx* c, const long long* d_qpool, const int64_t* d_goff, const int32_t* d_glist,
                       int32_t ngroups, const int32_t* d_cand_row, int64_t nslot, int32_t pool,
                       const int32_t* d_row_speaker, const uint8_t* d_row_trust, double threshold, int32_t k,
-                      int64_t row_offset, const float* d_gbound, float eps, int32_t* d_fb_count,
-                      int32_t* d_fb_list, int64_t* d_out_row, float* d_out_score, int32_t* d_out_count,
+                      int64_t row_offset, const float* d_gbound, float eps, const PaGroup* d_grp, int32_t upd_per_seg,
+                      int32_t* d_fb_count, int32_t* d_fb_list, int64_t* d_out_row, float* d_out_score, int32_t* d_out_count,
                       uint8_t* d_out_trust, int32_t* d_out_spk) {
     if (ngroups <= 0) return SDK_OK;
     sdk_prof_scope ps(c, "select");
     k_select<<<ngroups, SDK_SEL_THREADS, 0, c->stream>>>(const_cast<long long*>(d_qpool), d_goff, d_glist, d_cand_row,
                                                          nslot, pool, d_row_speaker, d_row_trust, threshold, k,
-                                                         row_offset, d_gbound, eps, d_fb_count, d_fb_list, d_out_row,
+                                                         row_offset, d_gbound, eps, d_grp, upd_per_seg, d_fb_count, d_fb_list, d_out_row,
                                                          d_out_score, d_out_count, d_out_trust, d_out_spk);
     c->launches++;
     SDK_CUDA(c, cudaGetLastError());

@@ -97,6 +97,16 @@ def test_tensor_path_certificate_fallback(ctx, oracle):
     assert_same(gpu, run_oracle(oracle, case, 1, 0, -1.0, 10), "fallback")
 
 
+def test_tensor_path_certificate_second_chance(ctx, oracle):
+    """No threshold and few candidates: some certificates fail on the first candidate list; the second, wider list
+    (64 candidates from the slots the GEMM left behind) settles them without the exhaustive pass."""
+    case = ragged_case(79, 192, P_speakers=900)
+    gpu = run_gpu(ctx, case, 1, 0, -1.0, 10, path=2, cand=10, eps=0.02)      # eps far above the real error: forces retries
+    assert ctx.last_retry() > 0, "expected first-list certificate failures"
+    assert ctx.last_path()[1] < ctx.last_retry()
+    assert_same(gpu, run_oracle(oracle, case, 1, 0, -1.0, 10), "second chance")
+
+
 def test_tensor_path_large_bank_many_rowblocks(ctx, oracle):
     rng = np.random.default_rng(5)
     case = synth.make_case(5, synth.zipf_counts(rng, 600, 6), 2100, 192, neighbours=5, impostor_frac=0.0)
