@@ -74,6 +74,14 @@ class B200Backend(EmbeddingBackend):
         key = tuple((c.get("id"), tuple(r.get("id") for r in (c.get("embeddings") or {}).get(self.name, [])),
                      c.get("updated_at")) for c in candidates)
         dtype = _native.DTYPE_BF16 if os.environ.get("SPEAKER_B200_DTYPE", "fp32") == "bf16" else _native.DTYPE_F32
+        if self._bank is None or key != self._bank_key:
+            # records enrolled by another backend / model generation: warn once per speaker (speechmatics_backend.py:396-405)
+            for cand in candidates:
+                for rec in (cand.get("embeddings") or {}).get(self.name, []):
+                    compat = self.check_embedding_compatibility(rec)
+                    if not compat["compatible"]:
+                        print(f"Warning: {cand.get('id')}: {compat['warning']}", file=sys.stderr)
+                        break
         if self._bank is None or key != self._bank_key or dtype != getattr(self, "_bank_dtype", None):
             build = store.build_bank if os.environ.get("SPEAKER_B200_BANK_CACHE", "1") == "0" else store.build_bank_cached
             bank = build(candidates, self.name, _env_int("SPEAKER_B200_DIM", 0) or None)

@@ -46,6 +46,45 @@ def load_speaker(speaker_id: str) -> Optional[Dict[str, Any]]:
         return json.load(fh)
 
 
+def normalize_speaker_id(speaker_id: str) -> str:
+    """speaker_detection:146-148."""
+    return speaker_id.lower().replace(" ", "-")
+
+
+def save_speaker(profile: Dict[str, Any]) -> None:
+    """speaker_detection:188-194 (stamps updated_at, 2-space JSON)."""
+    from datetime import datetime, timezone
+    get_speakers_db_path().mkdir(parents=True, exist_ok=True)
+    profile["updated_at"] = datetime.now(timezone.utc).isoformat()
+    with open(get_speakers_db_path() / f"{profile['id']}.json", "w") as fh:
+        json.dump(profile, fh, indent=2, ensure_ascii=False)
+
+
+def get_samples_by_source_audio(speaker_id: str, audio_b3sum: str) -> Dict[str, List[str]]:
+    """Sample hashes of one source recording by review status (speaker_detection:310-356): reads
+    samples/<speaker_id>/*.meta.yaml written by `speaker_samples`; no samples directory -> three empty lists."""
+    result: Dict[str, List[str]] = {"reviewed": [], "unreviewed": [], "rejected": []}
+    sdir = get_db_dir() / "samples" / speaker_id
+    if not sdir.exists():
+        return result
+    try:
+        import yaml
+    except ImportError:
+        yaml = None
+    for meta_path in sorted(sdir.glob("*.meta.yaml")):
+        try:
+            text = meta_path.read_text()
+            meta = (yaml.safe_load(text) if yaml else json.loads(text)) or {}
+        except Exception:
+            continue
+        if meta.get("source", {}).get("audio_b3sum") != audio_b3sum or not meta.get("b3sum"):
+            continue
+        status = meta.get("review", {}).get("status", "pending")
+        key = "reviewed" if status == "reviewed" else "rejected" if status == "rejected" else "unreviewed"
+        result[key].append(meta["b3sum"])
+    return result
+
+
 def list_all_speakers() -> List[Dict[str, Any]]:
     """Every db/*.json in sorted file order (speaker_detection:206-220); unreadable files are skipped with a warning."""
     db = get_speakers_db_path()
@@ -105,6 +144,27 @@ def vector_path(speaker_id: str, record: Dict[str, Any]) -> Optional[Path]:
         if c.exists():
             return c
     return None
+
+
+def bank_dimension(backend_name: str, speakers: Optional[List[Dict[str, Any]]] = None) -> Optional[int]:
+    """Dimension of the vectors already enrolled for `backend_name` (first readable one), or None for an empty bank."""
+    for prof in (speakers if speakers is not None else list_all_speakers()):
+        for rec in (prof.get("embeddings") or {}).get(backend_name) or []:
+            path = vector_path(prof.get("id"), rec)
+            if path is not None:
+                try:
+                    return int(np.load(path, mmap_mode="r").reshape(-1).shape[0])
+                except (OSError, ValueError):
+                    continue
+    return None
+
+
+def store_vector_canonical(speaker_id: str, emb_id: str, vec: np.ndarray) -> Path:
+    """embeddings/<speaker_id>/<emb_id>.npy -- the authoritative per-file layout (module docstring)."""
+    dst = get_embeddings_path() / speaker_id / f"{emb_id}.npy"
+    dst.parent.mkdir(parents=True, exist_ok=True)
+    np.save(dst, np.ascontiguousarray(vec, dtype=np.float32))
+    return dst
 
 
 def store_vector_cas(vec: np.ndarray) -> str:

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from oracle import matching_np as mnp
-from speaker_diarization_toolkit_b200 import _native, synth
+from speaker_diarization_toolkit_b200 import _native, store, synth
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
@@ -148,3 +148,35 @@ def test_assign_batch_equals_per_recording_assign(tmp_path, oracle):
         n_assigned += sum(1 for m in b["mappings"].values() if m["speaker_id"])
     assert n_assigned >= 5
     assert len(list((tmp_path / "assignments").glob("*.yaml"))) == 5
+
+
+def test_review_consistency_flags_mislabelled_segments(tmp_path, oracle):
+    """the config-5 pooled affinity behind `speaker-review consistency`: segments planted under the
+    wrong diarization label are exactly the ones reported, with the affinities the oracle computes."""
+    case = synth.make_case(21, [300, 260, 280, 40], 4, 256, truth=[0, 1, 2, 3], impostor_frac=0.0)
+    lab = case.seg_label.copy()
+    wrong = [5, 17, 400, 610, 845]                      # move five segments under a neighbouring label
+    for i in wrong:
+        lab[i] = (lab[i] + 1) % 4
+    labels = [f"S{int(l) + 1}" for l in lab]
+    audio = tmp_path / "m.wav"
+    audio.write_bytes(b"RIFF" + bytes(40) + b"review")
+    start = np.arange(len(lab)) * 1.0
+    store.save_segment_embeddings(audio, "b200", case.seg, labels, start, start + 0.9)
+    env = dict(os.environ, PYTHONPATH=str(ROOT), SPEAKER_DETECTION_BACKEND="b200")
+    rc, out, err = cli("speaker-review", "consistency", str(audio), "--format", "json", "--fail-on-suspects", env=env)
+    assert rc == 2, err
+    rep = json.loads(out)
+    se = store.load_segment_embeddings(audio, "b200")          # sidecar order: stable sort by label
+    flagged = sorted(round(s["start"]) for s in rep["suspects"])
+    assert flagged == sorted(wrong)
+    for s in rep["suspects"]:
+        assert s["closer_to"] == f"S{int(case.seg_label[round(s['start'])]) + 1}"       # points back at the true label
+    goff = np.r_[0, np.cumsum(np.bincount(se.label_index, minlength=4))].astype(np.int64)
+    ref = oracle.affinity(se.emb, goff, mode=1, pool=0)
+    for s in rep["suspects"]:
+        i = s["segment"]
+        assert abs(s["affinity"] - ref[i, se.label_index[i]]) < 2e-5
+    assert np.allclose(np.diag(np.asarray(rep["label_affinity"])), [np.mean(ref[goff[a]:goff[a + 1], a]) for a in range(4)], atol=2e-5)
+    rc, out, err = cli("speaker-review", "consistency", str(audio), env=env)
+    assert rc == 0 and "5 suspect segment(s)" in out

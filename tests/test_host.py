@@ -3,6 +3,8 @@ import argparse
 import ctypes
 import io
 import json
+import os
+import sys
 import re
 from contextlib import redirect_stderr, redirect_stdout
 from pathlib import Path
@@ -242,3 +244,105 @@ def test_packed_bank_cache(tmp_path, monkeypatch):
     assert same(got, store.build_bank(cands2, "b200"))
     assert sorted(Path(r).name for r in reads) == ["emb-20.npy", "emb-90.npy"]
     assert np.array_equal(got.rows[got.row_emb_id.index("emb-20")], np.arange(16, dtype=np.float32))
+
+
+# ---- enrollment / bank-writing path ------------------------------------------------------------
+ENROLL_RECORD_KEYS = ["id", "external_id", "source_audio", "source_audio_b3sum", "source_segments", "model_version", "samples",
+                      "trust_level", "created_at"]        # speaker_detection:890-901, in this order
+
+
+def _enroll_store(tmp_path, D=24, n=30, seed=5):
+    rng = np.random.default_rng(seed)
+    (tmp_path / "db").mkdir(parents=True)
+    prof = {"id": "alice", "version": 1, "names": {"default": "Alice"}, "nicknames": [], "description": "", "metadata": {},
+            "tags": [], "embeddings": {}, "created_at": "2026-01-01T00:00:00+00:00", "updated_at": "2026-01-01T00:00:00+00:00"}
+    (tmp_path / "db" / "alice.json").write_text(json.dumps(prof))
+    audio = tmp_path / "a.wav"
+    audio.write_bytes(b"RIFF" + bytes(40) + b"enroll")
+    emb = rng.standard_normal((n, D)).astype(np.float32) * rng.uniform(0.5, 9, size=(n, 1)).astype(np.float32)
+    labels = ["S1" if i % 3 else "S2" for i in range(n)]
+    start = np.arange(n) * 2.0
+    store.save_segment_embeddings(audio, "b200", emb, labels, start, start + 1.5)
+    return audio, emb, labels, start
+
+
+def test_enroll_cli_writes_reference_record_and_vector(tmp_path, monkeypatch, capsys):
+    from speaker_diarization_toolkit_b200 import identify_cli
+    monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(tmp_path))
+    monkeypatch.delenv("SPEAKER_BACKENDS_CONFIG", raising=False)
+    audio, emb, labels, start = _enroll_store(tmp_path)
+    # errors first, with the reference's messages and rc (speaker_detection:759-780)
+    assert identify_cli.main(["enroll", "bob", str(audio)]) == 1
+    assert "Error: Speaker 'bob' not found. Use 'add' first." in capsys.readouterr().err
+    assert identify_cli.main(["enroll", "alice", str(tmp_path / "nope.wav")]) == 1
+    assert "Error: Audio file not found:" in capsys.readouterr().err
+    assert identify_cli.main(["enroll", "alice", str(audio), "-s", "5:3"]) == 1
+    assert "Error: Invalid segment '5:3'. Start must be < end." in capsys.readouterr().err
+    assert identify_cli.main(["enroll", "alice", str(audio), "-s", "0:11", "--dry-run"]) == 0
+    out = capsys.readouterr().out
+    assert "Would enroll speaker: alice" in out and "Segments: 1 (11.0s total)" in out
+    # the real thing: segments overlapping [0, 11) s = sidecar rows 0..5
+    assert identify_cli.main(["-q", "enroll", "alice", str(audio), "-b", "b200", "-s", "0:11", "--trust-level", "high"]) == 0
+    cap = capsys.readouterr()
+    assert "Enrolled embedding emb-" in cap.out and "(no samples tracked)" in cap.out and cap.err == ""
+    prof = store.load_speaker("alice")
+    (rec,) = prof["embeddings"]["b200"]
+    assert list(rec.keys()) == ENROLL_RECORD_KEYS
+    assert rec["trust_level"] == "high" and rec["model_version"] == "b200-cosine-v1" and rec["source_segments"] == [{"start": 0.0, "end": 11.0}]
+    assert rec["samples"] == {"reviewed": [], "unreviewed": [], "rejected": []}
+    x = emb[:6].astype(np.float64)
+    want = (x / np.linalg.norm(x, axis=1, keepdims=True)).mean(axis=0).astype(np.float32)
+    canonical = tmp_path / "embeddings" / "alice" / f"{rec['id']}.npy"
+    assert np.array_equal(np.load(canonical), want)
+    assert np.array_equal(np.load(tmp_path / "embeddings" / rec["external_id"]), want)      # content-addressed handle
+    bank = store.build_bank_cached([prof], "b200")
+    assert bank.P == 1 and np.array_equal(bank.rows[0], want) and bank.row_emb_id == [rec["id"]]
+    # --from-transcript picks the label's segments; default trust (no samples) is "low" (speaker_detection:378-379)
+    words = []
+    for i, lab in enumerate(labels):
+        words.append({"type": "word", "start_time": float(start[i]), "end_time": float(start[i]) + 1.5,
+                      "alternatives": [{"content": "w", "confidence": 1.0, "speaker": lab}]})
+    tpath = tmp_path / "a.json"
+    tpath.write_text(json.dumps({"format": "2.9", "results": words}))
+    assert identify_cli.main(["enroll", "alice", str(audio), "-t", str(tpath)]) == 1
+    assert "--speaker-label required with --from-transcript" in capsys.readouterr().err
+    assert identify_cli.main(["enroll", "alice", str(audio), "-t", str(tpath), "-l", "S2"]) == 0
+    capsys.readouterr()
+    recs = store.load_speaker("alice")["embeddings"]["b200"]
+    assert len(recs) == 2 and recs[1]["trust_level"] == "low"
+    sel = np.asarray([l == "S2" for l in labels])
+    x = emb[sel].astype(np.float64)
+    want2 = (x / np.linalg.norm(x, axis=1, keepdims=True)).mean(axis=0).astype(np.float32)
+    assert np.array_equal(np.load(tmp_path / "embeddings" / "alice" / f"{recs[1]['id']}.npy"), want2)
+    # a recording whose embeddings have another dimension is rejected before anything is stored
+    audio2 = tmp_path / "b.wav"
+    audio2.write_bytes(b"RIFF" + bytes(40) + b"other")
+    store.save_segment_embeddings(audio2, "b200", np.ones((3, 16), np.float32), ["S1"] * 3)
+    assert identify_cli.main(["enroll", "alice", str(audio2)]) == 1
+    assert "Error during enrollment: embedding is 16-d but the bank enrolled for b200 is 24-d" in capsys.readouterr().err
+    assert len(store.load_speaker("alice")["embeddings"]["b200"]) == 2
+
+
+@pytest.mark.skipif(not Path("/root/reference/speaker_detection").exists(), reason="needs the reference tree (authoring container)")
+def test_enroll_through_the_reference_cli_with_the_b200_backend(tmp_path):
+    """The UNMODIFIED reference `speaker_detection enroll` with this package plugged in as a backend produces a record our
+    store resolves to the same vector (via the content-addressed external_id), and our `enroll` writes the same keys."""
+    import subprocess
+    audio, emb, labels, start = _enroll_store(tmp_path)
+    cfg = tmp_path / "backends.yaml"
+    cfg.write_text("backends:\n  b200:\n    module: speaker_diarization_toolkit_b200.backend\n")
+    env = dict(os.environ, SPEAKERS_EMBEDDINGS_DIR=str(tmp_path), SPEAKER_BACKENDS_CONFIG=str(cfg), PYTHONPATH=str(ROOT))
+    r = subprocess.run([sys.executable, "/root/reference/speaker_detection", "enroll", "alice", str(audio), "-b", "b200", "-s", "0:11"],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    os.environ["SPEAKERS_EMBEDDINGS_DIR"] = str(tmp_path)
+    try:
+        prof = store.load_speaker("alice")
+        (rec,) = prof["embeddings"]["b200"]
+        assert list(rec.keys()) == ENROLL_RECORD_KEYS
+        x = emb[:6].astype(np.float64)
+        want = (x / np.linalg.norm(x, axis=1, keepdims=True)).mean(axis=0).astype(np.float32)
+        bank = store.build_bank([prof], "b200")
+        assert bank.P == 1 and np.array_equal(bank.rows[0], want)
+    finally:
+        os.environ.pop("SPEAKERS_EMBEDDINGS_DIR", None)
