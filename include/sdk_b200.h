@@ -80,7 +80,8 @@ const char* sdk_last_error(sdk_ctx* ctx);
 /* tuning / test knobs: "path" (0 auto, 1 exact SIMT, 2 tcgen05), "eps" (certificate margin),
  * "profile" (1 = record per-kernel CUDA-event times), "cand" (re-scored candidates per label),
  * "chunk_mb" (host-buffer sdk_identify: size of the H2D/compute pipeline chunks, default 512),
- * "cta_group" (1 | 2: tcgen05 kernel variant), "acc" (1 = pool inside the MMA accumulation when applicable) */
+ * "cta_group" (1 | 2: tcgen05 kernel variant), "acc" (0 off | 1 auto | 2 force: pool inside the MMA accumulation),
+ * "gemv" (1 = stream the bank on the CUDA cores when there are <= 8 query segments) */
 int sdk_set_option(sdk_ctx* ctx, const char* key, double value);
 
 /* ---- profile bank (replaces: the candidates list handed to identify_speaker, base.py:133,
@@ -152,7 +153,7 @@ int sdk_profile_reset(sdk_ctx* ctx);
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 int64_t sdk_launch_count(sdk_ctx* ctx);
 /* which path the last identify took: 1 exact SIMT, 2 tcgen05 (pooling in the epilogue), 3 tcgen05 accumulate-pooling
- * (mean pooling inside the MMA accumulation); *n_fallback = label groups whose
+ * (mean pooling inside the MMA accumulation), 4 bank-stream GEMV (<= 8 query segments); *n_fallback = label groups whose
  * top-k certificate failed and were re-done exhaustively */
 int sdk_last_path(sdk_ctx* ctx, int32_t* path, int64_t* n_fallback);
 /* label groups of the last identify whose top-k certificate failed on the first candidate list and was settled by the

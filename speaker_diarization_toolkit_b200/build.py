@@ -12,7 +12,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libsdk_b200.so"
-SOURCES = ["api.cu", "normalize.cu", "exact.cu", "select.cu", "poolgemm.cu", "poolacc.cu"]
+SOURCES = ["api.cu", "normalize.cu", "exact.cu", "select.cu", "poolgemm.cu", "poolacc.cu", "gemv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -197,6 +197,9 @@ int sdk_set_option(sdk_ctx* c, const char* key, double value) {
     } else if (k == "acc") {
         if (value != 0 && value != 1 && value != 2) return sdk_fail(c, SDK_EINVAL, "acc must be 0 (off), 1 (auto) or 2 (force)");
         c->opt_acc = (int)value;
+    } else if (k == "gemv") {
+        if (value != 0 && value != 1) return sdk_fail(c, SDK_EINVAL, "gemv must be 0 or 1");
+        c->opt_gemv = (int)value;
     } else if (k == "chunk_mb") {
         if (value < 1 || value > 65536) return sdk_fail(c, SDK_EINVAL, "chunk_mb must be in 1..65536");
         c->opt_chunk_mb = (int)value;
@@ -324,7 +327,12 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
     // path choice: tcgen05 only where the contraction is big enough to be a real dense GEMM
     const double macs = (double)N * (double)P * (double)Dp;
     int path = c->opt_path;
-    if (path == 0) path = (macs > 2147483648.0 && sdk_poolgemm_supported(Dp) && c->tmap_encode) ? 2 : 1;
+    // (the exact kernel is thread-per-segment: label groups of a few segments against a big bank leave most of a CTA idle,
+    //  so those shapes -- e.g. 8 pooled centroids against a 125k-row shard -- go to the tensor path much earlier)
+    if (path == 0) {
+        const bool big = macs > 536870912.0 || (macs > 67108864.0 && (double)N < 64.0 * (double)L);
+        path = (big && sdk_poolgemm_supported(Dp) && c->tmap_encode) ? 2 : 1;
+    }
     if (path == 2 && !(sdk_poolgemm_supported(Dp) && c->tmap_encode))
         return sdk_fail(c, SDK_EINVAL, "tcgen05 path not available for this D / driver");
     c->last_path = path;
@@ -333,7 +341,9 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
     // straight into its group-interleaved bf16 layout.  Auto mode takes it where the generic kernel is bound by its
     // epilogue (D <= 256) or where there are enough groups for tight size classes, and only if the layout's zero
     // padding stays under 12 %.
-    bool use_acc = path == 2 && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048;
+    // a handful of query segments: one HBM-bound pass over the bank on the CUDA cores (gemv.cu)
+    const bool use_gemv = path == 2 && c->opt_gemv && sdk_gemv_applicable(N, Dp);
+    bool use_acc = path == 2 && !use_gemv && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048;
     if (use_acc && c->opt_acc != 2 && !(Dp <= 256 || L > 2048)) use_acc = false;
     int64_t acc_steps = 0;
     if (path == 2) {   // the plan of either tcgen05 kernel trusts goff: reject bad labels before going on
@@ -348,6 +358,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         if (c->opt_acc != 2 && (double)acc_steps * 256.0 > 1.12 * (double)N + 1024.0) use_acc = false;   // acc == 2 forces it (tests)
     }
     if (use_acc) c->last_path = 3;
+    if (use_gemv) c->last_path = 4;
     const bool need_bf16 = (bf16 || path == 2) && !use_acc;
     if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
     if (need_bf16) SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
@@ -387,6 +398,10 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
                                        (float*)c->gbound.p, nullptr, c->seg_bf16, &ig));
             if (bf16) seg_grp = ig;                            // bf16 operands live in the interleaved matrix
             acc_grp = ig;
+        } else if (use_gemv) {
+            SDK_TRY(sdk_launch_gemv_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p, N, Dp,
+                                               (const int64_t*)c->goff.p, L, pool, tau, ncand, (int32_t*)c->cand_row.p,
+                                               (float*)c->gbound.p));
         } else {
             SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p,
                                                    N, Dp, (const int64_t*)c->goff.p, L, pool, tau, ncand,
@@ -670,7 +685,7 @@ int sdk_affinity_pooled_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg
     SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, 0, (int64_t*)c->goff.p, (int32_t*)c->flags.p));
     const double macs = (double)N * (double)N * (double)Dp;
     int path = c->opt_path;
-    if (path == 0) path = (macs > 2147483648.0 && bf16 && sdk_poolgemm_supported(Dp) && c->tmap_encode) ? 2 : 1;
+    if (path == 0) path = (macs > 536870912.0 && bf16 && sdk_poolgemm_supported(Dp) && c->tmap_encode) ? 2 : 1;
     if (path == 2 && !(bf16 && sdk_poolgemm_supported(Dp) && c->tmap_encode))
         return sdk_fail(c, SDK_EINVAL, "tcgen05 affinity needs dtype bf16 and a supported D");
     c->last_path = path;

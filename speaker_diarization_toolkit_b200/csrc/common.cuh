@@ -47,6 +47,7 @@ struct sdk_ctx {
     int opt_cand = 16;         // re-scored candidates per label group (tensor path)
     int opt_cta_group = 1;     // tcgen05 path: 1 = single CTA (measured faster at D <= 256), 2 = CTA pairs (cta_group::2)
     int opt_acc = 1;           // mean pooling with many label groups: pool inside the MMA accumulation (poolacc.cu)
+    int opt_gemv = 1;          // <= 8 query segments: stream the bank once on the CUDA cores (gemv.cu) instead of tcgen05 tiles
     int opt_chunk_mb = 512;    // host-buffer identify: H2D/compute pipeline chunk size
     // bank
     int64_t P = 0;
@@ -158,6 +159,11 @@ int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int6
                                    const int64_t* d_goff, int32_t G, int32_t pool, float tau,
                                    int32_t ncand, int32_t* d_cand_row /*[G,ncand]*/,
                                    float* d_gbound /*[G]*/);
+// <= 8 query segments: HBM-bound bank stream on the CUDA cores (gemv.cu), same outputs as the tcgen05 stage A
+int sdk_gemv_applicable(int64_t N, int32_t Dp);
+int sdk_launch_gemv_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int64_t P, const __nv_bfloat16* d_seg, int64_t N, int32_t Dp,
+                               const int64_t* d_goff, int32_t G, int32_t pool, float tau, int32_t ncand, int32_t* d_cand_row,
+                               float* d_gbound);
 int sdk_launch_poolgemm_remerge(sdk_ctx* c, const int64_t* d_goff, const int32_t* d_glist, int32_t ngroups, float tau,
                                 int32_t ncand, int32_t* d_cand_row, float* d_gbound);
 // tcgen05 accumulate-pooling GEMM (mean pooling, >= 128 label groups): normalises the RAW segments into the group-

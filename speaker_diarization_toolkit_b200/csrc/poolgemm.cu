@@ -18,8 +18,8 @@
 // TMEM accumulator ring (2 x MT x NC columns <= 512) so the epilogue of chunk j overlaps the MMAs of chunk j+1.
 //
 // Flush (candidate mode): the warp keeps, for its 32*MT rows of label group g, the rows whose approximate
-// pooled score is >= tau (at most CS of them; if more pass, the CS largest, found with a ballot-based binary
-// search on the orderable key, plus the bound below which everything was dropped).  A merge kernel then
+// pooled score is >= tau (at most CS of them; if more pass, the CS largest by rank among the warp's 32 keys, plus
+// the bound below which everything was dropped).  A merge kernel then
 // picks the top `ncand` rows per label and the upper bound on every row left out; select.cu re-scores the
 // candidates canonically and checks the bound (the top-k certificate).
 // Flush (dense mode, config 5): out[row, g] = pooled value.
@@ -506,17 +506,33 @@ __global__ void k_pg_ranges(const int64_t* __restrict__ goff, int32_t g_a, int32
 }
 
 // ---- merge of the per-(row block, warp) candidate slots of one label group ------------------------
-// Picks the `ncand` rows with the largest approximate score (radix select, 4 x 8 bits, on the orderable
-// key) and the upper bound on the approximate score of every row that is NOT in the list.
-__global__ void __launch_bounds__(256)
+// Picks the `ncand` rows with the largest approximate score and the upper bound on the approximate score of every row
+// that is NOT in the list.  With no threshold every slot is full (half the bank per label group), so the scan is
+// organised to touch the slots twice: pass A takes, per thread, the largest key of its sub-slots; the ncand-th largest
+// of those per-thread maxima is a lower bound T0 on the ncand-th largest key overall.  Pass B compacts the few entries
+// >= T0 into shared memory, where they are ranked (descending key, ties by position).  An overfull compaction
+// (many equal keys) falls back to a radix select over the slots.
+#define PG_MERGE_THREADS 1024
+#define PG_MERGE_CAP 2048
+__device__ __forceinline__ void pg_load_slot(const float* __restrict__ vals, int c, float (&v)[PG_CS]) {
+    const float4* p = reinterpret_cast<const float4*>(vals);
+#pragma unroll
+    for (int q = 0; q < PG_CS / 4; ++q) {
+        float4 t = (q * 4 < c) ? __ldg(p + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+    }
+}
+__global__ void __launch_bounds__(PG_MERGE_THREADS)
 k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const int32_t* __restrict__ sorted_group,
            const int32_t* __restrict__ glist,
            const int32_t* __restrict__ slot_cnt, const int32_t* __restrict__ slot_row, const float* __restrict__ slot_val,
            const float* __restrict__ slot_bound, float tau, int32_t ncand, int32_t* __restrict__ cand_row,
            float* __restrict__ gbound) {
+    __shared__ unsigned int s_key[PG_MERGE_CAP];      // pass A: thread maxima (first 1024); pass B: compacted keys
+    __shared__ int32_t s_row[PG_MERGE_CAP];
     __shared__ int hist[256];
-    __shared__ int s_total, s_digit, s_need, s_out, s_ties;
-    __shared__ unsigned int s_bound_key;
+    __shared__ int s_total, s_digit, s_need, s_out, s_ties, s_m;
+    __shared__ unsigned int s_bound_key, s_t0;
     const int tid = threadIdx.x;
     // slot index gl -> label group; with a group list (second-chance merge of the groups whose certificate failed) the
     // launch index selects the group and the compact output row
@@ -530,31 +546,87 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const
     const int32_t* rows = slot_row + (int64_t)gl * nsub * PG_CS;
     const float* vals = slot_val + (int64_t)gl * nsub * PG_CS;
     const float* bnd = slot_bound + (int64_t)gl * nsub;
-    if (tid == 0) { s_total = 0; s_out = 0; s_ties = 0; s_bound_key = sdk_fkey(tau); }
+    if (tid == 0) { s_total = 0; s_out = 0; s_ties = 0; s_m = 0; s_t0 = 0u; s_bound_key = sdk_fkey(tau); }
     __syncthreads();
+    // ---- pass A ----
     int mytotal = 0;
-    unsigned int mybound = 0;
+    unsigned int mybound = 0, mymax = 0;
     for (int s = tid; s < nsub; s += blockDim.x) {
-        int c = cnt[s];
-        mytotal += c < PG_CS ? c : PG_CS;
-        if (c > PG_CS) { unsigned int kb = sdk_fkey(bnd[s]); mybound = kb > mybound ? kb : mybound; }
+        const int c0 = cnt[s];
+        const int c = c0 < PG_CS ? c0 : PG_CS;
+        mytotal += c;
+        if (c0 > PG_CS) { unsigned int kb = sdk_fkey(bnd[s]); mybound = kb > mybound ? kb : mybound; }
+        if (c > 0) {
+            float v[PG_CS];
+            pg_load_slot(vals + (int64_t)s * PG_CS, c, v);
+#pragma unroll
+            for (int i = 0; i < PG_CS; ++i) { const unsigned int k = i < c ? sdk_fkey(v[i]) : 0u; mymax = k > mymax ? k : mymax; }
+        }
     }
-    atomicAdd(&s_total, mytotal);
+    if (mytotal) atomicAdd(&s_total, mytotal);
     if (mybound) atomicMax(&s_bound_key, mybound);
+    s_key[tid] = mymax;
     __syncthreads();
     const int total = s_total;
-    const int64_t flat = (int64_t)nsub * PG_CS;
     if (total <= ncand) {
-        for (int64_t f = tid; f < flat; f += blockDim.x) {
-            int s = (int)(f / PG_CS), i = (int)(f - (int64_t)s * PG_CS);
-            int c = cnt[s];
-            if (i < (c < PG_CS ? c : PG_CS)) out[atomicAdd(&s_out, 1)] = rows[f];
+        for (int s = tid; s < nsub; s += blockDim.x) {
+            const int c0 = cnt[s];
+            const int c = c0 < PG_CS ? c0 : PG_CS;
+            for (int i = 0; i < c; ++i) out[atomicAdd(&s_out, 1)] = rows[(int64_t)s * PG_CS + i];
         }
         __syncthreads();
         if (tid == 0) gbound[g] = sdk_funkey(s_bound_key);
         return;
     }
-    // radix select of the ncand-th largest key
+    // T0 = ncand-th largest thread maximum (0 when fewer than ncand threads saw an entry)
+    {
+        int rank = 0;
+        for (int j = 0; j < (int)blockDim.x; ++j) { const unsigned int o = s_key[j]; rank += (o > mymax || (o == mymax && j < tid)) ? 1 : 0; }
+        if (rank == ncand - 1) s_t0 = mymax;
+    }
+    __syncthreads();
+    const unsigned int T0 = s_t0;
+    __syncthreads();                        // everyone has read the maxima before s_key is reused
+    // ---- pass B: compact the entries >= T0 ----
+    for (int s = tid; s < nsub; s += blockDim.x) {
+        const int c0 = cnt[s];
+        const int c = c0 < PG_CS ? c0 : PG_CS;
+        if (c > 0) {
+            float v[PG_CS];
+            pg_load_slot(vals + (int64_t)s * PG_CS, c, v);
+#pragma unroll
+            for (int i = 0; i < PG_CS; ++i) {
+                if (i < c) {
+                    const unsigned int k = sdk_fkey(v[i]);
+                    if (k >= T0) {
+                        const int pos = atomicAdd(&s_m, 1);
+                        if (pos < PG_MERGE_CAP) { s_key[pos] = k; s_row[pos] = rows[(int64_t)s * PG_CS + i]; }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int M = s_m;
+    if (M <= PG_MERGE_CAP) {
+        // rank inside the compacted list: descending key, ties by bank row (deterministic candidate order)
+        for (int i = tid; i < M; i += blockDim.x) {
+            const unsigned int k = s_key[i];
+            const int32_t r = s_row[i];
+            int rank = 0;
+            for (int j = 0; j < M; ++j) { const unsigned int o = s_key[j]; rank += (o > k || (o == k && s_row[j] < r)) ? 1 : 0; }
+            if (rank < ncand) out[rank] = r;
+            if (rank == ncand - 1) s_t0 = k;            // the ncand-th largest key: everything dropped is <= it
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int T = s_t0;
+            gbound[g] = sdk_funkey(s_bound_key > T ? s_bound_key : T);
+        }
+        return;
+    }
+    // ---- fallback: radix select of the ncand-th largest key over the slots (4 x 8 bits) ----
+    const int64_t flat = (int64_t)nsub * PG_CS;
     unsigned int prefix = 0, mask = 0;
     int need = ncand;
     for (int pass = 3; pass >= 0; --pass) {
@@ -610,7 +682,9 @@ void pg_launch_merge(sdk_ctx* c, const int64_t* d_goff, int32_t g_base, int32_t 
                      float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, const int32_t* d_glist) {
     if (ngroups <= 0) return;
     sdk_prof_scope ps(c, "merge");
-    k_pg_merge<<<(unsigned)ngroups, 256, 0, c->stream>>>(d_goff, g_base, nsub, d_sorted_group, d_glist, (const int32_t*)c->slot_cnt.p,
+    // small banks (a few hundred sub-slots per label group, tens of thousands of groups): a 256-thread CTA per group
+    const int threads = nsub <= 1024 ? 256 : PG_MERGE_THREADS;
+    k_pg_merge<<<(unsigned)ngroups, threads, 0, c->stream>>>(d_goff, g_base, nsub, d_sorted_group, d_glist, (const int32_t*)c->slot_cnt.p,
                                                          (const int32_t*)c->slot_row.p, (const float*)c->slot_val.p,
                                                          (const float*)c->slot_bound.p, tau, ncand, d_cand_row, d_gbound);
     c->launches++;

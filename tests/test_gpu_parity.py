@@ -11,10 +11,12 @@ from speaker_diarization_toolkit_b200 import _native, synth
 pytestmark = pytest.mark.gpu
 
 
-def run_gpu(ctx, case, dtype, pool, thr, k, path, cand=None, eps=None, acc=0):
-    """acc: 0 = generic tcgen05 kernel (pooling in the epilogue), 1 = auto, 2 = force accumulate-pooling."""
+def run_gpu(ctx, case, dtype, pool, thr, k, path, cand=None, eps=None, acc=0, gemv=0):
+    """acc: 0 = generic tcgen05 kernel (pooling in the epilogue), 1 = auto, 2 = force accumulate-pooling;
+    gemv: 1 = bank-stream kernel when there are <= 8 query segments."""
     ctx.set_option("path", path)
     ctx.set_option("acc", acc)
+    ctx.set_option("gemv", gemv)
     ctx.set_option("cand", cand if cand is not None else 16)
     ctx.set_option("eps", eps if eps is not None else -1.0)
     ctx.bank_load(case.bank, case.row_speaker, case.row_trust, dtype=dtype)
@@ -95,6 +97,27 @@ def test_tensor_path_certificate_fallback(ctx, oracle):
     gpu = run_gpu(ctx, case, 1, 0, -1.0, 10, path=2, cand=1, eps=0.5)
     assert ctx.last_path()[1] > 0, "expected certificate failures"
     assert_same(gpu, run_oracle(oracle, case, 1, 0, -1.0, 10), "fallback")
+
+
+@pytest.mark.parametrize("D,dtype,pool,thr,k,counts", [
+    (512, 1, 0, -1.0, 10, [1] * 8),                        # config 4 variant (i): 8 pooled label centroids
+    (192, 1, 0, 0.354, 4, [2, 0, 1, 3, 0, 0, 1]),
+    (256, 1, 1, 0.2, 10, [5, 3]),
+    (64, 1, 0, 0.354, 3, [1]),
+    (320, 0, 0, 0.354, 5, [0, 4, 4, 0]),                   # fp32 bank: stage A on the bf16 copy, re-score in fp32
+    (448, 1, 1, -1.0, 32, [1, 1, 1, 2]),
+])
+def test_bank_stream_gemv_path(ctx, oracle, D, dtype, pool, thr, k, counts):
+    """<= 8 query segments: stage A is one HBM-bound pass over the bank on the CUDA cores (path 4); same certified
+    top-k, same oracle, bit-exact."""
+    rng = np.random.default_rng(D + pool)
+    case = synth.make_case(1200 + D, counts, 700, D, rows_per_speaker=rng.choice([1, 2, 3], size=700), impostor_frac=0.25, neighbours=3)
+    gpu = run_gpu(ctx, case, dtype, pool, thr, k, path=2, gemv=1)
+    path, nfb = ctx.last_path()
+    assert path == 4, "expected the bank-stream kernel"
+    if thr > 0.3:
+        assert nfb == 0
+    assert_same(gpu, run_oracle(oracle, case, dtype, pool, thr, k), f"gemv D={D}")
 
 
 def test_tensor_path_certificate_second_chance(ctx, oracle):
