@@ -454,7 +454,17 @@ def main():
     names = ["plan", "normalize", "poolgemm", "merge", "exact", "select", "assign"]
     prof = {n: ctx.profile_get(n) for n in names}
     tot_prof = sum(v[0] for v in prof.values()) or 1.0
-    if path >= 2:
+    if path == 4:
+        # bank-stream stage A (gemv.cu): one pass over the bf16 bank, HBM-bound; algorithmic bytes = 2*Dp per bank row
+        gms, gl = prof["poolgemm"]
+        avg_ms = gms / max(1, gl)
+        Dp4 = (D + 63) // 64 * 64
+        ach = (P * Dp4 * 2 + N * Dp4 * 2) / (avg_ms * 1e-3) / 1e9
+        roof = {"kernel": "k_gemv8 (TMA ring + mma.sync m16n8k16, <= 8 query segments)", "bound": "hbm", "achieved": ach,
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                "peak_source": f"{pk_src} copy bandwidth", "algorithmic_bytes_per_bank_row": 2 * Dp4, "avg_launch_ms": avg_ms,
+                "share_of_step": gms / tot_prof}
+    elif path >= 2:
         gms, gl = prof["poolgemm"]
         per_launch_flops = 2.0 * pairs_rank * D / max(1, gl // max(1, args.steps))   # flops per launch = 2*D per pair
         avg_ms = gms / max(1, gl)
@@ -537,7 +547,7 @@ def main():
                            "segments_per_gpu": N, "label_groups_per_gpu": G, "bank_rows_per_gpu": P, "dim": D, "k": cfg["k"],
                            "threshold": cfg["thr"], "pool": "mean", "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
                            "l2": "working set larger than 2x L2 (no flush needed)" if flush is None else "256 MB flush buffer written between timed iterations",
-                           "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{args.cta_group}", 3: "tcgen05 accumulate-pooling"}.get(path, str(path)), "certificate_fallback_groups": nfb, "certificate_retry_groups": nretry, "scale": args.scale},
+                           "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{args.cta_group}", 3: "tcgen05 accumulate-pooling", 4: "bank-stream gemv"}.get(path, str(path)), "certificate_fallback_groups": nfb, "certificate_retry_groups": nretry, "scale": args.scale},
                 "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
                 "kernel_ms_per_step": {n: v[0] / args.steps for n, v in prof.items()}}
         print(json.dumps(line))

@@ -1,13 +1,25 @@
-set -x
+# Profiling pass of round 1 (run on the GPU box: `gpurun -- bash tools/ncu_job.sh v7`).  Every ncu command runs only after
+# the same bench command has exited 0 without ncu.  Reports land in gpurun_out/; summarise with tools/ncu_summary.py.
+V=${1:-v7}
 B="python bench.py --no-e2e --no-cpu"
-timeout 300 $B --steps 2 --warmup 1 > gpurun_out/ncu_plain.json 2> gpurun_out/ncu_plain.err || exit 1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_v6.csv $B --steps 2 --warmup 1 > gpurun_out/ncu_l.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_poolacc -s 1 -c 1 -f -o gpurun_out/r01_poolacc_v6 $B --steps 1 --warmup 1 > gpurun_out/ncu_a.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pa_normalize_scatter -s 1 -c 1 -f -o gpurun_out/r01_normscatter_v6 $B --steps 1 --warmup 1 > gpurun_out/ncu_b.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_exact_q30 -s 1 -c 1 -f -o gpurun_out/r01_exact_v6 $B --steps 1 --warmup 1 > gpurun_out/ncu_c.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_poolacc -s 1 -c 1 -f -o gpurun_out/r01_cfg5_poolacc_v6 $B --workload cfg5 --steps 1 --warmup 1 > gpurun_out/ncu_d.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r01_launches_cfg5_v6.csv $B --workload cfg5 --steps 2 --warmup 1 > gpurun_out/ncu_e.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_poolgemm -s 1 -c 1 -f -o gpurun_out/r01_cfg4_poolgemm_v6 $B --workload cfg4 --steps 1 --warmup 1 > gpurun_out/ncu_f.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r01_launches_cfg4_v6.csv $B --workload cfg4 --steps 2 --warmup 1 > gpurun_out/ncu_g.log 2>&1
-ls -la gpurun_out/ | tail -20
-tail -3 gpurun_out/ncu_a.log gpurun_out/ncu_b.log gpurun_out/ncu_c.log gpurun_out/ncu_d.log gpurun_out/ncu_f.log
+set -x
+for w in cfg3 cfg4 cfg5 cfg4i cfg4ii; do
+  timeout 300 $B --workload $w --steps 2 --warmup 1 > gpurun_out/ncu_plain_$w.json 2> gpurun_out/ncu_plain_$w.err || exit 1
+done
+# launch lists (share of the step per kernel)
+for w in cfg3 cfg4 cfg5 cfg4i; do
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r01_launches_${w}_$V.csv $B --workload $w --steps 2 --warmup 1 > gpurun_out/ncu_l_$w.log 2>&1
+done
+# full captures of the dominant kernels (one launch each, after the warm-up launches)
+cap() {  # workload kernel-regex name
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$2 -s 1 -c 1 -f -o gpurun_out/r01_$3_$V $B --workload $1 --steps 1 --warmup 1 > gpurun_out/ncu_$3.log 2>&1
+}
+cap cfg3 k_poolacc poolacc
+cap cfg3 k_pa_normalize_scatter normscatter
+cap cfg3 k_exact_q30 exact
+cap cfg3 k_pg_merge merge
+cap cfg5 k_poolacc cfg5_poolacc
+cap cfg4 "k_poolgemm<" cfg4_poolgemm
+cap cfg4i k_gemv8 cfg4i_gemv
+cap cfg4ii "k_poolgemm<" cfg4ii_poolgemm
+ls -la gpurun_out/*_$V* | tail -20
