@@ -272,16 +272,21 @@ k_pa_plan_bins(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t* 
         sTw[warp][lane] = T0;
         sTw[warp][lane + 32] = T1;
         __syncwarp();
-        // the kernel's schedule: unit u = b * RB + rb runs on CTA u % sms
+        // the kernel's schedule: unit u = b * RB + rb runs on CTA u % sms, i.e. CTA i gets RB / sms units of block b, plus
+        // one if (i - first CTA of the block) mod sms < RB % sms
         float worst = 0.f;
+        const int uq = pc.RB / pc.sms, ur = pc.RB % pc.sms;
         for (int i = lane; i < pc.sms; i += 32) {
             float t = 0.f;
+            int u0m = 0;                                                         // (b * RB) % sms
             for (int b = 0; b < nb; ++b) {
                 const int Tb = sTw[warp][b];
-                const long long u0 = (long long)b * pc.RB;                       // units u0 .. u0 + RB - 1
-                const int first = (int)((i - u0 % pc.sms + pc.sms) % pc.sms);    // first rb that lands on CTA i
-                const int cntu = first < pc.RB ? (pc.RB - first + pc.sms - 1) / pc.sms : 0;
+                int d = i - u0m;
+                d += d < 0 ? pc.sms : 0;
+                const int cntu = uq + (d < ur ? 1 : 0);
                 if (Tb > 0) t += (float)cntu * ((float)Tb * pc.step_cycles + pc.unit_cycles);
+                u0m += ur;
+                u0m -= u0m >= pc.sms ? pc.sms : 0;
             }
             worst = fmaxf(worst, t);
         }

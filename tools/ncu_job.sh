@@ -11,15 +11,18 @@ for w in cfg3 cfg4 cfg5 cfg4i; do
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r01_launches_${w}_$V.csv $B --workload $w --steps 2 --warmup 1 > gpurun_out/ncu_l_$w.log 2>&1
 done
 # full captures of the dominant kernels (one launch each, after the warm-up launches)
-cap() {  # workload kernel-regex name
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$2 -s 1 -c 1 -f -o gpurun_out/r01_$3_$V $B --workload $1 --steps 1 --warmup 1 > gpurun_out/ncu_$3.log 2>&1
+# (gpurun copies at most 64 MiB back: the reports are summarised here and only the first one is kept)
+cap() {  # workload kernel-regex name [traffic-key]
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$2 -s 1 -c 1 -f -o /tmp/r01_$3_$V $B --workload $1 --steps 1 --warmup 1 > gpurun_out/ncu_$3.log 2>&1
+  python tools/ncu_summary.py /tmp/r01_$3_$V.ncu-rep gpurun_out/r01_$3_${V}_ncu_summary.json ${4:+--traffic-key $4} --traffic-out gpurun_out/roofline_traffic.json
 }
-cap cfg3 k_poolacc poolacc
+cap cfg3 k_poolacc poolacc cfg3
+cp /tmp/r01_poolacc_$V.ncu-rep gpurun_out/
 cap cfg3 k_pa_normalize_scatter normscatter
 cap cfg3 k_exact_q30 exact
 cap cfg3 k_pg_merge merge
-cap cfg5 k_poolacc cfg5_poolacc
-cap cfg4 "k_poolgemm<" cfg4_poolgemm
-cap cfg4i k_gemv8 cfg4i_gemv
-cap cfg4ii "k_poolgemm<" cfg4ii_poolgemm
-ls -la gpurun_out/*_$V* | tail -20
+cap cfg5 k_poolacc cfg5_poolacc cfg5
+cap cfg4 "k_poolgemm<" cfg4_poolgemm cfg4
+cap cfg4i k_gemv8 cfg4i_gemv cfg4i
+cap cfg4ii "k_poolgemm<" cfg4ii_poolgemm cfg4ii
+ls -la gpurun_out/ | tail -30

@@ -52,6 +52,9 @@ def main() -> int:
     traffic_key = None
     if "--traffic-key" in sys.argv:
         traffic_key = sys.argv[sys.argv.index("--traffic-key") + 1]
+    traffic_path = "profiles/roofline_traffic.json"
+    if "--traffic-out" in sys.argv:                 # e.g. gpurun_out/roofline_traffic.json when summarising on the GPU box
+        traffic_path = sys.argv[sys.argv.index("--traffic-out") + 1]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     header, units, data = rows[0], rows[1], rows[2:]
@@ -81,7 +84,7 @@ def main() -> int:
     with open(out, "w") as fh:
         json.dump(summary, fh, indent=1)
     if traffic_key:
-        path = "profiles/roofline_traffic.json"
+        path = traffic_path
         try:
             table = json.load(open(path))
         except (OSError, ValueError):
