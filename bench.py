@@ -295,7 +295,13 @@ def run_cfg5(args, cfg):
             "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
             "traffic": ncu_traffic("cfg5", kname, args.scale == 1.0),
             "peak_source": f"{pk_src} bf16 burst (kernel timed alone, ~1 ms)", "avg_launch_ms": avg_ms}
-    hs, hl = seg.cpu().numpy(), lab.cpu().numpy()
+    # e2e through the host-pointer C-ABI call: inputs in PINNED host memory (the contract's rule), H2D + D2H inside
+    h_seg = torch.empty((N, D), dtype=torch.float32, pin_memory=True)
+    h_lab = torch.empty((N,), dtype=torch.int32, pin_memory=True)
+    h_seg.copy_(seg)
+    h_lab.copy_(lab)
+    torch.cuda.synchronize()
+    hs, hl = h_seg.numpy(), h_lab.numpy()
     ctx.affinity_pooled(hs, hl, L, dtype=1, pool=0)
     t0 = time.perf_counter()
     e_steps = max(1, min(3, args.steps))

@@ -179,6 +179,9 @@ int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, 
     // row-slot tile width: wide tiles for dense scans, narrow for the few re-scored candidates
     // the candidate list is front-packed, so on the sparse path tiles of 4 slots let the empty tail exit at once
     int RT = d_cand_row ? 4 : (nslot >= 16 ? 16 : (nslot > 4 ? 8 : 4));
+    // dense scans of a small bank (one meeting against a few hundred profiles): prefer enough CTAs for ~3 waves over
+    // wide tiles
+    while (!d_cand_row && RT > 4 && ((nslot + RT - 1) / RT) * (int64_t)ngroups < 3 * (int64_t)c->sm_count) RT /= 2;
     int64_t ntiles64 = (nslot + RT - 1) / RT;
     int64_t blocks = ntiles64 * ngroups;
     if (blocks > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "exact path: too many (group,row-tile) blocks");
