@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from speaker_diarization_toolkit_b200 import _native, identify_cli, plugin_api, signals, store, transcript
+from speaker_diarization_toolkit_b200 import _native, identify_cli, plugin_api, schemas, signals, store, transcript
 
 ROOT = Path(__file__).resolve().parent.parent
 GOLD = Path(__file__).parent / "golden"
@@ -346,3 +346,40 @@ def test_enroll_through_the_reference_cli_with_the_b200_backend(tmp_path):
         assert bank.P == 1 and np.array_equal(bank.rows[0], want)
     finally:
         os.environ.pop("SPEAKERS_EMBEDDINGS_DIR", None)
+
+
+# ---- schemas: the validators the new records must pass -------------------------------------------
+def test_schema_validators_match_the_reference_golden():
+    cases = load("schemas_golden.json")
+    assert len(cases) >= 170
+    n_err = 0
+    for c in cases:
+        fn = schemas.validate_embedding if c["kind"] == "embedding" else schemas.validate_profile
+        assert fn(c["record"]) == c["warnings"], c["record"]
+        if c["strict_error"] is None:
+            assert fn(c["record"], strict=True) == c["warnings"]
+        else:
+            n_err += 1
+            with pytest.raises(schemas.ValidationError) as exc:
+                fn(c["record"], strict=True)
+            assert str(exc.value) == c["strict_error"]
+    assert n_err > 50
+
+
+def test_enrolled_records_pass_the_validators(tmp_path, monkeypatch, capsys):
+    """What `enroll` writes is valid by the mirror and, where the reference tree is present, by the reference itself."""
+    monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(tmp_path))
+    monkeypatch.delenv("SPEAKER_BACKENDS_CONFIG", raising=False)
+    audio, *_ = _enroll_store(tmp_path)
+    assert identify_cli.main(["-q", "enroll", "alice", str(audio), "-s", "0:11"]) == 0
+    capsys.readouterr()
+    prof = store.load_speaker("alice")
+    assert schemas.validate_profile(prof, strict=True) == []
+    assert schemas.validate_embedding(prof["embeddings"]["b200"][0], strict=True) == []
+    if Path("/root/reference/speaker_detection_backends/schemas.py").exists():
+        sys.path.insert(0, "/root/reference")
+        try:
+            from speaker_detection_backends import schemas as ref_schemas
+            assert ref_schemas.validate_profile(prof, strict=True) == []
+        finally:
+            sys.path.remove("/root/reference")
