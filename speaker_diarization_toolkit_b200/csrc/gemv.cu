@@ -5,11 +5,12 @@
 // overlap; for <= 8 query segments that is 32x wasted tensor work and an exposed TMA round trip per 128 rows.  Here the
 // bank is streamed through shared memory by TMA (one elected producer thread, 2-D boxes of 64 rows x 64 bf16 with the
 // 128-byte swizzle): each of the eight consumer warps owns a private ring of 3 stages (mbarrier full/empty pairs; a
-// barrier is only ever waited on by its own warp, phase after phase), 192 KB in flight per SM.  The arithmetic is the
+// barrier is only ever waited on by its own warp, phase after phase), 192 KB in flight per SM (sixteen consumer warps,
+// 32-row stages).  The arithmetic is the
 // one tensor-core shape that fits 8 queries exactly: mma.sync m16n8k16 (bf16 in, fp32 accumulate) -- bank rows are the
-// M side (ldmatrix.x4 straight from the swizzled tile, conflict-free), the 8 queries are the N side and live in
-// registers for the whole kernel (2 words per 16-wide K step), 16 accumulator registers hold a 64-row chunk across the
-// K chunks.  That is ~100 instructions per 64x64 stage, so the SM only waits for HBM.  After the last K chunk the
+// M side (ldmatrix.x4 straight from the swizzled tile, conflict-free), the 8 queries are the N side (fragments pre-packed
+// in shared memory, 2 words per lane and 16-wide K step), 8 accumulator registers hold a 32-row chunk across the K
+// chunks.  That is ~50 instructions per 32x64 stage, so the SM only waits for HBM.  After the last K chunk the
 // accumulator fragments are transposed through shared memory; lane i then owns rows i and i+32, pools their scores per
 // label group and flushes the candidate slots exactly like the tensor-core epilogues (tcgen05.cuh: pg_flush), so merge /
 // canonical re-score / certificate downstream are unchanged.  (tcgen05.mma needs N >= 16 and a TMEM round trip; for
@@ -19,48 +20,45 @@
 #include "tcgen05.cuh"
 
 #define GV_NQ 8
-#define GV_CW 8                      // consumer warps
+#define GV_CW 16                     // consumer warps
 #define GV_THREADS (32 * (GV_CW + 1))
 #define GV_RING 3                    // stages per consumer warp
 #define GV_STAGES (GV_CW * GV_RING)
-#define GV_STAGE_BYTES 8192u         // 64 rows x 64 bf16
+#define GV_ROWS 32                   // bank rows per chunk / stage (one candidate sub-slot)
+#define GV_STAGE_BYTES 4096u         // 32 rows x 64 bf16
 
 struct GvParams {
     PgParams pg;
     int32_t N, G, Dp;
     int32_t nsub;                 // sub-slots per label group = ceil(P / 32)
-    int32_t nchunk;               // 64-row chunks of the bank = ceil(P / 64)
+    int32_t nchunk;               // 32-row chunks of the bank (== nsub)
 };
 
 // Pools and flushes one 64-row chunk (two 32-row sub-slots).  Out of line and rolled: every warp runs this only a couple
 // of times, so instruction-cache footprint matters more than unrolling.
-static __device__ __noinline__ void gv_flush_chunk(const GvParams& q, const float* __restrict__ sc /*[64][GV_NQ]*/, const int32_t* s_grp,
+static __device__ __noinline__ void gv_flush_chunk(const GvParams& q, const float* __restrict__ sc /*[32][GV_NQ]*/, const int32_t* s_grp,
                                                    const int32_t* s_len, int64_t chunk, int lane) {
     const PgParams& p = q.pg;
+    const int64_t row = chunk * GV_ROWS + lane;
+    const float* v = sc + lane * GV_NQ;
+    float a = p.pool == 0 ? 0.f : -3.0e38f;
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        const int64_t row = chunk * 64 + 32 * h + lane;
-        const int64_t sub32 = chunk * 2 + h;                    // 32-row sub-slot index
-        if (sub32 >= q.nsub) break;                             // (uniform) the bank ends inside the first half
-        const float* v = sc + (32 * h + lane) * GV_NQ;
-        float a = p.pool == 0 ? 0.f : -3.0e38f;
-#pragma unroll 1
-        for (int s = 0; s < q.N; ++s) {
-            a = p.pool == 0 ? a + v[s] : fmaxf(a, v[s]);
-            const int g = s_grp[s];
-            if (s + 1 == q.N || s_grp[s + 1] != g) {
-                pg_flush(p, a, g, s_len[s], (int64_t)(g - p.g_base) * q.nsub + sub32, lane, row);
-                a = p.pool == 0 ? 0.f : -3.0e38f;
-            }
+    for (int s = 0; s < q.N; ++s) {
+        a = p.pool == 0 ? a + v[s] : fmaxf(a, v[s]);
+        const int g = s_grp[s];
+        if (s + 1 == q.N || s_grp[s + 1] != g) {
+            pg_flush(p, a, g, s_len[s], (int64_t)(g - p.g_base) * q.nsub + chunk, lane, row);
+            a = p.pool == 0 ? 0.f : -3.0e38f;
         }
     }
 }
 
 template <int KCH>
 __global__ void __launch_bounds__(GV_THREADS, 1)
-k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const uint32_t* __restrict__ seg /*[N, Dp/2] bf16x2*/, const GvParams q) {
+k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const uint32_t* __restrict__ seg /*[N, Dp/2] bf16x2*/, const __grid_constant__ GvParams q) {
     extern __shared__ uint8_t gv_smem_raw[];
-    __shared__ __align__(16) float s_c[GV_CW][64][GV_NQ];     // accumulator transpose: [row of the chunk][query]
+    __shared__ __align__(16) float s_c[GV_CW][GV_ROWS][GV_NQ]; // accumulator transpose: [row of the chunk][query]
+    __shared__ __align__(8) uint2 s_bq[KCH * 4][32];           // B fragments of every 16-wide K step, per lane
     __shared__ int32_t s_grp[GV_NQ];              // label group of query s (-1: padding)
     __shared__ int32_t s_len[GV_NQ];              // segments of that group
     __shared__ __align__(8) uint64_t s_bar[2 * GV_STAGES];
@@ -90,6 +88,18 @@ k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const uint32_t* __restrict
         s_grp[s] = g;
         s_len[s] = len;
     }
+    // B fragments (mma.sync m16n8k16 "col" operand): lane l holds query n = l / 4, k = 16 * ks + 2 * (l % 4) (+8).  Kept in
+    // shared memory so that the K loop stays rolled: every warp runs the loop body only a couple of times, and a fully
+    // unrolled kernel spent more time missing the instruction cache than computing
+    for (int i = threadIdx.x; i < KCH * 4 * 32; i += GV_THREADS) {
+        const int ks = i >> 5, l = i & 31, n = l >> 2, kw = l & 3;
+        uint2 b = make_uint2(0u, 0u);
+        if (n < q.N) {
+            b.x = __ldg(seg + (int64_t)n * pitch + ks * 8 + kw);
+            b.y = __ldg(seg + (int64_t)n * pitch + ks * 8 + 4 + kw);
+        }
+        s_bq[ks][l] = b;
+    }
     __syncthreads();
     // chunks of this CTA: blockIdx.x, + gridDim.x, ...; the k-th goes to consumer warp k % GV_CW as that warp's chunk
     // number n = k / GV_CW; its K chunk kc is the warp's stage number m = KCH * n + kc -> stage (m % GV_RING) of its ring
@@ -110,7 +120,7 @@ k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const uint32_t* __restrict
                         const uint32_t use = (uint32_t)(m / GV_RING);
                         pg_mbar_wait(bar_empty + 8 * st, (use & 1u) ^ 1u);
                         pg_mbar_expect_tx(bar_full + 8 * st, GV_STAGE_BYTES);
-                        pg_tma_load_2d(ring + st * GV_STAGE_BYTES, &tmapBank, kc * 64, (int32_t)(chunk * 64), bar_full + 8 * st);   // rows past P: zero fill
+                        pg_tma_load_2d(ring + st * GV_STAGE_BYTES, &tmapBank, kc * 64, (int32_t)(chunk * GV_ROWS), bar_full + 8 * st);   // rows past P: zero fill
                     }
                 }
             }
@@ -118,43 +128,34 @@ k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const uint32_t* __restrict
         return;
     }
     const int cw = warp - 1;
-    // B fragments of every 16-wide K step: query n = lane / 4, k = 16 * ks + 2 * (lane % 4) (+8)
-    uint32_t bq[KCH * 4][2];
-    {
-        const int n = lane >> 2, kw = lane & 3;
-#pragma unroll
-        for (int ks = 0; ks < KCH * 4; ++ks) {
-            bq[ks][0] = n < q.N ? __ldg(seg + (int64_t)n * pitch + ks * 8 + kw) : 0u;
-            bq[ks][1] = n < q.N ? __ldg(seg + (int64_t)n * pitch + ks * 8 + 4 + kw) : 0u;
-        }
-    }
     // ldmatrix.x4 source row of this lane inside a 16-row tile, and which 8-wide K half it addresses
     const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = lane >> 4;
     int64_t m = 0;                                  // this warp's stage counter (walks its private ring)
     for (int64_t k = cw; k < n_mine; k += GV_CW) {
         const int64_t chunk = blockIdx.x + k * gridDim.x;
-        float acc[4][4];
+        float acc[GV_ROWS / 16][4];
 #pragma unroll
-        for (int rt = 0; rt < 4; ++rt)
+        for (int rt = 0; rt < GV_ROWS / 16; ++rt)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[rt][i] = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int kc = 0; kc < KCH; ++kc, ++m) {
             const int st = cw * GV_RING + (int)(m % GV_RING);
             const uint32_t use = (uint32_t)(m / GV_RING);
             pg_mbar_wait(bar_full + 8 * st, use & 1u);
             const uint32_t tile = ring + st * GV_STAGE_BYTES;
 #pragma unroll
-            for (int rt = 0; rt < 4; ++rt) {
-                const int r = rt * 16 + lrow;                       // row of the 64-row tile; swizzle: 16-byte piece ^= row % 8
+            for (int rt = 0; rt < GV_ROWS / 16; ++rt) {
+                const int r = rt * 16 + lrow;                       // row of the tile; swizzle: 16-byte piece ^= row % 8
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint32_t addr = tile + r * 128 + (((2 * ks + lhalf) ^ (r & 7)) << 4);
                     uint32_t a0, a1, a2, a3;
                     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+                    const uint2 b = s_bq[kc * 4 + ks][lane];
                     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                                  : "+f"(acc[rt][0]), "+f"(acc[rt][1]), "+f"(acc[rt][2]), "+f"(acc[rt][3])
-                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bq[kc * 4 + ks][0]), "r"(bq[kc * 4 + ks][1]));
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
                 }
             }
             __syncwarp();
@@ -163,13 +164,13 @@ k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const uint32_t* __restrict
         // transpose: fragment (row = lane/4 (+8), queries 2*(lane%4), +1)  ->  lane <-> row
         __syncwarp();
 #pragma unroll
-        for (int rt = 0; rt < 4; ++rt) {
+        for (int rt = 0; rt < GV_ROWS / 16; ++rt) {
             const int r = rt * 16 + (lane >> 2), cq = 2 * (lane & 3);
             *reinterpret_cast<float2*>(&s_c[cw][r][cq]) = make_float2(acc[rt][0], acc[rt][1]);
             *reinterpret_cast<float2*>(&s_c[cw][r + 8][cq]) = make_float2(acc[rt][2], acc[rt][3]);
         }
         __syncwarp();
-        // lane <-> bank rows chunk*64 + lane (+32): pool the queries of each label group (ascending segment order), flush
+        // lane <-> bank row chunk*32 + lane: pool the queries of each label group (ascending segment order), flush
         gv_flush_chunk(q, &s_c[cw][0][0], s_grp, s_len, chunk, lane);
         __syncwarp();                                               // s_c is rewritten by the next chunk
     }
@@ -211,12 +212,12 @@ int sdk_launch_gemv_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int64_t 
     q.G = G;
     q.Dp = Dp;
     q.nsub = nsub;
-    q.nchunk = (int32_t)((P + 63) / 64);
+    q.nchunk = nsub;
     const int grid = (int)std::min<int64_t>((q.nchunk + GV_CW - 1) / GV_CW, (int64_t)c->sm_count);
     const size_t smem = (size_t)GV_STAGES * GV_STAGE_BYTES + 1024;
     if (!c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "gemv path: cuTensorMapEncodeTiled unavailable");
     CUtensorMap tb;
-    SDK_TRY(pg_make_tmap(c, &tb, d_bank, P, Dp, 64));
+    SDK_TRY(pg_make_tmap(c, &tb, d_bank, P, Dp, GV_ROWS));
     {
         sdk_prof_scope ps(c, "poolgemm");         // stage A of the certified top-k, whichever kernel runs it
         const uint32_t* s32 = reinterpret_cast<const uint32_t*>(d_seg);

@@ -469,7 +469,7 @@ struct PaParams {
 
 template <int KCH, int MT, int STAGES>
 __global__ void __launch_bounds__(MT == 2 ? PG_THREADS2 : PG_THREADS, 1)
-k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const PaParams q) {
+k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ PaParams q) {
     constexpr int NC = PA_NB;
     constexpr uint32_t A_TILE = 128 * 128;
     constexpr uint32_t A_BYTES = MT * KCH * A_TILE;
