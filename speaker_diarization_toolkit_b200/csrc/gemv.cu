@@ -34,9 +34,10 @@ struct GvParams {
     int32_t nchunk;               // 32-row chunks of the bank (== nsub)
 };
 
-// Pools and flushes one 64-row chunk (two 32-row sub-slots).  Out of line and rolled: every warp runs this only a couple
-// of times, so instruction-cache footprint matters more than unrolling.
-static __device__ __noinline__ void gv_flush_chunk(const GvParams& q, const float* __restrict__ sc /*[32][GV_NQ]*/, const int32_t* s_grp,
+// Pools and flushes one 32-row chunk (one sub-slot per label group).  Rolled loops: every warp runs this only a few
+// times, so instruction-cache footprint matters more than unrolling; inlined so that the shared-memory operands are
+// read with shared-space loads (a generic-pointer version stalled on every label).
+static __device__ __forceinline__ void gv_flush_chunk(const GvParams& q, const float* __restrict__ sc /*[32][GV_NQ]*/, const int32_t* s_grp,
                                                    const int32_t* s_len, int64_t chunk, int lane) {
     const PgParams& p = q.pg;
     const int64_t row = chunk * GV_ROWS + lane;

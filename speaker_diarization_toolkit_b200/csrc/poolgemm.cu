@@ -508,8 +508,8 @@ __global__ void k_pg_ranges(const int64_t* __restrict__ goff, int32_t g_a, int32
 // ---- merge of the per-(row block, warp) candidate slots of one label group ------------------------
 // Picks the `ncand` rows with the largest approximate score and the upper bound on the approximate score of every row
 // that is NOT in the list.  With no threshold every slot is full (half the bank per label group), so the scan is
-// organised to touch the slots twice: pass A takes, per thread, the largest key of its sub-slots; the ncand-th largest
-// of those per-thread maxima is a lower bound T0 on the ncand-th largest key overall.  Pass B compacts the few entries
+// organised to touch the slots twice: pass A takes, per group of threads, the largest key of its sub-slots; the ncand-th
+// largest of those 32 / 64 group maxima is a lower bound T0 on the ncand-th largest key overall.  Pass B compacts the few entries
 // >= T0 into shared memory, where they are ranked (descending key, ties by position).  An overfull compaction
 // (many equal keys) falls back to a radix select over the slots.
 #define PG_MERGE_THREADS 1024
@@ -578,15 +578,29 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const
         if (tid == 0) gbound[g] = sdk_funkey(s_bound_key);
         return;
     }
-    // T0 = ncand-th largest thread maximum (0 when fewer than ncand threads saw an entry)
+    // T0 = ncand-th largest of NG group maxima (NG = 32 or 64 >= ncand groups of consecutive threads; every group maximum
+    // is a distinct entry, so at least ncand entries are >= T0; 0 when fewer than ncand groups saw an entry)
     {
-        int rank = 0;
-        for (int j = 0; j < (int)blockDim.x; ++j) { const unsigned int o = s_key[j]; rank += (o > mymax || (o == mymax && j < tid)) ? 1 : 0; }
-        if (rank == ncand - 1) s_t0 = mymax;
+        const int NG = ncand <= 32 ? 32 : 64;
+        const int W = (int)blockDim.x / NG;                 // 4..32 threads per group, a power of two inside one warp
+        unsigned int gm = mymax;
+        for (int off = W >> 1; off >= 1; off >>= 1) {
+            const unsigned int o = __shfl_xor_sync(0xffffffffu, gm, off);
+            gm = o > gm ? o : gm;
+        }
+        __syncthreads();                                    // all thread maxima were published above; reuse s_key[0..NG)
+        if ((tid & (W - 1)) == 0) s_key[tid / W] = gm;
+        __syncthreads();
+        if (tid < NG) {
+            const unsigned int mine = s_key[tid];
+            int rank = 0;
+            for (int j = 0; j < NG; ++j) { const unsigned int o = s_key[j]; rank += (o > mine || (o == mine && j < tid)) ? 1 : 0; }
+            if (rank == ncand - 1) s_t0 = mine;
+        }
     }
     __syncthreads();
     const unsigned int T0 = s_t0;
-    __syncthreads();                        // everyone has read the maxima before s_key is reused
+    __syncthreads();                        // everyone has read T0 / the maxima before s_key is reused
     // ---- pass B: compact the entries >= T0 ----
     for (int s = tid; s < nsub; s += blockDim.x) {
         const int c0 = cnt[s];
