@@ -119,7 +119,7 @@ __device__ __forceinline__ void pg_epi_job(PgPool& st, const PgParams& p, uint32
 // N = NC = 256 keeps the per-MMA shared-memory operand fetch (4 KB of A + NC*32 B of B) under the MMA time.
 template <int KCH, int MT, int NC, int STAGES>
 __global__ void __launch_bounds__(MT == 2 ? PG_THREADS2 : PG_THREADS, 1)
-k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ PgParams p) {
+k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const PgParams p) {
     constexpr uint32_t A_TILE = 128 * 128;               // 128 rows x 64 bf16
     constexpr uint32_t A_BYTES = MT * KCH * A_TILE;
     constexpr uint32_t B_STAGE = NC * 128;
@@ -325,7 +325,7 @@ __device__ __forceinline__ void pg_commit_2sm(uint32_t bar) {
 
 template <int KCH, int MT, int NC, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MT == 2 ? PG_THREADS2 : PG_THREADS, 1)
-k_poolgemm2(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ PgParams p) {
+k_poolgemm2(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const PgParams p) {
     constexpr uint32_t A_TILE = 128 * 128;               // this CTA's 128 rows x 64 bf16 of a 256-row tile
     constexpr uint32_t A_BYTES = MT * KCH * A_TILE;
     constexpr uint32_t B_HALF = (NC / 2) * 128;          // this CTA's half of a chunk's K stage
