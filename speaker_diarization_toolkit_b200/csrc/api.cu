@@ -342,7 +342,8 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
     // epilogue (D <= 256) or where there are enough groups for tight size classes, and only if the layout's zero
     // padding stays under 12 %.
     // a handful of query segments: one HBM-bound pass over the bank on the CUDA cores (gemv.cu)
-    const bool use_gemv = path == 2 && c->opt_gemv && sdk_gemv_applicable(N, Dp);
+    // (its candidate slots are indexed by label id: a handful of segments scattered over very many labels stays generic)
+    const bool use_gemv = path == 2 && c->opt_gemv && sdk_gemv_applicable(N, Dp) && L <= 64;
     bool use_acc = path == 2 && !use_gemv && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048;
     if (use_acc && c->opt_acc != 2 && !(Dp <= 256 || L > 2048)) use_acc = false;
     int64_t acc_steps = 0;
@@ -373,7 +374,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         const void* seg_ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
         SDK_TRY(sdk_reserve(c, c->qpool, (size_t)L * P * 8));
         SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, nullptr, L, nullptr, P,
-                                 pool, (long long*)c->qpool.p));
+                                 pool, (long long*)c->qpool.p, nullptr, N));
         SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L, nullptr, P, pool,
                                   (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
                                   c->row_offset, nullptr, 0.f, nullptr, 0, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
@@ -652,10 +653,12 @@ __global__ void k_affinity_finish(const long long* __restrict__ qpool /*[L,N]*/,
     out_nl[i] = sdk_pool_finish(qpool[(int64_t)l * N + n], goff[l + 1] - goff[l], pool);
 }
 // out_ll[a,b] = mean over the segments of label a of out_nl[.,b], pooled in Q30 integers
-__global__ void k_affinity_ll(const float* __restrict__ out_nl, const int64_t* __restrict__ goff, int32_t L,
+__global__ void k_affinity_ll(const float* __restrict__ out_nl, const int64_t* __restrict__ goff, int32_t L, int64_t N,
                               float* __restrict__ out_ll) {
     const int a = blockIdx.x, b = blockIdx.y;
-    const int64_t s0 = goff[a], s1 = goff[a + 1];
+    int64_t s0 = goff[a], s1 = goff[a + 1];            // (clamped: on the exact path the label flag is only read at the end)
+    s0 = s0 < 0 ? 0 : (s0 > N ? N : s0);
+    s1 = s1 < 0 ? 0 : (s1 > N ? N : s1);
     long long acc = 0;
     for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) acc += __double2ll_rn((double)out_nl[s * L + b] * SDK_Q30);
     __shared__ long long sh[32];
@@ -719,7 +722,7 @@ int sdk_affinity_pooled_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg
         const void* ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
         SDK_TRY(sdk_reserve(c, c->qpool, (size_t)L * N * 8));
         SDK_TRY(sdk_launch_exact(c, ops, ops, bf16, D, bf16 ? Dp : D, (const int64_t*)c->goff.p, nullptr, L, nullptr, N, pool,
-                                 (long long*)c->qpool.p));
+                                 (long long*)c->qpool.p, nullptr, N));
         sdk_prof_scope ps(c, "affinity");
         int64_t tot = N * L;
         k_affinity_finish<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>((const long long*)c->qpool.p,
@@ -728,7 +731,7 @@ int sdk_affinity_pooled_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg
         SDK_CUDA(c, cudaGetLastError());
     }
     if (d_out_ll) {
-        k_affinity_ll<<<dim3(L, L), 256, 0, c->stream>>>(d_out_nl, (const int64_t*)c->goff.p, L, d_out_ll);
+        k_affinity_ll<<<dim3(L, L), 256, 0, c->stream>>>(d_out_nl, (const int64_t*)c->goff.p, L, N, d_out_ll);
         c->launches++;
         SDK_CUDA(c, cudaGetLastError());
     }

@@ -132,7 +132,8 @@ int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_
 int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, int32_t is_bf16,
                      int32_t D, int32_t pitch, const int64_t* d_goff, const int32_t* d_glist,
                      int32_t ngroups, const int32_t* d_cand_row, int64_t nslot, int32_t pool,
-                     long long* d_qpool /*[ngroups,nslot]*/, const PaGroup* d_grp = nullptr);
+                     long long* d_qpool /*[ngroups,nslot]*/, const PaGroup* d_grp = nullptr,
+                     int64_t n_seg = -1 /* >= 0: clamp group offsets to [0, n_seg] (labels not validated yet) */);
 // select: speaker dedupe + threshold + ordered top-k (+ certificate on the sparse path)
 int sdk_launch_select(sdk_ctx* c, const long long* d_qpool, const int64_t* d_goff,
                       const int32_t* d_glist, int32_t ngroups, const int32_t* d_cand_row,

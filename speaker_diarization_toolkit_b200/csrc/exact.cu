@@ -85,14 +85,18 @@ __global__ void __launch_bounds__(SDK_EX_THREADS)
 k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops, int32_t D, int32_t pitch,
             const int64_t* __restrict__ goff, const int32_t* __restrict__ glist,
             const int32_t* __restrict__ cand_row, int64_t nslot, int32_t ntiles, int32_t pool,
-            long long* __restrict__ qpool, const PaGroup* __restrict__ grp) {
+            long long* __restrict__ qpool, const PaGroup* __restrict__ grp, int64_t n_seg) {
     __shared__ double bs[SDK_EX_DC][RT];
     __shared__ int32_t srow[RT];
     const int tid = threadIdx.x;
     const int32_t gi = blockIdx.x / ntiles;
     const int32_t tile = blockIdx.x - gi * ntiles;
     const int32_t g = glist ? glist[gi] : gi;
-    const int64_t s0 = goff[g], s1 = goff[g + 1];
+    int64_t s0 = goff[g], s1 = goff[g + 1];
+    if (n_seg >= 0) {       // labels not validated yet (exact path: the flag is read at fetch time): never read past the input
+        s0 = s0 < 0 ? 0 : (s0 > n_seg ? n_seg : s0);
+        s1 = s1 < 0 ? 0 : (s1 > n_seg ? n_seg : s1);
+    }
     if (s1 <= s0) return;
     // row of segment t in seg_ops: rbase + (t / gc) * gstep + t % gc   (plain layout: gc == 1, gstep == 1)
     int64_t rbase = s0, gstep = 1;
@@ -169,7 +173,7 @@ __global__ void k_fill_ll(long long* p, int64_t n, long long v) {
 
 int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, int32_t is_bf16, int32_t D,
                      int32_t pitch, const int64_t* d_goff, const int32_t* d_glist, int32_t ngroups,
-                     const int32_t* d_cand_row, int64_t nslot, int32_t pool, long long* d_qpool, const PaGroup* d_grp) {
+                     const int32_t* d_cand_row, int64_t nslot, int32_t pool, long long* d_qpool, const PaGroup* d_grp, int64_t n_seg) {
     if (ngroups <= 0 || nslot <= 0) return SDK_OK;
     sdk_prof_scope ps(c, "exact");
     int64_t total = (int64_t)ngroups * nslot;
@@ -195,8 +199,8 @@ int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, 
     int ntiles = (int)ntiles64;
 #define SDK_EX_CASE(RTV)                                                                                   \
     do {                                                                                                   \
-        if (is_bf16) k_exact_q30<RTV, true><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool, d_grp); \
-        else k_exact_q30<RTV, false><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool, d_grp); \
+        if (is_bf16) k_exact_q30<RTV, true><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool, d_grp, n_seg); \
+        else k_exact_q30<RTV, false><<<grid, SDK_EX_THREADS, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, d_cand_row, nslot, ntiles, pool, d_qpool, d_grp, n_seg); \
     } while (0)
     if (RT == 16) SDK_EX_CASE(16);
     else if (RT == 8) SDK_EX_CASE(8);
