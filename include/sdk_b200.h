@@ -79,7 +79,7 @@ void sdk_destroy(sdk_ctx* ctx);
 const char* sdk_last_error(sdk_ctx* ctx);
 /* tuning / test knobs: "path" (0 auto, 1 exact SIMT, 2 tcgen05), "eps" (certificate margin),
  * "profile" (1 = record per-kernel CUDA-event times), "cand" (re-scored candidates per label),
- * "chunk_mb" (host-buffer sdk_identify: size of the H2D/compute pipeline chunks, default 512),
+ * "chunk_mb" (host-buffer sdk_identify: size of the H2D/compute pipeline chunks, default 128),
  * "cta_group" (1 | 2: tcgen05 kernel variant), "acc" (0 off | 1 auto | 2 force: pool inside the MMA accumulation),
  * "gemv" (1 = stream the bank on the CUDA cores when there are <= 8 query segments) */
 int sdk_set_option(sdk_ctx* ctx, const char* key, double value);

@@ -48,7 +48,7 @@ struct sdk_ctx {
     int opt_cta_group = 1;     // tcgen05 path: 1 = single CTA (measured faster at D <= 256), 2 = CTA pairs (cta_group::2)
     int opt_acc = 1;           // mean pooling with many label groups: pool inside the MMA accumulation (poolacc.cu)
     int opt_gemv = 1;          // <= 8 query segments: stream the bank once on the CUDA cores (gemv.cu) instead of tcgen05 tiles
-    int opt_chunk_mb = 512;    // host-buffer identify: H2D/compute pipeline chunk size
+    int opt_chunk_mb = 128;    // host-buffer identify: H2D/compute pipeline chunk size
     // bank
     int64_t P = 0;
     int32_t D = 0, Dp = 0, dtype = 0;

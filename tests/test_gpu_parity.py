@@ -215,7 +215,7 @@ def test_host_pipeline_chunks(ctx, oracle, path, acc):
     try:
         gpu = run_gpu(ctx, case, 1, 0, 0.354, 6, path=path, acc=acc)
     finally:
-        ctx.set_option("chunk_mb", 512)
+        ctx.set_option("chunk_mb", 128)
     assert_same(gpu, run_oracle(oracle, case, 1, 0, 0.354, 6), "pipelined host path")
 
 
