@@ -22,7 +22,7 @@ cap cfg3 k_pa_normalize_scatter normscatter
 cap cfg3 k_exact_q30 exact
 cap cfg3 k_pg_merge merge
 cap cfg5 k_poolacc cfg5_poolacc cfg5
-cap cfg4 "k_poolgemm<" cfg4_poolgemm cfg4
+cap cfg4 "^k_poolgemm$" cfg4_poolgemm cfg4
 cap cfg4i k_gemv8 cfg4i_gemv cfg4i
-cap cfg4ii "k_poolgemm<" cfg4ii_poolgemm cfg4ii
+cap cfg4ii "^k_poolgemm$" cfg4ii_poolgemm cfg4ii
 ls -la gpurun_out/ | tail -30
