@@ -787,13 +787,22 @@ static int pg_launch2(sdk_ctx* c, const pg_cfg& cfg, const CUtensorMap& ta, cons
     }
 }
 
-// columns per range: enough units to balance the persistent CTAs (or CTA pairs), whole groups, multiple of NC
+// Columns per range.  Units (range x row block) are dealt to the persistent CTAs (or CTA pairs) round robin, so the step
+// takes ceil(units / workers) unit times: the number of ranges is chosen to waste little of the last wave while keeping
+// the per-unit bank-tile reload (worth ~384 columns of MMA time) amortised.  Whole groups, multiples of NC.
 static int64_t pg_range_cols(int64_t ncols, int32_t RB, int NC, int64_t workers) {
-    int64_t want_units = workers * 8;
-    int64_t T = (ncols * RB + want_units - 1) / want_units;
+    const double reload = 384.0;
+    int64_t best_n = 1;
+    double best = 1e300;
+    const int64_t n_max = std::max<int64_t>(1, std::min<int64_t>(64, ncols / (4 * NC)));
+    for (int64_t n = 1; n <= n_max; ++n) {
+        const int64_t waves = (n * RB + workers - 1) / workers;
+        const double cost = (double)waves * ((double)ncols / (double)n + reload);
+        if (cost < best * 0.999) { best = cost; best_n = n; }
+    }
+    int64_t T = (ncols + best_n - 1) / best_n;
     T = (T + NC - 1) / NC * NC;
     if (T < 4 * NC) T = 4 * NC;
-    if (T > 65536) T = 65536;
     return T;
 }
 
