@@ -165,6 +165,131 @@ k_exact_q30(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops,
     }
 }
 
+// ---- dense scans (every bank row against every segment of a label): a register-tiled fp64 "GEMM" -----------------------
+// The thread-per-segment kernel above re-reads a label's segments once per row tile and feeds every fp64 fma from its own
+// shared-memory broadcast; fine for a handful of candidate rows, wasteful for a whole bank.  Here a CTA owns a tile of
+// 64 segments x 64 bank rows of one label: both operands are staged once per 32-wide d chunk as fp64 in shared memory
+// (coalesced global loads), a thread keeps a 4 x 4 block of pair accumulators in registers (two 128-bit broadcasts +
+// two 128-bit loads feed 16 fmas).  The arithmetic per pair is unchanged -- one fp64 fma chain over ascending d, then
+// q = rint(score * 2^30) -- and the integer pooling over segments goes through shared-memory and global 64-bit atomics.
+#define SDK_EXD_TS 64          // segments per tile
+#define SDK_EXD_TR 64          // bank rows per tile
+#define SDK_EXD_DC 32          // d chunk
+#define SDK_EXD_LD 66          // padded leading dimension of the staged tiles (doubles)
+
+template <bool BF16>
+__device__ __forceinline__ float sdk_exd_load(const void* __restrict__ ops, int64_t row, int32_t pitch, int d) {
+    if (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ops)[row * (int64_t)pitch + d]);
+    return reinterpret_cast<const float*>(ops)[row * (int64_t)pitch + d];
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+k_exact_dense(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops, int32_t D, int32_t pitch,
+              const int64_t* __restrict__ goff, const int32_t* __restrict__ glist, int64_t P, int32_t ntiles, int32_t pool,
+              long long* __restrict__ qpool, const PaGroup* __restrict__ grp, int64_t n_seg) {
+    __shared__ __align__(16) double s_seg[SDK_EXD_DC][SDK_EXD_LD];
+    __shared__ __align__(16) double s_row[SDK_EXD_DC][SDK_EXD_LD];
+    __shared__ long long s_pool[SDK_EXD_TR];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;        // rows 4*tx.., segments 4*ty..
+    const int32_t gi = blockIdx.x / ntiles;
+    const int32_t tile = blockIdx.x - gi * ntiles;
+    const int32_t g = glist ? glist[gi] : gi;
+    int64_t s0 = goff[g], s1 = goff[g + 1];
+    if (n_seg >= 0) {
+        s0 = s0 < 0 ? 0 : (s0 > n_seg ? n_seg : s0);
+        s1 = s1 < 0 ? 0 : (s1 > n_seg ? n_seg : s1);
+    }
+    if (s1 <= s0) return;
+    int64_t rbase = s0, gstep = 1;
+    int32_t gc = 1;
+    if (grp) { const PaGroup pg = grp[g]; rbase = pg.base; gc = pg.c; gstep = 256; }
+    const int64_t row0 = (int64_t)tile * SDK_EXD_TR;
+    const int nz = gridDim.y;
+    for (int64_t cbase = s0 + (int64_t)blockIdx.y * SDK_EXD_TS; cbase < s1; cbase += (int64_t)nz * SDK_EXD_TS) {
+        double acc[4][4];                                             // [segment][row]
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        if (tid < SDK_EXD_TR) s_pool[tid] = pool == 0 ? 0ll : LLONG_MIN;
+        // staging: thread -> (item = tid / 32 + 8 * it, d = tid % 32): consecutive lanes read consecutive d (coalesced).  The
+        // global loads of chunk c+1 are issued before the fmas of chunk c and land in registers (software pipeline): a
+        // d chunk is only 32 x 16 fmas per thread, far too short to hide an L2 round trip otherwise.
+        const int dd = tid & 31;
+        int64_t seg_row[8];
+        bool seg_live[8], row_live[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int item = (tid >> 5) + 8 * it;
+            const int64_t s = cbase + item;
+            seg_live[it] = s < s1;
+            const int32_t t = (int32_t)(s - s0);
+            seg_row[it] = gc == 1 ? rbase + (int64_t)t * gstep : rbase + (int64_t)(t / gc) * gstep + (t % gc);
+            row_live[it] = row0 + item < P;
+        }
+        float pre_s[8], pre_r[8];                                     // raw operands (fp32 holds bf16 exactly); widened at the store
+        auto fetch = [&](int d0) {
+            const bool dlive = d0 + dd < D;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int item = (tid >> 5) + 8 * it;
+                pre_s[it] = (dlive && seg_live[it]) ? sdk_exd_load<BF16>(seg_ops, seg_row[it], pitch, d0 + dd) : 0.f;
+                pre_r[it] = (dlive && row_live[it]) ? sdk_exd_load<BF16>(bank_ops, row0 + item, pitch, d0 + dd) : 0.f;
+            }
+        };
+        fetch(0);
+        for (int d0 = 0; d0 < D; d0 += SDK_EXD_DC) {
+            __syncthreads();                                          // everyone is done reading the previous chunk
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int item = (tid >> 5) + 8 * it;
+                s_seg[dd][item] = (double)pre_s[it];
+                s_row[dd][item] = (double)pre_r[it];
+            }
+            __syncthreads();
+            if (d0 + SDK_EXD_DC < D) fetch(d0 + SDK_EXD_DC);          // in flight while this chunk is contracted
+#pragma unroll 8
+            for (int k = 0; k < SDK_EXD_DC; ++k) {
+                const double2 a01 = *reinterpret_cast<const double2*>(&s_seg[k][4 * ty]);
+                const double2 a23 = *reinterpret_cast<const double2*>(&s_seg[k][4 * ty + 2]);
+                const double2 b01 = *reinterpret_cast<const double2*>(&s_row[k][4 * tx]);
+                const double2 b23 = *reinterpret_cast<const double2*>(&s_row[k][4 * tx + 2]);
+                const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
+        }
+        // fixed point, pool this thread's 4 segments per row, then over the 16 threads that share the rows
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            long long q = pool == 0 ? 0ll : LLONG_MIN;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (cbase + 4 * ty + i < s1) {
+                    const long long v = __double2ll_rn(acc[i][j] * SDK_Q30);
+                    q = pool == 0 ? q + v : (v > q ? v : q);
+                }
+            }
+            // lanes l and l ^ 16 hold the same rows (ty differs by one): combine before the shared-memory atomic
+            const long long o = __shfl_xor_sync(0xffffffffu, q, 16);
+            q = pool == 0 ? q + o : (o > q ? o : q);
+            if ((tid & 16) == 0) {
+                if (pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_pool[4 * tx + j]), (unsigned long long)q);
+                else atomicMax(&s_pool[4 * tx + j], q);
+            }
+        }
+        __syncthreads();
+        if (tid < SDK_EXD_TR && row0 + tid < P) {
+            long long* dst = qpool + (int64_t)gi * P + row0 + tid;
+            if (pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)s_pool[tid]);
+            else atomicMax(dst, s_pool[tid]);
+        }
+    }
+}
+
 __global__ void k_fill_ll(long long* p, int64_t n, long long v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -180,6 +305,23 @@ int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, 
     int fb = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
     k_fill_ll<<<fb, 256, 0, c->stream>>>(d_qpool, total, pool == 0 ? 0ll : LLONG_MIN);
     c->launches++;
+    if (!d_cand_row && nslot >= SDK_EXD_TR) {
+        // dense scan of a bank: register-tiled kernel; long labels are split over blockIdx.y (64 segments per pass)
+        const int64_t ntiles64 = (nslot + SDK_EXD_TR - 1) / SDK_EXD_TR;
+        const int64_t blocks = ntiles64 * ngroups;
+        if (blocks > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "exact path: too many (group,row-tile) blocks");
+        int nz = 1;
+        if (blocks < 4 * (int64_t)c->sm_count) {
+            nz = (int)((4 * (int64_t)c->sm_count + blocks - 1) / blocks);
+            if (nz > 64) nz = 64;
+        }
+        dim3 grid((unsigned)blocks, (unsigned)nz);
+        if (is_bf16) k_exact_dense<true><<<grid, 256, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, nslot, (int)ntiles64, pool, d_qpool, d_grp, n_seg);
+        else k_exact_dense<false><<<grid, 256, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, nslot, (int)ntiles64, pool, d_qpool, d_grp, n_seg);
+        c->launches++;
+        SDK_CUDA(c, cudaGetLastError());
+        return SDK_OK;
+    }
     // row-slot tile width: wide tiles for dense scans, narrow for the few re-scored candidates
     // the candidate list is front-packed, so on the sparse path tiles of 4 slots let the empty tail exit at once
     int RT = d_cand_row ? 4 : (nslot >= 16 ? 16 : (nslot > 4 ? 8 : 4));
