@@ -133,12 +133,20 @@ class Clocks:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
+    """nvidia-smi sampler.  Started BEFORE the warm-up (the tool needs ~0.2 s to produce its first line), every sample is
+    stamped on arrival, and only the samples that fall inside the timed region [mark_begin, stop] are reported; a region
+    shorter than the sampling period falls back to the samples of the last half second under load."""
+
     def __init__(self, dev_index):
         self.samples, self.proc, self.dev = [], None, dev_index
+        self.t_begin = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -147,12 +155,13 @@ class Clocks:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        time.sleep(0.15)
+        t_end = time.time()
+        time.sleep(0.08)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -160,7 +169,11 @@ class Clocks:
             self.proc.kill()
         mhz, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [ln for ts, ln in self.samples if t0 <= ts <= t_end + 0.03]
+        if len(inside) < 2:
+            inside = [ln for ts, ln in self.samples if t_end - 0.5 <= ts <= t_end + 0.03]
+        for s in inside:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 6:
                 continue
@@ -267,13 +280,14 @@ def run_cfg5(args, cfg):
         ctx.affinity_pooled_dev(seg.data_ptr(), lab.data_ptr(), N, D, L, 1, 0, out_nl.data_ptr(), out_ll.data_ptr())
 
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)          # > L2: inputs (51 MB) would otherwise stay cached
+    clocks = Clocks(0)
+    clocks.start()
     for _ in range(args.warmup):
         step()
     ctx.sync()
     ctx.profile_reset()
     l0 = ctx.launch_count()
-    clocks = Clocks(0)
-    clocks.start()
+    clocks.mark_begin()
     tot = 0.0
     for _ in range(args.steps):
         flush.zero_()
@@ -418,6 +432,9 @@ def main():
         if world > 1:
             dist.barrier()
 
+    clocks = Clocks(local_rank)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         step_dev()
     barrier()
@@ -425,9 +442,7 @@ def main():
     nretry = ctx.last_retry()
     ctx.profile_reset()
     l0 = ctx.launch_count()
-    clocks = Clocks(local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks.mark_begin()
     # working set of one step: raw + operand copies of segments and bank.  Below 2x L2 the inputs would stay cached
     # between steps, so every step is timed on its own after a 256 MB flush write
     Dp_ = (D + 63) // 64 * 64
