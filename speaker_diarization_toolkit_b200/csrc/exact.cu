@@ -183,15 +183,16 @@ __device__ __forceinline__ float sdk_exd_load(const void* __restrict__ ops, int6
     return reinterpret_cast<const float*>(ops)[row * (int64_t)pitch + d];
 }
 
-template <bool BF16>
+template <bool BF16, int RPT /* bank rows per thread: 4 -> 64-row tiles, 2 -> 32-row tiles (more CTAs for small banks) */>
 __global__ void __launch_bounds__(256)
 k_exact_dense(const void* __restrict__ seg_ops, const void* __restrict__ bank_ops, int32_t D, int32_t pitch,
               const int64_t* __restrict__ goff, const int32_t* __restrict__ glist, int64_t P, int32_t ntiles, int32_t pool,
               long long* __restrict__ qpool, const PaGroup* __restrict__ grp, int64_t n_seg) {
     __shared__ __align__(16) double s_seg[SDK_EXD_DC][SDK_EXD_LD];
     __shared__ __align__(16) double s_row[SDK_EXD_DC][SDK_EXD_LD];
+    constexpr int TR = 16 * RPT;                                      // bank rows per tile
     __shared__ long long s_pool[SDK_EXD_TR];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;        // rows 4*tx.., segments 4*ty..
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;        // rows RPT*tx.., segments 4*ty..
     const int32_t gi = blockIdx.x / ntiles;
     const int32_t tile = blockIdx.x - gi * ntiles;
     const int32_t g = glist ? glist[gi] : gi;
@@ -204,15 +205,15 @@ k_exact_dense(const void* __restrict__ seg_ops, const void* __restrict__ bank_op
     int64_t rbase = s0, gstep = 1;
     int32_t gc = 1;
     if (grp) { const PaGroup pg = grp[g]; rbase = pg.base; gc = pg.c; gstep = 256; }
-    const int64_t row0 = (int64_t)tile * SDK_EXD_TR;
+    const int64_t row0 = (int64_t)tile * TR;
     const int nz = gridDim.y;
     for (int64_t cbase = s0 + (int64_t)blockIdx.y * SDK_EXD_TS; cbase < s1; cbase += (int64_t)nz * SDK_EXD_TS) {
-        double acc[4][4];                                             // [segment][row]
+        double acc[4][RPT];                                           // [segment][row]
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-        if (tid < SDK_EXD_TR) s_pool[tid] = pool == 0 ? 0ll : LLONG_MIN;
+            for (int j = 0; j < RPT; ++j) acc[i][j] = 0.0;
+        if (tid < TR) s_pool[tid] = pool == 0 ? 0ll : LLONG_MIN;
         // staging: thread -> (item = tid / 32 + 8 * it, d = tid % 32): consecutive lanes read consecutive d (coalesced).  The
         // global loads of chunk c+1 are issued before the fmas of chunk c and land in registers (software pipeline): a
         // d chunk is only 32 x 16 fmas per thread, far too short to hide an L2 round trip otherwise.
@@ -226,7 +227,7 @@ k_exact_dense(const void* __restrict__ seg_ops, const void* __restrict__ bank_op
             seg_live[it] = s < s1;
             const int32_t t = (int32_t)(s - s0);
             seg_row[it] = gc == 1 ? rbase + (int64_t)t * gstep : rbase + (int64_t)(t / gc) * gstep + (t % gc);
-            row_live[it] = row0 + item < P;
+            row_live[it] = item < TR && row0 + item < P;
         }
         float pre_s[8], pre_r[8];                                     // raw operands (fp32 holds bf16 exactly); widened at the store
         auto fetch = [&](int d0) {
@@ -253,18 +254,23 @@ k_exact_dense(const void* __restrict__ seg_ops, const void* __restrict__ bank_op
             for (int k = 0; k < SDK_EXD_DC; ++k) {
                 const double2 a01 = *reinterpret_cast<const double2*>(&s_seg[k][4 * ty]);
                 const double2 a23 = *reinterpret_cast<const double2*>(&s_seg[k][4 * ty + 2]);
-                const double2 b01 = *reinterpret_cast<const double2*>(&s_row[k][4 * tx]);
-                const double2 b23 = *reinterpret_cast<const double2*>(&s_row[k][4 * tx + 2]);
-                const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+                const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+                double b[RPT];
+#pragma unroll
+                for (int j = 0; j < RPT; j += 2) {
+                    const double2 bb = *reinterpret_cast<const double2*>(&s_row[k][RPT * tx + j]);
+                    b[j] = bb.x;
+                    b[j + 1] = bb.y;
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                    for (int j = 0; j < RPT; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
             }
         }
         // fixed point, pool this thread's 4 segments per row, then over the 16 threads that share the rows
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < RPT; ++j) {
             long long q = pool == 0 ? 0ll : LLONG_MIN;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -277,12 +283,12 @@ k_exact_dense(const void* __restrict__ seg_ops, const void* __restrict__ bank_op
             const long long o = __shfl_xor_sync(0xffffffffu, q, 16);
             q = pool == 0 ? q + o : (o > q ? o : q);
             if ((tid & 16) == 0) {
-                if (pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_pool[4 * tx + j]), (unsigned long long)q);
-                else atomicMax(&s_pool[4 * tx + j], q);
+                if (pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_pool[RPT * tx + j]), (unsigned long long)q);
+                else atomicMax(&s_pool[RPT * tx + j], q);
             }
         }
         __syncthreads();
-        if (tid < SDK_EXD_TR && row0 + tid < P) {
+        if (tid < TR && row0 + tid < P) {
             long long* dst = qpool + (int64_t)gi * P + row0 + tid;
             if (pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)s_pool[tid]);
             else atomicMax(dst, s_pool[tid]);
@@ -307,7 +313,11 @@ int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, 
     c->launches++;
     if (!d_cand_row && nslot >= SDK_EXD_TR) {
         // dense scan of a bank: register-tiled kernel; long labels are split over blockIdx.y (64 segments per pass)
-        const int64_t ntiles64 = (nslot + SDK_EXD_TR - 1) / SDK_EXD_TR;
+        // 64-row tiles; 32-row tiles when that is what it takes to give every SM a couple of CTAs (one meeting vs a few
+        // hundred profiles)
+        int rpt = 4;
+        if (((nslot + 63) / 64) * (int64_t)ngroups < 2 * (int64_t)c->sm_count) rpt = 2;
+        const int64_t ntiles64 = (nslot + 16 * rpt - 1) / (16 * rpt);
         const int64_t blocks = ntiles64 * ngroups;
         if (blocks > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "exact path: too many (group,row-tile) blocks");
         int nz = 1;
@@ -316,8 +326,10 @@ int sdk_launch_exact(sdk_ctx* c, const void* d_seg_ops, const void* d_bank_ops, 
             if (nz > 64) nz = 64;
         }
         dim3 grid((unsigned)blocks, (unsigned)nz);
-        if (is_bf16) k_exact_dense<true><<<grid, 256, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, nslot, (int)ntiles64, pool, d_qpool, d_grp, n_seg);
-        else k_exact_dense<false><<<grid, 256, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, nslot, (int)ntiles64, pool, d_qpool, d_grp, n_seg);
+#define SDK_EXD_CASE(B, R) k_exact_dense<B, R><<<grid, 256, 0, c->stream>>>(d_seg_ops, d_bank_ops, D, pitch, d_goff, d_glist, nslot, (int)ntiles64, pool, d_qpool, d_grp, n_seg)
+        if (is_bf16) { if (rpt == 4) SDK_EXD_CASE(true, 4); else SDK_EXD_CASE(true, 2); }
+        else { if (rpt == 4) SDK_EXD_CASE(false, 4); else SDK_EXD_CASE(false, 2); }
+#undef SDK_EXD_CASE
         c->launches++;
         SDK_CUDA(c, cudaGetLastError());
         return SDK_OK;
