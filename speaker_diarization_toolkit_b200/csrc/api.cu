@@ -160,7 +160,7 @@ void sdk_destroy(sdk_ctx* c) {
                        &c->out_count, &c->out_trust, &c->out_spk, &c->as_idx, &c->as_score, &c->as_conf,
                        &c->as_cidx, &c->as_cscore, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
                        &c->stage_lab[0], &c->stage_lab[1], &c->pa_hist, &c->pa_sorted, &c->pa_pos, &c->pa_col_group,
-                       &c->pa_col_meta, &c->pa_blockT, &c->pa_step0, &c->pa_grp, &c->seg_il, &c->fb_list2, &c->cand_row2, &c->qpool2};
+                       &c->pa_col_meta, &c->pa_blockT, &c->pa_step0, &c->pa_grp, &c->pa_col_last, &c->seg_il, &c->fb_list2, &c->cand_row2, &c->qpool2};
     for (sdk_buf* b : bufs) sdk_release(*b);
     for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int b = 0; b < 2; ++b) {
@@ -425,10 +425,10 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         if (hf[0] & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
         int32_t nfb = hf[1];
         const int32_t* fb = (const int32_t*)c->fb_list.p;
-        // second chance (generic kernel, all groups' candidate slots still live): re-merge the failed groups with the
+        // second chance (all groups' candidate slots still live): re-merge the failed groups with the
         // widest candidate list, re-score, certify again -- an exhaustive pass over a 125k-row shard costs ~2 ms per
         // group, this costs microseconds
-        if (nfb > 0 && ncand < 64 && !use_acc && c->slot_g0 == 0 && c->slot_g1 == L) {
+        if (nfb > 0 && ncand < 64 && c->slot_g0 == 0 && c->slot_g1 == L) {
             const int32_t ncand2 = 64;
             SDK_TRY(sdk_reserve(c, c->cand_row2, (size_t)nfb * ncand2 * 4));
             SDK_TRY(sdk_reserve(c, c->qpool2, (size_t)nfb * ncand2 * 8));

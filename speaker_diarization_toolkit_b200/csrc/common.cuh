@@ -58,9 +58,10 @@ struct sdk_ctx {
     sdk_buf seg_raw, seg_lab, seg_f32, seg_bf16, goff, qpool, dense, flags;
     sdk_buf cand_row, cand_val, cand_cnt, gbound, slot_cnt, slot_row, slot_val, slot_bound, range_g;
     sdk_buf fb_list, fb_rows, fb_list2, cand_row2, qpool2;
-    int32_t slot_g0 = 0, slot_g1 = 0, slot_nsub = 0;   // label groups whose candidate slots (generic tcgen05 kernel) are live
+    int32_t slot_g0 = 0, slot_g1 = 0, slot_nsub = 0;   // label groups whose candidate slots are live after stage A
+    bool slot_by_col = false;  // slots are indexed by accumulator column (accumulate-pooling): group -> pa_col_last
     sdk_buf stage_seg[2], stage_lab[2];
-    sdk_buf pa_hist, pa_sorted, pa_pos, pa_col_group, pa_col_meta, pa_blockT, pa_step0, pa_grp, seg_il;   // accumulate-pooling plan + layout
+    sdk_buf pa_hist, pa_sorted, pa_pos, pa_col_group, pa_col_meta, pa_blockT, pa_step0, pa_grp, pa_col_last, seg_il;   // accumulate-pooling plan + layout
     int32_t pa_blocks = 0;     // blocks of 256 accumulator columns in the current plan
     bool pa_split = false;     // current plan deals groups over several columns (col_meta != col_group)
     cudaStream_t copy_stream = nullptr;

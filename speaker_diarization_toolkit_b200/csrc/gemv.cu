@@ -246,5 +246,6 @@ int sdk_launch_gemv_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int64_t 
     c->slot_g0 = 0;
     c->slot_g1 = G;
     c->slot_nsub = nsub;
+    c->slot_by_col = false;
     return SDK_OK;
 }

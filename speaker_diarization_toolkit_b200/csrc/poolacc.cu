@@ -99,7 +99,7 @@ __global__ void k_pa_steps(const int32_t* __restrict__ blockT, int32_t n_blocks,
     if (lane == 0) { step0[n_blocks] = carry; plan_out[0] = carry; plan_out[1] = n_blocks; }
 }
 __global__ void k_pa_group_rows(const int64_t* __restrict__ goff, const int32_t* __restrict__ group_pos, const int64_t* __restrict__ step0,
-                                int32_t G, PaGroup* __restrict__ grp) {
+                                int32_t G, PaGroup* __restrict__ grp, int32_t* __restrict__ col_last) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
     int pos = group_pos[g];
@@ -109,6 +109,7 @@ __global__ void k_pa_group_rows(const int64_t* __restrict__ goff, const int32_t*
     r.base = (int32_t)(base > 0x7fffffff ? 0x7fffffff : base);      // the host rejects layouts of more than 2^31-1 rows
     r.c = 1;
     grp[g] = r;
+    col_last[g] = pos;
 }
 
 // ---- plan (B): few groups, columns split; one CTA ------------------------------------------------------------------
@@ -125,7 +126,7 @@ __device__ __forceinline__ int pa_cand_T(int i, int t_min) {      // geometric l
 __global__ void __launch_bounds__(1024)
 k_pa_plan_small(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t max_blocks, int32_t* __restrict__ col_group,
                 int32_t* __restrict__ col_meta, int32_t* __restrict__ blockT, int64_t* __restrict__ step0, int64_t* __restrict__ plan_out,
-                PaGroup* __restrict__ grp) {
+                PaGroup* __restrict__ grp, int32_t* __restrict__ col_last) {
     __shared__ int32_t sn[PA_SMALL_G];          // group sizes
     __shared__ int16_t sorder[PA_SMALL_G];      // groups by size, descending (ties: lower id first)
     __shared__ int32_t scol0[PA_SMALL_G];       // first column of the group (global column index)
@@ -210,16 +211,18 @@ k_pa_plan_small(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t 
         r.base = (int32_t)(base > 0x7fffffff ? 0x7fffffff : base);
         r.c = c;
         grp[g] = r;
+        col_last[g] = c0 + c - 1;
     }
 }
 
-// ---- plan (B1): at most PA_BINS_G groups -- balanced bins, one step count per block ------------------------------------
+// ---- plan (B1): at most PA_BINS_G (256) groups -- balanced bins, one step count per block ------------------------------------
 // With a handful of groups (the 16 labels of config 5, the 8 labels of one meeting) next-fit leaves blocks part empty and
 // the number of units rarely divides over the SMs.  Here the groups are dealt into nb bins (= blocks) by LPT, every
 // block gets ITS OWN step count T_b = min T with sum_g max(1, ceil(n_g / T)) <= 256 -- so every block is full -- and
 // nb is chosen by simulating the kernel's static unit -> CTA assignment (wave quantisation included).  Warp per candidate.
 #define PA_BINS_G 256
 #define PA_MAX_BINS 64
+#define PA_BIN_CAP 250            // label groups per bin (every group needs at least one of the 256 columns)
 __device__ __forceinline__ void pa_warp_argmin(long long& v, int& idx) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
@@ -228,15 +231,35 @@ __device__ __forceinline__ void pa_warp_argmin(long long& v, int& idx) {
         if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
     }
 }
+// one LPT pass of the size-sorted groups over nb bins; lane owns bins lane and lane + 32 (a full bin takes no more groups)
+__device__ __forceinline__ void pa_lpt(const int32_t* sn, const int16_t* sorder, int G, int nb, int lane, long long& load0, long long& load1,
+                                       int& cnt0, int& cnt1, int16_t* sbin /* may be null */) {
+    const long long INF = 0x7fffffffffffffffLL;
+    load0 = 0; load1 = 0; cnt0 = 0; cnt1 = 0;
+    for (int i = 0; i < G; ++i) {
+        const int g = sorder[i];
+        const int32_t n = sn[g];
+        const long long e0 = (lane < nb && cnt0 < PA_BIN_CAP) ? load0 : INF, e1 = (lane + 32 < nb && cnt1 < PA_BIN_CAP) ? load1 : INF;
+        long long v = e0 <= e1 ? e0 : e1;
+        int idx = e0 <= e1 ? lane : lane + 32;
+        pa_warp_argmin(v, idx);
+        if (idx == lane) { load0 += n; ++cnt0; }
+        if (idx == lane + 32) { load1 += n; ++cnt1; }
+        if (sbin && lane == 0) sbin[g] = (int16_t)idx;
+    }
+}
 __global__ void __launch_bounds__(1024)
 k_pa_plan_bins(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t* __restrict__ col_group, int32_t* __restrict__ col_meta,
-               int32_t* __restrict__ blockT, int64_t* __restrict__ step0, int64_t* __restrict__ plan_out, PaGroup* __restrict__ grp) {
+               int32_t* __restrict__ blockT, int64_t* __restrict__ step0, int64_t* __restrict__ plan_out, PaGroup* __restrict__ grp,
+               int32_t* __restrict__ col_last) {
     __shared__ int32_t sn[PA_BINS_G];
     __shared__ int16_t sorder[PA_BINS_G];
     __shared__ int16_t sbin[PA_BINS_G];
+    __shared__ int16_t slist[PA_BINS_G];       // groups bin by bin
+    __shared__ int32_t soff[PA_MAX_BINS + 1], scur[PA_MAX_BINS];
     __shared__ int32_t sT[PA_MAX_BINS];
     __shared__ int32_t sTw[32][PA_MAX_BINS];   // per warp: estimated T_b of the candidate being evaluated
-    __shared__ float scost[PA_MAX_BINS];
+    __shared__ float scost[32];
     __shared__ int s_nb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int g = tid; g < G; g += blockDim.x) {
@@ -251,82 +274,89 @@ k_pa_plan_bins(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t* 
         sorder[rank] = (int16_t)g;
     }
     __syncthreads();
-    const int nb_max = G < PA_MAX_BINS ? G : PA_MAX_BINS;
-    for (int nb = warp + 1; nb <= PA_MAX_BINS; nb += 32) {
-        if (nb > nb_max) { if (lane == 0) scost[nb - 1] = 3.0e38f; continue; }
-        // LPT: lane owns bins lane and lane + 32
-        long long load0 = lane < nb ? 0 : 0x7fffffffffffffffLL, load1 = lane + 32 < nb ? 0 : 0x7fffffffffffffffLL;
-        int cnt0 = 0, cnt1 = 0;
-        for (int i = 0; i < G; ++i) {
-            const int32_t n = sn[sorder[i]];
-            long long v = load0 <= load1 ? load0 : load1;
-            int idx = load0 <= load1 ? lane : lane + 32;
-            pa_warp_argmin(v, idx);
-            if (idx == lane) { load0 += n; ++cnt0; }
-            if (idx == lane + 32) { load1 += n; ++cnt1; }
-        }
-        // estimate of T_b (sufficient, a few percent high): load / (256 - groups)
-        int T0 = 0, T1 = 0;
-        if (lane < nb) { const int d = 256 - cnt0 > 1 ? 256 - cnt0 : 1; T0 = (int)((load0 + d - 1) / d); }
-        if (lane + 32 < nb) { const int d = 256 - cnt1 > 1 ? 256 - cnt1 : 1; T1 = (int)((load1 + d - 1) / d); }
-        sTw[warp][lane] = T0;
-        sTw[warp][lane + 32] = T1;
-        __syncwarp();
-        // the kernel's schedule: unit u = b * RB + rb runs on CTA u % sms, i.e. CTA i gets RB / sms units of block b, plus
-        // one if (i - first CTA of the block) mod sms < RB % sms
-        float worst = 0.f;
-        const int uq = pc.RB / pc.sms, ur = pc.RB % pc.sms;
-        for (int i = lane; i < pc.sms; i += 32) {
-            float t = 0.f;
-            int u0m = 0;                                                         // (b * RB) % sms
-            for (int b = 0; b < nb; ++b) {
-                const int Tb = sTw[warp][b];
-                int d = i - u0m;
-                d += d < 0 ? pc.sms : 0;
-                const int cntu = uq + (d < ur ? 1 : 0);
-                if (Tb > 0) t += (float)cntu * ((float)Tb * pc.step_cycles + pc.unit_cycles);
-                u0m += ur;
-                u0m -= u0m >= pc.sms ? pc.sms : 0;
+    // candidates: nb_min, nb_min + 1, ... one per warp
+    const int nb_min = (G + PA_BIN_CAP - 1) / PA_BIN_CAP;
+    const int nb_hi = G < PA_MAX_BINS ? G : PA_MAX_BINS;
+    {
+        const int nb = nb_min + warp;
+        if (nb > nb_hi) {
+            if (lane == 0) scost[warp] = 3.0e38f;
+        } else {
+            long long load0, load1;
+            int cnt0, cnt1;
+            pa_lpt(sn, sorder, G, nb, lane, load0, load1, cnt0, cnt1, nullptr);
+            // estimate of T_b (sufficient, a few percent high): load / (256 - groups)
+            int T0 = 0, T1 = 0;
+            if (lane < nb) { const int d = 256 - cnt0 > 1 ? 256 - cnt0 : 1; T0 = (int)((load0 + d - 1) / d); }
+            if (lane + 32 < nb) { const int d = 256 - cnt1 > 1 ? 256 - cnt1 : 1; T1 = (int)((load1 + d - 1) / d); }
+            sTw[warp][lane] = T0;
+            sTw[warp][lane + 32] = T1;
+            __syncwarp();
+            // the kernel's schedule: unit u = b * RB + rb runs on CTA u % sms, i.e. CTA i gets RB / sms units of block b,
+            // plus one if (i - first CTA of the block) mod sms < RB % sms
+            float worst = 0.f;
+            const int uq = pc.RB / pc.sms, ur = pc.RB % pc.sms;
+            for (int i = lane; i < pc.sms; i += 32) {
+                float t = 0.f;
+                int u0m = 0;                                                     // (b * RB) % sms
+                for (int b = 0; b < nb; ++b) {
+                    const int Tb = sTw[warp][b];
+                    int d = i - u0m;
+                    d += d < 0 ? pc.sms : 0;
+                    const int cntu = uq + (d < ur ? 1 : 0);
+                    if (Tb > 0) t += (float)cntu * ((float)Tb * pc.step_cycles + pc.unit_cycles);
+                    u0m += ur;
+                    u0m -= u0m >= pc.sms ? pc.sms : 0;
+                }
+                worst = fmaxf(worst, t);
             }
-            worst = fmaxf(worst, t);
-        }
-        __syncwarp();
+            __syncwarp();
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, off));
-        if (lane == 0) scost[nb - 1] = worst;
+            for (int off = 16; off >= 1; off >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, off));
+            if (lane == 0) scost[warp] = worst;
+        }
     }
     __syncthreads();
     if (tid == 0) {
         int best = 0;
-        for (int i = 1; i < PA_MAX_BINS; ++i) if (scost[i] < scost[best]) best = i;
-        s_nb = best + 1;
+        for (int i = 1; i < 32; ++i) if (scost[i] < scost[best]) best = i;
+        s_nb = nb_min + best;
     }
     __syncthreads();
     const int nb = s_nb;
     if (warp == 0) {
-        long long load0 = lane < nb ? 0 : 0x7fffffffffffffffLL, load1 = lane + 32 < nb ? 0 : 0x7fffffffffffffffLL;
-        for (int i = 0; i < G; ++i) {
-            const int g = sorder[i];
-            const int32_t n = sn[g];
-            long long v = load0 <= load1 ? load0 : load1;
-            int idx = load0 <= load1 ? lane : lane + 32;
-            pa_warp_argmin(v, idx);
-            if (idx == lane) load0 += n;
-            if (idx == lane + 32) load1 += n;
-            if (lane == 0) sbin[g] = (int16_t)idx;
+        long long load0, load1;
+        int cnt0, cnt1;
+        pa_lpt(sn, sorder, G, nb, lane, load0, load1, cnt0, cnt1, sbin);
+        // groups bin by bin (counting sort on the bin index)
+        if (lane < PA_MAX_BINS / 2) { scur[lane] = 0; scur[lane + 32] = 0; }
+        __syncwarp();
+        sTw[0][lane] = lane < nb ? cnt0 : 0;
+        sTw[0][lane + 32] = lane + 32 < nb ? cnt1 : 0;
+        __syncwarp();
+        if (lane == 0) {
+            int acc = 0;
+            for (int b = 0; b < nb; ++b) { soff[b] = acc; acc += sTw[0][b]; }
+            soff[nb] = acc;
+        }
+        __syncwarp();
+        for (int g = lane; g < G; g += 32) {
+            const int b = sbin[g];
+            slist[soff[b] + atomicAdd(&scur[b], 1)] = (int16_t)g;
         }
         __syncwarp();
         // exact T_b: smallest T with sum max(1, ceil(n / T)) <= 256 over the bin's groups
         for (int b = lane; b < nb; b += 32) {
+            const int l0 = soff[b], l1 = soff[b + 1];
             long long tot = 0;
             int32_t mx = 0;
-            for (int g = 0; g < G; ++g) if (sbin[g] == b) { tot += sn[g]; mx = sn[g] > mx ? sn[g] : mx; }
-            int lo = 1, hi = mx > 1 ? mx : 1;                       // T = max n always fits (<= 256 groups, one column each)
+            for (int i = l0; i < l1; ++i) { const int32_t n = sn[slist[i]]; tot += n; mx = n > mx ? n : mx; }
+            int lo = 1, hi = mx > 1 ? mx : 1;                       // T = max n always fits (<= 250 groups, one column each)
             if (tot == 0) { sT[b] = 0; continue; }
             while (lo < hi) {
                 const int T = lo + (hi - lo) / 2;
                 int cols = 0;
-                for (int g = 0; g < G; ++g) if (sbin[g] == b) cols += sn[g] > 0 ? (sn[g] + T - 1) / T : 1;
+                for (int i = l0; i < l1; ++i) { const int32_t n = sn[slist[i]]; cols += n > 0 ? (n + T - 1) / T : 1; }
                 if (cols <= PA_NB) hi = T; else lo = T + 1;
             }
             sT[b] = lo;
@@ -343,12 +373,12 @@ k_pa_plan_bins(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t* 
     __syncthreads();
     for (int i = tid; i < nb * PA_NB; i += blockDim.x) { col_group[i] = -1; col_meta[i] = -1; }
     __syncthreads();
-    // columns of a block: its groups in id order, c = ceil(n / T_b) each (lane-free, one thread per block)
+    // columns of a block: its groups, c = ceil(n / T_b) each (one thread per block)
     if (tid < nb) {
         const int b = tid, T = sT[b];
         int fill = 0;
-        for (int g = 0; g < G; ++g) {
-            if (sbin[g] != b) continue;
+        for (int i = soff[b]; i < soff[b + 1]; ++i) {
+            const int g = slist[i];
             const int32_t n = sn[g];
             const int c = (n > 0 && T > 0) ? (n + T - 1) / T : 1;
             for (int j = 0; j < c; ++j) { col_group[b * PA_NB + fill + j] = g; col_meta[b * PA_NB + fill + j] = j == c - 1 ? g : -2; }
@@ -358,6 +388,7 @@ k_pa_plan_bins(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t* 
             r.base = (int32_t)(base > 0x7fffffff ? 0x7fffffff : base);
             r.c = c;
             grp[g] = r;
+            col_last[g] = b * PA_NB + fill + c - 1;
             fill += c;
         }
     }
@@ -475,6 +506,7 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     constexpr uint32_t A_BYTES = MT * KCH * A_TILE;
     constexpr uint32_t B_STAGE = NC * 128;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t NSLOT = 512 / (MT * NC);            // accumulator sets in TMEM: 2 when one row tile per unit (MT == 1)
     static_assert(MT * NC <= 512, "TMEM columns");
     const PgParams& p = q.pg;
 
@@ -484,19 +516,19 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     const uint32_t sA = base;
     const uint32_t sB = sA + A_BYTES;
     const uint32_t sBar = sB + STAGES * B_STAGE;
-    const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8;
-    const uint32_t bar_b_full = sBar + 16, bar_b_empty = bar_b_full + 8 * STAGES;
-    const uint32_t bar_t_full = bar_b_empty + 8 * STAGES, bar_t_empty = bar_t_full + 8;
-    const uint32_t s_tmem = bar_t_empty + 8;
+    // bank tiles are handed over per K chunk: chunk kc of the NEXT unit is loaded as soon as the last step of this unit
+    // has consumed chunk kc, so only the tail of the reload is exposed
+    const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8 * KCH;
+    const uint32_t bar_b_full = bar_a_empty + 8 * KCH, bar_b_empty = bar_b_full + 8 * STAGES;
+    const uint32_t bar_t_full = bar_b_empty + 8 * STAGES, bar_t_empty = bar_t_full + 8 * NSLOT;
+    const uint32_t s_tmem = bar_t_empty + 8 * NSLOT;
     uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(pg_smem_raw + (s_tmem - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
-        pg_mbar_init(bar_a_full, 1);
-        pg_mbar_init(bar_a_empty, 1);
+        for (int kc = 0; kc < KCH; ++kc) { pg_mbar_init(bar_a_full + 8 * kc, 1); pg_mbar_init(bar_a_empty + 8 * kc, 1); }
         for (int s = 0; s < STAGES; ++s) { pg_mbar_init(bar_b_full + 8 * s, 1); pg_mbar_init(bar_b_empty + 8 * s, 1); }
-        pg_mbar_init(bar_t_full, 1);
-        pg_mbar_init(bar_t_empty, 4 * MT);
+        for (uint32_t i = 0; i < NSLOT; ++i) { pg_mbar_init(bar_t_full + 8 * i, 1); pg_mbar_init(bar_t_empty + 8 * i, 4 * MT); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -521,24 +553,25 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
                 const int32_t T = q.blockT[b];
                 if (T <= 0) continue;
                 const int64_t s0 = q.step0[b];
-                pg_mbar_wait(bar_a_empty, a_phase ^ 1);
-                pg_mbar_expect_tx(bar_a_full, A_BYTES);
-#pragma unroll 1
-                for (int rt = 0; rt < MT; ++rt)
-#pragma unroll 1
-                    for (int kc = 0; kc < KCH; ++kc)
-                        pg_tma_load_2d(sA + (rt * KCH + kc) * A_TILE, &tmapA, kc * 64, (int32_t)((int64_t)rb * MT * 128 + rt * 128), bar_a_full);
-                a_phase ^= 1;
                 for (int32_t t = 0; t < T; ++t) {
                     const int32_t crow = (int32_t)((s0 + t) * NC);
 #pragma unroll 1
                     for (int kc = 0; kc < KCH; ++kc) {
+                        if (t == 0) {       // this unit's bank tiles, chunk by chunk, in the order the MMAs will want them
+                            pg_mbar_wait(bar_a_empty + 8 * kc, a_phase ^ 1);
+                            pg_mbar_expect_tx(bar_a_full + 8 * kc, MT * A_TILE);
+#pragma unroll 1
+                            for (int rt = 0; rt < MT; ++rt)
+                                pg_tma_load_2d(sA + (rt * KCH + kc) * A_TILE, &tmapA, kc * 64, (int32_t)((int64_t)rb * MT * 128 + rt * 128),
+                                               bar_a_full + 8 * kc);
+                        }
                         pg_mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
                         pg_mbar_expect_tx(bar_b_full + 8 * stage, B_STAGE);
                         pg_tma_load_2d(sB + stage * B_STAGE, &tmapB, kc * 64, crow, bar_b_full + 8 * stage);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
+                a_phase ^= 1;
             }
         }
     } else if (warp == 1) {
@@ -549,13 +582,14 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
                 const int32_t bl = (int32_t)(u / p.RB);
                 const int32_t T = q.blockT[q.block_lo + bl];
                 if (T <= 0) continue;
-                pg_mbar_wait(bar_a_full, a_phase);
-                a_phase ^= 1;
-                pg_mbar_wait(bar_t_empty, (uidx & 1u) ^ 1u);           // previous unit's tiles have been read out
+                const uint32_t slot = uidx % NSLOT, use = uidx / NSLOT;
+                pg_mbar_wait(bar_t_empty + 8 * slot, (use & 1u) ^ 1u);      // this accumulator set has been read out
                 pg_fence_after();
+                const uint32_t td = tmem_base + slot * (MT * NC);
                 for (int32_t t = 0; t < T; ++t) {
 #pragma unroll 1
                     for (int kc = 0; kc < KCH; ++kc) {
+                        if (t == 0) pg_mbar_wait(bar_a_full + 8 * kc, a_phase);
                         pg_mbar_wait(bar_b_full + 8 * stage, phase);
                         pg_fence_after();
                         const uint64_t db = pg_make_desc(sB + stage * B_STAGE);
@@ -564,15 +598,16 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
                             const uint64_t da = pg_make_desc(sA + (rt * KCH + kc) * A_TILE);
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
-                                pg_mma_bf16(tmem_base + rt * NC, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC,
+                                pg_mma_bf16(td + rt * NC, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC,
                                             (t | kc | kk) != 0 ? 1u : 0u);
                         }
                         pg_commit(bar_b_empty + 8 * stage);
+                        if (t == T - 1) pg_commit(bar_a_empty + 8 * kc);     // the next unit's chunk kc may be loaded
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
-                pg_commit(bar_t_full);
-                pg_commit(bar_a_empty);
+                pg_commit(bar_t_full + 8 * slot);
+                a_phase ^= 1;
                 ++uidx;
             }
         }
@@ -600,13 +635,15 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
                 const int64_t n = g >= 0 ? p.goff[g + 1] - p.goff[g] : 0;
                 ginv[i] = n > 0 ? 1.0f / (float)n : 0.f;
             }
-            pg_mbar_wait(bar_t_full, uidx & 1u);
+            const uint32_t slot = uidx % NSLOT, use = uidx / NSLOT;
+            pg_mbar_wait(bar_t_full + 8 * slot, use & 1u);
             pg_fence_after();
+            const uint32_t td = tmem_base + slot * (MT * NC);
             float run = 0.f;                                                          // sum over the columns of one group
 #pragma unroll
             for (int blk = 0; blk < NC / 32; ++blk) {
                 float v[32];
-                pg_tmem_ld32(tmem_base + lane_base + rt * NC + blk * 32, v);
+                pg_tmem_ld32(td + lane_base + rt * NC + blk * 32, v);
                 pg_tmem_ld_wait();
 #pragma unroll
                 for (int cc = 0; cc < 32; ++cc) {
@@ -631,7 +668,7 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
             }
             pg_fence_before();
             __syncwarp();
-            if (lane == 0) pg_mbar_arrive(bar_t_empty);
+            if (lane == 0) pg_mbar_arrive(bar_t_empty + 8 * slot);
             ++uidx;
         }
     }
@@ -647,7 +684,7 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
 // ---- host side ----------------------------------------------------------------------------------------------------
 template <int KCH, int MT, int STAGES>
 static int pa_launch_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const PaParams& q, int grid) {
-    constexpr size_t smem = (size_t)MT * KCH * 16384 + (size_t)STAGES * PA_NB * 128 + 256 + 1024;
+    constexpr size_t smem = (size_t)MT * KCH * 16384 + (size_t)STAGES * PA_NB * 128 + 320 + 1024;
     static_assert(smem <= PG_SMEM_LIMIT, "shared memory budget");
     auto kern = k_poolacc<KCH, MT, STAGES>;
     SDK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -691,6 +728,7 @@ int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, in
     SDK_TRY(sdk_reserve(c, c->pa_blockT, (size_t)max_blocks * 4));
     SDK_TRY(sdk_reserve(c, c->pa_step0, (size_t)(max_blocks + 4) * 8));
     SDK_TRY(sdk_reserve(c, c->pa_grp, (size_t)G * sizeof(PaGroup)));
+    SDK_TRY(sdk_reserve(c, c->pa_col_last, (size_t)G * 4));
     int64_t* step0 = (int64_t*)c->pa_step0.p;
     int64_t* plan_out = step0 + max_blocks + 1;                     // {steps, blocks}
     if (small) {
@@ -704,10 +742,12 @@ int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, in
         sdk_prof_scope ps(c, "plan");
         if (G <= PA_BINS_G)
             k_pa_plan_bins<<<1, 1024, 0, c->stream>>>(d_goff, G, pc, (int32_t*)c->pa_col_group.p, (int32_t*)c->pa_col_meta.p,
-                                                      (int32_t*)c->pa_blockT.p, step0, plan_out, (PaGroup*)c->pa_grp.p);
+                                                      (int32_t*)c->pa_blockT.p, step0, plan_out, (PaGroup*)c->pa_grp.p,
+                                                      (int32_t*)c->pa_col_last.p);
         else
             k_pa_plan_small<<<1, 1024, 0, c->stream>>>(d_goff, G, pc, max_blocks, (int32_t*)c->pa_col_group.p, (int32_t*)c->pa_col_meta.p,
-                                                       (int32_t*)c->pa_blockT.p, step0, plan_out, (PaGroup*)c->pa_grp.p);
+                                                       (int32_t*)c->pa_blockT.p, step0, plan_out, (PaGroup*)c->pa_grp.p,
+                                                       (int32_t*)c->pa_col_last.p);
         c->launches += 1;
         SDK_CUDA(c, cudaGetLastError());
     } else {
@@ -723,7 +763,8 @@ int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, in
         k_pa_blocks<<<(max_blocks + 127) / 128, 128, 0, c->stream>>>(d_goff, (const int32_t*)c->pa_sorted.p, G, max_blocks,
                                                                      (int32_t*)c->pa_col_group.p, (int32_t*)c->pa_blockT.p);
         k_pa_steps<<<1, 32, 0, c->stream>>>((const int32_t*)c->pa_blockT.p, max_blocks, step0, plan_out);
-        k_pa_group_rows<<<(G + 255) / 256, 256, 0, c->stream>>>(d_goff, (const int32_t*)c->pa_pos.p, step0, G, (PaGroup*)c->pa_grp.p);
+        k_pa_group_rows<<<(G + 255) / 256, 256, 0, c->stream>>>(d_goff, (const int32_t*)c->pa_pos.p, step0, G, (PaGroup*)c->pa_grp.p,
+                                                                (int32_t*)c->pa_col_last.p);
         c->launches += 6;
         SDK_CUDA(c, cudaGetLastError());
     }
@@ -834,6 +875,12 @@ int sdk_launch_poolacc(sdk_ctx* c, const float* d_seg_raw, const int32_t* d_seg_
             pg_launch_merge(c, d_goff, (int32_t)(ba * PA_NB), (int32_t)((bb - ba) * PA_NB), nsub, col_meta, tau, ncand, d_cand_row, d_gbound);
             SDK_CUDA(c, cudaGetLastError());
         }
+    }
+    if (mode == 0 && bbatch >= n_blocks) {     // one batch: every label's candidate slots are still in memory (second chance)
+        c->slot_g0 = 0;
+        c->slot_g1 = G;
+        c->slot_nsub = nsub;
+        c->slot_by_col = true;
     }
     return SDK_OK;
 }

@@ -524,7 +524,7 @@ __device__ __forceinline__ void pg_load_slot(const float* __restrict__ vals, int
 }
 __global__ void __launch_bounds__(PG_MERGE_THREADS)
 k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const int32_t* __restrict__ sorted_group,
-           const int32_t* __restrict__ glist,
+           const int32_t* __restrict__ glist, const int32_t* __restrict__ group_col,
            const int32_t* __restrict__ slot_cnt, const int32_t* __restrict__ slot_row, const float* __restrict__ slot_val,
            const float* __restrict__ slot_bound, float tau, int32_t ncand, int32_t* __restrict__ cand_row,
            float* __restrict__ gbound) {
@@ -536,7 +536,8 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const
     const int tid = threadIdx.x;
     // slot index gl -> label group; with a group list (second-chance merge of the groups whose certificate failed) the
     // launch index selects the group and the compact output row
-    const int gl = glist ? glist[blockIdx.x] - g_base : blockIdx.x;
+    // (slots indexed by accumulator column: group_col maps the group to its last column)
+    const int gl = glist ? (group_col ? group_col[glist[blockIdx.x]] : glist[blockIdx.x]) - g_base : blockIdx.x;
     const int g = glist ? glist[blockIdx.x] : (sorted_group ? sorted_group[g_base + gl] : g_base + gl);
     if (g < 0) return;
     int32_t* out = cand_row + (int64_t)(glist ? blockIdx.x : g) * ncand;
@@ -693,12 +694,12 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const
 
 // ---- host side -----------------------------------------------------------------------------------
 void pg_launch_merge(sdk_ctx* c, const int64_t* d_goff, int32_t g_base, int32_t ngroups, int32_t nsub, const int32_t* d_sorted_group,
-                     float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, const int32_t* d_glist) {
+                     float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, const int32_t* d_glist, const int32_t* d_group_col) {
     if (ngroups <= 0) return;
     sdk_prof_scope ps(c, "merge");
     // small banks (a few hundred sub-slots per label group, tens of thousands of groups): a 256-thread CTA per group
     const int threads = nsub <= 1024 ? 256 : PG_MERGE_THREADS;
-    k_pg_merge<<<(unsigned)ngroups, threads, 0, c->stream>>>(d_goff, g_base, nsub, d_sorted_group, d_glist, (const int32_t*)c->slot_cnt.p,
+    k_pg_merge<<<(unsigned)ngroups, threads, 0, c->stream>>>(d_goff, g_base, nsub, d_sorted_group, d_glist, d_group_col, (const int32_t*)c->slot_cnt.p,
                                                          (const int32_t*)c->slot_row.p, (const float*)c->slot_val.p,
                                                          (const float*)c->slot_bound.p, tau, ncand, d_cand_row, d_gbound);
     c->launches++;
@@ -878,6 +879,7 @@ static int pg_run(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv
         if (mode == 0) {
             pg_launch_merge(c, d_goff, (int32_t)ga, (int32_t)(gb - ga), nsub, nullptr, tau, ncand, d_cand_row, d_gbound);
             SDK_CUDA(c, cudaGetLastError());
+            c->slot_by_col = false;
             c->slot_g0 = (int32_t)ga;        // groups whose candidate slots are still in memory after the call
             c->slot_g1 = (int32_t)gb;
             c->slot_nsub = nsub;
@@ -901,7 +903,8 @@ int sdk_launch_poolgemm_dense(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P
 int sdk_launch_poolgemm_remerge(sdk_ctx* c, const int64_t* d_goff, const int32_t* d_glist, int32_t ngroups, float tau, int32_t ncand,
                                 int32_t* d_cand_row /*[ngroups,ncand]*/, float* d_gbound /*[G]*/) {
     if (ngroups <= 0) return SDK_OK;
-    pg_launch_merge(c, d_goff, c->slot_g0, ngroups, c->slot_nsub, nullptr, tau, ncand, d_cand_row, d_gbound, d_glist);
+    pg_launch_merge(c, d_goff, c->slot_g0, ngroups, c->slot_nsub, nullptr, tau, ncand, d_cand_row, d_gbound, d_glist,
+                    c->slot_by_col ? (const int32_t*)c->pa_col_last.p : nullptr);
     SDK_CUDA(c, cudaGetLastError());
     return SDK_OK;
 }

@@ -181,4 +181,5 @@ static inline int pg_make_tmap(sdk_ctx* c, CUtensorMap* tm, const void* base, in
 // merge of the per-(32 bank rows) candidate slots of one label group (poolgemm.cu); `sorted_group` (may be null) maps
 // the launch index to the label group the result is written for
 void pg_launch_merge(sdk_ctx* c, const int64_t* d_goff, int32_t g_base, int32_t ngroups, int32_t nsub, const int32_t* d_sorted_group,
-                     float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, const int32_t* d_glist = nullptr);
+                     float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, const int32_t* d_glist = nullptr,
+                     const int32_t* d_group_col = nullptr);
