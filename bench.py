@@ -150,6 +150,9 @@ class Clocks:
                                           "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_wait = time.time() + 2.0            # short workloads finish before the tool prints its first line: wait for it
+            while not self.samples and time.time() < t_wait:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
