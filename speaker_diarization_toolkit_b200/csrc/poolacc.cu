@@ -498,12 +498,16 @@ struct PaParams {
     int32_t block_lo, n_blocks;    // blocks [block_lo, block_lo + n_blocks) of this batch
 };
 
-template <int KCH, int MT, int STAGES>
+// KH = passes over K: with KH == 2 only half of a unit's bank tiles (KCL = ceil(KCH / 2) K chunks of both row tiles) are
+// resident at a time -- pass 0 runs all T steps over the first K half, pass 1 over the second, into the same accumulators --
+// so that D > 256 still gets TWO row tiles per streamed B stage (half the L2 -> SM operand stream of MT == 1).
+template <int KCH, int MT, int STAGES, int KH>
 __global__ void __launch_bounds__(MT == 2 ? PG_THREADS2 : PG_THREADS, 1)
 k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ PaParams q) {
     constexpr int NC = PA_NB;
+    constexpr int KCL = (KCH + KH - 1) / KH;                // K chunks resident at a time
     constexpr uint32_t A_TILE = 128 * 128;
-    constexpr uint32_t A_BYTES = MT * KCH * A_TILE;
+    constexpr uint32_t A_BYTES = MT * KCL * A_TILE;
     constexpr uint32_t B_STAGE = NC * 128;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t NSLOT = 512 / (MT * NC);            // accumulator sets in TMEM: 2 when one row tile per unit (MT == 1)
@@ -518,15 +522,15 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     const uint32_t sBar = sB + STAGES * B_STAGE;
     // bank tiles are handed over per K chunk: chunk kc of the NEXT unit is loaded as soon as the last step of this unit
     // has consumed chunk kc, so only the tail of the reload is exposed
-    const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8 * KCH;
-    const uint32_t bar_b_full = bar_a_empty + 8 * KCH, bar_b_empty = bar_b_full + 8 * STAGES;
+    const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8 * KCL;
+    const uint32_t bar_b_full = bar_a_empty + 8 * KCL, bar_b_empty = bar_b_full + 8 * STAGES;
     const uint32_t bar_t_full = bar_b_empty + 8 * STAGES, bar_t_empty = bar_t_full + 8 * NSLOT;
     const uint32_t s_tmem = bar_t_empty + 8 * NSLOT;
     uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(pg_smem_raw + (s_tmem - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
-        for (int kc = 0; kc < KCH; ++kc) { pg_mbar_init(bar_a_full + 8 * kc, 1); pg_mbar_init(bar_a_empty + 8 * kc, 1); }
+        for (int kc = 0; kc < KCL; ++kc) { pg_mbar_init(bar_a_full + 8 * kc, 1); pg_mbar_init(bar_a_empty + 8 * kc, 1); }
         for (int s = 0; s < STAGES; ++s) { pg_mbar_init(bar_b_full + 8 * s, 1); pg_mbar_init(bar_b_empty + 8 * s, 1); }
         for (uint32_t i = 0; i < NSLOT; ++i) { pg_mbar_init(bar_t_full + 8 * i, 1); pg_mbar_init(bar_t_empty + 8 * i, 4 * MT); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -546,38 +550,43 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, a_phase = 0;
+            uint32_t stage = 0, phase = 0, a_bits = 0;              // a_bits: phase of every bank-tile barrier (bit per chunk slot)
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const int32_t bl = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)bl * p.RB);
                 const int32_t b = q.block_lo + bl;
                 const int32_t T = q.blockT[b];
                 if (T <= 0) continue;
                 const int64_t s0 = q.step0[b];
-                for (int32_t t = 0; t < T; ++t) {
-                    const int32_t crow = (int32_t)((s0 + t) * NC);
 #pragma unroll 1
-                    for (int kc = 0; kc < KCH; ++kc) {
-                        if (t == 0) {       // this unit's bank tiles, chunk by chunk, in the order the MMAs will want them
-                            pg_mbar_wait(bar_a_empty + 8 * kc, a_phase ^ 1);
-                            pg_mbar_expect_tx(bar_a_full + 8 * kc, MT * A_TILE);
+                for (int h = 0; h < KH; ++h) {
+                    const int kc0 = h * KCL, kc1 = kc0 + KCL < KCH ? kc0 + KCL : KCH;
+                    for (int32_t t = 0; t < T; ++t) {
+                        const int32_t crow = (int32_t)((s0 + t) * NC);
 #pragma unroll 1
-                            for (int rt = 0; rt < MT; ++rt)
-                                pg_tma_load_2d(sA + (rt * KCH + kc) * A_TILE, &tmapA, kc * 64, (int32_t)((int64_t)rb * MT * 128 + rt * 128),
-                                               bar_a_full + 8 * kc);
+                        for (int kc = kc0; kc < kc1; ++kc) {
+                            const int kcl = kc - kc0;
+                            if (t == 0) {   // this pass's bank tiles, chunk by chunk, in the order the MMAs will want them
+                                pg_mbar_wait(bar_a_empty + 8 * kcl, ((a_bits >> kcl) & 1u) ^ 1u);
+                                pg_mbar_expect_tx(bar_a_full + 8 * kcl, MT * A_TILE);
+#pragma unroll 1
+                                for (int rt = 0; rt < MT; ++rt)
+                                    pg_tma_load_2d(sA + (rt * KCL + kcl) * A_TILE, &tmapA, kc * 64,
+                                                   (int32_t)((int64_t)rb * MT * 128 + rt * 128), bar_a_full + 8 * kcl);
+                                a_bits ^= 1u << kcl;
+                            }
+                            pg_mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+                            pg_mbar_expect_tx(bar_b_full + 8 * stage, B_STAGE);
+                            pg_tma_load_2d(sB + stage * B_STAGE, &tmapB, kc * 64, crow, bar_b_full + 8 * stage);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
-                        pg_mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
-                        pg_mbar_expect_tx(bar_b_full + 8 * stage, B_STAGE);
-                        pg_tma_load_2d(sB + stage * B_STAGE, &tmapB, kc * 64, crow, bar_b_full + 8 * stage);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
-                a_phase ^= 1;
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer: all steps of the block accumulate into the same MT tiles =================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, a_phase = 0, uidx = 0;
+            uint32_t stage = 0, phase = 0, a_bits = 0, uidx = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const int32_t bl = (int32_t)(u / p.RB);
                 const int32_t T = q.blockT[q.block_lo + bl];
@@ -586,28 +595,35 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
                 pg_mbar_wait(bar_t_empty + 8 * slot, (use & 1u) ^ 1u);      // this accumulator set has been read out
                 pg_fence_after();
                 const uint32_t td = tmem_base + slot * (MT * NC);
-                for (int32_t t = 0; t < T; ++t) {
 #pragma unroll 1
-                    for (int kc = 0; kc < KCH; ++kc) {
-                        if (t == 0) pg_mbar_wait(bar_a_full + 8 * kc, a_phase);
-                        pg_mbar_wait(bar_b_full + 8 * stage, phase);
-                        pg_fence_after();
-                        const uint64_t db = pg_make_desc(sB + stage * B_STAGE);
+                for (int h = 0; h < KH; ++h) {
+                    const int kc0 = h * KCL, kc1 = kc0 + KCL < KCH ? kc0 + KCL : KCH;
+                    for (int32_t t = 0; t < T; ++t) {
+#pragma unroll 1
+                        for (int kc = kc0; kc < kc1; ++kc) {
+                            const int kcl = kc - kc0;
+                            if (t == 0) {
+                                pg_mbar_wait(bar_a_full + 8 * kcl, (a_bits >> kcl) & 1u);
+                                a_bits ^= 1u << kcl;
+                            }
+                            pg_mbar_wait(bar_b_full + 8 * stage, phase);
+                            pg_fence_after();
+                            const uint64_t db = pg_make_desc(sB + stage * B_STAGE);
 #pragma unroll
-                        for (int rt = 0; rt < MT; ++rt) {
-                            const uint64_t da = pg_make_desc(sA + (rt * KCH + kc) * A_TILE);
+                            for (int rt = 0; rt < MT; ++rt) {
+                                const uint64_t da = pg_make_desc(sA + (rt * KCL + kcl) * A_TILE);
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                pg_mma_bf16(td + rt * NC, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC,
-                                            (t | kc | kk) != 0 ? 1u : 0u);
+                                for (int kk = 0; kk < 4; ++kk)
+                                    pg_mma_bf16(td + rt * NC, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC,
+                                                (h | t | kc | kk) != 0 ? 1u : 0u);
+                            }
+                            pg_commit(bar_b_empty + 8 * stage);
+                            if (t == T - 1) pg_commit(bar_a_empty + 8 * kcl);   // the next pass's / unit's chunk may be loaded
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
-                        pg_commit(bar_b_empty + 8 * stage);
-                        if (t == T - 1) pg_commit(bar_a_empty + 8 * kc);     // the next unit's chunk kc may be loaded
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
                 pg_commit(bar_t_full + 8 * slot);
-                a_phase ^= 1;
                 ++uidx;
             }
         }
@@ -682,11 +698,12 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
-template <int KCH, int MT, int STAGES>
+template <int KCH, int MT, int STAGES, int KH>
 static int pa_launch_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const PaParams& q, int grid) {
-    constexpr size_t smem = (size_t)MT * KCH * 16384 + (size_t)STAGES * PA_NB * 128 + 320 + 1024;
+    constexpr int KCL = (KCH + KH - 1) / KH;
+    constexpr size_t smem = (size_t)MT * KCL * 16384 + (size_t)STAGES * PA_NB * 128 + 320 + 1024;
     static_assert(smem <= PG_SMEM_LIMIT, "shared memory budget");
-    auto kern = k_poolacc<KCH, MT, STAGES>;
+    auto kern = k_poolacc<KCH, MT, STAGES, KH>;
     SDK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, MT == 2 ? PG_THREADS2 : PG_THREADS, smem, c->stream>>>(ta, tb, q);
     c->launches++;
@@ -696,16 +713,20 @@ static int pa_launch_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb,
 
 static int pa_mt_for(int kch) { return kch <= 4 ? 2 : 1; }
 
+// (KCH, MT, STAGES, KH).  Shared memory = MT * ceil(KCH / KH) * 16 KB (bank tiles) + STAGES * 32 KB (B ring).  Above 256
+// dimensions one row tile per unit with all K chunks resident measured FASTER (config 4 forced: 10.8 ms) than two row
+// tiles with the K halves resident in turn (<8, 2, 3, 2>: 12.3 ms, although it halves the L2 -> SM operand stream), so
+// the KH = 2 instantiations are not used.
 static int pa_launch(sdk_ctx* c, int kch, const CUtensorMap& ta, const CUtensorMap& tb, const PaParams& q, int grid) {
     switch (kch) {
-        case 1: return pa_launch_t<1, 2, 6>(c, ta, tb, q, grid);
-        case 2: return pa_launch_t<2, 2, 5>(c, ta, tb, q, grid);
-        case 3: return pa_launch_t<3, 2, 4>(c, ta, tb, q, grid);
-        case 4: return pa_launch_t<4, 2, 3>(c, ta, tb, q, grid);
-        case 5: return pa_launch_t<5, 1, 4>(c, ta, tb, q, grid);
-        case 6: return pa_launch_t<6, 1, 4>(c, ta, tb, q, grid);
-        case 7: return pa_launch_t<7, 1, 3>(c, ta, tb, q, grid);
-        default: return pa_launch_t<8, 1, 3>(c, ta, tb, q, grid);
+        case 1: return pa_launch_t<1, 2, 6, 1>(c, ta, tb, q, grid);
+        case 2: return pa_launch_t<2, 2, 5, 1>(c, ta, tb, q, grid);
+        case 3: return pa_launch_t<3, 2, 4, 1>(c, ta, tb, q, grid);
+        case 4: return pa_launch_t<4, 2, 3, 1>(c, ta, tb, q, grid);
+        case 5: return pa_launch_t<5, 1, 4, 1>(c, ta, tb, q, grid);
+        case 6: return pa_launch_t<6, 1, 4, 1>(c, ta, tb, q, grid);
+        case 7: return pa_launch_t<7, 1, 3, 1>(c, ta, tb, q, grid);
+        default: return pa_launch_t<8, 1, 3, 1>(c, ta, tb, q, grid);
     }
 }
 
