@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import canonical
-from speaker_diarization_toolkit_b200 import _native, assign_cli, batch, signals as sg, store, synth
+from speaker_diarization_toolkit_b200 import _native, assign_cli, batch, review_cli, signals as sg, store, synth
 
 
 class OracleContext:
@@ -40,6 +40,14 @@ class OracleContext:
         t[ok] = self.trust[self.rows[ok]]
         self.t = t
         self.a = canonical.assign(self.rows, self.scores, t, self.counts, assign_threshold, _native.TRUST_CODES.get(min_trust, 99))
+
+    def affinity_pooled(self, seg, seg_label, L, dtype=_native.DTYPE_BF16, pool=0, want_ll=True):
+        lab = np.asarray(seg_label, np.int64)
+        goff = np.searchsorted(lab, np.arange(L + 1)).astype(np.int64)
+        nl = canonical.affinity(seg, goff, mode=dtype, pool=pool)
+        q = np.rint(nl.astype(np.float64) * 2.0 ** 30)
+        ll = np.stack([q[goff[a]:goff[a + 1]].sum(axis=0) / (max(1, goff[a + 1] - goff[a]) * 2.0 ** 30) for a in range(L)]).astype(np.float32)
+        return nl, ll
 
     def fetch(self, with_assign=False):
         out = {"row": self.rows, "score": self.scores, "count": self.counts, "trust": self.t}
@@ -131,4 +139,30 @@ def test_assign_batch_command(store_with_recordings, capsys):
     bad = root / "bad.json"
     bad.write_text(json.dumps([{"audio": str(root / "nope.wav"), "transcript": manifest[0]["transcript"]}]))
     assert assign_cli.main(["assign-batch", str(bad)]) == 1
+    assert "Error: Audio file not found:" in capsys.readouterr().err
+
+
+def test_review_consistency_host_logic(tmp_path, monkeypatch, capsys):
+    """`speaker-review consistency`: which segments are reported, how they are ordered, exit codes."""
+    monkeypatch.setattr(_native, "Context", OracleContext)
+    case = synth.make_case(21, [60, 50, 40], 3, 32, truth=[0, 1, 2], impostor_frac=0.0)
+    lab = case.seg_label.copy()
+    wrong = [3, 70, 120]
+    for i in wrong:
+        lab[i] = (lab[i] + 1) % 3
+    audio = tmp_path / "m.wav"
+    audio.write_bytes(b"RIFF" + bytes(40))
+    start = np.arange(len(lab)) * 1.0
+    store.save_segment_embeddings(audio, "b200", case.seg, [f"S{int(l) + 1}" for l in lab], start, start + 0.9)
+    rep = review_cli.consistency(audio)
+    assert sorted(round(s["start"]) for s in rep["suspects"]) == wrong and rep["segments_checked"] == 150
+    assert [s["gap"] for s in rep["suspects"]] == sorted(s["gap"] for s in rep["suspects"])       # worst first
+    for s in rep["suspects"]:
+        assert s["closer_to"] == f"S{int(case.seg_label[round(s['start'])]) + 1}" and s["closer_affinity"] > s["affinity"]
+    assert np.asarray(rep["label_affinity"]).shape == (3, 3)
+    assert review_cli.main(["consistency", str(audio), "--fail-on-suspects"]) == 2
+    assert "3 suspect segment(s)" in capsys.readouterr().out
+    assert review_cli.main(["consistency", str(audio), "--margin", "-1.0", "--format", "json", "--fail-on-suspects"]) == 0
+    assert json.loads(capsys.readouterr().out)["suspects"] == []
+    assert review_cli.main(["consistency", str(tmp_path / "nope.wav")]) == 1
     assert "Error: Audio file not found:" in capsys.readouterr().err
