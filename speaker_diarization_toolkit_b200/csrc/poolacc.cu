@@ -585,7 +585,8 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
         }
     } else if (warp == 1) {
         // ================= MMA issuer: all steps of the block accumulate into the same MT tiles =================
-        if (lane == 0) {
+        // (the whole warp runs the loop, one elected lane issues: see pg_elect_one)
+        {
             uint32_t stage = 0, phase = 0, a_bits = 0, uidx = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const int32_t bl = (int32_t)(u / p.RB);
@@ -609,21 +610,25 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
                             pg_mbar_wait(bar_b_full + 8 * stage, phase);
                             pg_fence_after();
                             const uint64_t db = pg_make_desc(sB + stage * B_STAGE);
+                            if (pg_elect_one()) {
 #pragma unroll
-                            for (int rt = 0; rt < MT; ++rt) {
-                                const uint64_t da = pg_make_desc(sA + (rt * KCL + kcl) * A_TILE);
+                                for (int rt = 0; rt < MT; ++rt) {
+                                    const uint64_t da = pg_make_desc(sA + (rt * KCL + kcl) * A_TILE);
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    pg_mma_bf16(td + rt * NC, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC,
-                                                (h | t | kc | kk) != 0 ? 1u : 0u);
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        pg_mma_bf16(td + rt * NC, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC,
+                                                    (h | t | kc | kk) != 0 ? 1u : 0u);
+                                }
+                                pg_commit(bar_b_empty + 8 * stage);
+                                if (t == T - 1) pg_commit(bar_a_empty + 8 * kcl);   // the next pass's / unit's chunk may be loaded
                             }
-                            pg_commit(bar_b_empty + 8 * stage);
-                            if (t == T - 1) pg_commit(bar_a_empty + 8 * kcl);   // the next pass's / unit's chunk may be loaded
+                            __syncwarp();
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
-                pg_commit(bar_t_full + 8 * slot);
+                if (pg_elect_one()) pg_commit(bar_t_full + 8 * slot);
+                __syncwarp();
                 ++uidx;
             }
         }

@@ -192,8 +192,8 @@ k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
+        {
             uint32_t stage = 0, phase = 0, a_phase = 0;
             uint32_t job = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -221,17 +221,22 @@ k_poolgemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
                             }
                             const uint64_t db = pg_make_desc(sB + st * B_STAGE);
                             const uint64_t da = pg_make_desc(sA + (rt * KCH + kc) * A_TILE);
+                            if (pg_elect_one()) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                pg_mma_bf16(td, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC, (kc | kk) != 0 ? 1u : 0u);
-                            if (rt == MT - 1) pg_commit(bar_b_empty + 8 * st);   // last row tile: this K stage is free
+                                for (int kk = 0; kk < 4; ++kk)
+                                    pg_mma_bf16(td, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC, (kc | kk) != 0 ? 1u : 0u);
+                                if (rt == MT - 1) pg_commit(bar_b_empty + 8 * st);   // last row tile: this K stage is free
+                            }
+                            __syncwarp();
                             if (++st == STAGES) { st = 0; ph ^= 1; }
                         }
-                        pg_commit(bar_t_full + 8 * slot);                         // accumulator of this job complete
+                        if (pg_elect_one()) pg_commit(bar_t_full + 8 * slot);         // accumulator of this job complete
+                        __syncwarp();
                         if (rt == MT - 1) { stage = st; phase = ph; }
                     }
                 }
-                pg_commit(bar_a_empty);                                           // bank tiles may be overwritten
+                if (pg_elect_one()) pg_commit(bar_a_empty);                           // bank tiles may be overwritten
+                __syncwarp();
             }
         }
     } else {

@@ -67,6 +67,20 @@ __device__ __forceinline__ void pg_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
 __device__ __forceinline__ void pg_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One lane of a CONVERGED warp.  The MMA-issuing warp runs its loop with all 32 lanes (loop counters, barrier addresses
+// and UMMA descriptors are then warp-uniform and live in uniform registers) and only the tcgen05.mma / tcgen05.commit
+// instructions are issued by the elected lane; a loop entered by lane 0 alone made the compiler re-elect and broadcast
+// every descriptor (ELECT + R2UR.BROADCAST per MMA), ~700 cycles of issue latency per 512 tensor cycles at D = 512.
+__device__ __forceinline__ bool pg_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void pg_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void pg_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void pg_tmem_ld16(uint32_t taddr, float (&v)[16]) {
