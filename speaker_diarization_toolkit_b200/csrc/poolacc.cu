@@ -14,11 +14,16 @@
 // T*256 segments instead of once per 256 segments, the B ring needs no chunk residency, and the kernel behaves like a
 // large-K GEMM.
 //
-// Plans.  (A) many groups (> 2048): c = 1, groups sorted by size (counting sort), blocks of 256 sorted groups -- hour-
-// long recordings by the ten thousand (config 3).  (B) few groups: one CTA sorts the groups, simulates the packing
-// for ~60 candidate step caps T (c = ceil(n / T) columns per group, next-fit into blocks, no group straddles a block)
-// under a cost model (MMA steps + per-unit tile load / read-out + wave quantisation over the SMs) and emits the best
-// -- the 16-label affinity of config 5 and single-meeting shapes.  Zero padding stays at a few percent in both.
+// Plans (built on the device per call).  (A) many groups (> 2048): c = 1, groups sorted by size (counting sort), blocks of
+// 256 sorted groups -- hour-long recordings by the ten thousand (config 3).  (B1) at most 256 groups: the groups are dealt
+// into nb bins (= blocks) by LPT, every block gets its own step count T_b = min T with sum max(1, ceil(n / T)) <= 256 so
+// that every block is full, and nb is chosen by simulating the kernel's static unit -> CTA schedule (wave quantisation
+// included) -- the 16-label affinity of config 5 and single-meeting shapes.  (B2) 257..2048 groups: next-fit packing of
+// c = ceil(n / T) columns per group for ~60 candidate step caps T under the same cost model.  No group straddles a block.
+//
+// Kernel pipeline: TMA producer warp / MMA-issuing warp / epilogue warpgroups.  The bank tiles of a unit are handed over per
+// K chunk (the next unit's chunk kc is loaded as soon as the last step of this unit has consumed chunk kc); with one row
+// tile per unit (MT == 1) two accumulator sets alternate in TMEM so that the read-out of unit u overlaps the MMAs of u + 1.
 //
 // Everything downstream is unchanged: the epilogue flushes per (group, 32 bank rows) candidate slots, k_pg_merge picks
 // the candidates, exact.cu re-scores them canonically (reading segments from the interleaved layout), select.cu
