@@ -289,8 +289,47 @@ def cmd_enroll(args, backend=None) -> int:
     return 0
 
 
+def cmd_validate(args) -> int:
+    """Mirror of cmd_validate (speaker_detection:1307-1361): schema check of the stored profiles and their embedding
+    records with this package's validators (schemas.py), same output and return codes."""
+    from . import schemas
+    if args.speaker_id:
+        speaker_id = store.normalize_speaker_id(args.speaker_id)
+        profile = store.load_speaker(speaker_id)
+        if not profile:
+            print(f"Error: Speaker '{speaker_id}' not found.", file=sys.stderr)
+            return 1
+        speakers = [profile]
+    else:
+        speakers = store.list_all_speakers()
+    if not speakers:
+        print("No speakers found.")
+        return 0
+    total_warnings = profiles_with_issues = 0
+    for profile in speakers:
+        speaker_id = profile["id"]
+        warnings = schemas.validate_profile(profile, strict=False)
+        if warnings:
+            profiles_with_issues += 1
+            total_warnings += len(warnings)
+            if args.verbose or not args.quiet:
+                print(f"\n{speaker_id}:")
+                for w in warnings:
+                    print(f"  - {w}")
+        elif args.verbose:
+            print(f"{speaker_id}: OK")
+    if not args.quiet:
+        print(f"\nValidated {len(speakers)} profiles")
+        if total_warnings > 0:
+            print(f"  {profiles_with_issues} profiles with issues")
+            print(f"  {total_warnings} total warnings")
+        else:
+            print("  All profiles valid")
+    return 1 if total_warnings > 0 and args.strict else 0
+
+
 def build_parser() -> argparse.ArgumentParser:
-    parser = argparse.ArgumentParser(prog="speaker_detection", description="identify / verify / enroll on the B200 matching path")
+    parser = argparse.ArgumentParser(prog="speaker_detection", description="identify / verify / enroll / validate on the B200 matching path")
     parser.add_argument("-q", "--quiet", action="store_true", help="Suppress status messages")   # speaker_detection:1374
     sub = parser.add_subparsers(dest="command")
     p = sub.add_parser("identify", help="Identify speaker in audio")
@@ -317,6 +356,12 @@ def build_parser() -> argparse.ArgumentParser:
     e.add_argument("-n", "--dry-run", action="store_true")
     e.add_argument("--trust-level", choices=["high", "medium", "low"])
     e.set_defaults(func=cmd_enroll)
+    c = sub.add_parser("validate", help="Validate schema of profiles and embeddings")      # speaker_detection:1525-1534
+    c.add_argument("speaker_id", nargs="?", help="Speaker ID (optional, validates all if omitted)")
+    c.add_argument("-v", "--verbose", action="store_true", help="Show OK profiles too")
+    c.add_argument("-q", "--quiet", action="store_true", help="Only show summary")
+    c.add_argument("--strict", action="store_true", help="Return non-zero exit code on warnings")
+    c.set_defaults(func=cmd_validate)
     return parser
 
 

@@ -383,3 +383,33 @@ def test_enrolled_records_pass_the_validators(tmp_path, monkeypatch, capsys):
             assert ref_schemas.validate_profile(prof, strict=True) == []
         finally:
             sys.path.remove("/root/reference")
+
+
+def test_validate_cli_matches_the_reference(tmp_path, monkeypatch, capsys):
+    """`speaker_detection validate` (speaker_detection:1307-1361): same stdout and return code as the reference CLI on a
+    store with a clean, a flawed and a badly flawed profile (reference run only where its tree is present)."""
+    import subprocess
+    monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(tmp_path))
+    (tmp_path / "db").mkdir()
+    good = {"id": "alice", "version": 1, "names": {"default": "Alice"}, "tags": ["a"], "embeddings": {"b200": [
+        {"id": "emb-1", "external_id": None, "created_at": "2026-01-01T00:00:00+00:00", "model_version": "b200-cosine-v1", "trust_level": "high"}]}}
+    # (every profile carries the current schema version: the reference migrates older ones in place when it loads them)
+    flawed = {"id": "bob", "version": 1, "names": {"work": "Bob"}, "tags": ["x"], "embeddings": {"b200": [
+        {"id": "emb-2", "external_id": 7, "created_at": "yesterday", "model_version": "unknown", "trust_level": "unknown"}]}}
+    bad = {"id": "carol", "version": 1, "names": ["Carol"], "tags": "t", "embeddings": {"b200": {}}}
+    for prof in (good, flawed, bad):
+        (tmp_path / "db" / f"{prof['id']}.json").write_text(json.dumps(prof))
+    runs = [["validate"], ["validate", "-v"], ["validate", "--strict"], ["validate", "bob", "--strict"], ["validate", "alice", "--strict", "-v"],
+            ["validate", "-q", "--strict"], ["validate", "nobody"]]
+    for argv in runs:
+        rc = identify_cli.main(argv)
+        cap = capsys.readouterr()
+        if argv == ["validate"]:
+            assert rc == 0 and "Validated 3 profiles" in cap.out and "2 profiles with issues" in cap.out
+            assert "  - embeddings.b200[0]: Embedding 'external_id' must be a string or null, got int" in cap.out
+        if argv == ["validate", "nobody"]:
+            assert rc == 1 and "Error: Speaker 'nobody' not found." in cap.err
+        if Path("/root/reference/speaker_detection").exists():
+            r = subprocess.run([sys.executable, "/root/reference/speaker_detection", *argv], capture_output=True, text=True,
+                               env=dict(os.environ, SPEAKERS_EMBEDDINGS_DIR=str(tmp_path)))
+            assert (r.returncode, r.stdout, r.stderr) == (rc, cap.out, cap.err), argv
