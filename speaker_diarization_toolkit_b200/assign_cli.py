@@ -259,6 +259,81 @@ def cmd_assign_batch(args, matcher=None) -> int:
     return 0
 
 
+def resolve_audio_b3sum(audio_arg: str) -> Optional[str]:
+    """A catalogued b3sum prefix (6..32 hex digits, unique) or a path to hash (speaker-assign:145-162)."""
+    if 6 <= len(audio_arg) <= 32 and all(ch in "0123456789abcdef" for ch in audio_arg.lower()):
+        matches = list((store.get_db_dir() / "catalog").glob(f"{audio_arg.lower()}*.yaml"))
+        if len(matches) == 1:
+            return matches[0].stem
+        if len(matches) > 1:
+            print(f"Error: Ambiguous b3sum prefix '{audio_arg}'", file=sys.stderr)
+            return None
+    path = Path(audio_arg).resolve()
+    return compute_b3sum(path) if path.exists() else None
+
+
+def cmd_show(args) -> int:
+    """Mirror of cmd_show (speaker-assign:652-702): the stored assignments of a recording as text / JSON / YAML."""
+    b3 = resolve_audio_b3sum(args.audio)
+    if not b3:
+        print(f"Error: Could not resolve audio: {args.audio}", file=sys.stderr)
+        return 1
+    path = store.get_db_dir() / "assignments" / f"{b3}.yaml"
+    if not path.exists():
+        print("Error: No assignments found for this recording", file=sys.stderr)
+        return 1
+    data = _load_yaml(path)
+    if args.format == "json" or (args.format == "yaml" and not _YAML):
+        print(json.dumps(data, indent=2, ensure_ascii=False))
+    elif args.format == "yaml":
+        print(yaml.dump(data, default_flow_style=False, sort_keys=False, allow_unicode=True))
+    else:
+        print(f"Assignments for: {b3[:8]}...")
+        print(f"Context: {data.get('context') or '-'}")
+        print(f"Method: {data.get('method', '-')}")
+        print(f"Assigned at: {data.get('assigned_at', '-')}")
+        print(f"Threshold: {data.get('threshold', '-')}")
+        print(f"Min trust: {data.get('min_trust', '-')}")
+        print()
+        mappings = data.get("mappings", {})
+        if not mappings:
+            print("No mappings found")
+        else:
+            print("Mappings:")
+            for label, info in mappings.items():
+                print(f"  {label} -> {info.get('speaker_id') or '(unassigned)'}")
+                print(f"       confidence: {info.get('confidence', '?')}, score: {info.get('score', 0):.3f}")
+                if info.get("signals"):
+                    print(f"       signals: {len(info['signals'])}")
+                    for sig in info["signals"][:3]:
+                        print(f"         - {sig.get('type', '?')}: {sig.get('score', 0):.2f}")
+                if info.get("candidates"):
+                    cands = ", ".join(f"{c['speaker_id']}({c['score']:.2f})" for c in info["candidates"])
+                    print(f"       candidates: {cands}")
+    return 0
+
+
+def cmd_clear(args) -> int:
+    """Mirror of cmd_clear (speaker-assign:705-728)."""
+    b3 = resolve_audio_b3sum(args.audio)
+    if not b3:
+        print(f"Error: Could not resolve audio: {args.audio}", file=sys.stderr)
+        return 1
+    path = store.get_db_dir() / "assignments" / f"{b3}.yaml"
+    if not path.exists():
+        print("No assignments found for this recording", file=sys.stderr)
+        return 0
+    if not args.force:
+        print(f"Clear assignments for: {b3[:8]}...?")
+        if input("Confirm [y/N]: ").lower() != "y":
+            print("Cancelled")
+            return 0
+    path.unlink()
+    if not args.quiet:
+        print(f"Cleared assignments: {b3[:8]}...")
+    return 0
+
+
 def build_parser() -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser(prog="speaker-assign", description="Multi-signal speaker name assignment (B200 embedding path)")
     parser.add_argument("-V", "--version", action="version", version=f"speaker-assign {VERSION}")
@@ -287,6 +362,14 @@ def build_parser() -> argparse.ArgumentParser:
     b.add_argument("--format", "-f", choices=["text", "json"], default="text")
     b.add_argument("--dry-run", "-n", action="store_true")
     b.set_defaults(func=cmd_assign_batch)
+    sh = sub.add_parser("show", help="Show current assignments for a recording")            # speaker-assign:763-766
+    sh.add_argument("audio", help="Path to audio file or b3sum prefix")
+    sh.add_argument("--format", "-f", choices=["text", "json", "yaml"], default="text")
+    sh.set_defaults(func=cmd_show)
+    cl = sub.add_parser("clear", help="Clear assignments for a recording")                  # speaker-assign:769-772
+    cl.add_argument("audio", help="Path to audio file or b3sum prefix")
+    cl.add_argument("--force", "-f", action="store_true", help="Skip confirmation")
+    cl.set_defaults(func=cmd_clear)
     return parser
 
 

@@ -413,3 +413,52 @@ def test_validate_cli_matches_the_reference(tmp_path, monkeypatch, capsys):
             r = subprocess.run([sys.executable, "/root/reference/speaker_detection", *argv], capture_output=True, text=True,
                                env=dict(os.environ, SPEAKERS_EMBEDDINGS_DIR=str(tmp_path)))
             assert (r.returncode, r.stdout, r.stderr) == (rc, cap.out, cap.err), argv
+
+
+def test_assign_show_and_clear_match_the_reference(tmp_path, monkeypatch, capsys):
+    """`speaker-assign show|clear` (speaker-assign:652-728): same stdout / stderr / return codes as the reference CLI on an
+    assignments file of the shape `assign` writes."""
+    import subprocess
+    from speaker_diarization_toolkit_b200 import assign_cli
+    monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(tmp_path))
+    audio = tmp_path / "a.wav"
+    audio.write_bytes(b"RIFF" + bytes(40) + b"show")
+    b3 = assign_cli.compute_b3sum(audio)
+    data = {"schema_version": 1, "recording_b3sum": b3, "transcript_path": "/x/t.json", "assigned_at": "2026-01-01T00:00:00Z",
+            "method": "speaker-assign-v1.0.0", "context": None, "min_trust": "low", "threshold": 0.3,
+            "mappings": {"S1": {"speaker_id": "alice", "confidence": "low", "score": 0.364,
+                                "signals": [{"type": "embedding_match", "score": 0.91, "embedding_id": "emb-1", "trust_level": "high", "backend": "b200"}],
+                                "candidates": [{"speaker_id": "bob", "score": 0.1736}]},
+                         "S2": {"speaker_id": None, "confidence": "unassigned", "score": 0.0, "signals": []}}}
+    adir = tmp_path / "assignments"
+    adir.mkdir()
+    ref_ok = Path("/root/reference/speaker-assign").exists()
+
+    def both(argv, restore=False):
+        if restore:
+            assign_cli._save_yaml(adir / f"{b3}.yaml", data)
+        rc = assign_cli.main(argv)
+        cap = capsys.readouterr()
+        if ref_ok:
+            if restore:
+                assign_cli._save_yaml(adir / f"{b3}.yaml", data)
+            r = subprocess.run([sys.executable, "/root/reference/speaker-assign", *argv], capture_output=True, text=True,
+                               env=dict(os.environ, SPEAKERS_EMBEDDINGS_DIR=str(tmp_path)))
+            assert (r.returncode, r.stdout, r.stderr) == (rc, cap.out, cap.err), argv
+        return rc, cap
+
+    rc, cap = both(["show", str(audio)])
+    assert rc == 1 and "Error: No assignments found for this recording" in cap.err
+    assign_cli._save_yaml(adir / f"{b3}.yaml", data)
+    rc, cap = both(["show", str(audio)])
+    assert rc == 0 and "  S1 -> alice" in cap.out and "  S2 -> (unassigned)" in cap.out and "candidates: bob(0.17)" in cap.out
+    for fmt in ("json", "yaml"):
+        rc, cap = both(["show", str(audio), "--format", fmt])
+        assert rc == 0
+    assert json.loads(both(["show", str(audio), "-f", "json"])[1].out) == data
+    rc, cap = both(["show", str(tmp_path / "nope.wav")])
+    assert rc == 1 and "Error: Could not resolve audio:" in cap.err
+    rc, cap = both(["clear", str(audio), "--force"], restore=True)
+    assert rc == 0 and f"Cleared assignments: {b3[:8]}..." in cap.out and not (adir / f"{b3}.yaml").exists()
+    rc, cap = both(["clear", str(audio), "--force"])
+    assert rc == 0 and "No assignments found for this recording" in cap.err
