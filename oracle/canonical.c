@@ -1,7 +1,7 @@
 /*
  * oracle/canonical.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * CPU restatement (plain C, scalar, one thread) of the embedding-matching path that
+ * CPU restatement (plain C; scalar per pair, bank rows spread over the host threads) of the embedding-matching path that
  * BASELINE.json's north_star names: L2-normalise -> cosine vs profile bank -> pool per
  * diarization label -> row->speaker max -> threshold / top-k -> label->profile assignment.
  *
@@ -38,7 +38,10 @@
  *   (6) assignment: fp64, exactly Python's float arithmetic of combine_signals.
  * |canonical - NumPy fp32| is ~1e-7 (checked in tests/test_oracle.py with tolerance 1e-5 rel).
  */
+#define _GNU_SOURCE
 #include <math.h>
+#include <pthread.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -109,18 +112,85 @@ static inline float orc_pool_finish(int64_t q, int64_t n, int32_t pool) {
  * bank [P,D]  operands
  * out  [G,P]  fp32 pooled similarity (0 for an empty group)
  * pool: 0 mean, 1 max */
+/* Every (group, row) cell is independent and every pair keeps its own sequential fma chain, so the
+ * order in which cells are visited cannot change a bit of the result.  The code below only arranges
+ * the work for speed (bench.py checks sampled label groups of the full-size workloads against it):
+ * blocks of ORC_PB bank rows are dealt to ORC_THREADS host threads (pthreads; ORC_THREADS from the
+ * environment, default = online cores, 1 = the plain loop), and the ORC_PB rows of a block are scored
+ * side by side against one segment so that ORC_PB independent chains fill the FMA pipeline. */
+enum { ORC_PB = 8 };
+typedef struct {
+    const float* seg; const float* bank; float* out;
+    int64_t s0, s1, P, blk0, blk1;
+    int32_t D, pool;
+} orc_pool_job;
+static void* orc_pool_worker(void* arg) {
+    const orc_pool_job* w = (const orc_pool_job*)arg;
+    const int32_t D = w->D, pool = w->pool;
+    const int64_t n = w->s1 - w->s0;
+    double* bt = (double*)malloc(sizeof(double) * (size_t)(D > 0 ? D : 1) * ORC_PB);
+    for (int64_t blk = w->blk0; blk < w->blk1; ++blk) {
+        int64_t p0 = blk * ORC_PB;
+        int nb = (int)(w->P - p0 < ORC_PB ? w->P - p0 : ORC_PB);
+        int64_t acc[ORC_PB];
+        /* the block's rows, widened to fp64 and transposed to [e][row] so that the compiler can keep the
+         * ORC_PB chains in SIMD lanes (each lane is still one pair's own ascending-d fma chain) */
+        for (int j = 0; j < ORC_PB; ++j) {
+            acc[j] = (pool == 0) ? 0 : INT64_MIN;
+            const float* bj = w->bank + (p0 + (j < nb ? j : 0)) * (int64_t)D;
+            for (int32_t e = 0; e < D; ++e) bt[(int64_t)e * ORC_PB + j] = (double)bj[e];
+        }
+        for (int64_t s = w->s0; s < w->s1; ++s) {
+            const float* a = w->seg + s * (int64_t)D;
+            double d[ORC_PB];
+            for (int j = 0; j < ORC_PB; ++j) d[j] = 0.0;
+            for (int32_t e = 0; e < D; ++e) {
+                const double ae = (double)a[e];
+                const double* be = bt + (int64_t)e * ORC_PB;
+                for (int j = 0; j < ORC_PB; ++j) d[j] = fma(ae, be[j], d[j]);
+            }
+            for (int j = 0; j < ORC_PB; ++j) {
+                int64_t q = (int64_t)llrint(d[j] * ORC_Q30);     /* == orc_pair_q30(a, bank row, D) */
+                if (pool == 0) acc[j] += q; else if (q > acc[j]) acc[j] = q;
+            }
+        }
+        for (int j = 0; j < nb; ++j) w->out[p0 + j] = orc_pool_finish(acc[j], n, pool);
+    }
+    free(bt);
+    return NULL;
+}
+static int orc_threads(void) {
+    const char* e = getenv("ORC_THREADS");
+    long n = e ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+    if (n < 1) n = 1;
+    if (n > 256) n = 256;
+    return (int)n;
+}
 void orc_pooled(const float* seg, const int64_t* goff, int32_t G, const float* bank, int64_t P,
                 int32_t D, int32_t pool, float* out) {
+    const int nt_max = orc_threads();
     for (int32_t g = 0; g < G; ++g) {
-        int64_t s0 = goff[g], s1 = goff[g + 1], n = s1 - s0;
-        for (int64_t p = 0; p < P; ++p) {
-            int64_t acc = (pool == 0) ? 0 : INT64_MIN;
-            for (int64_t s = s0; s < s1; ++s) {
-                int64_t q = orc_pair_q30(seg + s * (int64_t)D, bank + p * (int64_t)D, D);
-                if (pool == 0) acc += q; else if (q > acc) acc = q;
-            }
-            out[(int64_t)g * P + p] = orc_pool_finish(acc, n, pool);
+        const int64_t nblk = (P + ORC_PB - 1) / ORC_PB;
+        int nt = nt_max;
+        /* small cells are not worth a thread each */
+        if ((double)(goff[g + 1] - goff[g]) * (double)P * (double)D < 4.0e6) nt = 1;
+        if (nt > nblk) nt = (int)(nblk > 0 ? nblk : 1);
+        orc_pool_job jobs[256];
+        pthread_t th[256];
+        for (int t = 0; t < nt; ++t) {
+            orc_pool_job* w = &jobs[t];
+            w->seg = seg; w->bank = bank; w->out = out + (int64_t)g * P;
+            w->s0 = goff[g]; w->s1 = goff[g + 1]; w->P = P; w->D = D; w->pool = pool;
+            w->blk0 = nblk * t / nt; w->blk1 = nblk * (t + 1) / nt;
         }
+        int started = 0;
+        for (int t = 1; t < nt; ++t) {
+            if (pthread_create(&th[t], NULL, orc_pool_worker, &jobs[t]) != 0) break;
+            started = t;
+        }
+        orc_pool_worker(&jobs[0]);
+        for (int t = 1; t <= started; ++t) pthread_join(th[t], NULL);
+        for (int t = started + 1; t < nt; ++t) orc_pool_worker(&jobs[t]);   /* thread creation failed: do it here */
     }
 }
 

@@ -129,3 +129,94 @@ def test_embedding_only_bounds():
     assert mnp.combine_signals("S1", mk(0.74, "high"), 0.3)["speaker_id"] is None
     assert mnp.combine_signals("S1", mk(1.0, "medium"), 0.3)["speaker_id"] is None
     assert mnp.combine_signals("S1", mk(1.0, "low"), 0.3)["speaker_id"] is None
+
+
+# ---- independent float64 restatement of SURVEY 8c steps 1-5 (the tightest pin an unpinned path can get) ---------
+def _f64_pooled(seg, goff, bank, mode, pool):
+    """Plain NumPy: operands by the spec of step 1-2 (fp64 sum of squares -> fp32 norm -> ONE fp32 reciprocal per row ->
+    fp32 multiply -> bf16 RNE in mode 1; the operands are fp32 / bf16 VALUES in every implementation, and a 1-ulp
+    different normalisation would flip bf16 roundings), then a float64 GEMM and float64 mean / max per label.
+    Shares no code with the C oracle."""
+    def ops(x):
+        x64 = x.astype(np.float64)
+        nrm = np.sqrt((x64 * x64).sum(axis=1)).astype(np.float32)
+        inv = np.float32(1.0) / np.maximum(nrm, np.float32(1e-12))
+        y = x.astype(np.float32) * inv[:, None]
+        return (mnp.bf16_round(y) if mode == 1 else y).astype(np.float64)
+    S = ops(seg) @ ops(bank).T                                    # [N, P] float64
+    G = len(goff) - 1
+    out = np.zeros((G, bank.shape[0]))
+    for g in range(G):
+        a, b = int(goff[g]), int(goff[g + 1])
+        if b > a:
+            out[g] = S[a:b].mean(axis=0) if pool == 0 else S[a:b].max(axis=0)
+    return out
+
+
+FIVE_SHAPES = [
+    # name, case factory (sliced to sizes the fp64 product finishes in about a second), mode, threshold, k
+    ("cfg1", lambda: synth.config1(), 0, 0.354, 3),
+    ("cfg2", lambda: synth.config2(total=2000, P=500), 0, 0.354, 10),
+    ("cfg3", lambda: synth.config3(recordings=3, seg_per_rec=2000, P=1500, D=192), 1, 0.354, 4),
+    ("cfg4", lambda: synth.config4(P=3000, D=512, total=2000, neighbours=11), 1, -1.0, 10),
+]
+
+
+@pytest.mark.parametrize("pool", [0, 1])
+@pytest.mark.parametrize("shape", FIVE_SHAPES, ids=[s[0] for s in FIVE_SHAPES])
+def test_canonical_agrees_with_independent_float64(oracle, shape, pool):
+    """|canonical pooled similarity - float64 restatement| <= 1e-6 on every (label, bank row) cell of the BASELINE config
+    shapes (sliced), and the ordered top-k ids agree wherever the float64 scores are separated by more than that."""
+    name, make, mode, thr, k = shape
+    case = make()
+    ref = _f64_pooled(case.seg, case.goff, case.bank, mode, pool)
+    seg_ops, _ = oracle.normalize(case.seg, mode)
+    bank_ops, _ = oracle.normalize(case.bank, mode)
+    got = oracle.pooled(seg_ops, case.goff, bank_ops, pool)
+    err = np.abs(got.astype(np.float64) - ref).max()
+    assert err <= 1e-6, (name, err)
+    rows, scores, cnt = oracle.identify(case.seg, case.goff, case.bank, case.row_speaker, case.n_speakers, mode=mode, pool=pool,
+                                        threshold=thr, k=k)
+    # float64 top-k per label over speakers (max over a speaker's rows)
+    for g in range(case.G):
+        if case.goff[g + 1] == case.goff[g]:
+            assert cnt[g] == 0
+            continue
+        best = np.full(case.n_speakers, -np.inf)
+        np.maximum.at(best, case.row_speaker, ref[g])
+        order = np.argsort(-best, kind="stable")
+        keep = [s for s in order if best[s] >= thr][:k]
+        got_spk = case.row_speaker[rows[g, :cnt[g]]].tolist()
+        # compare rank by rank until the first float64 near-tie / near-threshold score (below 4e-6 the canonical order rules)
+        for i, s in enumerate(keep):
+            gap_next = best[s] - best[order[list(order).index(s) + 1]] if list(order).index(s) + 1 < len(order) else 1.0
+            if gap_next < 4e-6 or abs(best[s] - thr) < 4e-6:
+                break
+            assert i < len(got_spk) and got_spk[i] == s, (name, g, i)
+            assert abs(float(scores[g, i]) - best[s]) <= 1e-6
+
+
+def test_canonical_affinity_agrees_with_independent_float64(oracle):
+    """config 5 shape (sliced): pooled self-affinity [N, L] against the float64 restatement."""
+    case = synth.config5(N=1500, L=16, D=256)
+    for pool in (0, 1):
+        ref = _f64_pooled(case.seg, case.goff, case.seg, 1, pool).T            # [N, L]
+        got = oracle.affinity(case.seg, case.goff, mode=1, pool=pool)
+        assert np.abs(got.astype(np.float64) - ref).max() <= 1e-6
+
+
+def test_threaded_oracle_equals_single_thread(oracle, monkeypatch):
+    case = synth.config2(total=1200, P=700)
+    seg_ops, _ = oracle.normalize(case.seg, 1)
+    bank_ops, _ = oracle.normalize(case.bank, 1)
+    monkeypatch.setenv("ORC_THREADS", "1")
+    a = oracle.pooled(seg_ops, case.goff, bank_ops, 0)
+    monkeypatch.setenv("ORC_THREADS", "5")
+    b = oracle.pooled(seg_ops, case.goff, bank_ops, 0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # and equals the one-pair-at-a-time definition
+    q = sum(int(oracle.lib().orc_pair_q30(seg_ops[s].ctypes.data_as(__import__("ctypes").c_void_p),
+                                          bank_ops[17].ctypes.data_as(__import__("ctypes").c_void_p), seg_ops.shape[1]))
+            for s in range(int(case.goff[0]), int(case.goff[1])))
+    n = int(case.goff[1] - case.goff[0])
+    assert a[0, 17] == np.float32(q / (n * 2.0 ** 30))
