@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SDK_ABI_VERSION 1
+#define SDK_ABI_VERSION 2
 
 /* error codes */
 #define SDK_OK 0
@@ -41,6 +41,7 @@ extern "C" {
 #define SDK_ECUDA (-5)     /* CUDA runtime / driver error */
 #define SDK_ENCCL (-71)    /* NCCL error */
 #define SDK_ESTATE (-1)    /* call order (identify before bank_load, fetch before identify ...) */
+#define SDK_EPEER (-70)    /* row-sharded mode: another rank failed in this identify call; the merged result is void */
 
 /* operand precision of the canonical score: the bank fixes it at load time */
 #define SDK_DTYPE_F32 0   /* operands = fp32 normalised vectors */
@@ -81,7 +82,8 @@ const char* sdk_last_error(sdk_ctx* ctx);
  * "profile" (1 = record per-kernel CUDA-event times), "cand" (re-scored candidates per label),
  * "chunk_mb" (host-buffer sdk_identify: size of the H2D/compute pipeline chunks, default 128),
  * "cta_group" (1 | 2: tcgen05 kernel variant), "acc" (0 off | 1 auto | 2 force: pool inside the MMA accumulation),
- * "gemv" (1 = stream the bank on the CUDA cores when there are <= 8 query segments) */
+ * "gemv" (1 = stream the bank on the CUDA cores when there are <= 8 query segments),
+ * "inject_fail" (test knob: the next local identify pass returns SDK_EINVAL after its first kernels) */
 int sdk_set_option(sdk_ctx* ctx, const char* key, double value);
 
 /* ---- profile bank (replaces: the candidates list handed to identify_speaker, base.py:133,
@@ -89,7 +91,8 @@ int sdk_set_option(sdk_ctx* ctx, const char* key, double value);
 /* rows        [P,D] fp32, raw (un-normalised) enrolled vectors, row-major
  * row_speaker [P]   speaker index of each row; rows of one speaker must be contiguous
  * row_trust   [P]   SDK_TRUST_* of each row's embedding record (NULL = all unknown)
- * global_row_offset first global row id of this shard (0 when world == 1)                    */
+ * global_row_offset first global row id of this shard (0 when world == 1)
+ * world > 1 only: P == 0 is an EMPTY shard (more ranks than speaker runs); the rank still joins every all-gather. */
 int sdk_bank_load(sdk_ctx* ctx, const float* rows, const int32_t* row_speaker,
                   const uint8_t* row_trust, int64_t P, int32_t D, int32_t dtype,
                   int64_t global_row_offset);
@@ -109,7 +112,12 @@ int sdk_bank_load_dev(sdk_ctx* ctx, const float* d_rows, const int32_t* d_row_sp
 int sdk_identify(sdk_ctx* ctx, const float* seg, const int32_t* seg_label, int64_t N, int32_t L,
                  int32_t pool, double threshold, int32_t k,
                  int64_t* out_row, float* out_score, int32_t* out_count);
-/* device inputs; results stay on the device until sdk_results_fetch */
+/* device inputs; results stay on the device until sdk_results_fetch.
+ * Alignment: any 4-byte aligned float pointer is legal (a tensor view at an element offset); the 128-bit load paths
+ * (vector normalise, accumulate-pooling) are taken only when d_seg is 16-byte aligned and D % 4 == 0.
+ * Row-sharded mode (world > 1): every rank must make the same sequence of identify calls (same L and k); a rank whose
+ * local pass fails still joins the all-gather (empty lists + a status word), returns its own error, and its peers get
+ * SDK_EPEER from sdk_results_fetch. */
 int sdk_identify_dev(sdk_ctx* ctx, const float* d_seg, const int32_t* d_seg_label, int64_t N,
                      int32_t L, int32_t pool, double threshold, int32_t k);
 
@@ -123,6 +131,14 @@ int sdk_identify_dev(sdk_ctx* ctx, const float* d_seg, const int32_t* d_seg_labe
  *   assign_conf  [L]   SDK_CONF_*
  *   cand_idx     [L,3] match indices of the runner-up candidates (-1 pad), cand_score [L,3] */
 int sdk_assign(sdk_ctx* ctx, double assign_threshold, int32_t min_trust_code);
+
+/* ---- merge of per-shard result lists made elsewhere (replaces nothing in the reference: it is the host-visible form
+ *      of the step after the all-gather, SURVEY 8e, for shards that live in other processes or nodes) -------------- */
+/* rows [world,L,k] global bank rows (-1 pad), scores [world,L,k], counts [world,L], trust [world,L,k] or NULL.
+ * The merged lists, ordered by (-score, global row), become the context's results: sdk_assign / sdk_results_fetch
+ * work on them.  Shards must be cut on speaker boundaries (no speaker appears in two lists). */
+int sdk_merge_topk(sdk_ctx* ctx, int32_t world, int32_t L, int32_t k, const int64_t* rows,
+                   const float* scores, const int32_t* counts, const uint8_t* trust);
 
 /* copies the results of the last identify / assign to host buffers (any pointer may be NULL);
  * synchronises the stream.  out_trust [L,k] = trust code of each matched row. */
@@ -156,6 +172,13 @@ int64_t sdk_launch_count(sdk_ctx* ctx);
  * (mean pooling inside the MMA accumulation), 4 bank-stream GEMV (<= 8 query segments); *n_fallback = label groups whose
  * top-k certificate failed and were re-done exhaustively */
 int sdk_last_path(sdk_ctx* ctx, int32_t* path, int64_t* n_fallback);
+/* Diagnostics of the certified top-k (tests, bench.py): after an identify that took path 2-4 on ONE chunk, the
+ * first-chance candidate rows [L, *ncand] (shard-local row index, -1 pad) with their stage-A pooled scores, and the
+ * certificate's margin model: a row left out of the list has a canonical score <= its stage-A score + eps_base +
+ * eps_chain * chain (chain = segments per accumulator column, or n/32 + 70 with epilogue mean pooling).  cap = entries
+ * the two buffers hold (rows / approx may be NULL to read only the model). */
+int sdk_stage_a_fetch(sdk_ctx* ctx, int32_t* rows, float* approx, int64_t cap, int32_t* ncand,
+                      float* eps_base, float* eps_chain);
 /* label groups of the last identify whose top-k certificate failed on the first candidate list and was settled by the
  * second, wider one (64 candidates) without an exhaustive pass */
 int64_t sdk_last_retry(sdk_ctx* ctx);

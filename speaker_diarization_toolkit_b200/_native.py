@@ -30,7 +30,7 @@ EXPORTS = [
     "sdk_set_option", "sdk_bank_load", "sdk_bank_load_dev", "sdk_identify", "sdk_identify_dev", "sdk_assign",
     "sdk_results_fetch", "sdk_affinity_pooled", "sdk_affinity_pooled_dev", "sdk_sync", "sdk_stream",
     "sdk_timer_start", "sdk_timer_stop", "sdk_profile_get", "sdk_profile_reset", "sdk_launch_count", "sdk_last_path",
-    "sdk_last_retry",
+    "sdk_last_retry", "sdk_merge_topk", "sdk_stage_a_fetch",
 ]
 
 
@@ -82,6 +82,8 @@ def load() -> C.CDLL:
     lib.sdk_last_path.argtypes = [vp, C.POINTER(i32), C.POINTER(i64)]
     lib.sdk_last_retry.argtypes = [vp]
     lib.sdk_last_retry.restype = i64
+    lib.sdk_merge_topk.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.sdk_stage_a_fetch.argtypes = [vp, vp, vp, i64, C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _lib = lib
     return lib
 
@@ -174,6 +176,18 @@ class Context:
         self._ck(self.lib.sdk_identify_dev(self.h, d_seg_ptr, d_lab_ptr, N, L, pool, threshold, k))
         self.L, self.k = L, k
 
+    def merge_topk(self, rows, scores, counts, trust=None):
+        """Merge per-shard lists made elsewhere: rows [W,L,k] int64, scores [W,L,k] f32, counts [W,L] i32, trust
+        [W,L,k] u8 or None.  The merged lists become this context's results (assign / fetch)."""
+        rows = _np(rows, np.int64)
+        W, L, k = rows.shape
+        scores, counts = _np(scores, np.float32), _np(counts, np.int32)
+        if scores.shape != (W, L, k) or counts.shape != (W, L):
+            raise ValueError("scores must be [W,L,k] and counts [W,L]")
+        tr = None if trust is None else _np(trust, np.uint8)
+        self._ck(self.lib.sdk_merge_topk(self.h, W, L, k, _ptr(rows), _ptr(scores), _ptr(counts), _ptr(tr)))
+        self.L, self.k = L, k
+
     def assign(self, assign_threshold: float = 0.3, min_trust: str = "low"):
         self._ck(self.lib.sdk_assign(self.h, assign_threshold, TRUST_CODES.get(min_trust, 99)))
 
@@ -229,6 +243,15 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.sdk_launch_count(self.h))
+
+    def stage_a(self):
+        """(rows [L,ncand] int32 shard-local (-1 pad), approx [L,ncand] f32, eps_base, eps_chain) of the last tensor-path identify."""
+        n, eb, ec = C.c_int32(), C.c_float(), C.c_float()
+        self._ck(self.lib.sdk_stage_a_fetch(self.h, None, None, 0, C.byref(n), C.byref(eb), C.byref(ec)))
+        rows = np.empty((self.L, n.value), np.int32)
+        approx = np.empty((self.L, n.value), np.float32)
+        self._ck(self.lib.sdk_stage_a_fetch(self.h, _ptr(rows), _ptr(approx), rows.size, C.byref(n), C.byref(eb), C.byref(ec)))
+        return rows, approx, float(eb.value), float(ec.value)
 
     def last_retry(self) -> int:
         return int(self.lib.sdk_last_retry(self.h))

@@ -49,6 +49,7 @@ struct sdk_nccl_api {
     int (*GetUniqueId)(sdk_nccl_uid_t*) = nullptr;
     int (*CommInitRank)(void**, int, sdk_nccl_uid_t, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
+    int (*CommAbort)(void*) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -64,6 +65,7 @@ static int sdk_nccl_load() {
     g_nccl.GetUniqueId = (int (*)(sdk_nccl_uid_t*))dlsym(g_nccl.h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void**, int, sdk_nccl_uid_t, int))dlsym(g_nccl.h, "ncclCommInitRank");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.h, "ncclCommDestroy");
+    g_nccl.CommAbort = (int (*)(void*))dlsym(g_nccl.h, "ncclCommAbort");
     g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.h, "ncclAllGather");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather)
@@ -156,12 +158,11 @@ void sdk_destroy(sdk_ctx* c) {
     sdk_buf* bufs[] = {&c->bank_f32, &c->bank_bf16, &c->row_speaker, &c->row_trust, &c->seg_raw, &c->seg_lab,
                        &c->seg_f32, &c->seg_bf16, &c->goff, &c->qpool, &c->dense, &c->flags, &c->cand_row,
                        &c->cand_val, &c->cand_cnt, &c->gbound, &c->slot_cnt, &c->slot_row, &c->slot_val,
-                       &c->slot_bound, &c->range_g, &c->fb_list, &c->fb_rows, &c->out_row, &c->out_score,
-                       &c->out_count, &c->out_trust, &c->out_spk, &c->as_idx, &c->as_score, &c->as_conf,
-                       &c->as_cidx, &c->as_cscore, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
+                       &c->slot_bound, &c->range_g, &c->fb_list, &c->fb_rows, &c->out_pack, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
                        &c->stage_lab[0], &c->stage_lab[1], &c->pa_hist, &c->pa_sorted, &c->pa_pos, &c->pa_col_group,
                        &c->pa_col_meta, &c->pa_blockT, &c->pa_step0, &c->pa_grp, &c->pa_col_last, &c->seg_il, &c->fb_list2, &c->cand_row2, &c->qpool2};
     for (sdk_buf* b : bufs) sdk_release(*b);
+    if (c->h_pack) cudaFreeHost(c->h_pack);
     for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int b = 0; b < 2; ++b) {
         if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]);
@@ -203,6 +204,8 @@ int sdk_set_option(sdk_ctx* c, const char* key, double value) {
     } else if (k == "chunk_mb") {
         if (value < 1 || value > 65536) return sdk_fail(c, SDK_EINVAL, "chunk_mb must be in 1..65536");
         c->opt_chunk_mb = (int)value;
+    } else if (k == "inject_fail") {
+        c->opt_inject_fail = value != 0;          // test knob: the next local identify pass fails after its first kernels
     } else return sdk_fail(c, SDK_EINVAL, "unknown option " + k);
     return SDK_OK;
 }
@@ -210,9 +213,10 @@ int sdk_set_option(sdk_ctx* c, const char* key, double value) {
 // ---- bank ---------------------------------------------------------------------------------------
 static int sdk_check_bank_args(sdk_ctx* c, const void* rows, const void* spk, int64_t P, int32_t D, int32_t dtype) {
     if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
-    if (P < 1 || D < 1 || D > 8192) return sdk_fail(c, SDK_EINVAL, "bank needs P >= 1 and 1 <= D <= 8192");
+    // an EMPTY shard (P == 0) is legal in the row-sharded mode: the rank still joins every collective with empty lists
+    if (P < (c->world > 1 ? 0 : 1) || D < 1 || D > 8192) return sdk_fail(c, SDK_EINVAL, "bank needs P >= 1 and 1 <= D <= 8192");
     if (P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "at most 2^31-1 rows per shard");
-    if (!rows || !spk) return sdk_fail(c, SDK_EINVAL, "rows/row_speaker is NULL");
+    if (P > 0 && (!rows || !spk)) return sdk_fail(c, SDK_EINVAL, "rows/row_speaker is NULL");
     if (dtype != SDK_DTYPE_F32 && dtype != SDK_DTYPE_BF16) return sdk_fail(c, SDK_EINVAL, "dtype must be 0 (fp32) or 1 (bf16)");
     return SDK_OK;
 }
@@ -222,7 +226,14 @@ int sdk_bank_load_dev(sdk_ctx* c, const float* d_rows, const int32_t* d_row_spea
     SDK_TRY(sdk_check_bank_args(c, d_rows, d_row_speaker, P, D, dtype));
     cudaSetDevice(c->device);
     c->P = 0;
+    c->bank_ok = false;
     int32_t Dp = (D + 63) / 64 * 64;
+    if (P == 0) {
+        c->D = D; c->Dp = Dp; c->dtype = dtype; c->row_offset = global_row_offset;
+        c->bank_ok = true;
+        c->have_results = false;
+        return SDK_OK;
+    }
     SDK_TRY(sdk_reserve(c, c->bank_bf16, (size_t)P * Dp * 2));
     if (dtype == SDK_DTYPE_F32) SDK_TRY(sdk_reserve(c, c->bank_f32, (size_t)P * D * 4));
     SDK_TRY(sdk_reserve(c, c->row_speaker, (size_t)P * 4));
@@ -233,6 +244,7 @@ int sdk_bank_load_dev(sdk_ctx* c, const float* d_rows, const int32_t* d_row_spea
     SDK_TRY(sdk_launch_normalize(c, d_rows, P, D, Dp, dtype == SDK_DTYPE_F32 ? (float*)c->bank_f32.p : nullptr,
                                  (__nv_bfloat16*)c->bank_bf16.p));
     c->P = P; c->D = D; c->Dp = Dp; c->dtype = dtype; c->row_offset = global_row_offset;
+    c->bank_ok = true;
     c->have_results = false;
     return SDK_OK;
 }
@@ -240,6 +252,7 @@ int sdk_bank_load_dev(sdk_ctx* c, const float* d_rows, const int32_t* d_row_spea
 int sdk_bank_load(sdk_ctx* c, const float* rows, const int32_t* row_speaker, const uint8_t* row_trust, int64_t P,
                   int32_t D, int32_t dtype, int64_t global_row_offset) {
     SDK_TRY(sdk_check_bank_args(c, rows, row_speaker, P, D, dtype));
+    if (P == 0) return sdk_bank_load_dev(c, nullptr, nullptr, nullptr, 0, D, dtype, global_row_offset);
     // rows of one speaker must be contiguous (the select kernel and the shard cut rely on it)
     {
         std::vector<int32_t> seen;
@@ -274,20 +287,28 @@ int sdk_bank_load(sdk_ctx* c, const float* rows, const int32_t* row_speaker, con
 }
 
 // ---- identify -----------------------------------------------------------------------------------
-static int sdk_check_flags(sdk_ctx* c) {   // after a stream sync: label sanity flag lives in flags[0]
-    int32_t f = 0;
-    SDK_CUDA(c, cudaMemcpy(&f, c->flags.p, 4, cudaMemcpyDeviceToHost));
-    if (f & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
-    if (f & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
+static int sdk_flag_error(sdk_ctx* c, const int32_t* f) {
+    if (f[SDK_FLAG_LABEL] & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
+    if (f[SDK_FLAG_LABEL] & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
+    if (f[SDK_FLAG_PEER] != 0)
+        return sdk_fail(c, SDK_EPEER, "rank " + std::to_string(f[SDK_FLAG_PEER] - 1) + " of the row-sharded bank failed in this identify call "
+                                      "(bad labels or a local error); the merged result is not valid");
     return SDK_OK;
+}
+static int sdk_check_flags(sdk_ctx* c, const int32_t* d_flags) {   // after a stream sync
+    int32_t f[SDK_NFLAGS] = {0};
+    SDK_CUDA(c, cudaMemcpy(f, d_flags, sizeof(f), cudaMemcpyDeviceToHost));
+    return sdk_flag_error(c, f);
 }
 
 static int sdk_allgather_merge(sdk_ctx* c, int32_t L, int32_t k);
+static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L,
+                             int32_t label_base, int32_t pool, double threshold, int32_t k);
 
 static int sdk_check_identify_args(sdk_ctx* c, const void* seg, const void* lab, int64_t N, int32_t L, int32_t pool,
                                    double threshold, int32_t k) {
     if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
-    if (c->P <= 0) return sdk_fail(c, SDK_ESTATE, "sdk_identify before sdk_bank_load");
+    if (!c->bank_ok) return sdk_fail(c, SDK_ESTATE, "sdk_identify before sdk_bank_load");
     if (k < 1 || k > SDK_MAX_K) return sdk_fail(c, SDK_EINVAL, "k must be in 1..32");
     if (L < 1 || N < 0) return sdk_fail(c, SDK_EINVAL, "need L >= 1 and N >= 0");
     if (pool != SDK_POOL_MEAN && pool != SDK_POOL_MAX) return sdk_fail(c, SDK_EINVAL, "pool must be 0 (mean) or 1 (max)");
@@ -296,14 +317,39 @@ static int sdk_check_identify_args(sdk_ctx* c, const void* seg, const void* lab,
     return SDK_OK;
 }
 
+static size_t sdk_al16(size_t x) { return (x + 15) / 16 * 16; }
+// Lays the result record of L label groups x k matches out in c->out_pack (see sdk_out_view) and clears its flags.
 static int sdk_reserve_results(sdk_ctx* c, int32_t L, int32_t k) {
-    SDK_TRY(sdk_reserve(c, c->flags, 64));
-    SDK_TRY(sdk_reserve(c, c->out_row, (size_t)L * k * 8));
-    SDK_TRY(sdk_reserve(c, c->out_score, (size_t)L * k * 4));
-    SDK_TRY(sdk_reserve(c, c->out_count, (size_t)L * 4));
-    SDK_TRY(sdk_reserve(c, c->out_trust, (size_t)L * k));
-    SDK_TRY(sdk_reserve(c, c->out_spk, (size_t)L * k * 4));
-    SDK_CUDA(c, cudaMemsetAsync(c->flags.p, 0, 8, c->stream));   // [0] label sanity flag, [1] fallback counter
+    sdk_out_view v;
+    const size_t n = (size_t)L * k;
+    size_t o = SDK_NFLAGS * 4;
+    v.off_row = o;      o = sdk_al16(o + n * 8);
+    v.off_score = o;    o = sdk_al16(o + n * 4);
+    v.off_spk = o;      o = sdk_al16(o + n * 4);
+    v.off_count = o;    o = sdk_al16(o + (size_t)L * 4);
+    v.off_trust = o;    o = sdk_al16(o + n);
+    v.gather_bytes = o;
+    v.off_as_score = o; o = sdk_al16(o + (size_t)L * 8);
+    v.off_as_cscore = o; o = sdk_al16(o + (size_t)L * 24);
+    v.off_as_idx = o;   o = sdk_al16(o + (size_t)L * 4);
+    v.off_as_conf = o;  o = sdk_al16(o + (size_t)L * 4);
+    v.off_as_cidx = o;  o = sdk_al16(o + (size_t)L * 12);
+    v.bytes = o;
+    SDK_TRY(sdk_reserve(c, c->out_pack, v.bytes));
+    char* b = (char*)c->out_pack.p;
+    v.flags = (int32_t*)b;
+    v.row = (int64_t*)(b + v.off_row);
+    v.score = (float*)(b + v.off_score);
+    v.spk = (int32_t*)(b + v.off_spk);
+    v.count = (int32_t*)(b + v.off_count);
+    v.trust = (uint8_t*)(b + v.off_trust);
+    v.as_score = (double*)(b + v.off_as_score);
+    v.as_cscore = (double*)(b + v.off_as_cscore);
+    v.as_idx = (int32_t*)(b + v.off_as_idx);
+    v.as_conf = (int32_t*)(b + v.off_as_conf);
+    v.as_cidx = (int32_t*)(b + v.off_as_cidx);
+    c->out = v;
+    SDK_CUDA(c, cudaMemsetAsync(v.flags, 0, SDK_NFLAGS * 4, c->stream));
     return SDK_OK;
 }
 
@@ -314,15 +360,19 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
     const int32_t D = c->D, Dp = c->Dp;
     const int64_t P = c->P;
     const bool bf16 = c->dtype == SDK_DTYPE_BF16;
-    int64_t* o_row = (int64_t*)c->out_row.p + (size_t)label_base * k;
-    float* o_score = (float*)c->out_score.p + (size_t)label_base * k;
-    int32_t* o_count = (int32_t*)c->out_count.p + label_base;
-    uint8_t* o_trust = (uint8_t*)c->out_trust.p + (size_t)label_base * k;
-    int32_t* o_spk = (int32_t*)c->out_spk.p + (size_t)label_base * k;
+    int64_t* o_row = c->out.row + (size_t)label_base * k;
+    float* o_score = c->out.score + (size_t)label_base * k;
+    int32_t* o_count = c->out.count + label_base;
+    uint8_t* o_trust = c->out.trust + (size_t)label_base * k;
+    int32_t* o_spk = c->out.spk + (size_t)label_base * k;
 
     SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
-    int32_t* d_flags = (int32_t*)c->flags.p;
+    int32_t* d_flags = c->out.flags;
     SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, label_base, (int64_t*)c->goff.p, d_flags));
+    if (c->opt_inject_fail) {
+        c->opt_inject_fail = 0;
+        return sdk_fail(c, SDK_EINVAL, "injected failure (option inject_fail)");
+    }
 
     // path choice: tcgen05 only where the contraction is big enough to be a real dense GEMM
     const double macs = (double)N * (double)P * (double)Dp;
@@ -344,7 +394,8 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
     // a handful of query segments: one HBM-bound pass over the bank on the CUDA cores (gemv.cu)
     // (its candidate slots are indexed by label id: a handful of segments scattered over very many labels stays generic)
     const bool use_gemv = path == 2 && c->opt_gemv && sdk_gemv_applicable(N, Dp) && L <= 64;
-    bool use_acc = path == 2 && !use_gemv && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048;
+    bool use_acc = path == 2 && !use_gemv && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048 &&
+                   (uintptr_t)d_seg % 16 == 0;     // its scatter-normalise reads the raw rows with 128-bit loads
     if (use_acc && c->opt_acc != 2 && !(Dp <= 256 || L > 2048)) use_acc = false;
     int64_t acc_steps = 0;
     if (path == 2) {   // the plan of either tcgen05 kernel trusts goff: reject bad labels before going on
@@ -371,22 +422,42 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
     const PaGroup* seg_grp = nullptr;      // row addressing of the segment operands (identity unless interleaved)
 
     if (path == 1) {
+        c->last_ncand = 0;
         const void* seg_ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
         SDK_TRY(sdk_reserve(c, c->qpool, (size_t)L * P * 8));
         SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, nullptr, L, nullptr, P,
                                  pool, (long long*)c->qpool.p, nullptr, N));
         SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L, nullptr, P, pool,
                                   (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
-                                  c->row_offset, nullptr, 0.f, nullptr, 0, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
+                                  c->row_offset, nullptr, 0.f, 0.f, nullptr, 0, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
     } else {
         // stage A: tcgen05 pooled GEMM -> per-label candidate rows + bound on everything else.
-        // eps bounds |approx - canonical|: bf16 operands are shared (exact products, fp32 accumulate);
-        // for an fp32 bank stage A additionally rounds the operands to bf16 (2 * 2^-8 relative).
-        float eps = c->opt_eps >= 0 ? (float)c->opt_eps : (bf16 ? 1e-3f : 1.2e-2f);
+        // Certificate margin: eps_g = eps_base + eps_chain * chain_g bounds |stage-A pooled score - canonical| of group g
+        // (select.cu; derivation in DESIGN.md section 2).  u = 2^-21 per tensor-core accumulator update, relative to the
+        // running magnitude (4 ulp: truncating accumulation with >= 2 guard bits -- the model the adversarial tests
+        // validate); normalised operands, so |dot| <= ~1.01 and a partial pooled sum of t segments is <= ~1.01 t.
+        //   one segment's dot product: Dp/16 updates of magnitude <= 1             -> eps_dot = u * Dp/16
+        //   accumulate-pooling (chain = T segments per column): sum_t u*(Dp/16)*t / n  -> eps_chain = u/2 * Dp/16 per segment
+        //   epilogue mean pooling: fp32 adds of 32-column block sums, RN            -> 2^-24 per block (chain = n/32 + 70)
+        //   fp32 bank: stage A rounds both operands to bf16 (2 * 2^-9 relative)     -> + 2^-8 * 1.02, covered by 1.2e-2
+        const float u_mma = 4.76837158e-07f;                     // 2^-21
+        const float kc = (float)(Dp / 16);
+        float eps_base = (bf16 ? 0.f : 1.2e-2f) + 1.05f * u_mma * kc + 4.8e-7f, eps_chain = 0.f;
+        int32_t chain_div = 0;
+        double chain_max = 0.0;
+        if (use_acc) { eps_chain = 0.5f * 1.05f * u_mma * kc; chain_max = (double)c->pa_chain_max; }
+        else if (pool == SDK_POOL_MEAN && !use_gemv) { eps_chain = 6.1e-8f; chain_div = 32; chain_max = (double)(N / 32 + 70); }
+        if (c->opt_eps >= 0) { eps_base = (float)c->opt_eps; eps_chain = 0.f; }       // test knob: fixed margin
+        const float eps = eps_base + eps_chain * (float)chain_max;                     // launch-wide (candidate threshold tau)
+        c->last_eps_base = eps_base;
+        c->last_eps_chain = eps_chain;
         int ncand = std::max(c->opt_cand, k + 6);
         if (ncand > 64) ncand = 64;
         float tau = (float)(threshold - 2.0 * (double)eps);
         if (!(tau > -3.0e38f)) tau = -3.0e38f;
+        SDK_TRY(sdk_reserve(c, c->cand_val, (size_t)L * ncand * 4));
+        c->last_ncand = ncand;
+        c->last_cand_groups = L;
         SDK_TRY(sdk_reserve(c, c->cand_row, (size_t)L * ncand * 4));
         SDK_TRY(sdk_reserve(c, c->gbound, (size_t)L * 4));
         SDK_TRY(sdk_reserve(c, c->fb_list, (size_t)L * 4));
@@ -416,7 +487,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool.p, (const int64_t*)c->goff.p, nullptr, L,
                                   (const int32_t*)c->cand_row.p, ncand, pool, (const int32_t*)c->row_speaker.p,
                                   (const uint8_t*)c->row_trust.p, threshold, k, c->row_offset, (const float*)c->gbound.p,
-                                  eps, acc_grp, Dp / 16, d_flags + 1, (int32_t*)c->fb_list.p, o_row, o_score, o_count, o_trust, o_spk));
+                                  eps_base, eps_chain, acc_grp, chain_div, d_flags + 1, (int32_t*)c->fb_list.p, o_row, o_score, o_count, o_trust, o_spk));
         // groups whose certificate failed are re-done exhaustively in the canonical arithmetic
         int32_t hf[2] = {0, 0};
         SDK_CUDA(c, cudaMemcpyAsync(hf, d_flags, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -441,7 +512,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
             SDK_TRY(sdk_launch_select(c, (const long long*)c->qpool2.p, (const int64_t*)c->goff.p, fb, nfb,
                                       (const int32_t*)c->cand_row2.p, ncand2, pool, (const int32_t*)c->row_speaker.p,
                                       (const uint8_t*)c->row_trust.p, threshold, k, c->row_offset, (const float*)c->gbound.p,
-                                      eps, acc_grp, Dp / 16, d_flags + 1, (int32_t*)c->fb_list2.p, o_row, o_score, o_count, o_trust, o_spk));
+                                      eps_base, eps_chain, acc_grp, chain_div, d_flags + 1, (int32_t*)c->fb_list2.p, o_row, o_score, o_count, o_trust, o_spk));
             SDK_CUDA(c, cudaMemcpyAsync(hf, d_flags, 8, cudaMemcpyDeviceToHost, c->stream));
             SDK_CUDA(c, cudaStreamSynchronize(c->stream));
             c->last_retry += nfb;
@@ -458,11 +529,51 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
                                      pool, (long long*)c->dense.p, seg_grp));
             SDK_TRY(sdk_launch_select(c, (const long long*)c->dense.p, (const int64_t*)c->goff.p, gl, m, nullptr, P, pool,
                                       (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
-                                      c->row_offset, nullptr, 0.f, nullptr, 0, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
+                                      c->row_offset, nullptr, 0.f, 0.f, nullptr, 0, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
         }
         SDK_CUDA(c, cudaMemsetAsync(d_flags + 1, 0, 4, c->stream));   // fallback counter consumed
     }
     return SDK_OK;
+}
+
+// An empty shard (P == 0) has nothing to score: its lists are empty, and it still joins the collective.
+static int sdk_identify_any(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t label_base,
+                            int32_t pool, double threshold, int32_t k) {
+    if (c->P == 0) {
+        SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
+        SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, label_base, (int64_t*)c->goff.p, c->out.flags));   // labels are still validated
+        sdk_out_view v = c->out;
+        v.row += (size_t)label_base * k; v.score += (size_t)label_base * k; v.spk += (size_t)label_base * k;
+        v.trust += (size_t)label_base * k; v.count += label_base;
+        c->last_path = 0;
+        return sdk_launch_fill_empty(c, v, L, k);
+    }
+    return sdk_identify_core(c, d_seg, d_seg_label, N, L, label_base, pool, threshold, k);
+}
+
+// Row-sharded mode: every rank MUST enter the all-gather once per identify call, or its peers block forever.  A rank
+// whose local pass failed (bad labels are reported through the flags instead; this is for ENOMEM / tensor-map / CUDA
+// launch errors) publishes empty lists plus a status word, joins the collective, and returns its own error afterwards;
+// its peers see SDK_EPEER at fetch time.  If not even that is possible the communicator is aborted.
+static int sdk_finish_collective(sdk_ctx* c, int32_t L, int32_t k, int local_rc) {
+    if (c->world <= 1) return local_rc;
+    const std::string local_msg = c->err;
+    if (local_rc != SDK_OK) {
+        bool ok = c->out_pack.p && c->out.bytes > 0 && cudaGetLastError() == cudaSuccess;
+        if (ok) {
+            int32_t st = local_rc;
+            ok = sdk_launch_fill_empty(c, c->out, L, k) == SDK_OK &&
+                 cudaMemcpyAsync(c->out.flags + SDK_FLAG_STATUS, &st, 4, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+                 cudaStreamSynchronize(c->stream) == cudaSuccess;
+        }
+        if (!ok) {
+            if (c->nccl_comm && g_nccl.CommAbort) { g_nccl.CommAbort(c->nccl_comm); c->nccl_comm = nullptr; }
+            return sdk_fail(c, local_rc, local_msg + " (the NCCL communicator was aborted: this rank could not join the all-gather)");
+        }
+    }
+    int r = sdk_allgather_merge(c, L, k);
+    if (local_rc != SDK_OK) return sdk_fail(c, local_rc, local_msg);
+    return r;
 }
 
 int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t pool,
@@ -473,68 +584,68 @@ int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label,
     c->have_assign = false;
     c->last_fallback = 0;
     c->last_retry = 0;
-    SDK_TRY(sdk_reserve_results(c, L, k));
-    SDK_TRY(sdk_identify_core(c, d_seg, d_seg_label, N, L, 0, pool, threshold, k));
+    int r = sdk_reserve_results(c, L, k);
+    if (r == SDK_OK) r = sdk_identify_any(c, d_seg, d_seg_label, N, L, 0, pool, threshold, k);
     c->L = L; c->k = k; c->N = N;
-    if (c->world > 1) SDK_TRY(sdk_allgather_merge(c, L, k));
+    SDK_TRY(sdk_finish_collective(c, L, k, r));
     c->have_results = true;
     return SDK_OK;
 }
 
-// one ncclAllGather of the packed per-rank top-k, then K4 (the only collective)
+// one ncclAllGather of the head of every rank's result record, then K4 reads the gathered records in place
+// (the only collective; no packing or unpacking copies)
 static int sdk_allgather_merge(sdk_ctx* c, int32_t L, int32_t k) {
-    const size_t n = (size_t)L * k;
-    // packed per-rank record: rows i64 | scores f32 | spk i32 | counts i32 | trust u8
-    const size_t off_rows = 0, off_score = off_rows + n * 8, off_spk = off_score + n * 4, off_cnt = off_spk + n * 4,
-                 off_trust = off_cnt + (size_t)L * 4;
-    size_t rec = off_trust + n;
-    rec = (rec + 15) / 16 * 16;
-    SDK_TRY(sdk_reserve(c, c->gather, rec * (size_t)(c->world + 1)));
-    char* mine = (char*)c->gather.p;
-    char* all = mine + rec;
-    SDK_CUDA(c, cudaMemcpyAsync(mine + off_rows, c->out_row.p, n * 8, cudaMemcpyDeviceToDevice, c->stream));
-    SDK_CUDA(c, cudaMemcpyAsync(mine + off_score, c->out_score.p, n * 4, cudaMemcpyDeviceToDevice, c->stream));
-    SDK_CUDA(c, cudaMemcpyAsync(mine + off_spk, c->out_spk.p, n * 4, cudaMemcpyDeviceToDevice, c->stream));
-    SDK_CUDA(c, cudaMemcpyAsync(mine + off_cnt, c->out_count.p, (size_t)L * 4, cudaMemcpyDeviceToDevice, c->stream));
-    SDK_CUDA(c, cudaMemcpyAsync(mine + off_trust, c->out_trust.p, n, cudaMemcpyDeviceToDevice, c->stream));
-    int e = g_nccl.AllGather(mine, all, rec, SDK_NCCL_CHAR, c->nccl_comm, c->stream);
+    if (!c->nccl_comm) return sdk_fail(c, SDK_ENCCL, "the NCCL communicator of this context was aborted");
+    const size_t rec = c->out.gather_bytes;
+    SDK_TRY(sdk_reserve(c, c->gather, rec * (size_t)c->world));
+    int e = g_nccl.AllGather(c->out_pack.p, c->gather.p, rec, SDK_NCCL_CHAR, c->nccl_comm, c->stream);
     if (e != 0) return sdk_fail(c, SDK_ENCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error"));
-    // the merge kernel reads rank r's lists at all + r*rec; lists are [world][L,k] with stride rec,
-    // so repack pointers: K4 takes base pointers and assumes dense [world,L,k] -> compact first.
-    // (rec is tiny: L*k*21 bytes; compaction is 5 small D2D copies per rank)
-    SDK_TRY(sdk_reserve(c, c->dense, (size_t)c->world * (n * 17 + (size_t)L * 4) + 64));
-    char* d = (char*)c->dense.p;
-    int64_t* g_rows = (int64_t*)d;
-    float* g_score = (float*)(d + (size_t)c->world * n * 8);
-    int32_t* g_spk = (int32_t*)(d + (size_t)c->world * n * 12);
-    int32_t* g_cnt = (int32_t*)(d + (size_t)c->world * n * 16);
-    uint8_t* g_trust = (uint8_t*)(d + (size_t)c->world * n * 16 + (size_t)c->world * L * 4);
-    for (int r = 0; r < c->world; ++r) {
-        const char* src = all + (size_t)r * rec;
-        SDK_CUDA(c, cudaMemcpyAsync(g_rows + (size_t)r * n, src + off_rows, n * 8, cudaMemcpyDeviceToDevice, c->stream));
-        SDK_CUDA(c, cudaMemcpyAsync(g_score + (size_t)r * n, src + off_score, n * 4, cudaMemcpyDeviceToDevice, c->stream));
-        SDK_CUDA(c, cudaMemcpyAsync(g_spk + (size_t)r * n, src + off_spk, n * 4, cudaMemcpyDeviceToDevice, c->stream));
-        SDK_CUDA(c, cudaMemcpyAsync(g_cnt + (size_t)r * L, src + off_cnt, (size_t)L * 4, cudaMemcpyDeviceToDevice, c->stream));
-        SDK_CUDA(c, cudaMemcpyAsync(g_trust + (size_t)r * n, src + off_trust, n, cudaMemcpyDeviceToDevice, c->stream));
+    return sdk_launch_merge_topk(c, c->gather.p, rec, c->out, c->world, L, k);
+}
+
+// Merge of `world` per-shard result lists that were produced elsewhere (other processes / nodes, or two contexts of
+// one process): host arrays in, the merged lists become this context's results (sdk_assign / sdk_results_fetch work
+// on them).  Same kernel as the one that follows the all-gather.
+int sdk_merge_topk(sdk_ctx* c, int32_t world, int32_t L, int32_t k, const int64_t* rows, const float* scores,
+                   const int32_t* counts, const uint8_t* trust) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    if (world < 1 || world > 1024 || L < 1 || k < 1 || k > SDK_MAX_K) return sdk_fail(c, SDK_EINVAL, "merge: need 1 <= world <= 1024, L >= 1, 1 <= k <= 32");
+    if (!rows || !scores || !counts) return sdk_fail(c, SDK_EINVAL, "merge: rows/scores/counts is NULL");
+    cudaSetDevice(c->device);
+    c->have_results = false;
+    c->have_assign = false;
+    SDK_TRY(sdk_reserve_results(c, L, k));
+    const sdk_out_view& v = c->out;
+    const size_t rec = v.gather_bytes, n = (size_t)L * k;
+    std::vector<char> h(rec * (size_t)world, 0);
+    for (int w = 0; w < world; ++w) {
+        char* r = h.data() + rec * (size_t)w;
+        memcpy(r + v.off_row, rows + (size_t)w * n, n * 8);
+        memcpy(r + v.off_score, scores + (size_t)w * n, n * 4);
+        memset(r + v.off_spk, 0xff, n * 4);
+        memcpy(r + v.off_count, counts + (size_t)w * L, (size_t)L * 4);
+        if (trust) memcpy(r + v.off_trust, trust + (size_t)w * n, n);
+        else memset(r + v.off_trust, SDK_TRUST_UNKNOWN, n);
+        for (int32_t g = 0; g < L; ++g) {
+            const int32_t cnt = counts[(size_t)w * L + g];
+            if (cnt < 0 || cnt > k) return sdk_fail(c, SDK_EINVAL, "merge: counts must be in [0,k]");
+        }
     }
-    return sdk_launch_merge_topk(c, g_rows, g_score, g_trust, g_spk, g_cnt, c->world, L, k, (int64_t*)c->out_row.p,
-                                 (float*)c->out_score.p, (int32_t*)c->out_count.p, (uint8_t*)c->out_trust.p,
-                                 (int32_t*)c->out_spk.p);
+    SDK_TRY(sdk_reserve(c, c->gather, rec * (size_t)world));
+    SDK_CUDA(c, cudaMemcpyAsync(c->gather.p, h.data(), h.size(), cudaMemcpyHostToDevice, c->stream));
+    SDK_CUDA(c, cudaStreamSynchronize(c->stream));      // h goes out of scope
+    SDK_TRY(sdk_launch_merge_topk(c, c->gather.p, rec, v, world, L, k));
+    c->L = L; c->k = k; c->N = 0;
+    c->have_results = true;
+    return SDK_OK;
 }
 
 // Host-buffer entry point.  Large batches are cut at label-group boundaries into chunks that are copied on a second
 // stream into two staging buffers while the previous chunk is being scored, so end-to-end time is
 // max(PCIe, compute) instead of their sum, and the device footprint is two chunks instead of the whole batch.
-int sdk_identify(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
-                 double threshold, int32_t k, int64_t* out_row, float* out_score, int32_t* out_count) {
-    SDK_TRY(sdk_check_identify_args(c, seg, seg_label, N, L, pool, threshold, k));
-    cudaSetDevice(c->device);
-    c->have_results = false;
-    c->have_assign = false;
-    c->last_fallback = 0;
-    c->last_retry = 0;
+static int sdk_identify_host_body(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
+                                  double threshold, int32_t k) {
     const int32_t D = c->D;
-    SDK_TRY(sdk_reserve_results(c, L, k));
     const size_t row_bytes = (size_t)D * 4;
     const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)((size_t)c->opt_chunk_mb << 20) / (int64_t)row_bytes);
     if (N <= chunk_rows + chunk_rows / 4) {
@@ -544,7 +655,7 @@ int sdk_identify(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t
             SDK_CUDA(c, cudaMemcpyAsync(c->seg_raw.p, seg, (size_t)N * row_bytes, cudaMemcpyHostToDevice, c->stream));
             SDK_CUDA(c, cudaMemcpyAsync(c->seg_lab.p, seg_label, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
         }
-        SDK_TRY(sdk_identify_core(c, (const float*)c->seg_raw.p, (const int32_t*)c->seg_lab.p, N, L, 0, pool, threshold, k));
+        SDK_TRY(sdk_identify_any(c, (const float*)c->seg_raw.p, (const int32_t*)c->seg_lab.p, N, L, 0, pool, threshold, k));
     } else {
         // chunk cut points: first label change at or after each multiple of chunk_rows
         for (int64_t i = 1; i < N; ++i)
@@ -591,13 +702,26 @@ int sdk_identify(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t
             const int32_t g1 = (i + 1 < nchunk) ? seg_label[cut[i + 1]] : L;
             const int32_t gbeg = (i == 0) ? 0 : g0;
             SDK_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-            SDK_TRY(sdk_identify_core(c, (const float*)c->stage_seg[b].p, (const int32_t*)c->stage_lab[b].p, n, g1 - gbeg, gbeg,
+            SDK_TRY(sdk_identify_any(c, (const float*)c->stage_seg[b].p, (const int32_t*)c->stage_lab[b].p, n, g1 - gbeg, gbeg,
                                       pool, threshold, k));
             SDK_CUDA(c, cudaEventRecord(c->ev_consumed[b], c->stream));
         }
     }
+    return SDK_OK;
+}
+
+int sdk_identify(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
+                 double threshold, int32_t k, int64_t* out_row, float* out_score, int32_t* out_count) {
+    SDK_TRY(sdk_check_identify_args(c, seg, seg_label, N, L, pool, threshold, k));
+    cudaSetDevice(c->device);
+    c->have_results = false;
+    c->have_assign = false;
+    c->last_fallback = 0;
+    c->last_retry = 0;
+    int r = sdk_reserve_results(c, L, k);
+    if (r == SDK_OK) r = sdk_identify_host_body(c, seg, seg_label, N, L, pool, threshold, k);
     c->L = L; c->k = k; c->N = N;
-    if (c->world > 1) SDK_TRY(sdk_allgather_merge(c, L, k));
+    SDK_TRY(sdk_finish_collective(c, L, k, r));
     c->have_results = true;
     return sdk_results_fetch(c, out_row, out_score, out_count, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
@@ -607,15 +731,9 @@ int sdk_assign(sdk_ctx* c, double assign_threshold, int32_t min_trust_code) {
     if (!c->have_results) return sdk_fail(c, SDK_ESTATE, "sdk_assign before sdk_identify");
     cudaSetDevice(c->device);
     const int32_t L = c->L, k = c->k;
-    SDK_TRY(sdk_reserve(c, c->as_idx, (size_t)L * 4));
-    SDK_TRY(sdk_reserve(c, c->as_score, (size_t)L * 8));
-    SDK_TRY(sdk_reserve(c, c->as_conf, (size_t)L * 4));
-    SDK_TRY(sdk_reserve(c, c->as_cidx, (size_t)L * 12));
-    SDK_TRY(sdk_reserve(c, c->as_cscore, (size_t)L * 24));
-    SDK_TRY(sdk_launch_assign(c, (const int64_t*)c->out_row.p, (const float*)c->out_score.p, (const uint8_t*)c->out_trust.p,
-                              (const int32_t*)c->out_count.p, L, k, assign_threshold, min_trust_code, (int32_t*)c->as_idx.p,
-                              (double*)c->as_score.p, (int32_t*)c->as_conf.p, (int32_t*)c->as_cidx.p,
-                              (double*)c->as_cscore.p));
+    const sdk_out_view& v = c->out;
+    SDK_TRY(sdk_launch_assign(c, v.row, v.score, v.trust, v.count, L, k, assign_threshold, min_trust_code, v.as_idx,
+                              v.as_score, v.as_conf, v.as_cidx, v.as_cscore));
     c->have_assign = true;
     return SDK_OK;
 }
@@ -625,22 +743,52 @@ int sdk_results_fetch(sdk_ctx* c, int64_t* out_row, float* out_score, int32_t* o
                       double* cand_score) {
     if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
     if (!c->have_results) return sdk_fail(c, SDK_ESTATE, "no results: call sdk_identify first");
-    if ((assign_idx || assign_score || assign_conf || cand_idx || cand_score) && !c->have_assign)
-        return sdk_fail(c, SDK_ESTATE, "assignment outputs requested before sdk_assign");
+    const bool want_assign = assign_idx || assign_score || assign_conf || cand_idx || cand_score;
+    if (want_assign && !c->have_assign) return sdk_fail(c, SDK_ESTATE, "assignment outputs requested before sdk_assign");
     cudaSetDevice(c->device);
     const size_t n = (size_t)c->L * c->k, L = (size_t)c->L;
+    const sdk_out_view& v = c->out;
     cudaStream_t s = c->stream;
-    if (out_row) SDK_CUDA(c, cudaMemcpyAsync(out_row, c->out_row.p, n * 8, cudaMemcpyDeviceToHost, s));
-    if (out_score) SDK_CUDA(c, cudaMemcpyAsync(out_score, c->out_score.p, n * 4, cudaMemcpyDeviceToHost, s));
-    if (out_count) SDK_CUDA(c, cudaMemcpyAsync(out_count, c->out_count.p, L * 4, cudaMemcpyDeviceToHost, s));
-    if (out_trust) SDK_CUDA(c, cudaMemcpyAsync(out_trust, c->out_trust.p, n, cudaMemcpyDeviceToHost, s));
-    if (assign_idx) SDK_CUDA(c, cudaMemcpyAsync(assign_idx, c->as_idx.p, L * 4, cudaMemcpyDeviceToHost, s));
-    if (assign_score) SDK_CUDA(c, cudaMemcpyAsync(assign_score, c->as_score.p, L * 8, cudaMemcpyDeviceToHost, s));
-    if (assign_conf) SDK_CUDA(c, cudaMemcpyAsync(assign_conf, c->as_conf.p, L * 4, cudaMemcpyDeviceToHost, s));
-    if (cand_idx) SDK_CUDA(c, cudaMemcpyAsync(cand_idx, c->as_cidx.p, L * 12, cudaMemcpyDeviceToHost, s));
-    if (cand_score) SDK_CUDA(c, cudaMemcpyAsync(cand_score, c->as_cscore.p, L * 24, cudaMemcpyDeviceToHost, s));
+    const size_t need = want_assign ? v.bytes : v.gather_bytes;
+    if (need <= ((size_t)1 << 20)) {
+        // small record (latency shapes): ONE device -> host copy into pinned memory, then host copies
+        if (c->h_pack_cap < v.bytes) {
+            if (c->h_pack) cudaFreeHost(c->h_pack);
+            c->h_pack = nullptr;
+            c->h_pack_cap = 0;
+            const size_t cap = std::max<size_t>(v.bytes * 2, 65536);
+            if (cudaHostAlloc(&c->h_pack, cap, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return sdk_fail(c, SDK_ENOMEM, "cudaHostAlloc of the result staging buffer failed");
+            }
+            c->h_pack_cap = cap;
+        }
+        SDK_CUDA(c, cudaMemcpyAsync(c->h_pack, c->out_pack.p, need, cudaMemcpyDeviceToHost, s));
+        SDK_CUDA(c, cudaStreamSynchronize(s));
+        const char* h = (const char*)c->h_pack;
+        SDK_TRY(sdk_flag_error(c, (const int32_t*)h));
+        if (out_row) memcpy(out_row, h + v.off_row, n * 8);
+        if (out_score) memcpy(out_score, h + v.off_score, n * 4);
+        if (out_count) memcpy(out_count, h + v.off_count, L * 4);
+        if (out_trust) memcpy(out_trust, h + v.off_trust, n);
+        if (assign_idx) memcpy(assign_idx, h + v.off_as_idx, L * 4);
+        if (assign_score) memcpy(assign_score, h + v.off_as_score, L * 8);
+        if (assign_conf) memcpy(assign_conf, h + v.off_as_conf, L * 4);
+        if (cand_idx) memcpy(cand_idx, h + v.off_as_cidx, L * 12);
+        if (cand_score) memcpy(cand_score, h + v.off_as_cscore, L * 24);
+        return SDK_OK;
+    }
+    if (out_row) SDK_CUDA(c, cudaMemcpyAsync(out_row, v.row, n * 8, cudaMemcpyDeviceToHost, s));
+    if (out_score) SDK_CUDA(c, cudaMemcpyAsync(out_score, v.score, n * 4, cudaMemcpyDeviceToHost, s));
+    if (out_count) SDK_CUDA(c, cudaMemcpyAsync(out_count, v.count, L * 4, cudaMemcpyDeviceToHost, s));
+    if (out_trust) SDK_CUDA(c, cudaMemcpyAsync(out_trust, v.trust, n, cudaMemcpyDeviceToHost, s));
+    if (assign_idx) SDK_CUDA(c, cudaMemcpyAsync(assign_idx, v.as_idx, L * 4, cudaMemcpyDeviceToHost, s));
+    if (assign_score) SDK_CUDA(c, cudaMemcpyAsync(assign_score, v.as_score, L * 8, cudaMemcpyDeviceToHost, s));
+    if (assign_conf) SDK_CUDA(c, cudaMemcpyAsync(assign_conf, v.as_conf, L * 4, cudaMemcpyDeviceToHost, s));
+    if (cand_idx) SDK_CUDA(c, cudaMemcpyAsync(cand_idx, v.as_cidx, L * 12, cudaMemcpyDeviceToHost, s));
+    if (cand_score) SDK_CUDA(c, cudaMemcpyAsync(cand_score, v.as_cscore, L * 24, cudaMemcpyDeviceToHost, s));
     SDK_CUDA(c, cudaStreamSynchronize(s));
-    return sdk_check_flags(c);
+    return sdk_check_flags(c, v.flags);
 }
 
 // ---- config 5: pooled self-affinity -------------------------------------------------------------
@@ -683,8 +831,8 @@ int sdk_affinity_pooled_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg
     const bool bf16 = dtype == SDK_DTYPE_BF16;
     const int32_t Dp = (D + 63) / 64 * 64;
     SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
-    SDK_TRY(sdk_reserve(c, c->flags, 64));
-    SDK_CUDA(c, cudaMemsetAsync(c->flags.p, 0, 8, c->stream));
+    SDK_TRY(sdk_reserve(c, c->flags, SDK_NFLAGS * 4));
+    SDK_CUDA(c, cudaMemsetAsync(c->flags.p, 0, SDK_NFLAGS * 4, c->stream));
     SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, 0, (int64_t*)c->goff.p, (int32_t*)c->flags.p));
     const double macs = (double)N * (double)N * (double)Dp;
     int path = c->opt_path;
@@ -699,7 +847,7 @@ int sdk_affinity_pooled_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg
     if (path == 2) {
         SDK_CUDA(c, cudaMemsetAsync(d_out_nl, 0, (size_t)N * L * 4, c->stream));     // labels without segments: affinity 0
         // mean pooling: accumulate-pooling with the label columns split (poolacc.cu plan B); max pooling: generic kernel
-        bool use_acc = c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048;
+        bool use_acc = c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048 && (uintptr_t)d_seg % 16 == 0;
         int64_t acc_steps = 0;
         if (use_acc) {
             int32_t lf = 0;
@@ -754,7 +902,7 @@ int sdk_affinity_pooled(sdk_ctx* c, const float* seg, const int32_t* seg_label, 
     SDK_CUDA(c, cudaMemcpyAsync(out_nl, d_nl, (size_t)N * L * 4, cudaMemcpyDeviceToHost, c->stream));
     if (out_ll) SDK_CUDA(c, cudaMemcpyAsync(out_ll, d_ll, (size_t)L * L * 4, cudaMemcpyDeviceToHost, c->stream));
     SDK_CUDA(c, cudaStreamSynchronize(c->stream));
-    return sdk_check_flags(c);
+    return sdk_check_flags(c, (const int32_t*)c->flags.p);
 }
 
 // ---- stream / timing ----------------------------------------------------------------------------
@@ -805,6 +953,25 @@ int sdk_profile_reset(sdk_ctx* c) {
     return SDK_OK;
 }
 int64_t sdk_launch_count(sdk_ctx* c) { return c ? c->launches : 0; }
+
+// Diagnostics of the certified top-k: the first-chance candidate rows of every label group with their STAGE-A
+// (tensor-core / bank-stream) pooled scores, and the margin model eps_g = eps_base + eps_chain * chain_g.
+int sdk_stage_a_fetch(sdk_ctx* c, int32_t* rows, float* approx, int64_t cap, int32_t* ncand, float* eps_base, float* eps_chain) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    if (!c->have_results || c->last_ncand <= 0) return sdk_fail(c, SDK_ESTATE, "no stage-A lists: the last identify did not take a tensor / bank-stream path");
+    const int64_t n = (int64_t)c->last_cand_groups * c->last_ncand;
+    if (ncand) *ncand = c->last_ncand;
+    if (eps_base) *eps_base = c->last_eps_base;
+    if (eps_chain) *eps_chain = c->last_eps_chain;
+    if (rows || approx) {
+        if (cap < n) return sdk_fail(c, SDK_EINVAL, "stage-A fetch: buffers too small (need groups * ncand entries)");
+        cudaSetDevice(c->device);
+        if (rows) SDK_CUDA(c, cudaMemcpyAsync(rows, c->cand_row.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (approx) SDK_CUDA(c, cudaMemcpyAsync(approx, c->cand_val.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return SDK_OK;
+}
 int64_t sdk_last_retry(sdk_ctx* c) { return c ? c->last_retry : 0; }
 int sdk_last_path(sdk_ctx* c, int32_t* path, int64_t* n_fallback) {
     if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");

@@ -34,6 +34,30 @@ struct sdk_pending_ev {
     cudaEvent_t a, b;
 };
 
+// Result record of one rank.  ONE device allocation: the head [flags | rows | scores | spk | counts | trust] is exactly
+// what the row-sharded mode all-gathers (no packing copies), the tail holds the assignment outputs, and a fetch of a
+// small record is one device->host copy.
+#define SDK_FLAG_LABEL 0     // bit 0: label out of range, bit 1: labels not sorted
+#define SDK_FLAG_FB 1        // groups whose top-k certificate failed (counter, consumed by the host)
+#define SDK_FLAG_STATUS 2    // != 0: this rank failed before the collective (-error code)
+#define SDK_FLAG_PEER 3      // after the merge: 1 + first rank whose record carries a label flag / status
+#define SDK_NFLAGS 16
+struct sdk_out_view {
+    int32_t* flags = nullptr;
+    int64_t* row = nullptr;
+    float* score = nullptr;
+    int32_t* spk = nullptr;
+    int32_t* count = nullptr;
+    uint8_t* trust = nullptr;
+    int32_t* as_idx = nullptr;
+    double* as_score = nullptr;
+    int32_t* as_conf = nullptr;
+    int32_t* as_cidx = nullptr;
+    double* as_cscore = nullptr;
+    size_t off_row = 0, off_score = 0, off_spk = 0, off_count = 0, off_trust = 0, gather_bytes = 0;
+    size_t off_as_score = 0, off_as_cscore = 0, off_as_idx = 0, off_as_conf = 0, off_as_cidx = 0, bytes = 0;
+};
+
 struct sdk_ctx {
     int device = 0, world = 1, rank = 0;
     cudaStream_t stream = nullptr;
@@ -49,6 +73,7 @@ struct sdk_ctx {
     int opt_acc = 1;           // mean pooling with many label groups: pool inside the MMA accumulation (poolacc.cu)
     int opt_gemv = 1;          // <= 8 query segments: stream the bank once on the CUDA cores (gemv.cu) instead of tcgen05 tiles
     int opt_chunk_mb = 128;    // host-buffer identify: H2D/compute pipeline chunk size
+    int opt_inject_fail = 0;   // test knob (multi-rank error handling): fail the next local identify pass
     // bank
     int64_t P = 0;
     int32_t D = 0, Dp = 0, dtype = 0;
@@ -63,6 +88,7 @@ struct sdk_ctx {
     sdk_buf stage_seg[2], stage_lab[2];
     sdk_buf pa_hist, pa_sorted, pa_pos, pa_col_group, pa_col_meta, pa_blockT, pa_step0, pa_grp, pa_col_last, seg_il;   // accumulate-pooling plan + layout
     int32_t pa_blocks = 0;     // blocks of 256 accumulator columns in the current plan
+    int64_t pa_chain_max = 0;  // longest accumulation chain of the plan, in segments per column (max T_b)
     bool pa_split = false;     // current plan deals groups over several columns (col_meta != col_group)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
@@ -70,11 +96,16 @@ struct sdk_ctx {
     int32_t L = 0, k = 0;
     int64_t N = 0;
     bool have_results = false, have_assign = false;
-    sdk_buf out_row, out_score, out_count, out_trust, out_spk;
-    sdk_buf as_idx, as_score, as_conf, as_cidx, as_cscore;
-    sdk_buf gather;            // NCCL all-gather staging
+    sdk_buf out_pack;          // the result record (sdk_out_view)
+    sdk_out_view out;
+    void* h_pack = nullptr;    // pinned host copy of a small record (one D2H per fetch)
+    size_t h_pack_cap = 0;
+    sdk_buf gather;            // NCCL all-gather receive buffer: world records
+    bool bank_ok = false;      // a bank (possibly an empty shard of a row-sharded one) has been loaded
     void* nccl_comm = nullptr;
     int last_path = 0;
+    float last_eps_base = 0.f, last_eps_chain = 0.f;   // certificate margin model of the last tensor-path call (select.cu)
+    int32_t last_ncand = 0, last_cand_groups = 0;       // shape of cand_row / cand_val left by the last stage A
     int64_t last_fallback = 0;   // label groups re-done exhaustively (certificate failed twice)
     int64_t last_retry = 0;      // label groups whose certificate needed the second, wider candidate list
     int64_t launches = 0;
@@ -140,7 +171,7 @@ int sdk_launch_select(sdk_ctx* c, const long long* d_qpool, const int64_t* d_gof
                       const int32_t* d_glist, int32_t ngroups, const int32_t* d_cand_row,
                       int64_t nslot, int32_t pool, const int32_t* d_row_speaker,
                       const uint8_t* d_row_trust, double threshold, int32_t k, int64_t row_offset,
-                      const float* d_gbound /*null on dense*/, float eps, const PaGroup* d_grp, int32_t upd_per_seg,
+                      const float* d_gbound /*null on dense*/, float eps_base, float eps_chain, const PaGroup* d_grp, int32_t chain_div,
                       int32_t* d_fb_count,
                       int32_t* d_fb_list, int64_t* d_out_row, float* d_out_score,
                       int32_t* d_out_count, uint8_t* d_out_trust, int32_t* d_out_spk);
@@ -148,12 +179,10 @@ int sdk_launch_assign(sdk_ctx* c, const int64_t* d_row, const float* d_score,
                       const uint8_t* d_trust, const int32_t* d_count, int32_t L, int32_t k,
                       double thr, int32_t min_trust, int32_t* d_idx, double* d_ascore,
                       int32_t* d_conf, int32_t* d_cidx, double* d_cscore);
-// merge after the all-gather: world lists of [L,k] -> [L,k]
-int sdk_launch_merge_topk(sdk_ctx* c, const int64_t* d_rows, const float* d_scores,
-                          const uint8_t* d_trust, const int32_t* d_spk, const int32_t* d_counts,
-                          int32_t world, int32_t L, int32_t k, int64_t* d_out_row,
-                          float* d_out_score, int32_t* d_out_count, uint8_t* d_out_trust,
-                          int32_t* d_out_spk);
+// merge after the all-gather: `world` result records (layout of `v`, `stride` bytes apart, starting at d_all) -> v
+int sdk_launch_merge_topk(sdk_ctx* c, const void* d_all, size_t stride, const sdk_out_view& v, int32_t world, int32_t L, int32_t k);
+// rows -1 / counts 0 for the groups [0, L) of the record (a rank without bank rows, or one that failed)
+int sdk_launch_fill_empty(sdk_ctx* c, const sdk_out_view& v, int32_t L, int32_t k);
 // tcgen05 pooled GEMM (stage A): approximate pooled scores -> per-label candidate rows + bound
 int sdk_poolgemm_supported(int32_t Dp);
 int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int64_t P,

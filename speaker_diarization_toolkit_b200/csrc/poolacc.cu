@@ -89,10 +89,11 @@ __global__ void k_pa_blocks(const int64_t* __restrict__ goff, const int32_t* __r
 // step0 = exclusive prefix of T_b (one warp); plan_out = {total steps, blocks}
 __global__ void k_pa_steps(const int32_t* __restrict__ blockT, int32_t n_blocks, int64_t* __restrict__ step0, int64_t* __restrict__ plan_out) {
     const int lane = threadIdx.x;
-    int64_t carry = 0;
+    int64_t carry = 0, tmax = 0;
     for (int b0 = 0; b0 < n_blocks; b0 += 32) {
         const int b = b0 + lane;
         int64_t v = b < n_blocks ? blockT[b] : 0, incl = v;
+        tmax = v > tmax ? v : tmax;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             int64_t o = __shfl_up_sync(0xffffffffu, incl, off);
@@ -101,7 +102,9 @@ __global__ void k_pa_steps(const int32_t* __restrict__ blockT, int32_t n_blocks,
         if (b < n_blocks) step0[b] = carry + incl - v;
         carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) { step0[n_blocks] = carry; plan_out[0] = carry; plan_out[1] = n_blocks; }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { const int64_t o = __shfl_xor_sync(0xffffffffu, tmax, off); tmax = o > tmax ? o : tmax; }
+    if (lane == 0) { step0[n_blocks] = carry; plan_out[0] = carry; plan_out[1] = n_blocks; plan_out[2] = tmax; }
 }
 __global__ void k_pa_group_rows(const int64_t* __restrict__ goff, const int32_t* __restrict__ group_pos, const int64_t* __restrict__ step0,
                                 int32_t G, PaGroup* __restrict__ grp, int32_t* __restrict__ col_last) {
@@ -183,7 +186,7 @@ k_pa_plan_small(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t 
         if (!(scost[best] < 3.0e38f)) best = PA_NCAND - 1;      // cannot happen: the largest cap needs the fewest blocks
         sbest = best;
         const int T = pa_cand_T(best, pc.t_min);
-        int fill = 0, Tb = 0, nb = 0;
+        int fill = 0, Tb = 0, nb = 0, Tlong = 0;
         long long steps = 0;
         for (int i = 0; i < G; ++i) {
             const int g = sorder[i];
@@ -191,6 +194,7 @@ k_pa_plan_small(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t 
             int c = n > 0 ? (n + T - 1) / T : 1;
             if (c > PA_NB) c = PA_NB;
             const int s = n > 0 ? (n + c - 1) / c : 0;
+            Tlong = s > Tlong ? s : Tlong;
             if (fill + c > PA_NB) { blockT[nb] = Tb; step0[nb] = steps; steps += Tb; ++nb; fill = 0; Tb = 0; }
             scol0[g] = nb * PA_NB + fill;
             scnt[g] = (int16_t)c;
@@ -201,6 +205,7 @@ k_pa_plan_small(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t 
         step0[nb] = steps;
         plan_out[0] = steps;
         plan_out[1] = nb;
+        plan_out[2] = Tlong;
         s_nblocks = nb;
     }
     __syncthreads();
@@ -369,10 +374,12 @@ k_pa_plan_bins(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t* 
         __syncwarp();
         if (lane == 0) {
             long long steps = 0;
-            for (int b = 0; b < nb; ++b) { blockT[b] = sT[b]; step0[b] = steps; steps += sT[b]; }
+            int Tlong = 0;
+            for (int b = 0; b < nb; ++b) { blockT[b] = sT[b]; step0[b] = steps; steps += sT[b]; Tlong = sT[b] > Tlong ? sT[b] : Tlong; }
             step0[nb] = steps;
             plan_out[0] = steps;
             plan_out[1] = nb;
+            plan_out[2] = Tlong;
         }
     }
     __syncthreads();
@@ -799,12 +806,13 @@ int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, in
         c->launches += 6;
         SDK_CUDA(c, cudaGetLastError());
     }
-    int64_t h[2] = {0, 0};
-    SDK_CUDA(c, cudaMemcpyAsync(h, plan_out, 16, cudaMemcpyDeviceToHost, c->stream));
+    int64_t h[3] = {0, 0, 0};
+    SDK_CUDA(c, cudaMemcpyAsync(h, plan_out, 24, cudaMemcpyDeviceToHost, c->stream));
     SDK_CUDA(c, cudaStreamSynchronize(c->stream));
     if (h[1] < 0 || h[1] > max_blocks) return sdk_fail(c, SDK_ECUDA, "accumulate-pooling plan: inconsistent block count");
     c->pa_blocks = (int32_t)h[1];
     c->pa_split = small;
+    c->pa_chain_max = h[2];
     *steps_out = h[0];
     return SDK_OK;
 }
@@ -818,6 +826,7 @@ int sdk_launch_poolacc(sdk_ctx* c, const float* d_seg_raw, const int32_t* d_seg_
     if (!sdk_poolacc_applicable(Dp, G, SDK_POOL_MEAN) || !c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path unavailable");
     if (P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "tcgen05 path: at most 2^31-1 bank rows");
     if (D % 4 != 0 || D > 2048) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path needs D % 4 == 0");
+    if ((uintptr_t)d_seg_raw % 16 != 0) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path needs a 16-byte aligned segment matrix");
     const int kch = Dp / 64, MT = pa_mt_for(kch);
     const int32_t n_blocks = c->pa_blocks;
     int64_t* step0 = (int64_t*)c->pa_step0.p;

@@ -532,7 +532,7 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const
            const int32_t* __restrict__ glist, const int32_t* __restrict__ group_col,
            const int32_t* __restrict__ slot_cnt, const int32_t* __restrict__ slot_row, const float* __restrict__ slot_val,
            const float* __restrict__ slot_bound, float tau, int32_t ncand, int32_t* __restrict__ cand_row,
-           float* __restrict__ gbound) {
+           float* __restrict__ gbound, float* __restrict__ cand_val /* may be null: stage-A score of every candidate (diagnostics) */) {
     __shared__ unsigned int s_key[PG_MERGE_CAP];      // pass A: thread maxima (first 1024); pass B: compacted keys
     __shared__ int32_t s_row[PG_MERGE_CAP];
     __shared__ int hist[256];
@@ -546,6 +546,7 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const
     const int g = glist ? glist[blockIdx.x] : (sorted_group ? sorted_group[g_base + gl] : g_base + gl);
     if (g < 0) return;
     int32_t* out = cand_row + (int64_t)(glist ? blockIdx.x : g) * ncand;
+    float* outv = cand_val ? cand_val + (int64_t)(glist ? blockIdx.x : g) * ncand : nullptr;
     for (int i = tid; i < ncand; i += blockDim.x) out[i] = -1;
     if (goff[g + 1] <= goff[g]) { if (tid == 0) gbound[g] = -3.0e38f; return; }
     const int32_t* cnt = slot_cnt + (int64_t)gl * nsub;
@@ -578,7 +579,11 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const
         for (int s = tid; s < nsub; s += blockDim.x) {
             const int c0 = cnt[s];
             const int c = c0 < PG_CS ? c0 : PG_CS;
-            for (int i = 0; i < c; ++i) out[atomicAdd(&s_out, 1)] = rows[(int64_t)s * PG_CS + i];
+            for (int i = 0; i < c; ++i) {
+                const int pos = atomicAdd(&s_out, 1);
+                out[pos] = rows[(int64_t)s * PG_CS + i];
+                if (outv) outv[pos] = vals[(int64_t)s * PG_CS + i];
+            }
         }
         __syncthreads();
         if (tid == 0) gbound[g] = sdk_funkey(s_bound_key);
@@ -635,7 +640,7 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const
             const int32_t r = s_row[i];
             int rank = 0;
             for (int j = 0; j < M; ++j) { const unsigned int o = s_key[j]; rank += (o > k || (o == k && s_row[j] < r)) ? 1 : 0; }
-            if (rank < ncand) out[rank] = r;
+            if (rank < ncand) { out[rank] = r; if (outv) outv[rank] = sdk_funkey(k); }
             if (rank == ncand - 1) s_t0 = k;            // the ncand-th largest key: everything dropped is <= it
         }
         __syncthreads();
@@ -683,10 +688,10 @@ k_pg_merge(const int64_t* __restrict__ goff, int32_t g_base, int32_t nsub, const
         int c = cnt[s];
         if (i < (c < PG_CS ? c : PG_CS)) {
             unsigned int key = sdk_fkey(vals[f]);
-            if (key > T) out[atomicAdd(&s_out, 1)] = rows[f];
+            if (key > T) { const int pos = atomicAdd(&s_out, 1); out[pos] = rows[f]; if (outv) outv[pos] = vals[f]; }
             else if (key == T) {
                 int t = atomicAdd(&s_ties, 1);
-                if (t < need) out[atomicAdd(&s_out, 1)] = rows[f];
+                if (t < need) { const int pos = atomicAdd(&s_out, 1); out[pos] = rows[f]; if (outv) outv[pos] = vals[f]; }
             }
         }
     }
@@ -704,9 +709,11 @@ void pg_launch_merge(sdk_ctx* c, const int64_t* d_goff, int32_t g_base, int32_t 
     sdk_prof_scope ps(c, "merge");
     // small banks (a few hundred sub-slots per label group, tens of thousands of groups): a 256-thread CTA per group
     const int threads = nsub <= 1024 ? 256 : PG_MERGE_THREADS;
+    // the first-chance lists also record the stage-A score of every candidate (sdk_stage_a_fetch: measured certificate margin)
+    float* cv = (!d_glist && d_cand_row == (int32_t*)c->cand_row.p && c->cand_val.p) ? (float*)c->cand_val.p : nullptr;
     k_pg_merge<<<(unsigned)ngroups, threads, 0, c->stream>>>(d_goff, g_base, nsub, d_sorted_group, d_glist, d_group_col, (const int32_t*)c->slot_cnt.p,
                                                          (const int32_t*)c->slot_row.p, (const float*)c->slot_val.p,
-                                                         (const float*)c->slot_bound.p, tau, ncand, d_cand_row, d_gbound);
+                                                         (const float*)c->slot_bound.p, tau, ncand, d_cand_row, d_gbound, cv);
     c->launches++;
 }
 

@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(SDK_SEL_THREADS)
 k_select(long long* __restrict__ qpool, const int64_t* __restrict__ goff, const int32_t* __restrict__ glist,
          const int32_t* __restrict__ cand_row, int64_t nslot, int32_t pool,
          const int32_t* __restrict__ row_speaker, const uint8_t* __restrict__ row_trust, double threshold,
-         int32_t k, int64_t row_offset, const float* __restrict__ gbound, float eps, const PaGroup* __restrict__ grp,
-         int32_t upd_per_seg, int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list, int64_t* __restrict__ out_row,
+         int32_t k, int64_t row_offset, const float* __restrict__ gbound, float eps_base, float eps_chain, const PaGroup* __restrict__ grp,
+         int32_t chain_div, int32_t* __restrict__ fb_count, int32_t* __restrict__ fb_list, int64_t* __restrict__ out_row,
          float* __restrict__ out_score, int32_t* __restrict__ out_count, uint8_t* __restrict__ out_trust,
          int32_t* __restrict__ out_spk) {
     __shared__ unsigned long long sh[SDK_SEL_THREADS / 32];
@@ -98,10 +98,13 @@ k_select(long long* __restrict__ qpool, const int64_t* __restrict__ goff, const 
             // certificate: every row that was NOT re-scored has approx score <= bound, hence a
             // canonical score <= bound + eps.  It cannot enter the result if that is below the
             // threshold, or below the k-th kept score when the list is full.
-            // eps is the measured bound on |tensor-core pooled score - canonical| with a ~50x margin for chains of up to
-            // 2^16 fp32 accumulator updates; it grows linearly with the chain beyond that (giant label groups)
-            const double chain = grp ? (double)((n + grp[g].c - 1) / grp[g].c) * (double)upd_per_seg : (double)n;
-            const double eps_g = (double)eps * (chain > 65536.0 ? chain / 65536.0 : 1.0);
+            // eps_g bounds |stage-A pooled score - canonical| for THIS group: eps_base covers one segment's dot product (and,
+            // for fp32 banks, the bf16 rounding of the stage-A operands); eps_chain scales with the group's accumulation
+            // chain -- segments per accumulator column when pooling happens inside the MMA accumulation (grp != null:
+            // the partial sum grows with every segment, and so does the rounding unit), blocks of 32 columns when the
+            // epilogue pools (chain_div == 32), nothing for max pooling.  Model and derivation: DESIGN.md section 2.
+            const double chain = grp ? (double)((n + grp[g].c - 1) / grp[g].c) : (chain_div > 0 ? (double)(n / chain_div + 70) : 0.0);
+            const double eps_g = (double)eps_base + (double)eps_chain * chain;
             double b = (double)gbound[g] + eps_g;
             bool safe = (b < threshold) || (cnt == k && b < (double)kth);
             if (!safe) {
@@ -115,14 +118,14 @@ k_select(long long* __restrict__ qpool, const int64_t* __restrict__ goff, const 
 int sdk_launch_select(sdk_ctx* c, const long long* d_qpool, const int64_t* d_goff, const int32_t* d_glist,
                       int32_t ngroups, const int32_t* d_cand_row, int64_t nslot, int32_t pool,
                       const int32_t* d_row_speaker, const uint8_t* d_row_trust, double threshold, int32_t k,
-                      int64_t row_offset, const float* d_gbound, float eps, const PaGroup* d_grp, int32_t upd_per_seg,
+                      int64_t row_offset, const float* d_gbound, float eps_base, float eps_chain, const PaGroup* d_grp, int32_t chain_div,
                       int32_t* d_fb_count, int32_t* d_fb_list, int64_t* d_out_row, float* d_out_score, int32_t* d_out_count,
                       uint8_t* d_out_trust, int32_t* d_out_spk) {
     if (ngroups <= 0) return SDK_OK;
     sdk_prof_scope ps(c, "select");
     k_select<<<ngroups, SDK_SEL_THREADS, 0, c->stream>>>(const_cast<long long*>(d_qpool), d_goff, d_glist, d_cand_row,
                                                          nslot, pool, d_row_speaker, d_row_trust, threshold, k,
-                                                         row_offset, d_gbound, eps, d_grp, upd_per_seg, d_fb_count, d_fb_list, d_out_row,
+                                                         row_offset, d_gbound, eps_base, eps_chain, d_grp, chain_div, d_fb_count, d_fb_list, d_out_row,
                                                          d_out_score, d_out_count, d_out_trust, d_out_spk);
     c->launches++;
     SDK_CUDA(c, cudaGetLastError());
@@ -193,35 +196,51 @@ int sdk_launch_assign(sdk_ctx* c, const int64_t* d_row, const float* d_score, co
 // ---- K4: merge `world` per-rank top-k lists (after ncclAllGather) by (-score, global row) -------
 // Bank shards are cut on speaker boundaries (asserted by the host), so no cross-rank speaker
 // de-duplication is needed.  One warp per label group; world*k <= 8*32 entries, 8 per lane.
-__global__ void k_merge_topk(const int64_t* __restrict__ rows, const float* __restrict__ scores,
-                             const uint8_t* __restrict__ trust, const int32_t* __restrict__ spk,
-                             const int32_t* __restrict__ counts, int32_t world, int32_t L, int32_t k,
+// The lists are read in place from the gathered result records (rank r's record starts at all + r*stride and has the
+// layout of the local record: offsets o_*), so the all-gather needs no packing or unpacking copies.
+struct MergeSrc {
+    const char* all;
+    size_t stride, off_row, off_score, off_spk, off_count, off_trust;
+};
+__global__ void k_merge_topk(const MergeSrc src, int32_t world, int32_t L, int32_t k,
                              int64_t* __restrict__ o_row, float* __restrict__ o_score,
                              int32_t* __restrict__ o_count, uint8_t* __restrict__ o_trust,
-                             int32_t* __restrict__ o_spk) {
+                             int32_t* __restrict__ o_spk, int32_t* __restrict__ o_flags) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    if (warp == 0) {
+        // a peer that failed locally (status word) or saw bad labels poisons the merged result: tell the host at fetch time
+        int bad = 0x7fffffff;
+        for (int r = lane; r < world; r += 32) {
+            const int32_t* f = reinterpret_cast<const int32_t*>(src.all + (size_t)r * src.stride);
+            if (f[SDK_FLAG_STATUS] != 0 || f[SDK_FLAG_LABEL] != 0) bad = r < bad ? r : bad;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, bad, off); bad = o < bad ? o : bad; }
+        if (lane == 0 && bad != 0x7fffffff) o_flags[SDK_FLAG_PEER] = bad + 1;
+    }
     if (warp >= L) return;
     const int g = warp;
     const int total = world * k;
     int taken = 0;
-    unsigned long long last_hi = ~0ull;     // (score key << 32 | rank-major tiebreak) of the last pick
+    uint32_t last_key = 0;
     long long last_row = -1;
     for (int it = 0; it < k; ++it) {
         // best entry strictly after (last score, last row) in (-score, row) order
         uint32_t bkey = 0;
         long long brow = 0x7fffffffffffffffLL;
-        int bidx = -1;
+        int bidx = -1;                                    // rank * k + index
         for (int e = lane; e < total; e += 32) {
-            int r = e / k, i = e - r * k;
-            if (i >= counts[(int64_t)r * L + g]) continue;
-            int64_t off = ((int64_t)r * L + g) * k + i;
-            long long row = rows[off];
+            const int r = e / k, i = e - r * k;
+            const char* rec = src.all + (size_t)r * src.stride;
+            if (i >= reinterpret_cast<const int32_t*>(rec + src.off_count)[g]) continue;
+            const int64_t off = (int64_t)g * k + i;
+            const long long row = reinterpret_cast<const int64_t*>(rec + src.off_row)[off];
             if (row < 0) continue;
-            uint32_t key = sdk_fkey(scores[off]);
-            bool after = (it == 0) || key < (uint32_t)(last_hi) || (key == (uint32_t)last_hi && row > last_row);
+            const uint32_t key = sdk_fkey(reinterpret_cast<const float*>(rec + src.off_score)[off]);
+            const bool after = (it == 0) || key < last_key || (key == last_key && row > last_row);
             if (!after) continue;
-            if (bidx < 0 || key > bkey || (key == bkey && row < brow)) { bkey = key; brow = row; bidx = (int)off; }
+            if (bidx < 0 || key > bkey || (key == bkey && row < brow)) { bkey = key; brow = row; bidx = e; }
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
@@ -232,12 +251,15 @@ __global__ void k_merge_topk(const int64_t* __restrict__ rows, const float* __re
         }
         if (bidx < 0) break;
         if (lane == 0) {
+            const int r = bidx / k, i = bidx - r * k;
+            const char* rec = src.all + (size_t)r * src.stride;
+            const int64_t off = (int64_t)g * k + i;
             o_row[(int64_t)g * k + taken] = brow;
-            o_score[(int64_t)g * k + taken] = scores[bidx];
-            o_trust[(int64_t)g * k + taken] = trust[bidx];
-            o_spk[(int64_t)g * k + taken] = spk[bidx];
+            o_score[(int64_t)g * k + taken] = reinterpret_cast<const float*>(rec + src.off_score)[off];
+            o_trust[(int64_t)g * k + taken] = reinterpret_cast<const uint8_t*>(rec + src.off_trust)[off];
+            o_spk[(int64_t)g * k + taken] = reinterpret_cast<const int32_t*>(rec + src.off_spk)[off];
         }
-        last_hi = bkey;
+        last_key = bkey;
         last_row = brow;
         ++taken;
     }
@@ -252,16 +274,32 @@ __global__ void k_merge_topk(const int64_t* __restrict__ rows, const float* __re
     }
 }
 
-int sdk_launch_merge_topk(sdk_ctx* c, const int64_t* d_rows, const float* d_scores, const uint8_t* d_trust,
-                          const int32_t* d_spk, const int32_t* d_counts, int32_t world, int32_t L, int32_t k,
-                          int64_t* d_out_row, float* d_out_score, int32_t* d_out_count, uint8_t* d_out_trust,
-                          int32_t* d_out_spk) {
+int sdk_launch_merge_topk(sdk_ctx* c, const void* d_all, size_t stride, const sdk_out_view& v, int32_t world, int32_t L, int32_t k) {
     if (L <= 0) return SDK_OK;
     sdk_prof_scope ps(c, "merge");
+    MergeSrc src;
+    src.all = (const char*)d_all;
+    src.stride = stride;
+    src.off_row = v.off_row; src.off_score = v.off_score; src.off_spk = v.off_spk; src.off_count = v.off_count; src.off_trust = v.off_trust;
     int threads = 128, warps_per_block = threads / 32;
     int blocks = (L + warps_per_block - 1) / warps_per_block;
-    k_merge_topk<<<blocks, threads, 0, c->stream>>>(d_rows, d_scores, d_trust, d_spk, d_counts, world, L, k, d_out_row,
-                                                    d_out_score, d_out_count, d_out_trust, d_out_spk);
+    k_merge_topk<<<blocks, threads, 0, c->stream>>>(src, world, L, k, v.row, v.score, v.count, v.trust, v.spk, v.flags);
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}
+
+// empty lists for L label groups (a rank with no bank rows, or one that failed before the collective)
+__global__ void k_fill_empty(int64_t* __restrict__ row, float* __restrict__ score, int32_t* __restrict__ spk, int32_t* __restrict__ count,
+                             uint8_t* __restrict__ trust, int32_t L, int32_t k) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)L * k) { row[i] = -1; score[i] = 0.f; spk[i] = -1; trust[i] = SDK_TRUST_UNKNOWN; }
+    if (i < L) count[i] = 0;
+}
+int sdk_launch_fill_empty(sdk_ctx* c, const sdk_out_view& v, int32_t L, int32_t k) {
+    if (L <= 0) return SDK_OK;
+    const int64_t n = (int64_t)L * k;
+    k_fill_empty<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(v.row, v.score, v.spk, v.count, v.trust, L, k);
     c->launches++;
     SDK_CUDA(c, cudaGetLastError());
     return SDK_OK;

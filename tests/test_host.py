@@ -30,7 +30,7 @@ def test_abi_exports_every_declared_symbol():
     lib = _native.load()
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} not exported"
-    assert lib.sdk_abi_version() == 1
+    assert lib.sdk_abi_version() == 2
 
 
 def test_no_cpu_fallback():

@@ -52,6 +52,45 @@ def main():
         same = same and np.array_equal(out["assign_idx"], a[0]) and np.array_equal(out["assign_score"], a[1])
         print(f"[rank {rank}/{world}] {name}: shard rows [{p0},{p1}) path={ctx.last_path()} -> {'OK' if same else 'MISMATCH'}", flush=True)
         ok = ok and same
+    # ---- empty shards: more ranks than speaker runs: the ranks without rows still join the all-gather ----
+    case = synth.make_case(7, [30, 12, 25], 1, 128, rows_per_speaker=3, impostor_frac=0.0)
+    shards = sharding.shard_bank_rows(case.row_speaker, world)
+    p0, p1 = shards[rank]
+    assert sum(1 for a, b in shards if b > a) == 1
+    ctx.set_option("path", 0)
+    ctx.bank_load(case.bank[p0:p1], case.row_speaker[p0:p1], case.row_trust[p0:p1], dtype=1, global_row_offset=p0)
+    rows, scores, counts = ctx.identify(case.seg, case.seg_label, case.G, pool=0, threshold=-1.0, k=3)
+    ref = canonical.identify(case.seg, case.goff, case.bank, case.row_speaker, case.n_speakers, mode=1, pool=0, threshold=-1.0, k=3)
+    same = np.array_equal(rows, ref[0]) and np.array_equal(counts, ref[2]) and np.array_equal(scores.view(np.uint32), ref[1].view(np.uint32))
+    print(f"[rank {rank}/{world}] empty-shard: shard rows [{p0},{p1}) -> {'OK' if same else 'MISMATCH'}", flush=True)
+    ok = ok and same
+
+    # ---- a rank that fails locally must not hang its peers: it joins the collective with a status word, returns its
+    #      own error, and the others get SDK_EPEER at fetch time ----
+    rng = np.random.default_rng(3)
+    case = synth.make_case(9, synth.zipf_counts(rng, 300, 4), 64 * world, 64, impostor_frac=0.0)
+    shards = sharding.shard_bank_rows(case.row_speaker, world)
+    p0, p1 = shards[rank]
+    ctx.bank_load(case.bank[p0:p1], case.row_speaker[p0:p1], case.row_trust[p0:p1], dtype=1, global_row_offset=p0)
+    bad = world - 1
+    ctx.set_option("path", 1)
+    err = None
+    try:
+        if rank == bad:
+            ctx.set_option("inject_fail", 1)       # test knob: the next local pass fails (SDK_EINVAL) after its first kernels
+        ctx.identify(case.seg, case.seg_label, case.G, pool=0, threshold=-1.0, k=3)
+    except _native.NativeError as e:
+        err = e
+    want = (err is not None) and (err.code == (-22 if rank == bad else -70))
+    print(f"[rank {rank}/{world}] failing-peer: error {err.code if err else None} ({'expected' if want else 'UNEXPECTED'})", flush=True)
+    ok = ok and want
+    # the communicator is still usable afterwards
+    rows, scores, counts = ctx.identify(case.seg, case.seg_label, case.G, pool=0, threshold=-1.0, k=3)
+    ref = canonical.identify(case.seg, case.goff, case.bank, case.row_speaker, case.n_speakers, mode=1, pool=0, threshold=-1.0, k=3)
+    same = np.array_equal(rows, ref[0]) and np.array_equal(scores.view(np.uint32), ref[1].view(np.uint32))
+    print(f"[rank {rank}/{world}] after-failure: -> {'OK' if same else 'MISMATCH'}", flush=True)
+    ok = ok and same
+
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     ctx.close()
