@@ -28,6 +28,18 @@ import threading
 import time
 from pathlib import Path
 
+
+def _host_threads_for_the_cpu_arm():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the reference arm (rank 0 only, the other ranks exit)
+    must time the CPU path with ALL host threads, so the BLAS thread count is set before NumPy is imported."""
+    if "--impl" in sys.argv and "reference" in sys.argv[sys.argv.index("--impl") + 1:sys.argv.index("--impl") + 2]:
+        n = str(os.cpu_count() or 1)
+        for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+            os.environ[v] = n
+
+
+_host_threads_for_the_cpu_arm()
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
@@ -193,6 +205,18 @@ class Clocks:
 
 
 # ---- CPU port (cpu_baseline and --impl reference) -------------------------------------------------
+def blas_threads():
+    """threads the BLAS behind NumPy will really use (threadpoolctl), else the environment's word for it"""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [int(i.get("num_threads", 0)) for i in threadpool_info() if i.get("user_api") == "blas"]
+        if n:
+            return max(n)
+    except Exception:
+        pass
+    return int(os.environ.get("OMP_NUM_THREADS") or os.cpu_count() or 1)
+
+
 def cpu_port_rate(cfg, counts, truth, budget_s, rec_cap=None):
     """Times oracle/matching_np.identify (+ the combine_signals restatement) recording by recording on the host.
     Returns (pairs/s, recordings timed, seconds)."""
@@ -215,7 +239,7 @@ def cpu_port_rate(cfg, counts, truth, budget_s, rec_cap=None):
         tr = np.repeat(np.where(truth[r] >= 0, truth[r] % P, 0), c)
         seg = cent[tr] + (0.35 / math.sqrt(D)) * rng.standard_normal((n, D)).astype(np.float32)
         t0 = time.perf_counter()
-        rows, scores, cnt = mnp.identify(seg, goff, bank, row_speaker, mode=cfg["dtype"], pool=0, threshold=cfg["thr"], k=cfg["k"])
+        rows, scores, cnt = mnp.identify(seg, goff, bank, row_speaker, mode=cfg["dtype"], pool=cfg.get("pool", 0), threshold=cfg["thr"], k=cfg["k"])
         for g in range(L):
             sigs = [mnp.Signal("embedding_match", str(int(rows[g, i])), float(scores[g, i]),
                                {"trust_level": trust_names[int(rows[g, i]) % 3]}) for i in range(cnt[g])]
@@ -227,10 +251,16 @@ def cpu_port_rate(cfg, counts, truth, budget_s, rec_cap=None):
 
 
 def run_reference(args, cfg, counts, truth):
-    """`--impl reference`: the CPU port on the host cores; each step is a bounded sample of the workload."""
+    """`--impl reference`: the CPU port on the host cores, all of them; each step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    try:                                    # in case a BLAS was initialised with the launcher's OMP_NUM_THREADS=1 anyway
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+    nthreads = blas_threads()
     per_step = max(1.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_port_rate(cfg, counts, truth, per_step)
@@ -241,12 +271,12 @@ def run_reference(args, cfg, counts, truth):
         tot_t += t
         tot_rec += n_rec
     value = tot_pairs / tot_t
-    sample = f"{tot_rec / max(1, args.steps):.0f} recordings per step (~{per_step:.0f} s of NumPy/OpenBLAS), bank {cfg['P_cpu']} rows"
+    sample = f"{tot_rec / max(1, args.steps):.0f} recordings per step (~{per_step:.0f} s of NumPy/OpenBLAS on {nthreads} threads), bank {cfg['P_cpu']} rows"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
             "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "config": {"workload": cfg["desc"], "pool": "max" if cfg.get("pool") else "mean"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "host_cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0

@@ -433,14 +433,16 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
     } else {
         // stage A: tcgen05 pooled GEMM -> per-label candidate rows + bound on everything else.
         // Certificate margin: eps_g = eps_base + eps_chain * chain_g bounds |stage-A pooled score - canonical| of group g
-        // (select.cu; derivation in DESIGN.md section 2).  u = 2^-21 per tensor-core accumulator update, relative to the
-        // running magnitude (4 ulp: truncating accumulation with >= 2 guard bits -- the model the adversarial tests
-        // validate); normalised operands, so |dot| <= ~1.01 and a partial pooled sum of t segments is <= ~1.01 t.
+        // (select.cu; derivation in DESIGN.md section 2).  u = 6 * 2^-23 per tensor-core accumulator update (one K = 16 MMA),
+        // relative to the running magnitude: the accumulation TRUNCATES -- measured on all-positive data (every partial
+        // sum grows, tests/test_gpu_certificate.py) the loss is a systematic ~2.2 ulp per update, i.e. about five
+        // truncated addends of up to one ulp each; 6 ulp is the worst case of that model.  Normalised operands, so
+        // |dot| <= ~1.01 and a partial pooled sum of t segments is <= ~1.01 t.
         //   one segment's dot product: Dp/16 updates of magnitude <= 1             -> eps_dot = u * Dp/16
         //   accumulate-pooling (chain = T segments per column): sum_t u*(Dp/16)*t / n  -> eps_chain = u/2 * Dp/16 per segment
         //   epilogue mean pooling: fp32 adds of 32-column block sums, RN            -> 2^-24 per block (chain = n/32 + 70)
         //   fp32 bank: stage A rounds both operands to bf16 (2 * 2^-9 relative)     -> + 2^-8 * 1.02, covered by 1.2e-2
-        const float u_mma = 4.76837158e-07f;                     // 2^-21
+        const float u_mma = 7.15255737e-07f;                     // 6 * 2^-23
         const float kc = (float)(Dp / 16);
         float eps_base = (bf16 ? 0.f : 1.2e-2f) + 1.05f * u_mma * kc + 4.8e-7f, eps_chain = 0.f;
         int32_t chain_div = 0;
@@ -598,6 +600,7 @@ static int sdk_allgather_merge(sdk_ctx* c, int32_t L, int32_t k) {
     if (!c->nccl_comm) return sdk_fail(c, SDK_ENCCL, "the NCCL communicator of this context was aborted");
     const size_t rec = c->out.gather_bytes;
     SDK_TRY(sdk_reserve(c, c->gather, rec * (size_t)c->world));
+    sdk_prof_scope ps(c, "allgather");                   // the collective + K4 (bench.py: allgather_merge_us)
     int e = g_nccl.AllGather(c->out_pack.p, c->gather.p, rec, SDK_NCCL_CHAR, c->nccl_comm, c->stream);
     if (e != 0) return sdk_fail(c, SDK_ENCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error"));
     return sdk_launch_merge_topk(c, c->gather.p, rec, c->out, c->world, L, k);

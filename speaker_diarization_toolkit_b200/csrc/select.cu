@@ -276,7 +276,7 @@ __global__ void k_merge_topk(const MergeSrc src, int32_t world, int32_t L, int32
 
 int sdk_launch_merge_topk(sdk_ctx* c, const void* d_all, size_t stride, const sdk_out_view& v, int32_t world, int32_t L, int32_t k) {
     if (L <= 0) return SDK_OK;
-    sdk_prof_scope ps(c, "merge");
+    sdk_prof_scope ps(c, "merge_topk");
     MergeSrc src;
     src.all = (const char*)d_all;
     src.stride = stride;

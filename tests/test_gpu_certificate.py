@@ -3,7 +3,7 @@
 The tensor-core stage A only PROPOSES candidates; ids are bit-exact because (a) the candidates are re-scored in the
 canonical arithmetic and (b) a certificate proves that no row left out can enter the result: its stage-A score plus
 eps_g must stay below the k-th kept score (or the threshold).  eps_g is a MODEL of the stage-A rounding error (api.cu /
-DESIGN.md section 2: 2^-21 per accumulator update relative to the running magnitude).  These tests attack exactly that:
+DESIGN.md section 2: 6 * 2^-23 per accumulator update relative to the running magnitude).  These tests attack exactly that:
 all-positive embeddings (every partial sum grows monotonically: the worst case for a truncating accumulator), label
 groups of thousands of segments accumulated in ONE TMEM column, and dozens of bank rows whose canonical pooled scores
 differ by less than 1e-6 around the k-th place.  They assert the ids / order / scores against the oracle AND that the
@@ -109,7 +109,7 @@ def test_certificate_adversarial_accumulate_pooling_long_chain(ctx, oracle):
         eps_giant = eps_base + eps_chain * n_giant
         print(f"\n[certificate] accumulate-pooling chain {n_giant} x {D // 16} updates: measured max |stage A - canonical| = {worst:.3e}, "
               f"model eps_g = {eps_giant:.3e} (ratio {eps_giant / max(worst, 1e-12):.1f}), near-tie window {tie_span:.2e}")
-        assert worst <= 0.25 * eps_giant, (worst, eps_giant)
+        assert worst <= 0.6 * eps_giant, (worst, eps_giant)
     finally:
         ctx.set_option("path", 0)
         ctx.set_option("acc", 1)
@@ -138,7 +138,7 @@ def test_certificate_adversarial_epilogue_pooling(ctx, oracle, pool):
         eps_g = eps_base + eps_chain * (n // 32 + 70 if pool == 0 else 0)
         print(f"\n[certificate] epilogue pooling (pool={pool}), D=512, n={n}: measured {worst:.3e}, model {eps_g:.3e} "
               f"(ratio {eps_g / max(worst, 1e-12):.1f}), near-tie window {tie_span:.2e}")
-        assert worst <= 0.5 * eps_g, (worst, eps_g)
+        assert worst <= 0.6 * eps_g, (worst, eps_g)
     finally:
         ctx.set_option("path", 0)
         ctx.set_option("acc", 1)
@@ -162,7 +162,7 @@ def test_certificate_adversarial_bank_stream(ctx, oracle):
         assert ctx.last_path()[0] == 4
         worst, eps_base, eps_chain = _stage_a_error(ctx, oracle, seg8, goff, bank, 0, [0, 1, 2])
         print(f"\n[certificate] bank stream, D=512: measured {worst:.3e}, model {eps_base:.3e} (ratio {eps_base / max(worst, 1e-12):.1f})")
-        assert worst <= 0.5 * eps_base, (worst, eps_base)
+        assert worst <= 0.6 * eps_base, (worst, eps_base)
     finally:
         ctx.set_option("path", 0)
 
