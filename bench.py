@@ -380,44 +380,67 @@ def run_cfg5(args, cfg):
     return 0
 
 
-# ---- main -----------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the recordings (debug runs only; 1.0 = the named config)")
-    ap.add_argument("--cta-group", type=int, default=1, choices=[1, 2], help="tcgen05 kernel variant (2 = CTA pairs)")
-    ap.add_argument("--acc", type=int, default=1, choices=[0, 1, 2], help="accumulate-pooling kernel: 0 off, 1 auto, 2 force (A/B runs)")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    args = ap.parse_args()
-    cfg = dict(WORKLOADS[args.workload])
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    sharded = args.workload.startswith("cfg4")
+# ---- sampled full-scale parity (outside the timed region): the C oracle on randomly drawn label groups ----------------
+def parity_sample(torch, dist, ctx, cfg, seg, lab, counts_flat, bank_local, world, rank, sharded, dev, n_groups=32, fma_budget=1.5e12):
+    """Draws label groups of the batch this rank just scored, runs oracle/canonical.c (exhaustive canonical arithmetic,
+    whole GLOBAL bank) on them and compares with what the GPU returned: rows and order, counts, scores bit for bit.
+    Sharded bank: the shards are gathered to rank 0 first (the result is global).  Rank 0 reports."""
+    P_local, D = bank_local.shape
+    if sharded and world > 1:
+        parts = [torch.empty_like(bank_local) for _ in range(world)] if rank == 0 else None
+        dist.gather(bank_local, parts, dst=0)
+        bank = torch.cat(parts) if rank == 0 else None
+    else:
+        bank = bank_local
+    if rank != 0:
+        return None
+    from oracle import canonical
+    out = ctx.fetch()
+    goff = np.r_[0, np.cumsum(counts_flat)]
+    G = len(counts_flat)
+    P = bank.shape[0]
+    rng = np.random.default_rng(cfg["seed"] + 77)
+    order = rng.permutation(G)
+    pick, fma = [], 0.0
+    for g in order:                                    # random groups until the oracle's time budget is spent
+        c = float(counts_flat[g]) * P * D
+        if pick and fma + c > fma_budget:
+            break
+        pick.append(int(g))
+        fma += c
+        if len(pick) == n_groups:
+            break
+    pick.sort()
+    h_bank = bank.cpu().numpy()
+    segs = [seg[int(goff[g]):int(goff[g + 1])].cpu().numpy() for g in pick]
+    sgoff = np.r_[0, np.cumsum([len(x) for x in segs])].astype(np.int64)
+    t0 = time.perf_counter()
+    ref = canonical.identify(np.concatenate(segs), sgoff, h_bank, np.arange(P, dtype=np.int32), P, mode=cfg["dtype"], pool=cfg.get("pool", 0),
+                             threshold=cfg["thr"], k=cfg["k"])
+    t_or = time.perf_counter() - t0
+    ids_equal = bool(np.array_equal(out["row"][pick], ref[0]))
+    return {"groups": len(pick), "segments": int(sgoff[-1]), "bank_rows": int(P), "ids_equal": ids_equal,
+            "counts_equal": bool(np.array_equal(out["count"][pick], ref[2])),
+            "scores_bitequal": bool(np.array_equal(out["score"][pick].view(np.uint32), ref[1].view(np.uint32))),
+            "matched_groups": int((ref[2] > 0).sum()), "oracle": "oracle/canonical.c, exhaustive over the whole bank",
+            "oracle_s": round(t_or, 2), "status": "ok" if ids_equal else "MISMATCH"}
+
+
+# ---- identify workloads (cfg2, cfg3, cfg4*) ----------------------------------------------------------------------------
+def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
+    """One workload on `world` ranks: data, warm-up, timed steps, roofline, e2e, CPU baseline, sampled parity.
+    Returns the JSON line as a dict on rank 0 (None elsewhere)."""
+    from speaker_diarization_toolkit_b200 import _native
+    cfg = dict(WORKLOADS[name])
+    cfg["pool"] = 1 if args.pool == "max" else 0
+    sharded = name.startswith("cfg4")
     cfg["scaling"] = "weak" if sharded else "strong"
     cfg["P_total"] = cfg["P"] * (world if sharded else 1)
     cfg["P_cpu"] = cfg["P_total"]
     counts, truth = group_counts(cfg, args.scale)
     if sharded:
         truth = np.where(truth >= 0, truth * world, truth)        # true speakers spread over all shards
-    if args.impl == "reference":
-        return run_reference(args, cfg, counts, truth)
-    if args.workload == "cfg5":
-        return run_cfg5(args, cfg)
-
-    import torch
-    import torch.distributed as dist
-    from speaker_diarization_toolkit_b200 import _native
-
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     uid = None
     if sharded and world > 1:
         box = [_native.nccl_unique_id() if rank == 0 else None]
@@ -439,14 +462,13 @@ def main():
         cent, bank = make_bank(torch, cfg, dev, cfg["P"])
         row_off = 0
     P, D = bank.shape
-    spk = torch.arange(P, device=dev, dtype=torch.int32)
-    trust = (torch.arange(P, device=dev) % 3).to(torch.uint8)
+    spk = torch.arange(P, device=dev, dtype=torch.int32) + (row_off if sharded else 0)      # one speaker per row, global ids
+    trust = ((torch.arange(P, device=dev) + row_off) % 3).to(torch.uint8)
     ctx.bank_load_dev(bank.data_ptr(), spk.data_ptr(), trust.data_ptr(), P, D, cfg["dtype"], row_off)
     seg, lab, N, G = make_segments(torch, cfg, dev, cent, counts[r0:r1], truth[r0:r1], cfg["seed"] + (0 if sharded else 1000 + rank))
     del cent
     torch.cuda.synchronize()
     pairs_rank = float(N) * float(P)
-    pairs_total = pairs_rank * (1 if False else 1)
     if sharded:
         pairs_total = float(N) * float(P) * world          # every rank scores all queries against its shard
     else:
@@ -456,7 +478,7 @@ def main():
         pairs_total = float(t.item())
 
     def step_dev():
-        ctx.identify_dev(seg.data_ptr(), lab.data_ptr(), N, G, 0, cfg["thr"], cfg["k"])
+        ctx.identify_dev(seg.data_ptr(), lab.data_ptr(), N, G, cfg["pool"], cfg["thr"], cfg["k"])
         ctx.assign(0.3, "low")
 
     def barrier():
@@ -505,9 +527,9 @@ def main():
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on the library stream ----
     pk, pk_src = peaks()
-    names = ["plan", "normalize", "poolgemm", "merge", "exact", "select", "assign"]
+    names = ["plan", "normalize", "poolgemm", "merge", "exact", "select", "assign", "allgather", "merge_topk"]
     prof = {n: ctx.profile_get(n) for n in names}
-    tot_prof = sum(v[0] for v in prof.values()) or 1.0
+    tot_prof = sum(v[0] for n, v in prof.items() if n != "merge_topk") or 1.0     # merge_topk is nested inside allgather
     if path == 4:
         # bank-stream stage A (gemv.cu): one pass over the bf16 bank, HBM-bound; algorithmic bytes = 2*Dp per bank row
         gms, gl = prof["poolgemm"]
@@ -525,7 +547,7 @@ def main():
         ach = per_launch_flops / (avg_ms * 1e-3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         kname = "k_poolacc (tcgen05, mean pooling inside the MMA accumulation)" if path == 3 else \
-            f"k_poolgemm (tcgen05 cta_group::{args.cta_group}, pooling in the epilogue)"
+            f"k_poolgemm (tcgen05 cta_group::{args.cta_group}, {args.pool} pooling in the epilogue)"
         roof = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "peak_source": f"{pk_src} bf16 sustained (kernel timed inside a long step)",
                 "frac_of_burst_peak": ach / pk["bf16_tflops"], "algorithmic_flop_per_pair": 2 * D,
@@ -539,7 +561,26 @@ def main():
                 "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_src} copy bandwidth",
                 "avg_launch_ms": avg_ms, "share_of_step": gms / tot_prof,
                 "note": "latency-bound shape: the fraction is informational (SURVEY 8d)"}
-    roof["traffic"] = ncu_traffic(args.workload, roof["kernel"], args.scale == 1.0 and (world == 1 or sharded))
+    roof["traffic"] = ncu_traffic(name + ("_max" if cfg["pool"] else ""), roof["kernel"], args.scale == 1.0 and (world == 1 or sharded))
+    if roof["traffic"] is not None:
+        roof["traffic_source"] = "profiles/roofline_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this workload (not re-measured in this run)"
+
+    # ---- certificate: measured stage-A error of the sampled candidates is reported by the parity tests; here: the margin model ----
+    cert = None
+    if path >= 2:
+        try:
+            _, _, eb, ec = ctx.stage_a()
+            cert = {"eps_base": eb, "eps_per_chain_unit": ec, "fallback_groups": nfb, "retry_groups": nretry}
+        except Exception:
+            cert = None
+
+    # ---- sampled parity at full scale (outside every timed region) ----
+    par = None
+    if not args.no_parity:
+        step_dev()
+        barrier()
+        par = parity_sample(torch, dist, ctx, cfg, seg, lab, counts[r0:r1].reshape(-1), bank, world, rank, sharded, dev)
+        barrier()
 
     # ---- e2e: host buffers through the host-pointer C-ABI call ----
     e2e = None
@@ -562,7 +603,7 @@ def main():
         hs, hl = h_seg.numpy(), h_lab.numpy()
 
         def step_host():
-            ctx.identify(hs, hl, g_e, pool=0, threshold=cfg["thr"], k=cfg["k"])
+            ctx.identify(hs, hl, g_e, pool=cfg["pool"], threshold=cfg["thr"], k=cfg["k"])
             ctx.assign(0.3, "low")
             return ctx.fetch(with_assign=True)
 
@@ -575,7 +616,7 @@ def main():
         ctx.sync()
         te = time.perf_counter() - t0
         tt = torch.tensor([te], device=dev, dtype=torch.float64)
-        pe = torch.tensor([float(n_e) * float(P) * (world if sharded else 1) / (1 if sharded else 1)], device=dev, dtype=torch.float64)
+        pe = torch.tensor([float(n_e) * float(P) * (world if sharded else 1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             if not sharded:
@@ -588,24 +629,98 @@ def main():
 
     # ---- CPU baseline (rank 0, bounded sample) ----
     cpu = None
-    if rank == 0 and not args.no_cpu and world == 1:
+    if rank == 0 and not args.no_cpu and world == 1 and not sub:
         rate, n_rec, t = cpu_port_rate(cfg, counts, truth, 12.0)
-        cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": rate, "unit": UNIT, "cores": blas_threads(), "host_cores": os.cpu_count(), "kind": "port",
                "sample": f"{n_rec} recordings of the same workload in {t:.1f} s (NumPy/OpenBLAS sgemm + combine_signals), extrapolates linearly"}
 
+    line = None
     if rank == 0:
+        ag_ms, ag_n = prof["allgather"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
                 "dtype": "bf16" if cfg["dtype"] else "f32", "data": "synthetic",
                 "config": {"workload": cfg["desc"], "segments_total": int(pairs_total / (P * (world if sharded else 1))),
                            "segments_per_gpu": N, "label_groups_per_gpu": G, "bank_rows_per_gpu": P, "dim": D, "k": cfg["k"],
-                           "threshold": cfg["thr"], "pool": "mean", "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
+                           "threshold": cfg["thr"], "pool": args.pool, "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
                            "l2": "working set larger than 2x L2 (no flush needed)" if flush is None else "256 MB flush buffer written between timed iterations",
                            "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{args.cta_group}", 3: "tcgen05 accumulate-pooling", 4: "bank-stream gemv"}.get(path, str(path)), "certificate_fallback_groups": nfb, "certificate_retry_groups": nretry, "scale": args.scale},
                 "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+                "parity_sample": par, "certificate": cert,
+                "time_to_solution_ms": ms_max / args.steps,
                 "kernel_ms_per_step": {n: v[0] / args.steps for n, v in prof.items()}}
-        print(json.dumps(line))
+        if sharded and world > 1:
+            line["allgather_merge_us"] = 1e3 * ag_ms / max(1, ag_n)
     ctx.close()
+    del seg, lab, bank
+    torch.cuda.empty_cache()
+    return line
+
+
+def sharded_subrecord(sub):
+    """What the top-level line keeps of the row-sharded (configs[3]) run that follows the default workload."""
+    r = sub["roofline"]
+    return {"workload": sub["config"]["workload"], "value": sub["value"], "unit": UNIT, "ms_per_step": sub["ms_per_step"],
+            "n_gpus": sub["n_gpus"], "scaling": "weak", "bank_rows_total": sub["config"]["bank_rows_per_gpu"] * sub["n_gpus"],
+            "segments": sub["config"]["segments_per_gpu"], "label_groups": sub["config"]["label_groups_per_gpu"],
+            "roofline": {"kernel": r["kernel"], "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
+                         "frac": r["frac"], "avg_launch_ms": r["avg_launch_ms"], "share_of_step": r["share_of_step"], "traffic": r["traffic"],
+                         "whole_step_frac": 2.0 * sub["config"]["dim"] * sub["value"] / sub["n_gpus"] / 1e12 / r["peak"] if r["bound"] == "tensor" else None},
+            "allgather_merge_us": sub.get("allgather_merge_us"), "parity_sample": (sub["parity_sample"] or {}).get("status"),
+            "parity": sub["parity_sample"], "e2e": sub["e2e"], "clocks": sub["clocks"], "gpu_launches": sub["gpu_launches"],
+            "certificate": sub["certificate"], "path": sub["config"]["path"], "kernel_ms_per_step": sub["kernel_ms_per_step"]}
+
+
+# ---- main -----------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--pool", default="mean", choices=["mean", "max"], help="per-label pooling (north_star (3): mean/max)")
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the recordings (debug runs only; 1.0 = the named config)")
+    ap.add_argument("--cta-group", type=int, default=1, choices=[1, 2], help="tcgen05 kernel variant (2 = CTA pairs)")
+    ap.add_argument("--acc", type=int, default=1, choices=[0, 1, 2], help="accumulate-pooling kernel: 0 off, 1 auto, 2 force (A/B runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle check that follows the timed region")
+    ap.add_argument("--no-sharded", action="store_true", help="do not append the row-sharded configs[3] run to the default workload's line")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        cfg = dict(WORKLOADS[args.workload])
+        cfg["pool"] = 1 if args.pool == "max" else 0
+        sharded = args.workload.startswith("cfg4")
+        cfg["scaling"] = "weak" if sharded else "strong"
+        cfg["P_total"] = cfg["P"] * (world if sharded else 1)
+        cfg["P_cpu"] = cfg["P_total"]
+        counts, truth = group_counts(cfg, args.scale)
+        if sharded:
+            truth = np.where(truth >= 0, truth * world, truth)
+        return run_reference(args, cfg, counts, truth)
+    if args.workload == "cfg5":
+        return run_cfg5(args, dict(WORKLOADS["cfg5"]))
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = run_identify(args, args.workload, torch, dist, world, rank, local_rank)
+    # The default workload (configs[2], data-parallel, no collective) is followed by the row-sharded one (configs[3]:
+    # 125k bank rows per GPU, one ncclAllGather + merge per step) so that every driver run of `bench.py --gpus N` also
+    # measures the path north_star sets its target on.
+    if args.workload == "cfg3" and not args.no_sharded and args.scale == 1.0:
+        sub = run_identify(args, "cfg4", torch, dist, world, rank, local_rank, sub=True)
+        if rank == 0:
+            line["sharded"] = sharded_subrecord(sub)
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
