@@ -450,6 +450,7 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
     ctx.set_option("profile", 1)
     ctx.set_option("cta_group", args.cta_group)
     ctx.set_option("acc", args.acc)
+    ctx.set_option("kth", args.kth)
 
     # ---- data: bank (replicated, or this rank's row shard) + this rank's recordings ----
     R = counts.shape[0]
@@ -683,6 +684,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the recordings (debug runs only; 1.0 = the named config)")
     ap.add_argument("--cta-group", type=int, default=1, choices=[1, 2], help="tcgen05 kernel variant (2 = CTA pairs)")
     ap.add_argument("--acc", type=int, default=1, choices=[0, 1, 2], help="accumulate-pooling kernel: 0 off, 1 auto, 2 force (A/B runs)")
+    ap.add_argument("--kth", type=int, default=1, choices=[0, 1, 2], help="running k-th best pruning of the candidate flush: 0 off, 1 auto, 2 on (A/B runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle check that follows the timed region")

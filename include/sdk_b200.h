@@ -83,6 +83,7 @@ const char* sdk_last_error(sdk_ctx* ctx);
  * "chunk_mb" (host-buffer sdk_identify: size of the H2D/compute pipeline chunks, default 128),
  * "cta_group" (1 | 2: tcgen05 kernel variant), "acc" (0 off | 1 auto | 2 force: pool inside the MMA accumulation),
  * "gemv" (1 = stream the bank on the CUDA cores when there are <= 8 query segments),
+ * "kth" (0 off | 1 auto | 2 on: candidate flush prunes against a running per-label bound on the 64th best score),
  * "inject_fail" (test knob: the next local identify pass returns SDK_EINVAL after its first kernels) */
 int sdk_set_option(sdk_ctx* ctx, const char* key, double value);
 

@@ -158,7 +158,7 @@ void sdk_destroy(sdk_ctx* c) {
     sdk_buf* bufs[] = {&c->bank_f32, &c->bank_bf16, &c->row_speaker, &c->row_trust, &c->seg_raw, &c->seg_lab,
                        &c->seg_f32, &c->seg_bf16, &c->goff, &c->qpool, &c->dense, &c->flags, &c->cand_row,
                        &c->cand_val, &c->cand_cnt, &c->gbound, &c->slot_cnt, &c->slot_row, &c->slot_val,
-                       &c->slot_bound, &c->range_g, &c->fb_list, &c->fb_rows, &c->out_pack, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
+                       &c->slot_bound, &c->range_g, &c->kth, &c->fb_list, &c->fb_rows, &c->out_pack, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
                        &c->stage_lab[0], &c->stage_lab[1], &c->pa_hist, &c->pa_sorted, &c->pa_pos, &c->pa_col_group,
                        &c->pa_col_meta, &c->pa_blockT, &c->pa_step0, &c->pa_grp, &c->pa_col_last, &c->seg_il, &c->fb_list2, &c->cand_row2, &c->qpool2};
     for (sdk_buf* b : bufs) sdk_release(*b);
@@ -204,6 +204,9 @@ int sdk_set_option(sdk_ctx* c, const char* key, double value) {
     } else if (k == "chunk_mb") {
         if (value < 1 || value > 65536) return sdk_fail(c, SDK_EINVAL, "chunk_mb must be in 1..65536");
         c->opt_chunk_mb = (int)value;
+    } else if (k == "kth") {
+        if (value != 0 && value != 1 && value != 2) return sdk_fail(c, SDK_EINVAL, "kth must be 0 (off), 1 (auto) or 2 (on)");
+        c->opt_kth = (int)value;
     } else if (k == "inject_fail") {
         c->opt_inject_fail = value != 0;          // test knob: the next local identify pass fails after its first kernels
     } else return sdk_fail(c, SDK_EINVAL, "unknown option " + k);
@@ -458,6 +461,9 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         float tau = (float)(threshold - 2.0 * (double)eps);
         if (!(tau > -3.0e38f)) tau = -3.0e38f;
         SDK_TRY(sdk_reserve(c, c->cand_val, (size_t)L * ncand * 4));
+        // low / no threshold: most bank rows pass tau, so the flushes prune against a running per-label bound on the
+        // 64th best score instead of writing half the bank into the candidate slots (option "kth": 0 off, 1 auto, 2 on)
+        c->kth_on = c->opt_kth == 2 || (c->opt_kth == 1 && tau < 0.25f);
         c->last_ncand = ncand;
         c->last_cand_groups = L;
         SDK_TRY(sdk_reserve(c, c->cand_row, (size_t)L * ncand * 4));

@@ -73,6 +73,7 @@ struct sdk_ctx {
     int opt_acc = 1;           // mean pooling with many label groups: pool inside the MMA accumulation (poolacc.cu)
     int opt_gemv = 1;          // <= 8 query segments: stream the bank once on the CUDA cores (gemv.cu) instead of tcgen05 tiles
     int opt_chunk_mb = 128;    // host-buffer identify: H2D/compute pipeline chunk size
+    int opt_kth = 1;           // candidate flush prunes against a running per-label 64th-best bound: 0 off, 1 auto (low thresholds), 2 on
     int opt_inject_fail = 0;   // test knob (multi-rank error handling): fail the next local identify pass
     // bank
     int64_t P = 0;
@@ -83,6 +84,8 @@ struct sdk_ctx {
     sdk_buf seg_raw, seg_lab, seg_f32, seg_bf16, goff, qpool, dense, flags;
     sdk_buf cand_row, cand_val, cand_cnt, gbound, slot_cnt, slot_row, slot_val, slot_bound, range_g;
     sdk_buf fb_list, fb_rows, fb_list2, cand_row2, qpool2;
+    sdk_buf kth;               // running k-th best buckets of the candidate flush (tcgen05.cuh)
+    bool kth_on = false;       // set per identify call: the candidate threshold is low enough for noise rows to pass
     int32_t slot_g0 = 0, slot_g1 = 0, slot_nsub = 0;   // label groups whose candidate slots are live after stage A
     bool slot_by_col = false;  // slots are indexed by accumulator column (accumulate-pooling): group -> pa_col_last
     sdk_buf stage_seg[2], stage_lab[2];

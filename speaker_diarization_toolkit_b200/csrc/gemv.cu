@@ -42,13 +42,44 @@ static __device__ __forceinline__ void gv_flush_chunk(const GvParams& q, const f
     const PgParams& p = q.pg;
     const int64_t row = chunk * GV_ROWS + lane;
     const float* v = sc + lane * GV_NQ;
+    // running k-th best thresholds of the (at most GV_NQ) label groups: all loads are issued before the first is used --
+    // one L2 round trip per chunk instead of one per label (the flushes below then skip the per-flush lookup)
+    // (lane s keeps the threshold of query slot s; the flush loop stays rolled -- every warp runs it only a few times, so
+    //  instruction-cache footprint matters more than unrolling)
+    uint32_t thr_mine = 0u;
+    if (p.kth) {
+        uint32_t ka[GV_NQ], kb[GV_NQ];
+#pragma unroll
+        for (int s = 0; s < GV_NQ; ++s) {
+            const int g = s < q.N ? s_grp[s] : -1;
+            const uint32_t* kp = p.kth + (int64_t)(g < 0 ? 0 : g - p.g_base) * PG_KTH;
+            ka[s] = g >= 0 ? __ldcg(kp + lane) : 0u;
+            kb[s] = g >= 0 ? __ldcg(kp + lane + 32) : 0u;
+        }
+#pragma unroll
+        for (int s = 0; s < GV_NQ; ++s) {
+            const uint32_t t = __reduce_min_sync(0xffffffffu, ka[s] < kb[s] ? ka[s] : kb[s]);
+            thr_mine = lane == s ? t : thr_mine;
+        }
+    }
     float a = p.pool == 0 ? 0.f : -3.0e38f;
 #pragma unroll 1
     for (int s = 0; s < q.N; ++s) {
         a = p.pool == 0 ? a + v[s] : fmaxf(a, v[s]);
         const int g = s_grp[s];
         if (s + 1 == q.N || s_grp[s + 1] != g) {
-            pg_flush(p, a, g, s_len[s], (int64_t)(g - p.g_base) * q.nsub + chunk, lane, row);
+            const float val = p.pool == 0 ? a * (1.0f / (float)s_len[s]) : a;
+            const int64_t sg = g - p.g_base, sub = sg * p.nsub + chunk;
+            bool pass = (val >= p.tau) && (row < p.P);
+            if (p.kth) {
+                const uint32_t thr = __shfl_sync(0xffffffffu, thr_mine, s);
+                const uint32_t key = sdk_fkey(val);
+                pg_kth_update(p, sg, chunk, pass ? key : 0u, thr, lane);
+                pass = pass && key >= thr;
+            }
+            const uint32_t mpass = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0 && mpass == 0) p.slot_cnt[sub] = 0;
+            if (mpass != 0) pg_flush_write(p, val, pass, mpass, sub, lane, row);
             a = p.pool == 0 ? 0.f : -3.0e38f;
         }
     }
@@ -209,6 +240,15 @@ int sdk_launch_gemv_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int64_t 
     q.pg.slot_bound = (float*)c->slot_bound.p;
     q.pg.dense_out = nullptr;
     q.pg.dense_ld = 0;
+    q.pg.nsub = nsub;
+    q.pg.kth = nullptr;
+    // (with <= 8 queries the slot volume is small and the per-chunk bucket lookups cost more than they save -- measured
+    //  46.1 vs 43.6 us on config 4-i -- so the pruning is only taken when forced: option kth = 2)
+    if (c->kth_on && c->opt_kth == 2) {
+        SDK_TRY(sdk_reserve(c, c->kth, (size_t)G * PG_KTH * 4));
+        SDK_CUDA(c, cudaMemsetAsync(c->kth.p, 0, (size_t)G * PG_KTH * 4, c->stream));
+        q.pg.kth = (uint32_t*)c->kth.p;
+    }
     q.N = (int32_t)N;
     q.G = G;
     q.Dp = Dp;

@@ -692,10 +692,16 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
                         if (row < p.P) p.dense_out[row * (int64_t)p.dense_ld + g] = val;
                         continue;
                     }
-                    const bool pass = (val >= p.tau) && (row < p.P);
+                    bool pass = (val >= p.tau) && (row < p.P);
+                    const int64_t pos = (int64_t)b * NC + blk * 32 + cc - p.g_base;   // column inside the batch
+                    if (p.kth) {                                                      // running k-th best (low thresholds only)
+                        const uint32_t thr = pg_kth_load(p, pos, lane);
+                        const uint32_t key = sdk_fkey(val);
+                        pg_kth_update(p, pos, tile128 * 4 + wq, pass ? key : 0u, thr, lane);
+                        pass = pass && key >= thr;
+                    }
                     const uint32_t mpass = __ballot_sync(0xffffffffu, pass);
                     if (mpass == 0) continue;                                         // slot counts were zeroed before the launch
-                    const int64_t pos = (int64_t)b * NC + blk * 32 + cc - p.g_base;   // column inside the batch
                     pg_flush_write_call(&p, val, pass, mpass, pos * nsub + tile128 * 4 + wq, lane, row);
                 }
             }
@@ -898,6 +904,13 @@ int sdk_launch_poolacc(sdk_ctx* c, const float* d_seg_raw, const int32_t* d_seg_
         q.pg.slot_bound = (float*)c->slot_bound.p;
         q.pg.dense_out = d_dense;
         q.pg.dense_ld = G;
+        q.pg.nsub = nsub;
+        q.pg.kth = nullptr;
+        if (mode == 0 && c->kth_on) {
+            SDK_TRY(sdk_reserve(c, c->kth, (size_t)bbatch * PA_NB * PG_KTH * 4));
+            SDK_CUDA(c, cudaMemsetAsync(c->kth.p, 0, (size_t)(bb - ba) * PA_NB * PG_KTH * 4, c->stream));
+            q.pg.kth = (uint32_t*)c->kth.p;
+        }
         q.col_meta = col_meta;
         q.blockT = (const int32_t*)c->pa_blockT.p;
         q.step0 = step0;

@@ -23,6 +23,8 @@
 // picks the top `ncand` rows per label and the upper bound on every row left out; select.cu re-scores the
 // candidates canonically and checks the bound (the top-k certificate).
 // Flush (dense mode, config 5): out[row, g] = pooled value.
+#include <stdlib.h>
+
 #include "tcgen05.cuh"
 
 // ---- epilogue of one job: pool NC accumulator columns of this thread's bank row -------------------
@@ -45,39 +47,49 @@ __device__ __forceinline__ void pg_pool_init(PgPool& st, const PgParams& p, int3
     st.acc = p.pool == 0 ? 0.f : -3.0e38f;
 }
 
+// Reductions of one 32-column block as balanced trees (depth 5): one epilogue warp sits alone on its scheduler, so a
+// serial 32-long fmax / fadd chain is pure latency (4 cycles a link, ~130 cycles per block -- it made max pooling
+// epilogue-bound at D <= 256); the trees expose 16 independent operations per level instead.
+__device__ __forceinline__ float pg_tree_sum(const float (&w)[32]) {
+    float s[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = (w[4 * q] + w[4 * q + 1]) + (w[4 * q + 2] + w[4 * q + 3]);
+    return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+__device__ __forceinline__ float pg_tree_max(const float (&w)[32]) {
+    float s[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = fmaxf(fmaxf(w[4 * q], w[4 * q + 1]), fmaxf(w[4 * q + 2], w[4 * q + 3]));
+    return fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), fmaxf(fmaxf(s[4], s[5]), fmaxf(s[6], s[7])));
+}
+
 __device__ __forceinline__ void pg_pool_block(PgPool& st, const PgParams& p, const float (&v)[32], int64_t cbase, int64_t c1,
                                               int32_t g_hi, int64_t sub_stride_base, int64_t subbase, int32_t lane, int64_t row) {
     const int64_t left = c1 - cbase;
     const int nvalid = left < 32 ? (int)left : 32;
     if (nvalid == 32 && st.gend > cbase + 32) {
         // whole block inside the current label group
-        if (p.pool == 0) {
-            float s[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) s[q] = (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
-            st.acc += ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-        } else {
-            float m = st.acc;
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc) m = fmaxf(m, v[cc]);
-            st.acc = m;
-        }
+        if (p.pool == 0) st.acc += pg_tree_sum(v);
+        else st.acc = fmaxf(st.acc, pg_tree_max(v));
         return;
     }
     int c = 0;
     while (c < nvalid) {
         const int64_t togo = st.gend - cbase;
         const int run_end = togo < nvalid ? (int)togo : nvalid;
+        // columns [c, run_end) of the block belong to the current group: mask, then the same trees
+        float w[32];
+        const unsigned span = (unsigned)(run_end - c);
 #pragma unroll
         for (int cc = 0; cc < 32; ++cc) {
-            const bool on = cc >= c && cc < run_end;
-            if (p.pool == 0) st.acc += on ? v[cc] : 0.f;
-            else st.acc = on ? fmaxf(st.acc, v[cc]) : st.acc;
+            const bool on = (unsigned)(cc - c) < span;
+            w[cc] = on ? v[cc] : (p.pool == 0 ? 0.f : -3.0e38f);
         }
+        if (p.pool == 0) st.acc += pg_tree_sum(w);
+        else st.acc = fmaxf(st.acc, pg_tree_max(w));
         c = run_end;
         if (cbase + run_end == st.gend) {
-            const int64_t sub = (int64_t)(st.g - p.g_base) * sub_stride_base + subbase;
-            pg_flush(p, st.acc, st.g, st.gend - st.gbeg, sub, lane, row);
+            pg_flush(p, st.acc, st.g, st.gend - st.gbeg, (int64_t)(st.g - p.g_base), subbase, lane, row);
             st.acc = p.pool == 0 ? 0.f : -3.0e38f;
             st.gbeg = st.gend;
             if (st.g + 1 < g_hi) {
@@ -719,8 +731,19 @@ void pg_launch_merge(sdk_ctx* c, const int64_t* d_goff, int32_t g_base, int32_t 
 
 struct pg_cfg { int KCH, MT, NC, STAGES; };
 // (KCH, MT, NC, STAGES) per padded dimension; shared memory = MT*KCH*16 KB (bank tiles) + STAGES*NC*128 B (ring)
+// D <= 192: four 128-column accumulator slots (two per row tile) instead of two 256-column ones.  With one slot per row
+// tile the MMAs of chunk j+1 wait for the complete read-out of chunk j, and the read-out runs at the TMEM -> register rate
+// (~51-64 B/clk/SM measured: 128 KB per job pair = ~2 000-2 500 cycles against 1 536 MMA cycles at D = 192), so the
+// pipe idled a third of the time; with two slots per row tile the kernel runs at the read-out rate (config 3 with max
+// pooling: 67.1 -> 64.0 ms; generic mean: 68.0 -> 64.4 ms).  SDK_PG_NC=256 restores the wide slots (A/B runs).
+static bool pg_nc128() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SDK_PG_NC"); v = (e && atoi(e) == 256) ? 0 : 1; }
+    return v == 1;
+}
 static pg_cfg pg_config_for(int32_t Dp) {
     int kch = Dp / 64;
+    if (pg_nc128() && kch <= 3) return {kch, 2, 128, 6};
     switch (kch) {
         case 1: return {1, 2, 256, 6};
         case 2: return {2, 2, 256, 5};
@@ -748,6 +771,13 @@ static int pg_launch_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb,
 }
 
 static int pg_launch(sdk_ctx* c, const pg_cfg& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const PgParams& p, int grid) {
+    if (cfg.NC == 128 && cfg.KCH <= 3) {
+        switch (cfg.KCH) {
+            case 1: return pg_launch_t<1, 2, 128, 6>(c, ta, tb, p, grid);
+            case 2: return pg_launch_t<2, 2, 128, 6>(c, ta, tb, p, grid);
+            default: return pg_launch_t<3, 2, 128, 6>(c, ta, tb, p, grid);
+        }
+    }
     switch (cfg.KCH) {
         case 1: return pg_launch_t<1, 2, 256, 6>(c, ta, tb, p, grid);
         case 2: return pg_launch_t<2, 2, 256, 5>(c, ta, tb, p, grid);
@@ -876,6 +906,13 @@ static int pg_run(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P, const __nv
             p.slot_bound = (float*)c->slot_bound.p;
             p.dense_out = d_dense;
             p.dense_ld = G;
+            p.nsub = nsub;
+            p.kth = nullptr;
+            if (mode == 0 && c->kth_on) {
+                SDK_TRY(sdk_reserve(c, c->kth, (size_t)gbatch * PG_KTH * 4));
+                SDK_CUDA(c, cudaMemsetAsync(c->kth.p, 0, (size_t)(gb - ga) * PG_KTH * 4, c->stream));
+                p.kth = (uint32_t*)c->kth.p;
+            }
             const int64_t n_units = (int64_t)n_ranges * RB;
             {
                 sdk_prof_scope ps(c, "poolgemm");

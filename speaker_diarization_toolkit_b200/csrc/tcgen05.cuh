@@ -25,7 +25,14 @@ struct PgParams {
     float* slot_bound;
     float* dense_out;
     int32_t dense_ld;
+    // Running per-label lower bound on the 64th best stage-A score (un-thresholded / low-threshold queries): 64 buckets
+    // per slot group, bucket b = max key flushed so far by the sub-slots with index % 64 == b.  The 64 bucket maxima are
+    // 64 different bank rows, so their minimum can only be <= the 64th best score of the label: rows below it can never
+    // be among the (at most 64) candidates and are not written at all.  null = off.
+    uint32_t* kth;
+    int64_t nsub;               // sub-slots per slot group
 };
+#define PG_KTH 64
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,14 +150,33 @@ static __device__ __noinline__ void pg_flush_write_call(const PgParams* p, float
     pg_flush_write(*p, val, pass, mpass, sub, lane, row);
 }
 
-__device__ __forceinline__ void pg_flush(const PgParams& p, float accv, int32_t g, int64_t n_g, int64_t sub, int32_t lane,
+// running k-th best: threshold key of slot group sg (0 = nothing known yet)
+__device__ __forceinline__ uint32_t pg_kth_load(const PgParams& p, int64_t sg, int32_t lane) {
+    const uint32_t* kb = p.kth + sg * PG_KTH;
+    const uint32_t a = __ldcg(kb + lane), b = __ldcg(kb + lane + 32);     // L2: other SMs raise the buckets with atomics
+    return __reduce_min_sync(0xffffffffu, a < b ? a : b);
+}
+__device__ __forceinline__ void pg_kth_update(const PgParams& p, int64_t sg, int64_t si, uint32_t key_if_live, uint32_t thr, int32_t lane) {
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, key_if_live);
+    if (lane == 0 && wmax > thr) atomicMax(p.kth + sg * PG_KTH + (si & (PG_KTH - 1)), wmax);
+}
+
+// sg = slot group (label group or accumulator column, batch-relative), si = sub-slot inside the group
+__device__ __forceinline__ void pg_flush(const PgParams& p, float accv, int32_t g, int64_t n_g, int64_t sg, int64_t si, int32_t lane,
                                          int64_t row) {
     const float val = p.pool == 0 ? accv * (1.0f / (float)n_g) : accv;
     if (p.mode == 1) {
         if (row < p.P) p.dense_out[row * (int64_t)p.dense_ld + g] = val;
         return;
     }
-    const bool pass = (val >= p.tau) && (row < p.P);
+    const int64_t sub = sg * p.nsub + si;
+    bool pass = (val >= p.tau) && (row < p.P);
+    if (p.kth) {
+        const uint32_t thr = pg_kth_load(p, sg, lane);
+        const uint32_t key = sdk_fkey(val);
+        pg_kth_update(p, sg, si, pass ? key : 0u, thr, lane);
+        pass = pass && key >= thr;
+    }
     const uint32_t mpass = __ballot_sync(0xffffffffu, pass);
     if (lane == 0 && mpass == 0) p.slot_cnt[sub] = 0;
     if (mpass == 0) return;
