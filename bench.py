@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- scored segment x profile pairs / second on N B200s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg2|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg1|cfg2|cfg4|cfg4i|cfg4ii|cfg5] [--pool mean|max]
 
 Default workload = BASELINE.json configs[2] ("cfg3": batch of 10k recordings, ~20M segments, vs a 10k-profile
 bank, 192-d, bf16 operands) -- the configuration the metric "pairs/sec at 1/2/4/8 B200" is quoted on; it fits one
@@ -49,6 +49,8 @@ METRIC = "scored segment x profile pairs per second"
 UNIT = "pairs/s"
 
 WORKLOADS = {
+    "cfg1": dict(R=1, seg=40, labels=2, P=3, D=192, dtype=0, k=3, thr=0.354, seed=101,
+                 desc="configs[0]: speaker-assign CLI, 2 labels / 40 segments vs 3 enrolled profiles, 192-d fp32 (process-spawn bound)"),
     # name: recordings, segments/recording (Poisson mean), labels/recording, bank rows, D, dtype, k, threshold
     "cfg3": dict(R=10000, seg=2000, labels=8, P=10000, D=192, dtype=1, k=4, thr=0.354, seed=303,
                  desc="configs[2]: 10k recordings (~20M segments) vs 10k-profile bank, 192-d, bf16 operands, DP over recordings"),
@@ -138,6 +140,43 @@ def make_segments(torch, cfg, dev, cent, counts, truth, seed):
         x = x / x.norm(dim=1, keepdim=True) * (0.5 + 19.5 * torch.rand((b - a, 1), generator=g, device=dev))
         seg[a:b] = x
     return seg, lab, N, G
+
+
+# ---- NUMA placement of the pinned host buffers ---------------------------------------------------------------------
+_ALL_CPUS = None
+
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pinned host memory is placed by first touch: bind this process to the CPUs of the NUMA node its GPU hangs off
+    before allocating, so that with 8 ranks the H2D streams read from both sockets' memory instead of one.
+    Returns the node (None when sysfs does not say)."""
+    global _ALL_CPUS
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if _ALL_CPUS is None:
+            _ALL_CPUS = os.sched_getaffinity(0)
+        cpus &= _ALL_CPUS
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def unbind_cpus():
+    if _ALL_CPUS:
+        try:
+            os.sched_setaffinity(0, _ALL_CPUS)
+        except Exception:
+            pass
 
 
 # ---- clocks sampler ------------------------------------------------------------------------------
@@ -380,8 +419,126 @@ def run_cfg5(args, cfg):
     return 0
 
 
+# ---- config 1: the product-level entry, through the real CLIs (process spawn is the reference's true cost here) ----
+def run_cfg1(args):
+    """BASELINE.json configs[0]: `speaker-assign assign AUDIO -t TRANSCRIPT --use-embeddings` on one synthetic
+    Speechmatics-format transcript (2 labels, 40 segments) vs 3 enrolled profiles, 192-d ("cfg 1 timed through
+    the actual CLI ... because the reference's real cost there is process spawn", speaker-assign:283-294).
+      value  the in-process hot path on device-resident inputs (sdk_identify_dev + sdk_assign, CUDA events)
+      e2e    wall time of the whole `bin/speaker-assign` process (interpreter start, CUDA context, store + sidecar reads,
+             the backend plugin, H2D / D2H, JSON out), one process per step as the reference CLI does it
+    The reference's own CLI chain cannot run on this box (/root/reference does not travel), and the chain spawns one
+    `speaker_detection identify` process PER LABEL (speaker-assign:545-563) where this build makes one in-process call."""
+    import tempfile
+    import torch
+    from oracle import canonical, matching_np as mnp
+    from speaker_diarization_toolkit_b200 import _native, synth
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    case = synth.config1()
+    N, P, D, L, k = case.seg.shape[0], case.bank.shape[0], case.seg.shape[1], case.G, 3
+    pairs = float(N) * P
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    ctx = _native.Context(0)
+    ctx.set_option("profile", 1)
+    ctx.bank_load(case.bank, case.row_speaker, case.row_trust, dtype=_native.DTYPE_F32)
+    seg = torch.from_numpy(case.seg).to(dev)
+    lab = torch.from_numpy(case.seg_label.astype(np.int32)).to(dev)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    clocks = Clocks(0)
+    clocks.start()
+    for _ in range(max(3, args.warmup)):
+        ctx.identify_dev(seg.data_ptr(), lab.data_ptr(), N, L, 0, 0.354, k)
+        ctx.assign(0.3, "low")
+    ctx.sync()
+    ctx.profile_reset()
+    l0 = ctx.launch_count()
+    clocks.mark_begin()
+    steps = max(args.steps, 20)
+    ms = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        ctx.identify_dev(seg.data_ptr(), lab.data_ptr(), N, L, 0, 0.354, k)
+        ctx.assign(0.3, "low")
+        ms += ctx.timer_stop()
+    clk = clocks.stop()
+    launches = ctx.launch_count() - l0
+    out = ctx.fetch(with_assign=True)
+    ref = canonical.identify(case.seg, case.goff, case.bank, case.row_speaker, case.n_speakers, mode=0, pool=0, threshold=0.354, k=k)
+    a = canonical.assign(out["row"], out["score"], out["trust"], out["count"], 0.3, 2)
+    parity = {"ids_equal": bool(np.array_equal(out["row"], ref[0])), "counts_equal": bool(np.array_equal(out["count"], ref[2])),
+              "scores_bitequal": bool(np.array_equal(out["score"].view(np.uint32), ref[1].view(np.uint32))),
+              "assignment_equal": bool(np.array_equal(out["assign_idx"], a[0]) and np.array_equal(out["assign_score"], a[1])),
+              "oracle": "oracle/canonical.c (identify + the combine_signals restatement)"}
+    gms, gl = ctx.profile_get("exact")
+    pk, pk_src = peaks()
+    avg_ms = gms / max(1, gl)
+    roof = {"kernel": "k_exact_dense (fp64 SIMT, canonical arithmetic)", "bound": "hbm", "achieved": (N * D + P * D) * 4 / (avg_ms * 1e-3) / 1e9,
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": (N * D + P * D) * 4 / (avg_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+            "avg_launch_ms": avg_ms, "note": "33 KB of data: launch-latency bound, the fraction is informational (SURVEY 8d)"}
+    ctx.close()
+    # ---- through the real CLI, one process per step ----
+    with tempfile.TemporaryDirectory(prefix="cfg1-") as td:
+        audio, tpath, ids = synth.write_store(case, td, ["S1", "S2"], speaker_names=["alice", "bob", "carol"])
+        env = dict(os.environ, SPEAKERS_EMBEDDINGS_DIR=td, SPEAKER_DETECTION_BACKEND="b200", PYTHONPATH=str(ROOT))
+        env.pop("SPEAKER_BACKENDS_CONFIG", None)
+        cmd = [sys.executable, str(ROOT / "bin" / "speaker-assign"), "-q", "assign", str(audio), "-t", str(tpath), "-e", "-n", "--format", "json",
+               "--threshold", "0.2"]
+        subprocess.run(cmd, env=env, capture_output=True, text=True)                      # warm-up (page cache, cubin load)
+        e_steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        t_cli = (time.perf_counter() - t0) / e_steps
+        got = json.loads(r.stdout[r.stdout.index("{"):]) if r.returncode == 0 else {}
+        mapping = {l: m.get("speaker_id") for l, m in got.get("mappings", {}).items()}
+        trust = ["high", "medium", "low"]
+        want = {}
+        for g, label in enumerate(["S1", "S2"]):
+            sigs = [mnp.Signal("embedding_match", ids[case.row_speaker[int(ref[0][g, i])]], float(ref[1][g, i]),
+                               {"trust_level": trust[case.row_trust[int(ref[0][g, i])]]}) for i in range(ref[2][g])]
+            want[label] = mnp.combine_signals(label, sigs, threshold=0.2)["speaker_id"]
+        parity["cli_mapping"] = mapping
+        parity["cli_mapping_equal"] = mapping == want
+        # time of an empty interpreter + package import, for scale
+        t0 = time.perf_counter()
+        subprocess.run([sys.executable, "-c", "import numpy"], env=env, capture_output=True)
+        t_py = time.perf_counter() - t0
+    parity["status"] = "ok" if all(v for k_, v in parity.items() if k_.endswith("equal")) else "MISMATCH"
+    cpu = None
+    if not args.no_cpu:
+        goff = case.goff
+        t0 = time.perf_counter()
+        reps = 200
+        for _ in range(reps):
+            rows, scores, cnt = mnp.identify(case.seg, goff, case.bank, case.row_speaker, mode=0, pool=0, threshold=0.354, k=k)
+            for g in range(L):
+                mnp.combine_signals(f"S{g}", [mnp.Signal("embedding_match", str(int(rows[g, i])), float(scores[g, i]), {"trust_level": "high"})
+                                              for i in range(cnt[g])], threshold=0.3)
+        tc = (time.perf_counter() - t0) / reps
+        cpu = {"value": pairs / tc, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+               "sample": f"the bare NumPy call, {reps} repetitions ({tc * 1e6:.0f} us each); the reference's CLI chain adds one process per label on top"}
+    print(json.dumps({"metric": METRIC, "value": pairs * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup),
+                      "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic",
+                      "config": {"workload": "configs[0]: speaker-assign on one synthetic Speechmatics-format transcript (2 labels, 40 segments) vs 3 enrolled profiles, 192-d",
+                                 "segments": N, "labels": L, "bank_rows": P, "dim": D, "k": k, "l2": "256 MB flush buffer written between timed iterations",
+                                 "path": "exact-simt"},
+                      "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+                      "e2e": {"value": pairs / t_cli, "unit": UNIT, "h2d_bytes_per_step": int(case.seg.nbytes + case.seg_label.nbytes // 2 + case.bank.nbytes),
+                              "d2h_bytes_per_step": int(L * (k * 13 + 4)), "steps": e_steps, "seconds_per_cli_run": t_cli,
+                              "python_numpy_import_s": t_py,
+                              "sample": "one `bin/speaker-assign assign -e` PROCESS per step: interpreter start + CUDA context + store/sidecar reads + plugin + kernels + JSON"},
+                      "parity_sample": parity, "time_to_solution_ms": ms / steps}))
+    return 0
+
+
 # ---- sampled full-scale parity (outside the timed region): the C oracle on randomly drawn label groups ----------------
-def parity_sample(torch, dist, ctx, cfg, seg, lab, counts_flat, bank_local, world, rank, sharded, dev, n_groups=32, fma_budget=1.5e12):
+def parity_sample(torch, dist, ctx, cfg, seg, lab, counts_flat, bank_local, world, rank, sharded, dev, n_groups=32, fma_budget=1.5e12,
+                  as_f16=False):
     """Draws label groups of the batch this rank just scored, runs oracle/canonical.c (exhaustive canonical arithmetic,
     whole GLOBAL bank) on them and compares with what the GPU returned: rows and order, counts, scores bit for bit.
     Sharded bank: the shards are gathered to rank 0 first (the result is global).  Rank 0 reports."""
@@ -412,7 +569,10 @@ def parity_sample(torch, dist, ctx, cfg, seg, lab, counts_flat, bank_local, worl
             break
     pick.sort()
     h_bank = bank.cpu().numpy()
-    segs = [seg[int(goff[g]):int(goff[g + 1])].cpu().numpy() for g in pick]
+    if as_f16:      # what the fp16 host path scored: the embeddings rounded to fp16, widened back exactly
+        segs = [seg[int(goff[g]):int(goff[g + 1])].to(torch.float16).float().cpu().numpy() for g in pick]
+    else:
+        segs = [seg[int(goff[g]):int(goff[g + 1])].cpu().numpy() for g in pick]
     sgoff = np.r_[0, np.cumsum([len(x) for x in segs])].astype(np.int64)
     t0 = time.perf_counter()
     ref = canonical.identify(np.concatenate(segs), sgoff, h_bank, np.arange(P, dtype=np.int32), P, mode=cfg["dtype"], pool=cfg.get("pool", 0),
@@ -584,49 +744,77 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
         barrier()
 
     # ---- e2e: host buffers through the host-pointer C-ABI call ----
-    e2e = None
+    # Headline e2e: the segment embeddings sit in pinned host memory in the sidecar's compact fp16 form
+    # (store.save_segment_embeddings(dtype=float16); sdk_identify_f16 widens them exactly on the device), so a step moves
+    # 2*D bytes per segment over PCIe; `e2e_f32` is the same call on fp32 host embeddings (4*D bytes per segment).
+    # Each rank's pinned buffers are allocated while the process is bound to the CPUs of ITS GPU's NUMA node.
+    e2e, e2e_f32, par_e2e = None, None, None
     if not args.no_e2e:
         import psutil
-        need = N * D * 4
-        frac = 1.0
-        avail = psutil.virtual_memory().available
-        if need * 3 > avail:
-            frac = max(0.05, avail / (need * 3.0))
-        n_e = int(N * frac)
-        if frac < 1.0:                                     # cut at a label-group boundary
-            n_e = int((lab[:n_e] != lab[n_e - 1]).sum().item())
-        g_e = int(lab[n_e - 1].item()) + 1 if n_e else 0
-        h_seg = torch.empty((n_e, D), dtype=torch.float32, pin_memory=True)
-        h_lab = torch.empty((n_e,), dtype=torch.int32, pin_memory=True)
-        h_seg.copy_(seg[:n_e])
-        h_lab.copy_(lab[:n_e])
-        torch.cuda.synchronize()
-        hs, hl = h_seg.numpy(), h_lab.numpy()
+        numa = bind_to_gpu_numa_node(torch, local_rank)
 
-        def step_host():
-            ctx.identify(hs, hl, g_e, pool=cfg["pool"], threshold=cfg["thr"], k=cfg["k"])
-            ctx.assign(0.3, "low")
-            return ctx.fetch(with_assign=True)
+        def e2e_leg(f16):
+            esz = 2 if f16 else 4
+            need = N * D * esz
+            frac = 1.0
+            avail = psutil.virtual_memory().available
+            if need * 3 > avail:
+                frac = max(0.05, avail / (need * 3.0))
+            n_e = int(N * frac)
+            if frac < 1.0:                                     # cut at a label-group boundary
+                n_e = int((lab[:n_e] != lab[n_e - 1]).sum().item())
+            g_e = int(lab[n_e - 1].item()) + 1 if n_e else 0
+            h_seg = torch.empty((n_e, D), dtype=torch.float16 if f16 else torch.float32, pin_memory=True)
+            h_lab = torch.empty((n_e,), dtype=torch.int32, pin_memory=True)
+            step_rows = 1 << 21
+            for a in range(0, n_e, step_rows):                 # converted slice by slice: no second full-size device copy
+                b = min(n_e, a + step_rows)
+                h_seg[a:b].copy_(seg[a:b].to(h_seg.dtype) if f16 else seg[a:b])
+            h_lab.copy_(lab[:n_e])
+            torch.cuda.synchronize()
+            hs, hl = h_seg.numpy(), h_lab.numpy()
 
-        step_host()
-        barrier()
-        e_steps = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
+            def step_host():
+                ctx.identify(hs, hl, g_e, pool=cfg["pool"], threshold=cfg["thr"], k=cfg["k"])
+                ctx.assign(0.3, "low")
+                return ctx.fetch(with_assign=True)
+
             step_host()
-        ctx.sync()
-        te = time.perf_counter() - t0
-        tt = torch.tensor([te], device=dev, dtype=torch.float64)
-        pe = torch.tensor([float(n_e) * float(P) * (world if sharded else 1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            if not sharded:
-                dist.all_reduce(pe)
-        k = cfg["k"]
-        e2e = {"value": float(pe.item()) * e_steps / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(n_e * D * 4 + n_e * 4), "d2h_bytes_per_step": int(g_e * (k * 13 + 4 + 4 + 8 + 4 + 12 + 24)),
-               "steps": e_steps, "sample": "whole batch" if frac == 1.0 else f"first {frac:.2f} of the rank's batch (host memory bound)"}
-        del h_seg, h_lab
+            barrier()
+            e_steps = max(1, min(args.steps, 3))
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                step_host()
+            ctx.sync()
+            te = time.perf_counter() - t0
+            tt = torch.tensor([te], device=dev, dtype=torch.float64)
+            pe = torch.tensor([float(n_e) * float(P) * (world if sharded else 1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                if not sharded:
+                    dist.all_reduce(pe)
+            k = cfg["k"]
+            rec = {"value": float(pe.item()) * e_steps / float(tt.item()), "unit": UNIT,
+                   "h2d_bytes_per_step": int(n_e * D * esz + n_e * 4), "d2h_bytes_per_step": int(g_e * (k * 13 + 4 + 4 + 8 + 4 + 12 + 24)),
+                   "steps": e_steps, "sample": "whole batch" if frac == 1.0 else f"first {frac:.2f} of the rank's batch (host memory bound)",
+                   "input": ("fp16 segment embeddings in pinned host memory (compact sidecar form, widened exactly on the device)" if f16
+                             else "fp32 segment embeddings in pinned host memory"),
+                   "h2d_gbs_per_rank": (n_e * D * esz + n_e * 4) * e_steps / float(tt.item()) / 1e9, "numa_node_of_gpu": numa}
+            par = None
+            if f16 and not args.no_parity:
+                # the results of the last fp16 host step against the oracle on the widened fp16 values
+                par = parity_sample(torch, dist, ctx, cfg, seg[:n_e], lab[:n_e], counts[r0:r1].reshape(-1)[:g_e], bank, world, rank, sharded, dev,
+                                    n_groups=16, as_f16=True)
+            del h_seg, h_lab, hs, hl
+            return rec, par
+
+        if args.e2e_dtype in ("f16", "both"):
+            e2e, par_e2e = e2e_leg(True)
+        if args.e2e_dtype in ("f32", "both"):
+            e2e_f32, _ = e2e_leg(False)
+            if e2e is None:
+                e2e, e2e_f32 = e2e_f32, None
+        unbind_cpus()
 
     # ---- CPU baseline (rank 0, bounded sample) ----
     cpu = None
@@ -646,8 +834,8 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
                            "threshold": cfg["thr"], "pool": args.pool, "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
                            "l2": "working set larger than 2x L2 (no flush needed)" if flush is None else "256 MB flush buffer written between timed iterations",
                            "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{args.cta_group}", 3: "tcgen05 accumulate-pooling", 4: "bank-stream gemv"}.get(path, str(path)), "certificate_fallback_groups": nfb, "certificate_retry_groups": nretry, "scale": args.scale},
-                "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
-                "parity_sample": par, "certificate": cert,
+                "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_f32": e2e_f32,
+                "parity_sample": par, "parity_sample_e2e": par_e2e, "certificate": cert,
                 "time_to_solution_ms": ms_max / args.steps,
                 "kernel_ms_per_step": {n: v[0] / args.steps for n, v in prof.items()}}
         if sharded and world > 1:
@@ -668,7 +856,7 @@ def sharded_subrecord(sub):
                          "frac": r["frac"], "avg_launch_ms": r["avg_launch_ms"], "share_of_step": r["share_of_step"], "traffic": r["traffic"],
                          "whole_step_frac": 2.0 * sub["config"]["dim"] * sub["value"] / sub["n_gpus"] / 1e12 / r["peak"] if r["bound"] == "tensor" else None},
             "allgather_merge_us": sub.get("allgather_merge_us"), "parity_sample": (sub["parity_sample"] or {}).get("status"),
-            "parity": sub["parity_sample"], "e2e": sub["e2e"], "clocks": sub["clocks"], "gpu_launches": sub["gpu_launches"],
+            "parity": sub["parity_sample"], "e2e": sub["e2e"], "e2e_f32": sub.get("e2e_f32"), "clocks": sub["clocks"], "gpu_launches": sub["gpu_launches"],
             "certificate": sub["certificate"], "path": sub["config"]["path"], "kernel_ms_per_step": sub["kernel_ms_per_step"]}
 
 
@@ -686,6 +874,8 @@ def main():
     ap.add_argument("--acc", type=int, default=1, choices=[0, 1, 2], help="accumulate-pooling kernel: 0 off, 1 auto, 2 force (A/B runs)")
     ap.add_argument("--kth", type=int, default=1, choices=[0, 1, 2], help="running k-th best pruning of the candidate flush: 0 off, 1 auto, 2 on (A/B runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-dtype", default="both", choices=["f16", "f32", "both"],
+                    help="storage type of the host segment embeddings in the e2e leg (f16 = compact sidecar form, the headline; both = also e2e_f32)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle check that follows the timed region")
     ap.add_argument("--no-sharded", action="store_true", help="do not append the row-sharded configs[3] run to the default workload's line")
@@ -706,6 +896,8 @@ def main():
         return run_reference(args, cfg, counts, truth)
     if args.workload == "cfg5":
         return run_cfg5(args, dict(WORKLOADS["cfg5"]))
+    if args.workload == "cfg1":
+        return run_cfg1(args)
 
     import torch
     import torch.distributed as dist

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SDK_ABI_VERSION 2
+#define SDK_ABI_VERSION 3
 
 /* error codes */
 #define SDK_OK 0
@@ -121,6 +121,16 @@ int sdk_identify(sdk_ctx* ctx, const float* seg, const int32_t* seg_label, int64
  * SDK_EPEER from sdk_results_fetch. */
 int sdk_identify_dev(sdk_ctx* ctx, const float* d_seg, const int32_t* d_seg_label, int64_t N,
                      int32_t L, int32_t pool, double threshold, int32_t k);
+
+/* Raw per-segment embeddings stored as IEEE fp16 (the sidecar's compact form; SURVEY 8b leaves the sidecar format to
+ * the build).  Every element is widened to fp32 -- exactly -- before the canonical normalise, so the result equals
+ * sdk_identify on the widened matrix bit for bit; host->device traffic halves.  The 64-bit load paths need d_seg
+ * 8-byte aligned and D % 4 == 0 (otherwise the scalar kernel runs). */
+int sdk_identify_f16(sdk_ctx* ctx, const uint16_t* seg, const int32_t* seg_label, int64_t N, int32_t L,
+                     int32_t pool, double threshold, int32_t k,
+                     int64_t* out_row, float* out_score, int32_t* out_count);
+int sdk_identify_f16_dev(sdk_ctx* ctx, const uint16_t* d_seg, const int32_t* d_seg_label, int64_t N,
+                         int32_t L, int32_t pool, double threshold, int32_t k);
 
 /* ---- assignment (replaces combine_signals over embedding_match signals, speaker-assign:418-492,
  *      and the min-trust filter, speaker-assign:304-311), computed on the device in fp64 -------- */

@@ -30,7 +30,7 @@ EXPORTS = [
     "sdk_set_option", "sdk_bank_load", "sdk_bank_load_dev", "sdk_identify", "sdk_identify_dev", "sdk_assign",
     "sdk_results_fetch", "sdk_affinity_pooled", "sdk_affinity_pooled_dev", "sdk_sync", "sdk_stream",
     "sdk_timer_start", "sdk_timer_stop", "sdk_profile_get", "sdk_profile_reset", "sdk_launch_count", "sdk_last_path",
-    "sdk_last_retry", "sdk_merge_topk", "sdk_stage_a_fetch",
+    "sdk_last_retry", "sdk_merge_topk", "sdk_stage_a_fetch", "sdk_identify_f16", "sdk_identify_f16_dev",
 ]
 
 
@@ -66,6 +66,8 @@ def load() -> C.CDLL:
     lib.sdk_bank_load_dev.argtypes = [vp, vp, vp, vp, i64, i32, i32, i64]
     lib.sdk_identify.argtypes = [vp, vp, vp, i64, i32, i32, f64, i32, vp, vp, vp]
     lib.sdk_identify_dev.argtypes = [vp, vp, vp, i64, i32, i32, f64, i32]
+    lib.sdk_identify_f16.argtypes = [vp, vp, vp, i64, i32, i32, f64, i32, vp, vp, vp]
+    lib.sdk_identify_f16_dev.argtypes = [vp, vp, vp, i64, i32, i32, f64, i32]
     lib.sdk_assign.argtypes = [vp, f64, i32]
     lib.sdk_results_fetch.argtypes = [vp] + [vp] * 9
     lib.sdk_affinity_pooled.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]
@@ -159,21 +161,25 @@ class Context:
 
     # ---- identify ----
     def identify(self, seg, seg_label, L: int, pool: int = POOL_MEAN, threshold: float = 0.354, k: int = 10):
-        """Host buffers in, host results out.  Returns (rows [L,k] int64, scores [L,k] f32, counts [L] i32)."""
-        seg = _np(seg, np.float32).reshape(-1, self.D)
+        """Host buffers in, host results out.  Returns (rows [L,k] int64, scores [L,k] f32, counts [L] i32).
+        A float16 `seg` goes down as it is (sdk_identify_f16: half the host->device bytes, same result as on the
+        widened matrix); anything else is taken as float32."""
+        f16 = getattr(seg, "dtype", None) == np.float16
+        seg = _np(seg, np.float16 if f16 else np.float32).reshape(-1, self.D)
         lab = _np(seg_label, np.int32)
         if len(lab) != seg.shape[0]:
             raise ValueError("seg_label length must equal the number of segments")
         rows = np.empty((L, k), dtype=np.int64)
         scores = np.empty((L, k), dtype=np.float32)
         counts = np.empty(L, dtype=np.int32)
-        self._ck(self.lib.sdk_identify(self.h, _ptr(seg), _ptr(lab), seg.shape[0], L, pool, threshold, k, _ptr(rows),
-                                       _ptr(scores), _ptr(counts)))
+        fn = self.lib.sdk_identify_f16 if f16 else self.lib.sdk_identify
+        self._ck(fn(self.h, _ptr(seg), _ptr(lab), seg.shape[0], L, pool, threshold, k, _ptr(rows), _ptr(scores), _ptr(counts)))
         self.L, self.k = L, k
         return rows, scores, counts
 
-    def identify_dev(self, d_seg_ptr: int, d_lab_ptr: int, N: int, L: int, pool: int, threshold: float, k: int):
-        self._ck(self.lib.sdk_identify_dev(self.h, d_seg_ptr, d_lab_ptr, N, L, pool, threshold, k))
+    def identify_dev(self, d_seg_ptr: int, d_lab_ptr: int, N: int, L: int, pool: int, threshold: float, k: int, f16: bool = False):
+        fn = self.lib.sdk_identify_f16_dev if f16 else self.lib.sdk_identify_dev
+        self._ck(fn(self.h, d_seg_ptr, d_lab_ptr, N, L, pool, threshold, k))
         self.L, self.k = L, k
 
     def merge_topk(self, rows, scores, counts, trust=None):

@@ -204,6 +204,8 @@ def cmd_assign_batch(args, matcher=None) -> int:
         items = json.loads(text)
     except json.JSONDecodeError:
         items = [json.loads(line) for line in text.splitlines() if line.strip()]
+    if getattr(args, "gpus", 1) > 1 and matcher is None:
+        return _assign_batch_multi_gpu(args, items)
     audios, transcripts, b3s, expected = [], [], [], []
     for it in items:
         a, t = Path(it["audio"]).resolve(), Path(it["transcript"]).resolve()
@@ -256,6 +258,74 @@ def cmd_assign_batch(args, matcher=None) -> int:
         for a, out in zip(audios, outputs):
             done = sum(1 for m in out["mappings"].values() if m.get("speaker_id"))
             print(f"{a.name}: assigned {done}/{len(out['mappings'])}")
+    return 0
+
+
+def _assign_batch_multi_gpu(args, items) -> int:
+    """`assign-batch --gpus N`: one worker process per GPU (replaces the thread pool of per-recording process
+    trees at speaker-process:627-642).  Default: recordings are split over the GPUs, balanced by segment count, every
+    worker holds the whole bank -- no collective.  `--shard-bank`: every worker loads its slice of the bank rows and
+    scores all recordings; the library all-gathers the per-shard top-k (NCCL) and merges, rank 0 writes the output."""
+    import subprocess
+    import tempfile
+    from . import BACKEND_NAME, sharding
+    n = int(args.gpus)
+    from . import _native
+    n_dev = max(1, _native.device_count())       # more workers than GPUs: they share devices (data-parallel mode only)
+    if args.shard_bank and n > n_dev:
+        print(f"Error: --shard-bank needs one GPU per rank ({n} requested, {n_dev} visible)", file=sys.stderr)
+        return 1
+    pkg_root = str(Path(__file__).resolve().parent.parent)          # the workers import this package by name
+    os.environ["PYTHONPATH"] = pkg_root + (os.pathsep + os.environ["PYTHONPATH"] if os.environ.get("PYTHONPATH") else "")
+    base = [sys.executable, "-m", "speaker_diarization_toolkit_b200.assign_cli", "assign-batch"]
+    common = ["--gpus", "1", "--min-trust", args.min_trust, "--threshold", repr(float(args.threshold)), "--format", "json"]
+    if args.tags:
+        common += ["--tags", args.tags]
+    with tempfile.TemporaryDirectory(prefix="assign-batch-") as td:
+        jobs = []
+        if args.shard_bank:
+            man = Path(td) / "manifest.json"
+            man.write_text(json.dumps(items))
+            for r in range(n):
+                env = dict(os.environ, SPEAKER_B200_DEVICE=str(r % n_dev), SPEAKER_B200_WORLD=str(n), SPEAKER_B200_RANK=str(r),
+                           SPEAKER_B200_UID_FILE=str(Path(td) / "nccl.uid"))
+                extra = ["--dry-run"] if (args.dry_run or r != 0) else []
+                jobs.append((r, env, base + [str(man)] + common + extra))
+        else:
+            try:
+                counts = [store.sidecar_segment_count(Path(it["audio"]).resolve(), BACKEND_NAME) for it in items]
+            except (OSError, KeyError, ValueError) as exc:
+                print(f"Error during identification: {exc}", file=sys.stderr)
+                return 1
+            for r, (a, b) in enumerate(sharding.partition_recordings(counts, n)):
+                if a == b:
+                    continue
+                man = Path(td) / f"manifest.{r}.json"
+                man.write_text(json.dumps(items[a:b]))
+                env = dict(os.environ, SPEAKER_B200_DEVICE=str(r % n_dev))
+                for v in ("SPEAKER_B200_WORLD", "SPEAKER_B200_RANK", "SPEAKER_B200_UID_FILE"):
+                    env.pop(v, None)
+                jobs.append((r, env, base + [str(man)] + common + (["--dry-run"] if args.dry_run else [])))
+        procs = [(r, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)) for r, env, cmd in jobs]
+        outputs, rc = [], 0
+        for r, pr in procs:
+            out, err = pr.communicate()
+            if pr.returncode != 0:
+                print(f"Error: GPU worker {r} failed (exit {pr.returncode}):\n{err.strip()}", file=sys.stderr)
+                rc = 1
+                continue
+            if err.strip() and args.verbose:
+                print(err.strip(), file=sys.stderr)
+            if not args.shard_bank or r == 0:
+                outputs += json.loads(out)
+    if rc:
+        return rc
+    if args.format == "json":
+        print(json.dumps(outputs, indent=2, ensure_ascii=False))
+    elif not args.quiet:
+        for it, out in zip(items, outputs):
+            done = sum(1 for m in out["mappings"].values() if m.get("speaker_id"))
+            print(f"{Path(it['audio']).name}: assigned {done}/{len(out['mappings'])}")
     return 0
 
 
@@ -361,6 +431,9 @@ def build_parser() -> argparse.ArgumentParser:
     b.add_argument("--threshold", type=float, default=0.3)
     b.add_argument("--format", "-f", choices=["text", "json"], default="text")
     b.add_argument("--dry-run", "-n", action="store_true")
+    b.add_argument("--gpus", type=int, default=1, help="one worker process per GPU; recordings are split over them (no collective)")
+    b.add_argument("--shard-bank", action="store_true",
+                   help="with --gpus N: shard the bank rows over the GPUs instead (million-profile banks; NCCL all-gather + merge)")
     b.set_defaults(func=cmd_assign_batch)
     sh = sub.add_parser("show", help="Show current assignments for a recording")            # speaker-assign:763-766
     sh.add_argument("audio", help="Path to audio file or b3sum prefix")

@@ -35,7 +35,10 @@ class B200Backend(EmbeddingBackend):
     SPEAKER_B200_POOL = mean|max, SPEAKER_B200_TOPK (matches per label, default 10),
     SPEAKER_B200_SCOPE = label|recording (per-label rows, or whole-recording rows as the reference's
     speaker-assign expects), SPEAKER_B200_DTYPE = fp32|bf16, SPEAKER_B200_DEVICE (cuda index), SPEAKER_B200_DIM,
-    SPEAKER_B200_BANK_CACHE = 0 disables the packed bank cache (store.build_bank_cached)."""
+    SPEAKER_B200_BANK_CACHE = 0 disables the packed bank cache (store.build_bank_cached), = trust skips its per-file stat().
+    Row-sharded bank over several GPUs, one process per GPU: SPEAKER_B200_WORLD, SPEAKER_B200_RANK and
+    SPEAKER_B200_UID_FILE (rank 0 publishes the NCCL unique id there); every rank must make the same identify calls and
+    every rank gets the merged, global result."""
 
     def __init__(self):
         self._ctx: Optional[_native.Context] = None
@@ -67,7 +70,8 @@ class B200Backend(EmbeddingBackend):
     # -- device context, cached across calls (benchmark.py:105-158 reuses one backend instance) --
     def _context(self) -> _native.Context:
         if self._ctx is None:
-            self._ctx = _native.Context(_env_int("SPEAKER_B200_DEVICE", 0))
+            from .batch import sharded_context_from_env
+            self._world, self._rank, self._ctx = sharded_context_from_env(_env_int("SPEAKER_B200_DEVICE", 0))
         return self._ctx
 
     def _load_bank(self, candidates: List[Dict[str, Any]]) -> store.Bank:
@@ -86,7 +90,14 @@ class B200Backend(EmbeddingBackend):
             build = store.build_bank if os.environ.get("SPEAKER_B200_BANK_CACHE", "1") == "0" else store.build_bank_cached
             bank = build(candidates, self.name, _env_int("SPEAKER_B200_DIM", 0) or None)
             if bank.P:
-                self._context().bank_load(bank.rows, bank.row_speaker, bank.row_trust, dtype=dtype)
+                ctx = self._context()
+                if self._world > 1:     # this rank's slice of the rows, cut on speaker boundaries; result rows are global
+                    from .sharding import shard_bank_rows
+                    p0, p1 = shard_bank_rows(bank.row_speaker, self._world)[self._rank]
+                    ctx.bank_load(bank.rows[p0:p1].reshape(p1 - p0, bank.rows.shape[1]), bank.row_speaker[p0:p1], bank.row_trust[p0:p1],
+                                  dtype=dtype, global_row_offset=p0)
+                else:
+                    ctx.bank_load(bank.rows, bank.row_speaker, bank.row_trust, dtype=dtype)
             self._bank, self._bank_key, self._bank_dtype = bank, key, dtype
         return self._bank
 

@@ -305,7 +305,7 @@ static int sdk_check_flags(sdk_ctx* c, const int32_t* d_flags) {   // after a st
 }
 
 static int sdk_allgather_merge(sdk_ctx* c, int32_t L, int32_t k);
-static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L,
+static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L,
                              int32_t label_base, int32_t pool, double threshold, int32_t k);
 
 static int sdk_check_identify_args(sdk_ctx* c, const void* seg, const void* lab, int64_t N, int32_t L, int32_t pool,
@@ -357,8 +357,9 @@ static int sdk_reserve_results(sdk_ctx* c, int32_t L, int32_t k) {
 }
 
 // One pass of the hot path over the label groups [label_base, label_base + L): segments d_seg (N rows) carry
-// GLOBAL label ids; results land at group offset label_base of the context's result arrays.
-static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L,
+// GLOBAL label ids; results land at group offset label_base of the context's result arrays.  The raw rows are fp32 or
+// fp16 (c->in_dtype, set by the entry point).
+static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L,
                              int32_t label_base, int32_t pool, double threshold, int32_t k) {
     const int32_t D = c->D, Dp = c->Dp;
     const int64_t P = c->P;
@@ -398,7 +399,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
     // (its candidate slots are indexed by label id: a handful of segments scattered over very many labels stays generic)
     const bool use_gemv = path == 2 && c->opt_gemv && sdk_gemv_applicable(N, Dp) && L <= 64;
     bool use_acc = path == 2 && !use_gemv && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048 &&
-                   (uintptr_t)d_seg % 16 == 0;     // its scatter-normalise reads the raw rows with 128-bit loads
+                   (uintptr_t)d_seg % (c->in_dtype == SDK_IN_F16 ? 8 : 16) == 0;     // its scatter-normalise reads the raw rows with 128-bit (fp16: 64-bit) loads
     if (use_acc && c->opt_acc != 2 && !(Dp <= 256 || L > 2048)) use_acc = false;
     int64_t acc_steps = 0;
     if (path == 2) {   // the plan of either tcgen05 kernel trusts goff: reject bad labels before going on
@@ -418,8 +419,8 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
     if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
     if (need_bf16) SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
     if (!bf16 || need_bf16)
-        SDK_TRY(sdk_launch_normalize(c, d_seg, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
-                                     need_bf16 ? (__nv_bfloat16*)c->seg_bf16.p : nullptr));
+        SDK_TRY(sdk_launch_normalize_in(c, d_seg, c->in_dtype, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
+                                        need_bf16 ? (__nv_bfloat16*)c->seg_bf16.p : nullptr));
     const void* bank_ops = bf16 ? c->bank_bf16.p : c->bank_f32.p;
     const int32_t pitch = bf16 ? Dp : D;
     const PaGroup* seg_grp = nullptr;      // row addressing of the segment operands (identity unless interleaved)
@@ -473,7 +474,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
         c->slot_g0 = c->slot_g1 = 0;
         if (use_acc) {
             const PaGroup* ig = nullptr;
-            SDK_TRY(sdk_launch_poolacc(c, d_seg, d_seg_label, label_base, N, D, Dp, (const __nv_bfloat16*)c->bank_bf16.p, P,
+            SDK_TRY(sdk_launch_poolacc(c, d_seg, c->in_dtype, d_seg_label, label_base, N, D, Dp, (const __nv_bfloat16*)c->bank_bf16.p, P,
                                        (const int64_t*)c->goff.p, L, acc_steps, 0, tau, ncand, (int32_t*)c->cand_row.p,
                                        (float*)c->gbound.p, nullptr, c->seg_bf16, &ig));
             if (bf16) seg_grp = ig;                            // bf16 operands live in the interleaved matrix
@@ -545,7 +546,7 @@ static int sdk_identify_core(sdk_ctx* c, const float* d_seg, const int32_t* d_se
 }
 
 // An empty shard (P == 0) has nothing to score: its lists are empty, and it still joins the collective.
-static int sdk_identify_any(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t label_base,
+static int sdk_identify_any(sdk_ctx* c, const void* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t label_base,
                             int32_t pool, double threshold, int32_t k) {
     if (c->P == 0) {
         SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
@@ -584,10 +585,11 @@ static int sdk_finish_collective(sdk_ctx* c, int32_t L, int32_t k, int local_rc)
     return r;
 }
 
-int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t pool,
-                     double threshold, int32_t k) {
+static int sdk_identify_dev_in(sdk_ctx* c, const void* d_seg, int32_t in_dtype, const int32_t* d_seg_label, int64_t N, int32_t L,
+                               int32_t pool, double threshold, int32_t k) {
     SDK_TRY(sdk_check_identify_args(c, d_seg, d_seg_label, N, L, pool, threshold, k));
     cudaSetDevice(c->device);
+    c->in_dtype = in_dtype;
     c->have_results = false;
     c->have_assign = false;
     c->last_fallback = 0;
@@ -598,6 +600,14 @@ int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label,
     SDK_TRY(sdk_finish_collective(c, L, k, r));
     c->have_results = true;
     return SDK_OK;
+}
+int sdk_identify_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t pool,
+                     double threshold, int32_t k) {
+    return sdk_identify_dev_in(c, d_seg, SDK_IN_F32, d_seg_label, N, L, pool, threshold, k);
+}
+int sdk_identify_f16_dev(sdk_ctx* c, const uint16_t* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t pool,
+                         double threshold, int32_t k) {
+    return sdk_identify_dev_in(c, d_seg, SDK_IN_F16, d_seg_label, N, L, pool, threshold, k);
 }
 
 // one ncclAllGather of the head of every rank's result record, then K4 reads the gathered records in place
@@ -652,10 +662,11 @@ int sdk_merge_topk(sdk_ctx* c, int32_t world, int32_t L, int32_t k, const int64_
 // Host-buffer entry point.  Large batches are cut at label-group boundaries into chunks that are copied on a second
 // stream into two staging buffers while the previous chunk is being scored, so end-to-end time is
 // max(PCIe, compute) instead of their sum, and the device footprint is two chunks instead of the whole batch.
-static int sdk_identify_host_body(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
+static int sdk_identify_host_body(sdk_ctx* c, const void* seg_v, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
                                   double threshold, int32_t k) {
     const int32_t D = c->D;
-    const size_t row_bytes = (size_t)D * 4;
+    const char* seg = (const char*)seg_v;
+    const size_t row_bytes = (size_t)D * sdk_in_size(c->in_dtype);
     const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)((size_t)c->opt_chunk_mb << 20) / (int64_t)row_bytes);
     if (N <= chunk_rows + chunk_rows / 4) {
         SDK_TRY(sdk_reserve(c, c->seg_raw, (size_t)N * row_bytes));
@@ -664,7 +675,7 @@ static int sdk_identify_host_body(sdk_ctx* c, const float* seg, const int32_t* s
             SDK_CUDA(c, cudaMemcpyAsync(c->seg_raw.p, seg, (size_t)N * row_bytes, cudaMemcpyHostToDevice, c->stream));
             SDK_CUDA(c, cudaMemcpyAsync(c->seg_lab.p, seg_label, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
         }
-        SDK_TRY(sdk_identify_any(c, (const float*)c->seg_raw.p, (const int32_t*)c->seg_lab.p, N, L, 0, pool, threshold, k));
+        SDK_TRY(sdk_identify_any(c, c->seg_raw.p, (const int32_t*)c->seg_lab.p, N, L, 0, pool, threshold, k));
     } else {
         // chunk cut points: first label change at or after each multiple of chunk_rows
         for (int64_t i = 1; i < N; ++i)
@@ -695,7 +706,7 @@ static int sdk_identify_host_body(sdk_ctx* c, const float* seg, const int32_t* s
             const int b = (int)(i & 1);
             const int64_t a = cut[i], n = cut[i + 1] - cut[i];
             if (i >= 2) SDK_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
-            SDK_CUDA(c, cudaMemcpyAsync(c->stage_seg[b].p, seg + a * (int64_t)D, (size_t)n * row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+            SDK_CUDA(c, cudaMemcpyAsync(c->stage_seg[b].p, seg + (size_t)a * row_bytes, (size_t)n * row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
             SDK_CUDA(c, cudaMemcpyAsync(c->stage_lab[b].p, seg_label + a, (size_t)n * 4, cudaMemcpyHostToDevice, c->copy_stream));
             SDK_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
             return SDK_OK;
@@ -711,7 +722,7 @@ static int sdk_identify_host_body(sdk_ctx* c, const float* seg, const int32_t* s
             const int32_t g1 = (i + 1 < nchunk) ? seg_label[cut[i + 1]] : L;
             const int32_t gbeg = (i == 0) ? 0 : g0;
             SDK_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-            SDK_TRY(sdk_identify_any(c, (const float*)c->stage_seg[b].p, (const int32_t*)c->stage_lab[b].p, n, g1 - gbeg, gbeg,
+            SDK_TRY(sdk_identify_any(c, c->stage_seg[b].p, (const int32_t*)c->stage_lab[b].p, n, g1 - gbeg, gbeg,
                                       pool, threshold, k));
             SDK_CUDA(c, cudaEventRecord(c->ev_consumed[b], c->stream));
         }
@@ -719,10 +730,11 @@ static int sdk_identify_host_body(sdk_ctx* c, const float* seg, const int32_t* s
     return SDK_OK;
 }
 
-int sdk_identify(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
-                 double threshold, int32_t k, int64_t* out_row, float* out_score, int32_t* out_count) {
+static int sdk_identify_in(sdk_ctx* c, const void* seg, int32_t in_dtype, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
+                           double threshold, int32_t k, int64_t* out_row, float* out_score, int32_t* out_count) {
     SDK_TRY(sdk_check_identify_args(c, seg, seg_label, N, L, pool, threshold, k));
     cudaSetDevice(c->device);
+    c->in_dtype = in_dtype;
     c->have_results = false;
     c->have_assign = false;
     c->last_fallback = 0;
@@ -733,6 +745,14 @@ int sdk_identify(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t
     SDK_TRY(sdk_finish_collective(c, L, k, r));
     c->have_results = true;
     return sdk_results_fetch(c, out_row, out_score, out_count, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+int sdk_identify(sdk_ctx* c, const float* seg, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
+                 double threshold, int32_t k, int64_t* out_row, float* out_score, int32_t* out_count) {
+    return sdk_identify_in(c, seg, SDK_IN_F32, seg_label, N, L, pool, threshold, k, out_row, out_score, out_count);
+}
+int sdk_identify_f16(sdk_ctx* c, const uint16_t* seg, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
+                     double threshold, int32_t k, int64_t* out_row, float* out_score, int32_t* out_count) {
+    return sdk_identify_in(c, seg, SDK_IN_F16, seg_label, N, L, pool, threshold, k, out_row, out_score, out_count);
 }
 
 int sdk_assign(sdk_ctx* c, double assign_threshold, int32_t min_trust_code) {
@@ -869,7 +889,7 @@ int sdk_affinity_pooled_dev(sdk_ctx* c, const float* d_seg, const int32_t* d_seg
         }
         if (use_acc) {
             c->last_path = 3;
-            SDK_TRY(sdk_launch_poolacc(c, d_seg, d_seg_label, 0, N, D, Dp, (const __nv_bfloat16*)c->seg_bf16.p, N,
+            SDK_TRY(sdk_launch_poolacc(c, d_seg, SDK_IN_F32, d_seg_label, 0, N, D, Dp, (const __nv_bfloat16*)c->seg_bf16.p, N,
                                        (const int64_t*)c->goff.p, L, acc_steps, 1, 0.f, 0, nullptr, nullptr, d_out_nl, c->seg_il, nullptr));
         } else {
             SDK_TRY(sdk_launch_poolgemm_dense(c, (const __nv_bfloat16*)c->seg_bf16.p, N, (const __nv_bfloat16*)c->seg_bf16.p, N,

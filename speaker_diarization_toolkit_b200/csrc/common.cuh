@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
 #include <map>
@@ -78,6 +79,7 @@ struct sdk_ctx {
     // bank
     int64_t P = 0;
     int32_t D = 0, Dp = 0, dtype = 0;
+    int32_t in_dtype = 0;      // storage type of the raw segment rows of the identify call in progress (SDK_IN_*)
     int64_t row_offset = 0;
     sdk_buf bank_f32, bank_bf16, row_speaker, row_trust;
     // segments / scratch
@@ -158,6 +160,9 @@ struct sdk_prof_scope {
 // K1: canonical L2 normalise (+ optional fp32 copy, + optional zero-padded bf16 copy)
 int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int32_t Dp,
                          float* d_f32 /*[n,D] or null*/, __nv_bfloat16* d_bf16 /*[n,Dp] or null*/);
+// same, raw rows stored as fp32 (SDK_IN_F32) or IEEE fp16 (SDK_IN_F16: widened exactly to fp32, then the same arithmetic)
+int sdk_launch_normalize_in(sdk_ctx* c, const void* d_x, int32_t in_dtype, int64_t n, int32_t D, int32_t Dp,
+                            float* d_f32, __nv_bfloat16* d_bf16);
 // group offsets from sorted labels; *d_flag != 0 when labels are unsorted / out of range
 int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_t L, int32_t label_base,
                              int64_t* d_goff, int32_t* d_flag);
@@ -207,7 +212,7 @@ int sdk_poolacc_applicable(int32_t Dp, int32_t G, int32_t pool);
 int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, int64_t P, int32_t Dp, int64_t* steps_out);
 // mode 0: candidates (+ merge) into d_cand_row / d_gbound; mode 1: dense out[row, g] (config 5).  The interleaved
 // operands are written to `il` (grown as needed); *d_grp_out = per-group addressing for the canonical re-score.
-int sdk_launch_poolacc(sdk_ctx* c, const float* d_seg_raw, const int32_t* d_seg_label, int32_t label_base, int64_t N, int32_t D,
+int sdk_launch_poolacc(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype, const int32_t* d_seg_label, int32_t label_base, int64_t N, int32_t D,
                        int32_t Dp, const __nv_bfloat16* d_rows, int64_t P, const int64_t* d_goff, int32_t G, int64_t S,
                        int32_t mode, float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, float* d_dense,
                        sdk_buf& il, const PaGroup** d_grp_out);
@@ -217,6 +222,27 @@ int sdk_launch_poolgemm_dense(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P
                               const int64_t* d_goff, int32_t G, int32_t pool, float* d_out /*[P,G]*/);
 
 // ---- device helpers ---------------------------------------------------------------------------
+// Raw embedding rows as the caller stores them: fp32, or IEEE fp16 (half the PCIe / HBM bytes; widening to fp32 is
+// exact, so the canonical arithmetic downstream is unchanged).  ld4 = elements 4q .. 4q+3 of a row, streaming load.
+#define SDK_IN_F32 0
+#define SDK_IN_F16 1
+template <typename T> struct sdk_in;
+template <> struct sdk_in<float> {
+    static constexpr int align = 16;
+    static __device__ __forceinline__ float4 ld4(const float* row, int q) { return __ldcs(reinterpret_cast<const float4*>(row) + q); }
+    static __device__ __forceinline__ float ld1(const float* row, int e) { return row[e]; }
+};
+template <> struct sdk_in<__half> {
+    static constexpr int align = 8;
+    static __device__ __forceinline__ float4 ld4(const __half* row, int q) {
+        const uint2 u = __ldcs(reinterpret_cast<const uint2*>(row) + q);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ float ld1(const __half* row, int e) { return __half2float(row[e]); }
+};
+static inline size_t sdk_in_size(int32_t in_dtype) { return in_dtype == SDK_IN_F16 ? 2 : 4; }
 __device__ __forceinline__ uint32_t sdk_fkey(float f) {   // order-preserving float -> uint
     uint32_t u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);

@@ -10,8 +10,8 @@
 // lane over ascending elements, butterfly xor 16,8,4,2,1 -- identical on every lane.
 #include "common.cuh"
 
-template <int NQ>
-__global__ void __launch_bounds__(256) k_normalize_vec(const float* __restrict__ x, int64_t n, int32_t D,
+template <int NQ, typename TIn>
+__global__ void __launch_bounds__(256) k_normalize_vec(const TIn* __restrict__ x, int64_t n, int32_t D,
                                                        int32_t Dp, float* __restrict__ f32out,
                                                        __nv_bfloat16* __restrict__ bf16out) {
     // R consecutive rows per warp iteration: all of their loads are in flight before the first norm is reduced
@@ -28,11 +28,11 @@ __global__ void __launch_bounds__(256) k_normalize_vec(const float* __restrict__
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const bool live = row0 + r < n;
-            const float4* xr = reinterpret_cast<const float4*>(x + (live ? row0 + r : row0) * (int64_t)D);
+            const TIn* xr = x + (live ? row0 + r : row0) * (int64_t)D;
 #pragma unroll
             for (int i = 0; i < NQ; ++i) {
                 int q = lane + 32 * i;
-                v[r][i] = (live && q < nq) ? __ldcs(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[r][i] = (live && q < nq) ? sdk_in<TIn>::ld4(xr, q) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
@@ -80,19 +80,20 @@ __global__ void __launch_bounds__(256) k_normalize_vec(const float* __restrict__
 }
 
 // any D (scalar loads, two passes over the row; second pass hits L1/L2)
-__global__ void __launch_bounds__(256) k_normalize_generic(const float* __restrict__ x, int64_t n, int32_t D,
+template <typename TIn>
+__global__ void __launch_bounds__(256) k_normalize_generic(const TIn* __restrict__ x, int64_t n, int32_t D,
                                                            int32_t Dp, float* __restrict__ f32out,
                                                            __nv_bfloat16* __restrict__ bf16out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = warp0; row < n; row += nwarps) {
-        const float* xr = x + row * (int64_t)D;
+        const TIn* xr = x + row * (int64_t)D;
         double s = 0.0;
         for (int q = lane; 4 * q < D; q += 32)
             for (int t = 0; t < 4; ++t) {
                 int e = 4 * q + t;
-                if (e < D) { double a = (double)xr[e]; s = fma(a, a, s); }
+                if (e < D) { double a = (double)sdk_in<TIn>::ld1(xr, e); s = fma(a, a, s); }
             }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
@@ -100,24 +101,24 @@ __global__ void __launch_bounds__(256) k_normalize_generic(const float* __restri
         float den = nrm > 1e-12f ? nrm : 1e-12f;
         const float inv = __fdiv_rn(1.0f, den);
         for (int e = lane; e < Dp; e += 32) {
-            float o = e < D ? __fmul_rn(xr[e], inv) : 0.f;
+            float o = e < D ? __fmul_rn(sdk_in<TIn>::ld1(xr, e), inv) : 0.f;
             if (f32out && e < D) f32out[row * (int64_t)D + e] = o;
             if (bf16out) bf16out[row * (int64_t)Dp + e] = __float2bfloat16_rn(o);
         }
     }
 }
 
-int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int32_t Dp, float* d_f32,
-                         __nv_bfloat16* d_bf16) {
+template <typename TIn>
+static int sdk_launch_normalize_t(sdk_ctx* c, const TIn* d_x, int64_t n, int32_t D, int32_t Dp, float* d_f32, __nv_bfloat16* d_bf16) {
     if (n <= 0) return SDK_OK;
     sdk_prof_scope ps(c, "normalize");
-    bool vec = (D % 4 == 0) && (Dp % 4 == 0) && D <= 2048 && ((uintptr_t)d_x % 16 == 0);
+    bool vec = (D % 4 == 0) && (Dp % 4 == 0) && D <= 2048 && ((uintptr_t)d_x % sdk_in<TIn>::align == 0);
     if (vec) {
         int nq = (D / 4 + 31) / 32;
         const int R = nq <= 2 ? 4 : (nq <= 4 ? 2 : 1);
         int64_t blocks64 = ((n + R - 1) / R + 7) / 8;
         int blocks = (int)(blocks64 < (int64_t)c->sm_count * 8 ? blocks64 : (int64_t)c->sm_count * 8);
-#define SDK_NORM_CASE(NQ) k_normalize_vec<NQ><<<blocks, 256, 0, c->stream>>>(d_x, n, D, Dp, d_f32, d_bf16)
+#define SDK_NORM_CASE(NQ) k_normalize_vec<NQ, TIn><<<blocks, 256, 0, c->stream>>>(d_x, n, D, Dp, d_f32, d_bf16)
         if (nq <= 1) SDK_NORM_CASE(1);
         else if (nq <= 2) SDK_NORM_CASE(2);
         else if (nq <= 4) SDK_NORM_CASE(4);
@@ -127,11 +128,21 @@ int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int
     } else {
         int64_t blocks64 = (n + 7) / 8;
         int blocks = (int)(blocks64 < (int64_t)c->sm_count * 8 ? blocks64 : (int64_t)c->sm_count * 8);
-        k_normalize_generic<<<blocks, 256, 0, c->stream>>>(d_x, n, D, Dp, d_f32, d_bf16);
+        k_normalize_generic<TIn><<<blocks, 256, 0, c->stream>>>(d_x, n, D, Dp, d_f32, d_bf16);
     }
     c->launches++;
     SDK_CUDA(c, cudaGetLastError());
     return SDK_OK;
+}
+
+int sdk_launch_normalize_in(sdk_ctx* c, const void* d_x, int32_t in_dtype, int64_t n, int32_t D, int32_t Dp, float* d_f32,
+                            __nv_bfloat16* d_bf16) {
+    if (in_dtype == SDK_IN_F16) return sdk_launch_normalize_t<__half>(c, (const __half*)d_x, n, D, Dp, d_f32, d_bf16);
+    return sdk_launch_normalize_t<float>(c, (const float*)d_x, n, D, Dp, d_f32, d_bf16);
+}
+int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int32_t Dp, float* d_f32,
+                         __nv_bfloat16* d_bf16) {
+    return sdk_launch_normalize_t<float>(c, d_x, n, D, Dp, d_f32, d_bf16);
 }
 
 // goff[g] = first segment index whose (label - label_base) >= g  (labels non-decreasing, in [base, base+L))

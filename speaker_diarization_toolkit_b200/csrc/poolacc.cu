@@ -410,9 +410,9 @@ k_pa_plan_bins(const int64_t* __restrict__ goff, int32_t G, PaCost pc, int32_t* 
 // Source ordered: a warp owns R consecutive raw rows, all of their 128-bit loads are issued before anything else, the
 // (label -> group record) lookups of lanes 0..R-1 fly alongside; each row is written as one contiguous 2*Dp-byte run at
 // its interleaved position.  Arithmetic = k_normalize_vec (canonical).
-template <int NQ>
+template <int NQ, typename TIn>
 __global__ void __launch_bounds__(256)
-k_pa_normalize_scatter(const float* __restrict__ x, const int32_t* __restrict__ lab, int32_t label_base, int64_t n, int32_t D, int32_t Dp,
+k_pa_normalize_scatter(const TIn* __restrict__ x, const int32_t* __restrict__ lab, int32_t label_base, int64_t n, int32_t D, int32_t Dp,
                        const PaGroup* __restrict__ grp, __nv_bfloat16* __restrict__ out) {
     constexpr int R = (NQ <= 2) ? 4 : (NQ <= 4 ? 2 : 1);       // rows per warp iteration (register budget)
     const int lane = threadIdx.x & 31;
@@ -426,11 +426,11 @@ k_pa_normalize_scatter(const float* __restrict__ x, const int32_t* __restrict__ 
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const bool live = row0 + r < n;
-            const float4* xr = reinterpret_cast<const float4*>(x + (live ? row0 + r : row0) * (int64_t)D);
+            const TIn* xr = x + (live ? row0 + r : row0) * (int64_t)D;
 #pragma unroll
             for (int i = 0; i < NQ; ++i) {
                 int q = lane + 32 * i;
-                v[r][i] = (live && q < nq) ? __ldcs(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[r][i] = (live && q < nq) ? sdk_in<TIn>::ld4(xr, q) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         int64_t my_dst = -1;
@@ -825,14 +825,15 @@ int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, in
 
 // Normalises the raw segments into the planned interleaved layout (buffer `il`), runs the accumulate-pooling GEMM and,
 // in candidate mode, the slot merge.  `S` = steps from sdk_poolacc_plan (same goff, no other plan in between).
-int sdk_launch_poolacc(sdk_ctx* c, const float* d_seg_raw, const int32_t* d_seg_label, int32_t label_base, int64_t N, int32_t D,
+int sdk_launch_poolacc(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype, const int32_t* d_seg_label, int32_t label_base, int64_t N, int32_t D,
                        int32_t Dp, const __nv_bfloat16* d_rows, int64_t P, const int64_t* d_goff, int32_t G, int64_t S, int32_t mode,
                        float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, float* d_dense, sdk_buf& il,
                        const PaGroup** d_grp_out) {
     if (!sdk_poolacc_applicable(Dp, G, SDK_POOL_MEAN) || !c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path unavailable");
     if (P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "tcgen05 path: at most 2^31-1 bank rows");
     if (D % 4 != 0 || D > 2048) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path needs D % 4 == 0");
-    if ((uintptr_t)d_seg_raw % 16 != 0) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path needs a 16-byte aligned segment matrix");
+    if ((uintptr_t)d_seg_raw % (in_dtype == SDK_IN_F16 ? 8 : 16) != 0)
+        return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path needs a 16-byte (fp16 rows: 8-byte) aligned segment matrix");
     const int kch = Dp / 64, MT = pa_mt_for(kch);
     const int32_t n_blocks = c->pa_blocks;
     int64_t* step0 = (int64_t*)c->pa_step0.p;
@@ -855,7 +856,13 @@ int sdk_launch_poolacc(sdk_ctx* c, const float* d_seg_raw, const int32_t* d_seg_
         int64_t blocks64 = ((N + R - 1) / R + 7) / 8;
         if (blocks64 < 1) blocks64 = 1;
         int blocks = (int)(blocks64 < (int64_t)c->sm_count * 8 ? blocks64 : (int64_t)c->sm_count * 8);
-#define PA_NORM(NQ) k_pa_normalize_scatter<NQ><<<blocks, 256, 0, c->stream>>>(d_seg_raw, d_seg_label, label_base, N, D, Dp, grp, (__nv_bfloat16*)il.p)
+#define PA_NORM(NQ)                                                                                                                   \
+    do {                                                                                                                              \
+        if (in_dtype == SDK_IN_F16)                                                                                                   \
+            k_pa_normalize_scatter<NQ, __half><<<blocks, 256, 0, c->stream>>>((const __half*)d_seg_raw, d_seg_label, label_base, N, D, Dp, grp, (__nv_bfloat16*)il.p); \
+        else                                                                                                                          \
+            k_pa_normalize_scatter<NQ, float><<<blocks, 256, 0, c->stream>>>((const float*)d_seg_raw, d_seg_label, label_base, N, D, Dp, grp, (__nv_bfloat16*)il.p);   \
+    } while (0)
         if (nq <= 1) PA_NORM(1);
         else if (nq <= 2) PA_NORM(2);
         else if (nq <= 4) PA_NORM(4);

@@ -229,21 +229,34 @@ def sidecar_path(audio_path, backend_name: str) -> Path:
 
 @dataclass
 class SegmentEmbeddings:
-    emb: np.ndarray          # [N, D] fp32, sorted by label (stable)
+    emb: np.ndarray          # [N, D] fp32 (or fp16: compact sidecar), sorted by label (stable)
     label_index: np.ndarray  # [N] int32 index into labels, non-decreasing
     labels: List[str]        # sorted(set(labels))  (speaker-assign:196)
     start: np.ndarray
     end: np.ndarray
 
 
-def save_segment_embeddings(audio_path, backend_name: str, emb, labels, start=None, end=None) -> Path:
-    emb = np.ascontiguousarray(emb, dtype=np.float32)
+def save_segment_embeddings(audio_path, backend_name: str, emb, labels, start=None, end=None, dtype=None) -> Path:
+    """`dtype` = np.float16 stores the compact form of the sidecar (half the bytes on disk and over PCIe; the device
+    widens every element exactly to fp32 before the canonical normalise); default: float32, or float16 if `emb`
+    already is.  Labels keep their full length (the reference puts no limit on diarization labels)."""
+    emb = np.asarray(emb)
+    want = np.dtype(dtype) if dtype is not None else (np.dtype(np.float16) if emb.dtype == np.float16 else np.dtype(np.float32))
+    if want not in (np.dtype(np.float16), np.dtype(np.float32)):
+        raise ValueError("segment embeddings are stored as float32 or float16")
+    emb = np.ascontiguousarray(emb, dtype=want)
     n = emb.shape[0]
     path = sidecar_path(audio_path, backend_name)
-    np.savez(path, emb=emb, label=np.asarray(labels, dtype="<U32"),
+    np.savez(path, emb=emb, label=np.asarray([str(x) for x in labels], dtype=str),
              start=np.zeros(n) if start is None else np.asarray(start, np.float64),
              end=np.zeros(n) if end is None else np.asarray(end, np.float64))
     return path
+
+
+def sidecar_segment_count(audio_path, backend_name: str) -> int:
+    """Number of segments in a sidecar without reading the embeddings (partitioning a manifest over GPUs)."""
+    with np.load(sidecar_path(audio_path, backend_name), allow_pickle=False) as z:
+        return int(z["label"].shape[0])
 
 
 def load_segment_embeddings(audio_path, backend_name: str) -> SegmentEmbeddings:
@@ -251,7 +264,8 @@ def load_segment_embeddings(audio_path, backend_name: str) -> SegmentEmbeddings:
     if not path.exists():
         raise FileNotFoundError(f"segment-embedding sidecar not found: {path}")
     with np.load(path, allow_pickle=False) as z:
-        emb = np.ascontiguousarray(z["emb"], dtype=np.float32)
+        raw = z["emb"]
+        emb = np.ascontiguousarray(raw, dtype=np.float16 if raw.dtype == np.float16 else np.float32)
         lab = [str(x) for x in z["label"]]
         start = np.asarray(z["start"], np.float64) if "start" in z else np.zeros(len(lab))
         end = np.asarray(z["end"], np.float64) if "end" in z else np.zeros(len(lab))
@@ -268,87 +282,173 @@ def load_segment_embeddings(audio_path, backend_name: str) -> SegmentEmbeddings:
 # `cmd_identify` would otherwise open one .npy per embedding record on every call (speaker_detection:1054 ->
 # base.py:123); at a million-profile bank that, not the GPU, is the wall time.  The per-file layout stays
 # authoritative: the cache is `embeddings/.bank-<backend>-D<d>.f32` (raw fp32 [rows, D], mmap-able) +
-# `embeddings/.bank-<backend>-D<d>.idx.json` (speaker/emb id -> row, file size + mtime_ns).  A row is reused only if
-# its source file's (size, mtime_ns) still match; new / changed files are re-read and appended; the pack is
-# rewritten compacted when more than a quarter of it is stale.
+# `embeddings/.bank-<backend>-D<d>.idx.npz` (BINARY index: key "<speaker>/<emb id>" -> row, source file size +
+# mtime_ns; numpy arrays, so a million entries load in a fraction of a second where JSON took several).  A row is
+# reused only if its source file's (size, mtime_ns) still match; new / changed files are re-read and appended; the
+# pack is rewritten compacted when more than a quarter of it is stale.  Everything per-row is vectorised: one dict
+# lookup pass for key -> row, NumPy comparisons for the stat check, ONE fancy-index gather from the mmap (or the mmap
+# itself when the pack already is exactly the wanted rows in order).
+# SPEAKER_B200_BANK_CACHE=trust skips the per-file stat() calls (a pack row is reused whenever its key is present):
+# for stores whose vectors are never rewritten in place.
 def _cache_paths(backend_name: str, dim: int):
     root = get_embeddings_path()
-    return root / f".bank-{backend_name}-D{dim}.f32", root / f".bank-{backend_name}-D{dim}.idx.json"
+    return root / f".bank-{backend_name}-D{dim}.f32", root / f".bank-{backend_name}-D{dim}.idx.npz"
+
+
+def _load_cache_index(pack_path: Path, idx_path: Path, dim: int):
+    """(key -> position dict, row [n], size [n], mtime_ns [n], memmap) or None."""
+    if not (pack_path.exists() and idx_path.exists()):
+        return None
+    try:
+        with np.load(idx_path, allow_pickle=False) as z:
+            if int(z["dim"]) != dim:
+                return None
+            keys, row, size, mtime, n_rows = z["key"], z["row"], z["size"], z["mtime_ns"], int(z["rows"])
+        if pack_path.stat().st_size != n_rows * dim * 4 or not n_rows:
+            return None
+        pack = np.memmap(pack_path, dtype=np.float32, mode="r", shape=(n_rows, dim))
+        return dict(zip(keys.tolist(), range(len(keys)))), row, size, mtime, pack
+    except (OSError, ValueError, KeyError):
+        return None
+
+
+def _write_cache_index(idx_path: Path, dim: int, backend_name: str, keys, row, size, mtime, n_rows: int) -> None:
+    tmp = idx_path.with_name(idx_path.name + f".{os.getpid()}.tmp.npz")
+    np.savez(tmp, dim=np.int64(dim), rows=np.int64(n_rows), backend=np.asarray(backend_name), key=np.asarray(keys, dtype=str),
+             row=np.asarray(row, np.int64), size=np.asarray(size, np.int64), mtime_ns=np.asarray(mtime, np.int64))
+    os.replace(tmp, idx_path)
 
 
 def build_bank_cached(candidates: List[Dict[str, Any]], backend_name: str, dim: Optional[int] = None) -> Bank:
-    wanted = []     # (speaker index, speaker id, record, path, stat key)
+    trust_mode = os.environ.get("SPEAKER_B200_BANK_CACHE", "") == "trust"
+    root = get_embeddings_path()
+    unknown = TRUST_CODES["unknown"]
+    keys: List[str] = []
+    paths: List[Optional[Path]] = []
+    row_speaker_l: List[int] = []
+    row_trust_l: List[int] = []
+    emb_ids: List[Optional[str]] = []
+    spk_recs = []       # (speaker id, record) of every row, for lazy path resolution
     speaker_ids: List[str] = []
     for prof in candidates:
         sid = prof.get("id")
-        idx = None
-        for rec in (prof.get("embeddings") or {}).get(backend_name) or []:
-            path = vector_path(sid, rec)
-            if path is None:
-                print(f"Warning: no vector file for {sid}/{rec.get('id')} ({backend_name})", file=sys.stderr)
-                continue
-            if idx is None:
-                idx = len(speaker_ids)
-                speaker_ids.append(sid)
-            st = path.stat()
-            wanted.append((idx, sid, rec, path, [str(path), st.st_size, st.st_mtime_ns]))
-    if not wanted:
-        return Bank(np.zeros((0, dim or 0), np.float32), np.zeros(0, np.int32), np.zeros(0, np.uint8), [], [])
-    if dim is None:
-        packs = sorted(get_embeddings_path().glob(f".bank-{backend_name}-D*.idx.json"), key=lambda q: q.stat().st_mtime_ns)
-        if packs:       # a pack exists: its dimension (a mismatching vector is caught when it is read)
-            dim = int(packs[-1].name.split("-D")[-1].split(".")[0])
-        else:
-            dim = int(np.load(wanted[0][3]).reshape(-1).shape[0])
-    pack_path, idx_path = _cache_paths(backend_name, dim)
-    index, pack = {}, None
-    if pack_path.exists() and idx_path.exists():
-        try:
-            meta = json.loads(idx_path.read_text())
-            if meta.get("dim") == dim and pack_path.stat().st_size == meta.get("rows", -1) * dim * 4:
-                index = {k: v for k, v in meta.get("entries", {}).items()}
-                pack = np.memmap(pack_path, dtype=np.float32, mode="r", shape=(meta["rows"], dim)) if meta["rows"] else None
-        except (json.JSONDecodeError, OSError, ValueError):
-            index, pack = {}, None
-    rows = np.empty((len(wanted), dim), dtype=np.float32)
-    fresh = []      # (position, key, stat) that had to be read from the per-file layout
-    for pos, (_, sid, rec, path, stat) in enumerate(wanted):
-        key = f"{sid}/{rec.get('id')}"
-        ent = index.get(key)
-        if ent is not None and pack is not None and ent["stat"] == stat and ent["row"] < pack.shape[0]:
-            rows[pos] = pack[ent["row"]]
+        recs = (prof.get("embeddings") or {}).get(backend_name) or []
+        if not recs:
             continue
+        idx = len(speaker_ids)
+        used = False
+        for rec in recs:
+            rid = rec.get("id")
+            if trust_mode:
+                path = None             # resolved only for rows the pack does not hold
+            else:
+                path = vector_path(sid, rec)
+                if path is None:
+                    print(f"Warning: no vector file for {sid}/{rid} ({backend_name})", file=sys.stderr)
+                    continue
+            used = True
+            keys.append(f"{sid}/{rid}")
+            paths.append(path)
+            spk_recs.append((sid, rec))
+            row_speaker_l.append(idx)
+            row_trust_l.append(TRUST_CODES.get(rec.get("trust_level", "unknown"), unknown))
+            emb_ids.append(rid)
+        if used:                        # (a speaker without a usable record does not consume an index)
+            speaker_ids.append(sid)
+    n = len(keys)
+    if not n:
+        return Bank(np.zeros((0, dim or 0), np.float32), np.zeros(0, np.int32), np.zeros(0, np.uint8), [], [])
+    cache = None
+    if dim is None:
+        # The dimension of the WANTED vectors (not of whatever pack happens to be newest: a store re-enrolled at another D,
+        # or tag-filtered sub-banks of different D, must not inherit a stale pack's dimension): a pack that holds the
+        # first wanted key with an unchanged source file tells it without opening a .npy; otherwise that file's header.
+        st0 = None if trust_mode else paths[0].stat()
+        for ip in sorted(root.glob(f".bank-{backend_name}-D*.idx.npz")):
+            try:
+                d = int(ip.name.split("-D")[-1].split(".")[0])
+            except ValueError:
+                continue
+            cand = _load_cache_index(_cache_paths(backend_name, d)[0], ip, d)
+            if cand is None:
+                continue
+            at = cand[0].get(keys[0])
+            if at is not None and (trust_mode or (cand[2][at] == st0.st_size and cand[3][at] == st0.st_mtime_ns)):
+                dim, cache = d, cand
+                break
+        if dim is None:
+            first = paths[0] if paths[0] is not None else vector_path(*spk_recs[0])
+            if first is None:
+                raise ValueError(f"no vector file for {keys[0]} ({backend_name})")
+            dim = int(np.load(first, mmap_mode="r").reshape(-1).shape[0])
+    pack_path, idx_path = _cache_paths(backend_name, dim)
+    if cache is None:
+        cache = _load_cache_index(pack_path, idx_path, dim)
+    size, mtime = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    if not trust_mode:
+        st = [pp.stat() for pp in paths]
+        size = np.fromiter((x.st_size for x in st), np.int64, n)
+        mtime = np.fromiter((x.st_mtime_ns for x in st), np.int64, n)
+    hit = np.zeros(n, bool)
+    src = np.zeros(n, np.int64)
+    kpos, pack = {}, None
+    if cache is not None:
+        kpos, c_row, c_size, c_mtime, pack = cache
+        pos = np.fromiter((kpos.get(k, -1) for k in keys), np.int64, n)
+        hit = pos >= 0
+        pc = np.where(hit, pos, 0)
+        if trust_mode:                                   # rows taken on trust keep the stat the index already holds
+            size, mtime = np.where(hit, c_size[pc], 0), np.where(hit, c_mtime[pc], 0)
+        else:
+            hit &= (c_size[pc] == size) & (c_mtime[pc] == mtime)
+        src = np.where(hit, c_row[pc], 0)
+        hit &= src < pack.shape[0]
+    if pack is not None and hit.all() and n == pack.shape[0] and np.array_equal(src, np.arange(n)):
+        rows = np.asarray(pack)                          # the pack IS the bank: no copy, pages come in as they are read
+    else:
+        rows = np.empty((n, dim), dtype=np.float32)
+        if pack is not None and hit.any():
+            rows[hit] = pack[src[hit]]                   # one gather
+    miss = np.flatnonzero(~hit)
+    for i in miss.tolist():
+        path = paths[i] if paths[i] is not None else vector_path(*spk_recs[i])
+        if path is None:
+            raise ValueError(f"no vector file for {keys[i]} ({backend_name})")
         vec = np.load(path).astype(np.float32).reshape(-1)
         if vec.shape[0] != dim:
-            raise ValueError(f"embedding {key} has dimension {vec.shape[0]}, expected {dim}")
-        rows[pos] = vec
-        fresh.append((pos, key, stat))
-    if fresh or pack is None:
-        live = {f"{sid}/{rec.get('id')}" for _, sid, rec, _, _ in wanted}
-        stale = sum(1 for k in index if k not in live)
+            raise ValueError(f"embedding {keys[i]} has dimension {vec.shape[0]}, expected {dim}")
+        rows[i] = vec
+        if trust_mode:
+            stt = path.stat()
+            size[i], mtime[i] = stt.st_size, stt.st_mtime_ns
+    if len(miss) or pack is None:
         try:
-            if pack is None or stale * 4 > max(1, len(index)):
-                # rewrite compacted: exactly the rows in use now
-                tmp = pack_path.with_suffix(".tmp")
-                rows.tofile(tmp)
+            live = set(keys)
+            stale = sum(1 for k in kpos if k not in live)
+            if pack is None or stale * 4 > max(1, len(kpos)):
+                # rewrite compacted: exactly the rows in use now (unique temporary name: two processes rewriting at once
+                # must not interleave their rows)
+                tmp = pack_path.with_name(pack_path.name + f".{os.getpid()}.tmp")
+                np.ascontiguousarray(rows).tofile(tmp)
                 os.replace(tmp, pack_path)
-                entries = {f"{sid}/{rec.get('id')}": {"row": pos, "stat": stat} for pos, (_, sid, rec, _, stat) in enumerate(wanted)}
-                n_rows = len(wanted)
+                _write_cache_index(idx_path, dim, backend_name, keys, np.arange(n), size, mtime, n)
             else:
                 # append the new / changed rows
                 n_rows = pack.shape[0]
                 del pack
                 with open(pack_path, "ab") as fh:
-                    for pos, key, stat in fresh:
-                        rows[pos].tofile(fh)
-                        index[key] = {"row": n_rows, "stat": stat}
-                        n_rows += 1
-                entries = index
-            tmpi = idx_path.with_suffix(".tmp")
-            tmpi.write_text(json.dumps({"dim": dim, "rows": n_rows, "backend": backend_name, "entries": entries}))
-            os.replace(tmpi, idx_path)
+                    np.ascontiguousarray(rows[miss]).tofile(fh)
+                k_row, k_size, k_mtime = (np.asarray(x, np.int64).copy() for x in (c_row, c_size, c_mtime))
+                add_k, add_r, add_s, add_m = [], [], [], []
+                for j, i in enumerate(miss.tolist()):
+                    at = kpos.get(keys[i])
+                    if at is not None:
+                        k_row[at], k_size[at], k_mtime[at] = n_rows + j, size[i], mtime[i]
+                    else:
+                        add_k.append(keys[i]); add_r.append(n_rows + j); add_s.append(size[i]); add_m.append(mtime[i])
+                _write_cache_index(idx_path, dim, backend_name, list(kpos.keys()) + add_k, np.r_[k_row, np.asarray(add_r, np.int64)],
+                                   np.r_[k_size, np.asarray(add_s, np.int64)], np.r_[k_mtime, np.asarray(add_m, np.int64)],
+                                   n_rows + len(miss))
         except OSError as exc:      # read-only store: the cache is an optimisation, never a requirement
             print(f"Warning: could not update the packed bank cache: {exc}", file=sys.stderr)
-    row_speaker = np.asarray([w[0] for w in wanted], np.int32)
-    row_trust = np.asarray([TRUST_CODES.get(w[2].get("trust_level", "unknown"), TRUST_CODES["unknown"]) for w in wanted], np.uint8)
-    return Bank(rows, row_speaker, row_trust, [w[2].get("id") for w in wanted], speaker_ids)
+    return Bank(rows, np.asarray(row_speaker_l, np.int32), np.asarray(row_trust_l, np.uint8), emb_ids, speaker_ids)

@@ -166,3 +166,163 @@ def test_review_consistency_host_logic(tmp_path, monkeypatch, capsys):
     assert json.loads(capsys.readouterr().out)["suspects"] == []
     assert review_cli.main(["consistency", str(tmp_path / "nope.wav")]) == 1
     assert "Error: Audio file not found:" in capsys.readouterr().err
+
+
+# ---- multi-GPU orchestration of assign-batch, host logic on CPU -----------------------------------------
+class _InProcessWorker:
+    """Stand-in for subprocess.Popen: runs the worker command line of `assign-batch --gpus N` in this process (with the
+    oracle-backed context), so the partition of the manifest and the merge of the workers' outputs are tested on CPU."""
+    launched = []
+    real = None
+
+    def __new__(cls, cmd, *a, **k):
+        if list(cmd[1:3]) != ["-m", "speaker_diarization_toolkit_b200.assign_cli"]:
+            return cls.real(cmd, *a, **k)            # anything else (b3sum ...) is a real subprocess
+        return super().__new__(cls)
+
+    def __init__(self, cmd, env=None, stdout=None, stderr=None, text=None):
+        import contextlib
+        import io
+        import os
+        assert cmd[1:4] == ["-m", "speaker_diarization_toolkit_b200.assign_cli", "assign-batch"]
+        _InProcessWorker.launched.append((cmd, {k: v for k, v in env.items() if k.startswith("SPEAKER_B200_")}))
+        out, err = io.StringIO(), io.StringIO()
+        saved = {k: os.environ.get(k) for k in ("SPEAKER_B200_DEVICE",)}
+        os.environ["SPEAKER_B200_DEVICE"] = env["SPEAKER_B200_DEVICE"]
+        try:
+            with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+                self.returncode = assign_cli.main(cmd[3:])
+        finally:
+            for k, v in saved.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+        self._out, self._err = out.getvalue(), err.getvalue()
+
+    def communicate(self):
+        return self._out, self._err
+
+
+def test_assign_batch_gpus_splits_recordings_and_concatenates(store_with_recordings, capsys, monkeypatch):
+    import subprocess
+    root, manifest, ids = store_with_recordings
+    mpath = root / "manifest.json"
+    mpath.write_text(json.dumps([{"audio": it["audio"], "transcript": it["transcript"]} for it in manifest]))
+    assert assign_cli.main(["-q", "assign-batch", str(mpath), "--threshold", "0.2", "--format", "json", "--dry-run"]) == 0
+    single = json.loads(capsys.readouterr().out)
+    _InProcessWorker.real, _InProcessWorker.launched = subprocess.Popen, []
+    monkeypatch.setattr(subprocess, "Popen", _InProcessWorker)
+    assert assign_cli.main(["-q", "assign-batch", str(mpath), "--threshold", "0.2", "--format", "json", "--gpus", "3"]) == 0
+    multi = json.loads(capsys.readouterr().out)
+    strip = lambda o: {k: v for k, v in o.items() if k != "assigned_at"}
+    assert [strip(o) for o in multi] == [strip(o) for o in single]              # same answers, same order
+    devs = [env["SPEAKER_B200_DEVICE"] for _, env in _InProcessWorker.launched]
+    assert len(devs) >= 2 and devs == sorted(set(devs)) and all("SPEAKER_B200_WORLD" not in env for _, env in _InProcessWorker.launched)
+    assert len(list((root / "assignments").glob("*.yaml"))) == 4                # every worker wrote its recordings
+
+
+class _ShardContext(OracleContext):
+    """Two of these (world = 2) emulate the row-sharded library: local top-k on the shard, an in-process 'all-gather'
+    of the lists, the host mirror of the merge kernel."""
+    pool = {}
+
+    def __init__(self, device=0, world=1, rank=0, uid=None):
+        super().__init__()
+        self.world, self.rank = world, rank
+
+    def bank_load(self, rows, row_speaker, row_trust=None, dtype=_native.DTYPE_F32, global_row_offset=0):
+        super().bank_load(rows, row_speaker, row_trust, dtype, global_row_offset)
+        self.off = global_row_offset
+
+    def identify(self, seg, seg_label, L, pool=0, threshold=0.354, k=10):
+        import threading
+        from speaker_diarization_toolkit_b200 import sharding
+        lab = np.asarray(seg_label, np.int64)
+        goff = np.searchsorted(lab, np.arange(L + 1)).astype(np.int64)
+        if len(self.spk):
+            base = int(self.spk.min())
+            r, s, c = canonical.identify(np.asarray(seg, np.float32), goff, self.bank, self.spk - base, int(self.spk.max()) - base + 1,
+                                         mode=self.dtype, pool=pool, threshold=threshold, k=k)
+            r = np.where(r >= 0, r + self.off, r)
+        else:
+            r, s, c = np.full((L, k), -1, np.int64), np.zeros((L, k), np.float32), np.zeros(L, np.int32)
+        _ShardContext.pool[self.rank] = (r, s, c, self.trust, self.off)
+        _ShardContext.barrier.wait(timeout=60)
+        parts = [_ShardContext.pool[i] for i in range(self.world)]
+        self.rows, self.scores, self.counts, _ = sharding.merge_topk_lists(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]),
+                                                                           np.stack([p[2] for p in parts]), k)
+        self.gtrust = np.concatenate([p[3] for p in parts])
+        self.k = k
+        _ShardContext.barrier.wait(timeout=60)
+        return self.rows, self.scores, self.counts
+
+    def assign(self, assign_threshold=0.3, min_trust="low"):
+        t = np.full(self.rows.shape, 4, np.uint8)
+        ok = self.rows >= 0
+        t[ok] = self.gtrust[self.rows[ok]]
+        self.t = t
+        self.a = canonical.assign(self.rows, self.scores, t, self.counts, assign_threshold, _native.TRUST_CODES.get(min_trust, 99))
+
+
+def test_batch_matcher_row_sharded_world2_equals_single(store_with_recordings, monkeypatch):
+    import threading
+    root, manifest, ids = store_with_recordings
+    audios = [it["audio"] for it in manifest]
+    m1 = batch.BatchMatcher(threshold=0.354)
+    m1.load_bank()
+    want = m1.identify(audios, assign_threshold=0.2, min_trust="low")
+    monkeypatch.setattr(_native, "Context", _ShardContext)
+    _ShardContext.barrier, _ShardContext.pool = threading.Barrier(2), {}
+    got, errs = {}, []
+
+    def run(rank):
+        try:
+            m = batch.BatchMatcher(threshold=0.354, world=2, rank=rank, nccl_uid=b"x" * 128)
+            bank = m.load_bank()
+            assert m.ctx.off == ([0] + [p1 for _, p1 in __import__("speaker_diarization_toolkit_b200").sharding.shard_bank_rows(bank.row_speaker, 2)])[rank]
+            got[rank] = m.identify(audios, assign_threshold=0.2, min_trust="low")
+        except Exception as exc:       # pragma: no cover
+            errs.append(repr(exc))
+            _ShardContext.barrier.abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(120) for t in th]
+    assert not errs, errs
+    for rank in range(2):                       # every rank ends up with the global answer
+        assert [(r.labels, r.matches, r.mappings) for r in got[rank]] == [(r.labels, r.matches, r.mappings) for r in want]
+
+
+def test_sharded_context_from_env_publishes_the_unique_id(tmp_path, monkeypatch):
+    made = []
+    monkeypatch.setattr(_native, "Context", lambda *a: made.append(a) or "ctx")
+    monkeypatch.setattr(_native, "nccl_unique_id", lambda: bytes(range(128)))
+    assert batch.sharded_context_from_env(3)[:2] == (1, 0) and made[-1] == (3,)
+    monkeypatch.setenv("SPEAKER_B200_WORLD", "2")
+    with pytest.raises(ValueError):
+        batch.sharded_context_from_env(0)
+    monkeypatch.setenv("SPEAKER_B200_UID_FILE", str(tmp_path / "uid"))
+    monkeypatch.setenv("SPEAKER_B200_RANK", "0")
+    assert batch.sharded_context_from_env(0)[:2] == (2, 0) and made[-1] == (0, 2, 0, bytes(range(128)))
+    monkeypatch.setenv("SPEAKER_B200_RANK", "1")
+    assert batch.sharded_context_from_env(1)[:2] == (2, 1) and made[-1] == (1, 2, 1, bytes(range(128)))   # reads what rank 0 wrote
+    (tmp_path / "uid").unlink()
+    monkeypatch.setenv("SPEAKER_B200_UID_TIMEOUT", "0.1")
+    with pytest.raises(TimeoutError):
+        batch.sharded_context_from_env(1)
+
+
+def test_fp16_sidecar_and_long_labels_round_trip(tmp_path):
+    rng = np.random.default_rng(5)
+    emb = rng.standard_normal((6, 32)).astype(np.float32)
+    long_label = "speaker-" + "x" * 60                      # no 32-character cut (the reference has no label length limit)
+    labels = [long_label, "S1", long_label, "S1", "S2", "S2"]
+    audio = tmp_path / "a.wav"
+    store.save_segment_embeddings(audio, "b200", emb, labels, dtype=np.float16)
+    assert store.sidecar_segment_count(audio, "b200") == 6
+    got = store.load_segment_embeddings(audio, "b200")
+    assert got.emb.dtype == np.float16 and got.labels == sorted({long_label, "S1", "S2"})
+    order = np.argsort([got.labels.index(l) for l in labels], kind="stable")
+    assert np.array_equal(got.emb, emb.astype(np.float16)[order])
+    store.save_segment_embeddings(audio, "b200", emb, labels)
+    assert store.load_segment_embeddings(audio, "b200").emb.dtype == np.float32
+    with pytest.raises(ValueError):
+        store.save_segment_embeddings(audio, "b200", emb, labels, dtype=np.int8)

@@ -106,17 +106,16 @@ def test_verify_cli(cfg1_store):
     assert rc == 0 and "MATCH: Speaker 'alice' verified (confidence: 0." in out
 
 
-def test_assign_batch_equals_per_recording_assign(tmp_path, oracle):
-    """SURVEY 8f item 2: `assign-batch` (one resident backend call for all recordings, assignment on the device) writes
-    the same mappings as one `assign --use-embeddings` per recording."""
+def build_batch_store(tmp_path, n_rec=5):
+    """A store with 12 enrolled speakers (17 bank rows) and n_rec recordings; returns (manifest, manifest path, env)."""
     bank_case = synth.make_case(7, [1], 12, 192, rows_per_speaker=[1, 2, 1, 3, 1, 1, 2, 1, 1, 1, 2, 1], trust_cycle=(0, 0, 1, 2))
     ids = [f"spk{idx:04d}" for idx in range(12)]
-    manifest, singles = [], {}
+    manifest = []
     env = dict(os.environ, SPEAKERS_EMBEDDINGS_DIR=str(tmp_path), SPEAKER_DETECTION_BACKEND="b200", PYTHONPATH=str(ROOT))
     env.pop("SPEAKER_BACKENDS_CONFIG", None)
     from speaker_diarization_toolkit_b200.synth import Case
     rng = np.random.default_rng(3)
-    for r in range(5):
+    for r in range(n_rec):
         labels = [f"S{i + 1}" for i in range(2 + r % 3)]
         counts = rng.integers(3, 30, size=len(labels))
         rec = synth.make_case(100 + r, counts, 12, 192, truth=list(rng.integers(0, 12, size=len(labels))))
@@ -133,6 +132,18 @@ def test_assign_batch_equals_per_recording_assign(tmp_path, oracle):
         manifest.append({"audio": str(audio), "transcript": str(tpath)})
     mpath = tmp_path / "manifest.json"
     mpath.write_text(json.dumps(manifest))
+    return manifest, mpath, env
+
+
+def strip_time(outputs):
+    return [{k: v for k, v in o.items() if k != "assigned_at"} for o in outputs]
+
+
+def test_assign_batch_equals_per_recording_assign(tmp_path, oracle):
+    """SURVEY 8f item 2: `assign-batch` (one resident backend call for all recordings, assignment on the device) writes
+    the same mappings as one `assign --use-embeddings` per recording."""
+    manifest, mpath, env = build_batch_store(tmp_path)
+    singles = {}
     for item in manifest:
         rc, out, err = cli("speaker-assign", "-q", "assign", item["audio"], "-t", item["transcript"], "-e", "-n", "--format", "json",
                            "--threshold", "0.2", env=env)
@@ -147,6 +158,14 @@ def test_assign_batch_equals_per_recording_assign(tmp_path, oracle):
         assert b["mappings"] == singles[item["audio"]]
         n_assigned += sum(1 for m in b["mappings"].values() if m["speaker_id"])
     assert n_assigned >= 5
+    assert len(list((tmp_path / "assignments").glob("*.yaml"))) == 5
+    # `--gpus 3`: one worker process per GPU, the manifest split over them (workers share the device on a 1-GPU box);
+    # same output, same order, every recording written
+    for f in (tmp_path / "assignments").glob("*.yaml"):
+        f.unlink()
+    rc, out, err = cli("speaker-assign", "-q", "assign-batch", str(mpath), "--threshold", "0.2", "--format", "json", "--gpus", "3", env=env)
+    assert rc == 0, err
+    assert strip_time(json.loads(out)) == strip_time(batch)
     assert len(list((tmp_path / "assignments").glob("*.yaml"))) == 5
 
 

@@ -30,7 +30,7 @@ def test_abi_exports_every_declared_symbol():
     lib = _native.load()
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} not exported"
-    assert lib.sdk_abi_version() == 2
+    assert lib.sdk_abi_version() == 3
 
 
 def test_no_cpu_fallback():
@@ -231,7 +231,8 @@ def test_packed_bank_cache(tmp_path, monkeypatch):
     reads = []
     real_load = np.load
     monkeypatch.setattr(np, "load", lambda p, *a, **k: (reads.append(str(p)), real_load(p, *a, **k))[1])
-    assert same(store.build_bank_cached(cands, "b200"), plain) and reads == []   # warm: no .npy opened
+    assert same(store.build_bank_cached(cands, "b200"), plain)
+    assert [r for r in reads if r.endswith(".npy")] == []                    # warm: no vector file opened (only the binary index)
     # a changed vector is re-read (mtime/size), a new record is appended, a removed speaker disappears
     import os as _os, time as _time
     put("spk2", "emb-20", np.arange(16))
@@ -242,8 +243,52 @@ def test_packed_bank_cache(tmp_path, monkeypatch):
     got = store.build_bank_cached(cands2, "b200")
     monkeypatch.setattr(np, "load", real_load)
     assert same(got, store.build_bank(cands2, "b200"))
-    assert sorted(Path(r).name for r in reads) == ["emb-20.npy", "emb-90.npy"]
+    assert sorted(Path(r).name for r in reads if r.endswith(".npy")) == ["emb-20.npy", "emb-90.npy"]
     assert np.array_equal(got.rows[got.row_emb_id.index("emb-20")], np.arange(16, dtype=np.float32))
+
+
+def test_packed_bank_cache_trust_mode_and_dimension_change(tmp_path, monkeypatch):
+    """SPEAKER_B200_BANK_CACHE=trust takes pack rows by key without a stat() per file; a store re-enrolled at another
+    dimension gets its own pack instead of failing against the stale one; the index is a binary .npz."""
+    monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(tmp_path))
+    rng = np.random.default_rng(9)
+
+    def put(sid, eid, vec):
+        d = tmp_path / "embeddings" / sid
+        d.mkdir(parents=True, exist_ok=True)
+        np.save(d / f"{eid}.npy", np.asarray(vec, np.float32))
+
+    cands = []
+    for s in range(5):
+        put(f"spk{s}", f"e{s}", rng.standard_normal(8))
+        cands.append({"id": f"spk{s}", "embeddings": {"b200": [{"id": f"e{s}", "trust_level": "high"}]}})
+    plain = store.build_bank(cands, "b200")
+    assert np.array_equal(store.build_bank_cached(cands, "b200").rows, plain.rows)
+    assert (tmp_path / "embeddings" / ".bank-b200-D8.idx.npz").exists() and not list((tmp_path / "embeddings").glob("*.tmp*"))
+    monkeypatch.setenv("SPEAKER_B200_BANK_CACHE", "trust")
+    stats = []
+    real_stat = Path.stat
+    monkeypatch.setattr(Path, "stat", lambda self, **k: (stats.append(self.name), real_stat(self, **k))[1])
+    got = store.build_bank_cached(cands, "b200")
+    monkeypatch.setattr(Path, "stat", real_stat)
+    assert np.array_equal(got.rows, plain.rows) and got.speaker_ids == plain.speaker_ids
+    assert not [n for n in stats if n.endswith(".npy")]                       # no per-vector stat in trust mode
+    # a new speaker in trust mode: only that vector is read, the pack grows by one row
+    put("spk9", "e9", rng.standard_normal(8))
+    cands9 = cands + [{"id": "spk9", "embeddings": {"b200": [{"id": "e9"}]}}]
+    got = store.build_bank_cached(cands9, "b200")
+    assert np.array_equal(got.rows, store.build_bank(cands9, "b200").rows)
+    assert (tmp_path / "embeddings" / ".bank-b200-D8.f32").stat().st_size == 6 * 8 * 4
+    monkeypatch.delenv("SPEAKER_B200_BANK_CACHE")
+    assert np.array_equal(store.build_bank_cached(cands9, "b200").rows, got.rows)
+    # re-enrolled at D = 12: the D8 pack must not dictate the dimension
+    cands12 = []
+    for s in range(3):
+        put(f"spk{s}", f"e{s}", rng.standard_normal(12))
+        cands12.append({"id": f"spk{s}", "embeddings": {"b200": [{"id": f"e{s}"}]}})
+    got12 = store.build_bank_cached(cands12, "b200")
+    assert got12.rows.shape == (3, 12) and np.array_equal(got12.rows, store.build_bank(cands12, "b200").rows)
+    assert (tmp_path / "embeddings" / ".bank-b200-D12.f32").exists()
 
 
 # ---- enrollment / bank-writing path (SURVEY 8f item 3) ------------------------------------------------------------
