@@ -587,7 +587,7 @@ def parity_sample(torch, dist, ctx, cfg, seg, lab, counts_flat, bank_local, worl
 
 
 # ---- identify workloads (cfg2, cfg3, cfg4*) ----------------------------------------------------------------------------
-def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
+def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False, stage_a=None, e2e=True):
     """One workload on `world` ranks: data, warm-up, timed steps, roofline, e2e, CPU baseline, sampled parity.
     Returns the JSON line as a dict on rank 0 (None elsewhere)."""
     from speaker_diarization_toolkit_b200 import _native
@@ -611,6 +611,8 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
     ctx.set_option("cta_group", args.cta_group)
     ctx.set_option("acc", args.acc)
     ctx.set_option("kth", args.kth)
+    stage_a = stage_a or args.stage_a
+    ctx.set_option("poolfirst", 1 if stage_a == "poolfirst" else 0)
 
     # ---- data: bank (replicated, or this rank's row shard) + this rank's recordings ----
     R = counts.shape[0]
@@ -670,6 +672,9 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
             step_dev()
         ms = ctx.timer_stop()
     else:
+        # latency-bound shapes: the step is timed WITHOUT the per-kernel event pairs (two events per launch would be a
+        # third of a 50 us step); the kernel breakdown comes from a second, untimed round of the same steps
+        ctx.set_option("profile", 0)
         ms = 0.0
         for _ in range(args.steps):
             flush.zero_()
@@ -677,6 +682,13 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
             ctx.timer_start()
             step_dev()
             ms += ctx.timer_stop()
+        ctx.set_option("profile", 1)
+        ctx.profile_reset()
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            step_dev()
+        ctx.sync()
     barrier()
     clk = clocks.stop() if rank == 0 else None
     launches = ctx.launch_count() - l0
@@ -697,10 +709,24 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
         avg_ms = gms / max(1, gl)
         Dp4 = (D + 63) // 64 * 64
         ach = (P * Dp4 * 2 + N * Dp4 * 2) / (avg_ms * 1e-3) / 1e9
-        roof = {"kernel": "k_gemv8 (TMA ring + mma.sync m16n8k16, <= 8 query segments)", "bound": "hbm", "achieved": ach,
+        roof = {"kernel": "k_gemv8 (fused label offsets + normalise + TMA bank stream + mma.sync m16n8k16 + per-CTA top lists, <= 8 query segments)", "bound": "hbm", "achieved": ach,
                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
                 "peak_source": f"{pk_src} copy bandwidth", "algorithmic_bytes_per_bank_row": 2 * Dp4, "avg_launch_ms": avg_ms,
                 "share_of_step": gms / tot_prof}
+    elif path == 5:
+        # pool-first: a different algorithm (stage A contracts G centroids, not N segments): the step is HBM-bound on K1,
+        # which reads every raw segment once and writes its bf16 operand copy; algorithmic bytes = 4*D + 2*Dp per segment
+        gms, gl = prof["normalize"]
+        avg_ms = gms / max(1, gl // 1)
+        Dp5 = (D + 63) // 64 * 64
+        per_launch = N * (4 * D + 2 * Dp5) / max(1, gl // max(1, args.steps))
+        ach = per_launch / (avg_ms * 1e-3) / 1e9
+        roof = {"kernel": "k_normalize_centroid (K1 + label centroids; stage A = centroid GEMM)", "bound": "hbm", "achieved": ach,
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_src} copy bandwidth",
+                "algorithmic_bytes_per_segment": 4 * D + 2 * Dp5, "avg_launch_ms": avg_ms, "share_of_step": gms / tot_prof,
+                "whole_step_vs_hbm_floor": (N * 4 * D / (pk["hbm_gbs"] * 1e9)) / (1e-3 * ms_max / args.steps),
+                "contracted_pairs_per_step": float(2 * G) * P,
+                "note": "pairs/s below counts the segment x profile pairs of the WORKLOAD (what the step answers for), not pairs contracted"}
     elif path >= 2:
         gms, gl = prof["poolgemm"]
         per_launch_flops = 2.0 * pairs_rank * D / max(1, gl // max(1, args.steps))   # flops per launch = 2*D per pair
@@ -749,7 +775,7 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
     # 2*D bytes per segment over PCIe; `e2e_f32` is the same call on fp32 host embeddings (4*D bytes per segment).
     # Each rank's pinned buffers are allocated while the process is bound to the CPUs of ITS GPU's NUMA node.
     e2e, e2e_f32, par_e2e = None, None, None
-    if not args.no_e2e:
+    if not args.no_e2e and e2e:
         import psutil
         numa = bind_to_gpu_numa_node(torch, local_rank)
 
@@ -831,9 +857,9 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False):
                 "dtype": "bf16" if cfg["dtype"] else "f32", "data": "synthetic",
                 "config": {"workload": cfg["desc"], "segments_total": int(pairs_total / (P * (world if sharded else 1))),
                            "segments_per_gpu": N, "label_groups_per_gpu": G, "bank_rows_per_gpu": P, "dim": D, "k": cfg["k"],
-                           "threshold": cfg["thr"], "pool": args.pool, "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
+                           "threshold": cfg["thr"], "pool": args.pool, "stage_a": stage_a, "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
                            "l2": "working set larger than 2x L2 (no flush needed)" if flush is None else "256 MB flush buffer written between timed iterations",
-                           "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{args.cta_group}", 3: "tcgen05 accumulate-pooling", 4: "bank-stream gemv"}.get(path, str(path)), "certificate_fallback_groups": nfb, "certificate_retry_groups": nretry, "scale": args.scale},
+                           "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{args.cta_group}", 3: "tcgen05 accumulate-pooling", 4: "bank-stream gemv", 5: "pool-first (label centroids x bank on tcgen05, then the canonical re-score)"}.get(path, str(path)), "certificate_fallback_groups": nfb, "certificate_retry_groups": nretry, "scale": args.scale},
                 "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_f32": e2e_f32,
                 "parity_sample": par, "parity_sample_e2e": par_e2e, "certificate": cert,
                 "time_to_solution_ms": ms_max / args.steps,
@@ -873,6 +899,9 @@ def main():
     ap.add_argument("--cta-group", type=int, default=1, choices=[1, 2], help="tcgen05 kernel variant (2 = CTA pairs)")
     ap.add_argument("--acc", type=int, default=1, choices=[0, 1, 2], help="accumulate-pooling kernel: 0 off, 1 auto, 2 force (A/B runs)")
     ap.add_argument("--kth", type=int, default=1, choices=[0, 1, 2], help="running k-th best pruning of the candidate flush: 0 off, 1 auto, 2 on (A/B runs)")
+    ap.add_argument("--stage-a", default="contraction", choices=["contraction", "poolfirst"],
+                    help="poolfirst: stage A contracts the label centroids (mean pooling only; a different algorithm, HBM-bound)")
+    ap.add_argument("--no-poolfirst", action="store_true", help="do not append the pool-first sub-record to the default workload's line")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-dtype", default="both", choices=["f16", "f32", "both"],
                     help="storage type of the host segment embeddings in the e2e leg (f16 = compact sidecar form, the headline; both = also e2e_f32)")
@@ -913,6 +942,16 @@ def main():
         sub = run_identify(args, "cfg4", torch, dist, world, rank, local_rank, sub=True)
         if rank == 0:
             line["sharded"] = sharded_subrecord(sub)
+    # ... and, for mean pooling, by the same workload with the pool-first stage A: a DIFFERENT algorithm, reported
+    # beside the contraction as time to solution against the HBM roofline -- never as the headline pairs/s
+    if args.workload == "cfg3" and args.pool == "mean" and args.stage_a == "contraction" and not args.no_poolfirst:
+        pf = run_identify(args, "cfg3", torch, dist, world, rank, local_rank, sub=True, stage_a="poolfirst", e2e=False)
+        if rank == 0:
+            line["pool_first"] = {"algorithm": "stage A contracts the label centroids (mean pooling is linear); stage B re-scores the candidates over all segments in the canonical arithmetic",
+                                  "time_to_solution_ms": pf["ms_per_step"], "contraction_time_to_solution_ms": line["ms_per_step"],
+                                  "workload_pairs_per_s": pf["value"], "roofline": pf["roofline"], "parity_sample": pf["parity_sample"],
+                                  "certificate": pf["certificate"], "kernel_ms_per_step": pf["kernel_ms_per_step"], "clocks": pf["clocks"],
+                                  "gpu_launches": pf["gpu_launches"], "path": pf["config"]["path"]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -84,6 +84,8 @@ const char* sdk_last_error(sdk_ctx* ctx);
  * "cta_group" (1 | 2: tcgen05 kernel variant), "acc" (0 off | 1 auto | 2 force: pool inside the MMA accumulation),
  * "gemv" (1 = stream the bank on the CUDA cores when there are <= 8 query segments),
  * "kth" (0 off | 1 auto | 2 on: candidate flush prunes against a running per-label bound on the 64th best score),
+ * "poolfirst" (0 | 1: mean pooling on the tensor path contracts the label CENTROIDS in stage A -- a different algorithm,
+ *  N/L times fewer flops, HBM-bound; results are identical because stage B re-scores in the canonical arithmetic),
  * "inject_fail" (test knob: the next local identify pass returns SDK_EINVAL after its first kernels) */
 int sdk_set_option(sdk_ctx* ctx, const char* key, double value);
 
@@ -118,7 +120,11 @@ int sdk_identify(sdk_ctx* ctx, const float* seg, const int32_t* seg_label, int64
  * (vector normalise, accumulate-pooling) are taken only when d_seg is 16-byte aligned and D % 4 == 0.
  * Row-sharded mode (world > 1): every rank must make the same sequence of identify calls (same L and k); a rank whose
  * local pass fails still joins the all-gather (empty lists + a status word), returns its own error, and its peers get
- * SDK_EPEER from sdk_results_fetch. */
+ * SDK_EPEER from sdk_results_fetch.
+ * Small-query calls (<= 8 segments against a big bank, the bank-stream path) return with their two kernels queued and no
+ * host round trip: label errors of such a call, and the exhaustive pass for labels whose top-k certificate failed, are
+ * settled by the next sdk_results_fetch / sdk_last_path / sdk_stage_a_fetch (world == 1; a row-sharded context settles
+ * before its all-gather). */
 int sdk_identify_dev(sdk_ctx* ctx, const float* d_seg, const int32_t* d_seg_label, int64_t N,
                      int32_t L, int32_t pool, double threshold, int32_t k);
 
@@ -180,7 +186,8 @@ int sdk_profile_reset(sdk_ctx* ctx);
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 int64_t sdk_launch_count(sdk_ctx* ctx);
 /* which path the last identify took: 1 exact SIMT, 2 tcgen05 (pooling in the epilogue), 3 tcgen05 accumulate-pooling
- * (mean pooling inside the MMA accumulation), 4 bank-stream GEMV (<= 8 query segments); *n_fallback = label groups whose
+ * (mean pooling inside the MMA accumulation), 4 bank-stream GEMV (<= 8 query segments), 5 pool-first (centroid stage A);
+ * *n_fallback = label groups whose
  * top-k certificate failed and were re-done exhaustively */
 int sdk_last_path(sdk_ctx* ctx, int32_t* path, int64_t* n_fallback);
 /* Diagnostics of the certified top-k (tests, bench.py): after an identify that took path 2-4 on ONE chunk, the

@@ -89,7 +89,7 @@ class BatchMatcher:
         self.ctx.close()
 
     def load_bank(self, tags: Optional[str] = None, use_cache: bool = True) -> store.Bank:
-        speakers = store.list_all_speakers()
+        speakers = store.list_all_speakers_cached()
         if tags:
             speakers = store.filter_speakers_by_tags(speakers, [t.strip() for t in tags.split(",")], any_tag=False)
         candidates = [s for s in speakers if s.get("embeddings", {}).get(self.backend_name)]

@@ -160,7 +160,8 @@ void sdk_destroy(sdk_ctx* c) {
                        &c->cand_val, &c->cand_cnt, &c->gbound, &c->slot_cnt, &c->slot_row, &c->slot_val,
                        &c->slot_bound, &c->range_g, &c->kth, &c->fb_list, &c->fb_rows, &c->out_pack, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
                        &c->stage_lab[0], &c->stage_lab[1], &c->pa_hist, &c->pa_sorted, &c->pa_pos, &c->pa_col_group,
-                       &c->pa_col_meta, &c->pa_blockT, &c->pa_step0, &c->pa_grp, &c->pa_col_last, &c->seg_il, &c->fb_list2, &c->cand_row2, &c->qpool2};
+                       &c->pa_col_meta, &c->pa_blockT, &c->pa_step0, &c->pa_grp, &c->pa_col_last, &c->seg_il, &c->fb_list2, &c->cand_row2, &c->qpool2,
+                       &c->cent_sum, &c->cent_seg, &c->goff2};
     for (sdk_buf* b : bufs) sdk_release(*b);
     if (c->h_pack) cudaFreeHost(c->h_pack);
     for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -207,6 +208,9 @@ int sdk_set_option(sdk_ctx* c, const char* key, double value) {
     } else if (k == "kth") {
         if (value != 0 && value != 1 && value != 2) return sdk_fail(c, SDK_EINVAL, "kth must be 0 (off), 1 (auto) or 2 (on)");
         c->opt_kth = (int)value;
+    } else if (k == "poolfirst") {
+        if (value != 0 && value != 1) return sdk_fail(c, SDK_EINVAL, "poolfirst must be 0 or 1");
+        c->opt_poolfirst = (int)value;
     } else if (k == "inject_fail") {
         c->opt_inject_fail = value != 0;          // test knob: the next local identify pass fails after its first kernels
     } else return sdk_fail(c, SDK_EINVAL, "unknown option " + k);
@@ -306,7 +310,8 @@ static int sdk_check_flags(sdk_ctx* c, const int32_t* d_flags) {   // after a st
 
 static int sdk_allgather_merge(sdk_ctx* c, int32_t L, int32_t k);
 static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L,
-                             int32_t label_base, int32_t pool, double threshold, int32_t k);
+                             int32_t label_base, int32_t pool, double threshold, int32_t k, bool allow_lazy);
+static int sdk_settle(sdk_ctx* c, const int32_t* known_flags = nullptr);
 
 static int sdk_check_identify_args(sdk_ctx* c, const void* seg, const void* lab, int64_t N, int32_t L, int32_t pool,
                                    double threshold, int32_t k) {
@@ -359,8 +364,59 @@ static int sdk_reserve_results(sdk_ctx* c, int32_t L, int32_t k) {
 // One pass of the hot path over the label groups [label_base, label_base + L): segments d_seg (N rows) carry
 // GLOBAL label ids; results land at group offset label_base of the context's result arrays.  The raw rows are fp32 or
 // fp16 (c->in_dtype, set by the entry point).
+// Label groups whose top-k certificate failed are re-done exhaustively in the canonical arithmetic (rows of `fb`).
+static int sdk_exhaustive_fallback(sdk_ctx* c, const int32_t* fb, int32_t nfb, const void* seg_ops, const PaGroup* seg_grp, int32_t pool,
+                                   double threshold, int32_t k, int64_t* o_row, float* o_score, int32_t* o_count, uint8_t* o_trust, int32_t* o_spk) {
+    const bool bf16 = c->dtype == SDK_DTYPE_BF16;
+    const int64_t P = c->P;
+    const void* bank_ops = bf16 ? c->bank_bf16.p : c->bank_f32.p;
+    const int32_t pitch = bf16 ? c->Dp : c->D;
+    const int32_t chunk = (int32_t)std::max<int64_t>(1, std::min<int64_t>(nfb, (int64_t)(1u << 28) / std::max<int64_t>(P, 1)));
+    for (int32_t done = 0; done < nfb; done += chunk) {
+        int32_t m = std::min(chunk, nfb - done);
+        SDK_TRY(sdk_reserve(c, c->dense, (size_t)m * P * 8));
+        const int32_t* gl = fb + done;
+        SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, c->D, pitch, (const int64_t*)c->goff.p, gl, m, nullptr, P,
+                                 pool, (long long*)c->dense.p, seg_grp));
+        SDK_TRY(sdk_launch_select(c, (const long long*)c->dense.p, (const int64_t*)c->goff.p, gl, m, nullptr, P, pool,
+                                  (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
+                                  c->row_offset, nullptr, 0.f, 0.f, nullptr, 0, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
+    }
+    return SDK_OK;
+}
+
+// The small-query path (gemv.cu) does not stop for its certificate: the identify call returns with the kernels queued,
+// and whoever looks at the results next (fetch, last_path, stage_a, the all-gather) settles the open questions first --
+// the label flags, and the exhaustive pass for the (rare) labels on the fall-back list.  `known_flags`: the flag words
+// if the caller has just read them (the small-record fetch reads the whole record in one copy).
+static int sdk_settle(sdk_ctx* c, const int32_t* known_flags) {
+    if (!c->lazy.active) return SDK_OK;
+    c->lazy.active = false;
+    int32_t hf[2] = {0, 0};
+    if (known_flags) { hf[0] = known_flags[SDK_FLAG_LABEL]; hf[1] = known_flags[SDK_FLAG_FB]; }
+    else {
+        SDK_CUDA(c, cudaMemcpyAsync(hf, c->out.flags, 8, cudaMemcpyDeviceToHost, c->stream));
+        SDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    if (hf[0] & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
+    if (hf[0] & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
+    const int32_t nfb = hf[1];
+    if (nfb <= 0) return SDK_OK;
+    const sdk_lazy& z = c->lazy;
+    c->last_fallback += nfb;
+    SDK_TRY(sdk_exhaustive_fallback(c, (const int32_t*)c->fb_list.p, nfb, z.seg_ops, nullptr, z.pool, z.threshold, z.k, z.o_row, z.o_score,
+                                    z.o_count, z.o_trust, z.o_spk));
+    SDK_CUDA(c, cudaMemsetAsync(c->out.flags + SDK_FLAG_FB, 0, 4, c->stream));
+    if (c->have_assign) {                                  // the assignment was computed from the unsettled lists: redo it
+        const sdk_out_view& v = c->out;
+        SDK_TRY(sdk_launch_assign(c, v.row, v.score, v.trust, v.count, c->L, c->k, c->assign_thr, c->assign_min_trust, v.as_idx,
+                                  v.as_score, v.as_conf, v.as_cidx, v.as_cscore));
+    }
+    return SDK_OK;
+}
+
 static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L,
-                             int32_t label_base, int32_t pool, double threshold, int32_t k) {
+                             int32_t label_base, int32_t pool, double threshold, int32_t k, bool allow_lazy) {
     const int32_t D = c->D, Dp = c->Dp;
     const int64_t P = c->P;
     const bool bf16 = c->dtype == SDK_DTYPE_BF16;
@@ -370,14 +426,7 @@ static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg
     uint8_t* o_trust = c->out.trust + (size_t)label_base * k;
     int32_t* o_spk = c->out.spk + (size_t)label_base * k;
 
-    SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
     int32_t* d_flags = c->out.flags;
-    SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, label_base, (int64_t*)c->goff.p, d_flags));
-    if (c->opt_inject_fail) {
-        c->opt_inject_fail = 0;
-        return sdk_fail(c, SDK_EINVAL, "injected failure (option inject_fail)");
-    }
-
     // path choice: tcgen05 only where the contraction is big enough to be a real dense GEMM
     const double macs = (double)N * (double)P * (double)Dp;
     int path = c->opt_path;
@@ -398,7 +447,38 @@ static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg
     // a handful of query segments: one HBM-bound pass over the bank on the CUDA cores (gemv.cu)
     // (its candidate slots are indexed by label id: a handful of segments scattered over very many labels stays generic)
     const bool use_gemv = path == 2 && c->opt_gemv && sdk_gemv_applicable(N, Dp) && L <= 64;
-    bool use_acc = path == 2 && !use_gemv && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048 &&
+    if (use_gemv && !c->opt_inject_fail) {
+        // the small-query latency path: two kernels (label offsets, normalise, bank stream, per-CTA top lists | merge,
+        // canonical re-score, select, certificate), no host round trip inside the call
+        c->last_path = 4;
+        const float kc = (float)(Dp / 16);
+        float eps = (bf16 ? 0.f : 1.2e-2f) + 1.05f * 7.15255737e-07f * kc + 4.8e-7f;      // margin model: see the tensor path below
+        if (c->opt_eps >= 0) eps = (float)c->opt_eps;
+        int ncand = std::min(64, std::max(c->opt_cand, k + 6));
+        float tau = (float)(threshold - 2.0 * (double)eps);
+        if (!(tau > -3.0e38f)) tau = -3.0e38f;
+        c->last_eps_base = eps;
+        c->last_eps_chain = 0.f;
+        c->last_ncand = ncand;
+        c->last_cand_groups = L;
+        c->kth_on = false;
+        SDK_TRY(sdk_launch_gemv_identify(c, d_seg, c->in_dtype, d_seg_label, label_base, N, L, pool, threshold, k, tau, eps, ncand, d_flags,
+                                         o_row, o_score, o_count, o_trust, o_spk));
+        sdk_lazy& z = c->lazy;
+        z.active = true;
+        z.seg_ops = bf16 ? c->seg_bf16.p : c->seg_f32.p;
+        z.pool = pool; z.threshold = threshold; z.k = k;
+        z.o_row = o_row; z.o_score = o_score; z.o_count = o_count; z.o_trust = o_trust; z.o_spk = o_spk;
+        if (!allow_lazy) SDK_TRY(sdk_settle(c));
+        return SDK_OK;
+    }
+    SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
+    SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, label_base, (int64_t*)c->goff.p, d_flags));
+    if (c->opt_inject_fail) {
+        c->opt_inject_fail = 0;
+        return sdk_fail(c, SDK_EINVAL, "injected failure (option inject_fail)");
+    }
+    bool use_acc = path == 2 && c->opt_acc && sdk_poolacc_applicable(Dp, L, pool) && D % 4 == 0 && D <= 2048 &&
                    (uintptr_t)d_seg % (c->in_dtype == SDK_IN_F16 ? 8 : 16) == 0;     // its scatter-normalise reads the raw rows with 128-bit (fp16: 64-bit) loads
     if (use_acc && c->opt_acc != 2 && !(Dp <= 256 || L > 2048)) use_acc = false;
     int64_t acc_steps = 0;
@@ -409,16 +489,27 @@ static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg
         if (lf & 1) return sdk_fail(c, SDK_EINVAL, "seg_label out of range [0,L)");
         if (lf & 2) return sdk_fail(c, SDK_EINVAL, "seg_label must be non-decreasing (segments sorted by label group)");
     }
+    // pool-first (option "poolfirst", mean pooling): stage A contracts the label centroids instead of the segments -- a
+    // different algorithm (N/L times fewer flops, HBM-bound on K1); stage B and the certificate are unchanged
+    const bool use_pf = path == 2 && c->opt_poolfirst && pool == SDK_POOL_MEAN && N > 0 && sdk_poolfirst_applicable(d_seg, c->in_dtype, D, Dp);
+    if (use_pf) use_acc = false;
     if (use_acc) {
         SDK_TRY(sdk_poolacc_plan(c, (const int64_t*)c->goff.p, L, N, P, Dp, &acc_steps));
         if (c->opt_acc != 2 && (double)acc_steps * 256.0 > 1.12 * (double)N + 1024.0) use_acc = false;   // acc == 2 forces it (tests)
     }
     if (use_acc) c->last_path = 3;
-    if (use_gemv) c->last_path = 4;
+    if (use_pf) c->last_path = 5;
     const bool need_bf16 = (bf16 || path == 2) && !use_acc;
     if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
     if (need_bf16) SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
-    if (!bf16 || need_bf16)
+    if (use_pf) {
+        SDK_TRY(sdk_reserve(c, c->cent_sum, (size_t)L * Dp * 4));
+        SDK_TRY(sdk_reserve(c, c->cent_seg, (size_t)2 * L * Dp * 2));
+        SDK_TRY(sdk_reserve(c, c->goff2, (size_t)(L + 1) * 8));
+        SDK_TRY(sdk_launch_normalize_centroid(c, d_seg, c->in_dtype, d_seg_label, label_base, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
+                                              (__nv_bfloat16*)c->seg_bf16.p, (const int64_t*)c->goff.p, L, (float*)c->cent_sum.p,
+                                              (__nv_bfloat16*)c->cent_seg.p, (int64_t*)c->goff2.p, bf16 ? 1 : 0));
+    } else if (!bf16 || need_bf16)
         SDK_TRY(sdk_launch_normalize_in(c, d_seg, c->in_dtype, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
                                         need_bf16 ? (__nv_bfloat16*)c->seg_bf16.p : nullptr));
     const void* bank_ops = bf16 ? c->bank_bf16.p : c->bank_f32.p;
@@ -452,7 +543,16 @@ static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg
         int32_t chain_div = 0;
         double chain_max = 0.0;
         if (use_acc) { eps_chain = 0.5f * 1.05f * u_mma * kc; chain_max = (double)c->pa_chain_max; }
-        else if (pool == SDK_POOL_MEAN && !use_gemv) { eps_chain = 6.1e-8f; chain_div = 32; chain_max = (double)(N / 32 + 70); }
+        else if (use_pf) {
+            // pool-first: |<hi + lo, b> computed - canonical pooled score| <=  two dot products at operand magnitude 2 (the
+            // doubled halves), the epilogue mean of the two columns (70 * 6.1e-8), the hi/lo split residual (2^-18), the fp32
+            // centroid (64 register adds: 64 * 2^-24; n/64 atomic adds: 2^-24/64 per segment -> eps_chain), Q30 rounding
+            eps_base = (bf16 ? 0.f : 1.2e-2f) + 2.1f * u_mma * kc + 4.3e-6f + 3.9e-6f + 4.1e-6f + 4.8e-7f;
+            eps_chain = 9.4e-10f;
+            chain_div = 1;
+            chain_max = (double)(N + 70);
+        }
+        else if (pool == SDK_POOL_MEAN) { eps_chain = 6.1e-8f; chain_div = 32; chain_max = (double)(N / 32 + 70); }
         if (c->opt_eps >= 0) { eps_base = (float)c->opt_eps; eps_chain = 0.f; }       // test knob: fixed margin
         const float eps = eps_base + eps_chain * (float)chain_max;                     // launch-wide (candidate threshold tau)
         c->last_eps_base = eps_base;
@@ -479,10 +579,10 @@ static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg
                                        (float*)c->gbound.p, nullptr, c->seg_bf16, &ig));
             if (bf16) seg_grp = ig;                            // bf16 operands live in the interleaved matrix
             acc_grp = ig;
-        } else if (use_gemv) {
-            SDK_TRY(sdk_launch_gemv_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p, N, Dp,
-                                               (const int64_t*)c->goff.p, L, pool, tau, ncand, (int32_t*)c->cand_row.p,
-                                               (float*)c->gbound.p));
+        } else if (use_pf) {
+            SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->cent_seg.p,
+                                                   2 * (int64_t)L, Dp, (const int64_t*)c->goff2.p, L, SDK_POOL_MEAN, tau, ncand,
+                                                   (int32_t*)c->cand_row.p, (float*)c->gbound.p));
         } else {
             SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p,
                                                    N, Dp, (const int64_t*)c->goff.p, L, pool, tau, ncand,
@@ -529,17 +629,7 @@ static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg
             fb = (const int32_t*)c->fb_list2.p;
         }
         c->last_fallback += nfb;
-        const int32_t chunk = (int32_t)std::max<int64_t>(1, std::min<int64_t>(nfb, (int64_t)(1u << 28) / std::max<int64_t>(P, 1)));
-        for (int32_t done = 0; done < nfb; done += chunk) {
-            int32_t m = std::min(chunk, nfb - done);
-            SDK_TRY(sdk_reserve(c, c->dense, (size_t)m * P * 8));
-            const int32_t* gl = fb + done;
-            SDK_TRY(sdk_launch_exact(c, seg_ops, bank_ops, bf16, D, pitch, (const int64_t*)c->goff.p, gl, m, nullptr, P,
-                                     pool, (long long*)c->dense.p, seg_grp));
-            SDK_TRY(sdk_launch_select(c, (const long long*)c->dense.p, (const int64_t*)c->goff.p, gl, m, nullptr, P, pool,
-                                      (const int32_t*)c->row_speaker.p, (const uint8_t*)c->row_trust.p, threshold, k,
-                                      c->row_offset, nullptr, 0.f, 0.f, nullptr, 0, nullptr, nullptr, o_row, o_score, o_count, o_trust, o_spk));
-        }
+        SDK_TRY(sdk_exhaustive_fallback(c, fb, nfb, seg_ops, seg_grp, pool, threshold, k, o_row, o_score, o_count, o_trust, o_spk));
         SDK_CUDA(c, cudaMemsetAsync(d_flags + 1, 0, 4, c->stream));   // fallback counter consumed
     }
     return SDK_OK;
@@ -547,7 +637,7 @@ static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg
 
 // An empty shard (P == 0) has nothing to score: its lists are empty, and it still joins the collective.
 static int sdk_identify_any(sdk_ctx* c, const void* d_seg, const int32_t* d_seg_label, int64_t N, int32_t L, int32_t label_base,
-                            int32_t pool, double threshold, int32_t k) {
+                            int32_t pool, double threshold, int32_t k, bool allow_lazy = false) {
     if (c->P == 0) {
         SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
         SDK_TRY(sdk_launch_group_offsets(c, d_seg_label, N, L, label_base, (int64_t*)c->goff.p, c->out.flags));   // labels are still validated
@@ -557,7 +647,7 @@ static int sdk_identify_any(sdk_ctx* c, const void* d_seg, const int32_t* d_seg_
         c->last_path = 0;
         return sdk_launch_fill_empty(c, v, L, k);
     }
-    return sdk_identify_core(c, d_seg, d_seg_label, N, L, label_base, pool, threshold, k);
+    return sdk_identify_core(c, d_seg, d_seg_label, N, L, label_base, pool, threshold, k, allow_lazy);
 }
 
 // Row-sharded mode: every rank MUST enter the all-gather once per identify call, or its peers block forever.  A rank
@@ -592,10 +682,11 @@ static int sdk_identify_dev_in(sdk_ctx* c, const void* d_seg, int32_t in_dtype, 
     c->in_dtype = in_dtype;
     c->have_results = false;
     c->have_assign = false;
+    c->lazy.active = false;                                // whatever the previous call left open is void now
     c->last_fallback = 0;
     c->last_retry = 0;
     int r = sdk_reserve_results(c, L, k);
-    if (r == SDK_OK) r = sdk_identify_any(c, d_seg, d_seg_label, N, L, 0, pool, threshold, k);
+    if (r == SDK_OK) r = sdk_identify_any(c, d_seg, d_seg_label, N, L, 0, pool, threshold, k, /*allow_lazy=*/c->world == 1);
     c->L = L; c->k = k; c->N = N;
     SDK_TRY(sdk_finish_collective(c, L, k, r));
     c->have_results = true;
@@ -633,6 +724,7 @@ int sdk_merge_topk(sdk_ctx* c, int32_t world, int32_t L, int32_t k, const int64_
     cudaSetDevice(c->device);
     c->have_results = false;
     c->have_assign = false;
+    c->lazy.active = false;
     SDK_TRY(sdk_reserve_results(c, L, k));
     const sdk_out_view& v = c->out;
     const size_t rec = v.gather_bytes, n = (size_t)L * k;
@@ -675,7 +767,7 @@ static int sdk_identify_host_body(sdk_ctx* c, const void* seg_v, const int32_t* 
             SDK_CUDA(c, cudaMemcpyAsync(c->seg_raw.p, seg, (size_t)N * row_bytes, cudaMemcpyHostToDevice, c->stream));
             SDK_CUDA(c, cudaMemcpyAsync(c->seg_lab.p, seg_label, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
         }
-        SDK_TRY(sdk_identify_any(c, c->seg_raw.p, (const int32_t*)c->seg_lab.p, N, L, 0, pool, threshold, k));
+        SDK_TRY(sdk_identify_any(c, c->seg_raw.p, (const int32_t*)c->seg_lab.p, N, L, 0, pool, threshold, k, /*allow_lazy=*/c->world == 1));
     } else {
         // chunk cut points: first label change at or after each multiple of chunk_rows
         for (int64_t i = 1; i < N; ++i)
@@ -737,6 +829,7 @@ static int sdk_identify_in(sdk_ctx* c, const void* seg, int32_t in_dtype, const 
     c->in_dtype = in_dtype;
     c->have_results = false;
     c->have_assign = false;
+    c->lazy.active = false;
     c->last_fallback = 0;
     c->last_retry = 0;
     int r = sdk_reserve_results(c, L, k);
@@ -763,6 +856,8 @@ int sdk_assign(sdk_ctx* c, double assign_threshold, int32_t min_trust_code) {
     const sdk_out_view& v = c->out;
     SDK_TRY(sdk_launch_assign(c, v.row, v.score, v.trust, v.count, L, k, assign_threshold, min_trust_code, v.as_idx,
                               v.as_score, v.as_conf, v.as_cidx, v.as_cscore));
+    c->assign_thr = assign_threshold;                      // (a pending small-query certificate may make sdk_settle redo this)
+    c->assign_min_trust = min_trust_code;
     c->have_assign = true;
     return SDK_OK;
 }
@@ -794,6 +889,15 @@ int sdk_results_fetch(sdk_ctx* c, int64_t* out_row, float* out_score, int32_t* o
         }
         SDK_CUDA(c, cudaMemcpyAsync(c->h_pack, c->out_pack.p, need, cudaMemcpyDeviceToHost, s));
         SDK_CUDA(c, cudaStreamSynchronize(s));
+        if (c->lazy.active) {
+            // small-query path: the record just read carries the flags; only a failed certificate costs a second copy
+            const bool redo = ((const int32_t*)c->h_pack)[SDK_FLAG_FB] > 0;
+            SDK_TRY(sdk_settle(c, (const int32_t*)c->h_pack));
+            if (redo) {
+                SDK_CUDA(c, cudaMemcpyAsync(c->h_pack, c->out_pack.p, need, cudaMemcpyDeviceToHost, s));
+                SDK_CUDA(c, cudaStreamSynchronize(s));
+            }
+        }
         const char* h = (const char*)c->h_pack;
         SDK_TRY(sdk_flag_error(c, (const int32_t*)h));
         if (out_row) memcpy(out_row, h + v.off_row, n * 8);
@@ -807,6 +911,7 @@ int sdk_results_fetch(sdk_ctx* c, int64_t* out_row, float* out_score, int32_t* o
         if (cand_score) memcpy(cand_score, h + v.off_as_cscore, L * 24);
         return SDK_OK;
     }
+    SDK_TRY(sdk_settle(c));
     if (out_row) SDK_CUDA(c, cudaMemcpyAsync(out_row, v.row, n * 8, cudaMemcpyDeviceToHost, s));
     if (out_score) SDK_CUDA(c, cudaMemcpyAsync(out_score, v.score, n * 4, cudaMemcpyDeviceToHost, s));
     if (out_count) SDK_CUDA(c, cudaMemcpyAsync(out_count, v.count, L * 4, cudaMemcpyDeviceToHost, s));
@@ -988,6 +1093,7 @@ int64_t sdk_launch_count(sdk_ctx* c) { return c ? c->launches : 0; }
 int sdk_stage_a_fetch(sdk_ctx* c, int32_t* rows, float* approx, int64_t cap, int32_t* ncand, float* eps_base, float* eps_chain) {
     if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
     if (!c->have_results || c->last_ncand <= 0) return sdk_fail(c, SDK_ESTATE, "no stage-A lists: the last identify did not take a tensor / bank-stream path");
+    SDK_TRY(sdk_settle(c));
     const int64_t n = (int64_t)c->last_cand_groups * c->last_ncand;
     if (ncand) *ncand = c->last_ncand;
     if (eps_base) *eps_base = c->last_eps_base;
@@ -1004,6 +1110,7 @@ int sdk_stage_a_fetch(sdk_ctx* c, int32_t* rows, float* approx, int64_t cap, int
 int64_t sdk_last_retry(sdk_ctx* c) { return c ? c->last_retry : 0; }
 int sdk_last_path(sdk_ctx* c, int32_t* path, int64_t* n_fallback) {
     if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    SDK_TRY(sdk_settle(c));                                // the fall-back count of a small-query call is known only now
     if (path) *path = c->last_path;
     if (n_fallback) *n_fallback = c->last_fallback;
     return SDK_OK;

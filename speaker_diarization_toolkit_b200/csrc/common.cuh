@@ -59,6 +59,19 @@ struct sdk_out_view {
     size_t off_as_score = 0, off_as_cscore = 0, off_as_idx = 0, off_as_conf = 0, off_as_cidx = 0, bytes = 0;
 };
 
+// What the small-query path (gemv.cu) leaves open when its identify call returns: see sdk_settle (api.cu).
+struct sdk_lazy {
+    bool active = false;
+    const void* seg_ops = nullptr;
+    int32_t pool = 0, k = 0;
+    double threshold = 0.0;
+    int64_t* o_row = nullptr;
+    float* o_score = nullptr;
+    int32_t* o_count = nullptr;
+    uint8_t* o_trust = nullptr;
+    int32_t* o_spk = nullptr;
+};
+
 struct sdk_ctx {
     int device = 0, world = 1, rank = 0;
     cudaStream_t stream = nullptr;
@@ -75,6 +88,7 @@ struct sdk_ctx {
     int opt_gemv = 1;          // <= 8 query segments: stream the bank once on the CUDA cores (gemv.cu) instead of tcgen05 tiles
     int opt_chunk_mb = 128;    // host-buffer identify: H2D/compute pipeline chunk size
     int opt_kth = 1;           // candidate flush prunes against a running per-label 64th-best bound: 0 off, 1 auto (low thresholds), 2 on
+    int opt_poolfirst = 0;     // mean pooling on the tensor path: stage A contracts the label CENTROIDS (a different algorithm: HBM-bound)
     int opt_inject_fail = 0;   // test knob (multi-rank error handling): fail the next local identify pass
     // bank
     int64_t P = 0;
@@ -86,6 +100,7 @@ struct sdk_ctx {
     sdk_buf seg_raw, seg_lab, seg_f32, seg_bf16, goff, qpool, dense, flags;
     sdk_buf cand_row, cand_val, cand_cnt, gbound, slot_cnt, slot_row, slot_val, slot_bound, range_g;
     sdk_buf fb_list, fb_rows, fb_list2, cand_row2, qpool2;
+    sdk_buf cent_sum, cent_seg, goff2;   // pool-first stage A: fp32 centroid sums [G, Dp], hi/lo pseudo-segments [2G, Dp], their offsets
     sdk_buf kth;               // running k-th best buckets of the candidate flush (tcgen05.cuh)
     bool kth_on = false;       // set per identify call: the candidate threshold is low enough for noise rows to pass
     int32_t slot_g0 = 0, slot_g1 = 0, slot_nsub = 0;   // label groups whose candidate slots are live after stage A
@@ -101,6 +116,9 @@ struct sdk_ctx {
     int32_t L = 0, k = 0;
     int64_t N = 0;
     bool have_results = false, have_assign = false;
+    sdk_lazy lazy;             // pending certificate / label-flag check of a small-query identify
+    double assign_thr = 0.0;   // parameters of the last sdk_assign (re-run when a pending certificate changes the lists)
+    int32_t assign_min_trust = 99;
     sdk_buf out_pack;          // the result record (sdk_out_view)
     sdk_out_view out;
     void* h_pack = nullptr;    // pinned host copy of a small record (one D2H per fetch)
@@ -163,6 +181,11 @@ int sdk_launch_normalize(sdk_ctx* c, const float* d_x, int64_t n, int32_t D, int
 // same, raw rows stored as fp32 (SDK_IN_F32) or IEEE fp16 (SDK_IN_F16: widened exactly to fp32, then the same arithmetic)
 int sdk_launch_normalize_in(sdk_ctx* c, const void* d_x, int32_t in_dtype, int64_t n, int32_t D, int32_t Dp,
                             float* d_f32, __nv_bfloat16* d_bf16);
+// pool-first stage A (normalize.cu): K1 that also accumulates the label centroids, then the hi/lo bf16 split
+int sdk_poolfirst_applicable(const void* d_x, int32_t in_dtype, int32_t D, int32_t Dp);
+int sdk_launch_normalize_centroid(sdk_ctx* c, const void* d_x, int32_t in_dtype, const int32_t* d_lab, int32_t label_base, int64_t n,
+                                  int32_t D, int32_t Dp, float* d_f32, __nv_bfloat16* d_bf16, const int64_t* d_goff, int32_t G,
+                                  float* d_csum, __nv_bfloat16* d_cent, int64_t* d_goff2, int32_t round_bf16);
 // group offsets from sorted labels; *d_flag != 0 when labels are unsorted / out of range
 int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_t L, int32_t label_base,
                              int64_t* d_goff, int32_t* d_flag);
@@ -198,11 +221,13 @@ int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int6
                                    const int64_t* d_goff, int32_t G, int32_t pool, float tau,
                                    int32_t ncand, int32_t* d_cand_row /*[G,ncand]*/,
                                    float* d_gbound /*[G]*/);
-// <= 8 query segments: HBM-bound bank stream on the CUDA cores (gemv.cu), same outputs as the tcgen05 stage A
+// <= 8 query segments: the small-query latency path (gemv.cu) -- label offsets, normalise, HBM-bound bank stream and
+// per-CTA top lists in one kernel; merge, canonical re-score, select and certificate in a second; nothing synchronised.
+// Failed certificates are left on c->fb_list / flags[SDK_FLAG_FB] for sdk_settle.
 int sdk_gemv_applicable(int64_t N, int32_t Dp);
-int sdk_launch_gemv_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int64_t P, const __nv_bfloat16* d_seg, int64_t N, int32_t Dp,
-                               const int64_t* d_goff, int32_t G, int32_t pool, float tau, int32_t ncand, int32_t* d_cand_row,
-                               float* d_gbound);
+int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype, const int32_t* d_seg_label, int32_t label_base, int64_t N,
+                             int32_t L, int32_t pool, double threshold, int32_t k, float tau, float eps, int32_t ncand, int32_t* d_flags,
+                             int64_t* o_row, float* o_score, int32_t* o_count, uint8_t* o_trust, int32_t* o_spk);
 int sdk_launch_poolgemm_remerge(sdk_ctx* c, const int64_t* d_goff, const int32_t* d_glist, int32_t ngroups, float tau,
                                 int32_t ncand, int32_t* d_cand_row, float* d_gbound);
 // tcgen05 accumulate-pooling GEMM (mean pooling, >= 128 label groups): normalises the RAW segments into the group-

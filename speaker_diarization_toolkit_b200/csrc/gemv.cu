@@ -1,273 +1,620 @@
-// gemv.cu -- K2d: stage A for a HANDFUL of query segments against a big bank ("8 pooled label centroids vs a 125k-row
-// shard", BASELINE config 4 variant (i)).  One pass over the bank, HBM-bound: 2*Dp bytes per bank row, nothing else.
+// gemv.cu -- K2d: the small-query latency path.  A HANDFUL of query segments against a big bank ("8 pooled label centroids
+// vs a 125k-row shard", BASELINE config 4 variant (i)): the whole identify call is TWO kernels and no host round trip.
 //
-// The tcgen05 kernels need at least a 256-column accumulator tile and reload a 128-row bank tile per unit without
-// overlap; for <= 8 query segments that is 32x wasted tensor work and an exposed TMA round trip per 128 rows.  Here the
-// bank is streamed through shared memory by TMA (one elected producer thread, 2-D boxes of 64 rows x 64 bf16 with the
-// 128-byte swizzle): each of the eight consumer warps owns a private ring of 3 stages (mbarrier full/empty pairs; a
-// barrier is only ever waited on by its own warp, phase after phase), 192 KB in flight per SM (sixteen consumer warps,
-// 32-row stages).  The arithmetic is the
-// one tensor-core shape that fits 8 queries exactly: mma.sync m16n8k16 (bf16 in, fp32 accumulate) -- bank rows are the
-// M side (ldmatrix.x4 straight from the swizzled tile, conflict-free), the 8 queries are the N side (fragments pre-packed
-// in shared memory, 2 words per lane and 16-wide K step), 8 accumulator registers hold a 32-row chunk across the K
-// chunks.  That is ~50 instructions per 32x64 stage, so the SM only waits for HBM.  After the last K chunk the
-// accumulator fragments are transposed through shared memory; lane i then owns rows i and i+32, pools their scores per
-// label group and flushes the candidate slots exactly like the tensor-core epilogues (tcgen05.cuh: pg_flush), so merge /
-// canonical re-score / certificate downstream are unchanged.  (tcgen05.mma needs N >= 16 and a TMEM round trip; for
-// an HBM-bound 8-column product the warp-level MMA is the better fit.)
+//   k_gemv8       one HBM-bound pass over the bank (2*Dp bytes per bank row, nothing else), fused with everything that
+//                 used to be separate launches in front of it: label-group offsets + label validation, the canonical
+//                 normalise-and-cast of the <= 8 query rows (every CTA redoes it from the 16 KB of raw queries while its
+//                 first bank tiles are already in flight; CTA 0 publishes the operand copies for stage B), and behind it:
+//                 the per-CTA top-16 of every label's approximate pooled scores (+ a bound on everything dropped), so the
+//                 kernel leaves 2 x grid short sorted lists per label instead of one candidate slot per 32 bank rows.
+//   k_gemv8_tail  one CTA per label: merge of those lists (threshold from the list maxima, compaction, exact rank),
+//                 canonical fp64 re-score of the candidates (stage B), row->speaker max, threshold, ordered top-k and the
+//                 certificate -- what k_pg_merge + k_exact_q30 + k_select did in three launches over 4 MB of slots.
+//                 Launched with programmatic stream serialisation: its launch latency hides under the bank stream.
+// A failed certificate (rare) is not handled by a host check inside the call: the label is put on the fall-back list and
+// the library settles it -- exhaustively, in the canonical arithmetic -- when the results are next fetched (api.cu).
+//
+// The stream: a bank tile = 32 rows x Dp bf16, loaded as Dp/64 TMA boxes (64 columns x 32 rows, 128-byte swizzle) that
+// are issued back to back on ONE mbarrier, so the 1 KB rows of the tile are requested within a few hundred nanoseconds of
+// each other (the previous version walked the K chunks of sixteen different tiles round robin through three-deep rings:
+// every DRAM page was opened eight times; 45 % of the HBM peak).  One elected producer thread fills a ring of tiles that
+// the consumer warps share; tile i sits in stage i % nstage and belongs to consumer warp i % nstage (one waiter per mbarrier:
+// it sees every phase), which computes the complete dot products of its 32 rows with the 8 queries: mma.sync m16n8k16 (bf16 in, fp32 accumulate) -- bank rows are the M side (ldmatrix.x4 straight from
+// the swizzled tile, conflict-free), the queries the N side (fragments pre-packed in shared memory).  Every CTA owns a
+// contiguous range of the bank (nchunk * b / grid), so all SMs stream the same number of tiles +- 1.
 // Products of bf16 operands are exact in fp32; only the fp32 accumulation order differs from the canonical arithmetic,
-// well inside the certificate's eps.
+// well inside the certificate's eps (tests/test_gpu_certificate.py measures it).
 #include "tcgen05.cuh"
 
 #define GV_NQ 8
 #define GV_CW 16                     // consumer warps
 #define GV_THREADS (32 * (GV_CW + 1))
-#define GV_RING 3                    // stages per consumer warp
-#define GV_STAGES (GV_CW * GV_RING)
-#define GV_ROWS 32                   // bank rows per chunk / stage (one candidate sub-slot)
-#define GV_STAGE_BYTES 4096u         // 32 rows x 64 bf16
+#define GV_ROWS 32                   // bank rows per tile
+#define GV_PASS_TILES 32             // tiles whose raw scores are kept in shared memory before a selection pass
+#define GV_PASS_ROWS (GV_ROWS * GV_PASS_TILES)
+#define GV_RAW_LD (GV_PASS_ROWS + 8) // padded: the fragment stores of the four query pairs land in different banks
+#define GV_KEEP 16                   // kept per (label, CTA, half of the pass)
+#define GV_PARTS 2                   // selection warps per label: 8 labels x 2 = the 16 consumer warps
+#define GV_MAX_STAGES 8
+#define GV_TAIL_THREADS 256
+#define GV_TAIL_CAP 1024             // compacted candidates per label in the tail
 
 struct GvParams {
-    PgParams pg;
-    int32_t N, G, Dp;
-    int32_t nsub;                 // sub-slots per label group = ceil(P / 32)
-    int32_t nchunk;               // 32-row chunks of the bank (== nsub)
+    const void* seg_raw;          // [N, D] raw query rows, fp32 or fp16
+    const int32_t* seg_label;     // [N] global label ids
+    int32_t in_dtype, label_base;
+    int32_t N, L, D, Dp;
+    int64_t P;
+    int32_t pool;
+    float tau;
+    int32_t nchunk;               // 32-row tiles of the bank
+    int32_t nstage;               // ring depth
+    int32_t nslots;               // lists per query slot = grid * GV_PARTS
+    // published by CTA 0 for the tail / the fall-back
+    int64_t* goff;                // [L + 1]
+    int32_t* flags;               // label validation bits
+    __nv_bfloat16* seg_bf16;      // [N, Dp]
+    float* seg_f32;               // [N, D] or null (fp32 banks)
+    // lists: index (q0 * nslots + slot), q0 = first query of the label
+    int32_t* slot_cnt;
+    float* slot_bound;
+    int32_t* slot_row;            // [.., GV_KEEP]
+    float* slot_val;
 };
 
-// Pools and flushes one 32-row chunk (one sub-slot per label group).  Rolled loops: every warp runs this only a few
-// times, so instruction-cache footprint matters more than unrolling; inlined so that the shared-memory operands are
-// read with shared-space loads (a generic-pointer version stalled on every label).
-static __device__ __forceinline__ void gv_flush_chunk(const GvParams& q, const float* __restrict__ sc /*[32][GV_NQ]*/, const int32_t* s_grp,
-                                                   const int32_t* s_len, int64_t chunk, int lane) {
-    const PgParams& p = q.pg;
-    const int64_t row = chunk * GV_ROWS + lane;
-    const float* v = sc + lane * GV_NQ;
-    // running k-th best thresholds of the (at most GV_NQ) label groups: all loads are issued before the first is used --
-    // one L2 round trip per chunk instead of one per label (the flushes below then skip the per-flush lookup)
-    // (lane s keeps the threshold of query slot s; the flush loop stays rolled -- every warp runs it only a few times, so
-    //  instruction-cache footprint matters more than unrolling)
-    uint32_t thr_mine = 0u;
-    if (p.kth) {
-        uint32_t ka[GV_NQ], kb[GV_NQ];
-#pragma unroll
-        for (int s = 0; s < GV_NQ; ++s) {
-            const int g = s < q.N ? s_grp[s] : -1;
-            const uint32_t* kp = p.kth + (int64_t)(g < 0 ? 0 : g - p.g_base) * PG_KTH;
-            ka[s] = g >= 0 ? __ldcg(kp + lane) : 0u;
-            kb[s] = g >= 0 ? __ldcg(kp + lane + 32) : 0u;
+__device__ __forceinline__ void gv_bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(GV_CW * 32) : "memory"); }
+
+// canonical normalise of one row by one warp (oracle/canonical.c step (1); same element -> lane assignment and the same
+// order as k_normalize_vec / k_normalize_generic): bf16 copy into shared memory, optional global copies
+template <typename TIn>
+__device__ __forceinline__ void gv_normalize_row(const TIn* __restrict__ xr, int32_t D, int32_t Dp, int lane, __nv_bfloat16* s_out,
+                                                 __nv_bfloat16* g_bf16, float* g_f32) {
+    double s = 0.0;
+    for (int q4 = lane; 4 * q4 < D; q4 += 32)
+        for (int t = 0; t < 4; ++t) {
+            const int e = 4 * q4 + t;
+            if (e < D) { const double a = (double)sdk_in<TIn>::ld1(xr, e); s = fma(a, a, s); }
         }
 #pragma unroll
-        for (int s = 0; s < GV_NQ; ++s) {
-            const uint32_t t = __reduce_min_sync(0xffffffffu, ka[s] < kb[s] ? ka[s] : kb[s]);
-            thr_mine = lane == s ? t : thr_mine;
-        }
+    for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+    const float nrm = (float)sqrt(s);
+    const float den = nrm > 1e-12f ? nrm : 1e-12f;
+    const float inv = __fdiv_rn(1.0f, den);
+    for (int e = lane; e < Dp; e += 32) {
+        const float o = e < D ? __fmul_rn(sdk_in<TIn>::ld1(xr, e), inv) : 0.f;
+        const __nv_bfloat16 b = __float2bfloat16_rn(o);
+        s_out[e] = b;
+        if (g_bf16) g_bf16[e] = b;
+        if (g_f32 && e < D) g_f32[e] = o;
     }
-    float a = p.pool == 0 ? 0.f : -3.0e38f;
-#pragma unroll 1
-    for (int s = 0; s < q.N; ++s) {
-        a = p.pool == 0 ? a + v[s] : fmaxf(a, v[s]);
-        const int g = s_grp[s];
-        if (s + 1 == q.N || s_grp[s + 1] != g) {
-            const float val = p.pool == 0 ? a * (1.0f / (float)s_len[s]) : a;
-            const int64_t sg = g - p.g_base, sub = sg * p.nsub + chunk;
-            bool pass = (val >= p.tau) && (row < p.P);
-            if (p.kth) {
-                const uint32_t thr = __shfl_sync(0xffffffffu, thr_mine, s);
-                const uint32_t key = sdk_fkey(val);
-                pg_kth_update(p, sg, chunk, pass ? key : 0u, thr, lane);
-                pass = pass && key >= thr;
-            }
-            const uint32_t mpass = __ballot_sync(0xffffffffu, pass);
-            if (lane == 0 && mpass == 0) p.slot_cnt[sub] = 0;
-            if (mpass != 0) pg_flush_write(p, val, pass, mpass, sub, lane, row);
-            a = p.pool == 0 ? 0.f : -3.0e38f;
-        }
-    }
+}
+
+// 64-bit max over the warp (keys are unique or zero)
+__device__ __forceinline__ unsigned long long gv_warp_max_u64(unsigned long long v) {
+    const uint32_t hi = __reduce_max_sync(0xffffffffu, (uint32_t)(v >> 32));
+    const uint32_t lo = __reduce_max_sync(0xffffffffu, (uint32_t)(v >> 32) == hi ? (uint32_t)v : 0u);
+    return ((unsigned long long)hi << 32) | lo;
 }
 
 template <int KCH>
 __global__ void __launch_bounds__(GV_THREADS, 1)
-k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const uint32_t* __restrict__ seg /*[N, Dp/2] bf16x2*/, const __grid_constant__ GvParams q) {
+k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const __grid_constant__ GvParams q) {
     extern __shared__ uint8_t gv_smem_raw[];
-    __shared__ __align__(16) float s_c[GV_CW][GV_ROWS][GV_NQ]; // accumulator transpose: [row of the chunk][query]
     __shared__ __align__(8) uint2 s_bq[KCH * 4][32];           // B fragments of every 16-wide K step, per lane
-    __shared__ int32_t s_grp[GV_NQ];              // label group of query s (-1: padding)
-    __shared__ int32_t s_len[GV_NQ];              // segments of that group
-    __shared__ __align__(8) uint64_t s_bar[2 * GV_STAGES];
-    const PgParams& p = q.pg;
+    __shared__ int32_t s_lab[GV_NQ];                            // label of query s relative to label_base (clamped)
+    __shared__ int32_t s_run[GV_NQ];                            // > 0: query s starts a run of that many queries of one label
+    __shared__ __align__(8) uint64_t s_bar[2 * GV_MAX_STAGES];
+    constexpr uint32_t STAGE_BYTES = KCH * 4096u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pitch = q.Dp >> 1;
     const uint32_t raw = pg_smem_u32(gv_smem_raw);
     const uint32_t ring = (raw + 1023u) & ~1023u;                   // the swizzle atom is 1024 bytes
-    const uint32_t bar_full = pg_smem_u32(s_bar), bar_empty = bar_full + 8 * GV_STAGES;
+    uint8_t* dyn = gv_smem_raw + (ring - raw);
+    float* s_raw = reinterpret_cast<float*>(dyn + (size_t)q.nstage * STAGE_BYTES);                      // [GV_NQ][GV_RAW_LD]
+    __nv_bfloat16* s_q = reinterpret_cast<__nv_bfloat16*>(s_raw + GV_NQ * GV_RAW_LD);                   // [GV_NQ][Dp]
+    const uint32_t bar_full = pg_smem_u32(s_bar), bar_empty = bar_full + 8 * GV_MAX_STAGES;
+    // the tail kernel may be scheduled as soon as every CTA has got here (it waits for this grid's completion itself)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GV_STAGES; ++s) { pg_mbar_init(bar_full + 8 * s, 1); pg_mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < q.nstage; ++s) { pg_mbar_init(bar_full + 8 * s, 1); pg_mbar_init(bar_empty + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (threadIdx.x >= 32 && threadIdx.x < 32 + GV_NQ) {
-        const int s = threadIdx.x - 32;
-        int g = -1, len = 0;
-        if (s < q.N) {
-            int lo = 0, hi = q.G;                 // last g with goff[g] <= s (the non-empty group that holds segment s)
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (p.goff[mid] <= s) lo = mid; else hi = mid;
-            }
-            g = lo;
-            len = (int)(p.goff[g + 1] - p.goff[g]);
-        }
-        s_grp[s] = g;
-        s_len[s] = len;
-    }
-    // B fragments (mma.sync m16n8k16 "col" operand): lane l holds query n = l / 4, k = 16 * ks + 2 * (l % 4) (+8).  Kept in
-    // shared memory so that the K loop stays rolled: every warp runs the loop body only a couple of times, and a fully
-    // unrolled kernel spent more time missing the instruction cache than computing
-    for (int i = threadIdx.x; i < KCH * 4 * 32; i += GV_THREADS) {
-        const int ks = i >> 5, l = i & 31, n = l >> 2, kw = l & 3;
-        uint2 b = make_uint2(0u, 0u);
-        if (n < q.N) {
-            b.x = __ldg(seg + (int64_t)n * pitch + ks * 8 + kw);
-            b.y = __ldg(seg + (int64_t)n * pitch + ks * 8 + 4 + kw);
-        }
-        s_bq[ks][l] = b;
-    }
     __syncthreads();
-    // chunks of this CTA: blockIdx.x, + gridDim.x, ...; the k-th goes to consumer warp k % GV_CW as that warp's chunk
-    // number n = k / GV_CW; its K chunk kc is the warp's stage number m = KCH * n + kc -> stage (m % GV_RING) of its ring
-    const int64_t n_mine = q.nchunk > (int64_t)blockIdx.x ? (q.nchunk - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // this CTA's contiguous range of tiles
+    const int64_t c0 = (int64_t)q.nchunk * blockIdx.x / gridDim.x, c1 = (int64_t)q.nchunk * (blockIdx.x + 1) / gridDim.x;
+    const int64_t n_mine = c1 - c0;
     if (warp == 0) {
+        // ---- producer: the bank stream does not depend on the queries, it starts at once ----
         if (lane == 0) {
-            // issue order: K chunk by K chunk, round robin over the warps, so that a full ring of one warp never holds
-            // back the loads of the others
-            for (int64_t kb = 0; kb < n_mine; kb += GV_CW) {
-                const int64_t n = kb / GV_CW;
-                for (int kc = 0; kc < KCH; ++kc) {
-                    for (int w = 0; w < GV_CW; ++w) {
-                        const int64_t k = kb + w;
-                        if (k >= n_mine) break;
-                        const int64_t chunk = blockIdx.x + k * gridDim.x;
-                        const int64_t m = n * KCH + kc;
-                        const int st = w * GV_RING + (int)(m % GV_RING);
-                        const uint32_t use = (uint32_t)(m / GV_RING);
-                        pg_mbar_wait(bar_empty + 8 * st, (use & 1u) ^ 1u);
-                        pg_mbar_expect_tx(bar_full + 8 * st, GV_STAGE_BYTES);
-                        pg_tma_load_2d(ring + st * GV_STAGE_BYTES, &tmapBank, kc * 64, (int32_t)(chunk * GV_ROWS), bar_full + 8 * st);   // rows past P: zero fill
-                    }
-                }
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapBank)) : "memory");
+            for (int64_t i = 0; i < n_mine; ++i) {
+                const int st = (int)(i % q.nstage);
+                const uint32_t use = (uint32_t)(i / q.nstage);
+                pg_mbar_wait(bar_empty + 8 * st, (use & 1u) ^ 1u);
+                pg_mbar_expect_tx(bar_full + 8 * st, STAGE_BYTES);
+                const int32_t row0 = (int32_t)((c0 + i) * GV_ROWS);
+#pragma unroll
+                for (int kc = 0; kc < KCH; ++kc)                       // rows past P: zero fill
+                    pg_tma_load_2d(ring + st * STAGE_BYTES + kc * 4096u, &tmapBank, kc * 64, row0, bar_full + 8 * st);
             }
         }
         return;
     }
+    // ---- consumers: query preparation (labels, canonical normalise, B fragments) while the first tiles fly ----
     const int cw = warp - 1;
+    if (cw == 0 && lane < GV_NQ) {
+        int32_t l = 0x7fffffff;
+        if (lane < q.N) {
+            l = q.seg_label[lane] - q.label_base;
+            l = l < 0 ? 0 : (l >= q.L ? q.L - 1 : l);
+        }
+        s_lab[lane] = l;
+    }
+    if (cw < GV_NQ) {
+        __nv_bfloat16* so = s_q + (size_t)cw * q.Dp;
+        if (cw < q.N) {
+            const bool pub = blockIdx.x == 0;
+            __nv_bfloat16* gb = pub ? q.seg_bf16 + (size_t)cw * q.Dp : nullptr;
+            float* gf = (pub && q.seg_f32) ? q.seg_f32 + (size_t)cw * q.D : nullptr;
+            if (q.in_dtype == SDK_IN_F16)
+                gv_normalize_row<__half>(reinterpret_cast<const __half*>(q.seg_raw) + (size_t)cw * q.D, q.D, q.Dp, lane, so, gb, gf);
+            else
+                gv_normalize_row<float>(reinterpret_cast<const float*>(q.seg_raw) + (size_t)cw * q.D, q.D, q.Dp, lane, so, gb, gf);
+        } else {
+            for (int e = lane; e < q.Dp; e += 32) so[e] = __float2bfloat16_rn(0.f);
+        }
+    }
+    if (blockIdx.x == 0 && cw == GV_NQ) {
+        // label-group offsets (CSR) and label validation for the whole call: goff[g] = queries with a label < g.  Equal to
+        // the usual offsets for sorted labels, monotone and inside [0, N] for anything else (which is flagged).
+        int32_t f = 0, prev = -0x7fffffff;
+        int32_t labs[GV_NQ];
+#pragma unroll
+        for (int s = 0; s < GV_NQ; ++s) labs[s] = s < q.N ? q.seg_label[s] - q.label_base : 0x7fffffff;
+#pragma unroll
+        for (int s = 0; s < GV_NQ; ++s) {
+            if (s < q.N) {
+                if (labs[s] < 0 || labs[s] >= q.L) f |= 1;
+                if (labs[s] < prev) f |= 2;
+                prev = labs[s];
+            }
+        }
+        for (int g = lane; g <= q.L; g += 32) {
+            int cnt = 0;
+#pragma unroll
+            for (int s = 0; s < GV_NQ; ++s) cnt += labs[s] < g ? 1 : 0;
+            q.goff[g] = cnt;
+        }
+        if (f && lane == 0) atomicOr(q.flags, f);
+    }
+    gv_bar_consumers();
+    if (cw == 0 && lane < GV_NQ) {
+        int run = 0;
+        if (lane < q.N && (lane == 0 || s_lab[lane] != s_lab[lane - 1])) {
+            run = 1;
+            while (lane + run < q.N && s_lab[lane + run] == s_lab[lane]) ++run;
+        }
+        s_run[lane] = run;
+    }
+    // B fragments (mma.sync m16n8k16 "col" operand): lane l holds query n = l / 4, k = 16 * ks + 2 * (l % 4) (+8)
+    {
+        const uint32_t* sq32 = reinterpret_cast<const uint32_t*>(s_q);
+        const int pitch = q.Dp >> 1;
+        for (int i = threadIdx.x - 32; i < KCH * 4 * 32; i += GV_CW * 32) {
+            const int ks = i >> 5, l = i & 31, n = l >> 2, kw = l & 3;
+            s_bq[ks][l] = make_uint2(sq32[n * pitch + ks * 8 + kw], sq32[n * pitch + ks * 8 + 4 + kw]);
+        }
+    }
+    gv_bar_consumers();
+    // ---- selection state of this warp's (query slot, half): kept list in lanes 0..15, bound on everything dropped ----
+    const int sel_q = cw >> 1, sel_part = cw & 1;
+    const int sel_len = s_run[sel_q];
+    unsigned long long kept = 0ull;
+    float bound = -3.0e38f;
     // ldmatrix.x4 source row of this lane inside a 16-row tile, and which 8-wide K half it addresses
     const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = lane >> 4;
-    int64_t m = 0;                                  // this warp's stage counter (walks its private ring)
-    for (int64_t k = cw; k < n_mine; k += GV_CW) {
-        const int64_t chunk = blockIdx.x + k * gridDim.x;
-        float acc[GV_ROWS / 16][4];
+    for (int64_t pass0 = 0; pass0 < n_mine; pass0 += GV_PASS_TILES) {
+        const int npc = (int)((n_mine - pass0) < GV_PASS_TILES ? (n_mine - pass0) : GV_PASS_TILES);
+        // Stage `st` of the ring is consumed by warp `st` and by nobody else: an mbarrier phase wait is only meaningful for a
+        // waiter that sees EVERY phase of the barrier (a warp that skipped two uses of a stage would take the parity of an
+        // older fill for its own).  So the first `nstage` consumer warps do the MMAs (5..8 warps keep up with the ~44 GB/s an
+        // SM gets from HBM many times over); all sixteen take part in the preparation and the selection.
+        for (int64_t i = pass0 + (((int64_t)cw - pass0 % q.nstage) + q.nstage) % q.nstage; cw < q.nstage && i < pass0 + npc; i += q.nstage) {
+            const int j = (int)(i - pass0);
+            const int st = cw;
+            const uint32_t use = (uint32_t)(i / q.nstage);
+            float acc[GV_ROWS / 16][4];
 #pragma unroll
-        for (int rt = 0; rt < GV_ROWS / 16; ++rt)
+            for (int rt = 0; rt < GV_ROWS / 16; ++rt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[rt][i] = 0.f;
-#pragma unroll 1
-        for (int kc = 0; kc < KCH; ++kc, ++m) {
-            const int st = cw * GV_RING + (int)(m % GV_RING);
-            const uint32_t use = (uint32_t)(m / GV_RING);
+                for (int e = 0; e < 4; ++e) acc[rt][e] = 0.f;
             pg_mbar_wait(bar_full + 8 * st, use & 1u);
-            const uint32_t tile = ring + st * GV_STAGE_BYTES;
+#pragma unroll 1
+            for (int kc = 0; kc < KCH; ++kc) {
+                const uint32_t tile = ring + st * STAGE_BYTES + kc * 4096u;
 #pragma unroll
-            for (int rt = 0; rt < GV_ROWS / 16; ++rt) {
-                const int r = rt * 16 + lrow;                       // row of the tile; swizzle: 16-byte piece ^= row % 8
+                for (int rt = 0; rt < GV_ROWS / 16; ++rt) {
+                    const int r = rt * 16 + lrow;                       // row of the tile; swizzle: 16-byte piece ^= row % 8
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t addr = tile + r * 128 + (((2 * ks + lhalf) ^ (r & 7)) << 4);
-                    uint32_t a0, a1, a2, a3;
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
-                    const uint2 b = s_bq[kc * 4 + ks][lane];
-                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                 : "+f"(acc[rt][0]), "+f"(acc[rt][1]), "+f"(acc[rt][2]), "+f"(acc[rt][3])
-                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t addr = tile + r * 128 + (((2 * ks + lhalf) ^ (r & 7)) << 4);
+                        uint32_t a0, a1, a2, a3;
+                        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+                        const uint2 b = s_bq[kc * 4 + ks][lane];
+                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(acc[rt][0]), "+f"(acc[rt][1]), "+f"(acc[rt][2]), "+f"(acc[rt][3])
+                                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+                    }
                 }
             }
             __syncwarp();
-            if (lane == 0) pg_mbar_arrive(bar_empty + 8 * st);    // the stage may be refilled while this warp goes on
-        }
-        // transpose: fragment (row = lane/4 (+8), queries 2*(lane%4), +1)  ->  lane <-> row
-        __syncwarp();
+            if (lane == 0) pg_mbar_arrive(bar_empty + 8 * st);         // the stage may be refilled while this warp goes on
+            // fragment (row = lane/4 (+8), queries 2*(lane%4), +1) -> s_raw[query][row of the pass]
 #pragma unroll
-        for (int rt = 0; rt < GV_ROWS / 16; ++rt) {
-            const int r = rt * 16 + (lane >> 2), cq = 2 * (lane & 3);
-            *reinterpret_cast<float2*>(&s_c[cw][r][cq]) = make_float2(acc[rt][0], acc[rt][1]);
-            *reinterpret_cast<float2*>(&s_c[cw][r + 8][cq]) = make_float2(acc[rt][2], acc[rt][3]);
+            for (int rt = 0; rt < GV_ROWS / 16; ++rt) {
+                const int r = j * GV_ROWS + rt * 16 + (lane >> 2), cq = 2 * (lane & 3);
+                s_raw[cq * GV_RAW_LD + r] = acc[rt][0];
+                s_raw[(cq + 1) * GV_RAW_LD + r] = acc[rt][1];
+                s_raw[cq * GV_RAW_LD + r + 8] = acc[rt][2];
+                s_raw[(cq + 1) * GV_RAW_LD + r + 8] = acc[rt][3];
+            }
+        }
+        gv_bar_consumers();                                            // the raw scores of the pass are complete
+        if (sel_len > 0) {
+            // this warp's half of the pass: tiles [sel_part * 16, +16); lane <-> rows lane + 32 t.  Pool the label's queries
+            // (ascending), keep the GV_KEEP largest of (new rows, previously kept) by (score desc, row asc)
+            uint32_t vk[GV_PASS_TILES / GV_PARTS];
+            const float rlen = 1.0f / (float)sel_len;
+#pragma unroll
+            for (int t = 0; t < GV_PASS_TILES / GV_PARTS; ++t) {
+                const int tl = sel_part * (GV_PASS_TILES / GV_PARTS) + t;
+                const int64_t row = (c0 + pass0 + tl) * GV_ROWS + lane;
+                uint32_t key = 0u;
+                if (tl < npc && row < q.P) {
+                    const float* v = s_raw + (size_t)sel_q * GV_RAW_LD + tl * GV_ROWS + lane;
+                    float a = q.pool == 0 ? 0.f : -3.0e38f;
+                    for (int s = 0; s < sel_len; ++s) a = q.pool == 0 ? a + v[s * GV_RAW_LD] : fmaxf(a, v[s * GV_RAW_LD]);
+                    const float val = q.pool == 0 ? a * rlen : a;
+                    if (val >= q.tau) key = sdk_fkey(val);
+                }
+                vk[t] = key;
+            }
+            const uint32_t rbase = (uint32_t)((c0 + pass0 + sel_part * (GV_PASS_TILES / GV_PARTS)) * GV_ROWS + lane);
+            unsigned long long last = ~0ull, newkept = 0ull;
+#pragma unroll 1
+            for (int it = 0; it <= GV_KEEP; ++it) {
+                unsigned long long best = (kept < last) ? kept : 0ull;
+#pragma unroll
+                for (int t = 0; t < GV_PASS_TILES / GV_PARTS; ++t) {
+                    const unsigned long long comp = vk[t] ? (((unsigned long long)vk[t] << 32) | (0xffffffffu - (rbase + 32u * t))) : 0ull;
+                    best = (comp < last && comp > best) ? comp : best;
+                }
+                best = gv_warp_max_u64(best);
+                if (best == 0ull) break;
+                if (it == GV_KEEP) {                                   // the best row that is NOT kept bounds everything dropped
+                    bound = fmaxf(bound, sdk_funkey((uint32_t)(best >> 32)));
+                    break;
+                }
+                if (lane == it) newkept = best;
+                last = best;
+            }
+            kept = newkept;
+        }
+        gv_bar_consumers();                                            // s_raw is rewritten by the next pass
+    }
+    // ---- publish this warp's list (every (query slot, list) entry is written: unused ones as empty) ----
+    {
+        const int64_t li = (int64_t)sel_q * q.nslots + (int64_t)blockIdx.x * GV_PARTS + sel_part;
+        const uint32_t have = __ballot_sync(0xffffffffu, kept != 0ull);
+        if (lane == 0) {
+            q.slot_cnt[li] = sel_len > 0 ? __popc(have) : 0;
+            q.slot_bound[li] = bound;
+        }
+        if (lane < GV_KEEP && kept != 0ull) {
+            q.slot_row[li * GV_KEEP + lane] = (int32_t)(0xffffffffu - (uint32_t)kept);
+            q.slot_val[li * GV_KEEP + lane] = sdk_funkey((uint32_t)(kept >> 32));
+        }
+    }
+}
+
+// ---- tail: merge + canonical re-score + select + certificate, one CTA per label ------------------------------------
+struct GvTail {
+    const int64_t* goff;
+    int32_t N, L, k, pool, ncand, nslots, D, pitch, is_bf16;
+    double threshold;
+    float eps;
+    const int32_t* slot_cnt;
+    const float* slot_bound;
+    const int32_t* slot_row;
+    const float* slot_val;
+    const void* bank_ops;
+    const void* seg_ops;
+    const int32_t* row_speaker;
+    const uint8_t* row_trust;
+    int64_t row_offset;
+    int32_t* cand_row;            // [L, ncand] diagnostics (sdk_stage_a_fetch) + the fall-back's view of stage A
+    float* cand_val;
+    float* gbound;
+    int32_t* fb_count;
+    int32_t* fb_list;
+    int64_t* o_row;
+    float* o_score;
+    int32_t* o_count;
+    uint8_t* o_trust;
+    int32_t* o_spk;
+};
+
+// one fp64 fma chain over ascending d (the canonical order); zero padding beyond D adds exact zeros
+template <bool BF16>
+__device__ __forceinline__ double gv_dot(const void* __restrict__ a_ops, int64_t arow, const void* __restrict__ b_ops, int64_t brow,
+                                         int32_t pitch, int32_t D) {
+    double acc = 0.0;
+    if (BF16) {
+        const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a_ops) + arow * (int64_t)pitch);
+        const uint4* b = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(b_ops) + brow * (int64_t)pitch);
+        const int n8 = (D + 7) >> 3;                           // pitch is a multiple of 64 and zero padded
+        uint4 pa = __ldg(a), pb = __ldg(b);
+        for (int i = 0; i < n8; ++i) {
+            const uint4 ca = pa, cb = pb;
+            if (i + 1 < n8) { pa = __ldg(a + i + 1); pb = __ldg(b + i + 1); }
+            const uint32_t wa[4] = {ca.x, ca.y, ca.z, ca.w}, wb[4] = {cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                acc = fma((double)__uint_as_float(wa[h] << 16), (double)__uint_as_float(wb[h] << 16), acc);
+                acc = fma((double)__uint_as_float(wa[h] & 0xffff0000u), (double)__uint_as_float(wb[h] & 0xffff0000u), acc);
+            }
+        }
+    } else {
+        const float* a = reinterpret_cast<const float*>(a_ops) + arow * (int64_t)pitch;
+        const float* b = reinterpret_cast<const float*>(b_ops) + brow * (int64_t)pitch;
+        int d = 0;
+        if ((pitch & 3) == 0) {
+            for (; d + 4 <= D; d += 4) {
+                const float4 fa = __ldg(reinterpret_cast<const float4*>(a + d)), fb = __ldg(reinterpret_cast<const float4*>(b + d));
+                acc = fma((double)fa.x, (double)fb.x, acc);
+                acc = fma((double)fa.y, (double)fb.y, acc);
+                acc = fma((double)fa.z, (double)fb.z, acc);
+                acc = fma((double)fa.w, (double)fb.w, acc);
+            }
+        }
+        for (; d < D; ++d) acc = fma((double)__ldg(a + d), (double)__ldg(b + d), acc);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(GV_TAIL_THREADS)
+k_gemv8_tail(const __grid_constant__ GvTail p) {
+    __shared__ unsigned long long s_max[2 * 148 + 8];          // list maxima (grid <= 148 CTAs x 2 lists)
+    __shared__ unsigned long long s_key[GV_TAIL_CAP];          // compacted candidates
+    __shared__ unsigned long long s_sel[64];                   // the ncand best, by rank
+    __shared__ long long s_pool[64];
+    __shared__ int32_t s_spk[SDK_MAX_K];
+    __shared__ unsigned long long s_T0, s_Tsel;
+    __shared__ int s_m, s_over;
+    __shared__ float s_bnd[GV_TAIL_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x;
+    const int k = p.k, ncand = p.ncand, nslots = p.nslots;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // sdk_assign's kernel may queue up behind this one
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // everything the stream kernel wrote is visible
+    int64_t s0 = p.goff[g], s1 = p.goff[g + 1];
+    s0 = s0 < 0 ? 0 : (s0 > p.N ? p.N : s0);
+    s1 = s1 < 0 ? 0 : (s1 > p.N ? p.N : s1);
+    const int n = (int)(s1 - s0);
+    for (int i = tid; i < k; i += GV_TAIL_THREADS) {
+        p.o_row[(int64_t)g * k + i] = -1;
+        p.o_score[(int64_t)g * k + i] = 0.f;
+        p.o_trust[(int64_t)g * k + i] = SDK_TRUST_UNKNOWN;
+        p.o_spk[(int64_t)g * k + i] = -1;
+    }
+    for (int i = tid; i < ncand; i += GV_TAIL_THREADS) {
+        p.cand_row[(int64_t)g * ncand + i] = -1;
+        p.cand_val[(int64_t)g * ncand + i] = 0.f;
+    }
+    if (n <= 0) {
+        if (tid == 0) { p.o_count[g] = 0; p.gbound[g] = -3.0e38f; }
+        return;
+    }
+    const int64_t lbase = (int64_t)s0 * nslots;                // lists of the label: query slot = its first query
+    // ---- 1. T0 = ncand-th largest list maximum: a lower bound on the ncand-th best entry overall ----
+    if (tid == 0) { s_m = 0; s_over = 0; s_T0 = 0ull; s_Tsel = 0ull; }
+    for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
+        unsigned long long key = 0ull;
+        if (p.slot_cnt[lbase + s] > 0)
+            key = ((unsigned long long)sdk_fkey(p.slot_val[(lbase + s) * GV_KEEP]) << 32) | (0xffffffffu - (uint32_t)p.slot_row[(lbase + s) * GV_KEEP]);
+        s_max[s] = key;
+    }
+    __syncthreads();
+    for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
+        const unsigned long long mine = s_max[s];
+        if (mine == 0ull) continue;
+        int rank = 0;
+        for (int j = 0; j < nslots; ++j) rank += s_max[j] > mine ? 1 : 0;
+        if (rank == ncand - 1) s_T0 = mine;                        // keys are unique: exactly one list has this rank (if any)
+    }
+    __syncthreads();
+    // ---- 2. compaction of every entry >= T0 (each list is sorted: a prefix) ----
+    const unsigned long long T0 = s_T0;
+    for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
+        const int cnt = p.slot_cnt[lbase + s];
+        for (int e = 0; e < cnt; ++e) {
+            const unsigned long long key = ((unsigned long long)sdk_fkey(p.slot_val[(lbase + s) * GV_KEEP + e]) << 32) |
+                                           (0xffffffffu - (uint32_t)p.slot_row[(lbase + s) * GV_KEEP + e]);
+            if (key < T0) break;
+            const int pos = atomicAdd(&s_m, 1);
+            if (pos < GV_TAIL_CAP) s_key[pos] = key; else s_over = 1;
+        }
+    }
+    __syncthreads();
+    const int m = s_m < GV_TAIL_CAP ? s_m : GV_TAIL_CAP;
+    // ---- 3. exact rank of the compacted entries; the ncand best in order ----
+    for (int i = tid; i < 64; i += GV_TAIL_THREADS) s_sel[i] = 0ull;
+    __syncthreads();
+    for (int i = tid; i < m; i += GV_TAIL_THREADS) {
+        const unsigned long long mine = s_key[i];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) rank += s_key[j] > mine ? 1 : 0;
+        if (rank < ncand) s_sel[rank] = mine;
+        if (rank == ncand - 1) s_Tsel = mine;
+    }
+    __syncthreads();
+    const int nc = m < ncand ? m : ncand;
+    const unsigned long long Tsel = s_Tsel;                        // 0: every entry of every list was selected
+    // ---- 4. bound on everything that is not a candidate: dropped inside the stream kernel, or left in a list ----
+    float bnd = -3.0e38f;
+    for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
+        const int cnt = p.slot_cnt[lbase + s];
+        bnd = fmaxf(bnd, p.slot_bound[lbase + s]);
+        if (Tsel != 0ull) {
+            for (int e = 0; e < cnt; ++e) {
+                const float v = p.slot_val[(lbase + s) * GV_KEEP + e];
+                const unsigned long long key = ((unsigned long long)sdk_fkey(v) << 32) | (0xffffffffu - (uint32_t)p.slot_row[(lbase + s) * GV_KEEP + e]);
+                if (key < Tsel) { bnd = fmaxf(bnd, v); break; }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffffffffu, bnd, off));
+    if (lane == 0) s_bnd[warp] = bnd;
+    if (tid < 64) s_pool[tid] = p.pool == 0 ? 0ll : LLONG_MIN;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < GV_TAIL_THREADS / 32; ++w) bnd = fmaxf(bnd, s_bnd[w]);
+        if (s_over) bnd = 3.0e38f;                                 // more live entries than the tail holds: cannot certify
+        p.gbound[g] = bnd;
+        s_bnd[0] = bnd;
+    }
+    for (int i = tid; i < nc; i += GV_TAIL_THREADS) {
+        p.cand_row[(int64_t)g * ncand + i] = (int32_t)(0xffffffffu - (uint32_t)s_sel[i]);
+        p.cand_val[(int64_t)g * ncand + i] = sdk_funkey((uint32_t)(s_sel[i] >> 32));
+    }
+    // ---- 5. stage B: canonical pooled scores of the candidates (thread = (candidate, segment) pair) ----
+    for (int pr = tid; pr < nc * n; pr += GV_TAIL_THREADS) {
+        const int j = pr / n, t = pr - j * n;
+        const int64_t row = (int64_t)(0xffffffffu - (uint32_t)s_sel[j]);
+        const double sc = p.is_bf16 ? gv_dot<true>(p.seg_ops, s0 + t, p.bank_ops, row, p.pitch, p.D)
+                                    : gv_dot<false>(p.seg_ops, s0 + t, p.bank_ops, row, p.pitch, p.D);
+        const long long qv = __double2ll_rn(sc * SDK_Q30);
+        if (p.pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_pool[j]), (unsigned long long)qv);
+        else atomicMax(&s_pool[j], qv);
+    }
+    __syncthreads();
+    // ---- 6. row -> speaker max, threshold, ordered top-k, certificate (k_select's semantics), one warp ----
+    if (warp != 0) return;
+    unsigned long long key0 = 0ull, key1 = 0ull;
+    if (lane < nc) {
+        const uint32_t row = 0xffffffffu - (uint32_t)s_sel[lane];
+        key0 = ((unsigned long long)sdk_fkey(sdk_pool_finish(s_pool[lane], n, p.pool)) << 32) | (0xffffffffu - row);
+    }
+    if (lane + 32 < nc) {
+        const uint32_t row = 0xffffffffu - (uint32_t)s_sel[lane + 32];
+        key1 = ((unsigned long long)sdk_fkey(sdk_pool_finish(s_pool[lane + 32], n, p.pool)) << 32) | (0xffffffffu - row);
+    }
+    unsigned long long last = ~0ull;
+    int cnt = 0;
+    float kth = 0.f;
+    while (cnt < k) {
+        unsigned long long best = (key0 < last) ? key0 : 0ull;
+        best = (key1 < last && key1 > best) ? key1 : best;
+        best = gv_warp_max_u64(best);
+        if (best == 0ull) break;
+        last = best;
+        const float sim = sdk_funkey((uint32_t)(best >> 32));
+        if (!((double)sim >= p.threshold)) break;
+        const int32_t row = (int32_t)(0xffffffffu - (uint32_t)best);
+        const int32_t spk = p.row_speaker[row];
+        bool dup = false;
+        for (int i = 0; i < cnt; ++i) dup |= s_spk[i] == spk;
+        if (dup) continue;
+        if (lane == 0) {
+            s_spk[cnt] = spk;
+            p.o_row[(int64_t)g * k + cnt] = (int64_t)row + p.row_offset;
+            p.o_score[(int64_t)g * k + cnt] = sim;
+            p.o_trust[(int64_t)g * k + cnt] = p.row_trust ? p.row_trust[row] : SDK_TRUST_UNKNOWN;
+            p.o_spk[(int64_t)g * k + cnt] = spk;
         }
         __syncwarp();
-        // lane <-> bank row chunk*32 + lane: pool the queries of each label group (ascending segment order), flush
-        gv_flush_chunk(q, &s_c[cw][0][0], s_grp, s_len, chunk, lane);
-        __syncwarp();                                               // s_c is rewritten by the next chunk
+        kth = sim;
+        ++cnt;
+    }
+    if (lane == 0) {
+        p.o_count[g] = cnt;
+        // certificate (select.cu): every row that was not re-scored has a stage-A score <= bound, hence a canonical score
+        // <= bound + eps; it cannot enter the result if that is below the threshold, or below the k-th kept score
+        const double b = (double)s_bnd[0] + (double)p.eps;
+        const bool safe = (b < p.threshold) || (cnt == k && b < (double)kth);
+        if (!safe) {
+            const int pos = atomicAdd(p.fb_count, 1);
+            p.fb_list[pos] = g;
+        }
     }
 }
 
 int sdk_gemv_applicable(int64_t N, int32_t Dp) { return N >= 1 && N <= GV_NQ && sdk_poolgemm_supported(Dp); }
 
-// Candidates + bound per label group, like sdk_launch_poolgemm_candidates, for N <= 8 query segments.
-int sdk_launch_gemv_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int64_t P, const __nv_bfloat16* d_seg, int64_t N, int32_t Dp,
-                               const int64_t* d_goff, int32_t G, int32_t pool, float tau, int32_t ncand, int32_t* d_cand_row,
-                               float* d_gbound) {
+// The whole small-query identify: stream kernel + tail.  Everything it needs is reserved here; nothing is synchronised.
+int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype, const int32_t* d_seg_label, int32_t label_base, int64_t N,
+                             int32_t L, int32_t pool, double threshold, int32_t k, float tau, float eps, int32_t ncand, int32_t* d_flags,
+                             int64_t* o_row, float* o_score, int32_t* o_count, uint8_t* o_trust, int32_t* o_spk) {
+    const int32_t D = c->D, Dp = c->Dp;
+    const int64_t P = c->P;
+    const bool bf16 = c->dtype == SDK_DTYPE_BF16;
     if (!sdk_gemv_applicable(N, Dp)) return sdk_fail(c, SDK_EINVAL, "gemv path: needs 1..8 segments and a supported D");
     if (P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "gemv path: at most 2^31-1 bank rows");
-    const int32_t nsub = (int32_t)((P + 31) / 32);
-    // slots only for groups that can hold a segment: groups are flushed by id, so the arrays span all G groups
-    const size_t per_group = (size_t)nsub * (PG_CS * 8 + 8);
-    if (per_group * (size_t)G > (8192ull << 20)) return sdk_fail(c, SDK_EINVAL, "gemv path: too many label groups for this bank");
-    SDK_TRY(sdk_reserve(c, c->slot_cnt, (size_t)G * nsub * 4));
-    SDK_TRY(sdk_reserve(c, c->slot_bound, (size_t)G * nsub * 4));
-    SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)G * nsub * PG_CS * 4));
-    SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)G * nsub * PG_CS * 4));
-    GvParams q;
-    q.pg.goff = d_goff;
-    q.pg.range_g = nullptr;
-    q.pg.n_ranges = 0;
-    q.pg.RB = 0;
-    q.pg.P = P;
-    q.pg.g_base = 0;
-    q.pg.pool = pool;
-    q.pg.tau = tau;
-    q.pg.mode = 0;
-    q.pg.slot_cnt = (int32_t*)c->slot_cnt.p;
-    q.pg.slot_row = (int32_t*)c->slot_row.p;
-    q.pg.slot_val = (float*)c->slot_val.p;
-    q.pg.slot_bound = (float*)c->slot_bound.p;
-    q.pg.dense_out = nullptr;
-    q.pg.dense_ld = 0;
-    q.pg.nsub = nsub;
-    q.pg.kth = nullptr;
-    // (with <= 8 queries the slot volume is small and the per-chunk bucket lookups cost more than they save -- measured
-    //  46.1 vs 43.6 us on config 4-i -- so the pruning is only taken when forced: option kth = 2)
-    if (c->kth_on && c->opt_kth == 2) {
-        SDK_TRY(sdk_reserve(c, c->kth, (size_t)G * PG_KTH * 4));
-        SDK_CUDA(c, cudaMemsetAsync(c->kth.p, 0, (size_t)G * PG_KTH * 4, c->stream));
-        q.pg.kth = (uint32_t*)c->kth.p;
-    }
-    q.N = (int32_t)N;
-    q.G = G;
-    q.Dp = Dp;
-    q.nsub = nsub;
-    q.nchunk = nsub;
-    const int grid = (int)std::min<int64_t>((q.nchunk + GV_CW - 1) / GV_CW, (int64_t)c->sm_count);
-    const size_t smem = (size_t)GV_STAGES * GV_STAGE_BYTES + 1024;
     if (!c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "gemv path: cuTensorMapEncodeTiled unavailable");
+    if (ncand > 64) ncand = 64;
+    const int KCH = Dp / 64;
+    const int32_t nchunk = (int32_t)((P + GV_ROWS - 1) / GV_ROWS);
+    const int grid = (int)std::min<int64_t>(nchunk, std::min(c->sm_count, 148));
+    const int32_t nslots = grid * GV_PARTS;
+    const size_t fixed = (size_t)GV_NQ * GV_RAW_LD * 4 + (size_t)GV_NQ * Dp * 2 + 1024;
+    int nstage = (int)((PG_SMEM_LIMIT - 12288 - fixed) / ((size_t)KCH * 4096));       // 12 KB: the kernel's static shared memory
+    nstage = std::max(2, std::min(nstage, GV_MAX_STAGES));
+    const size_t smem = (size_t)nstage * KCH * 4096 + fixed;
+    SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
+    SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
+    if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
+    SDK_TRY(sdk_reserve(c, c->slot_cnt, (size_t)GV_NQ * nslots * 4));
+    SDK_TRY(sdk_reserve(c, c->slot_bound, (size_t)GV_NQ * nslots * 4));
+    SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)GV_NQ * nslots * GV_KEEP * 4));
+    SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)GV_NQ * nslots * GV_KEEP * 4));
+    SDK_TRY(sdk_reserve(c, c->cand_row, (size_t)L * ncand * 4));
+    SDK_TRY(sdk_reserve(c, c->cand_val, (size_t)L * ncand * 4));
+    SDK_TRY(sdk_reserve(c, c->gbound, (size_t)L * 4));
+    SDK_TRY(sdk_reserve(c, c->fb_list, (size_t)L * 4));
+    GvParams q;
+    q.seg_raw = d_seg_raw;
+    q.seg_label = d_seg_label;
+    q.in_dtype = in_dtype;
+    q.label_base = label_base;
+    q.N = (int32_t)N;
+    q.L = L;
+    q.D = D;
+    q.Dp = Dp;
+    q.P = P;
+    q.pool = pool;
+    q.tau = tau;
+    q.nchunk = nchunk;
+    q.nstage = nstage;
+    q.nslots = nslots;
+    q.goff = (int64_t*)c->goff.p;
+    q.flags = d_flags + SDK_FLAG_LABEL;
+    q.seg_bf16 = (__nv_bfloat16*)c->seg_bf16.p;
+    q.seg_f32 = bf16 ? nullptr : (float*)c->seg_f32.p;
+    q.slot_cnt = (int32_t*)c->slot_cnt.p;
+    q.slot_bound = (float*)c->slot_bound.p;
+    q.slot_row = (int32_t*)c->slot_row.p;
+    q.slot_val = (float*)c->slot_val.p;
     CUtensorMap tb;
-    SDK_TRY(pg_make_tmap(c, &tb, d_bank, P, Dp, GV_ROWS));
+    SDK_TRY(pg_make_tmap(c, &tb, c->bank_bf16.p, P, Dp, GV_ROWS));
     {
         sdk_prof_scope ps(c, "poolgemm");         // stage A of the certified top-k, whichever kernel runs it
-        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(d_seg);
 #define GV_LAUNCH(K)                                                                                            \
     do {                                                                                                            \
         SDK_CUDA(c, cudaFuncSetAttribute(k_gemv8<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        k_gemv8<K><<<grid, GV_THREADS, smem, c->stream>>>(tb, s32, q);                                             \
+        k_gemv8<K><<<grid, GV_THREADS, smem, c->stream>>>(tb, q);                                                  \
     } while (0)
-        switch (Dp / 64) {
+        switch (KCH) {
             case 1: GV_LAUNCH(1); break;
             case 2: GV_LAUNCH(2); break;
             case 3: GV_LAUNCH(3); break;
@@ -281,11 +628,55 @@ int sdk_launch_gemv_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int64_t 
         c->launches++;
         SDK_CUDA(c, cudaGetLastError());
     }
-    pg_launch_merge(c, d_goff, 0, G, nsub, nullptr, tau, ncand, d_cand_row, d_gbound);
-    SDK_CUDA(c, cudaGetLastError());
-    c->slot_g0 = 0;
-    c->slot_g1 = G;
-    c->slot_nsub = nsub;
+    GvTail t;
+    t.goff = (const int64_t*)c->goff.p;
+    t.N = (int32_t)N;
+    t.L = L;
+    t.k = k;
+    t.pool = pool;
+    t.ncand = ncand;
+    t.nslots = nslots;
+    t.D = D;
+    t.pitch = bf16 ? Dp : D;
+    t.is_bf16 = bf16 ? 1 : 0;
+    t.threshold = threshold;
+    t.eps = eps;
+    t.slot_cnt = q.slot_cnt;
+    t.slot_bound = q.slot_bound;
+    t.slot_row = q.slot_row;
+    t.slot_val = q.slot_val;
+    t.bank_ops = bf16 ? c->bank_bf16.p : c->bank_f32.p;
+    t.seg_ops = bf16 ? (const void*)c->seg_bf16.p : (const void*)c->seg_f32.p;
+    t.row_speaker = (const int32_t*)c->row_speaker.p;
+    t.row_trust = (const uint8_t*)c->row_trust.p;
+    t.row_offset = c->row_offset;
+    t.cand_row = (int32_t*)c->cand_row.p;
+    t.cand_val = (float*)c->cand_val.p;
+    t.gbound = (float*)c->gbound.p;
+    t.fb_count = d_flags + SDK_FLAG_FB;
+    t.fb_list = (int32_t*)c->fb_list.p;
+    t.o_row = o_row;
+    t.o_score = o_score;
+    t.o_count = o_count;
+    t.o_trust = o_trust;
+    t.o_spk = o_spk;
+    {
+        sdk_prof_scope ps(c, "select");           // merge + canonical re-score + select + certificate in one launch
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)L);
+        cfg.blockDim = dim3(GV_TAIL_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        SDK_CUDA(c, cudaLaunchKernelEx(&cfg, k_gemv8_tail, t));
+        c->launches++;
+    }
+    c->slot_g0 = c->slot_g1 = 0;                  // no candidate slots of the tcgen05 kind: a failed certificate goes to the exhaustive pass
+    c->slot_nsub = 0;
     c->slot_by_col = false;
     return SDK_OK;
 }

@@ -108,6 +108,169 @@ __global__ void __launch_bounds__(256) k_normalize_generic(const TIn* __restrict
     }
 }
 
+// ---- pool-first stage A (a DIFFERENT algorithm for mean pooling, option "poolfirst"): K1 also accumulates the label
+// centroids.  Mean pooling is linear: mean_t <x_t, b> = <mean_t x_t, b>, so a stage A that only has to be eps-accurate
+// (stage B re-scores the candidates in the canonical arithmetic) can contract G centroids instead of N segments against
+// the bank -- N/G times fewer flops, and the step becomes HBM-bound on this kernel: read 4*D (fp16 input: 2*D), write
+// 2*Dp bytes per segment.  A warp owns 64 consecutive rows (R at a time in flight, as k_normalize_vec), keeps the running
+// sum of the operand values (bf16-rounded for bf16 banks: the values stage B multiplies) of the current label in
+// registers and flushes it with 128-bit vector atomics when the label changes: ~1.3 flushes per 64 rows on config 3.
+// fp32 sums: <= 64 register adds + n/64 atomic adds per label (the certificate's margin model counts them).
+#define SDK_PF_CHUNK 64
+template <int NQ, typename TIn>
+__global__ void __launch_bounds__(256) k_normalize_centroid(const TIn* __restrict__ x, const int32_t* __restrict__ lab, int32_t label_base,
+                                                            int64_t n, int32_t D, int32_t Dp, float* __restrict__ f32out,
+                                                            __nv_bfloat16* __restrict__ bf16out, float* __restrict__ csum, int32_t round_bf16) {
+    constexpr int R = (NQ <= 2) ? 4 : (NQ <= 4 ? 2 : 1);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nq = D >> 2, nqp = Dp >> 2;
+    const int64_t n_chunks = (n + SDK_PF_CHUNK - 1) / SDK_PF_CHUNK;
+    for (int64_t chunk = warp0; chunk < n_chunks; chunk += nwarps) {
+        const int64_t row_lo = chunk * SDK_PF_CHUNK, row_hi = (row_lo + SDK_PF_CHUNK < n) ? row_lo + SDK_PF_CHUNK : n;
+        float4 acc[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int32_t cur = -1;
+        auto flush = [&](int32_t g) {
+            float4* dst = reinterpret_cast<float4*>(csum + (int64_t)g * Dp);
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                const int q = lane + 32 * i;
+                if (q < nq) atomicAdd(dst + q, acc[i]);
+                acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        for (int64_t row0 = row_lo; row0 < row_hi; row0 += R) {
+            float4 v[R][NQ];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool live = row0 + r < row_hi;
+                const TIn* xr = x + (live ? row0 + r : row0) * (int64_t)D;
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) {
+                    int q = lane + 32 * i;
+                    v[r][i] = (live && q < nq) ? sdk_in<TIn>::ld4(xr, q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            int32_t my_lab = -1;
+            if (lane < R && row0 + lane < row_hi) my_lab = lab[row0 + lane] - label_base;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t row = row0 + r;
+                const int32_t g = __shfl_sync(0xffffffffu, my_lab, r);
+                if (row >= row_hi) break;
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) {
+                    double a = (double)v[r][i].x, b = (double)v[r][i].y, c = (double)v[r][i].z, d = (double)v[r][i].w;
+                    s = fma(a, a, s);
+                    s = fma(b, b, s);
+                    s = fma(c, c, s);
+                    s = fma(d, d, s);
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+                float nrm = (float)sqrt(s);
+                float den = nrm > 1e-12f ? nrm : 1e-12f;
+                const float inv = __fdiv_rn(1.0f, den);
+                if (g != cur) {
+                    if (cur >= 0) flush(cur);
+                    cur = g;
+                }
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) {
+                    int q = lane + 32 * i;
+                    float4 o;
+                    o.x = __fmul_rn(v[r][i].x, inv);
+                    o.y = __fmul_rn(v[r][i].y, inv);
+                    o.z = __fmul_rn(v[r][i].z, inv);
+                    o.w = __fmul_rn(v[r][i].w, inv);
+                    if (f32out && q < nq) reinterpret_cast<float4*>(f32out + row * (int64_t)D)[q] = o;
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);   // zero beyond D (v was zero)
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(o.z, o.w);
+                    if (q < nqp) {
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                        reinterpret_cast<uint2*>(bf16out + row * (int64_t)Dp)[q] = pk;
+                    }
+                    if (round_bf16) {
+                        const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+                        o = make_float4(a.x, a.y, b.x, b.y);
+                    }
+                    acc[i].x += o.x; acc[i].y += o.y; acc[i].z += o.z; acc[i].w += o.w;
+                }
+                for (int q = lane + 32 * NQ; q < nqp; q += 32) reinterpret_cast<uint2*>(bf16out + row * (int64_t)Dp)[q] = make_uint2(0u, 0u);
+            }
+        }
+        if (cur >= 0) flush(cur);
+    }
+}
+
+// centroid = sum / n, split into two bf16 rows (hi + lo: 16 significant bits), both doubled so that the generic kernel's
+// mean over the two "segments" of a label gives <hi, b> + <lo, b>.  Rows 2g and 2g+1 of out; goff2[g] = 2 g.
+__global__ void __launch_bounds__(256) k_centroid_split(const float* __restrict__ csum, const int64_t* __restrict__ goff, int32_t G, int32_t Dp,
+                                                        __nv_bfloat16* __restrict__ out, int64_t* __restrict__ goff2) {
+    const int lane = threadIdx.x & 31;
+    const int g = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g > G) return;
+    if (lane == 0) goff2[g] = 2 * (int64_t)g;
+    if (g == G) return;
+    const long long n = goff[g + 1] - goff[g];
+    const float rn = n > 0 ? 1.0f / (float)n : 0.f;
+    for (int e = lane; e < Dp; e += 32) {
+        const float c = csum[(int64_t)g * Dp + e] * rn;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(c);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(c - __bfloat162float(hi));
+        out[(int64_t)(2 * g) * Dp + e] = __float2bfloat16_rn(2.0f * __bfloat162float(hi));
+        out[(int64_t)(2 * g + 1) * Dp + e] = __float2bfloat16_rn(2.0f * __bfloat162float(lo));
+    }
+}
+
+int sdk_poolfirst_applicable(const void* d_x, int32_t in_dtype, int32_t D, int32_t Dp) {
+    return D % 4 == 0 && Dp % 4 == 0 && D <= 2048 && (uintptr_t)d_x % (in_dtype == SDK_IN_F16 ? 8 : 16) == 0;
+}
+
+template <typename TIn>
+static int sdk_launch_normalize_centroid_t(sdk_ctx* c, const TIn* d_x, const int32_t* d_lab, int32_t label_base, int64_t n, int32_t D, int32_t Dp,
+                                           float* d_f32, __nv_bfloat16* d_bf16, float* d_csum, int32_t round_bf16) {
+    const int nq = (D / 4 + 31) / 32;
+    const int64_t chunks = (n + SDK_PF_CHUNK - 1) / SDK_PF_CHUNK;
+    int64_t blocks64 = (chunks + 7) / 8;
+    int blocks = (int)(blocks64 < (int64_t)c->sm_count * 8 ? blocks64 : (int64_t)c->sm_count * 8);
+#define SDK_PF_CASE(NQ) k_normalize_centroid<NQ, TIn><<<blocks, 256, 0, c->stream>>>(d_x, d_lab, label_base, n, D, Dp, d_f32, d_bf16, d_csum, round_bf16)
+    if (nq <= 1) SDK_PF_CASE(1);
+    else if (nq <= 2) SDK_PF_CASE(2);
+    else if (nq <= 4) SDK_PF_CASE(4);
+    else if (nq <= 8) SDK_PF_CASE(8);
+    else SDK_PF_CASE(16);
+#undef SDK_PF_CASE
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}
+
+// K1 + centroids + hi/lo split: d_bf16 [n, Dp] normalised operands, d_cent [2 G, Dp] pseudo-segments, d_goff2 [G + 1]
+int sdk_launch_normalize_centroid(sdk_ctx* c, const void* d_x, int32_t in_dtype, const int32_t* d_lab, int32_t label_base, int64_t n,
+                                  int32_t D, int32_t Dp, float* d_f32, __nv_bfloat16* d_bf16, const int64_t* d_goff, int32_t G,
+                                  float* d_csum, __nv_bfloat16* d_cent, int64_t* d_goff2, int32_t round_bf16) {
+    if (!sdk_poolfirst_applicable(d_x, in_dtype, D, Dp)) return sdk_fail(c, SDK_EINVAL, "pool-first stage A needs D % 4 == 0 and an aligned segment matrix");
+    sdk_prof_scope ps(c, "normalize");
+    SDK_CUDA(c, cudaMemsetAsync(d_csum, 0, (size_t)G * Dp * 4, c->stream));
+    if (n > 0) {
+        if (in_dtype == SDK_IN_F16)
+            SDK_TRY(sdk_launch_normalize_centroid_t<__half>(c, (const __half*)d_x, d_lab, label_base, n, D, Dp, d_f32, d_bf16, d_csum, round_bf16));
+        else
+            SDK_TRY(sdk_launch_normalize_centroid_t<float>(c, (const float*)d_x, d_lab, label_base, n, D, Dp, d_f32, d_bf16, d_csum, round_bf16));
+    }
+    k_centroid_split<<<(unsigned)(((int64_t)G + 1 + 7) / 8), 256, 0, c->stream>>>(d_csum, d_goff, G, Dp, d_cent, d_goff2);
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}
+
 template <typename TIn>
 static int sdk_launch_normalize_t(sdk_ctx* c, const TIn* d_x, int64_t n, int32_t D, int32_t Dp, float* d_f32, __nv_bfloat16* d_bf16) {
     if (n <= 0) return SDK_OK;

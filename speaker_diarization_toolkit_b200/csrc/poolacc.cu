@@ -720,6 +720,214 @@ k_poolacc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     }
 }
 
+// =================================================================================================
+// 2-CTA variant (cta_group::2, option "cta_group" = 2): a cluster of two CTAs issues 256 x 256 x 16 MMAs.  CTA r owns bank
+// rows [.., r*128 .. r*128+127] of every 256-row tile (its half of A and its own accumulators) and HALF of every streamed
+// slab of the interleaved segment matrix (B is split along N across the pair): per CTA the L2 -> SM traffic of the streamed
+// operand and its shared-memory footprint are halved (a B stage is 16 KB: the ring is twice as deep).  The leader CTA
+// issues all MMAs; "full" barriers live in the leader and collect the TMA bytes of both CTAs; "empty" and accumulator-full
+// barriers are signalled in both CTAs by multicast tcgen05.commit; the accumulator-empty barrier lives in the leader and
+// is armed by the epilogue warps of both CTAs.  Unit = (block of 256 columns, pair of row blocks = MT * 256 bank rows).
+// =================================================================================================
+template <int KCH, int MT, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MT == 2 ? PG_THREADS2 : PG_THREADS, 1)
+k_poolacc2(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ PaParams q) {
+    constexpr int NC = PA_NB;
+    constexpr uint32_t A_TILE = 128 * 128;                  // this CTA's 128 rows x 64 bf16 of a 256-row tile
+    constexpr uint32_t A_BYTES = MT * KCH * A_TILE;
+    constexpr uint32_t B_HALF = (NC / 2) * 128;             // this CTA's half of a (step, K chunk) slab
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    constexpr uint32_t NSLOT = 512 / (MT * NC);
+    static_assert(MT * NC <= 512, "TMEM columns");
+    const PgParams& p = q.pg;
+
+    extern __shared__ uint8_t pg_smem_raw[];
+    const uint32_t raw = pg_smem_u32(pg_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sA = base;
+    const uint32_t sB = sA + A_BYTES;
+    const uint32_t sBar = sB + STAGES * B_HALF;
+    const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8 * KCH;
+    const uint32_t bar_b_full = bar_a_empty + 8 * KCH, bar_b_empty = bar_b_full + 8 * STAGES;
+    const uint32_t bar_t_full = bar_b_empty + 8 * STAGES, bar_t_empty = bar_t_full + 8 * NSLOT;
+    const uint32_t s_tmem = bar_t_empty + 8 * NSLOT;
+    uint32_t* s_tmem_ptr = reinterpret_cast<uint32_t*>(pg_smem_raw + (s_tmem - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = pg_cluster_rank();
+    const bool leader = crank == 0;
+    if (warp == 0 && lane == 0) {
+        for (int kc = 0; kc < KCH; ++kc) { pg_mbar_init(bar_a_full + 8 * kc, 1); pg_mbar_init(bar_a_empty + 8 * kc, 1); }
+        for (int s = 0; s < STAGES; ++s) { pg_mbar_init(bar_b_full + 8 * s, 1); pg_mbar_init(bar_b_empty + 8 * s, 1); }
+        for (uint32_t i = 0; i < NSLOT; ++i) { pg_mbar_init(bar_t_full + 8 * i, 1); pg_mbar_init(bar_t_empty + 8 * i, 2 * 4 * MT); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    pg_fence_before();
+    __syncthreads();
+    pg_cluster_sync();                                      // peer barriers are initialised before anyone signals them
+    pg_fence_after();
+    const uint32_t tmem_base = *s_tmem_ptr;
+
+    const int64_t n_units = (int64_t)q.n_blocks * p.RB;     // RB = pairs of row blocks (MT * 256 bank rows each)
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const uint32_t l_a_full = pg_mapa(bar_a_full, 0), l_b_full = pg_mapa(bar_b_full, 0), l_t_empty = pg_mapa(bar_t_empty, 0);
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_bits = 0;
+            for (int64_t u = pair; u < n_units; u += npairs) {
+                const int32_t bl = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)bl * p.RB);
+                const int32_t b = q.block_lo + bl;
+                const int32_t T = q.blockT[b];
+                if (T <= 0) continue;
+                const int64_t s0 = q.step0[b];
+                for (int32_t t = 0; t < T; ++t) {
+                    const int32_t crow = (int32_t)((s0 + t) * NC + crank * (NC / 2));
+#pragma unroll 1
+                    for (int kc = 0; kc < KCH; ++kc) {
+                        if (t == 0) {   // this unit's bank tiles, chunk by chunk, in the order the MMAs will want them
+                            pg_mbar_wait(bar_a_empty + 8 * kc, ((a_bits >> kc) & 1u) ^ 1u);
+                            if (leader) pg_mbar_expect_tx(bar_a_full + 8 * kc, 2 * MT * A_TILE);
+#pragma unroll 1
+                            for (int rt = 0; rt < MT; ++rt)
+                                pg_tma_load_2d_2sm(sA + (rt * KCH + kc) * A_TILE, &tmapA, kc * 64,
+                                                   (int32_t)(((int64_t)rb * MT + rt) * 256 + crank * 128), l_a_full + 8 * kc);
+                            a_bits ^= 1u << kc;
+                        }
+                        pg_mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+                        if (leader) pg_mbar_expect_tx(bar_b_full + 8 * stage, 2 * B_HALF);
+                        pg_tma_load_2d_2sm(sB + stage * B_HALF, &tmapB, kc * 64, crow, l_b_full + 8 * stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only; the whole warp runs the loop, one elected lane issues) =================
+        if (leader) {
+            uint32_t stage = 0, phase = 0, a_bits = 0, uidx = 0;
+            for (int64_t u = pair; u < n_units; u += npairs) {
+                const int32_t bl = (int32_t)(u / p.RB);
+                const int32_t T = q.blockT[q.block_lo + bl];
+                if (T <= 0) continue;
+                const uint32_t slot = uidx % NSLOT, use = uidx / NSLOT;
+                pg_mbar_wait(bar_t_empty + 8 * slot, (use & 1u) ^ 1u);      // both CTAs have read this accumulator set out
+                pg_fence_after();
+                const uint32_t td = tmem_base + slot * (MT * NC);
+                for (int32_t t = 0; t < T; ++t) {
+#pragma unroll 1
+                    for (int kc = 0; kc < KCH; ++kc) {
+                        if (t == 0) {
+                            pg_mbar_wait(bar_a_full + 8 * kc, (a_bits >> kc) & 1u);
+                            a_bits ^= 1u << kc;
+                        }
+                        pg_mbar_wait(bar_b_full + 8 * stage, phase);
+                        pg_fence_after();
+                        const uint64_t db = pg_make_desc(sB + stage * B_HALF);
+                        if (pg_elect_one()) {
+#pragma unroll
+                            for (int rt = 0; rt < MT; ++rt) {
+                                const uint64_t da = pg_make_desc(sA + (rt * KCH + kc) * A_TILE);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    pg_mma_bf16_2sm(td + rt * NC, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC,
+                                                    (t | kc | kk) != 0 ? 1u : 0u);
+                            }
+                            pg_commit_2sm(bar_b_empty + 8 * stage);
+                            if (t == T - 1) pg_commit_2sm(bar_a_empty + 8 * kc);   // the next unit's chunk may be loaded (both CTAs)
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                if (pg_elect_one()) pg_commit_2sm(bar_t_full + 8 * slot);
+                __syncwarp();
+                ++uidx;
+            }
+        }
+    } else {
+        // ================= epilogue (both CTAs): warpgroup wg <-> row tile; thread <-> one of this CTA's 128 bank rows =========
+        const int wq = warp & 3;
+        const int wg = (warp - 2) >> 2;
+        const int rt = MT == 2 ? wg : 0;
+        const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
+        uint32_t uidx = 0;
+        for (int64_t u = pair; u < n_units; u += npairs) {
+            const int32_t bl = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)bl * p.RB);
+            const int32_t b = q.block_lo + bl;
+            if (q.blockT[b] <= 0) continue;
+            const int64_t tile128 = ((int64_t)rb * MT + rt) * 2 + crank;              // index of this CTA's 128-row tile
+            const int64_t row = tile128 * 128 + wq * 32 + lane;
+            const int64_t nsub = (int64_t)p.RB * MT * 8;
+            int32_t gid[NC / 32];
+            float ginv[NC / 32];
+#pragma unroll
+            for (int i = 0; i < NC / 32; ++i) {
+                const int g = q.col_meta[b * NC + i * 32 + lane];
+                gid[i] = g;
+                const int64_t n = g >= 0 ? p.goff[g + 1] - p.goff[g] : 0;
+                ginv[i] = n > 0 ? 1.0f / (float)n : 0.f;
+            }
+            const uint32_t slot = uidx % NSLOT, use = uidx / NSLOT;
+            pg_mbar_wait(bar_t_full + 8 * slot, use & 1u);
+            pg_fence_after();
+            const uint32_t td = tmem_base + slot * (MT * NC);
+            float run = 0.f;                                                          // sum over the columns of one group
+#pragma unroll
+            for (int blk = 0; blk < NC / 32; ++blk) {
+                float v[32];
+                pg_tmem_ld32(td + lane_base + rt * NC + blk * 32, v);
+                pg_tmem_ld_wait();
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc) {
+                    const int g = __shfl_sync(0xffffffffu, gid[blk], cc);
+                    const float inv = __shfl_sync(0xffffffffu, ginv[blk], cc);
+                    if (g == -1) continue;                                            // unused column (uniform)
+                    run += v[cc];
+                    if (g < 0) continue;                                              // inner column: the group goes on
+                    const float val = run * inv;
+                    run = 0.f;
+                    if (inv == 0.f) continue;                                         // empty group
+                    if (p.mode == 1) {
+                        if (row < p.P) p.dense_out[row * (int64_t)p.dense_ld + g] = val;
+                        continue;
+                    }
+                    bool pass = (val >= p.tau) && (row < p.P);
+                    const int64_t pos = (int64_t)b * NC + blk * 32 + cc - p.g_base;   // column inside the batch
+                    if (p.kth) {                                                      // running k-th best (low thresholds only)
+                        const uint32_t thr = pg_kth_load(p, pos, lane);
+                        const uint32_t key = sdk_fkey(val);
+                        pg_kth_update(p, pos, tile128 * 4 + wq, pass ? key : 0u, thr, lane);
+                        pass = pass && key >= thr;
+                    }
+                    const uint32_t mpass = __ballot_sync(0xffffffffu, pass);
+                    if (mpass == 0) continue;                                         // slot counts were zeroed before the launch
+                    pg_flush_write_call(&p, val, pass, mpass, pos * nsub + tile128 * 4 + wq, lane, row);
+                }
+            }
+            pg_fence_before();
+            __syncwarp();
+            if (lane == 0) pg_mbar_arrive_cluster(l_t_empty + 8 * slot);
+            ++uidx;
+        }
+    }
+
+    // ---- teardown: nobody leaves (or frees TMEM) while the pair still signals each other ----
+    pg_fence_before();
+    __syncthreads();
+    pg_cluster_sync();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------
 template <int KCH, int MT, int STAGES, int KH>
 static int pa_launch_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const PaParams& q, int grid) {
@@ -735,6 +943,31 @@ static int pa_launch_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb,
 }
 
 static int pa_mt_for(int kch) { return kch <= 4 ? 2 : 1; }
+
+template <int KCH, int MT, int STAGES>
+static int pa_launch2_t(sdk_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const PaParams& q, int grid) {
+    constexpr size_t smem = (size_t)MT * KCH * 16384 + (size_t)STAGES * (PA_NB / 2) * 128 + 384 + 1024;
+    static_assert(smem <= PG_SMEM_LIMIT, "shared memory budget");
+    auto kern = k_poolacc2<KCH, MT, STAGES>;
+    SDK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, MT == 2 ? PG_THREADS2 : PG_THREADS, smem, c->stream>>>(ta, tb, q);      // __cluster_dims__(2,1,1): grid must be even
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
+    return SDK_OK;
+}
+// cta_group::2: B stages are half as large, so the ring is twice as deep in the same shared memory
+static int pa_launch2(sdk_ctx* c, int kch, const CUtensorMap& ta, const CUtensorMap& tb, const PaParams& q, int grid) {
+    switch (kch) {
+        case 1: return pa_launch2_t<1, 2, 8>(c, ta, tb, q, grid);
+        case 2: return pa_launch2_t<2, 2, 8>(c, ta, tb, q, grid);
+        case 3: return pa_launch2_t<3, 2, 8>(c, ta, tb, q, grid);
+        case 4: return pa_launch2_t<4, 2, 6>(c, ta, tb, q, grid);
+        case 5: return pa_launch2_t<5, 1, 8>(c, ta, tb, q, grid);
+        case 6: return pa_launch2_t<6, 1, 8>(c, ta, tb, q, grid);
+        case 7: return pa_launch2_t<7, 1, 6>(c, ta, tb, q, grid);
+        default: return pa_launch2_t<8, 1, 6>(c, ta, tb, q, grid);
+    }
+}
 
 // (KCH, MT, STAGES, KH).  Shared memory = MT * ceil(KCH / KH) * 16 KB (bank tiles) + STAGES * 32 KB (B ring).  Above 256
 // dimensions one row tile per unit with all K chunks resident measured FASTER (config 4 forced: 10.8 ms) than two row
@@ -876,9 +1109,11 @@ int sdk_launch_poolacc(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype, cons
         SDK_CUDA(c, cudaGetLastError());
     }
     // ---- GEMM (+ merge), in batches of blocks that keep the candidate slots under ~6 GB ----
-    const int64_t rows_per_block = (int64_t)MT * 128;
+    // option "cta_group" = 2: CTA pairs (k_poolacc2); a unit then covers MT * 256 bank rows and RB counts row-block PAIRS
+    const bool cta2 = c->opt_cta_group == 2 && c->sm_count >= 2;
+    const int64_t rows_per_block = (int64_t)MT * (cta2 ? 256 : 128);
     const int32_t RB = (int32_t)((P + rows_per_block - 1) / rows_per_block);
-    const int32_t nsub = RB * MT * 4;
+    const int32_t nsub = RB * MT * (cta2 ? 8 : 4);
     const size_t per_group = (size_t)nsub * (PG_CS * 8 + 8);
     int64_t bbatch = n_blocks;
     if (mode == 0) {
@@ -892,7 +1127,7 @@ int sdk_launch_poolacc(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype, cons
     }
     CUtensorMap ta, tb;
     SDK_TRY(pg_make_tmap(c, &ta, d_rows, P, Dp, 128));
-    SDK_TRY(pg_make_tmap(c, &tb, il.p, n_rows, Dp, PA_NB));
+    SDK_TRY(pg_make_tmap(c, &tb, il.p, n_rows, Dp, cta2 ? PA_NB / 2 : PA_NB));
     for (int64_t ba = 0; ba < n_blocks; ba += bbatch) {
         const int64_t bb = std::min<int64_t>(n_blocks, ba + bbatch);
         PaParams q;
@@ -924,12 +1159,13 @@ int sdk_launch_poolacc(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype, cons
         q.block_lo = (int32_t)ba;
         q.n_blocks = (int32_t)(bb - ba);
         const int64_t n_units = (bb - ba) * RB;
-        const int grid = (int)std::min<int64_t>(n_units, c->sm_count);
+        const int grid = cta2 ? 2 * (int)std::min<int64_t>(n_units, c->sm_count / 2) : (int)std::min<int64_t>(n_units, c->sm_count);
         // slots of columns that are never flushed (inner / unused columns, empty groups) must read as empty
         if (mode == 0) SDK_CUDA(c, cudaMemsetAsync(c->slot_cnt.p, 0, (size_t)(bb - ba) * PA_NB * nsub * 4, c->stream));
         {
             sdk_prof_scope ps(c, "poolgemm");
-            SDK_TRY(pa_launch(c, kch, ta, tb, q, grid));
+            if (cta2) SDK_TRY(pa_launch2(c, kch, ta, tb, q, grid));
+            else SDK_TRY(pa_launch(c, kch, ta, tb, q, grid));
         }
         if (mode == 0) {
             pg_launch_merge(c, d_goff, (int32_t)(ba * PA_NB), (int32_t)((bb - ba) * PA_NB), nsub, col_meta, tau, ncand, d_cand_row, d_gbound);

@@ -100,6 +100,60 @@ def list_all_speakers() -> List[Dict[str, Any]]:
     return out
 
 
+def list_all_speakers_cached() -> List[Dict[str, Any]]:
+    """Same list as `list_all_speakers`, without re-parsing a million unchanged JSON files on every call (SURVEY 8f item 1:
+    the reference's per-call O(P) pass, speaker_detection:206-220, is what a million-profile identify waits for).
+    `db/.profiles.pack` holds the parsed profiles in file order plus every file's (size, mtime_ns); one scandir + stat pass
+    finds what changed, only those files are parsed again, and the pack is rewritten when anything did.  The per-file
+    layout stays authoritative.  SPEAKER_B200_PROFILE_CACHE=0 disables it."""
+    db = get_speakers_db_path()
+    if os.environ.get("SPEAKER_B200_PROFILE_CACHE", "1") == "0" or not db.exists():
+        return list_all_speakers()
+    pack_path = db / ".profiles.pack"
+    cur = {}
+    with os.scandir(db) as it:
+        for e in it:
+            if e.name.endswith(".json") and not e.name.startswith("."):
+                st = e.stat()
+                cur[e.name] = (st.st_size, st.st_mtime_ns)
+    names = sorted(cur)
+    old_stat, old_prof = {}, {}
+    if pack_path.exists():
+        try:
+            with open(pack_path, "r") as fh:
+                pack = json.load(fh)
+            old_stat = {n: tuple(v) for n, v in zip(pack["names"], pack["stats"])}
+            old_prof = dict(zip(pack["names"], pack["profiles"]))
+        except (OSError, ValueError, KeyError):
+            old_stat, old_prof = {}, {}
+    out: List[Dict[str, Any]] = []
+    kept_names, kept_stats = [], []
+    dirty = len(old_stat) != len(cur)
+    for n in names:
+        if old_stat.get(n) == cur[n]:
+            prof = old_prof[n]
+        else:
+            dirty = True
+            try:
+                with open(db / n, "r") as fh:
+                    prof = json.load(fh)
+            except (json.JSONDecodeError, IOError) as exc:
+                print(f"Warning: Failed to load {db / n}: {exc}", file=sys.stderr)
+                continue
+        out.append(prof)
+        kept_names.append(n)
+        kept_stats.append(cur[n])
+    if dirty:
+        try:
+            tmp = pack_path.with_name(pack_path.name + f".{os.getpid()}.tmp")
+            with open(tmp, "w") as fh:
+                json.dump({"names": kept_names, "stats": kept_stats, "profiles": out}, fh)
+            os.replace(tmp, pack_path)
+        except OSError as exc:
+            print(f"Warning: could not update the profile pack: {exc}", file=sys.stderr)
+    return out
+
+
 def filter_speakers_by_tags(speakers, tags: Optional[Sequence[str]] = None, any_tag: bool = False):
     """AND (default) / OR tag filter (speaker_detection:223-246)."""
     if not tags:
@@ -324,12 +378,15 @@ def build_bank_cached(candidates: List[Dict[str, Any]], backend_name: str, dim: 
     root = get_embeddings_path()
     unknown = TRUST_CODES["unknown"]
     keys: List[str] = []
-    paths: List[Optional[Path]] = []
+    paths: List[Any] = []           # str / Path of the vector file, None = not resolved yet (trust mode)
+    sizes: List[int] = []
+    mtimes: List[int] = []
     row_speaker_l: List[int] = []
     row_trust_l: List[int] = []
     emb_ids: List[Optional[str]] = []
     spk_recs = []       # (speaker id, record) of every row, for lazy path resolution
     speaker_ids: List[str] = []
+    root_s = str(root)
     for prof in candidates:
         sid = prof.get("id")
         recs = (prof.get("embeddings") or {}).get(backend_name) or []
@@ -339,13 +396,25 @@ def build_bank_cached(candidates: List[Dict[str, Any]], backend_name: str, dim: 
         used = False
         for rec in recs:
             rid = rec.get("id")
-            if trust_mode:
-                path = None             # resolved only for rows the pack does not hold
-            else:
-                path = vector_path(sid, rec)
-                if path is None:
-                    print(f"Warning: no vector file for {sid}/{rid} ({backend_name})", file=sys.stderr)
-                    continue
+            path = None
+            if not trust_mode:
+                # one stat() per record on the canonical location (existence, size and mtime in a single system call);
+                # the other locations (content-addressed handle, explicit file) only if that one is missing
+                st = None
+                if rid:
+                    path = f"{root_s}/{sid}/{rid}.npy"
+                    try:
+                        st = os.stat(path)
+                    except OSError:
+                        st = None
+                if st is None:
+                    path = vector_path(sid, rec)
+                    if path is None:
+                        print(f"Warning: no vector file for {sid}/{rid} ({backend_name})", file=sys.stderr)
+                        continue
+                    st = path.stat()
+                sizes.append(st.st_size)
+                mtimes.append(st.st_mtime_ns)
             used = True
             keys.append(f"{sid}/{rid}")
             paths.append(path)
@@ -363,7 +432,7 @@ def build_bank_cached(candidates: List[Dict[str, Any]], backend_name: str, dim: 
         # The dimension of the WANTED vectors (not of whatever pack happens to be newest: a store re-enrolled at another D,
         # or tag-filtered sub-banks of different D, must not inherit a stale pack's dimension): a pack that holds the
         # first wanted key with an unchanged source file tells it without opening a .npy; otherwise that file's header.
-        st0 = None if trust_mode else paths[0].stat()
+        st0 = None if trust_mode else os.stat(paths[0])
         for ip in sorted(root.glob(f".bank-{backend_name}-D*.idx.npz")):
             try:
                 d = int(ip.name.split("-D")[-1].split(".")[0])
@@ -386,9 +455,7 @@ def build_bank_cached(candidates: List[Dict[str, Any]], backend_name: str, dim: 
         cache = _load_cache_index(pack_path, idx_path, dim)
     size, mtime = np.zeros(n, np.int64), np.zeros(n, np.int64)
     if not trust_mode:
-        st = [pp.stat() for pp in paths]
-        size = np.fromiter((x.st_size for x in st), np.int64, n)
-        mtime = np.fromiter((x.st_mtime_ns for x in st), np.int64, n)
+        size, mtime = np.asarray(sizes, np.int64), np.asarray(mtimes, np.int64)
     hit = np.zeros(n, bool)
     src = np.zeros(n, np.int64)
     kpos, pack = {}, None
@@ -419,7 +486,7 @@ def build_bank_cached(candidates: List[Dict[str, Any]], backend_name: str, dim: 
             raise ValueError(f"embedding {keys[i]} has dimension {vec.shape[0]}, expected {dim}")
         rows[i] = vec
         if trust_mode:
-            stt = path.stat()
+            stt = os.stat(path)
             size[i], mtime[i] = stt.st_size, stt.st_mtime_ns
     if len(miss) or pack is None:
         try:

@@ -210,6 +210,7 @@ def test_assign_batch_gpus_splits_recordings_and_concatenates(store_with_recordi
     single = json.loads(capsys.readouterr().out)
     _InProcessWorker.real, _InProcessWorker.launched = subprocess.Popen, []
     monkeypatch.setattr(subprocess, "Popen", _InProcessWorker)
+    monkeypatch.setattr(_native, "device_count", lambda: 3)
     assert assign_cli.main(["-q", "assign-batch", str(mpath), "--threshold", "0.2", "--format", "json", "--gpus", "3"]) == 0
     multi = json.loads(capsys.readouterr().out)
     strip = lambda o: {k: v for k, v in o.items() if k != "assigned_at"}

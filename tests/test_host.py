@@ -291,6 +291,36 @@ def test_packed_bank_cache_trust_mode_and_dimension_change(tmp_path, monkeypatch
     assert (tmp_path / "embeddings" / ".bank-b200-D12.f32").exists()
 
 
+def test_profile_pack_equals_the_per_file_listing(tmp_path, monkeypatch):
+    """list_all_speakers_cached: same list and order as the reference's per-file pass; only changed files are parsed again"""
+    import builtins
+    monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(tmp_path))
+    (tmp_path / "db").mkdir()
+    for i in (3, 1, 2):
+        (tmp_path / "db" / f"spk{i}.json").write_text(json.dumps({"id": f"spk{i}", "tags": ["t"] if i == 2 else []}))
+    (tmp_path / "db" / "broken.json").write_text("{nope")
+    plain = store.list_all_speakers()
+    assert [p["id"] for p in plain] == ["spk1", "spk2", "spk3"]
+    assert store.list_all_speakers_cached() == plain and (tmp_path / "db" / ".profiles.pack").exists()
+    assert store.list_all_speakers() == plain                         # the pack is invisible to the per-file glob
+    opened = []
+    real_open = builtins.open
+    monkeypatch.setattr(builtins, "open", lambda f, *a, **k: (opened.append(str(f)), real_open(f, *a, **k))[1])
+    assert store.list_all_speakers_cached() == plain
+    assert [o for o in opened if o.endswith(".json") and "spk" in o] == []       # warm: no profile file opened
+    opened.clear()
+    monkeypatch.setattr(builtins, "open", real_open)
+    import os as _os, time as _time
+    (tmp_path / "db" / "spk2.json").write_text(json.dumps({"id": "spk2", "tags": ["changed"]}))
+    _os.utime(tmp_path / "db" / "spk2.json", ns=(_time.time_ns(), _time.time_ns() + 10**9))
+    (tmp_path / "db" / "spk0.json").write_text(json.dumps({"id": "spk0"}))
+    (tmp_path / "db" / "spk3.json").unlink()
+    got = store.list_all_speakers_cached()
+    assert got == store.list_all_speakers() and [p["id"] for p in got] == ["spk0", "spk1", "spk2"] and got[2]["tags"] == ["changed"]
+    monkeypatch.setenv("SPEAKER_B200_PROFILE_CACHE", "0")
+    assert store.list_all_speakers_cached() == got
+
+
 # ---- enrollment / bank-writing path (SURVEY 8f item 3) ------------------------------------------------------------
 ENROLL_RECORD_KEYS = ["id", "external_id", "source_audio", "source_audio_b3sum", "source_segments", "model_version", "samples",
                       "trust_level", "created_at"]        # speaker_detection:890-901, in this order
