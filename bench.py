@@ -733,8 +733,8 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False, st
         avg_ms = gms / max(1, gl)
         ach = per_launch_flops / (avg_ms * 1e-3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-        kname = "k_poolacc (tcgen05, mean pooling inside the MMA accumulation)" if path == 3 else \
-            f"k_poolgemm (tcgen05 cta_group::{args.cta_group}, {args.pool} pooling in the epilogue)"
+        kname = f"k_poolacc{'' if args.cta_group == 1 else '2'} (tcgen05 cta_group::{1 if args.cta_group == 1 else 2}, mean pooling inside the MMA accumulation)" if path == 3 else \
+            f"k_poolgemm (tcgen05 cta_group::{2 if args.cta_group == 2 else 1}, {args.pool} pooling in the epilogue)"
         roof = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "peak_source": f"{pk_src} bf16 sustained (kernel timed inside a long step)",
                 "frac_of_burst_peak": ach / pk["bf16_tflops"], "algorithmic_flop_per_pair": 2 * D,
@@ -859,7 +859,7 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False, st
                            "segments_per_gpu": N, "label_groups_per_gpu": G, "bank_rows_per_gpu": P, "dim": D, "k": cfg["k"],
                            "threshold": cfg["thr"], "pool": args.pool, "stage_a": stage_a, "parallelism": ("bank-row-sharded x" if sharded else "dp") + str(world),
                            "l2": "working set larger than 2x L2 (no flush needed)" if flush is None else "256 MB flush buffer written between timed iterations",
-                           "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{args.cta_group}", 3: "tcgen05 accumulate-pooling", 4: "bank-stream gemv", 5: "pool-first (label centroids x bank on tcgen05, then the canonical re-score)"}.get(path, str(path)), "certificate_fallback_groups": nfb, "certificate_retry_groups": nretry, "scale": args.scale},
+                           "path": {1: "exact-simt", 2: f"tcgen05 cta_group::{2 if args.cta_group == 2 else 1}", 3: f"tcgen05 accumulate-pooling cta_group::{1 if args.cta_group == 1 else 2}", 4: "bank-stream gemv", 5: "pool-first (label centroids x bank on tcgen05, then the canonical re-score)"}.get(path, str(path)), "certificate_fallback_groups": nfb, "certificate_retry_groups": nretry, "scale": args.scale},
                 "clocks": clk, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_f32": e2e_f32,
                 "parity_sample": par, "parity_sample_e2e": par_e2e, "certificate": cert,
                 "time_to_solution_ms": ms_max / args.steps,
@@ -896,7 +896,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--pool", default="mean", choices=["mean", "max"], help="per-label pooling (north_star (3): mean/max)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the recordings (debug runs only; 1.0 = the named config)")
-    ap.add_argument("--cta-group", type=int, default=1, choices=[1, 2], help="tcgen05 kernel variant (2 = CTA pairs)")
+    ap.add_argument("--cta-group", type=int, default=0, choices=[0, 1, 2], help="tcgen05 kernel variant: 1 single CTA, 2 CTA pairs, 0 auto (pairs for accumulate-pooling)")
     ap.add_argument("--acc", type=int, default=1, choices=[0, 1, 2], help="accumulate-pooling kernel: 0 off, 1 auto, 2 force (A/B runs)")
     ap.add_argument("--kth", type=int, default=1, choices=[0, 1, 2], help="running k-th best pruning of the candidate flush: 0 off, 1 auto, 2 on (A/B runs)")
     ap.add_argument("--stage-a", default="contraction", choices=["contraction", "poolfirst"],

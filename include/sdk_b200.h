@@ -81,7 +81,7 @@ const char* sdk_last_error(sdk_ctx* ctx);
 /* tuning / test knobs: "path" (0 auto, 1 exact SIMT, 2 tcgen05), "eps" (certificate margin),
  * "profile" (1 = record per-kernel CUDA-event times), "cand" (re-scored candidates per label),
  * "chunk_mb" (host-buffer sdk_identify: size of the H2D/compute pipeline chunks, default 128),
- * "cta_group" (1 | 2: tcgen05 kernel variant), "acc" (0 off | 1 auto | 2 force: pool inside the MMA accumulation),
+ * "cta_group" (0 auto | 1 | 2: tcgen05 kernel variant, 2 = CTA pairs; auto takes pairs for accumulate-pooling over many groups), "acc" (0 off | 1 auto | 2 force: pool inside the MMA accumulation),
  * "gemv" (1 = stream the bank on the CUDA cores when there are <= 8 query segments),
  * "kth" (0 off | 1 auto | 2 on: candidate flush prunes against a running per-label bound on the 64th best score),
  * "poolfirst" (0 | 1: mean pooling on the tensor path contracts the label CENTROIDS in stage A -- a different algorithm,

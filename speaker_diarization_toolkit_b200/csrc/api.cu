@@ -194,7 +194,7 @@ int sdk_set_option(sdk_ctx* c, const char* key, double value) {
         if (value < 1 || value > 64) return sdk_fail(c, SDK_EINVAL, "cand must be in 1..64");
         c->opt_cand = (int)value;
     } else if (k == "cta_group") {
-        if (value != 1 && value != 2) return sdk_fail(c, SDK_EINVAL, "cta_group must be 1 or 2");
+        if (value != 0 && value != 1 && value != 2) return sdk_fail(c, SDK_EINVAL, "cta_group must be 0 (auto), 1 or 2");
         c->opt_cta_group = (int)value;
     } else if (k == "acc") {
         if (value != 0 && value != 1 && value != 2) return sdk_fail(c, SDK_EINVAL, "acc must be 0 (off), 1 (auto) or 2 (force)");
@@ -502,13 +502,10 @@ static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg
     const bool need_bf16 = (bf16 || path == 2) && !use_acc;
     if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
     if (need_bf16) SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
+    int64_t pf_rows = 0;
     if (use_pf) {
-        SDK_TRY(sdk_reserve(c, c->cent_sum, (size_t)L * Dp * 4));
-        SDK_TRY(sdk_reserve(c, c->cent_seg, (size_t)2 * L * Dp * 2));
-        SDK_TRY(sdk_reserve(c, c->goff2, (size_t)(L + 1) * 8));
         SDK_TRY(sdk_launch_normalize_centroid(c, d_seg, c->in_dtype, d_seg_label, label_base, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
-                                              (__nv_bfloat16*)c->seg_bf16.p, (const int64_t*)c->goff.p, L, (float*)c->cent_sum.p,
-                                              (__nv_bfloat16*)c->cent_seg.p, (int64_t*)c->goff2.p, bf16 ? 1 : 0));
+                                              (__nv_bfloat16*)c->seg_bf16.p, (const int64_t*)c->goff.p, L, bf16 ? 1 : 0, &pf_rows));
     } else if (!bf16 || need_bf16)
         SDK_TRY(sdk_launch_normalize_in(c, d_seg, c->in_dtype, N, D, Dp, bf16 ? nullptr : (float*)c->seg_f32.p,
                                         need_bf16 ? (__nv_bfloat16*)c->seg_bf16.p : nullptr));
@@ -545,7 +542,7 @@ static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg
         if (use_acc) { eps_chain = 0.5f * 1.05f * u_mma * kc; chain_max = (double)c->pa_chain_max; }
         else if (use_pf) {
             // pool-first: |<hi + lo, b> computed - canonical pooled score| <=  two dot products at operand magnitude 2 (the
-            // doubled halves), the epilogue mean of the two columns (70 * 6.1e-8), the hi/lo split residual (2^-18), the fp32
+            // doubled halves) accumulated in one tile (+ slack 4.3e-6), the hi/lo split residual (2^-18), the fp32
             // centroid (64 register adds: 64 * 2^-24; n/64 atomic adds: 2^-24/64 per segment -> eps_chain), Q30 rounding
             eps_base = (bf16 ? 0.f : 1.2e-2f) + 2.1f * u_mma * kc + 4.3e-6f + 3.9e-6f + 4.1e-6f + 4.8e-7f;
             eps_chain = 9.4e-10f;
@@ -580,9 +577,9 @@ static int sdk_identify_core(sdk_ctx* c, const void* d_seg, const int32_t* d_seg
             if (bf16) seg_grp = ig;                            // bf16 operands live in the interleaved matrix
             acc_grp = ig;
         } else if (use_pf) {
-            SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->cent_seg.p,
-                                                   2 * (int64_t)L, Dp, (const int64_t*)c->goff2.p, L, SDK_POOL_MEAN, tau, ncand,
-                                                   (int32_t*)c->cand_row.p, (float*)c->gbound.p));
+            // the centroid GEMM runs on the accumulate-pooling kernel: one column per label, two steps (hi, lo) per block
+            SDK_TRY(sdk_launch_poolacc_prepared(c, c->cent_seg.p, pf_rows, Dp, (const __nv_bfloat16*)c->bank_bf16.p, P,
+                                                (const int64_t*)c->goff2.p, L, tau, ncand, (int32_t*)c->cand_row.p, (float*)c->gbound.p));
         } else {
             SDK_TRY(sdk_launch_poolgemm_candidates(c, (const __nv_bfloat16*)c->bank_bf16.p, P, (const __nv_bfloat16*)c->seg_bf16.p,
                                                    N, Dp, (const int64_t*)c->goff.p, L, pool, tau, ncand,

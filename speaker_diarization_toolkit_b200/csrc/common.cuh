@@ -83,7 +83,8 @@ struct sdk_ctx {
     double opt_eps = -1.0;     // <0: default by dtype
     int opt_profile = 0;
     int opt_cand = 16;         // re-scored candidates per label group (tensor path)
-    int opt_cta_group = 1;     // tcgen05 path: 1 = single CTA (measured faster at D <= 256), 2 = CTA pairs (cta_group::2)
+    int opt_cta_group = 0;     // tcgen05 kernels: 1 = single CTA, 2 = CTA pairs (cta_group::2), 0 = auto: pairs for accumulate-pooling
+                               // (+3 % on config 3 at equal power: half the L2 -> SM operand stream), single CTA for k_poolgemm
     int opt_acc = 1;           // mean pooling with many label groups: pool inside the MMA accumulation (poolacc.cu)
     int opt_gemv = 1;          // <= 8 query segments: stream the bank once on the CUDA cores (gemv.cu) instead of tcgen05 tiles
     int opt_chunk_mb = 128;    // host-buffer identify: H2D/compute pipeline chunk size
@@ -185,7 +186,7 @@ int sdk_launch_normalize_in(sdk_ctx* c, const void* d_x, int32_t in_dtype, int64
 int sdk_poolfirst_applicable(const void* d_x, int32_t in_dtype, int32_t D, int32_t Dp);
 int sdk_launch_normalize_centroid(sdk_ctx* c, const void* d_x, int32_t in_dtype, const int32_t* d_lab, int32_t label_base, int64_t n,
                                   int32_t D, int32_t Dp, float* d_f32, __nv_bfloat16* d_bf16, const int64_t* d_goff, int32_t G,
-                                  float* d_csum, __nv_bfloat16* d_cent, int64_t* d_goff2, int32_t round_bf16);
+                                  int32_t round_bf16, int64_t* n_rows_out);
 // group offsets from sorted labels; *d_flag != 0 when labels are unsorted / out of range
 int sdk_launch_group_offsets(sdk_ctx* c, const int32_t* d_lab, int64_t N, int32_t L, int32_t label_base,
                              int64_t* d_goff, int32_t* d_flag);
@@ -241,6 +242,9 @@ int sdk_launch_poolacc(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype, cons
                        int32_t Dp, const __nv_bfloat16* d_rows, int64_t P, const int64_t* d_goff, int32_t G, int64_t S,
                        int32_t mode, float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, float* d_dense,
                        sdk_buf& il, const PaGroup** d_grp_out);
+// stage A over an already interleaved matrix whose plan is in c->pa_* (pool-first centroids)
+int sdk_launch_poolacc_prepared(sdk_ctx* c, const void* d_il, int64_t n_rows, int32_t Dp, const __nv_bfloat16* d_rows, int64_t P,
+                                const int64_t* d_goff, int32_t G, float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound);
 // tcgen05 pooled GEMM, dense output out[row, g] (config 5)
 int sdk_launch_poolgemm_dense(sdk_ctx* c, const __nv_bfloat16* d_rows, int64_t P,
                               const __nv_bfloat16* d_cols, int64_t N, int32_t Dp,

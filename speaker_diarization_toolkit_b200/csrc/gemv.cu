@@ -14,28 +14,26 @@
 // A failed certificate (rare) is not handled by a host check inside the call: the label is put on the fall-back list and
 // the library settles it -- exhaustively, in the canonical arithmetic -- when the results are next fetched (api.cu).
 //
-// The stream: a bank tile = 32 rows x Dp bf16, loaded as Dp/64 TMA boxes (64 columns x 32 rows, 128-byte swizzle) that
-// are issued back to back on ONE mbarrier, so the 1 KB rows of the tile are requested within a few hundred nanoseconds of
-// each other (the previous version walked the K chunks of sixteen different tiles round robin through three-deep rings:
-// every DRAM page was opened eight times; 45 % of the HBM peak).  One elected producer thread fills a ring of tiles that
-// the consumer warps share; tile i sits in stage i % nstage and belongs to consumer warp i % nstage (one waiter per mbarrier:
-// it sees every phase), which computes the complete dot products of its 32 rows with the 8 queries: mma.sync m16n8k16 (bf16 in, fp32 accumulate) -- bank rows are the M side (ldmatrix.x4 straight from
-// the swizzled tile, conflict-free), the queries the N side (fragments pre-packed in shared memory).  Every CTA owns a
-// contiguous range of the bank (nchunk * b / grid), so all SMs stream the same number of tiles +- 1.
+// The stream: every CTA owns a contiguous range of the bank (nchunk * b / grid tiles of 32 rows, so all SMs stream the same
+// amount +- one tile); tile j of a pass belongs to warp j % 16, which computes the complete dot products of its 32 rows with
+// the 8 queries on mma.sync m16n8k16 (bf16 in, fp32 accumulate) -- bank rows are the M side, read STRAIGHT FROM GLOBAL
+// MEMORY into the A fragments with 128-bit loads (see k_gemv8), the queries the N side (fragments pre-packed in shared
+// memory).  Two TMA versions were measured first: per-warp rings of 4 KB K-chunk stages (round 1: 45 % of the HBM peak) and
+// a CTA-wide ring of whole 32 KB row tiles (47 %; ncu: DRAM 38 % busy, every tile 8 us from request to release) -- with one
+// elected producer and a handful of stages the number of bytes in flight per SM, not the DRAM, was the bound.
 // Products of bf16 operands are exact in fp32; only the fp32 accumulation order differs from the canonical arithmetic,
 // well inside the certificate's eps (tests/test_gpu_certificate.py measures it).
 #include "tcgen05.cuh"
 
 #define GV_NQ 8
 #define GV_CW 16                     // consumer warps
-#define GV_THREADS (32 * (GV_CW + 1))
+#define GV_THREADS (32 * GV_CW)
 #define GV_ROWS 32                   // bank rows per tile
 #define GV_PASS_TILES 32             // tiles whose raw scores are kept in shared memory before a selection pass
 #define GV_PASS_ROWS (GV_ROWS * GV_PASS_TILES)
 #define GV_RAW_LD (GV_PASS_ROWS + 8) // padded: the fragment stores of the four query pairs land in different banks
 #define GV_KEEP 16                   // kept per (label, CTA, half of the pass)
 #define GV_PARTS 2                   // selection warps per label: 8 labels x 2 = the 16 consumer warps
-#define GV_MAX_STAGES 8
 #define GV_TAIL_THREADS 256
 #define GV_TAIL_CAP 1024             // compacted candidates per label in the tail
 
@@ -47,8 +45,8 @@ struct GvParams {
     int64_t P;
     int32_t pool;
     float tau;
+    const __nv_bfloat16* bank;    // [P, Dp] normalised bf16 bank operands
     int32_t nchunk;               // 32-row tiles of the bank
-    int32_t nstage;               // ring depth
     int32_t nslots;               // lists per query slot = grid * GV_PARTS
     // published by CTA 0 for the tail / the fall-back
     int64_t* goff;                // [L + 1]
@@ -61,8 +59,6 @@ struct GvParams {
     int32_t* slot_row;            // [.., GV_KEEP]
     float* slot_val;
 };
-
-__device__ __forceinline__ void gv_bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(GV_CW * 32) : "memory"); }
 
 // canonical normalise of one row by one warp (oracle/canonical.c step (1); same element -> lane assignment and the same
 // order as k_normalize_vec / k_normalize_generic): bf16 copy into shared memory, optional global copies
@@ -96,52 +92,114 @@ __device__ __forceinline__ unsigned long long gv_warp_max_u64(unsigned long long
     return ((unsigned long long)hi << 32) | lo;
 }
 
-template <int KCH>
+// Top-GV_KEEP of this warp's half of a pass (+ the list kept from earlier passes), by (score desc, row asc).
+// vk[t] = orderable key of row rbase + 32 t (0 = not a candidate).  Fast path: the GV_KEEP-th largest of the 32 per-lane
+// maxima is a lower bound T0 on the GV_KEEP-th best entry, so only the handful of entries >= T0 are compacted (ballots)
+// and ranked exactly; if more than 64 entries survive (clustered data), the extraction loop does it the slow way.
+// Returns the new kept entry of this lane (lanes 0 .. GV_KEEP-1, descending) and raises `bound` to the best dropped score.
+__device__ __forceinline__ unsigned long long gv_select_top(const uint32_t (&vk)[GV_PASS_TILES / GV_PARTS], uint32_t rbase, unsigned long long kept,
+                                                             float& bound, unsigned long long* s_cmp /*[64] per warp*/, int lane) {
+    constexpr int T = GV_PASS_TILES / GV_PARTS;
+    auto comp_of = [&](int t) -> unsigned long long {
+        return vk[t] ? (((unsigned long long)vk[t] << 32) | (0xffffffffu - (rbase + 32u * (uint32_t)t))) : 0ull;
+    };
+    // per-lane maximum (the kept entry of an earlier pass counts as one more value of its lane)
+    unsigned long long lmax = kept;
+#pragma unroll
+    for (int t = 0; t < T; ++t) { const unsigned long long c = comp_of(t); lmax = c > lmax ? c : lmax; }
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const unsigned long long o = __shfl_sync(0xffffffffu, lmax, j);
+        rank += (o > lmax || (o == lmax && j < lane)) ? 1 : 0;
+    }
+    const uint32_t mT = __ballot_sync(0xffffffffu, rank == GV_KEEP - 1);       // ranks are a permutation: exactly one lane
+    const unsigned long long T0 = __shfl_sync(0xffffffffu, lmax, __ffs(mT) - 1); // 0 when fewer than GV_KEEP lanes hold anything
+    // compaction of everything >= T0 (zero keys never pass: T0 == 0 keeps every live entry)
+    int m = 0, nlive = 0;
+    {
+        const bool p = kept != 0ull && kept >= T0;
+        const uint32_t mk = __ballot_sync(0xffffffffu, p);
+        if (p) { const int pos = m + __popc(mk & ((1u << lane) - 1u)); if (pos < 64) s_cmp[pos] = kept; }
+        m += __popc(mk);
+        nlive += __popc(__ballot_sync(0xffffffffu, kept != 0ull));
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const unsigned long long c = comp_of(t);
+        const bool p = c != 0ull && c >= T0;
+        const uint32_t ml = __ballot_sync(0xffffffffu, c != 0ull);
+        if (ml) {
+            const uint32_t mk = __ballot_sync(0xffffffffu, p);
+            if (p) { const int pos = m + __popc(mk & ((1u << lane) - 1u)); if (pos < 64) s_cmp[pos] = c; }
+            m += __popc(mk);
+            nlive += __popc(ml);
+        }
+    }
+    __syncwarp();
+    unsigned long long newkept = 0ull;
+    if (m <= 64) {
+        // exact rank of the survivors: lane holds entries lane and lane + 32
+        const unsigned long long e0 = lane < m ? s_cmp[lane] : 0ull, e1 = lane + 32 < m ? s_cmp[lane + 32] : 0ull;
+        int r0 = 0, r1 = 0;
+        for (int j = 0; j < m; ++j) {
+            const unsigned long long o = s_cmp[j];
+            r0 += o > e0 ? 1 : 0;
+            r1 += o > e1 ? 1 : 0;
+        }
+        __syncwarp();
+        // scatter by rank: positions 0 .. GV_KEEP-1 are the new list, position GV_KEEP is the best dropped entry
+        if (e0 != 0ull && r0 <= GV_KEEP) s_cmp[64 + r0] = e0;
+        if (e1 != 0ull && r1 <= GV_KEEP) s_cmp[64 + r1] = e1;
+        __syncwarp();
+        const int nk = m < GV_KEEP ? m : GV_KEEP;
+        if (lane < nk) newkept = s_cmp[64 + lane];
+        if (m > GV_KEEP) bound = fmaxf(bound, sdk_funkey((uint32_t)(s_cmp[64 + GV_KEEP] >> 32)));
+        else if (nlive > m) bound = fmaxf(bound, sdk_funkey((uint32_t)(T0 >> 32)));   // live entries below T0 were never compacted
+        __syncwarp();
+        return newkept;
+    }
+    // slow path: repeated extraction of the largest key below the last one
+    unsigned long long last = ~0ull;
+#pragma unroll 1
+    for (int it = 0; it <= GV_KEEP; ++it) {
+        unsigned long long best = (kept < last) ? kept : 0ull;
+#pragma unroll
+        for (int t = 0; t < T; ++t) { const unsigned long long c = comp_of(t); best = (c < last && c > best) ? c : best; }
+        best = gv_warp_max_u64(best);
+        if (best == 0ull) break;
+        if (it == GV_KEEP) { bound = fmaxf(bound, sdk_funkey((uint32_t)(best >> 32))); break; }
+        if (lane == it) newkept = best;
+        last = best;
+    }
+    return newkept;
+}
+
+// KB = Dp / 32 (K blocks of 32).  The bank is read straight from global memory into the A fragments: lane (g = lane / 4,
+// c = lane % 4) loads 16 bytes -- the 8 bf16 at k = 32 kb + 8 c .. + 7 -- of bank rows g and g + 8 of a 16-row tile; the four
+// lanes of a quad cover 64 contiguous bytes of a row, a warp instruction 8 rows x 64 B in full 32-byte sectors.  Those 8
+// values feed TWO m16n8k16 MMAs (4 values each: the k index of a dot product may be permuted at will as long as both
+// operands agree, so MMA j takes k = 32 kb + 8 c + 4 j + {0,1} for the fragment's columns {2c, 2c+1} and + {2,3} for
+// {2c+8, 2c+9}); the query fragments are packed in shared memory in the same order.  16 independent 128-bit loads per lane
+// are in flight before the first MMA of a group, sixteen warps per SM: plain loads with that much memory-level parallelism
+// are what K1 reaches 82 % of the HBM peak with; the TMA ring version of this kernel stalled at 47 %.
+template <int KB>
 __global__ void __launch_bounds__(GV_THREADS, 1)
-k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const __grid_constant__ GvParams q) {
+k_gemv8(const __grid_constant__ GvParams q) {
     extern __shared__ uint8_t gv_smem_raw[];
-    __shared__ __align__(8) uint2 s_bq[KCH * 4][32];           // B fragments of every 16-wide K step, per lane
+    __shared__ __align__(8) uint2 s_bq[KB * 2][32];            // B fragments of MMA (kb, j), per lane
     __shared__ int32_t s_lab[GV_NQ];                            // label of query s relative to label_base (clamped)
     __shared__ int32_t s_run[GV_NQ];                            // > 0: query s starts a run of that many queries of one label
-    __shared__ __align__(8) uint64_t s_bar[2 * GV_MAX_STAGES];
-    constexpr uint32_t STAGE_BYTES = KCH * 4096u;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t raw = pg_smem_u32(gv_smem_raw);
-    const uint32_t ring = (raw + 1023u) & ~1023u;                   // the swizzle atom is 1024 bytes
-    uint8_t* dyn = gv_smem_raw + (ring - raw);
-    float* s_raw = reinterpret_cast<float*>(dyn + (size_t)q.nstage * STAGE_BYTES);                      // [GV_NQ][GV_RAW_LD]
+    __shared__ __align__(8) unsigned long long s_cmp[GV_CW][64 + GV_KEEP + 2];
+    const int lane = threadIdx.x & 31, cw = threadIdx.x >> 5;
+    float* s_raw = reinterpret_cast<float*>(gv_smem_raw);                                               // [GV_NQ][GV_RAW_LD]
     __nv_bfloat16* s_q = reinterpret_cast<__nv_bfloat16*>(s_raw + GV_NQ * GV_RAW_LD);                   // [GV_NQ][Dp]
-    const uint32_t bar_full = pg_smem_u32(s_bar), bar_empty = bar_full + 8 * GV_MAX_STAGES;
     // the tail kernel may be scheduled as soon as every CTA has got here (it waits for this grid's completion itself)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < q.nstage; ++s) { pg_mbar_init(bar_full + 8 * s, 1); pg_mbar_init(bar_empty + 8 * s, 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    // this CTA's contiguous range of tiles
+    // this CTA's contiguous range of 32-row tiles
     const int64_t c0 = (int64_t)q.nchunk * blockIdx.x / gridDim.x, c1 = (int64_t)q.nchunk * (blockIdx.x + 1) / gridDim.x;
     const int64_t n_mine = c1 - c0;
-    if (warp == 0) {
-        // ---- producer: the bank stream does not depend on the queries, it starts at once ----
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapBank)) : "memory");
-            for (int64_t i = 0; i < n_mine; ++i) {
-                const int st = (int)(i % q.nstage);
-                const uint32_t use = (uint32_t)(i / q.nstage);
-                pg_mbar_wait(bar_empty + 8 * st, (use & 1u) ^ 1u);
-                pg_mbar_expect_tx(bar_full + 8 * st, STAGE_BYTES);
-                const int32_t row0 = (int32_t)((c0 + i) * GV_ROWS);
-#pragma unroll
-                for (int kc = 0; kc < KCH; ++kc)                       // rows past P: zero fill
-                    pg_tma_load_2d(ring + st * STAGE_BYTES + kc * 4096u, &tmapBank, kc * 64, row0, bar_full + 8 * st);
-            }
-        }
-        return;
-    }
-    // ---- consumers: query preparation (labels, canonical normalise, B fragments) while the first tiles fly ----
-    const int cw = warp - 1;
+    // ---- query preparation: labels, canonical normalise, B fragments ----
     if (cw == 0 && lane < GV_NQ) {
         int32_t l = 0x7fffffff;
         if (lane < q.N) {
@@ -187,7 +245,7 @@ k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const __grid_constant__ Gv
         }
         if (f && lane == 0) atomicOr(q.flags, f);
     }
-    gv_bar_consumers();
+    __syncthreads();
     if (cw == 0 && lane < GV_NQ) {
         int run = 0;
         if (lane < q.N && (lane == 0 || s_lab[lane] != s_lab[lane - 1])) {
@@ -196,70 +254,78 @@ k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const __grid_constant__ Gv
         }
         s_run[lane] = run;
     }
-    // B fragments (mma.sync m16n8k16 "col" operand): lane l holds query n = l / 4, k = 16 * ks + 2 * (l % 4) (+8)
     {
+        // B fragment of MMA (kb, j), lane (n = l / 4, c = l % 4): b0 = q[n][32 kb + 8 c + 4 j + {0,1}], b1 = .. + {2,3}
         const uint32_t* sq32 = reinterpret_cast<const uint32_t*>(s_q);
         const int pitch = q.Dp >> 1;
-        for (int i = threadIdx.x - 32; i < KCH * 4 * 32; i += GV_CW * 32) {
-            const int ks = i >> 5, l = i & 31, n = l >> 2, kw = l & 3;
-            s_bq[ks][l] = make_uint2(sq32[n * pitch + ks * 8 + kw], sq32[n * pitch + ks * 8 + 4 + kw]);
+        for (int i = threadIdx.x; i < KB * 2 * 32; i += GV_THREADS) {
+            const int m = i >> 5, l = i & 31, kb = m >> 1, j = m & 1, n = l >> 2, c = l & 3;
+            const int w = kb * 16 + 4 * c + 2 * j;
+            s_bq[m][l] = make_uint2(sq32[n * pitch + w], sq32[n * pitch + w + 1]);
         }
     }
-    gv_bar_consumers();
+    __syncthreads();
     // ---- selection state of this warp's (query slot, half): kept list in lanes 0..15, bound on everything dropped ----
     const int sel_q = cw >> 1, sel_part = cw & 1;
     const int sel_len = s_run[sel_q];
     unsigned long long kept = 0ull;
     float bound = -3.0e38f;
-    // ldmatrix.x4 source row of this lane inside a 16-row tile, and which 8-wide K half it addresses
-    const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = lane >> 4;
+    const int g8 = lane >> 2, c4 = lane & 3;
+    const uint4* bank = reinterpret_cast<const uint4*>(q.bank);
+    const int64_t pitch16 = q.Dp >> 3;                                 // row pitch in 16-byte units
     for (int64_t pass0 = 0; pass0 < n_mine; pass0 += GV_PASS_TILES) {
         const int npc = (int)((n_mine - pass0) < GV_PASS_TILES ? (n_mine - pass0) : GV_PASS_TILES);
-        // Stage `st` of the ring is consumed by warp `st` and by nobody else: an mbarrier phase wait is only meaningful for a
-        // waiter that sees EVERY phase of the barrier (a warp that skipped two uses of a stage would take the parity of an
-        // older fill for its own).  So the first `nstage` consumer warps do the MMAs (5..8 warps keep up with the ~44 GB/s an
-        // SM gets from HBM many times over); all sixteen take part in the preparation and the selection.
-        for (int64_t i = pass0 + (((int64_t)cw - pass0 % q.nstage) + q.nstage) % q.nstage; cw < q.nstage && i < pass0 + npc; i += q.nstage) {
-            const int j = (int)(i - pass0);
-            const int st = cw;
-            const uint32_t use = (uint32_t)(i / q.nstage);
-            float acc[GV_ROWS / 16][4];
+        for (int j = cw; j < npc; j += GV_CW) {
+            const int64_t row0 = (c0 + pass0 + j) * GV_ROWS;
+            // the four bank rows of this lane (two per 16-row tile); rows past P are read from the last row and dropped later
+            const uint4* rp[4];
 #pragma unroll
-            for (int rt = 0; rt < GV_ROWS / 16; ++rt)
+            for (int h = 0; h < 4; ++h) {
+                int64_t r = row0 + (h >> 1) * 16 + (h & 1) * 8 + g8;
+                r = r < q.P ? r : q.P - 1;
+                rp[h] = bank + r * pitch16 + c4;
+            }
+            float acc[2][4];
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[rt][e] = 0.f;
-            pg_mbar_wait(bar_full + 8 * st, use & 1u);
 #pragma unroll 1
-            for (int kc = 0; kc < KCH; ++kc) {
-                const uint32_t tile = ring + st * STAGE_BYTES + kc * 4096u;
+            for (int kg = 0; kg < KB; kg += 4) {
+                uint4 v[4][4];                                         // [k block of the group][row h]
 #pragma unroll
-                for (int rt = 0; rt < GV_ROWS / 16; ++rt) {
-                    const int r = rt * 16 + lrow;                       // row of the tile; swizzle: 16-byte piece ^= row % 8
+                for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t addr = tile + r * 128 + (((2 * ks + lhalf) ^ (r & 7)) << 4);
-                        uint32_t a0, a1, a2, a3;
-                        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
-                        const uint2 b = s_bq[kc * 4 + ks][lane];
-                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+f"(acc[rt][0]), "+f"(acc[rt][1]), "+f"(acc[rt][2]), "+f"(acc[rt][3])
-                                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+                    for (int h = 0; h < 4; ++h)
+                        v[kb][h] = (kg + kb < KB) ? __ldcs(rp[h] + (kg + kb) * 4) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    if (kg + kb < KB) {
+                        const uint2 b0 = s_bq[(kg + kb) * 2][lane], b1 = s_bq[(kg + kb) * 2 + 1][lane];
+#pragma unroll
+                        for (int rt = 0; rt < 2; ++rt) {
+                            const uint4 lo = v[kb][rt * 2], hi = v[kb][rt * 2 + 1];
+                            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                         : "+f"(acc[rt][0]), "+f"(acc[rt][1]), "+f"(acc[rt][2]), "+f"(acc[rt][3])
+                                         : "r"(lo.x), "r"(hi.x), "r"(lo.y), "r"(hi.y), "r"(b0.x), "r"(b0.y));
+                            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                         : "+f"(acc[rt][0]), "+f"(acc[rt][1]), "+f"(acc[rt][2]), "+f"(acc[rt][3])
+                                         : "r"(lo.z), "r"(hi.z), "r"(lo.w), "r"(hi.w), "r"(b1.x), "r"(b1.y));
+                        }
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) pg_mbar_arrive(bar_empty + 8 * st);         // the stage may be refilled while this warp goes on
             // fragment (row = lane/4 (+8), queries 2*(lane%4), +1) -> s_raw[query][row of the pass]
 #pragma unroll
-            for (int rt = 0; rt < GV_ROWS / 16; ++rt) {
-                const int r = j * GV_ROWS + rt * 16 + (lane >> 2), cq = 2 * (lane & 3);
+            for (int rt = 0; rt < 2; ++rt) {
+                const int r = j * GV_ROWS + rt * 16 + g8, cq = 2 * c4;
                 s_raw[cq * GV_RAW_LD + r] = acc[rt][0];
                 s_raw[(cq + 1) * GV_RAW_LD + r] = acc[rt][1];
                 s_raw[cq * GV_RAW_LD + r + 8] = acc[rt][2];
                 s_raw[(cq + 1) * GV_RAW_LD + r + 8] = acc[rt][3];
             }
         }
-        gv_bar_consumers();                                            // the raw scores of the pass are complete
+        __syncthreads();                                               // the raw scores of the pass are complete
         if (sel_len > 0) {
             // this warp's half of the pass: tiles [sel_part * 16, +16); lane <-> rows lane + 32 t.  Pool the label's queries
             // (ascending), keep the GV_KEEP largest of (new rows, previously kept) by (score desc, row asc)
@@ -280,27 +346,9 @@ k_gemv8(const __grid_constant__ CUtensorMap tmapBank, const __grid_constant__ Gv
                 vk[t] = key;
             }
             const uint32_t rbase = (uint32_t)((c0 + pass0 + sel_part * (GV_PASS_TILES / GV_PARTS)) * GV_ROWS + lane);
-            unsigned long long last = ~0ull, newkept = 0ull;
-#pragma unroll 1
-            for (int it = 0; it <= GV_KEEP; ++it) {
-                unsigned long long best = (kept < last) ? kept : 0ull;
-#pragma unroll
-                for (int t = 0; t < GV_PASS_TILES / GV_PARTS; ++t) {
-                    const unsigned long long comp = vk[t] ? (((unsigned long long)vk[t] << 32) | (0xffffffffu - (rbase + 32u * t))) : 0ull;
-                    best = (comp < last && comp > best) ? comp : best;
-                }
-                best = gv_warp_max_u64(best);
-                if (best == 0ull) break;
-                if (it == GV_KEEP) {                                   // the best row that is NOT kept bounds everything dropped
-                    bound = fmaxf(bound, sdk_funkey((uint32_t)(best >> 32)));
-                    break;
-                }
-                if (lane == it) newkept = best;
-                last = best;
-            }
-            kept = newkept;
+            kept = gv_select_top(vk, rbase, kept, bound, s_cmp[cw], lane);
         }
-        gv_bar_consumers();                                            // s_raw is rewritten by the next pass
+        __syncthreads();                                               // s_raw is rewritten by the next pass
     }
     // ---- publish this warp's list (every (query slot, list) entry is written: unused ones as empty) ----
     {
@@ -382,8 +430,31 @@ __device__ __forceinline__ double gv_dot(const void* __restrict__ a_ops, int64_t
     return acc;
 }
 
+// the same chain over operand rows staged in shared memory (16-byte pieces; n16 pieces cover D)
+template <bool BF16>
+__device__ __forceinline__ double gv_dot_smem(const uint4* __restrict__ a, const uint4* __restrict__ b, int n16) {
+    double acc = 0.0;
+#pragma unroll 4
+    for (int i = 0; i < n16; ++i) {
+        const uint4 ca = a[i], cb = b[i];
+        const uint32_t wa[4] = {ca.x, ca.y, ca.z, ca.w}, wb[4] = {cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            if (BF16) {
+                acc = fma((double)__uint_as_float(wa[h] << 16), (double)__uint_as_float(wb[h] << 16), acc);
+                acc = fma((double)__uint_as_float(wa[h] & 0xffff0000u), (double)__uint_as_float(wb[h] & 0xffff0000u), acc);
+            } else {
+                acc = fma((double)__uint_as_float(wa[h]), (double)__uint_as_float(wb[h]), acc);
+            }
+        }
+    }
+    return acc;
+}
+
+#define GV_TAIL_CHUNK 16             // candidate rows staged at a time
 __global__ void __launch_bounds__(GV_TAIL_THREADS)
 k_gemv8_tail(const __grid_constant__ GvTail p) {
+    extern __shared__ uint4 s_stage[];                         // [GV_NQ segment rows + GV_TAIL_CHUNK bank rows][row16 + 1]
     __shared__ unsigned long long s_max[2 * 148 + 8];          // list maxima (grid <= 148 CTAs x 2 lists)
     __shared__ unsigned long long s_key[GV_TAIL_CAP];          // compacted candidates
     __shared__ unsigned long long s_sel[64];                   // the ncand best, by rank
@@ -488,27 +559,66 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
         p.cand_row[(int64_t)g * ncand + i] = (int32_t)(0xffffffffu - (uint32_t)s_sel[i]);
         p.cand_val[(int64_t)g * ncand + i] = sdk_funkey((uint32_t)(s_sel[i] >> 32));
     }
-    // ---- 5. stage B: canonical pooled scores of the candidates (thread = (candidate, segment) pair) ----
-    for (int pr = tid; pr < nc * n; pr += GV_TAIL_THREADS) {
-        const int j = pr / n, t = pr - j * n;
-        const int64_t row = (int64_t)(0xffffffffu - (uint32_t)s_sel[j]);
-        const double sc = p.is_bf16 ? gv_dot<true>(p.seg_ops, s0 + t, p.bank_ops, row, p.pitch, p.D)
-                                    : gv_dot<false>(p.seg_ops, s0 + t, p.bank_ops, row, p.pitch, p.D);
-        const long long qv = __double2ll_rn(sc * SDK_Q30);
-        if (p.pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_pool[j]), (unsigned long long)qv);
-        else atomicMax(&s_pool[j], qv);
+    // ---- 5. stage B: canonical pooled scores of the candidates (thread = (candidate, segment) pair).  The operand rows are
+    //         staged in shared memory by the whole CTA first (coalesced, all loads in flight): a serial fp64 chain fed from
+    //         global memory waits a DRAM round trip per 16 bytes (measured: 41 us for this kernel, 8 labels x 16 x 1 KB) ----
+    const int row_bytes = p.is_bf16 ? p.pitch * 2 : p.pitch * 4;
+    if ((row_bytes & 15) == 0) {
+        const int row16 = row_bytes >> 4, ld16 = row16 + 1;        // + 16 bytes: rows of different candidates in different banks
+        const int n16 = p.is_bf16 ? (p.D + 7) >> 3 : p.D >> 2;
+        uint4* s_seg = s_stage;
+        uint4* s_row = s_stage + GV_NQ * ld16;
+        const uint4* gseg = reinterpret_cast<const uint4*>(p.seg_ops);
+        const uint4* gbank = reinterpret_cast<const uint4*>(p.bank_ops);
+        for (int idx = tid; idx < n * row16; idx += GV_TAIL_THREADS) {
+            const int t = idx / row16, i = idx - t * row16;
+            s_seg[t * ld16 + i] = __ldg(gseg + (s0 + t) * (int64_t)row16 + i);
+        }
+        for (int cb = 0; cb < nc; cb += GV_TAIL_CHUNK) {
+            const int cc = nc - cb < GV_TAIL_CHUNK ? nc - cb : GV_TAIL_CHUNK;
+            __syncthreads();                                       // the previous chunk has been consumed
+            for (int idx = tid; idx < cc * row16; idx += GV_TAIL_THREADS) {
+                const int j = idx / row16, i = idx - j * row16;
+                const int64_t row = (int64_t)(0xffffffffu - (uint32_t)s_sel[cb + j]);
+                s_row[j * ld16 + i] = __ldg(gbank + row * row16 + i);
+            }
+            __syncthreads();
+            for (int pr = tid; pr < cc * n; pr += GV_TAIL_THREADS) {
+                const int j = pr / n, t = pr - j * n;
+                const double sc = p.is_bf16 ? gv_dot_smem<true>(s_seg + t * ld16, s_row + j * ld16, n16)
+                                            : gv_dot_smem<false>(s_seg + t * ld16, s_row + j * ld16, n16);
+                const long long qv = __double2ll_rn(sc * SDK_Q30);
+                if (p.pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_pool[cb + j]), (unsigned long long)qv);
+                else atomicMax(&s_pool[cb + j], qv);
+            }
+        }
+    } else {
+        for (int pr = tid; pr < nc * n; pr += GV_TAIL_THREADS) {   // fp32 rows that are not 16-byte multiples: straight from global
+            const int j = pr / n, t = pr - j * n;
+            const int64_t row = (int64_t)(0xffffffffu - (uint32_t)s_sel[j]);
+            const double sc = gv_dot<false>(p.seg_ops, s0 + t, p.bank_ops, row, p.pitch, p.D);
+            const long long qv = __double2ll_rn(sc * SDK_Q30);
+            if (p.pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_pool[j]), (unsigned long long)qv);
+            else atomicMax(&s_pool[j], qv);
+        }
     }
     __syncthreads();
     // ---- 6. row -> speaker max, threshold, ordered top-k, certificate (k_select's semantics), one warp ----
     if (warp != 0) return;
     unsigned long long key0 = 0ull, key1 = 0ull;
+    int32_t spk0 = -1, spk1 = -1;
+    uint32_t tr0 = SDK_TRUST_UNKNOWN, tr1 = SDK_TRUST_UNKNOWN;
     if (lane < nc) {
         const uint32_t row = 0xffffffffu - (uint32_t)s_sel[lane];
         key0 = ((unsigned long long)sdk_fkey(sdk_pool_finish(s_pool[lane], n, p.pool)) << 32) | (0xffffffffu - row);
+        spk0 = p.row_speaker[row];                                  // every candidate's speaker / trust is fetched up front:
+        if (p.row_trust) tr0 = p.row_trust[row];                    // the extraction loop below then never waits for memory
     }
     if (lane + 32 < nc) {
         const uint32_t row = 0xffffffffu - (uint32_t)s_sel[lane + 32];
         key1 = ((unsigned long long)sdk_fkey(sdk_pool_finish(s_pool[lane + 32], n, p.pool)) << 32) | (0xffffffffu - row);
+        spk1 = p.row_speaker[row];
+        if (p.row_trust) tr1 = p.row_trust[row];
     }
     unsigned long long last = ~0ull;
     int cnt = 0;
@@ -522,7 +632,10 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
         const float sim = sdk_funkey((uint32_t)(best >> 32));
         if (!((double)sim >= p.threshold)) break;
         const int32_t row = (int32_t)(0xffffffffu - (uint32_t)best);
-        const int32_t spk = p.row_speaker[row];
+        const uint32_t m0 = __ballot_sync(0xffffffffu, key0 == best), m1 = __ballot_sync(0xffffffffu, key1 == best);
+        const int src = m0 ? __ffs(m0) - 1 : __ffs(m1) - 1;
+        const int32_t spk = __shfl_sync(0xffffffffu, m0 ? spk0 : spk1, src);
+        const uint32_t tr = __shfl_sync(0xffffffffu, m0 ? tr0 : tr1, src);
         bool dup = false;
         for (int i = 0; i < cnt; ++i) dup |= s_spk[i] == spk;
         if (dup) continue;
@@ -530,7 +643,7 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
             s_spk[cnt] = spk;
             p.o_row[(int64_t)g * k + cnt] = (int64_t)row + p.row_offset;
             p.o_score[(int64_t)g * k + cnt] = sim;
-            p.o_trust[(int64_t)g * k + cnt] = p.row_trust ? p.row_trust[row] : SDK_TRUST_UNKNOWN;
+            p.o_trust[(int64_t)g * k + cnt] = (uint8_t)tr;
             p.o_spk[(int64_t)g * k + cnt] = spk;
         }
         __syncwarp();
@@ -561,16 +674,11 @@ int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype
     const bool bf16 = c->dtype == SDK_DTYPE_BF16;
     if (!sdk_gemv_applicable(N, Dp)) return sdk_fail(c, SDK_EINVAL, "gemv path: needs 1..8 segments and a supported D");
     if (P > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "gemv path: at most 2^31-1 bank rows");
-    if (!c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "gemv path: cuTensorMapEncodeTiled unavailable");
     if (ncand > 64) ncand = 64;
-    const int KCH = Dp / 64;
     const int32_t nchunk = (int32_t)((P + GV_ROWS - 1) / GV_ROWS);
     const int grid = (int)std::min<int64_t>(nchunk, std::min(c->sm_count, 148));
     const int32_t nslots = grid * GV_PARTS;
-    const size_t fixed = (size_t)GV_NQ * GV_RAW_LD * 4 + (size_t)GV_NQ * Dp * 2 + 1024;
-    int nstage = (int)((PG_SMEM_LIMIT - 12288 - fixed) / ((size_t)KCH * 4096));       // 12 KB: the kernel's static shared memory
-    nstage = std::max(2, std::min(nstage, GV_MAX_STAGES));
-    const size_t smem = (size_t)nstage * KCH * 4096 + fixed;
+    const size_t smem = (size_t)GV_NQ * GV_RAW_LD * 4 + (size_t)GV_NQ * Dp * 2;
     SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
     SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
     if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
@@ -595,7 +703,7 @@ int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype
     q.pool = pool;
     q.tau = tau;
     q.nchunk = nchunk;
-    q.nstage = nstage;
+    q.bank = (const __nv_bfloat16*)c->bank_bf16.p;
     q.nslots = nslots;
     q.goff = (int64_t*)c->goff.p;
     q.flags = d_flags + SDK_FLAG_LABEL;
@@ -605,24 +713,22 @@ int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype
     q.slot_bound = (float*)c->slot_bound.p;
     q.slot_row = (int32_t*)c->slot_row.p;
     q.slot_val = (float*)c->slot_val.p;
-    CUtensorMap tb;
-    SDK_TRY(pg_make_tmap(c, &tb, c->bank_bf16.p, P, Dp, GV_ROWS));
     {
         sdk_prof_scope ps(c, "poolgemm");         // stage A of the certified top-k, whichever kernel runs it
 #define GV_LAUNCH(K)                                                                                            \
     do {                                                                                                            \
         SDK_CUDA(c, cudaFuncSetAttribute(k_gemv8<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        k_gemv8<K><<<grid, GV_THREADS, smem, c->stream>>>(tb, q);                                                  \
+        k_gemv8<K><<<grid, GV_THREADS, smem, c->stream>>>(q);                                                      \
     } while (0)
-        switch (KCH) {
-            case 1: GV_LAUNCH(1); break;
+        switch (Dp / 32) {
             case 2: GV_LAUNCH(2); break;
-            case 3: GV_LAUNCH(3); break;
             case 4: GV_LAUNCH(4); break;
-            case 5: GV_LAUNCH(5); break;
             case 6: GV_LAUNCH(6); break;
-            case 7: GV_LAUNCH(7); break;
-            default: GV_LAUNCH(8); break;
+            case 8: GV_LAUNCH(8); break;
+            case 10: GV_LAUNCH(10); break;
+            case 12: GV_LAUNCH(12); break;
+            case 14: GV_LAUNCH(14); break;
+            default: GV_LAUNCH(16); break;
         }
 #undef GV_LAUNCH
         c->launches++;
@@ -665,7 +771,10 @@ int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)L);
         cfg.blockDim = dim3(GV_TAIL_THREADS);
-        cfg.dynamicSmemBytes = 0;
+        const int row_bytes = bf16 ? Dp * 2 : D * 4;
+        const size_t tail_smem = (row_bytes & 15) == 0 ? (size_t)(GV_NQ + GV_TAIL_CHUNK) * (row_bytes + 16) : 16;
+        SDK_CUDA(c, cudaFuncSetAttribute(k_gemv8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+        cfg.dynamicSmemBytes = tail_smem;
         cfg.stream = c->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -209,23 +209,48 @@ __global__ void __launch_bounds__(256) k_normalize_centroid(const TIn* __restric
     }
 }
 
-// centroid = sum / n, split into two bf16 rows (hi + lo: 16 significant bits), both doubled so that the generic kernel's
-// mean over the two "segments" of a label gives <hi, b> + <lo, b>.  Rows 2g and 2g+1 of out; goff2[g] = 2 g.
-__global__ void __launch_bounds__(256) k_centroid_split(const float* __restrict__ csum, const int64_t* __restrict__ goff, int32_t G, int32_t Dp,
-                                                        __nv_bfloat16* __restrict__ out, int64_t* __restrict__ goff2) {
+// centroid = sum / n, split into two bf16 rows (hi + lo: 16 significant bits), both doubled so that the MEAN over the two
+// "segments" of a label gives <hi, b> + <lo, b>.  The rows are written straight into the accumulate-pooling layout
+// (poolacc.cu) together with its plan: one accumulator column per label, blocks of 256 labels, two steps per block --
+// row of (label g, half t) = ((g / 256) * 2 + t) * 256 + g % 256; the unused columns of the last block are zero rows.
+// goff2[g] = 2 g (every label "has" two segments).
+#define SDK_PF_NB 256
+__global__ void __launch_bounds__(256) k_centroid_split_plan(const float* __restrict__ csum, const int64_t* __restrict__ goff, int32_t G, int32_t Dp,
+                                                             __nv_bfloat16* __restrict__ out, int64_t* __restrict__ goff2,
+                                                             int32_t* __restrict__ col_group, int32_t* __restrict__ blockT,
+                                                             int64_t* __restrict__ step0, PaGroup* __restrict__ grp, int32_t* __restrict__ col_last) {
     const int lane = threadIdx.x & 31;
-    const int g = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (g > G) return;
-    if (lane == 0) goff2[g] = 2 * (int64_t)g;
-    if (g == G) return;
-    const long long n = goff[g + 1] - goff[g];
-    const float rn = n > 0 ? 1.0f / (float)n : 0.f;
+    const int col = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);       // one warp per accumulator column
+    const int n_blocks = (G + SDK_PF_NB - 1) / SDK_PF_NB;
+    if (col >= n_blocks * SDK_PF_NB) return;
+    const int b = col / SDK_PF_NB, j = col % SDK_PF_NB;
+    const int g = col < G ? col : -1;
+    const int64_t r0 = ((int64_t)b * 2) * SDK_PF_NB + j, r1 = r0 + SDK_PF_NB;
+    if (lane == 0) {
+        col_group[col] = g;
+        if (j == 0) { blockT[b] = 2; step0[b] = 2 * (int64_t)b; if (b == n_blocks - 1) step0[n_blocks] = 2 * (int64_t)n_blocks; }
+        if (g >= 0) {
+            goff2[g] = 2 * (int64_t)g;
+            if (g == G - 1) goff2[G] = 2 * (int64_t)G;
+            PaGroup r;
+            r.goff0 = 2 * (int64_t)g;
+            r.base = (int32_t)r0;
+            r.c = 1;
+            grp[g] = r;
+            col_last[g] = col;
+        }
+    }
+    float rn = 0.f;
+    if (g >= 0) {
+        const long long n = goff[g + 1] - goff[g];
+        rn = n > 0 ? 1.0f / (float)n : 0.f;
+    }
     for (int e = lane; e < Dp; e += 32) {
-        const float c = csum[(int64_t)g * Dp + e] * rn;
+        const float c = g >= 0 ? csum[(int64_t)g * Dp + e] * rn : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(c);
         const __nv_bfloat16 lo = __float2bfloat16_rn(c - __bfloat162float(hi));
-        out[(int64_t)(2 * g) * Dp + e] = __float2bfloat16_rn(2.0f * __bfloat162float(hi));
-        out[(int64_t)(2 * g + 1) * Dp + e] = __float2bfloat16_rn(2.0f * __bfloat162float(lo));
+        out[r0 * Dp + e] = __float2bfloat16_rn(2.0f * __bfloat162float(hi));
+        out[r1 * Dp + e] = __float2bfloat16_rn(2.0f * __bfloat162float(lo));
     }
 }
 
@@ -252,12 +277,25 @@ static int sdk_launch_normalize_centroid_t(sdk_ctx* c, const TIn* d_x, const int
     return SDK_OK;
 }
 
-// K1 + centroids + hi/lo split: d_bf16 [n, Dp] normalised operands, d_cent [2 G, Dp] pseudo-segments, d_goff2 [G + 1]
+// K1 + centroids + hi/lo split.  d_bf16 [n, Dp] = normalised operands (stage B); the pseudo-segments of the centroids go
+// into c->cent_seg in the accumulate-pooling layout with their plan in c->pa_* (see k_centroid_split_plan); returns the
+// number of rows of that matrix.
 int sdk_launch_normalize_centroid(sdk_ctx* c, const void* d_x, int32_t in_dtype, const int32_t* d_lab, int32_t label_base, int64_t n,
                                   int32_t D, int32_t Dp, float* d_f32, __nv_bfloat16* d_bf16, const int64_t* d_goff, int32_t G,
-                                  float* d_csum, __nv_bfloat16* d_cent, int64_t* d_goff2, int32_t round_bf16) {
+                                  int32_t round_bf16, int64_t* n_rows_out) {
     if (!sdk_poolfirst_applicable(d_x, in_dtype, D, Dp)) return sdk_fail(c, SDK_EINVAL, "pool-first stage A needs D % 4 == 0 and an aligned segment matrix");
+    const int32_t n_blocks = (G + SDK_PF_NB - 1) / SDK_PF_NB;
+    const int64_t n_rows = (int64_t)n_blocks * 2 * SDK_PF_NB;
+    SDK_TRY(sdk_reserve(c, c->cent_sum, (size_t)G * Dp * 4));
+    SDK_TRY(sdk_reserve(c, c->cent_seg, (size_t)n_rows * Dp * 2));
+    SDK_TRY(sdk_reserve(c, c->goff2, (size_t)(G + 1) * 8));
+    SDK_TRY(sdk_reserve(c, c->pa_col_group, (size_t)n_blocks * SDK_PF_NB * 4));
+    SDK_TRY(sdk_reserve(c, c->pa_blockT, (size_t)n_blocks * 4));
+    SDK_TRY(sdk_reserve(c, c->pa_step0, (size_t)(n_blocks + 1) * 8));
+    SDK_TRY(sdk_reserve(c, c->pa_grp, (size_t)G * sizeof(PaGroup)));
+    SDK_TRY(sdk_reserve(c, c->pa_col_last, (size_t)G * 4));
     sdk_prof_scope ps(c, "normalize");
+    float* d_csum = (float*)c->cent_sum.p;
     SDK_CUDA(c, cudaMemsetAsync(d_csum, 0, (size_t)G * Dp * 4, c->stream));
     if (n > 0) {
         if (in_dtype == SDK_IN_F16)
@@ -265,9 +303,15 @@ int sdk_launch_normalize_centroid(sdk_ctx* c, const void* d_x, int32_t in_dtype,
         else
             SDK_TRY(sdk_launch_normalize_centroid_t<float>(c, (const float*)d_x, d_lab, label_base, n, D, Dp, d_f32, d_bf16, d_csum, round_bf16));
     }
-    k_centroid_split<<<(unsigned)(((int64_t)G + 1 + 7) / 8), 256, 0, c->stream>>>(d_csum, d_goff, G, Dp, d_cent, d_goff2);
+    k_centroid_split_plan<<<(unsigned)(((int64_t)n_blocks * SDK_PF_NB + 7) / 8), 256, 0, c->stream>>>(
+        d_csum, d_goff, G, Dp, (__nv_bfloat16*)c->cent_seg.p, (int64_t*)c->goff2.p, (int32_t*)c->pa_col_group.p, (int32_t*)c->pa_blockT.p,
+        (int64_t*)c->pa_step0.p, (PaGroup*)c->pa_grp.p, (int32_t*)c->pa_col_last.p);
     c->launches++;
     SDK_CUDA(c, cudaGetLastError());
+    c->pa_blocks = n_blocks;
+    c->pa_split = false;
+    c->pa_chain_max = 2;
+    if (n_rows_out) *n_rows_out = n_rows;
     return SDK_OK;
 }
 

@@ -1056,6 +1056,90 @@ int sdk_poolacc_plan(sdk_ctx* c, const int64_t* d_goff, int32_t G, int64_t N, in
     return SDK_OK;
 }
 
+// The GEMM (+ merge) over a prepared interleaved matrix and the plan in c->pa_* (n_blocks = c->pa_blocks), in batches of
+// blocks that keep the candidate slots under ~6 GB.
+static int pa_gemm(sdk_ctx* c, const void* il_p, int64_t n_rows, int32_t Dp, const __nv_bfloat16* d_rows, int64_t P, const int64_t* d_goff,
+                   int32_t G, int32_t mode, float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound, float* d_dense) {
+    const int kch = Dp / 64, MT = pa_mt_for(kch);
+    const int32_t n_blocks = c->pa_blocks;
+    const int64_t* step0 = (const int64_t*)c->pa_step0.p;
+    const int32_t* col_group = (const int32_t*)c->pa_col_group.p;
+    const int32_t* col_meta = c->pa_split ? (const int32_t*)c->pa_col_meta.p : col_group;    // c == 1: every column is a last column
+    // ---- GEMM (+ merge), in batches of blocks that keep the candidate slots under ~6 GB ----
+    // option "cta_group" = 2: CTA pairs (k_poolacc2); a unit then covers MT * 256 bank rows and RB counts row-block PAIRS
+    // (auto: many one-column groups -- config 3, the pool-first centroids; the column-split plans of a few large groups
+    //  were tuned against the single-CTA schedule and stay there)
+    const bool cta2 = c->sm_count >= 2 && (c->opt_cta_group == 2 || (c->opt_cta_group == 0 && mode == 0 && !c->pa_split && n_blocks >= 64));
+    const int64_t rows_per_block = (int64_t)MT * (cta2 ? 256 : 128);
+    const int32_t RB = (int32_t)((P + rows_per_block - 1) / rows_per_block);
+    const int32_t nsub = RB * MT * (cta2 ? 8 : 4);
+    const size_t per_group = (size_t)nsub * (PG_CS * 8 + 8);
+    int64_t bbatch = n_blocks;
+    if (mode == 0) {
+        bbatch = (int64_t)((size_t)(6144ull << 20) / (per_group * PA_NB));
+        if (bbatch < 1) bbatch = 1;
+        if (bbatch > n_blocks) bbatch = n_blocks;
+        SDK_TRY(sdk_reserve(c, c->slot_cnt, (size_t)bbatch * PA_NB * nsub * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_bound, (size_t)bbatch * PA_NB * nsub * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)bbatch * PA_NB * nsub * PG_CS * 4));
+        SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)bbatch * PA_NB * nsub * PG_CS * 4));
+    }
+    CUtensorMap ta, tb;
+    SDK_TRY(pg_make_tmap(c, &ta, d_rows, P, Dp, 128));
+    SDK_TRY(pg_make_tmap(c, &tb, il_p, n_rows, Dp, cta2 ? PA_NB / 2 : PA_NB));
+    for (int64_t ba = 0; ba < n_blocks; ba += bbatch) {
+        const int64_t bb = std::min<int64_t>(n_blocks, ba + bbatch);
+        PaParams q;
+        q.pg.goff = d_goff;
+        q.pg.range_g = nullptr;
+        q.pg.n_ranges = 0;
+        q.pg.RB = RB;
+        q.pg.P = P;
+        q.pg.g_base = (int32_t)(ba * PA_NB);
+        q.pg.pool = SDK_POOL_MEAN;
+        q.pg.tau = tau;
+        q.pg.mode = mode;
+        q.pg.slot_cnt = (int32_t*)c->slot_cnt.p;
+        q.pg.slot_row = (int32_t*)c->slot_row.p;
+        q.pg.slot_val = (float*)c->slot_val.p;
+        q.pg.slot_bound = (float*)c->slot_bound.p;
+        q.pg.dense_out = d_dense;
+        q.pg.dense_ld = G;
+        q.pg.nsub = nsub;
+        q.pg.kth = nullptr;
+        if (mode == 0 && c->kth_on) {
+            SDK_TRY(sdk_reserve(c, c->kth, (size_t)bbatch * PA_NB * PG_KTH * 4));
+            SDK_CUDA(c, cudaMemsetAsync(c->kth.p, 0, (size_t)(bb - ba) * PA_NB * PG_KTH * 4, c->stream));
+            q.pg.kth = (uint32_t*)c->kth.p;
+        }
+        q.col_meta = col_meta;
+        q.blockT = (const int32_t*)c->pa_blockT.p;
+        q.step0 = step0;
+        q.block_lo = (int32_t)ba;
+        q.n_blocks = (int32_t)(bb - ba);
+        const int64_t n_units = (bb - ba) * RB;
+        const int grid = cta2 ? 2 * (int)std::min<int64_t>(n_units, c->sm_count / 2) : (int)std::min<int64_t>(n_units, c->sm_count);
+        // slots of columns that are never flushed (inner / unused columns, empty groups) must read as empty
+        if (mode == 0) SDK_CUDA(c, cudaMemsetAsync(c->slot_cnt.p, 0, (size_t)(bb - ba) * PA_NB * nsub * 4, c->stream));
+        {
+            sdk_prof_scope ps(c, "poolgemm");
+            if (cta2) SDK_TRY(pa_launch2(c, kch, ta, tb, q, grid));
+            else SDK_TRY(pa_launch(c, kch, ta, tb, q, grid));
+        }
+        if (mode == 0) {
+            pg_launch_merge(c, d_goff, (int32_t)(ba * PA_NB), (int32_t)((bb - ba) * PA_NB), nsub, col_meta, tau, ncand, d_cand_row, d_gbound);
+            SDK_CUDA(c, cudaGetLastError());
+        }
+    }
+    if (mode == 0 && bbatch >= n_blocks) {     // one batch: every label's candidate slots are still in memory (second chance)
+        c->slot_g0 = 0;
+        c->slot_g1 = G;
+        c->slot_nsub = nsub;
+        c->slot_by_col = true;
+    }
+    return SDK_OK;
+}
+
 // Normalises the raw segments into the planned interleaved layout (buffer `il`), runs the accumulate-pooling GEMM and,
 // in candidate mode, the slot merge.  `S` = steps from sdk_poolacc_plan (same goff, no other plan in between).
 int sdk_launch_poolacc(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype, const int32_t* d_seg_label, int32_t label_base, int64_t N, int32_t D,
@@ -1108,75 +1192,14 @@ int sdk_launch_poolacc(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype, cons
         c->launches += 2;
         SDK_CUDA(c, cudaGetLastError());
     }
-    // ---- GEMM (+ merge), in batches of blocks that keep the candidate slots under ~6 GB ----
-    // option "cta_group" = 2: CTA pairs (k_poolacc2); a unit then covers MT * 256 bank rows and RB counts row-block PAIRS
-    const bool cta2 = c->opt_cta_group == 2 && c->sm_count >= 2;
-    const int64_t rows_per_block = (int64_t)MT * (cta2 ? 256 : 128);
-    const int32_t RB = (int32_t)((P + rows_per_block - 1) / rows_per_block);
-    const int32_t nsub = RB * MT * (cta2 ? 8 : 4);
-    const size_t per_group = (size_t)nsub * (PG_CS * 8 + 8);
-    int64_t bbatch = n_blocks;
-    if (mode == 0) {
-        bbatch = (int64_t)((size_t)(6144ull << 20) / (per_group * PA_NB));
-        if (bbatch < 1) bbatch = 1;
-        if (bbatch > n_blocks) bbatch = n_blocks;
-        SDK_TRY(sdk_reserve(c, c->slot_cnt, (size_t)bbatch * PA_NB * nsub * 4));
-        SDK_TRY(sdk_reserve(c, c->slot_bound, (size_t)bbatch * PA_NB * nsub * 4));
-        SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)bbatch * PA_NB * nsub * PG_CS * 4));
-        SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)bbatch * PA_NB * nsub * PG_CS * 4));
-    }
-    CUtensorMap ta, tb;
-    SDK_TRY(pg_make_tmap(c, &ta, d_rows, P, Dp, 128));
-    SDK_TRY(pg_make_tmap(c, &tb, il.p, n_rows, Dp, cta2 ? PA_NB / 2 : PA_NB));
-    for (int64_t ba = 0; ba < n_blocks; ba += bbatch) {
-        const int64_t bb = std::min<int64_t>(n_blocks, ba + bbatch);
-        PaParams q;
-        q.pg.goff = d_goff;
-        q.pg.range_g = nullptr;
-        q.pg.n_ranges = 0;
-        q.pg.RB = RB;
-        q.pg.P = P;
-        q.pg.g_base = (int32_t)(ba * PA_NB);
-        q.pg.pool = SDK_POOL_MEAN;
-        q.pg.tau = tau;
-        q.pg.mode = mode;
-        q.pg.slot_cnt = (int32_t*)c->slot_cnt.p;
-        q.pg.slot_row = (int32_t*)c->slot_row.p;
-        q.pg.slot_val = (float*)c->slot_val.p;
-        q.pg.slot_bound = (float*)c->slot_bound.p;
-        q.pg.dense_out = d_dense;
-        q.pg.dense_ld = G;
-        q.pg.nsub = nsub;
-        q.pg.kth = nullptr;
-        if (mode == 0 && c->kth_on) {
-            SDK_TRY(sdk_reserve(c, c->kth, (size_t)bbatch * PA_NB * PG_KTH * 4));
-            SDK_CUDA(c, cudaMemsetAsync(c->kth.p, 0, (size_t)(bb - ba) * PA_NB * PG_KTH * 4, c->stream));
-            q.pg.kth = (uint32_t*)c->kth.p;
-        }
-        q.col_meta = col_meta;
-        q.blockT = (const int32_t*)c->pa_blockT.p;
-        q.step0 = step0;
-        q.block_lo = (int32_t)ba;
-        q.n_blocks = (int32_t)(bb - ba);
-        const int64_t n_units = (bb - ba) * RB;
-        const int grid = cta2 ? 2 * (int)std::min<int64_t>(n_units, c->sm_count / 2) : (int)std::min<int64_t>(n_units, c->sm_count);
-        // slots of columns that are never flushed (inner / unused columns, empty groups) must read as empty
-        if (mode == 0) SDK_CUDA(c, cudaMemsetAsync(c->slot_cnt.p, 0, (size_t)(bb - ba) * PA_NB * nsub * 4, c->stream));
-        {
-            sdk_prof_scope ps(c, "poolgemm");
-            if (cta2) SDK_TRY(pa_launch2(c, kch, ta, tb, q, grid));
-            else SDK_TRY(pa_launch(c, kch, ta, tb, q, grid));
-        }
-        if (mode == 0) {
-            pg_launch_merge(c, d_goff, (int32_t)(ba * PA_NB), (int32_t)((bb - ba) * PA_NB), nsub, col_meta, tau, ncand, d_cand_row, d_gbound);
-            SDK_CUDA(c, cudaGetLastError());
-        }
-    }
-    if (mode == 0 && bbatch >= n_blocks) {     // one batch: every label's candidate slots are still in memory (second chance)
-        c->slot_g0 = 0;
-        c->slot_g1 = G;
-        c->slot_nsub = nsub;
-        c->slot_by_col = true;
-    }
-    return SDK_OK;
+    return pa_gemm(c, il.p, n_rows, Dp, d_rows, P, d_goff, G, mode, tau, ncand, d_cand_row, d_gbound, d_dense);
+}
+
+// Stage A over a matrix that is ALREADY in the interleaved layout with its plan in c->pa_* (pool-first: normalize.cu builds
+// both for the label centroids -- two rows per label, one column per label, two steps per block).
+int sdk_launch_poolacc_prepared(sdk_ctx* c, const void* d_il, int64_t n_rows, int32_t Dp, const __nv_bfloat16* d_rows, int64_t P,
+                                const int64_t* d_goff, int32_t G, float tau, int32_t ncand, int32_t* d_cand_row, float* d_gbound) {
+    if (!sdk_poolacc_applicable(Dp, G, SDK_POOL_MEAN) || !c->tmap_encode) return sdk_fail(c, SDK_EINVAL, "accumulate-pooling path unavailable");
+    if (P > 0x7fffffffLL || n_rows > 0x7fffffffLL) return sdk_fail(c, SDK_EINVAL, "tcgen05 path: at most 2^31-1 rows");
+    return pa_gemm(c, d_il, n_rows, Dp, d_rows, P, d_goff, G, 0, tau, ncand, d_cand_row, d_gbound, nullptr);
 }
