@@ -183,6 +183,9 @@ int sdk_timer_stop(sdk_ctx* ctx, float* ms);         /* records, synchronises, r
  * ("normalize", "poolgemm", "exact", "merge", "select", "assign", "affinity") since the last reset */
 int sdk_profile_get(sdk_ctx* ctx, const char* name, float* ms_total, int64_t* launches);
 int sdk_profile_reset(sdk_ctx* ctx);
+/* one plain read pass over the loaded bank's bf16 operands (asynchronous, on the context stream): timed by bench.py with
+ * sdk_timer_start / sdk_timer_stop as the practical ceiling of an HBM-bound pass over this bank on this GPU */
+int sdk_probe_bank_read(sdk_ctx* ctx);
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 int64_t sdk_launch_count(sdk_ctx* ctx);
 /* which path the last identify took: 1 exact SIMT, 2 tcgen05 (pooling in the epilogue), 3 tcgen05 accumulate-pooling

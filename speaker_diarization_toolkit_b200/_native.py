@@ -30,7 +30,7 @@ EXPORTS = [
     "sdk_set_option", "sdk_bank_load", "sdk_bank_load_dev", "sdk_identify", "sdk_identify_dev", "sdk_assign",
     "sdk_results_fetch", "sdk_affinity_pooled", "sdk_affinity_pooled_dev", "sdk_sync", "sdk_stream",
     "sdk_timer_start", "sdk_timer_stop", "sdk_profile_get", "sdk_profile_reset", "sdk_launch_count", "sdk_last_path",
-    "sdk_last_retry", "sdk_merge_topk", "sdk_stage_a_fetch", "sdk_identify_f16", "sdk_identify_f16_dev",
+    "sdk_last_retry", "sdk_merge_topk", "sdk_stage_a_fetch", "sdk_identify_f16", "sdk_identify_f16_dev", "sdk_probe_bank_read",
 ]
 
 
@@ -72,6 +72,7 @@ def load() -> C.CDLL:
     lib.sdk_results_fetch.argtypes = [vp] + [vp] * 9
     lib.sdk_affinity_pooled.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]
     lib.sdk_affinity_pooled_dev.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]
+    lib.sdk_probe_bank_read.argtypes = [vp]
     lib.sdk_sync.argtypes = [vp]
     lib.sdk_stream.argtypes = [vp]
     lib.sdk_stream.restype = vp
@@ -246,6 +247,9 @@ class Context:
 
     def profile_reset(self):
         self._ck(self.lib.sdk_profile_reset(self.h))
+
+    def probe_bank_read(self):
+        self._ck(self.lib.sdk_probe_bank_read(self.h))
 
     def launch_count(self) -> int:
         return int(self.lib.sdk_launch_count(self.h))

@@ -1084,6 +1084,11 @@ int sdk_profile_reset(sdk_ctx* c) {
     return SDK_OK;
 }
 int64_t sdk_launch_count(sdk_ctx* c) { return c ? c->launches : 0; }
+int sdk_probe_bank_read(sdk_ctx* c) {
+    if (!c) return sdk_fail(nullptr, SDK_EINVAL, "ctx is NULL");
+    cudaSetDevice(c->device);
+    return sdk_launch_probe_read(c);
+}
 
 // Diagnostics of the certified top-k: the first-chance candidate rows of every label group with their STAGE-A
 // (tensor-core / bank-stream) pooled scores, and the margin model eps_g = eps_base + eps_chain * chain_g.

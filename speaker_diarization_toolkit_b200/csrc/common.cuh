@@ -222,6 +222,7 @@ int sdk_launch_poolgemm_candidates(sdk_ctx* c, const __nv_bfloat16* d_bank, int6
                                    const int64_t* d_goff, int32_t G, int32_t pool, float tau,
                                    int32_t ncand, int32_t* d_cand_row /*[G,ncand]*/,
                                    float* d_gbound /*[G]*/);
+int sdk_launch_probe_read(sdk_ctx* c);     // one plain read pass over the bf16 bank operands (bench.py's practical HBM ceiling)
 // <= 8 query segments: the small-query latency path (gemv.cu) -- label offsets, normalise, HBM-bound bank stream and
 // per-CTA top lists in one kernel; merge, canonical re-score, select and certificate in a second; nothing synchronised.
 // Failed certificates are left on c->fb_list / flags[SDK_FLAG_FB] for sdk_settle.

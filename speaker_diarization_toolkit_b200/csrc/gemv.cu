@@ -60,28 +60,57 @@ struct GvParams {
     float* slot_val;
 };
 
-// canonical normalise of one row by one warp (oracle/canonical.c step (1); same element -> lane assignment and the same
-// order as k_normalize_vec / k_normalize_generic): bf16 copy into shared memory, optional global copies
+// canonical normalise of one row (D <= 512) by one warp (oracle/canonical.c step (1); same element -> lane assignment and
+// the same order as k_normalize_vec / k_normalize_generic): bf16 copy into shared memory, optional global copies.  All of the
+// lane's elements are loaded BEFORE the first one is used (a load -> convert -> fma loop that waits for memory sixteen times
+// in a row cost 6-8 us here, a third of the kernel).
 template <typename TIn>
 __device__ __forceinline__ void gv_normalize_row(const TIn* __restrict__ xr, int32_t D, int32_t Dp, int lane, __nv_bfloat16* s_out,
                                                  __nv_bfloat16* g_bf16, float* g_f32) {
-    double s = 0.0;
-    for (int q4 = lane; 4 * q4 < D; q4 += 32)
-        for (int t = 0; t < 4; ++t) {
-            const int e = 4 * q4 + t;
-            if (e < D) { const double a = (double)sdk_in<TIn>::ld1(xr, e); s = fma(a, a, s); }
+    const int nq = D >> 2;
+    const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) % sdk_in<TIn>::align) == 0;
+    float4 v[4];                                               // chunks lane, lane + 32, ..: elements 4q .. 4q + 3
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = lane + 32 * i;
+        if (vec) v[i] = q < nq ? sdk_in<TIn>::ld4(xr, q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        else {
+            v[i].x = 4 * q + 0 < D ? sdk_in<TIn>::ld1(xr, 4 * q + 0) : 0.f;
+            v[i].y = 4 * q + 1 < D ? sdk_in<TIn>::ld1(xr, 4 * q + 1) : 0.f;
+            v[i].z = 4 * q + 2 < D ? sdk_in<TIn>::ld1(xr, 4 * q + 2) : 0.f;
+            v[i].w = 4 * q + 3 < D ? sdk_in<TIn>::ld1(xr, 4 * q + 3) : 0.f;
         }
+    }
+    double s = 0.0;                                            // (elements past D are zero: fma(0, 0, s) == s exactly)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double a = (double)v[i].x, b = (double)v[i].y, c = (double)v[i].z, d = (double)v[i].w;
+        s = fma(a, a, s);
+        s = fma(b, b, s);
+        s = fma(c, c, s);
+        s = fma(d, d, s);
+    }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
     const float nrm = (float)sqrt(s);
     const float den = nrm > 1e-12f ? nrm : 1e-12f;
     const float inv = __fdiv_rn(1.0f, den);
-    for (int e = lane; e < Dp; e += 32) {
-        const float o = e < D ? __fmul_rn(sdk_in<TIn>::ld1(xr, e), inv) : 0.f;
-        const __nv_bfloat16 b = __float2bfloat16_rn(o);
-        s_out[e] = b;
-        if (g_bf16) g_bf16[e] = b;
-        if (g_f32 && e < D) g_f32[e] = o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = lane + 32 * i;
+        if (4 * q >= Dp) continue;
+        const float o[4] = {__fmul_rn(v[i].x, inv), __fmul_rn(v[i].y, inv), __fmul_rn(v[i].z, inv), __fmul_rn(v[i].w, inv)};
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(s_out)[q] = pk;
+        if (g_bf16) reinterpret_cast<uint2*>(g_bf16)[q] = pk;
+        if (g_f32) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (4 * q + t < D) g_f32[4 * q + t] = o[t];
+        }
     }
 }
 
@@ -93,45 +122,46 @@ __device__ __forceinline__ unsigned long long gv_warp_max_u64(unsigned long long
 }
 
 // Top-GV_KEEP of this warp's half of a pass (+ the list kept from earlier passes), by (score desc, row asc).
-// vk[t] = orderable key of row rbase + 32 t (0 = not a candidate).  Fast path: the GV_KEEP-th largest of the 32 per-lane
-// maxima is a lower bound T0 on the GV_KEEP-th best entry, so only the handful of entries >= T0 are compacted (ballots)
-// and ranked exactly; if more than 64 entries survive (clustered data), the extraction loop does it the slow way.
-// Returns the new kept entry of this lane (lanes 0 .. GV_KEEP-1, descending) and raises `bound` to the best dropped score.
+// vk[t] = orderable score key of row rbase + 32 t (0 = not a candidate).  The GV_KEEP-th largest of the 32 per-lane maxima
+// is a lower bound T0 on the GV_KEEP-th best score, so only the handful of entries >= T0 are compacted (ballots) and ranked
+// exactly, on full (score, row) keys; everything up to there works on the 32-bit score keys alone.  If more than 64 entries
+// survive (clustered data), the extraction loop does it the slow way.  Returns the new kept entry of this lane (lanes
+// 0 .. GV_KEEP-1, descending) and raises `bound` to the best dropped score.
 __device__ __forceinline__ unsigned long long gv_select_top(const uint32_t (&vk)[GV_PASS_TILES / GV_PARTS], uint32_t rbase, unsigned long long kept,
-                                                             float& bound, unsigned long long* s_cmp /*[64] per warp*/, int lane) {
+                                                             float& bound, unsigned long long* s_cmp /*[64 + GV_KEEP + 2] per warp*/, int lane) {
     constexpr int T = GV_PASS_TILES / GV_PARTS;
-    auto comp_of = [&](int t) -> unsigned long long {
-        return vk[t] ? (((unsigned long long)vk[t] << 32) | (0xffffffffu - (rbase + 32u * (uint32_t)t))) : 0ull;
-    };
-    // per-lane maximum (the kept entry of an earlier pass counts as one more value of its lane)
-    unsigned long long lmax = kept;
+    const uint32_t kv = (uint32_t)(kept >> 32);                // score key of the entry kept from earlier passes (0: none)
+    uint32_t lmax = kv;
 #pragma unroll
-    for (int t = 0; t < T; ++t) { const unsigned long long c = comp_of(t); lmax = c > lmax ? c : lmax; }
+    for (int t = 0; t < T; ++t) lmax = vk[t] > lmax ? vk[t] : lmax;
     int rank = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const unsigned long long o = __shfl_sync(0xffffffffu, lmax, j);
+        const uint32_t o = __shfl_sync(0xffffffffu, lmax, j);
         rank += (o > lmax || (o == lmax && j < lane)) ? 1 : 0;
     }
     const uint32_t mT = __ballot_sync(0xffffffffu, rank == GV_KEEP - 1);       // ranks are a permutation: exactly one lane
-    const unsigned long long T0 = __shfl_sync(0xffffffffu, lmax, __ffs(mT) - 1); // 0 when fewer than GV_KEEP lanes hold anything
-    // compaction of everything >= T0 (zero keys never pass: T0 == 0 keeps every live entry)
+    const uint32_t T0 = __shfl_sync(0xffffffffu, lmax, __ffs(mT) - 1);           // 0 when fewer than GV_KEEP lanes hold anything
+    // compaction of everything with a score >= T0 (zero keys never pass: T0 == 0 keeps every live entry)
     int m = 0, nlive = 0;
+    const uint32_t lt = (1u << lane) - 1u;
     {
-        const bool p = kept != 0ull && kept >= T0;
+        const bool p = kv != 0u && kv >= T0;
         const uint32_t mk = __ballot_sync(0xffffffffu, p);
-        if (p) { const int pos = m + __popc(mk & ((1u << lane) - 1u)); if (pos < 64) s_cmp[pos] = kept; }
-        m += __popc(mk);
-        nlive += __popc(__ballot_sync(0xffffffffu, kept != 0ull));
+        if (p) { const int pos = __popc(mk & lt); if (pos < 64) s_cmp[pos] = kept; }
+        m = __popc(mk);
+        nlive = __popc(__ballot_sync(0xffffffffu, kv != 0u));
     }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        const unsigned long long c = comp_of(t);
-        const bool p = c != 0ull && c >= T0;
-        const uint32_t ml = __ballot_sync(0xffffffffu, c != 0ull);
+        const uint32_t ml = __ballot_sync(0xffffffffu, vk[t] != 0u);
         if (ml) {
+            const bool p = vk[t] != 0u && vk[t] >= T0;
             const uint32_t mk = __ballot_sync(0xffffffffu, p);
-            if (p) { const int pos = m + __popc(mk & ((1u << lane) - 1u)); if (pos < 64) s_cmp[pos] = c; }
+            if (p) {
+                const int pos = m + __popc(mk & lt);
+                if (pos < 64) s_cmp[pos] = ((unsigned long long)vk[t] << 32) | (0xffffffffu - (rbase + 32u * (uint32_t)t));
+            }
             m += __popc(mk);
             nlive += __popc(ml);
         }
@@ -155,7 +185,7 @@ __device__ __forceinline__ unsigned long long gv_select_top(const uint32_t (&vk)
         const int nk = m < GV_KEEP ? m : GV_KEEP;
         if (lane < nk) newkept = s_cmp[64 + lane];
         if (m > GV_KEEP) bound = fmaxf(bound, sdk_funkey((uint32_t)(s_cmp[64 + GV_KEEP] >> 32)));
-        else if (nlive > m) bound = fmaxf(bound, sdk_funkey((uint32_t)(T0 >> 32)));   // live entries below T0 were never compacted
+        else if (nlive > m) bound = fmaxf(bound, sdk_funkey(T0));               // live entries below T0 were never compacted
         __syncwarp();
         return newkept;
     }
@@ -164,8 +194,11 @@ __device__ __forceinline__ unsigned long long gv_select_top(const uint32_t (&vk)
 #pragma unroll 1
     for (int it = 0; it <= GV_KEEP; ++it) {
         unsigned long long best = (kept < last) ? kept : 0ull;
-#pragma unroll
-        for (int t = 0; t < T; ++t) { const unsigned long long c = comp_of(t); best = (c < last && c > best) ? c : best; }
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            const unsigned long long c = vk[t] ? (((unsigned long long)vk[t] << 32) | (0xffffffffu - (rbase + 32u * (uint32_t)t))) : 0ull;
+            best = (c < last && c > best) ? c : best;
+        }
         best = gv_warp_max_u64(best);
         if (best == 0ull) break;
         if (it == GV_KEEP) { bound = fmaxf(bound, sdk_funkey((uint32_t)(best >> 32))); break; }
@@ -199,6 +232,23 @@ k_gemv8(const __grid_constant__ GvParams q) {
     // this CTA's contiguous range of 32-row tiles
     const int64_t c0 = (int64_t)q.nchunk * blockIdx.x / gridDim.x, c1 = (int64_t)q.nchunk * (blockIdx.x + 1) / gridDim.x;
     const int64_t n_mine = c1 - c0;
+    // Every warp asks the memory system for the tiles of its next pass with ONE bulk L2 prefetch each (no registers, no
+    // shared memory): the whole pass is requested from DRAM at once, HBM runs at its own pace from the first microsecond
+    // (also under the query preparation below), and the 128-bit loads of the tile loop find their lines in L2.  With
+    // loads alone the bytes in flight per SM -- 16 x 16 bytes per lane -- did not cover the DRAM latency (ncu: DRAM 36 % busy).
+    auto prefetch_pass = [&](int64_t pass0) {
+        if (lane != 0) return;
+#pragma unroll
+        for (int h = 0; h < GV_PASS_TILES / GV_CW; ++h) {
+            const int64_t t = pass0 + cw + h * GV_CW;
+            if (t >= n_mine || t >= pass0 + GV_PASS_TILES) break;
+            const int64_t row0 = (c0 + t) * GV_ROWS;
+            const int64_t rows = q.P - row0 < GV_ROWS ? q.P - row0 : GV_ROWS;
+            if (rows <= 0) break;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q.bank + row0 * q.Dp), "r"((uint32_t)(rows * q.Dp * 2)) : "memory");
+        }
+    };
+    prefetch_pass(0);
     // ---- query preparation: labels, canonical normalise, B fragments ----
     if (cw == 0 && lane < GV_NQ) {
         int32_t l = 0x7fffffff;
@@ -326,6 +376,7 @@ k_gemv8(const __grid_constant__ GvParams q) {
             }
         }
         __syncthreads();                                               // the raw scores of the pass are complete
+        prefetch_pass(pass0 + GV_PASS_TILES);                          // the next pass streams in under the selection
         if (sel_len > 0) {
             // this warp's half of the pass: tiles [sel_part * 16, +16); lane <-> rows lane + 32 t.  Pool the label's queries
             // (ascending), keep the GV_KEEP largest of (new rows, previously kept) by (score desc, row asc)
@@ -369,6 +420,7 @@ k_gemv8(const __grid_constant__ GvParams q) {
 struct GvTail {
     const int64_t* goff;
     int32_t N, L, k, pool, ncand, nslots, D, pitch, is_bf16;
+    int32_t stage16;              // 16-byte pieces of the operand staging area at the head of the dynamic shared memory
     double threshold;
     float eps;
     const int32_t* slot_cnt;
@@ -455,7 +507,6 @@ __device__ __forceinline__ double gv_dot_smem(const uint4* __restrict__ a, const
 __global__ void __launch_bounds__(GV_TAIL_THREADS)
 k_gemv8_tail(const __grid_constant__ GvTail p) {
     extern __shared__ uint4 s_stage[];                         // [GV_NQ segment rows + GV_TAIL_CHUNK bank rows][row16 + 1]
-    __shared__ unsigned long long s_max[2 * 148 + 8];          // list maxima (grid <= 148 CTAs x 2 lists)
     __shared__ unsigned long long s_key[GV_TAIL_CAP];          // compacted candidates
     __shared__ unsigned long long s_sel[64];                   // the ncand best, by rank
     __shared__ long long s_pool[64];
@@ -487,30 +538,39 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
         return;
     }
     const int64_t lbase = (int64_t)s0 * nslots;                // lists of the label: query slot = its first query
-    // ---- 1. T0 = ncand-th largest list maximum: a lower bound on the ncand-th best entry overall ----
+    // ---- 0. the label's lists come into shared memory in one coalesced sweep (everything below reads them there: the
+    //         list-by-list walks would otherwise wait a memory round trip per entry) ----
+    unsigned long long* s_lkey = reinterpret_cast<unsigned long long*>(s_stage + p.stage16);   // [nslots][GV_KEEP] keys, 0 = no entry
+    float* s_lbound = reinterpret_cast<float*>(s_lkey + (size_t)nslots * GV_KEEP);            // [nslots]
+    int32_t* s_lcnt = reinterpret_cast<int32_t*>(s_lbound + nslots);                          // [nslots]
     if (tid == 0) { s_m = 0; s_over = 0; s_T0 = 0ull; s_Tsel = 0ull; }
     for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
+        s_lcnt[s] = p.slot_cnt[lbase + s];
+        s_lbound[s] = p.slot_bound[lbase + s];
+    }
+    for (int i = tid; i < nslots * GV_KEEP; i += GV_TAIL_THREADS) {
+        const int s = i / GV_KEEP, e = i - s * GV_KEEP;
         unsigned long long key = 0ull;
-        if (p.slot_cnt[lbase + s] > 0)
-            key = ((unsigned long long)sdk_fkey(p.slot_val[(lbase + s) * GV_KEEP]) << 32) | (0xffffffffu - (uint32_t)p.slot_row[(lbase + s) * GV_KEEP]);
-        s_max[s] = key;
+        if (e < p.slot_cnt[lbase + s])
+            key = ((unsigned long long)sdk_fkey(p.slot_val[lbase * GV_KEEP + i]) << 32) | (0xffffffffu - (uint32_t)p.slot_row[lbase * GV_KEEP + i]);
+        s_lkey[i] = key;
     }
     __syncthreads();
+    // ---- 1. T0 = ncand-th largest list maximum: a lower bound on the ncand-th best entry overall ----
     for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
-        const unsigned long long mine = s_max[s];
+        const unsigned long long mine = s_lkey[s * GV_KEEP];
         if (mine == 0ull) continue;
         int rank = 0;
-        for (int j = 0; j < nslots; ++j) rank += s_max[j] > mine ? 1 : 0;
+        for (int j = 0; j < nslots; ++j) rank += s_lkey[j * GV_KEEP] > mine ? 1 : 0;
         if (rank == ncand - 1) s_T0 = mine;                        // keys are unique: exactly one list has this rank (if any)
     }
     __syncthreads();
     // ---- 2. compaction of every entry >= T0 (each list is sorted: a prefix) ----
     const unsigned long long T0 = s_T0;
     for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
-        const int cnt = p.slot_cnt[lbase + s];
+        const int cnt = s_lcnt[s];
         for (int e = 0; e < cnt; ++e) {
-            const unsigned long long key = ((unsigned long long)sdk_fkey(p.slot_val[(lbase + s) * GV_KEEP + e]) << 32) |
-                                           (0xffffffffu - (uint32_t)p.slot_row[(lbase + s) * GV_KEEP + e]);
+            const unsigned long long key = s_lkey[s * GV_KEEP + e];
             if (key < T0) break;
             const int pos = atomicAdd(&s_m, 1);
             if (pos < GV_TAIL_CAP) s_key[pos] = key; else s_over = 1;
@@ -534,13 +594,12 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
     // ---- 4. bound on everything that is not a candidate: dropped inside the stream kernel, or left in a list ----
     float bnd = -3.0e38f;
     for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
-        const int cnt = p.slot_cnt[lbase + s];
-        bnd = fmaxf(bnd, p.slot_bound[lbase + s]);
+        const int cnt = s_lcnt[s];
+        bnd = fmaxf(bnd, s_lbound[s]);
         if (Tsel != 0ull) {
             for (int e = 0; e < cnt; ++e) {
-                const float v = p.slot_val[(lbase + s) * GV_KEEP + e];
-                const unsigned long long key = ((unsigned long long)sdk_fkey(v) << 32) | (0xffffffffu - (uint32_t)p.slot_row[(lbase + s) * GV_KEEP + e]);
-                if (key < Tsel) { bnd = fmaxf(bnd, v); break; }
+                const unsigned long long key = s_lkey[s * GV_KEEP + e];
+                if (key < Tsel) { bnd = fmaxf(bnd, sdk_funkey((uint32_t)(key >> 32))); break; }
             }
         }
     }
@@ -772,7 +831,9 @@ int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype
         cfg.gridDim = dim3((unsigned)L);
         cfg.blockDim = dim3(GV_TAIL_THREADS);
         const int row_bytes = bf16 ? Dp * 2 : D * 4;
-        const size_t tail_smem = (row_bytes & 15) == 0 ? (size_t)(GV_NQ + GV_TAIL_CHUNK) * (row_bytes + 16) : 16;
+        const size_t stage_bytes = (row_bytes & 15) == 0 ? (size_t)(GV_NQ + GV_TAIL_CHUNK) * (row_bytes + 16) : 16;
+        t.stage16 = (int32_t)(stage_bytes / 16);
+        const size_t tail_smem = stage_bytes + (size_t)nslots * (GV_KEEP * 8 + 8);
         SDK_CUDA(c, cudaFuncSetAttribute(k_gemv8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
         cfg.dynamicSmemBytes = tail_smem;
         cfg.stream = c->stream;
@@ -787,5 +848,31 @@ int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype
     c->slot_g0 = c->slot_g1 = 0;                  // no candidate slots of the tcgen05 kind: a failed certificate goes to the exhaustive pass
     c->slot_nsub = 0;
     c->slot_by_col = false;
+    return SDK_OK;
+}
+
+// ---- read probe: what ONE plain pass over the bank operands costs on this GPU (bench.py: the practical ceiling beside
+// the nominal copy bandwidth, which was measured on a read+write copy of 2 GB, not on a 40 us read of 128 MB) ----
+__global__ void __launch_bounds__(512) k_probe_read(const uint4* __restrict__ p, int64_t n16, uint32_t* __restrict__ out) {
+    uint32_t acc = 0u;
+    const int64_t stride = (int64_t)gridDim.x * 512;
+    int64_t i = (int64_t)blockIdx.x * 512 + threadIdx.x;
+    for (; i + 7 * stride < n16; i += 8 * stride) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(p + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+    }
+    for (; i < n16; i += stride) { const uint4 v = __ldcs(p + i); acc ^= v.x ^ v.y ^ v.z ^ v.w; }
+    if (acc == 0x9e3779b9u) out[0] = acc;                  // (keeps the loads alive; practically never taken)
+}
+int sdk_launch_probe_read(sdk_ctx* c) {
+    if (!c->bank_ok || c->P <= 0) return sdk_fail(c, SDK_ESTATE, "read probe: no bank loaded");
+    SDK_TRY(sdk_reserve(c, c->flags, SDK_NFLAGS * 4));
+    const int64_t n16 = (int64_t)c->P * c->Dp / 8;
+    k_probe_read<<<c->sm_count * 2, 512, 0, c->stream>>>((const uint4*)c->bank_bf16.p, n16, (uint32_t*)c->flags.p);
+    c->launches++;
+    SDK_CUDA(c, cudaGetLastError());
     return SDK_OK;
 }

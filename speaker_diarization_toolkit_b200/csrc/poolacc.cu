@@ -865,29 +865,34 @@ k_poolacc2(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
             const int64_t tile128 = ((int64_t)rb * MT + rt) * 2 + crank;              // index of this CTA's 128-row tile
             const int64_t row = tile128 * 128 + wq * 32 + lane;
             const int64_t nsub = (int64_t)p.RB * MT * 8;
-            int32_t gid[NC / 32];
-            float ginv[NC / 32];
-#pragma unroll
-            for (int i = 0; i < NC / 32; ++i) {
-                const int g = q.col_meta[b * NC + i * 32 + lane];
-                gid[i] = g;
+            // lane l holds the column record of column blk * 32 + l; the records of the next 32 columns are fetched while this
+            // block of 32 is processed.  The loop over the eight blocks is ROLLED: fully unrolled, the 256 copies of the
+            // per-column code (60 KB of instructions) streamed through the instruction cache once per unit -- invisible behind
+            // hundreds of accumulation steps (config 3), but 70 us per unit when a unit is two steps (pool-first centroids).
+            auto col_record = [&](int blk, int32_t& g_out, float& inv_out) {
+                const int g = q.col_meta[b * NC + blk * 32 + lane];
                 const int64_t n = g >= 0 ? p.goff[g + 1] - p.goff[g] : 0;
-                ginv[i] = n > 0 ? 1.0f / (float)n : 0.f;
-            }
+                g_out = g;
+                inv_out = n > 0 ? 1.0f / (float)n : 0.f;
+            };
+            int32_t gid_c, gid_n = -1;
+            float ginv_c, ginv_n = 0.f;
+            col_record(0, gid_c, ginv_c);
             const uint32_t slot = uidx % NSLOT, use = uidx / NSLOT;
             pg_mbar_wait(bar_t_full + 8 * slot, use & 1u);
             pg_fence_after();
             const uint32_t td = tmem_base + slot * (MT * NC);
             float run = 0.f;                                                          // sum over the columns of one group
-#pragma unroll
+#pragma unroll 1
             for (int blk = 0; blk < NC / 32; ++blk) {
+                if (blk + 1 < NC / 32) col_record(blk + 1, gid_n, ginv_n);
                 float v[32];
                 pg_tmem_ld32(td + lane_base + rt * NC + blk * 32, v);
                 pg_tmem_ld_wait();
 #pragma unroll
                 for (int cc = 0; cc < 32; ++cc) {
-                    const int g = __shfl_sync(0xffffffffu, gid[blk], cc);
-                    const float inv = __shfl_sync(0xffffffffu, ginv[blk], cc);
+                    const int g = __shfl_sync(0xffffffffu, gid_c, cc);
+                    const float inv = __shfl_sync(0xffffffffu, ginv_c, cc);
                     if (g == -1) continue;                                            // unused column (uniform)
                     run += v[cc];
                     if (g < 0) continue;                                              // inner column: the group goes on
@@ -910,6 +915,8 @@ k_poolacc2(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
                     if (mpass == 0) continue;                                         // slot counts were zeroed before the launch
                     pg_flush_write_call(&p, val, pass, mpass, pos * nsub + tile128 * 4 + wq, lane, row);
                 }
+                gid_c = gid_n;
+                ginv_c = ginv_n;
             }
             pg_fence_before();
             __syncwarp();

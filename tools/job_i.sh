@@ -1,0 +1,19 @@
+# round 2, job i: L2-prefetched stream kernel + shared-memory tail, read probe; pool-first kernel times
+set -o pipefail
+T="timeout 420 python -m pytest -q -x --timeout 100 -m gpu"
+$T tests/test_gpu_small.py tests/test_gpu_certificate.py tests/test_gpu_cli.py tests/test_gpu_fuzz.py 2>&1 | tail -8 | tee gpurun_out/r02_gputests_i1.log || { echo "SMALL PATH TESTS FAILED"; exit 1; }
+B="python bench.py --no-cpu --no-sharded --no-poolfirst"
+timeout 150 $B --workload cfg4i --steps 20 --warmup 5 > gpurun_out/r02_bench_cfg4i_n1_i.json 2> gpurun_out/r02_bench_cfg4i_i.err || tail -5 gpurun_out/r02_bench_cfg4i_i.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02_bench_cfg4i_n1_i.json').read().strip().splitlines()[-1])
+print('cfg4i ms', round(d['ms_per_step'],4), 'roof', round(d['roofline']['frac'],3), 'avg', round(d['roofline']['avg_launch_ms'],4), 'probe', d['roofline'].get('read_probe'), 'par', (d.get('parity_sample') or {}).get('status'), {k:round(v,4) for k,v in d.get('kernel_ms_per_step',{}).items() if v>0}, 'e2e', d['e2e'] and '%.3g'%d['e2e']['value'])
+PY
+BB="python bench.py --no-e2e --no-cpu --no-sharded --no-poolfirst --no-parity"
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_launches_cfg4i_i.csv $BB --workload cfg4i --steps 3 --warmup 2 > gpurun_out/ncu_l_cfg4i.log 2>&1
+python tools/launch_share.py gpurun_out/r02_launches_cfg4i_i.csv | head -8
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_launches_cfg3_poolfirst_i.csv $BB --workload cfg3 --stage-a poolfirst --steps 1 --warmup 1 > gpurun_out/ncu_l_pf.log 2>&1
+python tools/launch_share.py gpurun_out/r02_launches_cfg3_poolfirst_i.csv | head -12
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gemv8 -s 4 -c 2 -f -o gpurun_out/r02_cfg4i_gemv_i $BB --workload cfg4i --steps 2 --warmup 2 > gpurun_out/ncu_cfg4i_gemv.log 2>&1
+python tools/ncu_summary.py gpurun_out/r02_cfg4i_gemv_i.ncu-rep gpurun_out/r02_cfg4i_gemv_i_ncu_summary.json --traffic-key cfg4i --traffic-out gpurun_out/roofline_traffic_i.json
+timeout 600 python -m pytest -q -x --timeout 150 -m gpu tests 2>&1 | tail -6 | tee gpurun_out/r02_gputests_i.log
