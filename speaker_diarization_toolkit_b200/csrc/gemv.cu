@@ -29,7 +29,8 @@
 #define GV_CW 16                     // consumer warps
 #define GV_THREADS (32 * GV_CW)
 #define GV_ROWS 32                   // bank rows per tile
-#define GV_PASS_TILES 32             // tiles whose raw scores are kept in shared memory before a selection pass
+#define GV_PASS_TILES 16             // tiles per pass (one per warp): their raw scores wait in shared memory for the selection,
+                                     // which then runs while the next pass is already streaming in from DRAM
 #define GV_PASS_ROWS (GV_ROWS * GV_PASS_TILES)
 #define GV_RAW_LD (GV_PASS_ROWS + 8) // padded: the fragment stores of the four query pairs land in different banks
 #define GV_KEEP 16                   // kept per (label, CTA, half of the pass)
@@ -64,9 +65,9 @@ struct GvParams {
 // the same order as k_normalize_vec / k_normalize_generic): bf16 copy into shared memory, optional global copies.  All of the
 // lane's elements are loaded BEFORE the first one is used (a load -> convert -> fma loop that waits for memory sixteen times
 // in a row cost 6-8 us here, a third of the kernel).
-template <typename TIn>
+template <typename TIn, typename AfterLoads>
 __device__ __forceinline__ void gv_normalize_row(const TIn* __restrict__ xr, int32_t D, int32_t Dp, int lane, __nv_bfloat16* s_out,
-                                                 __nv_bfloat16* g_bf16, float* g_f32) {
+                                                 __nv_bfloat16* g_bf16, float* g_f32, AfterLoads after_loads) {
     const int nq = D >> 2;
     const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) % sdk_in<TIn>::align) == 0;
     float4 v[4];                                               // chunks lane, lane + 32, ..: elements 4q .. 4q + 3
@@ -81,6 +82,7 @@ __device__ __forceinline__ void gv_normalize_row(const TIn* __restrict__ xr, int
             v[i].w = 4 * q + 3 < D ? sdk_in<TIn>::ld1(xr, 4 * q + 3) : 0.f;
         }
     }
+    after_loads();                                             // (the bank prefetch goes out behind the query loads, not in front)
     double s = 0.0;                                            // (elements past D are zero: fma(0, 0, s) == s exactly)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -248,8 +250,8 @@ k_gemv8(const __grid_constant__ GvParams q) {
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q.bank + row0 * q.Dp), "r"((uint32_t)(rows * q.Dp * 2)) : "memory");
         }
     };
-    prefetch_pass(0);
     // ---- query preparation: labels, canonical normalise, B fragments ----
+    auto prefetch_first = [&]() { prefetch_pass(0); prefetch_pass(GV_PASS_TILES); };
     if (cw == 0 && lane < GV_NQ) {
         int32_t l = 0x7fffffff;
         if (lane < q.N) {
@@ -265,12 +267,15 @@ k_gemv8(const __grid_constant__ GvParams q) {
             __nv_bfloat16* gb = pub ? q.seg_bf16 + (size_t)cw * q.Dp : nullptr;
             float* gf = (pub && q.seg_f32) ? q.seg_f32 + (size_t)cw * q.D : nullptr;
             if (q.in_dtype == SDK_IN_F16)
-                gv_normalize_row<__half>(reinterpret_cast<const __half*>(q.seg_raw) + (size_t)cw * q.D, q.D, q.Dp, lane, so, gb, gf);
+                gv_normalize_row<__half>(reinterpret_cast<const __half*>(q.seg_raw) + (size_t)cw * q.D, q.D, q.Dp, lane, so, gb, gf, prefetch_first);
             else
-                gv_normalize_row<float>(reinterpret_cast<const float*>(q.seg_raw) + (size_t)cw * q.D, q.D, q.Dp, lane, so, gb, gf);
+                gv_normalize_row<float>(reinterpret_cast<const float*>(q.seg_raw) + (size_t)cw * q.D, q.D, q.Dp, lane, so, gb, gf, prefetch_first);
         } else {
+            prefetch_first();
             for (int e = lane; e < q.Dp; e += 32) so[e] = __float2bfloat16_rn(0.f);
         }
+    } else {
+        prefetch_first();
     }
     if (blockIdx.x == 0 && cw == GV_NQ) {
         // label-group offsets (CSR) and label validation for the whole call: goff[g] = queries with a label < g.  Equal to
@@ -376,7 +381,7 @@ k_gemv8(const __grid_constant__ GvParams q) {
             }
         }
         __syncthreads();                                               // the raw scores of the pass are complete
-        prefetch_pass(pass0 + GV_PASS_TILES);                          // the next pass streams in under the selection
+        prefetch_pass(pass0 + 2 * GV_PASS_TILES);                      // two passes ahead: DRAM keeps streaming under the selection
         if (sel_len > 0) {
             // this warp's half of the pass: tiles [sel_part * 16, +16); lane <-> rows lane + 32 t.  Pool the label's queries
             // (ascending), keep the GV_KEEP largest of (new rows, previously kept) by (score desc, row asc)
@@ -493,6 +498,8 @@ __device__ __forceinline__ double gv_dot_smem(const uint4* __restrict__ a, const
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             if (BF16) {
+                // (F2F.F64.F32 conversions: an integer re-bias of the bf16 bits was tried -- the chain is bound by the DFMA
+                //  dependency, and the extra integer instructions doubled the kernel's time)
                 acc = fma((double)__uint_as_float(wa[h] << 16), (double)__uint_as_float(wb[h] << 16), acc);
                 acc = fma((double)__uint_as_float(wa[h] & 0xffff0000u), (double)__uint_as_float(wb[h] & 0xffff0000u), acc);
             } else {
@@ -550,18 +557,21 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
     }
     for (int i = tid; i < nslots * GV_KEEP; i += GV_TAIL_THREADS) {
         const int s = i / GV_KEEP, e = i - s * GV_KEEP;
-        unsigned long long key = 0ull;
-        if (e < p.slot_cnt[lbase + s])
-            key = ((unsigned long long)sdk_fkey(p.slot_val[lbase * GV_KEEP + i]) << 32) | (0xffffffffu - (uint32_t)p.slot_row[lbase * GV_KEEP + i]);
-        s_lkey[i] = key;
+        // (all three loads go out together; entries past the list's count are stale and masked here)
+        const int32_t cnt = p.slot_cnt[lbase + s];
+        const float v = p.slot_val[lbase * GV_KEEP + i];
+        const int32_t r = p.slot_row[lbase * GV_KEEP + i];
+        s_lkey[i] = e < cnt ? (((unsigned long long)sdk_fkey(v) << 32) | (0xffffffffu - (uint32_t)r)) : 0ull;
     }
     __syncthreads();
     // ---- 1. T0 = ncand-th largest list maximum: a lower bound on the ncand-th best entry overall ----
-    for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
+    // (any lower bound will do: the maxima of the first 128 lists are ranked, not all 2 x grid of them)
+    const int nmax = nslots < 128 ? nslots : 128;
+    for (int s = tid; s < nmax; s += GV_TAIL_THREADS) {
         const unsigned long long mine = s_lkey[s * GV_KEEP];
         if (mine == 0ull) continue;
         int rank = 0;
-        for (int j = 0; j < nslots; ++j) rank += s_lkey[j * GV_KEEP] > mine ? 1 : 0;
+        for (int j = 0; j < nmax; ++j) rank += s_lkey[j * GV_KEEP] > mine ? 1 : 0;
         if (rank == ncand - 1) s_T0 = mine;                        // keys are unique: exactly one list has this rank (if any)
     }
     __syncthreads();
@@ -591,6 +601,22 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
     __syncthreads();
     const int nc = m < ncand ? m : ncand;
     const unsigned long long Tsel = s_Tsel;                        // 0: every entry of every list was selected
+    // every candidate's speaker / trust is requested now and used after stage B: the extraction loop at the end then never
+    // waits for memory
+    int32_t spk0 = -1, spk1 = -1;
+    uint32_t tr0 = SDK_TRUST_UNKNOWN, tr1 = SDK_TRUST_UNKNOWN;
+    if (warp == 0) {
+        if (lane < nc) {
+            const uint32_t row = 0xffffffffu - (uint32_t)s_sel[lane];
+            spk0 = p.row_speaker[row];
+            if (p.row_trust) tr0 = p.row_trust[row];
+        }
+        if (lane + 32 < nc) {
+            const uint32_t row = 0xffffffffu - (uint32_t)s_sel[lane + 32];
+            spk1 = p.row_speaker[row];
+            if (p.row_trust) tr1 = p.row_trust[row];
+        }
+    }
     // ---- 4. bound on everything that is not a candidate: dropped inside the stream kernel, or left in a list ----
     float bnd = -3.0e38f;
     for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
@@ -665,19 +691,13 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
     // ---- 6. row -> speaker max, threshold, ordered top-k, certificate (k_select's semantics), one warp ----
     if (warp != 0) return;
     unsigned long long key0 = 0ull, key1 = 0ull;
-    int32_t spk0 = -1, spk1 = -1;
-    uint32_t tr0 = SDK_TRUST_UNKNOWN, tr1 = SDK_TRUST_UNKNOWN;
     if (lane < nc) {
         const uint32_t row = 0xffffffffu - (uint32_t)s_sel[lane];
         key0 = ((unsigned long long)sdk_fkey(sdk_pool_finish(s_pool[lane], n, p.pool)) << 32) | (0xffffffffu - row);
-        spk0 = p.row_speaker[row];                                  // every candidate's speaker / trust is fetched up front:
-        if (p.row_trust) tr0 = p.row_trust[row];                    // the extraction loop below then never waits for memory
     }
     if (lane + 32 < nc) {
         const uint32_t row = 0xffffffffu - (uint32_t)s_sel[lane + 32];
         key1 = ((unsigned long long)sdk_fkey(sdk_pool_finish(s_pool[lane + 32], n, p.pool)) << 32) | (0xffffffffu - row);
-        spk1 = p.row_speaker[row];
-        if (p.row_trust) tr1 = p.row_trust[row];
     }
     unsigned long long last = ~0ull;
     int cnt = 0;

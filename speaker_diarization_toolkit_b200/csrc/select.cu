@@ -146,6 +146,9 @@ k_assign(const int64_t* __restrict__ m_row, const float* __restrict__ m_score,
          double* __restrict__ c_score) {
     const int32_t g = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
+    // launched as a programmatic dependent (its launch latency hides under the kernel before it): wait for that kernel's
+    // results; a no-op after a kernel that never signals early
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (g >= L) return;
     auto rank_of = [](int code) { return code == 2 ? 0 : code == 1 ? 1 : code == 0 ? 2 : -1; };
     const int min_rank = rank_of(min_trust);
@@ -201,10 +204,17 @@ int sdk_launch_assign(sdk_ctx* c, const int64_t* d_row, const float* d_score, co
                       double* d_ascore, int32_t* d_conf, int32_t* d_cidx, double* d_cscore) {
     if (L <= 0) return SDK_OK;
     sdk_prof_scope ps(c, "assign");
-    k_assign<<<(L + 3) / 4, 128, 0, c->stream>>>(d_row, d_score, d_trust, d_count, L, k, thr, min_trust, d_idx,
-                                                  d_ascore, d_conf, d_cidx, d_cscore);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((L + 3) / 4));
+    cfg.blockDim = dim3(128);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SDK_CUDA(c, cudaLaunchKernelEx(&cfg, k_assign, d_row, d_score, d_trust, d_count, L, k, thr, min_trust, d_idx, d_ascore, d_conf, d_cidx, d_cscore));
     c->launches++;
-    SDK_CUDA(c, cudaGetLastError());
     return SDK_OK;
 }
 
