@@ -587,7 +587,7 @@ def parity_sample(torch, dist, ctx, cfg, seg, lab, counts_flat, bank_local, worl
 
 
 # ---- identify workloads (cfg2, cfg3, cfg4*) ----------------------------------------------------------------------------
-def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False, stage_a=None, e2e=True):
+def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False, stage_a=None, do_e2e=True):
     """One workload on `world` ranks: data, warm-up, timed steps, roofline, e2e, CPU baseline, sampled parity.
     Returns the JSON line as a dict on rank 0 (None elsewhere)."""
     from speaker_diarization_toolkit_b200 import _native
@@ -793,7 +793,7 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False, st
     # 2*D bytes per segment over PCIe; `e2e_f32` is the same call on fp32 host embeddings (4*D bytes per segment).
     # Each rank's pinned buffers are allocated while the process is bound to the CPUs of ITS GPU's NUMA node.
     e2e, e2e_f32, par_e2e = None, None, None
-    if not args.no_e2e and e2e:
+    if not args.no_e2e and do_e2e:
         import psutil
         numa = bind_to_gpu_numa_node(torch, local_rank)
 
@@ -963,7 +963,7 @@ def main():
     # ... and, for mean pooling, by the same workload with the pool-first stage A: a DIFFERENT algorithm, reported
     # beside the contraction as time to solution against the HBM roofline -- never as the headline pairs/s
     if args.workload == "cfg3" and args.pool == "mean" and args.stage_a == "contraction" and not args.no_poolfirst:
-        pf = run_identify(args, "cfg3", torch, dist, world, rank, local_rank, sub=True, stage_a="poolfirst", e2e=False)
+        pf = run_identify(args, "cfg3", torch, dist, world, rank, local_rank, sub=True, stage_a="poolfirst", do_e2e=False)
         if rank == 0:
             line["pool_first"] = {"algorithm": "stage A contracts the label centroids (mean pooling is linear); stage B re-scores the candidates over all segments in the canonical arithmetic",
                                   "time_to_solution_ms": pf["ms_per_step"], "contraction_time_to_solution_ms": line["ms_per_step"],

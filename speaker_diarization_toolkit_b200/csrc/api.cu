@@ -158,14 +158,14 @@ void sdk_destroy(sdk_ctx* c) {
     sdk_buf* bufs[] = {&c->bank_f32, &c->bank_bf16, &c->row_speaker, &c->row_trust, &c->seg_raw, &c->seg_lab,
                        &c->seg_f32, &c->seg_bf16, &c->goff, &c->qpool, &c->dense, &c->flags, &c->cand_row,
                        &c->cand_val, &c->cand_cnt, &c->gbound, &c->slot_cnt, &c->slot_row, &c->slot_val,
-                       &c->slot_bound, &c->range_g, &c->kth, &c->fb_list, &c->fb_rows, &c->out_pack, &c->gather, &c->stage_seg[0], &c->stage_seg[1],
-                       &c->stage_lab[0], &c->stage_lab[1], &c->pa_hist, &c->pa_sorted, &c->pa_pos, &c->pa_col_group,
+                       &c->slot_bound, &c->range_g, &c->kth, &c->fb_list, &c->fb_rows, &c->out_pack, &c->gather, &c->stage_seg[0], &c->stage_seg[1], &c->stage_seg[2],
+                       &c->stage_lab[0], &c->stage_lab[1], &c->stage_lab[2], &c->pa_hist, &c->pa_sorted, &c->pa_pos, &c->pa_col_group,
                        &c->pa_col_meta, &c->pa_blockT, &c->pa_step0, &c->pa_grp, &c->pa_col_last, &c->seg_il, &c->fb_list2, &c->cand_row2, &c->qpool2,
                        &c->cent_sum, &c->cent_seg, &c->goff2};
     for (sdk_buf* b : bufs) sdk_release(*b);
     if (c->h_pack) cudaFreeHost(c->h_pack);
     for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < SDK_NSTAGE; ++b) {
         if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]);
         if (c->ev_consumed[b]) cudaEventDestroy(c->ev_consumed[b]);
     }
@@ -749,8 +749,8 @@ int sdk_merge_topk(sdk_ctx* c, int32_t world, int32_t L, int32_t k, const int64_
 }
 
 // Host-buffer entry point.  Large batches are cut at label-group boundaries into chunks that are copied on a second
-// stream into two staging buffers while the previous chunk is being scored, so end-to-end time is
-// max(PCIe, compute) instead of their sum, and the device footprint is two chunks instead of the whole batch.
+// stream into a ring of three staging buffers while earlier chunks are being scored, so end-to-end time is
+// max(PCIe, compute) instead of their sum, and the device footprint is three chunks instead of the whole batch.
 static int sdk_identify_host_body(sdk_ctx* c, const void* seg_v, const int32_t* seg_label, int64_t N, int32_t L, int32_t pool,
                                   double threshold, int32_t k) {
     const int32_t D = c->D;
@@ -780,30 +780,32 @@ static int sdk_identify_host_body(sdk_ctx* c, const void* seg_v, const int32_t* 
         for (size_t i = 1; i < cut.size(); ++i) max_rows = std::max(max_rows, cut[i] - cut[i - 1]);
         if (!c->copy_stream) {
             SDK_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < SDK_NSTAGE; ++b) {
                 SDK_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
                 SDK_CUDA(c, cudaEventCreateWithFlags(&c->ev_consumed[b], cudaEventDisableTiming));
             }
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < SDK_NSTAGE; ++b) {
             SDK_TRY(sdk_reserve(c, c->stage_seg[b], (size_t)max_rows * row_bytes));
             SDK_TRY(sdk_reserve(c, c->stage_lab[b], (size_t)max_rows * 4));
         }
         SDK_CUDA(c, cudaStreamSynchronize(c->stream));
         const size_t nchunk = cut.size() - 1;
         auto enqueue_copy = [&](size_t i) -> int {
-            const int b = (int)(i & 1);
+            const int b = (int)(i % SDK_NSTAGE);
             const int64_t a = cut[i], n = cut[i + 1] - cut[i];
-            if (i >= 2) SDK_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+            if (i >= SDK_NSTAGE) SDK_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
             SDK_CUDA(c, cudaMemcpyAsync(c->stage_seg[b].p, seg + (size_t)a * row_bytes, (size_t)n * row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
             SDK_CUDA(c, cudaMemcpyAsync(c->stage_lab[b].p, seg_label + a, (size_t)n * 4, cudaMemcpyHostToDevice, c->copy_stream));
             SDK_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
             return SDK_OK;
         };
-        SDK_TRY(enqueue_copy(0));
+        // three staging buffers: the copy engine runs two chunks ahead of the kernels, so a chunk whose scoring takes as long
+        // as its copy (fp16 rows: twice the segments per byte) never holds the next copy back
+        for (size_t i = 0; i + 1 < SDK_NSTAGE && i < nchunk; ++i) SDK_TRY(enqueue_copy(i));
         for (size_t i = 0; i < nchunk; ++i) {
-            if (i + 1 < nchunk) SDK_TRY(enqueue_copy(i + 1));
-            const int b = (int)(i & 1);
+            if (i + SDK_NSTAGE - 1 < nchunk) SDK_TRY(enqueue_copy(i + SDK_NSTAGE - 1));
+            const int b = (int)(i % SDK_NSTAGE);
             const int64_t a = cut[i], n = cut[i + 1] - cut[i];
             const int32_t g0 = seg_label[a];
             // groups of this chunk: [g0, g1) where g1 = first label of the next chunk (empty groups in between

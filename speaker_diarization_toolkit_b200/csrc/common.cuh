@@ -11,6 +11,7 @@
 #include "../../include/sdk_b200.h"
 
 #define SDK_Q30 1073741824.0
+#define SDK_NSTAGE 3
 
 struct sdk_buf {               // grow-only device buffer
     void* p = nullptr;
@@ -106,13 +107,13 @@ struct sdk_ctx {
     bool kth_on = false;       // set per identify call: the candidate threshold is low enough for noise rows to pass
     int32_t slot_g0 = 0, slot_g1 = 0, slot_nsub = 0;   // label groups whose candidate slots are live after stage A
     bool slot_by_col = false;  // slots are indexed by accumulator column (accumulate-pooling): group -> pa_col_last
-    sdk_buf stage_seg[2], stage_lab[2];
+    sdk_buf stage_seg[SDK_NSTAGE], stage_lab[SDK_NSTAGE];     // host-buffer identify: H2D staging ring
     sdk_buf pa_hist, pa_sorted, pa_pos, pa_col_group, pa_col_meta, pa_blockT, pa_step0, pa_grp, pa_col_last, seg_il;   // accumulate-pooling plan + layout
     int32_t pa_blocks = 0;     // blocks of 256 accumulator columns in the current plan
     int64_t pa_chain_max = 0;  // longest accumulation chain of the plan, in segments per column (max T_b)
     bool pa_split = false;     // current plan deals groups over several columns (col_meta != col_group)
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[SDK_NSTAGE] = {}, ev_consumed[SDK_NSTAGE] = {};
     // results of the last identify
     int32_t L = 0, k = 0;
     int64_t N = 0;
