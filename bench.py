@@ -766,7 +766,8 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False, st
                 "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_src} copy bandwidth",
                 "avg_launch_ms": avg_ms, "share_of_step": gms / tot_prof,
                 "note": "latency-bound shape: the fraction is informational (SURVEY 8d)"}
-    roof["traffic"] = ncu_traffic(name + ("_max" if cfg["pool"] else ""), roof["kernel"], args.scale == 1.0 and (world == 1 or sharded))
+    roof["traffic"] = ncu_traffic(name + ("_max" if cfg["pool"] else "") + ("_poolfirst" if path == 5 else ""), roof["kernel"],
+                                  args.scale == 1.0 and (world == 1 or sharded))
     if roof["traffic"] is not None:
         roof["traffic_source"] = "profiles/roofline_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this workload (not re-measured in this run)"
 

@@ -317,7 +317,15 @@ def _assign_batch_multi_gpu(args, items) -> int:
             if err.strip() and args.verbose:
                 print(err.strip(), file=sys.stderr)
             if not args.shard_bank or r == 0:
-                outputs += json.loads(out)
+                # (libraries may write to the worker's stdout as well -- NCCL prints its version line there when NCCL_DEBUG
+                #  is set: take the JSON list the worker printed, not the whole stream)
+                a = out.find("[\n") if "[\n" in out else out.find("[]")
+                b = out.rfind("]")
+                if a < 0 or b < a:
+                    print(f"Error: GPU worker {r} printed no result list:\n{out.strip()[:400]}\n{err.strip()[:400]}", file=sys.stderr)
+                    rc = 1
+                    continue
+                outputs += json.loads(out[a:b + 1])
     if rc:
         return rc
     if args.format == "json":
