@@ -195,7 +195,8 @@ class _InProcessWorker:
         finally:
             for k, v in saved.items():
                 os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
-        self._out, self._err = out.getvalue(), err.getvalue()
+        # (NCCL writes its version line to stdout under NCCL_DEBUG=VERSION: the parent must cope with such noise)
+        self._out, self._err = "NCCL version 2.27.3+cuda12.9\n" + out.getvalue(), err.getvalue()
 
     def communicate(self):
         return self._out, self._err
