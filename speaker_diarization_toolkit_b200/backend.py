@@ -35,6 +35,7 @@ class B200Backend(EmbeddingBackend):
     SPEAKER_B200_POOL = mean|max, SPEAKER_B200_TOPK (matches per label, default 10),
     SPEAKER_B200_SCOPE = label|recording (per-label rows, or whole-recording rows as the reference's
     speaker-assign expects), SPEAKER_B200_DTYPE = fp32|bf16, SPEAKER_B200_DEVICE (cuda index), SPEAKER_B200_DIM,
+    SPEAKER_B200_STAGE_A = poolfirst (mean pooling: centroid stage A, same certified result),
     SPEAKER_B200_BANK_CACHE = 0 disables the packed bank cache (store.build_bank_cached), = trust skips its per-file stat().
     Row-sharded bank over several GPUs, one process per GPU: SPEAKER_B200_WORLD, SPEAKER_B200_RANK and
     SPEAKER_B200_UID_FILE (rank 0 publishes the NCCL unique id there); every rank must make the same identify calls and
@@ -72,6 +73,8 @@ class B200Backend(EmbeddingBackend):
         if self._ctx is None:
             from .batch import sharded_context_from_env
             self._world, self._rank, self._ctx = sharded_context_from_env(_env_int("SPEAKER_B200_DEVICE", 0))
+            if os.environ.get("SPEAKER_B200_STAGE_A", "") == "poolfirst":
+                self._ctx.set_option("poolfirst", 1)
         return self._ctx
 
     def _load_bank(self, candidates: List[Dict[str, Any]]) -> store.Bank:

@@ -79,6 +79,10 @@ class BatchMatcher:
         else:
             self.world, self.rank = int(world), int(rank)
             self.ctx = _native.Context(dev, self.world, self.rank, nccl_uid) if self.world > 1 else _native.Context(dev)
+        if os.environ.get("SPEAKER_B200_STAGE_A", "") == "poolfirst":
+            # mean pooling: stage A contracts the label centroids instead of the segments (a different algorithm with the
+            # same, certified result: DESIGN.md section 5); several times less time to solution on long recordings
+            self.ctx.set_option("poolfirst", 1)
         self.dtype = _native.DTYPE_BF16 if (dtype or os.environ.get("SPEAKER_B200_DTYPE", "fp32")) == "bf16" else _native.DTYPE_F32
         self.pool = _native.POOL_MAX if (pool or os.environ.get("SPEAKER_B200_POOL", "mean")) == "max" else _native.POOL_MEAN
         self.k = max(1, min(_native.MAX_K, int(k or os.environ.get("SPEAKER_B200_TOPK", 10))))

@@ -28,6 +28,8 @@
 // Everything downstream is unchanged: the epilogue flushes per (group, 32 bank rows) candidate slots, k_pg_merge picks
 // the candidates, exact.cu re-scores them canonically (reading segments from the interleaved layout), select.cu
 // certifies.  Max pooling stays on poolgemm.cu.
+#include <stdlib.h>
+
 #include "tcgen05.cuh"
 
 #define PA_NB 256                 // accumulator columns per block
@@ -1125,7 +1127,11 @@ static int pa_gemm(sdk_ctx* c, const void* il_p, int64_t n_rows, int32_t Dp, con
         q.block_lo = (int32_t)ba;
         q.n_blocks = (int32_t)(bb - ba);
         const int64_t n_units = (bb - ba) * RB;
-        const int grid = cta2 ? 2 * (int)std::min<int64_t>(n_units, c->sm_count / 2) : (int)std::min<int64_t>(n_units, c->sm_count);
+        int grid = cta2 ? 2 * (int)std::min<int64_t>(n_units, c->sm_count / 2) : (int)std::min<int64_t>(n_units, c->sm_count);
+        if (const char* e = getenv("SDK_PA_GRID")) {            // experiment knob (profiles/r02_poolacc_grid_*): fewer CTAs than SMs
+            const int g = atoi(e);
+            if (g >= 2 && g < grid) grid = cta2 ? (g & ~1) : g;
+        }
         // slots of columns that are never flushed (inner / unused columns, empty groups) must read as empty
         if (mode == 0) SDK_CUDA(c, cudaMemsetAsync(c->slot_cnt.p, 0, (size_t)(bb - ba) * PA_NB * nsub * 4, c->stream));
         {

@@ -37,19 +37,23 @@ def random_case(seed):
 def test_random_shapes_all_paths(ctx, oracle, seed):
     case, dtype, pool, thr, k = random_case(7000 + seed)
     ref = oracle.identify(case.seg, case.goff, case.bank, case.row_speaker, case.n_speakers, mode=dtype, pool=pool, threshold=thr, k=k)
-    # (path, acc, gemv): auto, exact, generic tcgen05, accumulate-pooling (forced; mean pooling only), bank stream
-    variants = [(0, 1, 1), (1, 0, 0), (2, 0, 0), (2, 2, 0), (2, 1, 1)]
+    # (path, acc, gemv, cta_group, poolfirst): auto, exact, generic tcgen05, accumulate-pooling (forced; mean pooling only)
+    # on single CTAs and on CTA pairs, bank stream, pool-first (mean pooling only; also on CTA pairs)
+    variants = [(0, 1, 1, 0, 0), (1, 0, 0, 0, 0), (2, 0, 0, 0, 0), (2, 2, 0, 1, 0), (2, 2, 0, 2, 0), (2, 1, 1, 0, 0), (2, 1, 0, 0, 1),
+                (2, 1, 0, 2, 1)]
     N = int(case.goff[-1])
-    for path, acc, gemv in variants:
+    for path, acc, gemv, cta_group, poolfirst in variants:
         ctx.set_option("path", path)
         ctx.set_option("acc", acc)
         ctx.set_option("gemv", gemv)
+        ctx.set_option("cta_group", cta_group)
+        ctx.set_option("poolfirst", poolfirst)
         ctx.set_option("cand", 16)
         ctx.set_option("eps", -1.0)
         ctx.bank_load(case.bank, case.row_speaker, case.row_trust, dtype=dtype)
         rows, scores, counts = ctx.identify(case.seg, case.seg_label, case.G, pool=pool, threshold=thr, k=k)
         what = f"seed {seed} D={case.seg.shape[1]} G={case.G} N={N} P={case.bank.shape[0]} dtype={dtype} pool={pool} thr={thr} k={k} " \
-               f"variant={(path, acc, gemv)} took path {ctx.last_path()}"
+               f"variant={(path, acc, gemv, cta_group, poolfirst)} took path {ctx.last_path()}"
         assert np.array_equal(counts, ref[2]), what
         assert np.array_equal(rows, ref[0]), what
         assert np.array_equal(scores.view(np.uint32), ref[1].view(np.uint32)), what
@@ -60,6 +64,10 @@ def test_random_shapes_all_paths(ctx, oracle, seed):
             assert took == 3, what
         if path == 2 and gemv == 1 and N <= 8 and case.G <= 64:
             assert took == 4, what
+        if poolfirst and pool == 0 and case.seg.shape[1] % 4 == 0:
+            assert took == 5, what
     ctx.set_option("path", 0)
     ctx.set_option("acc", 1)
     ctx.set_option("gemv", 1)
+    ctx.set_option("cta_group", 0)
+    ctx.set_option("poolfirst", 0)
