@@ -510,6 +510,72 @@ struct PaParams {
     const int32_t* blockT;         // [n_blocks] steps of each block
     const int64_t* step0;          // [n_blocks+1] first step of each block
     int32_t block_lo, n_blocks;    // blocks [block_lo, block_lo + n_blocks) of this batch
+    int32_t sched_groups;          // k_poolacc2: 1 = static GROUP schedule (PaSched), 0 = units dealt round robin
+};
+
+// ---- static unit schedule of the CTA pairs (k_poolacc2) ----------------------------------------------------------------
+// The RB units of a block stream the same slabs of the interleaved segment matrix, so they should run at the same time
+// on different pairs: L2 then serves each slab RB times for one DRAM read.  Dealing the units round robin over the pairs
+// (u -> pair u % npairs) only does that while npairs is a multiple of RB: with 74 pairs and 20 units per block the set of
+// pairs that share a block changes every round, pairs arrive from blocks of different lengths, drift apart, and the slabs
+// are fetched from DRAM three times (ncu, config 3: 23.6 GB per launch; 9.7 GB with 60 pairs, 8.0 GB with 40).
+// GROUP schedule: pairs [g*RB, (g+1)*RB) form group g and always work on ONE block together (pair i of the group owns row
+// block i).  The rem = npairs % RB left-over pairs form a last group; with d = gcd(RB, rem) it finishes Bl = rem / d blocks in
+// R = RB / d rounds when their Bl * RB units are dealt round robin over its rem pairs (every pair busy in every round), while
+// every full group finishes R blocks.  A super-round is therefore S = n_full * R + Bl blocks in R rounds with no idle pair
+// (config 3: 3 groups of 20 + one of 14: R = 10, Bl = 7, S = 37).
+struct PaSched {
+    int32_t RB, n_blocks, npairs, n_full, rem, R, Bl, S, groups;
+    int32_t p;                     // this pair
+    int64_t i;                     // full groups / round robin: units taken so far; last group: super-round
+    int32_t t;                     // last group: units taken in this super-round
+    __device__ __forceinline__ void init(int32_t RB_, int32_t n_blocks_, int32_t npairs_, int32_t pair, int32_t groups_) {
+        RB = RB_; n_blocks = n_blocks_; npairs = npairs_; p = pair; i = 0; t = 0;
+        n_full = npairs / RB;
+        rem = npairs - n_full * RB;
+        int32_t d = RB, e = rem;
+        while (e) { const int32_t r = d % e; d = e; e = r; }       // gcd(RB, rem); rem == 0 -> d = RB
+        R = RB / d;
+        Bl = rem / d;
+        S = n_full * R + Bl;
+        groups = (groups_ && n_full >= 1) ? 1 : 0;
+    }
+    __device__ __forceinline__ bool next(int32_t& bl, int32_t& rb) {
+        if (!groups) {                                               // round robin over all units, block major
+            const int64_t u = (int64_t)p + i * npairs;
+            if (u >= (int64_t)n_blocks * RB) return false;
+            bl = (int32_t)(u / RB);
+            rb = (int32_t)(u - (int64_t)bl * RB);
+            ++i;
+            return true;
+        }
+        if (p < n_full * RB) {                                       // a full group: one unit of every block the group takes
+            const int32_t g = p / RB;
+            const int64_t sr = i / R, r = i - sr * R;
+            const int64_t b = sr * S + r * n_full + g;
+            if (b >= n_blocks) return false;
+            bl = (int32_t)b;
+            rb = p - g * RB;
+            ++i;
+            return true;
+        }
+        const int32_t q = p - n_full * RB;                          // the last group: its Bl blocks dealt round robin over rem pairs
+        for (;;) {
+            const int64_t base = i * S + (int64_t)n_full * R;
+            if (base >= n_blocks) return false;
+            const int32_t v = q + t * rem;
+            if (v < Bl * RB) {
+                const int64_t b = base + v / RB;
+                ++t;
+                if (b >= n_blocks) continue;                        // (a partial last super-round)
+                bl = (int32_t)b;
+                rb = v % RB;
+                return true;
+            }
+            ++i;
+            t = 0;
+        }
+    }
 };
 
 // KH = passes over K: with KH == 2 only half of a unit's bank tiles (KCL = ceil(KCH / 2) K chunks of both row tiles) are
@@ -775,7 +841,7 @@ k_poolacc2(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
     pg_fence_after();
     const uint32_t tmem_base = *s_tmem_ptr;
 
-    const int64_t n_units = (int64_t)q.n_blocks * p.RB;     // RB = pairs of row blocks (MT * 256 bank rows each)
+    // (p.RB = pairs of row blocks, MT * 256 bank rows each; the units of this pair come from PaSched)
     const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const uint32_t l_a_full = pg_mapa(bar_a_full, 0), l_b_full = pg_mapa(bar_b_full, 0), l_t_empty = pg_mapa(bar_t_empty, 0);
 
@@ -783,8 +849,10 @@ k_poolacc2(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
         // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, a_bits = 0;
-            for (int64_t u = pair; u < n_units; u += npairs) {
-                const int32_t bl = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)bl * p.RB);
+            PaSched sch;
+            sch.init(p.RB, q.n_blocks, (int32_t)npairs, (int32_t)pair, q.sched_groups);
+            int32_t bl, rb;
+            while (sch.next(bl, rb)) {
                 const int32_t b = q.block_lo + bl;
                 const int32_t T = q.blockT[b];
                 if (T <= 0) continue;
@@ -814,8 +882,10 @@ k_poolacc2(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
         // ================= MMA issuer (leader CTA only; the whole warp runs the loop, one elected lane issues) =================
         if (leader) {
             uint32_t stage = 0, phase = 0, a_bits = 0, uidx = 0;
-            for (int64_t u = pair; u < n_units; u += npairs) {
-                const int32_t bl = (int32_t)(u / p.RB);
+            PaSched sch;
+            sch.init(p.RB, q.n_blocks, (int32_t)npairs, (int32_t)pair, q.sched_groups);
+            int32_t bl, rb;
+            while (sch.next(bl, rb)) {
                 const int32_t T = q.blockT[q.block_lo + bl];
                 if (T <= 0) continue;
                 const uint32_t slot = uidx % NSLOT, use = uidx / NSLOT;
@@ -860,8 +930,10 @@ k_poolacc2(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
         const int rt = MT == 2 ? wg : 0;
         const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
         uint32_t uidx = 0;
-        for (int64_t u = pair; u < n_units; u += npairs) {
-            const int32_t bl = (int32_t)(u / p.RB), rb = (int32_t)(u - (int64_t)bl * p.RB);
+        PaSched sch;
+        sch.init(p.RB, q.n_blocks, (int32_t)npairs, (int32_t)pair, q.sched_groups);
+        int32_t bl, rb;
+        while (sch.next(bl, rb)) {
             const int32_t b = q.block_lo + bl;
             if (q.blockT[b] <= 0) continue;
             const int64_t tile128 = ((int64_t)rb * MT + rt) * 2 + crank;              // index of this CTA's 128-row tile
@@ -1126,11 +1198,24 @@ static int pa_gemm(sdk_ctx* c, const void* il_p, int64_t n_rows, int32_t Dp, con
         q.step0 = step0;
         q.block_lo = (int32_t)ba;
         q.n_blocks = (int32_t)(bb - ba);
+        q.sched_groups = 0;
         const int64_t n_units = (bb - ba) * RB;
         int grid = cta2 ? 2 * (int)std::min<int64_t>(n_units, c->sm_count / 2) : (int)std::min<int64_t>(n_units, c->sm_count);
-        if (const char* e = getenv("SDK_PA_GRID")) {            // experiment knob (profiles/r02_poolacc_grid_*): fewer CTAs than SMs
+        if (const char* e = getenv("SDK_PA_GRID")) {            // experiment knob (profiles/r02_poolacc_exp_*): fewer CTAs than SMs
             const int g = atoi(e);
             if (g >= 2 && g < grid) grid = cta2 ? (g & ~1) : g;
+        }
+        if (cta2) {
+            // group schedule (PaSched) when the pairs split into groups of RB that stay busy: n_full groups take w blocks
+            // while the rem left-over pairs finish one
+            const int npairs = grid / 2, n_full = npairs / RB, rem = npairs - n_full * RB;
+            if (n_full >= 1) {
+                int d = RB, e = rem;
+                while (e) { const int r = d % e; d = e; e = r; }
+                const int S = n_full * (RB / d) + rem / d;                 // blocks per super-round (PaSched)
+                q.sched_groups = q.n_blocks >= 4 * S ? 1 : 0;              // (a few blocks only: the left-over pairs would idle)
+            }
+            if (const char* e = getenv("SDK_PA_SCHED")) q.sched_groups = atoi(e) != 0 ? 1 : 0;     // A/B runs
         }
         // slots of columns that are never flushed (inner / unused columns, empty groups) must read as empty
         if (mode == 0) SDK_CUDA(c, cudaMemsetAsync(c->slot_cnt.p, 0, (size_t)(bb - ba) * PA_NB * nsub * 4, c->stream));

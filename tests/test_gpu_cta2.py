@@ -63,3 +63,18 @@ def test_auto_takes_pairs_for_many_groups_and_single_cta_can_be_forced(ctx, orac
             ctx.set_option("cta_group", 0)
         assert ctx.last_path() == (3, 0)
         assert_same(gpu, ref, f"cta_group={cg}")
+
+
+@pytest.mark.parametrize("sched", ["0", "1"])
+def test_cta2_group_schedule_covers_every_unit(pairs, oracle, monkeypatch, sched):
+    """The static GROUP schedule of the CTA pairs (PaSched: full groups of RB pairs + a last group that deals its blocks round
+    robin) must visit every (block, row block) unit exactly once: 20 000 one-column groups = 79 blocks x 3 row blocks on 74
+    pairs -> 24 full groups and a last group of 2 pairs, one full super-round of 74 blocks and a partial one."""
+    monkeypatch.setenv("SDK_PA_SCHED", sched)
+    rng = np.random.default_rng(64)
+    counts = rng.integers(1, 4, size=20000)
+    case = synth.make_case(6400, counts, 700, 64, rows_per_speaker=rng.choice([1, 2, 3], size=700), impostor_frac=0.2)
+    assert 1024 < case.bank.shape[0] <= 1536                            # 3 row blocks of 512 rows
+    gpu = run_gpu(pairs, case, 1, 0, 0.354, 4, path=2, acc=2)
+    assert pairs.last_path() == (3, 0)
+    assert_same(gpu, run_oracle(oracle, case, 1, 0, 0.354, 4), f"group schedule {sched}")
