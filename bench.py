@@ -146,29 +146,68 @@ def make_segments(torch, cfg, dev, cent, counts, truth, seed):
 _ALL_CPUS = None
 
 
+def _node_cpus(node):
+    cpus = set()
+    for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+        a, _, b = part.partition("-")
+        if a:
+            cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa_node(torch, local_rank):
     """Pinned host memory is placed by first touch: bind this process to the CPUs of the NUMA node its GPU hangs off
-    before allocating, so that with 8 ranks the H2D streams read from both sockets' memory instead of one.
-    Returns the node (None when sysfs does not say)."""
+    before allocating, so that with 8 ranks the H2D streams read from both sockets' memory instead of one.  The node comes
+    from sysfs; where sysfs does not say (-1: virtualised PCI topology) and the host has several nodes, every node is tried
+    with a 64 MB pinned buffer and the one with the fastest host->device copy wins.  Returns (node, how) or (None, why)."""
     global _ALL_CPUS
     try:
-        pr = torch.cuda.get_device_properties(local_rank)
-        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
-        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
         if _ALL_CPUS is None:
             _ALL_CPUS = os.sched_getaffinity(0)
-        cpus &= _ALL_CPUS
+        nodes = sorted(int(p.name[4:]) for p in Path("/sys/devices/system/node").glob("node[0-9]*"))
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = -1
+        try:
+            node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        except Exception:
+            node = -1
+        how = "sysfs"
+        if node < 0:
+            if len(nodes) < 2:
+                return None, "single NUMA node"
+            dev = torch.device("cuda", local_rank)
+            best, rates = None, {}
+            d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+            for nd in nodes:
+                cpus = _node_cpus(nd) & _ALL_CPUS
+                if not cpus:
+                    continue
+                os.sched_setaffinity(0, cpus)
+                h = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
+                h.fill_(1)
+                d.copy_(h, non_blocking=True)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(4):
+                    d.copy_(h, non_blocking=True)
+                e1.record()
+                torch.cuda.synchronize()
+                rates[nd] = 4 * h.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+                del h
+                if best is None or rates[nd] > rates[best]:
+                    best = nd
+            os.sched_setaffinity(0, _ALL_CPUS)
+            if best is None:
+                return None, "no usable NUMA node"
+            node, how = best, "h2d probe " + ", ".join(f"node{k}: {v:.1f} GB/s" for k, v in sorted(rates.items()))
+        cpus = _node_cpus(node) & _ALL_CPUS
         if cpus:
             os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:
-        return None
+        return node, how
+    except Exception as exc:
+        return None, f"unavailable ({type(exc).__name__})"
 
 
 def unbind_cpus():
@@ -796,7 +835,7 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False, st
     e2e, e2e_f32, par_e2e = None, None, None
     if not args.no_e2e and do_e2e:
         import psutil
-        numa = bind_to_gpu_numa_node(torch, local_rank)
+        numa, numa_how = bind_to_gpu_numa_node(torch, local_rank)
 
         def e2e_leg(f16):
             esz = 2 if f16 else 4
@@ -844,7 +883,8 @@ def run_identify(args, name, torch, dist, world, rank, local_rank, sub=False, st
                    "steps": e_steps, "sample": "whole batch" if frac == 1.0 else f"first {frac:.2f} of the rank's batch (host memory bound)",
                    "input": ("fp16 segment embeddings in pinned host memory (compact sidecar form, widened exactly on the device)" if f16
                              else "fp32 segment embeddings in pinned host memory"),
-                   "h2d_gbs_per_rank": (n_e * D * esz + n_e * 4) * e_steps / float(tt.item()) / 1e9, "numa_node_of_gpu": numa}
+                   "h2d_gbs_per_rank": (n_e * D * esz + n_e * 4) * e_steps / float(tt.item()) / 1e9, "numa_node_of_gpu": numa,
+                   "numa_placement": numa_how}
             par = None
             if f16 and not args.no_parity:
                 # the results of the last fp16 host step against the oracle on the widened fp16 values
