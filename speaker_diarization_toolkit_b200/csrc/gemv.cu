@@ -38,6 +38,21 @@
 #define GV_TAIL_THREADS 256
 #define GV_TAIL_CAP 1024             // compacted candidates per label in the tail
 
+// Phase trace of the two kernels (tools/gv_trace.py builds a separate library with -DSDK_GV_TRACE; the shipped one has none
+// of this): thread 0 of every CTA stamps clock64 at the phase boundaries, plus globaltimer at both ends.
+#ifdef SDK_GV_TRACE
+__device__ unsigned long long gv_trace[2][160][24];
+__device__ __forceinline__ unsigned long long gv_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define GV_T(kern, slot) do { if (threadIdx.x == 0 && blockIdx.x < 160) gv_trace[kern][blockIdx.x][slot] = (unsigned long long)clock64(); } while (0)
+#define GV_TG(kern, slot) do { if (threadIdx.x == 0 && blockIdx.x < 160) gv_trace[kern][blockIdx.x][slot] = gv_gtime(); } while (0)
+extern "C" int sdk_debug_gv_trace(unsigned long long* out) {
+    return cudaMemcpyFromSymbol(out, gv_trace, sizeof(gv_trace)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define GV_T(kern, slot) do { } while (0)
+#define GV_TG(kern, slot) do { } while (0)
+#endif
+
 struct GvParams {
     const void* seg_raw;          // [N, D] raw query rows, fp32 or fp16
     const int32_t* seg_label;     // [N] global label ids
@@ -55,18 +70,16 @@ struct GvParams {
     __nv_bfloat16* seg_bf16;      // [N, Dp]
     float* seg_f32;               // [N, D] or null (fp32 banks)
     // lists: index (q0 * nslots + slot), q0 = first query of the label
-    int32_t* slot_cnt;
     float* slot_bound;
-    int32_t* slot_row;            // [.., GV_KEEP]
-    float* slot_val;
+    unsigned long long* slot_key; // [.., GV_KEEP] (score key << 32 | ~row), descending, 0 = no entry: every entry is written
 };
 
 // canonical normalise of one row (D <= 512) by one warp (oracle/canonical.c step (1); same element -> lane assignment and
-// the same order as k_normalize_vec / k_normalize_generic): bf16 copy into shared memory, optional global copies.  All of the
-// lane's elements are loaded BEFORE the first one is used (a load -> convert -> fma loop that waits for memory sixteen times
-// in a row cost 6-8 us here, a third of the kernel).
+// the same order as k_normalize_vec / k_normalize_generic): the bf16 copy goes STRAIGHT INTO THE B FRAGMENTS of query n in
+// shared memory (layout: see k_gemv8), optional global copies.  All of the lane's elements are loaded BEFORE the first one
+// is used (a load -> convert -> fma loop that waits for memory sixteen times in a row cost 6-8 us here, a third of the kernel).
 template <typename TIn, typename AfterLoads>
-__device__ __forceinline__ void gv_normalize_row(const TIn* __restrict__ xr, int32_t D, int32_t Dp, int lane, __nv_bfloat16* s_out,
+__device__ __forceinline__ void gv_normalize_row(const TIn* __restrict__ xr, int32_t D, int32_t Dp, int lane, uint2* s_frag, int n,
                                                  __nv_bfloat16* g_bf16, float* g_f32, AfterLoads after_loads) {
     const int nq = D >> 2;
     const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) % sdk_in<TIn>::align) == 0;
@@ -83,6 +96,7 @@ __device__ __forceinline__ void gv_normalize_row(const TIn* __restrict__ xr, int
         }
     }
     after_loads();                                             // (the bank prefetch goes out behind the query loads, not in front)
+    GV_T(0, 18);
     double s = 0.0;                                            // (elements past D are zero: fma(0, 0, s) == s exactly)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -97,6 +111,7 @@ __device__ __forceinline__ void gv_normalize_row(const TIn* __restrict__ xr, int
     const float nrm = (float)sqrt(s);
     const float den = nrm > 1e-12f ? nrm : 1e-12f;
     const float inv = __fdiv_rn(1.0f, den);
+    GV_T(0, 19);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int q = lane + 32 * i;
@@ -106,7 +121,8 @@ __device__ __forceinline__ void gv_normalize_row(const TIn* __restrict__ xr, int
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        reinterpret_cast<uint2*>(s_out)[q] = pk;
+        // 32-bit words 2q, 2q + 1 of the row = k block q / 8, MMA j = q % 2, fragment lane (n, c = (q % 8) / 2)
+        s_frag[((q >> 3) * 2 + (q & 1)) * 32 + n * 4 + ((q & 7) >> 1)] = pk;
         if (g_bf16) reinterpret_cast<uint2*>(g_bf16)[q] = pk;
         if (g_f32) {
 #pragma unroll
@@ -129,55 +145,76 @@ __device__ __forceinline__ unsigned long long gv_warp_max_u64(unsigned long long
 // exactly, on full (score, row) keys; everything up to there works on the 32-bit score keys alone.  If more than 64 entries
 // survive (clustered data), the extraction loop does it the slow way.  Returns the new kept entry of this lane (lanes
 // 0 .. GV_KEEP-1, descending) and raises `bound` to the best dropped score.
+// The phase is bound by instruction issue (all sixteen warps select at once, ~9 cycles per warp instruction: measured with
+// tools/gv_trace.py), so what counts is the number of instructions: a bitonic network for T0, no per-tile bookkeeping.
 __device__ __forceinline__ unsigned long long gv_select_top(const uint32_t (&vk)[GV_PASS_TILES / GV_PARTS], uint32_t rbase, unsigned long long kept,
                                                              float& bound, unsigned long long* s_cmp /*[64 + GV_KEEP + 2] per warp*/, int lane) {
     constexpr int T = GV_PASS_TILES / GV_PARTS;
     const uint32_t kv = (uint32_t)(kept >> 32);                // score key of the entry kept from earlier passes (0: none)
     uint32_t lmax = kv;
+    int nl = kv != 0u ? 1 : 0;
 #pragma unroll
-    for (int t = 0; t < T; ++t) lmax = vk[t] > lmax ? vk[t] : lmax;
-    int rank = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const uint32_t o = __shfl_sync(0xffffffffu, lmax, j);
-        rank += (o > lmax || (o == lmax && j < lane)) ? 1 : 0;
+    for (int t = 0; t < T; ++t) {
+        lmax = vk[t] > lmax ? vk[t] : lmax;
+        nl += vk[t] != 0u ? 1 : 0;
     }
-    const uint32_t mT = __ballot_sync(0xffffffffu, rank == GV_KEEP - 1);       // ranks are a permutation: exactly one lane
-    const uint32_t T0 = __shfl_sync(0xffffffffu, lmax, __ffs(mT) - 1);           // 0 when fewer than GV_KEEP lanes hold anything
-    // compaction of everything with a score >= T0 (zero keys never pass: T0 == 0 keeps every live entry)
-    int m = 0, nlive = 0;
+    // the GV_KEEP-th largest lane maximum: bitonic sort of the 32 values across the lanes (descending), read at lane GV_KEEP-1
+    uint32_t sv = lmax;
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j >= 1; j >>= 1) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, sv, j);
+            const bool up = ((lane & k2) == 0) == ((lane & j) == 0);      // this lane keeps the larger of the pair
+            sv = up ? (o > sv ? o : sv) : (o < sv ? o : sv);
+        }
+    }
+    GV_T(0, 21);
+    const uint32_t T0 = __shfl_sync(0xffffffffu, sv, GV_KEEP - 1);               // 0 when fewer than GV_KEEP lanes hold anything
+    const uint32_t T0e = T0 != 0u ? T0 : 1u;                                     // (zero keys never pass)
+    const int nlive = __reduce_add_sync(0xffffffffu, nl);
+    // compaction of everything with a score >= T0
+    int m = 0;
     const uint32_t lt = (1u << lane) - 1u;
     {
-        const bool p = kv != 0u && kv >= T0;
+        const bool p = kv >= T0e;
         const uint32_t mk = __ballot_sync(0xffffffffu, p);
-        if (p) { const int pos = __popc(mk & lt); if (pos < 64) s_cmp[pos] = kept; }
+        if (p) s_cmp[__popc(mk & lt)] = kept;
         m = __popc(mk);
-        nlive = __popc(__ballot_sync(0xffffffffu, kv != 0u));
     }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        const uint32_t ml = __ballot_sync(0xffffffffu, vk[t] != 0u);
-        if (ml) {
-            const bool p = vk[t] != 0u && vk[t] >= T0;
-            const uint32_t mk = __ballot_sync(0xffffffffu, p);
-            if (p) {
-                const int pos = m + __popc(mk & lt);
-                if (pos < 64) s_cmp[pos] = ((unsigned long long)vk[t] << 32) | (0xffffffffu - (rbase + 32u * (uint32_t)t));
-            }
-            m += __popc(mk);
-            nlive += __popc(ml);
+        const bool p = vk[t] >= T0e;
+        const uint32_t mk = __ballot_sync(0xffffffffu, p);
+        if (p) {
+            const int pos = m + __popc(mk & lt);
+            if (pos < 64) s_cmp[pos] = ((unsigned long long)vk[t] << 32) | (0xffffffffu - (rbase + 32u * (uint32_t)t));
         }
+        m += __popc(mk);
     }
     __syncwarp();
+    GV_T(0, 22);
+#ifdef SDK_GV_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 160) gv_trace[0][blockIdx.x][12] = (unsigned long long)m;
+#endif
     unsigned long long newkept = 0ull;
     if (m <= 64) {
         // exact rank of the survivors: lane holds entries lane and lane + 32
-        const unsigned long long e0 = lane < m ? s_cmp[lane] : 0ull, e1 = lane + 32 < m ? s_cmp[lane + 32] : 0ull;
-        int r0 = 0, r1 = 0;
-        for (int j = 0; j < m; ++j) {
-            const unsigned long long o = s_cmp[j];
-            r0 += o > e0 ? 1 : 0;
-            r1 += o > e1 ? 1 : 0;
+        const unsigned long long e0 = lane < m ? s_cmp[lane] : 0ull;
+        int r0 = 0;
+        unsigned long long e1 = 0ull;
+        int r1 = 0;
+        if (m <= 32) {
+#pragma unroll 4
+            for (int j = 0; j < m; ++j) r0 += s_cmp[j] > e0 ? 1 : 0;
+        } else {
+            e1 = lane + 32 < m ? s_cmp[lane + 32] : 0ull;
+#pragma unroll 4
+            for (int j = 0; j < m; ++j) {
+                const unsigned long long o = s_cmp[j];
+                r0 += o > e0 ? 1 : 0;
+                r1 += o > e1 ? 1 : 0;
+            }
         }
         __syncwarp();
         // scatter by rank: positions 0 .. GV_KEEP-1 are the new list, position GV_KEEP is the best dropped entry
@@ -196,7 +233,7 @@ __device__ __forceinline__ unsigned long long gv_select_top(const uint32_t (&vk)
 #pragma unroll 1
     for (int it = 0; it <= GV_KEEP; ++it) {
         unsigned long long best = (kept < last) ? kept : 0ull;
-#pragma unroll 1
+#pragma unroll
         for (int t = 0; t < T; ++t) {
             const unsigned long long c = vk[t] ? (((unsigned long long)vk[t] << 32) | (0xffffffffu - (rbase + 32u * (uint32_t)t))) : 0ull;
             best = (c < last && c > best) ? c : best;
@@ -222,15 +259,16 @@ template <int KB>
 __global__ void __launch_bounds__(GV_THREADS, 1)
 k_gemv8(const __grid_constant__ GvParams q) {
     extern __shared__ uint8_t gv_smem_raw[];
-    __shared__ __align__(8) uint2 s_bq[KB * 2][32];            // B fragments of MMA (kb, j), per lane
-    __shared__ int32_t s_lab[GV_NQ];                            // label of query s relative to label_base (clamped)
-    __shared__ int32_t s_run[GV_NQ];                            // > 0: query s starts a run of that many queries of one label
+    // B fragments of MMA (kb, j), per lane (n = l / 4, c = l % 4): b0 = q[n][32 kb + 8 c + 4 j + {0,1}], b1 = .. + {2,3};
+    // written by the warp that normalises query n (gv_normalize_row), zeros for absent queries
+    __shared__ __align__(8) uint2 s_bq[KB * 2][32];
     __shared__ __align__(8) unsigned long long s_cmp[GV_CW][64 + GV_KEEP + 2];
     const int lane = threadIdx.x & 31, cw = threadIdx.x >> 5;
     float* s_raw = reinterpret_cast<float*>(gv_smem_raw);                                               // [GV_NQ][GV_RAW_LD]
-    __nv_bfloat16* s_q = reinterpret_cast<__nv_bfloat16*>(s_raw + GV_NQ * GV_RAW_LD);                   // [GV_NQ][Dp]
     // the tail kernel may be scheduled as soon as every CTA has got here (it waits for this grid's completion itself)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    GV_TG(0, 0);
+    GV_T(0, 1);
     // this CTA's contiguous range of 32-row tiles
     const int64_t c0 = (int64_t)q.nchunk * blockIdx.x / gridDim.x, c1 = (int64_t)q.nchunk * (blockIdx.x + 1) / gridDim.x;
     const int64_t n_mine = c1 - c0;
@@ -238,41 +276,42 @@ k_gemv8(const __grid_constant__ GvParams q) {
     // shared memory): the whole pass is requested from DRAM at once, HBM runs at its own pace from the first microsecond
     // (also under the query preparation below), and the 128-bit loads of the tile loop find their lines in L2.  With
     // loads alone the bytes in flight per SM -- 16 x 16 bytes per lane -- did not cover the DRAM latency (ncu: DRAM 36 % busy).
-    auto prefetch_pass = [&](int64_t pass0) {
-        if (lane != 0) return;
-#pragma unroll
-        for (int h = 0; h < GV_PASS_TILES / GV_CW; ++h) {
-            const int64_t t = pass0 + cw + h * GV_CW;
-            if (t >= n_mine || t >= pass0 + GV_PASS_TILES) break;
-            const int64_t row0 = (c0 + t) * GV_ROWS;
-            const int64_t rows = q.P - row0 < GV_ROWS ? q.P - row0 : GV_ROWS;
-            if (rows <= 0) break;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q.bank + row0 * q.Dp), "r"((uint32_t)(rows * q.Dp * 2)) : "memory");
-        }
+    static_assert(GV_PASS_TILES == GV_CW, "one tile per warp and pass");
+    auto prefetch_pass = [&](int64_t pass0, int len) {
+        const int64_t t = pass0 + cw;
+        if (lane != 0 || cw >= len || t >= n_mine) return;
+        const int64_t row0 = (c0 + t) * GV_ROWS;
+        const int64_t rows = q.P - row0 < GV_ROWS ? q.P - row0 : GV_ROWS;
+        if (rows <= 0) return;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q.bank + row0 * q.Dp), "r"((uint32_t)(rows * q.Dp * 2)) : "memory");
     };
+    // The SHORT pass comes first (n_mine mod 16 tiles, then full passes of 16): its selection then runs while the DRAM is
+    // still busy with the tiles of the next pass, and the last MMA loop is paced by the DRAM, not by the L2 round trips of a
+    // few straggling tiles.  With the full pass first (26 tiles per CTA on config 4-i: 16 + 10) the first selection (4.9 us)
+    // and the second MMA loop (5.5 us) both ran after the last byte had arrived (tools/gv_trace.py).
+    const int first_len = n_mine > 0 ? (int)(n_mine - ((n_mine - 1) / GV_PASS_TILES) * GV_PASS_TILES) : 0;
     // ---- query preparation: labels, canonical normalise, B fragments ----
-    auto prefetch_first = [&]() { prefetch_pass(0); prefetch_pass(GV_PASS_TILES); };
-    if (cw == 0 && lane < GV_NQ) {
-        int32_t l = 0x7fffffff;
-        if (lane < q.N) {
-            l = q.seg_label[lane] - q.label_base;
-            l = l < 0 ? 0 : (l >= q.L ? q.L - 1 : l);
-        }
-        s_lab[lane] = l;
+    auto prefetch_first = [&]() { prefetch_pass(0, first_len); prefetch_pass(first_len, GV_PASS_TILES); };
+    // every warp reads the labels itself (lane s: query s, relative to label_base, clamped): the run of its selection
+    // slot needs no shared memory and no second barrier
+    int32_t mylab = 0x7fffffff;
+    if (lane < q.N) {
+        const int32_t l = q.seg_label[lane] - q.label_base;
+        mylab = l < 0 ? 0 : (l >= q.L ? q.L - 1 : l);
     }
     if (cw < GV_NQ) {
-        __nv_bfloat16* so = s_q + (size_t)cw * q.Dp;
+        uint2* so = &s_bq[0][0];
         if (cw < q.N) {
             const bool pub = blockIdx.x == 0;
             __nv_bfloat16* gb = pub ? q.seg_bf16 + (size_t)cw * q.Dp : nullptr;
             float* gf = (pub && q.seg_f32) ? q.seg_f32 + (size_t)cw * q.D : nullptr;
             if (q.in_dtype == SDK_IN_F16)
-                gv_normalize_row<__half>(reinterpret_cast<const __half*>(q.seg_raw) + (size_t)cw * q.D, q.D, q.Dp, lane, so, gb, gf, prefetch_first);
+                gv_normalize_row<__half>(reinterpret_cast<const __half*>(q.seg_raw) + (size_t)cw * q.D, q.D, q.Dp, lane, so, cw, gb, gf, prefetch_first);
             else
-                gv_normalize_row<float>(reinterpret_cast<const float*>(q.seg_raw) + (size_t)cw * q.D, q.D, q.Dp, lane, so, gb, gf, prefetch_first);
+                gv_normalize_row<float>(reinterpret_cast<const float*>(q.seg_raw) + (size_t)cw * q.D, q.D, q.Dp, lane, so, cw, gb, gf, prefetch_first);
         } else {
             prefetch_first();
-            for (int e = lane; e < q.Dp; e += 32) so[e] = __float2bfloat16_rn(0.f);
+            for (int e = lane; e < KB * 8; e += 32) so[(e >> 2) * 32 + cw * 4 + (e & 3)] = make_uint2(0u, 0u);
         }
     } else {
         prefetch_first();
@@ -301,35 +340,27 @@ k_gemv8(const __grid_constant__ GvParams q) {
         if (f && lane == 0) atomicOr(q.flags, f);
     }
     __syncthreads();
-    if (cw == 0 && lane < GV_NQ) {
-        int run = 0;
-        if (lane < q.N && (lane == 0 || s_lab[lane] != s_lab[lane - 1])) {
-            run = 1;
-            while (lane + run < q.N && s_lab[lane + run] == s_lab[lane]) ++run;
-        }
-        s_run[lane] = run;
-    }
-    {
-        // B fragment of MMA (kb, j), lane (n = l / 4, c = l % 4): b0 = q[n][32 kb + 8 c + 4 j + {0,1}], b1 = .. + {2,3}
-        const uint32_t* sq32 = reinterpret_cast<const uint32_t*>(s_q);
-        const int pitch = q.Dp >> 1;
-        for (int i = threadIdx.x; i < KB * 2 * 32; i += GV_THREADS) {
-            const int m = i >> 5, l = i & 31, kb = m >> 1, j = m & 1, n = l >> 2, c = l & 3;
-            const int w = kb * 16 + 4 * c + 2 * j;
-            s_bq[m][l] = make_uint2(sq32[n * pitch + w], sq32[n * pitch + w + 1]);
-        }
-    }
-    __syncthreads();
+    GV_T(0, 2);
+    GV_T(0, 3);
     // ---- selection state of this warp's (query slot, half): kept list in lanes 0..15, bound on everything dropped ----
     const int sel_q = cw >> 1, sel_part = cw & 1;
-    const int sel_len = s_run[sel_q];
+    int sel_len = 0;                                               // > 0: query sel_q starts a run of that many queries of one label
+    {
+        const int32_t lab_q = __shfl_sync(0xffffffffu, mylab, sel_q), lab_p = __shfl_sync(0xffffffffu, mylab, sel_q > 0 ? sel_q - 1 : 0);
+        const uint32_t eq = __ballot_sync(0xffffffffu, lane < q.N && lane >= sel_q && mylab == lab_q);
+        if (sel_q < q.N && (sel_q == 0 || lab_p != lab_q)) sel_len = __ffs((int)~(eq >> sel_q)) - 1;
+    }
     unsigned long long kept = 0ull;
     float bound = -3.0e38f;
     const int g8 = lane >> 2, c4 = lane & 3;
     const uint4* bank = reinterpret_cast<const uint4*>(q.bank);
     const int64_t pitch16 = q.Dp >> 3;                                 // row pitch in 16-byte units
-    for (int64_t pass0 = 0; pass0 < n_mine; pass0 += GV_PASS_TILES) {
-        const int npc = (int)((n_mine - pass0) < GV_PASS_TILES ? (n_mine - pass0) : GV_PASS_TILES);
+#ifdef SDK_GV_TRACE
+    int tpass = 0;
+#endif
+    int plen = first_len;
+    for (int64_t pass0 = 0; pass0 < n_mine; pass0 += plen, plen = GV_PASS_TILES) {
+        const int npc = plen;                                          // (first_len + a multiple of 16 = n_mine)
         for (int j = cw; j < npc; j += GV_CW) {
             const int64_t row0 = (c0 + pass0 + j) * GV_ROWS;
             // the four bank rows of this lane (two per 16-row tile); rows past P are read from the last row and dropped later
@@ -380,58 +411,80 @@ k_gemv8(const __grid_constant__ GvParams q) {
                 s_raw[(cq + 1) * GV_RAW_LD + r + 8] = acc[rt][3];
             }
         }
+#ifdef SDK_GV_TRACE
+        if (tpass < 3) GV_T(0, 4 + 4 * tpass);
+#endif
         __syncthreads();                                               // the raw scores of the pass are complete
-        prefetch_pass(pass0 + 2 * GV_PASS_TILES);                      // two passes ahead: DRAM keeps streaming under the selection
+#ifdef SDK_GV_TRACE
+        if (tpass < 3) GV_T(0, 5 + 4 * tpass);
+#endif
+        prefetch_pass(pass0 + plen + GV_PASS_TILES, GV_PASS_TILES);    // two passes ahead: DRAM keeps streaming under the selection
         if (sel_len > 0) {
-            // this warp's half of the pass: tiles [sel_part * 16, +16); lane <-> rows lane + 32 t.  Pool the label's queries
+            // this warp's half of the pass: tiles [sel_part * 8, +8); lane <-> rows lane + 32 t.  Pool the label's queries
             // (ascending), keep the GV_KEEP largest of (new rows, previously kept) by (score desc, row asc)
-            uint32_t vk[GV_PASS_TILES / GV_PARTS];
-            const float rlen = 1.0f / (float)sel_len;
+            constexpr int T = GV_PASS_TILES / GV_PARTS;
+            uint32_t vk[T];
+            // rows of this pass that exist: local index (tile * 32 + lane) < lim
+            const int64_t left = q.P - (c0 + pass0) * GV_ROWS;
+            const int lim = (int)(left < (int64_t)npc * GV_ROWS ? left : (int64_t)npc * GV_ROWS);
+            const int rl0 = sel_part * T * GV_ROWS + lane;
+            const float* v0 = s_raw + (size_t)sel_q * GV_RAW_LD + rl0;
+            const float tau = q.tau;
+            if (sel_len == 1) {                                        // one query per label (pooled centroids): no pooling loop
 #pragma unroll
-            for (int t = 0; t < GV_PASS_TILES / GV_PARTS; ++t) {
-                const int tl = sel_part * (GV_PASS_TILES / GV_PARTS) + t;
-                const int64_t row = (c0 + pass0 + tl) * GV_ROWS + lane;
-                uint32_t key = 0u;
-                if (tl < npc && row < q.P) {
-                    const float* v = s_raw + (size_t)sel_q * GV_RAW_LD + tl * GV_ROWS + lane;
-                    float a = q.pool == 0 ? 0.f : -3.0e38f;
-                    for (int s = 0; s < sel_len; ++s) a = q.pool == 0 ? a + v[s * GV_RAW_LD] : fmaxf(a, v[s * GV_RAW_LD]);
-                    const float val = q.pool == 0 ? a * rlen : a;
-                    if (val >= q.tau) key = sdk_fkey(val);
+                for (int t = 0; t < T; ++t) {
+                    const float val = v0[t * GV_ROWS];
+                    vk[t] = (rl0 + t * GV_ROWS < lim && val >= tau) ? sdk_fkey(val) : 0u;
                 }
-                vk[t] = key;
+            } else if (q.pool == 0) {
+                const float rlen = 1.0f / (float)sel_len;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    float a = 0.f;
+                    for (int s = 0; s < sel_len; ++s) a += v0[t * GV_ROWS + s * GV_RAW_LD];
+                    const float val = a * rlen;
+                    vk[t] = (rl0 + t * GV_ROWS < lim && val >= tau) ? sdk_fkey(val) : 0u;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    float a = -3.0e38f;
+                    for (int s = 0; s < sel_len; ++s) a = fmaxf(a, v0[t * GV_ROWS + s * GV_RAW_LD]);
+                    vk[t] = (rl0 + t * GV_ROWS < lim && a >= tau) ? sdk_fkey(a) : 0u;
+                }
             }
             const uint32_t rbase = (uint32_t)((c0 + pass0 + sel_part * (GV_PASS_TILES / GV_PARTS)) * GV_ROWS + lane);
+            GV_T(0, 20);
             kept = gv_select_top(vk, rbase, kept, bound, s_cmp[cw], lane);
         }
+#ifdef SDK_GV_TRACE
+        if (tpass < 3) GV_T(0, 6 + 4 * tpass);
+#endif
         __syncthreads();                                               // s_raw is rewritten by the next pass
+#ifdef SDK_GV_TRACE
+        if (tpass < 3) GV_T(0, 7 + 4 * tpass);
+        ++tpass;
+#endif
     }
-    // ---- publish this warp's list (every (query slot, list) entry is written: unused ones as empty) ----
+    // ---- publish this warp's list (every entry of every (query slot, list) is written: unused ones as 0) ----
     {
         const int64_t li = (int64_t)sel_q * q.nslots + (int64_t)blockIdx.x * GV_PARTS + sel_part;
-        const uint32_t have = __ballot_sync(0xffffffffu, kept != 0ull);
-        if (lane == 0) {
-            q.slot_cnt[li] = sel_len > 0 ? __popc(have) : 0;
-            q.slot_bound[li] = bound;
-        }
-        if (lane < GV_KEEP && kept != 0ull) {
-            q.slot_row[li * GV_KEEP + lane] = (int32_t)(0xffffffffu - (uint32_t)kept);
-            q.slot_val[li * GV_KEEP + lane] = sdk_funkey((uint32_t)(kept >> 32));
-        }
+        if (lane == 0) q.slot_bound[li] = bound;
+        if (lane < GV_KEEP) q.slot_key[li * GV_KEEP + lane] = kept;
     }
+    GV_T(0, 16);
+    GV_TG(0, 17);
 }
 
 // ---- tail: merge + canonical re-score + select + certificate, one CTA per label ------------------------------------
 struct GvTail {
     const int64_t* goff;
     int32_t N, L, k, pool, ncand, nslots, D, pitch, is_bf16;
-    int32_t stage16;              // 16-byte pieces of the operand staging area at the head of the dynamic shared memory
+    int32_t stage16;              // 16-byte pieces of the fp64 operand area at the head of the dynamic shared memory
     double threshold;
     float eps;
-    const int32_t* slot_cnt;
     const float* slot_bound;
-    const int32_t* slot_row;
-    const float* slot_val;
+    const unsigned long long* slot_key;
     const void* bank_ops;
     const void* seg_ops;
     const int32_t* row_speaker;
@@ -487,37 +540,49 @@ __device__ __forceinline__ double gv_dot(const void* __restrict__ a_ops, int64_t
     return acc;
 }
 
-// the same chain over operand rows staged in shared memory (16-byte pieces; n16 pieces cover D)
+// ---- stage B operands in shared memory: WIDENED TO fp64 WHILE THEY ARE STAGED ------------------------------------------
+// The canonical chain is one fma per element, in order, so its floor is the DFMA latency times D.  Converting inside the
+// chain put two F2F.F64.F32 in front of every DFMA; that unit takes 8 cycles per warp instruction, and with all pairs of a
+// small label in one warp the chain ran at 25 cycles per element (6.7 us for D = 512: tools/gv_trace.py).  The conversions
+// are exact whoever does them, so the 256 threads that copy the rows do them, in parallel, and the chain is LDS + DFMA.
 template <bool BF16>
-__device__ __forceinline__ double gv_dot_smem(const uint4* __restrict__ a, const uint4* __restrict__ b, int n16) {
-    double acc = 0.0;
-#pragma unroll 4
-    for (int i = 0; i < n16; ++i) {
-        const uint4 ca = a[i], cb = b[i];
-        const uint32_t wa[4] = {ca.x, ca.y, ca.z, ca.w}, wb[4] = {cb.x, cb.y, cb.z, cb.w};
+__device__ __forceinline__ void gv_widen_store(double* __restrict__ row, int i, const uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (BF16) {
+        double2* d = reinterpret_cast<double2*>(row + 8 * i);          // piece i = elements 8 i .. 8 i + 7
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            if (BF16) {
-                // (F2F.F64.F32 conversions: an integer re-bias of the bf16 bits was tried -- the chain is bound by the DFMA
-                //  dependency, and the extra integer instructions doubled the kernel's time)
-                acc = fma((double)__uint_as_float(wa[h] << 16), (double)__uint_as_float(wb[h] << 16), acc);
-                acc = fma((double)__uint_as_float(wa[h] & 0xffff0000u), (double)__uint_as_float(wb[h] & 0xffff0000u), acc);
-            } else {
-                acc = fma((double)__uint_as_float(wa[h]), (double)__uint_as_float(wb[h]), acc);
-            }
-        }
+        for (int h = 0; h < 4; ++h)
+            d[h] = make_double2((double)__uint_as_float(w[h] << 16), (double)__uint_as_float(w[h] & 0xffff0000u));
+    } else {
+        double2* d = reinterpret_cast<double2*>(row + 4 * i);          // piece i = elements 4 i .. 4 i + 3
+        d[0] = make_double2((double)__uint_as_float(w[0]), (double)__uint_as_float(w[1]));
+        d[1] = make_double2((double)__uint_as_float(w[2]), (double)__uint_as_float(w[3]));
+    }
+}
+// one fp64 fma chain over ascending d (the canonical order); n2 = pairs of elements (an odd D ends in a zero pair half)
+__device__ __forceinline__ double gv_dot_f64(const double* __restrict__ a, const double* __restrict__ b, int n2) {
+    const double2* a2 = reinterpret_cast<const double2*>(a);
+    const double2* b2 = reinterpret_cast<const double2*>(b);
+    double acc = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < n2; ++i) {
+        const double2 x = a2[i], y = b2[i];
+        acc = fma(x.x, y.x, acc);
+        acc = fma(x.y, y.y, acc);
     }
     return acc;
 }
 
 #define GV_TAIL_CHUNK 16             // candidate rows staged at a time
+#define GV_TAIL_LB 10                // 16-byte list pieces per thread in flight (2 x 148 lists x 16 keys = 2368 pieces: one batch)
+#define GV_TAIL_RB 4                 // 16-byte operand pieces per thread in flight (16 rows x 1 KB = 1024 pieces: one batch)
 __global__ void __launch_bounds__(GV_TAIL_THREADS)
 k_gemv8_tail(const __grid_constant__ GvTail p) {
-    extern __shared__ uint4 s_stage[];                         // [GV_NQ segment rows + GV_TAIL_CHUNK bank rows][row16 + 1]
+    extern __shared__ uint4 s_stage[];                         // fp64 operands [GV_NQ segment rows + GV_TAIL_CHUNK bank rows][pitch + 2], then the lists
     __shared__ unsigned long long s_key[GV_TAIL_CAP];          // compacted candidates
     __shared__ unsigned long long s_sel[64];                   // the ncand best, by rank
     __shared__ long long s_pool[64];
-    __shared__ int32_t s_spk[SDK_MAX_K];
+    __shared__ int s_rank[128];
     __shared__ unsigned long long s_T0, s_Tsel;
     __shared__ int s_m, s_over;
     __shared__ float s_bnd[GV_TAIL_THREADS / 32];
@@ -525,7 +590,10 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
     const int g = blockIdx.x;
     const int k = p.k, ncand = p.ncand, nslots = p.nslots;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // sdk_assign's kernel may queue up behind this one
+    GV_TG(1, 0);
     asm volatile("griddepcontrol.wait;" ::: "memory");                // everything the stream kernel wrote is visible
+    GV_TG(1, 1);
+    GV_T(1, 2);
     int64_t s0 = p.goff[g], s1 = p.goff[g + 1];
     s0 = s0 < 0 ? 0 : (s0 > p.N ? p.N : s0);
     s1 = s1 < 0 ? 0 : (s1 > p.N ? p.N : s1);
@@ -545,48 +613,107 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
         return;
     }
     const int64_t lbase = (int64_t)s0 * nslots;                // lists of the label: query slot = its first query
-    // ---- 0. the label's lists come into shared memory in one coalesced sweep (everything below reads them there: the
-    //         list-by-list walks would otherwise wait a memory round trip per entry) ----
+    // operand geometry: rows of `pitch` elements (bf16: Dp, zero padded; fp32: D), copied in 16-byte pieces
+    const int row_bytes = p.is_bf16 ? p.pitch * 2 : p.pitch * 4;
+    const bool staged = (row_bytes & 15) == 0;
+    const int row16 = row_bytes >> 4;
+    const int ldd = p.pitch + 2;                               // + 16 bytes: rows of different candidates in different banks
+    double* s_seg = reinterpret_cast<double*>(s_stage);
+    double* s_row = s_seg + (size_t)GV_NQ * ldd;
     unsigned long long* s_lkey = reinterpret_cast<unsigned long long*>(s_stage + p.stage16);   // [nslots][GV_KEEP] keys, 0 = no entry
     float* s_lbound = reinterpret_cast<float*>(s_lkey + (size_t)nslots * GV_KEEP);            // [nslots]
-    int32_t* s_lcnt = reinterpret_cast<int32_t*>(s_lbound + nslots);                          // [nslots]
     if (tid == 0) { s_m = 0; s_over = 0; s_T0 = 0ull; s_Tsel = 0ull; }
-    for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
-        s_lcnt[s] = p.slot_cnt[lbase + s];
-        s_lbound[s] = p.slot_bound[lbase + s];
+    if (tid < 128) s_rank[tid] = 0;
+    // ---- 0. everything this CTA needs from the stream kernel is REQUESTED before anything is used: the label's segment
+    //         operands, its lists (one coalesced sweep of 16-byte pieces) and their bounds; then stored (the lists as they
+    //         are, the operands widened to fp64).  Read list by list this phase cost a memory round trip per entry. ----
+    const uint4* gseg = reinterpret_cast<const uint4*>(p.seg_ops) + (int64_t)s0 * row16;      // the label's rows are contiguous
+    const int nseg16 = staged ? n * row16 : 0;
+    uint4 sb[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int idx = tid + u * GV_TAIL_THREADS;
+        if (idx < nseg16) sb[u] = __ldg(gseg + idx);
     }
-    for (int i = tid; i < nslots * GV_KEEP; i += GV_TAIL_THREADS) {
-        const int s = i / GV_KEEP, e = i - s * GV_KEEP;
-        // (all three loads go out together; entries past the list's count are stale and masked here)
-        const int32_t cnt = p.slot_cnt[lbase + s];
-        const float v = p.slot_val[lbase * GV_KEEP + i];
-        const int32_t r = p.slot_row[lbase * GV_KEEP + i];
-        s_lkey[i] = e < cnt ? (((unsigned long long)sdk_fkey(v) << 32) | (0xffffffffu - (uint32_t)r)) : 0ull;
+    float bb[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int sidx = tid + u * GV_TAIL_THREADS;
+        bb[u] = sidx < nslots ? p.slot_bound[lbase + sidx] : -3.0e38f;
+    }
+    {
+        const ulonglong2* gk = reinterpret_cast<const ulonglong2*>(p.slot_key + lbase * GV_KEEP);
+        ulonglong2* sk2 = reinterpret_cast<ulonglong2*>(s_lkey);
+        const int nl16 = nslots * (GV_KEEP / 2);
+        for (int base = 0; base < nl16; base += GV_TAIL_THREADS * GV_TAIL_LB) {
+            ulonglong2 lb[GV_TAIL_LB];
+#pragma unroll
+            for (int u = 0; u < GV_TAIL_LB; ++u) {
+                const int idx = base + u * GV_TAIL_THREADS + tid;
+                if (idx < nl16) lb[u] = gk[idx];
+            }
+#pragma unroll
+            for (int u = 0; u < GV_TAIL_LB; ++u) {
+                const int idx = base + u * GV_TAIL_THREADS + tid;
+                if (idx < nl16) sk2[idx] = lb[u];
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int sidx = tid + u * GV_TAIL_THREADS;
+        if (sidx < nslots) s_lbound[sidx] = bb[u];
+    }
+    for (int sidx = tid + 2 * GV_TAIL_THREADS; sidx < nslots; sidx += GV_TAIL_THREADS) s_lbound[sidx] = p.slot_bound[lbase + sidx];
+    for (int base = 0; base < nseg16; base += 2 * GV_TAIL_THREADS) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int idx = base + tid + u * GV_TAIL_THREADS;
+            if (idx < nseg16) {
+                if (base > 0) sb[u] = __ldg(gseg + idx);
+                const int t = idx / row16, i = idx - t * row16;
+                if (p.is_bf16) gv_widen_store<true>(s_seg + (size_t)t * ldd, i, sb[u]);
+                else gv_widen_store<false>(s_seg + (size_t)t * ldd, i, sb[u]);
+            }
+        }
     }
     __syncthreads();
+    GV_T(1, 3);
     // ---- 1. T0 = ncand-th largest list maximum: a lower bound on the ncand-th best entry overall ----
-    // (any lower bound will do: the maxima of the first 128 lists are ranked, not all 2 x grid of them)
+    // (any lower bound will do: the maxima of the first 128 lists are ranked, not all 2 x grid of them; two threads per list)
     const int nmax = nslots < 128 ? nslots : 128;
-    for (int s = tid; s < nmax; s += GV_TAIL_THREADS) {
-        const unsigned long long mine = s_lkey[s * GV_KEEP];
-        if (mine == 0ull) continue;
-        int rank = 0;
-        for (int j = 0; j < nmax; ++j) rank += s_lkey[j * GV_KEEP] > mine ? 1 : 0;
-        if (rank == ncand - 1) s_T0 = mine;                        // keys are unique: exactly one list has this rank (if any)
+    {
+        const int sidx = tid & 127, half = tid >> 7, mid = (nmax + 1) >> 1;
+        if (sidx < nmax) {
+            const unsigned long long mine = s_lkey[sidx * GV_KEEP];
+            if (mine != 0ull) {
+                const int j0 = half ? mid : 0, j1 = half ? nmax : mid;
+                int rank = 0;
+#pragma unroll 4
+                for (int j = j0; j < j1; ++j) rank += s_lkey[j * GV_KEEP] > mine ? 1 : 0;
+                if (rank) atomicAdd(&s_rank[sidx], rank);
+            }
+        }
     }
     __syncthreads();
+    if (tid < nmax) {
+        const unsigned long long mine = s_lkey[tid * GV_KEEP];
+        if (mine != 0ull && s_rank[tid] == ncand - 1) s_T0 = mine;  // keys are unique: exactly one list has this rank (if any)
+    }
+    __syncthreads();
+    GV_T(1, 4);
     // ---- 2. compaction of every entry >= T0 (each list is sorted: a prefix) ----
     const unsigned long long T0 = s_T0;
-    for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
-        const int cnt = s_lcnt[s];
-        for (int e = 0; e < cnt; ++e) {
-            const unsigned long long key = s_lkey[s * GV_KEEP + e];
-            if (key < T0) break;
+    for (int sidx = tid; sidx < nslots; sidx += GV_TAIL_THREADS) {
+        for (int e = 0; e < GV_KEEP; ++e) {
+            const unsigned long long key = s_lkey[sidx * GV_KEEP + e];
+            if (key == 0ull || key < T0) break;
             const int pos = atomicAdd(&s_m, 1);
             if (pos < GV_TAIL_CAP) s_key[pos] = key; else s_over = 1;
         }
     }
     __syncthreads();
+    GV_T(1, 5);
     const int m = s_m < GV_TAIL_CAP ? s_m : GV_TAIL_CAP;
     // ---- 3. exact rank of the compacted entries; the ncand best in order ----
     for (int i = tid; i < 64; i += GV_TAIL_THREADS) s_sel[i] = 0ull;
@@ -594,15 +721,32 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
     for (int i = tid; i < m; i += GV_TAIL_THREADS) {
         const unsigned long long mine = s_key[i];
         int rank = 0;
+#pragma unroll 4
         for (int j = 0; j < m; ++j) rank += s_key[j] > mine ? 1 : 0;
         if (rank < ncand) s_sel[rank] = mine;
         if (rank == ncand - 1) s_Tsel = mine;
     }
     __syncthreads();
+    GV_T(1, 6);
     const int nc = m < ncand ? m : ncand;
     const unsigned long long Tsel = s_Tsel;                        // 0: every entry of every list was selected
-    // every candidate's speaker / trust is requested now and used after stage B: the extraction loop at the end then never
-    // waits for memory
+    // the first chunk of candidate rows is requested NOW and stored after the bound phase; every candidate's speaker /
+    // trust too (used after stage B: the extraction loop at the end then never waits for memory)
+    const uint4* gbank = reinterpret_cast<const uint4*>(p.bank_ops);
+    uint4 rb[GV_TAIL_RB];
+    {
+        const int cc0 = nc < GV_TAIL_CHUNK ? nc : GV_TAIL_CHUNK;
+        const int np0 = staged ? cc0 * row16 : 0;
+#pragma unroll
+        for (int u = 0; u < GV_TAIL_RB; ++u) {
+            const int idx = tid + u * GV_TAIL_THREADS;
+            if (idx < np0) {
+                const int j = idx / row16, i = idx - j * row16;
+                const int64_t row = (int64_t)(0xffffffffu - (uint32_t)s_sel[j]);
+                rb[u] = __ldg(gbank + row * row16 + i);
+            }
+        }
+    }
     int32_t spk0 = -1, spk1 = -1;
     uint32_t tr0 = SDK_TRUST_UNKNOWN, tr1 = SDK_TRUST_UNKNOWN;
     if (warp == 0) {
@@ -619,12 +763,12 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
     }
     // ---- 4. bound on everything that is not a candidate: dropped inside the stream kernel, or left in a list ----
     float bnd = -3.0e38f;
-    for (int s = tid; s < nslots; s += GV_TAIL_THREADS) {
-        const int cnt = s_lcnt[s];
-        bnd = fmaxf(bnd, s_lbound[s]);
+    for (int sidx = tid; sidx < nslots; sidx += GV_TAIL_THREADS) {
+        bnd = fmaxf(bnd, s_lbound[sidx]);
         if (Tsel != 0ull) {
-            for (int e = 0; e < cnt; ++e) {
-                const unsigned long long key = s_lkey[s * GV_KEEP + e];
+            for (int e = 0; e < GV_KEEP; ++e) {
+                const unsigned long long key = s_lkey[sidx * GV_KEEP + e];
+                if (key == 0ull) break;
                 if (key < Tsel) { bnd = fmaxf(bnd, sdk_funkey((uint32_t)(key >> 32))); break; }
             }
         }
@@ -634,6 +778,7 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
     if (lane == 0) s_bnd[warp] = bnd;
     if (tid < 64) s_pool[tid] = p.pool == 0 ? 0ll : LLONG_MIN;
     __syncthreads();
+    GV_T(1, 7);
     if (tid == 0) {
         for (int w = 1; w < GV_TAIL_THREADS / 32; ++w) bnd = fmaxf(bnd, s_bnd[w]);
         if (s_over) bnd = 3.0e38f;                                 // more live entries than the tail holds: cannot certify
@@ -644,34 +789,37 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
         p.cand_row[(int64_t)g * ncand + i] = (int32_t)(0xffffffffu - (uint32_t)s_sel[i]);
         p.cand_val[(int64_t)g * ncand + i] = sdk_funkey((uint32_t)(s_sel[i] >> 32));
     }
-    // ---- 5. stage B: canonical pooled scores of the candidates (thread = (candidate, segment) pair).  The operand rows are
-    //         staged in shared memory by the whole CTA first (coalesced, all loads in flight): a serial fp64 chain fed from
-    //         global memory waits a DRAM round trip per 16 bytes (measured: 41 us for this kernel, 8 labels x 16 x 1 KB) ----
-    const int row_bytes = p.is_bf16 ? p.pitch * 2 : p.pitch * 4;
-    if ((row_bytes & 15) == 0) {
-        const int row16 = row_bytes >> 4, ld16 = row16 + 1;        // + 16 bytes: rows of different candidates in different banks
-        const int n16 = p.is_bf16 ? (p.D + 7) >> 3 : p.D >> 2;
-        uint4* s_seg = s_stage;
-        uint4* s_row = s_stage + GV_NQ * ld16;
-        const uint4* gseg = reinterpret_cast<const uint4*>(p.seg_ops);
-        const uint4* gbank = reinterpret_cast<const uint4*>(p.bank_ops);
-        for (int idx = tid; idx < n * row16; idx += GV_TAIL_THREADS) {
-            const int t = idx / row16, i = idx - t * row16;
-            s_seg[t * ld16 + i] = __ldg(gseg + (s0 + t) * (int64_t)row16 + i);
-        }
+    // ---- 5. stage B: canonical pooled scores of the candidates (thread = (candidate, segment) pair) over the fp64 rows ----
+    if (staged) {
+        const int n2 = p.is_bf16 ? (p.D + 1) >> 1 : p.D >> 1;      // (bf16 rows are zero padded past D; fp32 rows here have D % 4 == 0)
         for (int cb = 0; cb < nc; cb += GV_TAIL_CHUNK) {
             const int cc = nc - cb < GV_TAIL_CHUNK ? nc - cb : GV_TAIL_CHUNK;
-            __syncthreads();                                       // the previous chunk has been consumed
-            for (int idx = tid; idx < cc * row16; idx += GV_TAIL_THREADS) {
-                const int j = idx / row16, i = idx - j * row16;
-                const int64_t row = (int64_t)(0xffffffffu - (uint32_t)s_sel[cb + j]);
-                s_row[j * ld16 + i] = __ldg(gbank + row * row16 + i);
+            if (cb > 0) __syncthreads();                           // the previous chunk has been consumed
+            for (int base = 0; base < cc * row16; base += GV_TAIL_RB * GV_TAIL_THREADS) {
+#pragma unroll
+                for (int u = 0; u < GV_TAIL_RB; ++u) {
+                    const int idx = base + tid + u * GV_TAIL_THREADS;
+                    if (idx < cc * row16 && (cb > 0 || base > 0)) {
+                        const int j = idx / row16, i = idx - j * row16;
+                        const int64_t row = (int64_t)(0xffffffffu - (uint32_t)s_sel[cb + j]);
+                        rb[u] = __ldg(gbank + row * row16 + i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < GV_TAIL_RB; ++u) {
+                    const int idx = base + tid + u * GV_TAIL_THREADS;
+                    if (idx < cc * row16) {
+                        const int j = idx / row16, i = idx - j * row16;
+                        if (p.is_bf16) gv_widen_store<true>(s_row + (size_t)j * ldd, i, rb[u]);
+                        else gv_widen_store<false>(s_row + (size_t)j * ldd, i, rb[u]);
+                    }
+                }
             }
             __syncthreads();
+            if (cb == 0) GV_T(1, 8);
             for (int pr = tid; pr < cc * n; pr += GV_TAIL_THREADS) {
                 const int j = pr / n, t = pr - j * n;
-                const double sc = p.is_bf16 ? gv_dot_smem<true>(s_seg + t * ld16, s_row + j * ld16, n16)
-                                            : gv_dot_smem<false>(s_seg + t * ld16, s_row + j * ld16, n16);
+                const double sc = gv_dot_f64(s_seg + (size_t)t * ldd, s_row + (size_t)j * ldd, n2);
                 const long long qv = __double2ll_rn(sc * SDK_Q30);
                 if (p.pool == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_pool[cb + j]), (unsigned long long)qv);
                 else atomicMax(&s_pool[cb + j], qv);
@@ -688,7 +836,9 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
         }
     }
     __syncthreads();
-    // ---- 6. row -> speaker max, threshold, ordered top-k, certificate (k_select's semantics), one warp ----
+    GV_T(1, 9);
+    // ---- 6. row -> speaker max, threshold, ordered top-k, certificate (k_select's semantics), one warp.  The accepted
+    //         matches stay in registers (lane i holds the i-th) and are written together at the end ----
     if (warp != 0) return;
     unsigned long long key0 = 0ull, key1 = 0ull;
     if (lane < nc) {
@@ -702,6 +852,9 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
     unsigned long long last = ~0ull;
     int cnt = 0;
     float kth = 0.f;
+    int32_t a_spk = -1, a_row = -1;
+    float a_sim = 0.f;
+    uint32_t a_tr = SDK_TRUST_UNKNOWN;
     while (cnt < k) {
         unsigned long long best = (key0 < last) ? key0 : 0ull;
         best = (key1 < last && key1 > best) ? key1 : best;
@@ -710,24 +863,25 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
         last = best;
         const float sim = sdk_funkey((uint32_t)(best >> 32));
         if (!((double)sim >= p.threshold)) break;
-        const int32_t row = (int32_t)(0xffffffffu - (uint32_t)best);
         const uint32_t m0 = __ballot_sync(0xffffffffu, key0 == best), m1 = __ballot_sync(0xffffffffu, key1 == best);
         const int src = m0 ? __ffs(m0) - 1 : __ffs(m1) - 1;
         const int32_t spk = __shfl_sync(0xffffffffu, m0 ? spk0 : spk1, src);
         const uint32_t tr = __shfl_sync(0xffffffffu, m0 ? tr0 : tr1, src);
-        bool dup = false;
-        for (int i = 0; i < cnt; ++i) dup |= s_spk[i] == spk;
-        if (dup) continue;
-        if (lane == 0) {
-            s_spk[cnt] = spk;
-            p.o_row[(int64_t)g * k + cnt] = (int64_t)row + p.row_offset;
-            p.o_score[(int64_t)g * k + cnt] = sim;
-            p.o_trust[(int64_t)g * k + cnt] = (uint8_t)tr;
-            p.o_spk[(int64_t)g * k + cnt] = spk;
+        if (__ballot_sync(0xffffffffu, lane < cnt && a_spk == spk) != 0u) continue;     // a better row of this speaker is in
+        if (lane == cnt) {
+            a_spk = spk;
+            a_row = (int32_t)(0xffffffffu - (uint32_t)best);
+            a_sim = sim;
+            a_tr = tr;
         }
-        __syncwarp();
         kth = sim;
         ++cnt;
+    }
+    if (lane < cnt) {
+        p.o_row[(int64_t)g * k + lane] = (int64_t)a_row + p.row_offset;
+        p.o_score[(int64_t)g * k + lane] = a_sim;
+        p.o_trust[(int64_t)g * k + lane] = (uint8_t)a_tr;
+        p.o_spk[(int64_t)g * k + lane] = a_spk;
     }
     if (lane == 0) {
         p.o_count[g] = cnt;
@@ -740,6 +894,8 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
             p.fb_list[pos] = g;
         }
     }
+    GV_T(1, 10);
+    GV_TG(1, 11);
 }
 
 int sdk_gemv_applicable(int64_t N, int32_t Dp) { return N >= 1 && N <= GV_NQ && sdk_poolgemm_supported(Dp); }
@@ -757,14 +913,12 @@ int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype
     const int32_t nchunk = (int32_t)((P + GV_ROWS - 1) / GV_ROWS);
     const int grid = (int)std::min<int64_t>(nchunk, std::min(c->sm_count, 148));
     const int32_t nslots = grid * GV_PARTS;
-    const size_t smem = (size_t)GV_NQ * GV_RAW_LD * 4 + (size_t)GV_NQ * Dp * 2;
+    const size_t smem = (size_t)GV_NQ * GV_RAW_LD * 4;
     SDK_TRY(sdk_reserve(c, c->goff, (size_t)(L + 1) * 8));
     SDK_TRY(sdk_reserve(c, c->seg_bf16, (size_t)N * Dp * 2));
     if (!bf16) SDK_TRY(sdk_reserve(c, c->seg_f32, (size_t)N * D * 4));
-    SDK_TRY(sdk_reserve(c, c->slot_cnt, (size_t)GV_NQ * nslots * 4));
     SDK_TRY(sdk_reserve(c, c->slot_bound, (size_t)GV_NQ * nslots * 4));
-    SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)GV_NQ * nslots * GV_KEEP * 4));
-    SDK_TRY(sdk_reserve(c, c->slot_val, (size_t)GV_NQ * nslots * GV_KEEP * 4));
+    SDK_TRY(sdk_reserve(c, c->slot_row, (size_t)GV_NQ * nslots * GV_KEEP * 8));          // 64-bit keys on this path
     SDK_TRY(sdk_reserve(c, c->cand_row, (size_t)L * ncand * 4));
     SDK_TRY(sdk_reserve(c, c->cand_val, (size_t)L * ncand * 4));
     SDK_TRY(sdk_reserve(c, c->gbound, (size_t)L * 4));
@@ -788,10 +942,8 @@ int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype
     q.flags = d_flags + SDK_FLAG_LABEL;
     q.seg_bf16 = (__nv_bfloat16*)c->seg_bf16.p;
     q.seg_f32 = bf16 ? nullptr : (float*)c->seg_f32.p;
-    q.slot_cnt = (int32_t*)c->slot_cnt.p;
     q.slot_bound = (float*)c->slot_bound.p;
-    q.slot_row = (int32_t*)c->slot_row.p;
-    q.slot_val = (float*)c->slot_val.p;
+    q.slot_key = (unsigned long long*)c->slot_row.p;
     {
         sdk_prof_scope ps(c, "poolgemm");         // stage A of the certified top-k, whichever kernel runs it
 #define GV_LAUNCH(K)                                                                                            \
@@ -826,10 +978,8 @@ int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype
     t.is_bf16 = bf16 ? 1 : 0;
     t.threshold = threshold;
     t.eps = eps;
-    t.slot_cnt = q.slot_cnt;
     t.slot_bound = q.slot_bound;
-    t.slot_row = q.slot_row;
-    t.slot_val = q.slot_val;
+    t.slot_key = q.slot_key;
     t.bank_ops = bf16 ? c->bank_bf16.p : c->bank_f32.p;
     t.seg_ops = bf16 ? (const void*)c->seg_bf16.p : (const void*)c->seg_f32.p;
     t.row_speaker = (const int32_t*)c->row_speaker.p;
@@ -851,7 +1001,7 @@ int sdk_launch_gemv_identify(sdk_ctx* c, const void* d_seg_raw, int32_t in_dtype
         cfg.gridDim = dim3((unsigned)L);
         cfg.blockDim = dim3(GV_TAIL_THREADS);
         const int row_bytes = bf16 ? Dp * 2 : D * 4;
-        const size_t stage_bytes = (row_bytes & 15) == 0 ? (size_t)(GV_NQ + GV_TAIL_CHUNK) * (row_bytes + 16) : 16;
+        const size_t stage_bytes = (row_bytes & 15) == 0 ? (size_t)(GV_NQ + GV_TAIL_CHUNK) * (size_t)(t.pitch + 2) * 8 : 16;
         t.stage16 = (int32_t)(stage_bytes / 16);
         const size_t tail_smem = stage_bytes + (size_t)nslots * (GV_KEEP * 8 + 8);
         SDK_CUDA(c, cudaFuncSetAttribute(k_gemv8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));

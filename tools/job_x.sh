@@ -1,0 +1,16 @@
+# round 2, job x: small-query path after the phase trace (short pass first, slim selection, fp64-staged tail)
+set -o pipefail
+S=${1:-x}
+T="timeout 420 python -m pytest -q -x --timeout 100 -m gpu"
+$T tests/test_gpu_small.py tests/test_gpu_certificate.py tests/test_gpu_f16.py tests/test_gpu_fuzz.py 2>&1 | tail -12 | tee gpurun_out/r02_gputests_${S}1.log || { echo "SMALL PATH TESTS FAILED"; exit 1; }
+timeout 120 python tools/gv_trace.py 2>&1 | tee gpurun_out/gv_trace_${S}.log
+B="python bench.py --no-cpu --no-sharded --no-poolfirst"
+timeout 150 $B --workload cfg4i --steps 20 --warmup 5 > gpurun_out/r02_bench_cfg4i_n1_${S}.json 2> gpurun_out/r02_bench_cfg4i_${S}.err || tail -5 gpurun_out/r02_bench_cfg4i_${S}.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r02_bench_cfg4i_n1_${S}.json').read().strip().splitlines()[-1])
+print('cfg4i ms', round(d['ms_per_step'],4), 'roof', round(d['roofline']['frac'],3), 'avg', round(d['roofline']['avg_launch_ms'],4), 'par', (d.get('parity_sample') or {}).get('status'), {k:round(v,4) for k,v in d.get('kernel_ms_per_step',{}).items() if v>0}, 'e2e', '%.3g'%d['e2e']['value'] if d['e2e'] else None, d['clocks']['sm_mhz'])
+PY
+BB="python bench.py --no-e2e --no-cpu --no-sharded --no-poolfirst --no-parity"
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_launches_cfg4i_${S}.csv $BB --workload cfg4i --steps 3 --warmup 2 > gpurun_out/ncu_l_cfg4i.log 2>&1
+python tools/launch_share.py gpurun_out/r02_launches_cfg4i_${S}.csv | head -8
