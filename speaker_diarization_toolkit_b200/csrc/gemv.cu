@@ -272,10 +272,14 @@ k_gemv8(const __grid_constant__ GvParams q) {
     // this CTA's contiguous range of 32-row tiles
     const int64_t c0 = (int64_t)q.nchunk * blockIdx.x / gridDim.x, c1 = (int64_t)q.nchunk * (blockIdx.x + 1) / gridDim.x;
     const int64_t n_mine = c1 - c0;
-    // Every warp asks the memory system for the tiles of its next pass with ONE bulk L2 prefetch each (no registers, no
-    // shared memory): the whole pass is requested from DRAM at once, HBM runs at its own pace from the first microsecond
-    // (also under the query preparation below), and the 128-bit loads of the tile loop find their lines in L2.  With
-    // loads alone the bytes in flight per SM -- 16 x 16 bytes per lane -- did not cover the DRAM latency (ncu: DRAM 36 % busy).
+    // The FIRST pass is asked for with one bulk L2 prefetch per warp and tile before the query preparation (no registers, no
+    // shared memory): HBM runs from the first microsecond, under the 3-4 us the queries take, and the loads of the first
+    // tile loop find their lines in L2.  Every later pass is read with the loads alone (16 warps x 16 x 16 bytes per lane in
+    // flight: 7.0 TB/s measured for the second pass of config 4-i) plus a two-line prefetch per row issued before each
+    // selection.  Requesting the later passes up front as well was measured 2.3 us slower (tools/gv_trace.py,
+    // profiles/r02_gv_trace_e*.log): the two passes are then served interleaved, the first one is complete only when 70 % of
+    // everything has arrived, every load queues behind 128 MB of outstanding requests (2-3 us per group even for lines
+    // that are already in L2), and all of the bank crosses the L2 slices twice.
     static_assert(GV_PASS_TILES == GV_CW, "one tile per warp and pass");
     auto prefetch_pass = [&](int64_t pass0, int len) {
         const int64_t t = pass0 + cw;
@@ -285,13 +289,12 @@ k_gemv8(const __grid_constant__ GvParams q) {
         if (rows <= 0) return;
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q.bank + row0 * q.Dp), "r"((uint32_t)(rows * q.Dp * 2)) : "memory");
     };
-    // The SHORT pass comes first (n_mine mod 16 tiles, then full passes of 16): its selection then runs while the DRAM is
-    // still busy with the tiles of the next pass, and the last MMA loop is paced by the DRAM, not by the L2 round trips of a
-    // few straggling tiles.  With the full pass first (26 tiles per CTA on config 4-i: 16 + 10) the first selection (4.9 us)
-    // and the second MMA loop (5.5 us) both ran after the last byte had arrived (tools/gv_trace.py).
+    // The SHORT pass comes first (n_mine mod 16 tiles, then full passes of 16): the prefetched part is small and complete
+    // early (10 us on config 4-i: 10-11 of 26-27 tiles), and the passes that stream with loads alone have a tile for every
+    // warp.
     const int first_len = n_mine > 0 ? (int)(n_mine - ((n_mine - 1) / GV_PASS_TILES) * GV_PASS_TILES) : 0;
     // ---- query preparation: labels, canonical normalise, B fragments ----
-    auto prefetch_first = [&]() { prefetch_pass(0, first_len); prefetch_pass(first_len, GV_PASS_TILES); };
+    auto prefetch_first = [&]() { prefetch_pass(0, first_len); };
     // every warp reads the labels itself (lane s: query s, relative to label_base, clamped): the run of its selection
     // slot needs no shared memory and no second barrier
     int32_t mylab = 0x7fffffff;
@@ -418,7 +421,17 @@ k_gemv8(const __grid_constant__ GvParams q) {
 #ifdef SDK_GV_TRACE
         if (tpass < 3) GV_T(0, 5 + 4 * tpass);
 #endif
-        prefetch_pass(pass0 + plen + GV_PASS_TILES, GV_PASS_TILES);    // two passes ahead: DRAM keeps streaming under the selection
+        {   // the first load group of this warp's tile of the NEXT pass (lane r: the first 256 bytes of row r, two lines): the
+            // DRAM works on it while the CTA selects.  Plain prefetch instructions: a bulk prefetch per lane kept the warp
+            // busy for a microsecond.
+            const int64_t t = pass0 + plen + cw;
+            const int64_t row = (c0 + t) * GV_ROWS + lane;
+            if (t < n_mine && row < q.P) {
+                const char* a = reinterpret_cast<const char*>(q.bank + row * q.Dp);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                if (q.Dp * 2 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
+            }
+        }
         if (sel_len > 0) {
             // this warp's half of the pass: tiles [sel_part * 8, +8); lane <-> rows lane + 32 t.  Pool the label's queries
             // (ascending), keep the GV_KEEP largest of (new rows, previously kept) by (score desc, row asc)

@@ -1,7 +1,7 @@
 """Phase trace of the small-query kernels (k_gemv8 / k_gemv8_tail) on config 4-i.
 
   python tools/gv_trace.py --build     here: compiles gemv.cu with -DSDK_GV_TRACE and links libsdk_b200_trace.so
-  python tools/gv_trace.py             on the GPU box: runs 4-i through that library and prints the phase table
+  python tools/gv_trace.py [--lib X]   on the GPU box: runs 4-i through that library and prints the phase table
 
 The trace build is a diagnostic; the shipped libsdk_b200.so holds none of it."""
 import os
@@ -15,18 +15,27 @@ PKG = ROOT / "speaker_diarization_toolkit_b200"
 TRACE_SO = PKG / "libsdk_b200_trace.so"
 
 
+def _arg(name, default=None, many=False):
+    vals = [sys.argv[i + 1] for i, a in enumerate(sys.argv[:-1]) if a == name]
+    return vals if many else (vals[-1] if vals else default)
+
+
 def build():
+    """--build [--define NAME[=V]]... [--out libsdk_b200_traceX.so]"""
     from speaker_diarization_toolkit_b200 import build as b
     b.build()
-    obj = PKG / "build" / "gemv_trace.o"
-    subprocess.run([b.nvcc(), *b.NVCC_FLAGS, "-DSDK_GV_TRACE", "-c", str(b.CSRC / "gemv.cu"), "-o", str(obj)], check=True)
+    out = PKG / _arg("--out", TRACE_SO.name)
+    obj = PKG / "build" / (out.stem + "_gemv.o")
+    defs = ["-D" + d for d in _arg("--define", many=True)]
+    subprocess.run([b.nvcc(), *b.NVCC_FLAGS, "-DSDK_GV_TRACE", *defs, "-c", str(b.CSRC / "gemv.cu"), "-o", str(obj)], check=True)
     objs = [str(PKG / "build" / (s + ".o")) for s in b.SOURCES if s != "gemv.cu"] + [str(obj)]
-    subprocess.run([b.nvcc(), "-shared", "-o", str(TRACE_SO), *objs, "-cudart", "shared", "-ldl"], check=True)
-    print(TRACE_SO)
+    subprocess.run([b.nvcc(), "-shared", "-o", str(out), *objs, "-cudart", "shared", "-ldl"], check=True)
+    print(out)
 
 
 def main():
-    os.environ["SDK_B200_LIB"] = str(TRACE_SO)
+    os.environ["SDK_B200_LIB"] = str(PKG / _arg("--lib", TRACE_SO.name))
+    print("library", os.environ["SDK_B200_LIB"])
     import ctypes as C
     import numpy as np
     import torch

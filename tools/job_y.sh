@@ -15,3 +15,6 @@ BB="python bench.py --no-e2e --no-cpu --no-sharded --no-poolfirst --no-parity"
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_launches_cfg4i_${S}.csv $BB --workload cfg4i --steps 3 --warmup 2 > gpurun_out/ncu_l_cfg4i.log 2>&1
 python tools/launch_share.py gpurun_out/r02_launches_cfg4i_${S}.csv | head -8
 timeout 900 python -m pytest -q -x --timeout 150 -m gpu tests 2>&1 | tail -6 | tee gpurun_out/r02_gputests_${S}.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gemv8 -s 4 -c 2 -f -o gpurun_out/r02_cfg4i_gemv_${S} $BB --workload cfg4i --steps 2 --warmup 2 > gpurun_out/ncu_cfg4i_gemv.log 2>&1
+python tools/ncu_summary.py gpurun_out/r02_cfg4i_gemv_${S}.ncu-rep gpurun_out/r02_cfg4i_gemv_${S}_ncu_summary.json --traffic-key cfg4i --traffic-out gpurun_out/roofline_traffic_${S}.json
+timeout 150 $B --workload cfg2 --steps 20 --warmup 5 > gpurun_out/r02_bench_cfg2_n1_${S}.json 2> gpurun_out/r02_bench_cfg2_${S}.err || tail -5 gpurun_out/r02_bench_cfg2_${S}.err
