@@ -850,51 +850,68 @@ k_gemv8_tail(const __grid_constant__ GvTail p) {
     }
     __syncthreads();
     GV_T(1, 9);
-    // ---- 6. row -> speaker max, threshold, ordered top-k, certificate (k_select's semantics), one warp.  The accepted
-    //         matches stay in registers (lane i holds the i-th) and are written together at the end ----
+    // ---- 6. row -> speaker max, threshold, ordered top-k, certificate (k_select's semantics), one warp, no serial
+    //         extraction: a candidate is a match iff it passes the threshold and no passing candidate of the same speaker has
+    //         a larger (score, row) key; its position is the number of matches with a larger key (the first k are written).
+    //         Same result as taking the candidates in key order, skipping speakers already taken, stopping at the first
+    //         score below the threshold or at k matches -- scores do not increase along that order. ----
     if (warp != 0) return;
-    unsigned long long key0 = 0ull, key1 = 0ull;
+    unsigned long long kp0 = 0ull, kp1 = 0ull;                     // keys of the lane's candidates that pass the threshold
     if (lane < nc) {
-        const uint32_t row = 0xffffffffu - (uint32_t)s_sel[lane];
-        key0 = ((unsigned long long)sdk_fkey(sdk_pool_finish(s_pool[lane], n, p.pool)) << 32) | (0xffffffffu - row);
+        const float sim = sdk_pool_finish(s_pool[lane], n, p.pool);
+        if ((double)sim >= p.threshold) kp0 = ((unsigned long long)sdk_fkey(sim) << 32) | (uint32_t)s_sel[lane];
     }
     if (lane + 32 < nc) {
-        const uint32_t row = 0xffffffffu - (uint32_t)s_sel[lane + 32];
-        key1 = ((unsigned long long)sdk_fkey(sdk_pool_finish(s_pool[lane + 32], n, p.pool)) << 32) | (0xffffffffu - row);
+        const float sim = sdk_pool_finish(s_pool[lane + 32], n, p.pool);
+        if ((double)sim >= p.threshold) kp1 = ((unsigned long long)sdk_fkey(sim) << 32) | (uint32_t)s_sel[lane + 32];
     }
-    unsigned long long last = ~0ull;
-    int cnt = 0;
+    const int n_lo = nc < 32 ? nc : 32;
+    bool d0 = false, d1 = false;
+    for (int j = 0; j < n_lo; ++j) {
+        const unsigned long long kj = __shfl_sync(0xffffffffu, kp0, j);
+        const int32_t sj = __shfl_sync(0xffffffffu, spk0, j);
+        d0 |= kj > kp0 && sj == spk0;
+        d1 |= kj > kp1 && sj == spk1;
+    }
+    for (int j = 32; j < nc; ++j) {
+        const unsigned long long kj = __shfl_sync(0xffffffffu, kp1, j - 32);
+        const int32_t sj = __shfl_sync(0xffffffffu, spk1, j - 32);
+        d0 |= kj > kp0 && sj == spk0;
+        d1 |= kj > kp1 && sj == spk1;
+    }
+    const unsigned long long ku0 = d0 ? 0ull : kp0, ku1 = d1 ? 0ull : kp1;                  // the matches
+    int r0 = 0, r1 = 0;
+    for (int j = 0; j < n_lo; ++j) {
+        const unsigned long long kj = __shfl_sync(0xffffffffu, ku0, j);
+        r0 += kj > ku0 ? 1 : 0;
+        r1 += kj > ku1 ? 1 : 0;
+    }
+    for (int j = 32; j < nc; ++j) {
+        const unsigned long long kj = __shfl_sync(0xffffffffu, ku1, j - 32);
+        r0 += kj > ku0 ? 1 : 0;
+        r1 += kj > ku1 ? 1 : 0;
+    }
+    const int nu = __popc(__ballot_sync(0xffffffffu, ku0 != 0ull)) + __popc(__ballot_sync(0xffffffffu, ku1 != 0ull));
+    const int cnt = nu < k ? nu : k;
+    if (ku0 != 0ull && r0 < k) {
+        p.o_row[(int64_t)g * k + r0] = (int64_t)(int32_t)(0xffffffffu - (uint32_t)ku0) + p.row_offset;
+        p.o_score[(int64_t)g * k + r0] = sdk_funkey((uint32_t)(ku0 >> 32));
+        p.o_trust[(int64_t)g * k + r0] = (uint8_t)tr0;
+        p.o_spk[(int64_t)g * k + r0] = spk0;
+    }
+    if (ku1 != 0ull && r1 < k) {
+        p.o_row[(int64_t)g * k + r1] = (int64_t)(int32_t)(0xffffffffu - (uint32_t)ku1) + p.row_offset;
+        p.o_score[(int64_t)g * k + r1] = sdk_funkey((uint32_t)(ku1 >> 32));
+        p.o_trust[(int64_t)g * k + r1] = (uint8_t)tr1;
+        p.o_spk[(int64_t)g * k + r1] = spk1;
+    }
+    // the k-th match's score (only read when there are k of them)
     float kth = 0.f;
-    int32_t a_spk = -1, a_row = -1;
-    float a_sim = 0.f;
-    uint32_t a_tr = SDK_TRUST_UNKNOWN;
-    while (cnt < k) {
-        unsigned long long best = (key0 < last) ? key0 : 0ull;
-        best = (key1 < last && key1 > best) ? key1 : best;
-        best = gv_warp_max_u64(best);
-        if (best == 0ull) break;
-        last = best;
-        const float sim = sdk_funkey((uint32_t)(best >> 32));
-        if (!((double)sim >= p.threshold)) break;
-        const uint32_t m0 = __ballot_sync(0xffffffffu, key0 == best), m1 = __ballot_sync(0xffffffffu, key1 == best);
-        const int src = m0 ? __ffs(m0) - 1 : __ffs(m1) - 1;
-        const int32_t spk = __shfl_sync(0xffffffffu, m0 ? spk0 : spk1, src);
-        const uint32_t tr = __shfl_sync(0xffffffffu, m0 ? tr0 : tr1, src);
-        if (__ballot_sync(0xffffffffu, lane < cnt && a_spk == spk) != 0u) continue;     // a better row of this speaker is in
-        if (lane == cnt) {
-            a_spk = spk;
-            a_row = (int32_t)(0xffffffffu - (uint32_t)best);
-            a_sim = sim;
-            a_tr = tr;
-        }
-        kth = sim;
-        ++cnt;
-    }
-    if (lane < cnt) {
-        p.o_row[(int64_t)g * k + lane] = (int64_t)a_row + p.row_offset;
-        p.o_score[(int64_t)g * k + lane] = a_sim;
-        p.o_trust[(int64_t)g * k + lane] = (uint8_t)a_tr;
-        p.o_spk[(int64_t)g * k + lane] = a_spk;
+    {
+        const uint32_t m0 = __ballot_sync(0xffffffffu, ku0 != 0ull && r0 == k - 1), m1 = __ballot_sync(0xffffffffu, ku1 != 0ull && r1 == k - 1);
+        const float f0 = sdk_funkey((uint32_t)(ku0 >> 32)), f1 = sdk_funkey((uint32_t)(ku1 >> 32));
+        if (m0) kth = __shfl_sync(0xffffffffu, f0, __ffs(m0) - 1);
+        else if (m1) kth = __shfl_sync(0xffffffffu, f1, __ffs(m1) - 1);
     }
     if (lane == 0) {
         p.o_count[g] = cnt;
