@@ -361,6 +361,19 @@ k_gemv8(const __grid_constant__ GvParams q) {
 #ifdef SDK_GV_TRACE
     int tpass = 0;
 #endif
+    // the first load group (two lines of every row; lane r: row r) of this warp's tile of the NEXT pass, issued before each
+    // selection.  Plain prefetch instructions: a bulk prefetch per lane kept the warp busy for a microsecond.  Four lines, or
+    // issuing them before the MMA loop instead, measured no better (profiles/r02_gv_trace_g*.log).
+    auto prefetch_next = [&](int64_t pass0, int plen_) {
+        const int64_t t = pass0 + plen_ + cw;
+        const int64_t row = (c0 + t) * GV_ROWS + lane;
+        if (t < n_mine && row < q.P) {
+            const char* a = reinterpret_cast<const char*>(q.bank + row * q.Dp);
+#pragma unroll
+            for (int l = 0; l < 2; ++l)
+                if (q.Dp * 2 > 128 * l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128 * l));
+        }
+    };
     int plen = first_len;
     for (int64_t pass0 = 0; pass0 < n_mine; pass0 += plen, plen = GV_PASS_TILES) {
         const int npc = plen;                                          // (first_len + a multiple of 16 = n_mine)
@@ -421,17 +434,7 @@ k_gemv8(const __grid_constant__ GvParams q) {
 #ifdef SDK_GV_TRACE
         if (tpass < 3) GV_T(0, 5 + 4 * tpass);
 #endif
-        {   // the first load group of this warp's tile of the NEXT pass (lane r: the first 256 bytes of row r, two lines): the
-            // DRAM works on it while the CTA selects.  Plain prefetch instructions: a bulk prefetch per lane kept the warp
-            // busy for a microsecond.
-            const int64_t t = pass0 + plen + cw;
-            const int64_t row = (c0 + t) * GV_ROWS + lane;
-            if (t < n_mine && row < q.P) {
-                const char* a = reinterpret_cast<const char*>(q.bank + row * q.Dp);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-                if (q.Dp * 2 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
-            }
-        }
+        prefetch_next(pass0, plen);                                   // the DRAM works on it while the CTA selects
         if (sel_len > 0) {
             // this warp's half of the pass: tiles [sel_part * 8, +8); lane <-> rows lane + 32 t.  Pool the label's queries
             // (ascending), keep the GV_KEEP largest of (new rows, previously kept) by (score desc, row asc)
