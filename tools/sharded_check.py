@@ -30,10 +30,12 @@ def main():
     ctx = _native.Context(local, world, rank, box[0])
     ok = True
     for name, path, dtype, pool, thr, k in [("tc-top10", 2, 1, 0, -1.0, 10), ("tc-thr", 2, 1, 1, 0.354, 10),
-                                            ("exact-f32", 1, 0, 0, 0.3, 5)]:
+                                            ("exact-f32", 1, 0, 0, 0.3, 5), ("small-query", 2, 1, 0, -1.0, 10)]:
         rng = np.random.default_rng(11)
         rps = rng.choice([1, 2, 3], size=900)
-        case = synth.make_case(404, synth.zipf_counts(rng, 900, 8), 900, 128 if path == 1 else 512, rows_per_speaker=rps,
+        # "small-query": 7 segments of 4 labels -> the bank-stream kernels (last_path 4) on every shard, settled before the gather
+        counts = [2, 1, 3, 1] if name == "small-query" else synth.zipf_counts(rng, 900, 8)
+        case = synth.make_case(404, counts, 900, 128 if path == 1 else 512, rows_per_speaker=rps,
                                neighbours=5, impostor_frac=0.1)
         shards = sharding.shard_bank_rows(case.row_speaker, world)
         p0, p1 = shards[rank]
@@ -50,6 +52,8 @@ def main():
         same = same and np.array_equal(out["trust"], tr_ref.astype(np.uint8))
         a = canonical.assign(ref[0], ref[1], tr_ref.astype(np.uint8), ref[2], 0.2, 2)
         same = same and np.array_equal(out["assign_idx"], a[0]) and np.array_equal(out["assign_score"], a[1])
+        if name == "small-query":
+            same = same and ctx.last_path()[0] == 4
         print(f"[rank {rank}/{world}] {name}: shard rows [{p0},{p1}) path={ctx.last_path()} -> {'OK' if same else 'MISMATCH'}", flush=True)
         ok = ok and same
     # ---- empty shards: more ranks than speaker runs: the ranks without rows still join the all-gather ----
