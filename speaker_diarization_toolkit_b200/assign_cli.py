@@ -102,16 +102,26 @@ def assign_labels(audio_path: Path, transcript_data: dict, *, use_embeddings: bo
         if verbose:
             print(f"\nProcessing speaker {label} ({len(segs)} segments)...")
         sigs: List[sg.Signal] = []
-        if use_embeddings and rows is not None:
-            emb = sg.signals_from_matches(rows, min_trust=min_trust, label=label)
+        if use_embeddings:                                  # (the progress lines of speaker-assign:558-590, verbatim)
+            if verbose:
+                print("  Collecting embedding signals...")
+            emb = sg.signals_from_matches(rows, min_trust=min_trust, label=label) if rows is not None else []
             sigs.extend(emb)
             if verbose:
                 for s in emb:
                     print(f"    - {s.speaker_id}: {s.score:.2f} (trust: {s.evidence.get('trust_level', '-')})")
         if expected_speakers:
+            if verbose:
+                print("  Collecting context signals...")
             sigs.extend(sg.collect_context_signals(label, context_name, expected_speakers))
         if use_llm and transcript_path is not None:
-            sigs.extend(collect_llm_signals(label, transcript_path, context_name))
+            if verbose:
+                print("  Collecting LLM signals...")
+            llm = collect_llm_signals(label, transcript_path, context_name)
+            sigs.extend(llm)
+            if verbose:
+                for s in llm:
+                    print(f"    - {s.speaker_id}: {s.score:.2f}")
         a = sg.combine_signals(label, sigs, threshold=threshold)
         mappings[label] = {"speaker_id": a.speaker_id, "confidence": a.confidence, "score": round(a.score, 3),
                            "signals": a.signals}
