@@ -92,7 +92,7 @@ def env(tmp_path, monkeypatch):
     for k, v in e.items():
         monkeypatch.setenv(k, v)
     monkeypatch.syspath_prepend(str(mod))
-    monkeypatch.setattr(plugin_api, "_LOADED_BACKENDS", None, raising=False)     # the registry caches its config per process
+    monkeypatch.setattr(plugin_api, "_loaded", None)     # the registry caches its config per process (restored afterwards)
     return {"root": tmp_path, "audio": audio, "rows": rows, "env": e, "mod": mod}
 
 
