@@ -91,7 +91,7 @@ def assign_labels(audio_path: Path, transcript_data: dict, *, use_embeddings: bo
     if use_embeddings:
         # identify is never given assign's --threshold / --backend by the reference either:
         # backend from $SPEAKER_DETECTION_BACKEND, threshold 0.354
-        rc, rows, msg = identify_rows(audio_path, default_backend_name(None), tags, 0.354, backend)
+        rc, rows, msg = identify_rows(audio_path, default_backend_name(None), tags, 0.354, backend, status=False)
         if rc != 0:
             if verbose:
                 print(f"  identify: {msg}", file=sys.stderr)

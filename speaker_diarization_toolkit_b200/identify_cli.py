@@ -64,8 +64,9 @@ def decorate_results(results: List[Dict[str, Any]], backend_name: str) -> List[D
     return out
 
 
-def identify_rows(audio_path: Path, backend_name: str, tags: Optional[str], threshold: float, backend=None):
-    """Shared by the CLI and by speaker-assign's in-process embedding step.
+def identify_rows(audio_path: Path, backend_name: str, tags: Optional[str], threshold: float, backend=None, status: bool = True):
+    """Shared by the CLI and by speaker-assign's in-process embedding step (status=False there: the reference's assign
+    runs identify as a subprocess and swallows its stderr, speaker-assign:288-293).
     Returns (rc, rows, message): rc 0 with rows, or rc 1 with the reference's stderr message."""
     speakers = store.list_all_speakers()
     if tags:
@@ -80,7 +81,8 @@ def identify_rows(audio_path: Path, backend_name: str, tags: Optional[str], thre
             backend = get_backend(backend_name)
         except (ValueError, ImportError) as exc:
             return 1, [], f"Error loading backend: {exc}"
-    print(f"Identifying speaker in {audio_path.name} against {len(candidates)} candidates...", file=sys.stderr)
+    if status:
+        print(f"Identifying speaker in {audio_path.name} against {len(candidates)} candidates...", file=sys.stderr)
     try:
         results = backend.identify_speaker(audio_path, candidates, threshold)
     except Exception as exc:

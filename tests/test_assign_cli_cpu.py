@@ -76,17 +76,20 @@ class Pair:
         self.theirs.mkdir()
         self.monkeypatch, self.capsys = monkeypatch, capsys
         self.ref_ok = REF.exists()
+        self.extra = {}                 # environment both sides get on top of SPEAKERS_EMBEDDINGS_DIR
 
     def both(self, build, argv_of):
         """build(root) -> dict of paths; argv_of(paths) -> argv.  Returns (rc, out, err, ours_root, paths)."""
         paths = build(self.ours)
         self.monkeypatch.setenv("SPEAKERS_EMBEDDINGS_DIR", str(self.ours))
+        for key, val in self.extra.items():
+            self.monkeypatch.setenv(key, val)
         rc = assign_cli.main(argv_of(paths))
         cap = self.capsys.readouterr()
         if self.ref_ok:
             rpaths = build(self.theirs)
             r = subprocess.run([sys.executable, str(REF), *argv_of(rpaths)], capture_output=True, text=True,
-                               env=dict(os.environ, SPEAKERS_EMBEDDINGS_DIR=str(self.theirs)))
+                               env=dict(os.environ, **self.extra, SPEAKERS_EMBEDDINGS_DIR=str(self.theirs)))
             swap = lambda s: scrub(s).replace(str(self.theirs), "<ROOT>")
             mine = lambda s: scrub(s).replace(str(self.ours), "<ROOT>")
             assert (r.returncode, swap(r.stdout), swap(r.stderr)) == (rc, mine(cap.out), mine(cap.err)), argv_of(paths)
@@ -221,3 +224,57 @@ def test_assign_speechmatics_transcript(pair):
     rc, out, err, paths = pair.both(sm, lambda p: ["-v", "assign", str(p["audio"]), "-t", str(p["t"])])
     assert rc == 0 and "Found 2 speakers: S1, S2" in out and "Processing speaker S1 (2 segments)..." in out
     assert set(saved(paths)["mappings"]) == {"S1", "S2"}
+
+
+def test_assign_with_the_embedding_step_through_a_stub_backend(pair, tmp_path, monkeypatch):
+    """`assign -e` (speaker-assign:262-328, :556-570): the reference forks `speaker_detection identify` per label and keeps
+    every row for every label; this repo calls the backend once, in process, and keeps whole-recording rows (no `label`
+    key) for every label as well -- so with the same stub backend behind both (the reference's own `speaker_detection` on
+    $PATH for its side) the records, the progress lines and the return codes are the same: min-trust filter (`low` rows
+    dropped at `medium`, `unknown` kept), trust multipliers, default threshold and a lower one, text and JSON."""
+    from speaker_diarization_toolkit_b200 import plugin_api
+    from test_identify_cli_cpu import PROFILES, ROWS, STUB
+    plug = tmp_path / "plug"
+    plug.mkdir()
+    (plug / "stub_backend_mod.py").write_text(STUB)
+    cfg = tmp_path / "backends.yaml"
+    cfg.write_text("backends:\n  stub:\n    module: stub_backend_mod\n")
+    rows = tmp_path / "rows.json"
+    rows.write_text(json.dumps({"rows": ROWS}))
+    shim = tmp_path / "bin"
+    shim.mkdir()
+    (shim / "speaker_detection").write_text(f"#!/bin/sh\nexec {sys.executable} /root/reference/speaker_detection \"$@\"\n")
+    (shim / "speaker_detection").chmod(0o755)
+    root = Path(__file__).resolve().parent.parent
+    pair.extra = {"SPEAKER_BACKENDS_CONFIG": str(cfg), "STUB_ROWS": str(rows), "SPEAKER_DETECTION_BACKEND": "stub",
+                  "PYTHONPATH": os.pathsep.join([str(plug), str(root)]), "PATH": str(shim) + os.pathsep + os.environ.get("PATH", "")}
+    monkeypatch.syspath_prepend(str(plug))
+    monkeypatch.setattr(plugin_api, "_loaded", None)
+
+    def build(uid):
+        def go(r):
+            (r / "db").mkdir(exist_ok=True)
+            for pid, prof in PROFILES.items():
+                (r / "db" / f"{pid}.json").write_text(json.dumps(dict(prof, version=1)))
+            return two(r, 2, uid)
+        return go
+
+    rc, out, err, paths = pair.both(build("emb"), lambda p: ["-v", "assign", str(p["audio"]), "-t", str(p["t"]), "-e"])
+    assert rc == 0 and err == "" and "  Collecting embedding signals..." in out and "    - alice: 0.91 (trust: low)" in out
+    rec = saved(paths)
+    for label in ("A", "B"):                                   # 0.4 x 0.4 x 0.91 = 0.1456 < 0.3: candidates only
+        m = rec["mappings"][label]
+        assert m["speaker_id"] is None and m["score"] == 0.146 and [c["speaker_id"] for c in m["candidates"]] == ["alice", "dave", "bob"]
+        assert m["signals"] == [{"type": "embedding_match", "score": 0.91, "embedding_id": "emb-a2", "trust_level": "low", "backend": "stub"}]
+    rc, out, err, paths = pair.both(build("emb-thr"), lambda p: ["assign", str(p["audio"]), "-t", str(p["t"]), "-e", "--threshold", "0.1", "-f", "json"])
+    rec = json.loads(out[out.index("{"):])
+    assert rc == 0 and rec["mappings"]["A"]["speaker_id"] == "alice" and [c["speaker_id"] for c in rec["mappings"]["A"]["candidates"]] == ["dave", "bob"]
+    rc, out, err, paths = pair.both(build("emb-trust"), lambda p: ["assign", str(p["audio"]), "-t", str(p["t"]), "-e", "--min-trust", "medium",
+                                                                  "--threshold", "0.1", "-n", "-f", "json"])
+    rec = json.loads(out[out.index("{"):])                      # alice's row is `low`: dropped; `unknown` is not in the order: kept
+    assert rc == 0 and rec["mappings"]["B"]["speaker_id"] == "dave" and rec["mappings"]["B"]["score"] == 0.124
+    rc, out, err, paths = pair.both(build("emb-tags"), lambda p: ["assign", str(p["audio"]), "-t", str(p["t"]), "-e", "--tags", "team,eng",
+                                                                 "--expected-speakers", "dave", "--threshold", "0.2", "-n", "-f", "json"])
+    rec = json.loads(out[out.index("{"):])                      # bob is filtered by the tags; dave: 0.124 + 0.1 beats alice's 0.1456
+    assert rc == 0 and rec["mappings"]["A"]["speaker_id"] == "dave" and rec["mappings"]["A"]["score"] == 0.224
+    assert [s["type"] for s in rec["mappings"]["A"]["signals"]] == ["embedding_match", "context_expected"]
