@@ -207,6 +207,7 @@ def bind_to_gpu_numa_node(torch, local_rank):
             os.sched_setaffinity(0, cpus)
         return node, how
     except Exception as exc:
+        unbind_cpus()                                       # (a probe that failed half way must not leave the process bound)
         return None, f"unavailable ({type(exc).__name__})"
 
 
