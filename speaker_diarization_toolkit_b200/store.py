@@ -12,6 +12,7 @@ Layout (unchanged from the reference):
 from __future__ import annotations
 
 import hashlib
+import gc
 import json
 import os
 import sys
@@ -113,18 +114,28 @@ def list_all_speakers_cached() -> List[Dict[str, Any]]:
     cur = {}
     with os.scandir(db) as it:
         for e in it:
-            if e.name.endswith(".json") and not e.name.startswith("."):
+            n = e.name
+            if n.endswith(".json") and n[0] != ".":
                 st = e.stat()
-                cur[e.name] = (st.st_size, st.st_mtime_ns)
+                cur[n] = [st.st_size, st.st_mtime_ns]
     names = sorted(cur)
     old_stat, old_prof = {}, {}
     if pack_path.exists():
         try:
-            with open(pack_path, "r") as fh:
-                pack = json.load(fh)
-            old_stat = {n: tuple(v) for n, v in zip(pack["names"], pack["stats"])}
+            gc_was_on = gc.isenabled()
+            gc.disable()                       # (a million fresh dicts: the cycle collector would walk them again and again)
+            try:
+                with open(pack_path, "r") as fh:
+                    pack = json.load(fh)
+            finally:
+                if gc_was_on:
+                    gc.enable()
+            # nothing changed (the usual call): two list comparisons, no per-profile Python work
+            if pack["names"] == names and pack["stats"] == [cur[n] for n in names] and len(pack["profiles"]) == len(names):
+                return pack["profiles"]
+            old_stat = dict(zip(pack["names"], pack["stats"]))
             old_prof = dict(zip(pack["names"], pack["profiles"]))
-        except (OSError, ValueError, KeyError):
+        except (OSError, ValueError, KeyError, TypeError):
             old_stat, old_prof = {}, {}
     out: List[Dict[str, Any]] = []
     kept_names, kept_stats = [], []
