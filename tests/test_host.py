@@ -537,3 +537,20 @@ def test_assign_show_and_clear_match_the_reference(tmp_path, monkeypatch, capsys
     assert rc == 0 and f"Cleared assignments: {b3[:8]}..." in cap.out and not (adir / f"{b3}.yaml").exists()
     rc, cap = both(["clear", str(audio), "--force"])
     assert rc == 0 and "No assignments found for this recording" in cap.err
+
+
+def test_phase_trace_build_of_the_small_query_kernels_compiles(tmp_path):
+    """tools/gv_trace.py: the diagnostic build (-DSDK_GV_TRACE: clock stamps at the phase boundaries of k_gemv8 /
+    k_gemv8_tail) must keep compiling next to the shipped one; only the object is built here, into a scratch directory."""
+    import shutil
+    import subprocess
+    from speaker_diarization_toolkit_b200 import build as b
+    if not (shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists()):
+        pytest.skip("no nvcc")
+    obj = tmp_path / "gemv_trace.o"
+    r = subprocess.run([b.nvcc(), *b.NVCC_FLAGS, "-DSDK_GV_TRACE", "-c", str(b.CSRC / "gemv.cu"), "-o", str(obj)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    sym = subprocess.run(["nm", str(obj)], capture_output=True, text=True).stdout
+    assert "sdk_debug_gv_trace" in sym
+    shipped = subprocess.run(["nm", "-D", str(_native.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sdk_debug_gv_trace" not in shipped          # the shipped library holds none of it
